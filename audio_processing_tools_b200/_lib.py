@@ -1,0 +1,120 @@
+"""ctypes binding of libapt_b200.so (include/apt_b200.h).
+
+The shared library is the product: there is no CPU fallback.  If it is missing or no CUDA
+device is visible every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libapt_b200.so")
+CSRC = os.path.join(_PKG, "csrc")
+
+MAX_MODES, MAX_SOS, N_RAW, N_TD, N_STATS = 8, 4, 21, 5, 8
+ABI_VERSION = 1
+STAGE_FEATURES, STAGE_FULL = 1, 2
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
+              "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
+
+
+class AptParams(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("fs", C.c_int32), ("n_fft", C.c_int32), ("hop", C.c_int32),
+        ("band_lo", C.c_int32), ("band_hi", C.c_int32), ("n_modes", C.c_int32),
+        ("mode_lo", C.c_int32 * MAX_MODES), ("mode_hi", C.c_int32 * MAX_MODES),
+        ("mode_band_lo", C.c_int32 * MAX_MODES), ("mode_band_hi", C.c_int32 * MAX_MODES),
+        ("mode_weight", C.c_double * MAX_MODES),
+        ("trk_eta", C.c_float), ("trk_scale_alpha", C.c_float), ("trk_one_minus_alpha", C.c_float),
+        ("trk_step_floor", C.c_float), ("trk_q", C.c_float), ("trk_neg_one_minus_q", C.c_float),
+        ("trk_maxr", C.c_float),
+        ("ema_up", C.c_double), ("ema_down", C.c_double),
+        ("warmup_need", C.c_int32), ("eps_f32", C.c_float),
+        ("detector_use_noise_norm", C.c_int32), ("norm_ratio_db", C.c_int32),
+        ("bl_q", C.c_double), ("bl_eta", C.c_double), ("bl_scale_alpha", C.c_double), ("bl_floor", C.c_double),
+        ("norm_enable", C.c_int32), ("norm_min_f32", C.c_float),
+        ("thr_primary", C.c_float), ("thr_m1", C.c_float), ("thr_m2", C.c_float), ("thr_m3", C.c_float),
+        ("min_support", C.c_int32), ("td_gate_thr", C.c_float), ("has_kurt_upper", C.c_int32),
+        ("kurt_upper", C.c_float), ("noise_hi", C.c_float), ("mode_flux_noise_max", C.c_float),
+        ("n_sos", C.c_int32), ("padlen", C.c_int32),
+        ("sos", (C.c_double * 6) * MAX_SOS), ("zi", (C.c_double * 2) * MAX_SOS),
+        ("eps_f64", C.c_double),
+        ("blk_len", C.c_int32), ("blk_hop", C.c_int32), ("blk_post_pre", C.c_int32), ("blk_smooth", C.c_int32),
+        ("low_lo", C.c_int32), ("low_hi", C.c_int32), ("rain_lo", C.c_int32), ("rain_hi", C.c_int32),
+        ("rolloff_fraction", C.c_double),
+        ("suppressor_bypass", C.c_int32), ("clip_rain_min_frames", C.c_int32),
+        ("fft_f64", C.c_int32), ("reserved0", C.c_int32),
+        ("window", C.c_void_p), ("freqs", C.c_void_p),
+    ]
+
+
+OUT_FIELDS = ("frame_class", "rain_conf", "noise_conf", "event_idx", "event_count", "clip_stats",
+              "S", "P", "det_noise_psd", "det_noise_lag", "D", "noise_psd", "mode_flux", "norm_flux",
+              "score", "td", "raw", "band_energy", "gate", "x_td")
+
+
+class AptOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in OUT_FIELDS]
+
+
+# every symbol include/apt_b200.h declares
+EXPORTS = ("apt_init", "apt_destroy", "apt_last_error", "apt_abi_version", "apt_sizeof_params",
+           "apt_sizeof_out", "apt_params_default", "apt_plan_create", "apt_plan_destroy",
+           "apt_plan_offsets", "apt_plan_total_frames", "apt_plan_total_samples",
+           "apt_plan_scratch_bytes", "apt_run_i16", "apt_run_f32", "apt_plan_last_launches",
+           "apt_run_host_i16")
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/apt_b200.cu for sm_100a into the package directory (in-tree .so)."""
+    srcs = [os.path.join(CSRC, f) for f in ("apt_b200.cu", "apt_kernels.cuh", "apt_math.cuh")]
+    srcs.append(os.path.join(_REPO, "include", "apt_b200.h"))
+    if not force and os.path.exists(LIB_PATH) and all(
+            os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "apt_b200.cu")]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library and type its entry points.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`."
+            " There is no CPU fallback for this path.")
+    L = C.CDLL(LIB_PATH)
+    vp, i64p = C.c_void_p, C.POINTER(C.c_int64)
+    L.apt_init.argtypes = [C.c_int, C.POINTER(vp)]
+    L.apt_destroy.argtypes = [vp]
+    L.apt_last_error.argtypes = [vp]
+    L.apt_last_error.restype = C.c_char_p
+    L.apt_params_default.argtypes = [C.POINTER(AptParams)]
+    L.apt_plan_create.argtypes = [vp, C.POINTER(AptParams), C.c_int, i64p, C.POINTER(vp)]
+    L.apt_plan_destroy.argtypes = [vp]
+    L.apt_plan_offsets.argtypes = [vp, i64p, i64p]
+    for f in ("apt_plan_total_frames", "apt_plan_total_samples", "apt_plan_scratch_bytes"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = C.c_int64
+    L.apt_plan_last_launches.argtypes = [vp]
+    L.apt_run_i16.argtypes = [vp, C.c_int, vp, C.POINTER(AptOut), vp]
+    L.apt_run_f32.argtypes = [vp, C.c_int, vp, C.POINTER(AptOut), vp]
+    L.apt_run_host_i16.argtypes = [vp] * 8
+    if L.apt_abi_version() != ABI_VERSION:
+        raise RuntimeError("libapt_b200.so ABI version mismatch")
+    if L.apt_sizeof_params() != C.sizeof(AptParams) or L.apt_sizeof_out() != C.sizeof(AptOut):
+        raise RuntimeError("libapt_b200.so struct layout differs from the Python binding")
+    _lib = L
+    return L

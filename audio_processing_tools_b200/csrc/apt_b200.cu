@@ -1,0 +1,505 @@
+// apt_b200.cu -- C ABI (include/apt_b200.h) over the kernels in apt_kernels.cuh.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "apt_kernels.cuh"
+
+using namespace apt;
+
+struct apt_ctx {
+    int device;
+    int sm_count;
+    std::string err;
+};
+
+static int fail(apt_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+#define CUDA_OK(ctx, call)                                                                         \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(ctx, -10, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        free_();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    void free_() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { free_(); }
+};
+
+struct apt_plan {
+    apt_ctx* ctx = nullptr;
+    apt_params_t prm;
+    DevParams dp;
+    int n_clips = 0;
+    std::vector<int64_t> len, samp_off, frame_off, stft_tile_off, td_tile_off, sel_chunk_off;
+    int64_t nS = 0, nF = 0;
+    DevBuf<int64_t> d_samp_off, d_frame_off, d_stft_tile_off, d_td_tile_off, d_sel_chunk_off;
+    // tables
+    DevBuf<double> d_win64; DevBuf<cx<double>> d_tw128_64, d_tw256_64;
+    DevBuf<float> d_win32;  DevBuf<cx<float>> d_tw128_32, d_tw256_32;
+    DevBuf<float> d_freqs;
+    DevBuf<double> d_Apow, d_H;
+    TdTables tdt;
+    int td_ns = 0;
+    size_t td_smem = 0;
+    // scratch
+    DevBuf<float> d_Pband, d_db, d_td;
+    DevBuf<double> d_dbsum;
+    DevBuf<SelState> d_sel;
+    DevBuf<uint32_t> d_hist;
+    DevBuf<int> d_counter;
+    // host-path staging
+    DevBuf<int16_t> d_pcm;
+    DevBuf<int8_t> d_fc; DevBuf<float> d_rc, d_nc, d_stats; DevBuf<int32_t> d_ev, d_evc;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_back = nullptr;
+    int last_launches = 0;
+    size_t scratch_bytes = 0;
+};
+
+static void build_td_tables(const apt_params_t& prm, int ns, const double sos[][6], int chunk,
+                            std::vector<double>& Apow, std::vector<double>& H) {
+    const int dim = 2 * ns;
+    std::vector<double> A(dim * dim, 0.0);
+    H.assign((size_t)chunk * dim, 0.0);
+    for (int r = 0; r < dim; r++) {
+        std::vector<double> z(dim, 0.0);
+        z[r] = 1.0;
+        for (int n = 0; n < chunk; n++) {
+            double x = 0.0;
+            for (int s = 0; s < ns; s++) {
+                const double* c = sos[s];
+                double y = c[0] * x + z[2 * s];
+                z[2 * s] = c[1] * x - c[4] * y + z[2 * s + 1];
+                z[2 * s + 1] = c[2] * x - c[5] * y;
+                x = y;
+            }
+            H[(size_t)n * dim + r] = x;
+        }
+        for (int q = 0; q < dim; q++) A[q * dim + r] = z[q];
+    }
+    Apow.assign((size_t)8 * dim * dim, 0.0);
+    std::vector<double> cur = A, nxt(dim * dim);
+    for (int k = 0; k < 8; k++) {
+        std::copy(cur.begin(), cur.end(), Apow.begin() + (size_t)k * dim * dim);
+        for (int i = 0; i < dim; i++)
+            for (int j = 0; j < dim; j++) {
+                double s = 0.0;
+                for (int q = 0; q < dim; q++) s += cur[i * dim + q] * cur[q * dim + j];
+                nxt[i * dim + j] = s;
+            }
+        cur = nxt;
+    }
+    (void)prm;
+}
+
+template <typename T>
+static cudaError_t upload(DevBuf<T>& b, const std::vector<T>& h) {
+    cudaError_t e = b.alloc(h.size());
+    if (e != cudaSuccess) return e;
+    if (h.empty()) return cudaSuccess;
+    return cudaMemcpy(b.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" {
+
+int apt_abi_version(void) { return APT_ABI_VERSION; }
+int apt_sizeof_params(void) { return (int)sizeof(apt_params_t); }
+int apt_sizeof_out(void) { return (int)sizeof(apt_out_t); }
+
+int apt_init(int device_ordinal, apt_ctx** out) {
+    if (!out) return -1;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return -2;   // no CUDA device: there is no CPU path
+    if (device_ordinal < 0 || device_ordinal >= n) return -3;
+    apt_ctx* c = new apt_ctx();
+    c->device = device_ordinal;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete c; return -4; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) { delete c; return -5; }
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return 0;
+}
+
+void apt_destroy(apt_ctx* ctx) { delete ctx; }
+
+const char* apt_last_error(apt_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (is a CUDA device visible?)"; }
+
+int apt_params_default(apt_params_t* p) {
+    if (!p) return -1;
+    memset(p, 0, sizeof(*p));
+    p->abi_version = APT_ABI_VERSION;
+    p->fs = 11162; p->n_fft = 256; p->hop = 128;
+    p->band_lo = 10; p->band_hi = 80;
+    p->n_modes = 0;
+    for (int i = 0; i < APT_MAX_MODES; i++) { p->mode_lo[i] = 1; p->mode_hi[i] = 0; p->mode_band_lo[i] = 1; p->mode_band_hi[i] = 0; p->mode_weight[i] = 1.0; }
+    // W = max(10, int(0.5 * 11162/128)) = 43
+    p->trk_eta = (float)(2.0 / 44.0); p->trk_scale_alpha = 0.95f; p->trk_one_minus_alpha = (float)(1.0 - 0.95);
+    p->trk_step_floor = 1e-9f; p->trk_q = 0.25f; p->trk_neg_one_minus_q = -0.75f; p->trk_maxr = 1.0f;
+    p->ema_up = 0.6; p->ema_down = 0.95; p->warmup_need = 21; p->eps_f32 = 1e-9f;
+    p->detector_use_noise_norm = 1; p->norm_ratio_db = 0;
+    p->bl_q = 0.2; p->bl_eta = 2.0 / 45.0; p->bl_scale_alpha = 1.0 - 2.0 / 45.0; p->bl_floor = 1.0;
+    p->norm_enable = 1; p->norm_min_f32 = 1.0f;
+    p->thr_primary = 1.8f; p->thr_m1 = 2.6f; p->thr_m2 = 2.6f; p->thr_m3 = 3.0f; p->min_support = 2;
+    p->td_gate_thr = 2.5f; p->has_kurt_upper = 0; p->kurt_upper = 0.0f;
+    p->noise_hi = 0.8f; p->mode_flux_noise_max = 1.5f;
+    p->n_sos = 0; p->padlen = 0; p->eps_f64 = 1e-9;
+    p->blk_len = 8; p->blk_hop = 8; p->blk_post_pre = 4; p->blk_smooth = 1;
+    p->low_lo = 2; p->low_hi = 4; p->rain_lo = 10; p->rain_hi = 18; p->rolloff_fraction = 0.85;
+    p->suppressor_bypass = 0; p->clip_rain_min_frames = 1; p->fft_f64 = 1;
+    return 0;
+}
+
+int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int64_t* clip_len, apt_plan_t** out) {
+    if (!ctx) return -1;
+    if (!p || !out || !clip_len || n_clips <= 0) return fail(ctx, -1, "apt_plan_create: bad arguments");
+    *out = nullptr;
+    if (p->abi_version != APT_ABI_VERSION) return fail(ctx, -20, "params abi_version %d != %d", p->abi_version, APT_ABI_VERSION);
+    if (p->n_fft != 256 || p->hop < 1 || p->hop > 256 || 256 % p->hop != 0 || p->hop != 128)
+        return fail(ctx, -21, "unsupported STFT geometry n_fft=%d hop=%d (this build: n_fft=256, hop=128)", p->n_fft, p->hop);
+    const int F = p->n_fft / 2 + 1;
+    const int K = p->band_hi - p->band_lo + 1;
+    if (p->band_lo < 0 || p->band_hi >= F || K < 1 || K > SEQ_KMAX) return fail(ctx, -22, "operating band bins [%d,%d] unsupported", p->band_lo, p->band_hi);
+    if (p->n_modes < 4 || p->n_modes > APT_MAX_MODES) return fail(ctx, -23, "n_modes=%d outside [4,%d]", p->n_modes, APT_MAX_MODES);
+    if (p->n_sos < 0 || p->n_sos > APT_MAX_SOS) return fail(ctx, -24, "n_sos=%d outside [0,%d]", p->n_sos, APT_MAX_SOS);
+    if (!p->window || !p->freqs) return fail(ctx, -25, "window / freqs tables missing");
+    if (p->blk_len < 1 || p->blk_hop < 1 || p->blk_len > 64 || p->blk_hop != p->blk_len)
+        return fail(ctx, -26, "unsupported block-energy geometry len=%d hop=%d", p->blk_len, p->blk_hop);
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+
+    apt_plan* pl = new apt_plan();
+    pl->ctx = ctx;
+    pl->prm = *p;
+    pl->n_clips = n_clips;
+    DevParams& d = pl->dp;
+    memset(&d, 0, sizeof(d));
+    d.n_fft = p->n_fft; d.hop = p->hop; d.F = F; d.band_lo = p->band_lo; d.K = K; d.M = p->n_modes;
+    for (int i = 0; i < APT_MAX_MODES; i++) {
+        d.mode_lo[i] = p->mode_lo[i]; d.mode_hi[i] = p->mode_hi[i];
+        d.mode_blo[i] = p->mode_band_lo[i]; d.mode_bhi[i] = p->mode_band_hi[i];
+        d.mode_w[i] = p->mode_weight[i];
+        if (i < p->n_modes && (p->mode_hi[i] >= F || (p->mode_band_hi[i] >= K && p->mode_band_lo[i] <= p->mode_band_hi[i]))) {
+            delete pl; return fail(ctx, -27, "mode band %d out of range", i);
+        }
+    }
+    d.trk_eta = p->trk_eta; d.trk_alpha = p->trk_scale_alpha; d.trk_1m_alpha = p->trk_one_minus_alpha; d.trk_floor = p->trk_step_floor;
+    d.trk_q = p->trk_q; d.trk_nq = p->trk_neg_one_minus_q; d.trk_maxr = p->trk_maxr;
+    d.ema_up = p->ema_up; d.ema_down = p->ema_down; d.warm_need = p->warmup_need; d.eps32 = p->eps_f32;
+    d.use_norm = p->detector_use_noise_norm; d.ratio_db = p->norm_ratio_db;
+    d.bl_q = p->bl_q; d.bl_eta = p->bl_eta; d.bl_alpha = p->bl_scale_alpha; d.bl_floor = p->bl_floor;
+    d.norm_enable = p->norm_enable; d.norm_min = p->norm_min_f32;
+    d.thr0 = p->thr_primary; d.thr1 = p->thr_m1; d.thr2 = p->thr_m2; d.thr3 = p->thr_m3; d.min_support = p->min_support;
+    d.gate_thr = p->td_gate_thr; d.has_ku = p->has_kurt_upper; d.ku = p->kurt_upper;
+    d.noise_hi = p->noise_hi; d.mf_noise_max = p->mode_flux_noise_max;
+    d.eps64 = p->eps_f64;
+    d.blk_len = p->blk_len; d.blk_hop = p->blk_hop; d.blk_pp = p->blk_post_pre; d.blk_smooth = p->blk_smooth;
+    d.low_lo = p->low_lo; d.low_hi = p->low_hi; d.rain_lo = p->rain_lo; d.rain_hi = p->rain_hi; d.rolloff = p->rolloff_fraction;
+    d.suppressor_bypass = p->suppressor_bypass; d.min_frames = p->clip_rain_min_frames;
+    // TD prefilter: n_sos == 0 is run as one identity section
+    double sos[APT_MAX_SOS][6];
+    int ns = p->n_sos;
+    if (ns == 0) {
+        ns = 1;
+        const double ident[6] = {1, 0, 0, 1, 0, 0};
+        memcpy(sos[0], ident, sizeof(ident));
+        d.zi[0][0] = d.zi[0][1] = 0.0;
+        d.padlen = 0;
+    } else {
+        for (int s = 0; s < ns; s++) { memcpy(sos[s], p->sos[s], sizeof(double) * 6); d.zi[s][0] = p->zi[s][0]; d.zi[s][1] = p->zi[s][1]; }
+        d.padlen = p->padlen;
+    }
+    d.n_sos = ns;
+    for (int s = 0; s < ns; s++) memcpy(d.sos[s], sos[s], sizeof(double) * 6);
+    pl->td_ns = ns;
+
+    // offsets
+    pl->len.assign(clip_len, clip_len + n_clips);
+    pl->samp_off.assign(n_clips + 1, 0); pl->frame_off.assign(n_clips + 1, 0);
+    pl->stft_tile_off.assign(n_clips + 1, 0); pl->td_tile_off.assign(n_clips + 1, 0); pl->sel_chunk_off.assign(n_clips + 1, 0);
+    for (int c = 0; c < n_clips; c++) {
+        const int64_t N = clip_len[c];
+        if (N < p->n_fft || N <= d.padlen + 1) { delete pl; return fail(ctx, -28, "clip %d too short (%lld samples)", c, (long long)N); }
+        const int64_t T = 1 + N / p->hop;
+        const int64_t Tloc = 1 + (N - p->n_fft) / p->hop;
+        pl->samp_off[c + 1] = pl->samp_off[c] + N;
+        pl->frame_off[c + 1] = pl->frame_off[c] + T;
+        pl->stft_tile_off[c + 1] = pl->stft_tile_off[c] + (T + STFT_TF - 1) / STFT_TF;
+        pl->td_tile_off[c + 1] = pl->td_tile_off[c] + std::max<int64_t>(1, (Tloc + TD_FT - 1) / TD_FT);
+        pl->sel_chunk_off[c + 1] = pl->sel_chunk_off[c] + (T + SEL_CHUNK - 1) / SEL_CHUNK;
+    }
+    pl->nS = pl->samp_off[n_clips]; pl->nF = pl->frame_off[n_clips];
+    if (pl->stft_tile_off[n_clips] > 0x7fffffffLL || pl->td_tile_off[n_clips] > 0x7fffffffLL) { delete pl; return fail(ctx, -29, "batch too large for one launch"); }
+
+#define PL_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int r_ = fail(ctx, -10, "%s failed: %s", #call, cudaGetErrorString(e_)); delete pl; return r_; } } while (0)
+    PL_OK(upload(pl->d_samp_off, pl->samp_off));
+    PL_OK(upload(pl->d_frame_off, pl->frame_off));
+    PL_OK(upload(pl->d_stft_tile_off, pl->stft_tile_off));
+    PL_OK(upload(pl->d_td_tile_off, pl->td_tile_off));
+    PL_OK(upload(pl->d_sel_chunk_off, pl->sel_chunk_off));
+
+    // FFT tables
+    {
+        std::vector<double> w64(p->window, p->window + 256);
+        std::vector<float> w32(256);
+        for (int i = 0; i < 256; i++) w32[i] = (float)w64[i];
+        std::vector<cx<double>> a(128), bq(129);
+        std::vector<cx<float>> af(128), bf(129);
+        for (int m = 0; m < 128; m++) { a[m] = {cos(2.0 * M_PI * m / 128.0), -sin(2.0 * M_PI * m / 128.0)}; af[m] = {(float)a[m].x, (float)a[m].y}; }
+        for (int k = 0; k <= 128; k++) { bq[k] = {cos(2.0 * M_PI * k / 256.0), -sin(2.0 * M_PI * k / 256.0)}; bf[k] = {(float)bq[k].x, (float)bq[k].y}; }
+        PL_OK(upload(pl->d_win64, w64)); PL_OK(upload(pl->d_tw128_64, a)); PL_OK(upload(pl->d_tw256_64, bq));
+        PL_OK(upload(pl->d_win32, w32)); PL_OK(upload(pl->d_tw128_32, af)); PL_OK(upload(pl->d_tw256_32, bf));
+        std::vector<float> fr(p->freqs, p->freqs + F);
+        PL_OK(upload(pl->d_freqs, fr));
+    }
+    // TD tables
+    {
+        const int halo = (p->blk_post_pre + 2) * p->blk_hop + p->blk_len;
+        const int lb = TD_FT * p->hop + p->n_fft + 2 * halo + 2 * TD_WARM + 2 * 64;
+        const int chunk = (lb + TD_NT - 1) / TD_NT;
+        std::vector<double> Apow, H;
+        build_td_tables(*p, ns, sos, chunk, Apow, H);
+        PL_OK(upload(pl->d_Apow, Apow)); PL_OK(upload(pl->d_H, H));
+        pl->tdt.Apow = pl->d_Apow.p; pl->tdt.H = pl->d_H.p; pl->tdt.chunk = chunk; pl->tdt.lb_max = chunk * TD_NT; pl->tdt.halo = halo;
+        const int env_cap = (TD_FT * p->hop + p->n_fft + 2 * halo) / std::max(1, p->blk_hop) + 4;
+        pl->td_smem = sizeof(double) * ((size_t)pl->tdt.lb_max + 2 * TD_NT * 2 * ns + env_cap) +
+                      sizeof(float) * (size_t)(TD_FT * p->hop + p->n_fft + 2 * halo + 64);
+    }
+    // scratch
+    PL_OK(pl->d_Pband.alloc((size_t)pl->nF * K));
+    PL_OK(pl->d_db.alloc((size_t)pl->nF * K));
+    PL_OK(pl->d_td.alloc((size_t)pl->nF * APT_N_TD_FEATURES));
+    PL_OK(pl->d_dbsum.alloc(n_clips));
+    PL_OK(pl->d_sel.alloc(n_clips));
+    PL_OK(pl->d_hist.alloc((size_t)n_clips * 2 * SEL_BINS));
+    PL_OK(pl->d_counter.alloc(64));
+    pl->scratch_bytes = sizeof(float) * ((size_t)pl->nF * K * 2 + (size_t)pl->nF * APT_N_TD_FEATURES) +
+                        (size_t)n_clips * (sizeof(double) + sizeof(SelState) + 2 * SEL_BINS * sizeof(uint32_t));
+    PL_OK(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
+    PL_OK(cudaStreamCreateWithFlags(&pl->s_comp, cudaStreamNonBlocking));
+    PL_OK(cudaStreamCreateWithFlags(&pl->s_back, cudaStreamNonBlocking));
+#undef PL_OK
+    *out = pl;
+    return 0;
+}
+
+void apt_plan_destroy(apt_plan_t* plan) {
+    if (!plan) return;
+    if (plan->s_copy) cudaStreamDestroy(plan->s_copy);
+    if (plan->s_comp) cudaStreamDestroy(plan->s_comp);
+    if (plan->s_back) cudaStreamDestroy(plan->s_back);
+    delete plan;
+}
+
+int apt_plan_offsets(const apt_plan_t* plan, int64_t* so, int64_t* fo) {
+    if (!plan) return -1;
+    if (so) memcpy(so, plan->samp_off.data(), sizeof(int64_t) * (plan->n_clips + 1));
+    if (fo) memcpy(fo, plan->frame_off.data(), sizeof(int64_t) * (plan->n_clips + 1));
+    return 0;
+}
+int64_t apt_plan_total_frames(const apt_plan_t* plan) { return plan ? plan->nF : -1; }
+int64_t apt_plan_total_samples(const apt_plan_t* plan) { return plan ? plan->nS : -1; }
+int64_t apt_plan_scratch_bytes(const apt_plan_t* plan) { return plan ? (int64_t)plan->scratch_bytes : -1; }
+int apt_plan_last_launches(const apt_plan_t* plan) { return plan ? plan->last_launches : -1; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename PCM>
+static cudaError_t launch_stft(apt_plan* pl, const Batch& b, const PCM* pcm, const StftOut& so, cudaStream_t st) {
+    const int64_t tiles = pl->stft_tile_off[b.clip0 + b.n_clips] - pl->stft_tile_off[b.clip0];
+    if (tiles <= 0) return cudaSuccess;
+    FftTables<T> tab;
+    if constexpr (sizeof(T) == 8) { tab.win = pl->d_win64.p; tab.tw128 = pl->d_tw128_64.p; tab.tw256 = pl->d_tw256_64.p; }
+    else { tab.win = pl->d_win32.p; tab.tw128 = pl->d_tw128_32.p; tab.tw256 = pl->d_tw256_32.p; }
+    const size_t smem = stft_smem_bytes<T>();
+    auto kern = stft256_kernel<T, PCM>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)tiles, STFT_NT, smem, st>>>(pl->dp, b, pcm, pl->d_stft_tile_off.p, tab, so);
+    pl->last_launches++;
+    return cudaGetLastError();
+}
+
+template <int NS, typename PCM>
+static cudaError_t launch_td_ns(apt_plan* pl, const Batch& b, const PCM* pcm, const TdOut& to, cudaStream_t st) {
+    const int64_t tiles = pl->td_tile_off[b.clip0 + b.n_clips] - pl->td_tile_off[b.clip0];
+    if (tiles <= 0) return cudaSuccess;
+    auto kern = td_features_kernel<NS, PCM>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->td_smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)tiles, TD_NT, pl->td_smem, st>>>(pl->dp, b, pcm, pl->d_td_tile_off.p, pl->tdt, to);
+    pl->last_launches++;
+    return cudaGetLastError();
+}
+template <typename PCM>
+static cudaError_t launch_td(apt_plan* pl, const Batch& b, const PCM* pcm, const TdOut& to, cudaStream_t st) {
+    switch (pl->td_ns) {
+        case 1: return launch_td_ns<1, PCM>(pl, b, pcm, to, st);
+        case 2: return launch_td_ns<2, PCM>(pl, b, pcm, to, st);
+        case 3: return launch_td_ns<3, PCM>(pl, b, pcm, to, st);
+        case 4: return launch_td_ns<4, PCM>(pl, b, pcm, to, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <typename PCM>
+static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM* pcm, const apt_out_t* out, cudaStream_t st,
+                     int counter_slot) {
+    apt_ctx* ctx = pl->ctx;
+    const DevParams& d = pl->dp;
+    Batch b{clip0, n_clips, pl->d_samp_off.p, pl->d_frame_off.p};
+    const bool full = (stages & APT_STAGE_FULL) != 0;
+    if (full && (!out->frame_class || !out->rain_conf || !out->noise_conf || !out->event_idx || !out->event_count || !out->clip_stats))
+        return fail(ctx, -30, "full pipeline requires frame_class, rain_conf, noise_conf, event_idx, event_count, clip_stats buffers");
+    if (!full && !(out->band_energy || out->P || out->S || out->raw))
+        return fail(ctx, -31, "features stage requires at least one of band_energy / P / S / raw");
+
+    StftOut so;
+    so.S = out->S; so.P = out->P; so.P_band = full ? pl->d_Pband.p : nullptr; so.band_energy = out->band_energy;
+    so.raw = out->raw; so.freqs = pl->d_freqs.p; so.nF = pl->nF;
+    cudaError_t e = pl->prm.fft_f64 ? launch_stft<double, PCM>(pl, b, pcm, so, st) : launch_stft<float, PCM>(pl, b, pcm, so, st);
+    if (e != cudaSuccess) return fail(ctx, -11, "stft launch failed: %s", cudaGetErrorString(e));
+    if (!full) return 0;
+
+    TdOut to;
+    to.td = out->td ? out->td : pl->d_td.p; to.x_td = out->x_td; to.nF = pl->nF;
+    to.want_block = out->td != nullptr; to.want_kurt = (out->td != nullptr) || d.has_ku;
+    e = launch_td<PCM>(pl, b, pcm, to, st);
+    if (e != cudaSuccess) return fail(ctx, -11, "td launch failed: %s", cudaGetErrorString(e));
+
+    SeqIO io;
+    io.P_band = pl->d_Pband.p; io.td = to.td;
+    io.frame_class = out->frame_class; io.rain_conf = out->rain_conf; io.noise_conf = out->noise_conf;
+    io.event_idx = out->event_idx; io.event_count = out->event_count;
+    io.det_noise_psd = out->det_noise_psd; io.det_noise_lag = out->det_noise_lag; io.D = out->D; io.noise_psd = out->noise_psd;
+    io.mode_flux = out->mode_flux; io.norm_flux = out->norm_flux; io.score = out->score; io.gate = out->gate;
+    io.db_plane = pl->d_db.p; io.db_sum = pl->d_dbsum.p; io.clip_counter = pl->d_counter.p + counter_slot; io.nF = pl->nF;
+    CUDA_OK(ctx, cudaMemsetAsync(io.clip_counter, 0, sizeof(int), st));
+    int occ = 0;
+    const size_t seq_smem = seq_smem_bytes(d.K);
+    CUDA_OK(ctx, cudaFuncSetAttribute(clip_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem));
+    CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clip_seq_kernel, SEQ_NT, seq_smem));
+    if (occ < 1) occ = 1;
+    const int grid = std::min(n_clips, ctx->sm_count * occ);
+    clip_seq_kernel<<<grid, SEQ_NT, seq_smem, st>>>(pl->dp, b, io);
+    pl->last_launches++;
+    CUDA_OK(ctx, cudaGetLastError());
+
+    // exact median of the dB plane
+    if (!d.suppressor_bypass) {
+        select_init_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(b, d.K, pl->d_sel.p);
+        pl->last_launches++;
+        const int64_t chunks = pl->sel_chunk_off[clip0 + n_clips] - pl->sel_chunk_off[clip0];
+        uint32_t* hist = pl->d_hist.p;
+        for (int level = 0; level < 3; level++) {
+            CUDA_OK(ctx, cudaMemsetAsync(hist + (size_t)clip0 * 2 * SEL_BINS, 0, sizeof(uint32_t) * (size_t)n_clips * 2 * SEL_BINS, st));
+            select_hist_kernel<<<(unsigned)chunks, 128, 0, st>>>(b, d.K, pl->d_db.p, pl->d_sel_chunk_off.p, level, pl->d_sel.p, hist);
+            select_scan_kernel<<<(n_clips * 32 + 127) / 128, 128, 0, st>>>(clip0, n_clips, level, pl->d_sel.p, hist);
+            pl->last_launches += 2;
+        }
+        CUDA_OK(ctx, cudaGetLastError());
+    }
+    finalize_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(pl->dp, b, pl->d_sel.p, pl->d_dbsum.p, out->event_count, out->clip_stats, 0);
+    pl->last_launches++;
+    CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int apt_run_i16(apt_plan_t* plan, int stages, const int16_t* dev_pcm, const apt_out_t* out, void* stream) {
+    if (!plan) return -1;
+    if (!dev_pcm || !out) return fail(plan->ctx, -1, "apt_run_i16: null buffer");
+    CUDA_OK(plan->ctx, cudaSetDevice(plan->ctx->device));
+    plan->last_launches = 0;
+    return run_range<int16_t>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream, 0);
+}
+
+int apt_run_f32(apt_plan_t* plan, int stages, const float* dev_pcm, const apt_out_t* out, void* stream) {
+    if (!plan) return -1;
+    if (!dev_pcm || !out) return fail(plan->ctx, -1, "apt_run_f32: null buffer");
+    CUDA_OK(plan->ctx, cudaSetDevice(plan->ctx->device));
+    plan->last_launches = 0;
+    return run_range<float>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream, 0);
+}
+
+int apt_run_host_i16(apt_plan_t* pl, const int16_t* host_pcm, int8_t* frame_class, float* rain_conf, float* noise_conf,
+                     int32_t* event_idx, int32_t* event_count, float* clip_stats) {
+    if (!pl) return -1;
+    apt_ctx* ctx = pl->ctx;
+    if (!host_pcm) return fail(ctx, -1, "apt_run_host_i16: null PCM");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    pl->last_launches = 0;
+    if (!pl->d_pcm.p) {
+        CUDA_OK(ctx, pl->d_pcm.alloc((size_t)pl->nS));
+        CUDA_OK(ctx, pl->d_fc.alloc((size_t)pl->nF)); CUDA_OK(ctx, pl->d_rc.alloc((size_t)pl->nF)); CUDA_OK(ctx, pl->d_nc.alloc((size_t)pl->nF));
+        CUDA_OK(ctx, pl->d_ev.alloc((size_t)pl->nF)); CUDA_OK(ctx, pl->d_evc.alloc((size_t)pl->n_clips));
+        CUDA_OK(ctx, pl->d_stats.alloc((size_t)pl->n_clips * APT_N_CLIP_STATS));
+    }
+    apt_out_t o;
+    memset(&o, 0, sizeof(o));
+    o.frame_class = pl->d_fc.p; o.rain_conf = pl->d_rc.p; o.noise_conf = pl->d_nc.p;
+    o.event_idx = pl->d_ev.p; o.event_count = pl->d_evc.p; o.clip_stats = pl->d_stats.p;
+    // clip groups: group g+1 is copied in (copy stream) while group g computes (compute stream) and
+    // group g-1's results travel back (return stream)
+    const int n_groups = std::min(pl->n_clips, 8);
+    std::vector<cudaEvent_t> ev(n_groups, nullptr), done(n_groups, nullptr);
+    int rc = 0;
+    for (int g = 0; g < n_groups && rc == 0; g++) {
+        const int c0 = (int)((int64_t)pl->n_clips * g / n_groups), c1 = (int)((int64_t)pl->n_clips * (g + 1) / n_groups);
+        const int64_t s0 = pl->samp_off[c0], s1 = pl->samp_off[c1];
+        const int64_t f0 = pl->frame_off[c0], f1 = pl->frame_off[c1];
+        cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming);
+        cudaMemcpyAsync(pl->d_pcm.p + s0, host_pcm + s0, (size_t)(s1 - s0) * sizeof(int16_t), cudaMemcpyHostToDevice, pl->s_copy);
+        cudaEventRecord(ev[g], pl->s_copy);
+        cudaStreamWaitEvent(pl->s_comp, ev[g], 0);
+        rc = run_range<int16_t>(pl, APT_STAGE_FULL, c0, c1 - c0, pl->d_pcm.p, &o, pl->s_comp, g);
+        if (rc != 0) break;
+        cudaEventRecord(done[g], pl->s_comp);
+        cudaStreamWaitEvent(pl->s_back, done[g], 0);
+        if (frame_class) cudaMemcpyAsync(frame_class + f0, pl->d_fc.p + f0, (size_t)(f1 - f0), cudaMemcpyDeviceToHost, pl->s_back);
+        if (rain_conf) cudaMemcpyAsync(rain_conf + f0, pl->d_rc.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, pl->s_back);
+        if (noise_conf) cudaMemcpyAsync(noise_conf + f0, pl->d_nc.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, pl->s_back);
+        if (event_idx) cudaMemcpyAsync(event_idx + f0, pl->d_ev.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, pl->s_back);
+        if (event_count) cudaMemcpyAsync(event_count + c0, pl->d_evc.p + c0, (size_t)(c1 - c0) * 4, cudaMemcpyDeviceToHost, pl->s_back);
+        if (clip_stats) cudaMemcpyAsync(clip_stats + (size_t)c0 * APT_N_CLIP_STATS, pl->d_stats.p + (size_t)c0 * APT_N_CLIP_STATS,
+                                        (size_t)(c1 - c0) * APT_N_CLIP_STATS * 4, cudaMemcpyDeviceToHost, pl->s_back);
+    }
+    cudaError_t e0 = cudaStreamSynchronize(pl->s_copy), e1 = cudaStreamSynchronize(pl->s_comp), e2 = cudaStreamSynchronize(pl->s_back);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : done) if (e) cudaEventDestroy(e);
+    if (rc != 0) return rc;
+    if (e0 != cudaSuccess) return fail(ctx, -12, "copy stream: %s", cudaGetErrorString(e0));
+    if (e1 != cudaSuccess) return fail(ctx, -12, "compute stream: %s", cudaGetErrorString(e1));
+    if (e2 != cudaSuccess) return fail(ctx, -12, "return stream: %s", cudaGetErrorString(e2));
+    return 0;
+}
+
+}  // extern "C"

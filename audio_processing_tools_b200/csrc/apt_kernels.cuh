@@ -1,0 +1,1076 @@
+// apt_kernels.cuh -- sm_100a kernels of the hot path.
+//
+// Kernel map (DESIGN.md has the data layout and rooflines):
+//   stft256_kernel      K1+K2+K3  PCM -> frames -> Hann -> rFFT-256 -> power -> band planes
+//   td_features_kernel  K6+K7     PCM -> zero-phase SOS prefilter -> crest / kurtosis / block features
+//   clip_seq_kernel     K4+K5+K8+K9  per-clip time recursions: tracker pass 1, dB normalisation, flux,
+//                                 baselines, decision, labels, event compaction, tracker pass 2, dB stats
+//   select_*            K9        exact median of the noise-floor dB plane (3-level radix select)
+//   finalize_kernel     K9        clip statistics rows
+//
+// Compile with -fmad=false: roundings are deliberate (see apt_math.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include "apt_math.cuh"
+#include "../../include/apt_b200.h"
+
+namespace apt {
+
+__constant__ uint32_t kSvmlLog10TabDev[64] = {
+    0xbdc9ae9b, 0xbda6fcf4, 0xbd8bac76, 0xbd6bca30, 0xbd48a99b, 0xbd2c0a9f, 0xbd1480db, 0xbd00faf2,
+    0xbe823aa9, 0xbe656348, 0xbe4afbb9, 0xbe346895, 0xbe20ffff, 0xbe103a0b, 0xbe01a91c, 0xbde9e84e,
+    0x3e13d888, 0x3e10a87c, 0x3e0b95c3, 0x3e057f0b, 0x3dfde038, 0x3df080d9, 0x3de34c1e, 0x3dd68333,
+    0x3dac6e8e, 0x3dd54a51, 0x3df30f40, 0x3e04235d, 0x3e0b7033, 0x3e102c90, 0x3e12ebad, 0x3e141ff8,
+    0xbe5e5a9b, 0xbe5e2677, 0xbe5d83f5, 0xbe5c6016, 0xbe5abd0b, 0xbe58a6fd, 0xbe562e02, 0xbe5362f8,
+    0xbe68e27c, 0xbe646747, 0xbe619a73, 0xbe5ff05a, 0xbe5f0570, 0xbe5e92d0, 0xbe5e662b, 0xbe5e5c08,
+    0x3ede5bd8, 0x3ede5b45, 0x3ede57d8, 0x3ede4eb1, 0x3ede3d37, 0x3ede2166, 0x3eddf9d9, 0x3eddc5bb,
+    0x3ede08ed, 0x3ede32e7, 0x3ede4967, 0x3ede5490, 0x3ede597f, 0x3ede5b50, 0x3ede5bca, 0x3ede5bd9};
+
+struct DevParams {
+    int n_fft, hop, F, band_lo, K, M;
+    int mode_lo[APT_MAX_MODES], mode_hi[APT_MAX_MODES];
+    int mode_blo[APT_MAX_MODES], mode_bhi[APT_MAX_MODES];
+    double mode_w[APT_MAX_MODES];
+    float trk_eta, trk_alpha, trk_1m_alpha, trk_floor, trk_q, trk_nq, trk_maxr;
+    double ema_up, ema_down;
+    int warm_need;
+    float eps32;
+    int use_norm, ratio_db;
+    double bl_q, bl_eta, bl_alpha, bl_floor;
+    int norm_enable;
+    float norm_min;
+    float thr0, thr1, thr2, thr3;
+    int min_support;
+    float gate_thr;
+    int has_ku;
+    float ku;
+    float noise_hi, mf_noise_max;
+    int n_sos, padlen;
+    double sos[APT_MAX_SOS][6];
+    double zi[APT_MAX_SOS][2];
+    double eps64;
+    int blk_len, blk_hop, blk_pp, blk_smooth;
+    int low_lo, low_hi, rain_lo, rain_hi;
+    double rolloff;
+    int suppressor_bypass;
+    int min_frames;
+};
+
+// A launch covers clips [clip0, clip0 + n_clips) of the plan; the offset arrays are the plan's
+// (absolute) prefix arrays.
+struct Batch {
+    int clip0, n_clips;
+    const int64_t* samp_off;   // [plan clips + 1]
+    const int64_t* frame_off;  // [plan clips + 1]
+};
+
+// tile -> clip: tile_off is the plan's absolute prefix array of tiles per clip
+__device__ __forceinline__ int find_clip(const int64_t* __restrict__ off, int n_clips, int64_t x) {
+    // largest c with off[c] <= x
+    int lo = 0, hi = n_clips;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ int tile_clip(const Batch& b, const int64_t* __restrict__ tile_off, int64_t& tile_in_clip) {
+    const int64_t x = (int64_t)blockIdx.x + __ldg(tile_off + b.clip0);
+    const int c = b.clip0 + find_clip(tile_off + b.clip0, b.n_clips, x);
+    tile_in_clip = x - __ldg(tile_off + c);
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PCM access: int16 (wire format) or float32 (what the reference's loader hands to processors)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float load_sample(const int16_t* p, int64_t i) { return pcm_to_f32(__ldg(p + i)); }
+__device__ __forceinline__ float load_sample(const float* p, int64_t i) { return __ldg(p + i); }
+
+// Stages samples [s0, s0+n) of a clip (clip-relative indices, zero outside [0, N)) into shared memory
+// as float32.  The body uses 128-bit global loads on 16-byte aligned addresses.
+template <typename PCM>
+__device__ __forceinline__ void stage_clip_f32(const PCM* __restrict__ pcm, int64_t clip_base, int64_t N,
+                                               int64_t s0, int n, float* __restrict__ dst) {
+    constexpr int VEC = 16 / (int)sizeof(PCM);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // global element index of dst[0]
+    const int64_t g0 = clip_base + s0;
+    // first i such that (g0 + i) is a multiple of VEC
+    int head = (int)((VEC - (g0 % VEC + VEC) % VEC) % VEC);
+    if (head > n) head = n;
+    for (int i = tid; i < head; i += nt) {
+        int64_t s = s0 + i;
+        dst[i] = (s >= 0 && s < N) ? load_sample(pcm, clip_base + s) : 0.0f;
+    }
+    const int nvec = (n - head) / VEC;
+    for (int v = tid; v < nvec; v += nt) {
+        const int i = head + v * VEC;
+        const int64_t s = s0 + i;
+        if (s >= 0 && s + VEC <= N) {
+            const int4 raw = __ldg(reinterpret_cast<const int4*>(pcm + clip_base + s));
+            if constexpr (sizeof(PCM) == 2) {
+                const int16_t* h = reinterpret_cast<const int16_t*>(&raw);
+#pragma unroll
+                for (int e = 0; e < 8; e++) dst[i + e] = pcm_to_f32(h[e]);
+            } else {
+                const float* f = reinterpret_cast<const float*>(&raw);
+#pragma unroll
+                for (int e = 0; e < 4; e++) dst[i + e] = f[e];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; e++) {
+                int64_t se = s + e;
+                dst[i + e] = (se >= 0 && se < N) ? load_sample(pcm, clip_base + se) : 0.0f;
+            }
+        }
+    }
+    for (int i = head + nvec * VEC + tid; i < n; i += nt) {
+        int64_t s = s0 + i;
+        dst[i] = (s >= 0 && s < N) ? load_sample(pcm, clip_base + s) : 0.0f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1+K2+K3: STFT (n_fft = 256) + power + band planes
+// ---------------------------------------------------------------------------------------------
+constexpr int STFT_TF = 32;          // frames per tile
+constexpr int STFT_NT = STFT_TF * 8; // 8 lanes per frame
+constexpr int STFT_PS = 132;         // row stride of the power tile (F = 129)
+
+template <typename T>
+struct FftTables {
+    const T* win;          // [256]
+    const cx<T>* tw128;    // [128]
+    const cx<T>* tw256;    // [129]
+};
+
+struct StftOut {
+    float* S;            // [nF][F][2]
+    float* P;            // [nF][F]
+    float* P_band;       // [nF][K]   (scratch plane consumed by clip_seq_kernel)
+    float* band_energy;  // [M+1][nF]
+    float* raw;          // [21][nF]
+    const float* freqs;  // [F] device
+    int64_t nF;
+};
+
+template <typename T>
+constexpr size_t stft_smem_bytes() {
+    return sizeof(float) * ((STFT_TF + 1) * 128) + sizeof(cx<T>) * (size_t)STFT_TF * kExSize + sizeof(T) * 256 +
+           sizeof(cx<T>) * (128 + 129) + sizeof(float) * STFT_TF * STFT_PS + 64;
+}
+
+__device__ void raw_features_frame(const DevParams& p, const float* __restrict__ Pt, const float* __restrict__ freqs,
+                                   float* __restrict__ out, int64_t stride);
+
+template <typename T, typename PCM>
+__global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant__ DevParams p, Batch b,
+                                                          const PCM* __restrict__ pcm,
+                                                          const int64_t* __restrict__ tile_off, FftTables<T> tab,
+                                                          StftOut o) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* s_ex = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* s_tw128 = s_ex + (size_t)STFT_TF * kExSize;
+    cx<T>* s_tw256 = s_tw128 + 128;
+    T* s_win = reinterpret_cast<T*>(s_tw256 + 129);
+    float* s_x = reinterpret_cast<float*>(s_win + 256);
+    float* s_P = s_x + (STFT_TF + 1) * 128;
+
+    const int tid = threadIdx.x;
+    int64_t tile_in_clip;
+    const int c = tile_clip(b, tile_off, tile_in_clip);
+    const int t0 = (int)tile_in_clip * STFT_TF;
+    const int64_t base = __ldg(b.samp_off + c);
+    const int64_t N = __ldg(b.samp_off + c + 1) - base;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T_clip = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int nfr = min(STFT_TF, T_clip - t0);
+
+    for (int i = tid; i < 256; i += STFT_NT) s_win[i] = tab.win[i];
+    for (int i = tid; i < 128; i += STFT_NT) s_tw128[i] = tab.tw128[i];
+    for (int i = tid; i < 129; i += STFT_NT) s_tw256[i] = tab.tw256[i];
+    stage_clip_f32(pcm, base, N, (int64_t)t0 * 128 - 128, (STFT_TF + 1) * 128, s_x);
+    __syncthreads();
+
+    const int fr = tid >> 3, lane = tid & 7;
+    const float* xs = s_x + fr * 128;
+    cx<T>* ex = s_ex + (size_t)fr * kExSize;
+    if (fr < nfr) rfft256_passA<T>(lane, [&](int n) { return xs[n]; }, s_win, s_tw128, ex);
+    __syncthreads();
+    if (fr < nfr) {
+        float* Pt = s_P + fr * STFT_PS;
+        float* Sg = o.S ? o.S + ((f0 + t0 + fr) * (int64_t)p.F) * 2 : nullptr;
+        rfft256_passB<T>(lane, ex, s_tw256, [&](int k, T re, T im) {
+            float sr = d2f((double)re), si = d2f((double)im);
+            if (Sg) { Sg[2 * k] = sr; Sg[2 * k + 1] = si; }
+            float a = np_cabsf(sr, si);
+            Pt[k] = a * a;
+        });
+    }
+    __syncthreads();
+
+    // coalesced plane writes
+    const int64_t fbase = f0 + t0;
+    if (o.P_band) {
+        float* dst = o.P_band + fbase * p.K;
+        for (int i = tid; i < nfr * p.K; i += STFT_NT) {
+            int t = i / p.K, k = i - t * p.K;
+            dst[i] = s_P[t * STFT_PS + p.band_lo + k];
+        }
+    }
+    if (o.P) {
+        float* dst = o.P + fbase * p.F;
+        for (int i = tid; i < nfr * p.F; i += STFT_NT) {
+            int t = i / p.F, k = i - t * p.F;
+            dst[i] = s_P[t * STFT_PS + k];
+        }
+    }
+    if (o.band_energy) {
+        for (int i = tid; i < nfr * (p.M + 1); i += STFT_NT) {
+            int m = i / nfr, t = i - m * nfr;
+            const float* Pt = s_P + t * STFT_PS;
+            double s = 0.0;
+            if (m < p.M) {
+                for (int k = p.mode_lo[m]; k <= p.mode_hi[m]; k++) s += (double)Pt[k];
+            } else {
+                for (int k = 0; k < p.K; k++) s += (double)Pt[p.band_lo + k];
+                s += p.eps64;
+            }
+            o.band_energy[(int64_t)m * o.nF + fbase + t] = d2f(s);
+        }
+    }
+    if (o.raw) {
+        if (tid < nfr) raw_features_frame(p, s_P + tid * STFT_PS, o.freqs, o.raw + fbase + tid, o.nF);
+    }
+}
+
+// raw spectral features of one frame in float64 (feature_extraction.py:610-747)
+__device__ void raw_features_frame(const DevParams& p, const float* __restrict__ Pt, const float* __restrict__ freqs,
+                                   float* __restrict__ out, int64_t stride) {
+    const double eps = p.eps64;
+    const int lo = p.band_lo, K = p.K, F = p.F;
+    double total = 0.0;
+    for (int k = 1; k < F; k++) total += (double)Pt[k];
+    const double total_nodc = F > 1 ? total + eps : (double)Pt[0] + eps;
+    double op = 0.0, cen = 0.0;
+    for (int k = 0; k < K; k++) { double v = (double)Pt[lo + k]; op += v; cen += (double)__ldg(freqs + lo + k) * v; }
+    op += eps;
+    cen /= op;
+    double bw = 0.0;
+    for (int k = 0; k < K; k++) { double d = (double)__ldg(freqs + lo + k) - cen; bw += d * d * (double)Pt[lo + k]; }
+    bw = sqrt(bw / op);
+    double lowr = 0.0, rainr = 0.0;
+    for (int k = p.low_lo; k <= p.low_hi; k++) lowr += (double)Pt[k];
+    for (int k = p.rain_lo; k <= p.rain_hi; k++) rainr += (double)Pt[k];
+    lowr /= total_nodc; rainr /= total_nodc;
+    double mbp[APT_MAX_MODES], mtot = 0.0;
+    for (int i = 0; i < p.M; i++) {
+        double s = 0.0;
+        for (int k = p.mode_lo[i]; k <= p.mode_hi[i]; k++) s += (double)Pt[k];
+        mbp[i] = s; mtot += s;
+    }
+    mtot += eps;
+    double ent = 0.0, mean = 0.0, mx = -1e300;
+    for (int i = 0; i < p.M; i++) {
+        double r = mbp[i] / mtot;
+        mbp[i] = r;
+        ent += r * log(r + eps);
+        mean += r;
+        mx = r > mx ? r : mx;
+    }
+    mean /= (double)p.M;
+    double var = 0.0;
+    for (int i = 0; i < p.M; i++) { double d = mbp[i] - mean; var += d * d; }
+    const double sd = sqrt(var / (double)p.M);
+    double mlog = 0.0, marith = 0.0;
+    for (int k = 0; k < K; k++) { double v = (double)Pt[lo + k] + eps; mlog += log(v); marith += v; }
+    const double flat = exp(mlog / (double)K) / (marith / (double)K + eps);
+    double frac = p.rolloff < 0.0 ? 0.0 : (p.rolloff > 1.0 ? 1.0 : p.rolloff);
+    const double thr = frac * op;
+    double cs = 0.0;
+    int ridx = 0, found = 0, dom = 0;
+    for (int k = 0; k < K; k++) {
+        cs += (double)Pt[lo + k];
+        if (!found && cs >= thr) { ridx = k; found = 1; }
+        if (Pt[lo + k] > Pt[lo + dom]) dom = k;
+    }
+    const int ncep = 2 * (K - 1);
+    double cep[5] = {0, 0, 0, 0, 0};
+    if (K >= 2) {
+        const double l0 = log(fmax((double)Pt[lo], eps)), lN = log(fmax((double)Pt[lo + K - 1], eps));
+        for (int j = 0; j < 5; j++) cep[j] = l0 + ((j & 1) ? -lN : lN);
+        for (int k = 1; k < K - 1; k++) {
+            const double lg = 2.0 * log(fmax((double)Pt[lo + k], eps));
+            for (int j = 0; j < 5; j++) cep[j] += lg * cospi(2.0 * (double)j * (double)k / (double)ncep);
+        }
+        for (int j = 0; j < 5; j++) cep[j] = (j < ncep) ? cep[j] / (double)ncep : 0.0;
+    }
+    out[0 * stride] = d2f(cen); out[1 * stride] = d2f(bw); out[2 * stride] = d2f(lowr); out[3 * stride] = d2f(rainr);
+    for (int i = 0; i < 5; i++) out[(4 + i) * stride] = i < p.M ? d2f(mbp[i]) : 0.0f;
+    out[9 * stride] = d2f(-ent); out[10 * stride] = d2f(sd); out[11 * stride] = d2f(mx); out[12 * stride] = d2f(flat);
+    out[13 * stride] = __ldg(freqs + lo + ridx); out[14 * stride] = __ldg(freqs + lo + dom); out[15 * stride] = d2f(op);
+    for (int j = 0; j < 5; j++) out[(16 + j) * stride] = d2f(cep[j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6+K7: zero-phase SOS prefilter (scipy.signal.sosfiltfilt, float64) + TD frame features
+// ---------------------------------------------------------------------------------------------
+constexpr int TD_NT = 256;
+constexpr int TD_FT = 32;       // TD frames per tile
+constexpr int TD_WARM = 512;    // warm-up samples each side (pole radius 0.928 -> < 2^-53 after 490)
+constexpr int TD_MAXDIM = 2 * APT_MAX_SOS;
+
+struct TdTables {
+    // block-parallel IIR tables, computed at plan time for chunk length `chunk` (state dim = 2*n_sos):
+    const double* Apow;  // [8][dim][dim]  A^(2^k), A = transition over one chunk
+    const double* H;     // [chunk][dim]   output response at step n to a unit initial state
+    int chunk;           // samples per thread
+    int lb_max;          // capacity of the float64 buffer (samples)
+    int halo;            // extra valid samples each side of the frames (block features)
+};
+
+struct TdOut {
+    float* td;       // [5][nF]  (rows: crest, kurtosis, block crest, block width, block post/pre)
+    float* x_td;     // [nS] optional
+    int64_t nF;
+    int want_kurt;   // compute kurtosis
+    int want_block;  // compute block features
+};
+
+// one biquad cascade step (DF2T), float64, FMAs allowed (not bit-compared; 1e-16 level)
+template <int NS>
+__device__ __forceinline__ double sos_step(const double (&c)[NS][6], double (&z)[NS][2], double x) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        double y = d_fma(c[s][0], x, z[s][0]);
+        z[s][0] = d_fma(-c[s][4], y, d_fma(c[s][1], x, z[s][1]));
+        z[s][1] = d_fma(-c[s][5], y, c[s][2] * x);
+        x = y;
+    }
+    return x;
+}
+
+// In-place block-parallel filtering of buf[0..len) (forward if !rev, else over reversed positions).
+// Thread i owns positions [i*chunk, (i+1)*chunk).  init: state entering position 0 (or nullptr = zero).
+template <int NS>
+__device__ void block_iir(const DevParams& p, const TdTables& tb, double* __restrict__ buf, int len, bool rev,
+                          const double* init, double* __restrict__ s_state /*[TD_NT][2*NS] x2*/) {
+    constexpr int DIM = 2 * NS;
+    const int tid = threadIdx.x;
+    const int c = tb.chunk;
+    const int a = tid * c, e = min(len, a + c);
+    double coef[NS][6];
+#pragma unroll
+    for (int s = 0; s < NS; s++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) coef[s][j] = p.sos[s][j];
+    double z[NS][2];
+#pragma unroll
+    for (int s = 0; s < NS; s++) { z[s][0] = (tid == 0 && init) ? init[2 * s] : 0.0; z[s][1] = (tid == 0 && init) ? init[2 * s + 1] : 0.0; }
+    for (int i = a; i < e; i++) {
+        const int pos = rev ? len - 1 - i : i;
+        buf[pos] = sos_step<NS>(coef, z, buf[pos]);
+    }
+    // a partial (or empty) chunk still has to carry its state across the missing samples so that the
+    // scan below can use one transition matrix; only the last active chunk can be partial and nothing
+    // follows it, so its outgoing state is irrelevant.
+    double* v0 = s_state;
+    double* v1 = s_state + TD_NT * DIM;
+#pragma unroll
+    for (int s = 0; s < NS; s++) { v0[tid * DIM + 2 * s] = z[s][0]; v0[tid * DIM + 2 * s + 1] = z[s][1]; }
+    __syncthreads();
+    // Kogge-Stone: v_i <- v_i + A^(2^k) v_{i-2^k}
+    double* src = v0;
+    double* dst = v1;
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        const int d = 1 << k;
+        double acc[DIM];
+#pragma unroll
+        for (int r = 0; r < DIM; r++) acc[r] = src[tid * DIM + r];
+        if (tid >= d) {
+            const double* A = tb.Apow + k * DIM * DIM;
+            double u[DIM];
+#pragma unroll
+            for (int r = 0; r < DIM; r++) u[r] = src[(tid - d) * DIM + r];
+#pragma unroll
+            for (int r = 0; r < DIM; r++)
+#pragma unroll
+                for (int q = 0; q < DIM; q++) acc[r] = d_fma(__ldg(A + r * DIM + q), u[q], acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < DIM; r++) dst[tid * DIM + r] = acc[r];
+        __syncthreads();
+        double* t = src; src = dst; dst = t;
+    }
+    // incoming state of thread i (i >= 1) is the scanned value of thread i-1; add its homogeneous response
+    if (tid >= 1 && a < len) {
+        double sin_[DIM];
+#pragma unroll
+        for (int r = 0; r < DIM; r++) sin_[r] = src[(tid - 1) * DIM + r];
+        for (int i = a; i < e; i++) {
+            const int pos = rev ? len - 1 - i : i;
+            const double* h = tb.H + (i - a) * DIM;
+            double y = buf[pos];
+#pragma unroll
+            for (int r = 0; r < DIM; r++) y = d_fma(__ldg(h + r), sin_[r], y);
+            buf[pos] = y;
+        }
+    }
+    __syncthreads();
+}
+
+// numpy pairwise sum of n = 128 * 2^m contiguous float32 values spread over 8 lanes (lane j = accumulator j).
+// `ld(i)` returns element i.  All 8 lanes of the group return the total (0 + pairwise).
+template <typename Load>
+__device__ __forceinline__ float group8_np_sum(Load ld, int n, int lane, unsigned gmask) {
+    float part[32];  // per 128-block results (n <= 4096)
+    const int nblk = n >> 7;
+    for (int blk = 0; blk < nblk; blk++) {
+        float r = ld(blk * 128 + lane);
+#pragma unroll
+        for (int i = 1; i < 16; i++) r += ld(blk * 128 + 8 * i + lane);
+        // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
+        float o1 = __shfl_xor_sync(gmask, r, 1);
+        float s1 = (lane & 1) ? o1 + r : r + o1;
+        float o2 = __shfl_xor_sync(gmask, s1, 2);
+        float s2 = (lane & 2) ? o2 + s1 : s1 + o2;
+        float o4 = __shfl_xor_sync(gmask, s2, 4);
+        part[blk] = (lane & 4) ? o4 + s2 : s2 + o4;
+    }
+    // binary tree over blocks (n2 = n/2 is a multiple of 8 for these sizes)
+    for (int w = 1; w < nblk; w <<= 1)
+        for (int i = 0; i + w < nblk; i += 2 * w) part[i] = part[i] + part[i + w];
+    return 0.0f + part[0];
+}
+
+__device__ double td_peak_width_half(const double* x, int n, int peak) {
+    int i = peak, lb = peak, rb = peak;
+    double lmin = x[peak], rmin = x[peak];
+    while (0 <= i && x[i] <= x[peak]) { if (x[i] < lmin) { lmin = x[i]; lb = i; } i--; }
+    i = peak;
+    while (i <= n - 1 && x[i] <= x[peak]) { if (x[i] < rmin) { rmin = x[i]; rb = i; } i++; }
+    const double prom = x[peak] - (lmin > rmin ? lmin : rmin);
+    const double height = x[peak] - prom * 0.5;
+    i = peak;
+    while (lb < i && height < x[i]) i--;
+    double lip = (double)i;
+    if (x[i] < height) lip += (height - x[i]) / (x[i + 1] - x[i]);
+    i = peak;
+    while (i < rb && height < x[i]) i++;
+    double rip = (double)i;
+    if (x[i] < height) rip -= (height - x[i]) / (x[i - 1] - x[i]);
+    return rip - lip;
+}
+
+template <int NS, typename PCM>
+__global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constant__ DevParams p, Batch b,
+                                                            const PCM* __restrict__ pcm,
+                                                            const int64_t* __restrict__ tile_off, TdTables tb, TdOut o) {
+    constexpr int DIM = 2 * NS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_buf = reinterpret_cast<double*>(smem_raw);            // [lb_max]
+    double* s_state = s_buf + tb.lb_max;                            // [2][TD_NT][DIM]
+    double* s_env = s_state + 2 * TD_NT * DIM;                      // block envelope (want_block)
+    const int L = p.n_fft, hop = p.hop;
+    const int env_cap = (TD_FT * hop + L + 2 * tb.halo) / max(1, p.blk_hop) + 4;
+    float* s_xf = reinterpret_cast<float*>(s_env + env_cap);        // valid x_td range as float32
+    __shared__ double s_init[TD_MAXDIM];
+
+    const int tid = threadIdx.x;
+    int64_t tile_in_clip;
+    const int c = tile_clip(b, tile_off, tile_in_clip);
+    const int tile = (int)tile_in_clip;
+    const int64_t base = __ldg(b.samp_off + c);
+    const int64_t N = __ldg(b.samp_off + c + 1) - base;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T_clip = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int Tloc = N < L ? 0 : (int)(1 + (N - L) / hop);
+    const int n_tiles = (int)(__ldg(tile_off + c + 1) - __ldg(tile_off + c));
+    const int t0 = tile * TD_FT, t1 = min(Tloc, t0 + TD_FT);
+    const bool last = tile == n_tiles - 1;
+    const int pad = p.padlen;
+
+    // valid x_td range of this tile (clip-relative), then the filter buffer around it
+    int64_t vs = (int64_t)t0 * hop - tb.halo; if (vs < 0 || tile == 0) vs = 0;
+    int64_t ve = last ? N : (int64_t)(t1 - 1) * hop + L + tb.halo; if (ve > N) ve = N;
+    int64_t bs = vs - TD_WARM; if (bs < -pad) bs = -pad;
+    int64_t be = ve + TD_WARM; if (be > N + pad) be = N + pad;
+    const int len = (int)(be - bs);
+    const bool exact_l = bs == -pad, exact_r = be == N + pad;
+
+    // stage the odd-extended signal in float64 (scipy odd_ext: 2*x[0]-x[i], 2*x[N-1]-x[N-1-i])
+    for (int i = tid; i < len; i += TD_NT) {
+        const int64_t s = bs + i;
+        double v;
+        if (s < 0) v = 2.0 * (double)load_sample(pcm, base) - (double)load_sample(pcm, base - s);
+        else if (s >= N) v = 2.0 * (double)load_sample(pcm, base + N - 1) - (double)load_sample(pcm, base + 2 * (N - 1) - s);
+        else v = (double)load_sample(pcm, base + s);
+        s_buf[i] = v;
+    }
+    __syncthreads();
+    if (NS > 0) {
+        if (tid < DIM) s_init[tid] = p.zi[tid >> 1][tid & 1] * s_buf[0];
+        __syncthreads();
+        block_iir<NS>(p, tb, s_buf, len, false, exact_l ? s_init : nullptr, s_state);
+        if (tid < DIM) s_init[tid] = p.zi[tid >> 1][tid & 1] * s_buf[len - 1];
+        __syncthreads();
+        block_iir<NS>(p, tb, s_buf, len, true, exact_r ? s_init : nullptr, s_state);
+    }
+    // float32 x_td over the valid range
+    const int nv = (int)(ve - vs), voff = (int)(vs - bs);
+    for (int i = tid; i < nv; i += TD_NT) s_xf[i] = d2f(s_buf[voff + i]);
+    __syncthreads();
+    if (o.x_td) {
+        // each tile owns samples [t0*hop, (t0+TD_FT)*hop), the last tile through N
+        int64_t w0 = (int64_t)t0 * hop, w1 = last ? N : (int64_t)(t0 + TD_FT) * hop;
+        if (w1 > N) w1 = N;
+        for (int64_t s = w0 + tid; s < w1; s += TD_NT) o.x_td[base + s] = s_xf[s - vs];
+    }
+
+    // crest factor / kurtosis: 8 lanes per frame, numpy float32 summation order
+    const int grp = tid >> 3, lane = tid & 7;
+    const unsigned gmask = 0xffu << ((tid & 31) & ~7);
+    float* crest_o = o.td + f0;
+    float* kurt_o = o.td + o.nF + f0;
+    for (int fr = grp; fr < TD_FT; fr += TD_NT / 8) {
+        const int t = t0 + fr;
+        if (t >= t1) continue;   // uniform per group
+        const float* seg = s_xf + ((int64_t)t * hop - vs);
+        const float sumsq = group8_np_sum([&](int i) { float v = seg[i]; return v * v; }, L, lane, gmask);
+        float pk = 0.0f;
+        for (int i = lane; i < L; i += 8) pk = fmaxf(pk, fabsf(seg[i]));
+        pk = fmaxf(pk, __shfl_xor_sync(gmask, pk, 1));
+        pk = fmaxf(pk, __shfl_xor_sync(gmask, pk, 2));
+        pk = fmaxf(pk, __shfl_xor_sync(gmask, pk, 4));
+        float kv = 0.0f;
+        if (o.want_kurt) {
+            const float mean = f_div(group8_np_sum([&](int i) { return seg[i]; }, L, lane, gmask), (float)L);
+            const float m2 = f_div(group8_np_sum([&](int i) { float d = seg[i] - mean; return d * d; }, L, lane, gmask), (float)L);
+            const float m4 = f_div(group8_np_sum([&](int i) { double d = (double)(seg[i] - mean); return d2f((d * d) * (d * d)); }, L, lane, gmask), (float)L);
+            const float lim = 1.1920929e-07f * mean;
+            if (!(m2 <= lim * lim)) {
+                const double nn = (double)L;
+                float a = f_div(d2f(nn * nn - 1.0) * m4, m2 * m2) - d2f(3.0 * (nn - 1.0) * (nn - 1.0));
+                kv = d2f(1.0 / (nn - 2.0) / (nn - 3.0)) * a + 3.0f;
+                if (isnan(kv) || isinf(kv)) kv = 0.0f;
+            }
+        }
+        if (lane == 0) {
+            const float mean_sq = f_div(sumsq, (float)L);
+            const float rms = f_sqrt(mean_sq + d2f(p.eps64));
+            const double r = (double)rms;
+            float cf = d2f((double)pk / (r > p.eps64 ? r : p.eps64));
+            if (isnan(cf) || isinf(cf)) cf = 0.0f;
+            crest_o[t] = cf;
+            kurt_o[t] = kv;
+        }
+    }
+    // frames beyond the TD grid are zero (rain_frame_classifier.py:178-194 zero-fill alignment)
+    if (last)
+        for (int t = max(Tloc, 0) + tid; t < T_clip; t += TD_NT) {
+            crest_o[t] = 0.0f; kurt_o[t] = 0.0f;
+            if (o.want_block) { o.td[2 * o.nF + f0 + t] = 0.0f; o.td[3 * o.nF + f0 + t] = 0.0f; o.td[4 * o.nF + f0 + t] = 0.0f; }
+        }
+
+    if (o.want_block) {
+        // block-RMS envelope (feature_extraction.py:253-366).  Block sums are taken directly in float64
+        // (the reference differences a float64 cumulative sum: same value to ~1e-13 relative).
+        const int B = max(1, p.blk_len), H = max(1, p.blk_hop);
+        const int64_t nb_total = N >= B ? (N - B) / H + 1 : 0;
+        const int bstep = max(1, (int)rint((double)hop / (double)H));
+        const int bpf = max(1, (L + H - 1) / H);
+        const int pp = max(1, p.blk_pp);
+        // envelope blocks needed: [bq0, bq1) plus one neighbour each side for the smoother
+        int64_t bq0 = (int64_t)t0 * bstep - pp; if (bq0 < 0) bq0 = 0;
+        int64_t bq1 = (int64_t)(t1 - 1) * bstep + bpf + pp + 1; if (bq1 > nb_total) bq1 = nb_total;
+        const int64_t br0 = bq0 > 0 ? bq0 - 1 : 0, br1 = bq1 < nb_total ? bq1 + 1 : nb_total;
+        const int nraw = (int)(br1 - br0);
+        double* raw_env = s_buf;            // reuse (filter buffer is dead now)
+        __syncthreads();
+        for (int i = tid; i < nraw; i += TD_NT) {
+            const int64_t s = (br0 + i) * H - vs;
+            double acc = 0.0;
+            for (int e = 0; e < B; e++) { double v = (double)s_xf[s + e]; acc += v * v; }
+            const double en = acc / (double)B;
+            raw_env[i] = sqrt(en > 0.0 ? en : 0.0);
+        }
+        __syncthreads();
+        const int nenv = (int)(bq1 - bq0);
+        for (int i = tid; i < nenv; i += TD_NT) {
+            const int64_t bidx = bq0 + i;
+            const int r = (int)(bidx - br0);
+            double v = raw_env[r];
+            if (p.blk_smooth && nb_total >= 3) {
+                double acc = 0.0;
+                if (bidx > 0) acc = raw_env[r - 1] * 0.25;
+                acc = (bidx > 0) ? acc + raw_env[r] * 0.5 : raw_env[r] * 0.5;
+                if (bidx + 1 < nb_total) acc += raw_env[r + 1] * 0.25;
+                v = acc;
+            }
+            s_env[i] = v;
+        }
+        __syncthreads();
+        for (int fr = tid; fr < t1 - t0; fr += TD_NT) {
+            const int t = t0 + fr;
+            int64_t b0 = (int64_t)t * bstep, b1 = b0 + bpf;
+            if (b1 > nb_total) b1 = nb_total;
+            float oc = 0.0f, ow = 0.0f, orat = 0.0f;
+            if (b1 > b0) {
+                const int m = (int)(b1 - b0);
+                const double* fe = s_env + (b0 - bq0);
+                int pi = 0;
+                for (int i = 1; i < m; i++) if (fe[i] > fe[pi]) pi = i;
+                const double ssum = 0.0 + np_pairwise<double>([&](int i) { return fe[i] * fe[i]; }, 0, m);
+                const double rms = sqrt(ssum / (double)m);
+                const double pv = fe[pi];
+                oc = d2f(pv / (rms > p.eps64 ? rms : p.eps64));
+                if (pv > p.eps64 && m >= 3 && pi > 0 && pi < m - 1) {
+                    const double lv = fe[pi - 1], rv = fe[pi + 1];
+                    if (pv - (lv > rv ? lv : rv) > p.eps64) {
+                        const double wv = td_peak_width_half(fe, m, pi);
+                        if (isfinite(wv) && wv > 0.0) ow = d2f(wv);
+                    }
+                }
+                const int64_t pidx = b0 + pi;
+                const int64_t pre0 = pidx - pp > 0 ? pidx - pp : 0, pre1 = pidx;
+                const int64_t po0 = pidx + 1, po1 = pidx + 1 + pp < nb_total ? pidx + 1 + pp : nb_total;
+                const double* eg = s_env - bq0;
+                double pre = 0.0, post = 0.0;
+                if (pre1 > pre0) pre = (0.0 + np_pairwise<double>([&](int i) { return eg[i]; }, (int)pre0, (int)(pre1 - pre0))) / (double)(pre1 - pre0);
+                if (po1 > po0) post = (0.0 + np_pairwise<double>([&](int i) { return eg[i]; }, (int)po0, (int)(po1 - po0))) / (double)(po1 - po0);
+                orat = d2f(log((post + p.eps64) / (pre + p.eps64)));
+                if (isnan(orat) || isinf(orat)) orat = 0.0f;
+                if (isnan(oc) || isinf(oc)) oc = 0.0f;
+            }
+            o.td[2 * o.nF + f0 + t] = oc;
+            o.td[3 * o.nF + f0 + t] = ow;
+            o.td[4 * o.nF + f0 + t] = orat;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4+K5+K8+K9: per-clip time recursions.  One CTA walks one clip at a time (clips are pulled from a
+// global counter); the time axis is processed in tiles of SEQ_TF frames held in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int SEQ_NT = 128;
+constexpr int SEQ_TF = 32;
+constexpr int SEQ_KMAX = 128;  // operating-band bins supported by this kernel (n_fft = 256 -> 71)
+inline size_t seq_smem_bytes(int K) { return sizeof(float) * (size_t)(3 * SEQ_TF + 2) * K; }
+
+struct SeqIO {
+    const float* P_band;   // [nF][K]
+    const float* td;       // [5][nF] (crest row 0, kurtosis row 1)
+    int8_t* frame_class; float* rain_conf; float* noise_conf;
+    int32_t* event_idx; int32_t* event_count;
+    float* det_noise_psd; float* det_noise_lag; float* D; float* noise_psd;
+    float* mode_flux; float* norm_flux; float* score; uint8_t* gate;
+    float* db_plane;       // [nF][K] noise-floor dB (scratch for the median select); may be null
+    double* db_sum;        // [n_clips]
+    int* clip_counter;     // dynamic clip scheduler
+    int64_t nF;
+};
+
+struct Tracker {
+    float trk, ts, nprev;
+};
+
+// one step of _update_noise_psd_frame for one bin (rain_signal_processor.py:594-666); t > 0
+__device__ __forceinline__ float tracker_step(const DevParams& p, Tracker& s, float pk, bool allow) {
+    const float err = pk - s.trk;
+    s.ts = p.trk_alpha * s.ts + p.trk_1m_alpha * fabsf(err);
+    const float step = p.trk_eta * f_max(s.ts, p.trk_floor);
+    const float delta = (pk >= s.trk) ? p.trk_q * step : p.trk_nq * step;
+    const float cand = f_max(s.trk + delta, 0.0f);
+    if (allow) s.trk = cand;
+    const float raw = s.trk;
+    const double lam = (raw > s.nprev) ? p.ema_up : p.ema_down;
+    double nb = lam * (double)s.nprev + (1.0 - lam) * (double)raw;
+    const double cap = (double)(p.trk_maxr * pk);
+    nb = cap < nb ? cap : nb;
+    nb = nb < 0.0 ? 0.0 : nb;
+    s.nprev = d2f(nb);
+    return s.nprev;
+}
+__device__ __forceinline__ float tracker_first(const DevParams& p, Tracker& s, float pk) {
+    s.trk = f_max(pk, 0.0f);
+    s.ts = f_max(fabsf(pk), p.trk_floor);
+    s.nprev = f_max(f_min(s.trk, p.trk_maxr * pk), 0.0f);
+    return s.nprev;
+}
+
+__global__ void __launch_bounds__(SEQ_NT) clip_seq_kernel(const __grid_constant__ DevParams p, Batch b, SeqIO io) {
+    // dynamic: s_P[2][SEQ_TF*K] power tiles (double buffer), s_D[(SEQ_TF+2)*K] dB rows (2 history rows)
+    extern __shared__ __align__(16) float seq_smem[];
+    float* const s_P0 = seq_smem;
+    float* const s_P1 = seq_smem + SEQ_TF * p.K;
+    float* const s_D = seq_smem + 2 * SEQ_TF * p.K;
+    __shared__ float s_mf[(APT_MAX_MODES + 1) * SEQ_TF];   // raw flux per mode, row M = weighted total
+    __shared__ float s_nf[(APT_MAX_MODES + 1) * SEQ_TF];   // normalised (row 0 = total score, 1.. = modes)
+    __shared__ uint8_t s_excl[SEQ_TF];
+    __shared__ float s_ltab[64];
+    __shared__ double s_red[SEQ_NT];
+    __shared__ int s_clip;
+
+    const int tid = threadIdx.x;
+    const int K = p.K, M = p.M;
+    if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_clip = atomicAdd(io.clip_counter, 1);
+        __syncthreads();
+        if (s_clip >= b.n_clips) break;
+        const int c = b.clip0 + s_clip;
+        const int64_t f0 = __ldg(b.frame_off + c);
+        const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
+        const float* Pg = io.P_band + f0 * K;
+        const int n_tiles = (T + SEQ_TF - 1) / SEQ_TF;
+
+        Tracker tr1 = {0, 0, 0}, tr2 = {0, 0, 0};
+        int warm2 = 0;
+        double bl_base = 0.0, bl_scale = 0.0;   // lanes 0..M
+        double dbsum = 0.0;
+        int rain_count = 0;                     // warp 0 lanes keep it uniform
+
+        // preload tile 0
+        for (int i = tid; i < min(SEQ_TF, T) * K; i += SEQ_NT) s_P0[i] = __ldg(Pg + i);
+        if (tid < K) { s_D[tid] = 0.0f; s_D[K + tid] = 0.0f; }
+        __syncthreads();
+
+        for (int tile = 0; tile < n_tiles; tile++) {
+            const int t0 = tile * SEQ_TF;
+            const int nt = min(SEQ_TF, T - t0);
+            const float* sP = (tile & 1) ? s_P1 : s_P0;
+            // prefetch the next tile into registers (stored to the other buffer at the end)
+            constexpr int PF = (SEQ_TF * SEQ_KMAX + SEQ_NT - 1) / SEQ_NT;
+            float pf[PF];
+            const int nnext = (tile + 1 < n_tiles) ? min(SEQ_TF, T - t0 - SEQ_TF) * K : 0;
+            {
+                const float* src = Pg + (int64_t)(t0 + SEQ_TF) * K;
+#pragma unroll
+                for (int r = 0; r < PF; r++) {
+                    const int i = tid + r * SEQ_NT;
+                    pf[r] = (i < nnext) ? __ldg(src + i) : 0.0f;
+                }
+            }
+
+            // ---- phase B: tracker pass 1 + detector normalisation (rain_signal_processor.py:862-888)
+            if (tid < K) {
+                const int k = tid;
+                for (int t = 0; t < nt; t++) {
+                    const float pk = sP[t * K + k];
+                    float dval;
+                    if (p.use_norm) {
+                        const float nlag_src = (t0 + t == 0) ? 0.0f : tr1.nprev;   // N1[t-1]
+                        const float n1 = (t0 + t == 0) ? tracker_first(p, tr1, pk) : tracker_step(p, tr1, pk, true);
+                        float nl = (t0 + t == 0) ? n1 : nlag_src;
+                        nl = f_min(nl, p.trk_maxr * pk);
+                        if (p.ratio_db)
+                            dval = 10.0f * svml_log10f(f_div(pk, nl + p.eps32) + p.eps32, s_ltab);
+                        else
+                            dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab) - 10.0f * svml_log10f(nl + p.eps32, s_ltab);
+                        const int64_t gi = (f0 + t0 + t) * K + k;
+                        if (io.det_noise_psd) io.det_noise_psd[gi] = n1;
+                        if (io.det_noise_lag) io.det_noise_lag[gi] = nl;
+                    } else {
+                        dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab);
+                    }
+                    s_D[(t + 2) * K + k] = dval;
+                    if (io.D) io.D[(f0 + t0 + t) * K + k] = dval;
+                }
+            }
+            __syncthreads();
+
+            // ---- phase C1: positive t-vs-(t-2) flux summed per mode (rain_frame_classifier.py:741-755)
+            for (int i = tid; i < nt * M; i += SEQ_NT) {
+                const int m = i / nt, t = i - m * nt;
+                float s = 0.0f;
+                if (t0 + t >= 2) {
+                    const int lo = p.mode_blo[m], n = p.mode_bhi[m] - lo + 1;
+                    const float* d2 = s_D + (t + 2) * K;
+                    const float* d0 = s_D + t * K;
+                    if (n > 0)
+                        s = 0.0f + np_pairwise<float>([&](int kk) { float d = d2[kk] - d0[kk]; return d > 0.0f ? d : (d != d ? d : 0.0f); }, lo, n);
+                }
+                s_mf[m * SEQ_TF + t] = s;
+            }
+            __syncthreads();
+            // ---- phase C2: weighted total in float64 (Python float accumulation, :752-759)
+            if (tid < nt) {
+                double tot = 0.0;
+                for (int m = 0; m < M; m++) tot += p.mode_w[m] * (double)s_mf[m * SEQ_TF + tid];
+                s_mf[M * SEQ_TF + tid] = (t0 + tid >= 2) ? d2f(tot) : 0.0f;
+            }
+            __syncthreads();
+            if (io.mode_flux)
+                for (int i = tid; i < nt * M; i += SEQ_NT) {
+                    const int m = i / nt, t = i - m * nt;
+                    io.mode_flux[(int64_t)m * io.nF + f0 + t0 + t] = s_mf[m * SEQ_TF + t];
+                }
+
+            // ---- phase D: causal stochastic low-quantile baselines in float64 (:31-82, :873-893)
+            if (tid <= M) {
+                const float* x = s_mf + ((tid == 0) ? M : tid - 1) * SEQ_TF;
+                const float ffloor = d2f(p.bl_floor);
+                for (int t = 0; t < nt; t++) {
+                    const double xt = (double)x[t];
+                    if (t0 + t == 0) {
+                        bl_base = xt > p.bl_floor ? xt : p.bl_floor;
+                        bl_scale = fabs(xt) > p.bl_floor ? fabs(xt) : p.bl_floor;
+                    }
+                    float ob = d2f(bl_base);
+                    if (isnan(ob) || isinf(ob)) ob = ffloor;
+                    ob = f_max(ob, ffloor);
+                    const double err = xt - bl_base;
+                    bl_scale = p.bl_alpha * bl_scale + (1.0 - p.bl_alpha) * fabs(err);
+                    const double step = p.bl_eta * (bl_scale > p.bl_floor ? bl_scale : p.bl_floor);
+                    const double delta = (xt >= bl_base) ? p.bl_q * step : -(1.0 - p.bl_q) * step;
+                    const double nb = bl_base + delta;
+                    bl_base = nb > p.bl_floor ? nb : p.bl_floor;
+                    const float ex = f_max(x[t] - ob, 0.0f);
+                    float sc = p.norm_enable ? f_div(ex, ob + p.norm_min) : ex;
+                    if (isnan(sc) || isinf(sc)) sc = 0.0f;
+                    s_nf[tid * SEQ_TF + t] = sc;
+                }
+            }
+            __syncthreads();
+            if (io.norm_flux)
+                for (int i = tid; i < nt * M; i += SEQ_NT) {
+                    const int m = i / nt, t = i - m * nt;
+                    io.norm_flux[(int64_t)m * io.nF + f0 + t0 + t] = s_nf[(m + 1) * SEQ_TF + t];
+                }
+
+            // ---- phase E: TD gate, fixed-band decision, labels, event compaction (warp 0: lane = frame)
+            if (tid < 32) {
+                const int t = tid;
+                bool is_rain = false;
+                if (t < nt) {
+                    const int64_t g = f0 + t0 + t;
+                    const float crest = __ldg(io.td + g);
+                    bool gate = crest > p.gate_thr;
+                    if (p.has_ku) gate = gate && (__ldg(io.td + io.nF + g) <= p.ku);
+                    const float gs = gate ? 1.0f : 0.0f;
+                    const float l0 = svml_log1pf(f_max(s_nf[1 * SEQ_TF + t] * gs, 0.0f));
+                    const float l1 = svml_log1pf(f_max(s_nf[2 * SEQ_TF + t] * gs, 0.0f));
+                    const float l2 = svml_log1pf(f_max(s_nf[3 * SEQ_TF + t] * gs, 0.0f));
+                    const float l3 = svml_log1pf(f_max(s_nf[4 * SEQ_TF + t] * gs, 0.0f));
+                    const int hits = (l1 >= p.thr1) + (l2 >= p.thr2) + (l3 >= p.thr3);
+                    is_rain = (l0 >= p.thr0) && (hits >= max(1, p.min_support));
+                    const float rc = is_rain ? 1.0f : 0.0f;
+                    float nc = 1.0f - rc;
+                    nc = nc < 0.0f ? 0.0f : (nc > 1.0f ? 1.0f : nc);
+                    const float score = s_nf[t];
+                    const bool weak = (score * gs) <= p.mf_noise_max;
+                    int8_t cls = 1;
+                    if (nc >= p.noise_hi && weak && !is_rain) cls = 0;
+                    if (is_rain) cls = 2;
+                    io.frame_class[g] = cls; io.rain_conf[g] = rc; io.noise_conf[g] = nc;
+                    if (io.score) io.score[g] = score;
+                    if (io.gate) io.gate[g] = gate ? 1 : 0;
+                    s_excl[t] = cls != 0;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, is_rain);
+                if (is_rain) io.event_idx[f0 + rain_count + __popc(m & ((1u << t) - 1u))] = t0 + t;
+                rain_count += __popc(m);
+            }
+            __syncthreads();
+
+            // ---- phase F: tracker pass 2 gated by the labels (:1006-1028) + noise-floor dB
+            if (tid < K && !p.suppressor_bypass) {
+                const int k = tid;
+                for (int t = 0; t < nt; t++) {
+                    const float pk = sP[t * K + k];
+                    const bool allow = (warm2 < p.warm_need) || !s_excl[t];
+                    const float n2 = (t0 + t == 0) ? tracker_first(p, tr2, pk) : tracker_step(p, tr2, pk, allow);
+                    if (allow) warm2++;
+                    const float db = 10.0f * svml_log10f(n2 + p.eps32, s_ltab);
+                    dbsum += (double)db;
+                    const int64_t gi = (f0 + t0 + t) * K + k;
+                    if (io.noise_psd) io.noise_psd[gi] = n2;
+                    if (io.db_plane) io.db_plane[gi] = db;
+                }
+            }
+            // publish the prefetched tile and roll the D history
+            {
+                float* dstP = ((tile + 1) & 1) ? s_P1 : s_P0;
+#pragma unroll
+                for (int r = 0; r < PF; r++) {
+                    const int i = tid + r * SEQ_NT;
+                    if (i < nnext) dstP[i] = pf[r];
+                }
+            }
+            __syncthreads();
+            if (tid < K) {
+                const float a = s_D[(nt) * K + tid], bb = s_D[(nt + 1) * K + tid];
+                s_D[tid] = a; s_D[K + tid] = bb;
+            }
+            __syncthreads();
+        }
+        // clip epilogue
+        s_red[tid] = (tid < K) ? dbsum : 0.0;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int k = 0; k < K; k++) s += s_red[k];
+            io.db_sum[c] = s;
+            io.event_count[c] = rain_count;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact median of the dB plane per clip: 3-level MSD radix select on order-preserving keys.
+// Two ranks are selected at once (lower / upper middle of an even count).
+// ---------------------------------------------------------------------------------------------
+constexpr int SEL_BINS = 2048;
+constexpr int SEL_CHUNK = 1024;  // frames per CTA
+struct SelState {
+    uint32_t prefix[2];
+    int64_t rank[2];
+};
+__device__ __forceinline__ uint32_t db_key(float v) {
+    const uint32_t u = f2u(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_db(uint32_t k) {
+    return u2f((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void select_init_kernel(Batch b, int K, SelState* st) {
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= b.n_clips) return;
+    const int c = b.clip0 + ci;
+    const int64_t n = (b.frame_off[c + 1] - b.frame_off[c]) * (int64_t)K;
+    st[c].prefix[0] = st[c].prefix[1] = 0;
+    st[c].rank[0] = (n - 1) / 2;
+    st[c].rank[1] = n / 2;
+}
+
+// level 0: bits 31..21, level 1: bits 20..10, level 2: bits 9..0
+__global__ void __launch_bounds__(128) select_hist_kernel(Batch b, int K, const float* __restrict__ db,
+                                                          const int64_t* __restrict__ chunk_off, int level,
+                                                          const SelState* __restrict__ st, uint32_t* __restrict__ hist) {
+    int64_t chunk_in_clip;
+    const int c = tile_clip(b, chunk_off, chunk_in_clip);
+    const int chunk = (int)chunk_in_clip;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int ta = chunk * SEL_CHUNK, tb = min(T, ta + SEL_CHUNK);
+    const int k = threadIdx.x;
+    if (k >= K) return;
+    const int sh = level == 0 ? 21 : (level == 1 ? 10 : 0);
+    const uint32_t mask = level == 2 ? 1023u : 2047u;
+    const uint32_t pre0 = st[c].prefix[0], pre1 = st[c].prefix[1];
+    const int shp = level == 0 ? 32 : (level == 1 ? 21 : 10);
+    uint32_t* h0 = hist + ((size_t)c * 2 + 0) * SEL_BINS;
+    uint32_t* h1 = hist + ((size_t)c * 2 + 1) * SEL_BINS;
+    int run_bin[2] = {-1, -1};
+    uint32_t run_cnt[2] = {0, 0};
+    const float* src = db + (f0 + ta) * K + k;
+    for (int t = ta; t < tb; t++, src += K) {
+        const uint32_t key = db_key(__ldg(src));
+        const uint32_t hi = (level == 0) ? 0u : (key >> shp);
+        const int bin = (int)((key >> sh) & mask);
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+            const uint32_t pre = w ? pre1 : pre0;
+            if (w == 1 && (level == 0 || pre1 == pre0)) continue;   // identical prefix: copy 0 serves both
+            if (level != 0 && hi != pre) continue;
+            if (bin == run_bin[w]) run_cnt[w]++;
+            else {
+                if (run_cnt[w]) atomicAdd((w ? h1 : h0) + run_bin[w], run_cnt[w]);
+                run_bin[w] = bin; run_cnt[w] = 1;
+            }
+        }
+    }
+    if (run_cnt[0]) atomicAdd(h0 + run_bin[0], run_cnt[0]);
+    if (run_cnt[1]) atomicAdd(h1 + run_bin[1], run_cnt[1]);
+}
+
+// one warp per clip: find the bins holding the two ranks, refine prefix/rank (histograms are cleared
+// by the host between levels)
+__device__ __forceinline__ int warp_find_rank(const uint32_t* __restrict__ h, int nb, int64_t rank, int64_t& before_out) {
+    const int lane = threadIdx.x & 31;
+    int64_t cum = 0;
+    int found = -1;
+    for (int base = 0; base < nb && found < 0; base += 32) {
+        const uint32_t v = h[base + lane];
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        const bool hit = (cum + (int64_t)inc) > rank;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            const int l = __ffs(m) - 1;
+            const uint32_t before = __shfl_sync(0xffffffffu, inc - v, l);
+            found = base + l;
+            cum += before;
+        } else {
+            cum += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    before_out = cum;
+    return found;
+}
+
+__global__ void select_scan_kernel(int clip0, int n_clips, int level, SelState* st, const uint32_t* __restrict__ hist) {
+    const int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (ci >= n_clips) return;
+    const int c = clip0 + ci;
+    const uint32_t pre0 = st[c].prefix[0], pre1 = st[c].prefix[1];
+    const int64_t r0 = st[c].rank[0], r1 = st[c].rank[1];
+    const bool shared01 = (level == 0) || (pre0 == pre1);
+    const int nb = level == 2 ? 1024 : 2048, bits = level == 2 ? 10 : 11;
+    const uint32_t* h0 = hist + ((size_t)c * 2 + 0) * SEL_BINS;
+    const uint32_t* h1 = hist + ((size_t)c * 2 + (shared01 ? 0 : 1)) * SEL_BINS;
+    int64_t b0, b1;
+    const int f0 = warp_find_rank(h0, nb, r0, b0);
+    const int f1 = warp_find_rank(h1, nb, r1, b1);
+    if (lane == 0) {
+        st[c].prefix[0] = (pre0 << bits) | (uint32_t)(f0 < 0 ? 0 : f0);
+        st[c].prefix[1] = (pre1 << bits) | (uint32_t)(f1 < 0 ? 0 : f1);
+        st[c].rank[0] = r0 - b0;
+        st[c].rank[1] = r1 - b1;
+    }
+}
+
+__global__ void finalize_kernel(const __grid_constant__ DevParams p, Batch b, const SelState* __restrict__ st,
+                                const double* __restrict__ db_sum, const int32_t* __restrict__ event_count,
+                                float* __restrict__ stats, int clip_id_base) {
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= b.n_clips) return;
+    const int c = b.clip0 + ci;
+    const int T = (int)(b.frame_off[c + 1] - b.frame_off[c]);
+    const int cnt = event_count[c];
+    const int minf = p.min_frames < 1 ? 1 : p.min_frames;
+    const double frac = T > 0 ? (double)cnt / (double)T : 0.0;
+    const double med_conf = cnt > 0 ? 1.0 : 0.0;
+    double ab = (double)cnt / (double)(2 * minf);
+    ab = ab < 0.0 ? 0.0 : (ab > 1.0 ? 1.0 : ab);
+    float* r = stats + (size_t)c * APT_N_CLIP_STATS;
+    r[0] = (float)(clip_id_base + c);
+    r[1] = (float)cnt;
+    r[2] = d2f(frac);
+    r[3] = cnt >= minf ? 1.0f : 0.0f;
+    r[4] = d2f(med_conf > ab ? med_conf : ab);
+    r[5] = d2f(med_conf);
+    if (p.suppressor_bypass || T == 0) {
+        // noise_psd is all zeros: every dB value is 10*log10(eps)
+        float lt[64];
+        for (int i = 0; i < 64; i++) lt[i] = u2f(kSvmlLog10TabDev[i]);
+        r[6] = r[7] = T > 0 ? 10.0f * svml_log10f(p.eps32, lt) : 0.0f;
+    } else {
+        r[6] = d2f(db_sum[c] / ((double)T * (double)p.K));
+        const float a = key_db(st[c].prefix[0]), bb = key_db(st[c].prefix[1]);
+        r[7] = f_div(a + bb, 2.0f);
+    }
+}
+
+}  // namespace apt

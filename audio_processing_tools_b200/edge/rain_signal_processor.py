@@ -1,0 +1,322 @@
+"""GPU-backed twins of the reference's spectral noise engine and its framework-facing processor.
+
+  * ``SpectralNoiseProcessor``  -- edge/rain_signal_processor.py:257-1198 (``setup`` / ``process``)
+  * ``RainDetectorProcessor``   -- edge/rain_signal_processor.py:1205-1344 (``run``), plus the additive
+                                   ``run_batch`` hook the batched orchestrator uses
+  * ``NoiseProcessorConfig`` / ``build_noise_config`` re-exported from ..config
+
+Every array is computed by the CUDA kernels behind include/apt_b200.h; this module only validates
+inputs, resolves parameters and packages results into the reference's dictionaries.
+"""
+from __future__ import annotations
+
+import json
+import time
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ..config import DetectorView, NoiseProcessorConfig, build_noise_config, validate_config
+from ..engine import BatchEngine
+from ..processors import BaseProcessor
+from .rain_frame_classifier import FrameClass
+
+RAW_SPECTRAL_FEATURE_NAMES = (
+    "raw_spectral_centroid_hz", "raw_spectral_bandwidth_hz", "raw_low_freq_ratio",
+    "raw_rain_band_ratio", "raw_mode_band_ratio_0", "raw_mode_band_ratio_1",
+    "raw_mode_band_ratio_2", "raw_mode_band_ratio_3", "raw_mode_band_ratio_4",
+    "raw_mode_band_entropy", "raw_mode_band_std", "raw_mode_band_max_ratio",
+    "raw_spectral_flatness", "raw_spectral_rolloff_hz", "raw_dominant_freq_hz",
+    "raw_frame_energy", "raw_cepstrum_coeff_0", "raw_cepstrum_coeff_1",
+    "raw_cepstrum_coeff_2", "raw_cepstrum_coeff_3", "raw_cepstrum_coeff_4")
+TD_FEATURE_ROWS = ("td_crest_factor", "td_kurtosis", "td_block_energy_crest",
+                   "td_block_peak_width_50", "td_block_post_pre_energy_ratio")
+
+__all__ = ["NoiseProcessorConfig", "build_noise_config", "SpectralNoiseProcessor",
+           "RainDetectorProcessor", "FrameClass"]
+
+
+class SpectralNoiseProcessor:
+    """STFT -> rain-frame detection -> noise-PSD estimation, on the GPU, for one or many clips."""
+
+    def __init__(self, config: Optional[NoiseProcessorConfig] = None, *, device: int = 0, fft_f64: bool = True):
+        self.cfg = config
+        self._device = device
+        self._fft_f64 = fft_f64
+        self._engine: Optional[BatchEngine] = None
+        self._engine_key = None
+        self._is_setup = config is not None
+        if self._is_setup:
+            validate_config(self.cfg)
+
+    def setup(self, params: Dict[str, Any]):
+        if self._is_setup:
+            return
+        sr = int(params.get("sample_rate", params.get("fs", 11162)))
+        self.cfg = build_noise_config(sample_rate=sr, params=params)
+        validate_config(self.cfg)
+        self._is_setup = True
+
+    # -- engine management -------------------------------------------------------------------
+    def _get_engine(self, sr: int, clip_rain_min_frames: int = 1) -> BatchEngine:
+        key = (int(sr), int(clip_rain_min_frames))
+        if self._engine is None or self._engine_key != key:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = BatchEngine(self.cfg, sr, device=self._device,
+                                       clip_rain_min_frames=clip_rain_min_frames, fft_f64=self._fft_f64)
+            self._engine_key = key
+        return self._engine
+
+    def __getstate__(self):  # engines own GPU resources: never pickled (ProcessPool boundary)
+        d = dict(self.__dict__)
+        d["_engine"] = None
+        d["_engine_key"] = None
+        return d
+
+    # -- main API ---------------------------------------------------------------------------
+    def process(self, x: np.ndarray, sr: Optional[int] = None) -> Dict[str, Any]:
+        return self.process_batch([x], sr=sr)[0]
+
+    def process_batch(self, clips: Sequence[np.ndarray], sr: Optional[int] = None,
+                      clip_rain_min_frames: int = 1, with_stats: bool = False) -> List[Dict[str, Any]]:
+        if self.cfg is None:
+            self.setup({"sample_rate": sr or 11162})
+        cfg = self.cfg
+        if sr is None:
+            sr = cfg.fs
+        if bool(cfg.compute_output_audio):
+            raise NotImplementedError("compute_output_audio=True (ISTFT of the suppressed spectrum) is not "
+                                      "implemented on the CUDA path")
+        dv = DetectorView(cfg)
+        keep_debug = bool(cfg.return_debug) or bool(cfg.debug_enable)
+        keep_det = bool(cfg.return_detector_debug) or bool(cfg.debug_enable)
+        keep_spectra = bool(cfg.return_spectra)
+        keep_noise = bool(cfg.return_noise_psd)
+        keep_filt = bool(cfg.return_filtered_audio)
+        want = []
+        if keep_debug:
+            want += ["det_noise_psd", "det_noise_lag", "noise_psd"]
+        if keep_noise and "noise_psd" not in want:
+            want.append("noise_psd")
+        if keep_det:
+            want += ["norm_flux", "score", "td", "gate"]
+            if dv.get("raw_spectral_shape_enable", True):
+                want.append("raw")
+        if keep_spectra:
+            want.append("S")
+        if keep_filt:
+            want.append("x_td")
+        arrays = []
+        for x in clips:
+            a = np.asarray(x)
+            arrays.append(a.reshape(-1) if a.dtype == np.int16 else np.asarray(a, dtype=np.float32).reshape(-1))
+        eng = self._get_engine(int(sr), clip_rain_min_frames)
+        plan, out = eng.run_clips(arrays, want)
+        rp = eng.rp
+        band = rp.band_mask
+        results = []
+        for c in range(plan.n_clips):
+            f0, f1 = int(plan.frame_off[c]), int(plan.frame_off[c + 1])
+            s0, s1 = int(plan.sample_off[c]), int(plan.sample_off[c + 1])
+            T = f1 - f0
+            times = np.asarray((np.arange(T) * int(cfg.hop)).astype(int) / float(sr), dtype=np.float32)
+            res: Dict[str, Any] = {
+                "frame_class": out["frame_class"][f0:f1].copy(),
+                "freqs": rp.freqs.copy(),
+                "times": times,
+                "rain_conf": out["rain_conf"][f0:f1].copy(),
+                "noise_conf": out["noise_conf"][f0:f1].copy(),
+            }
+            if keep_det:
+                res["det_debug"] = self._det_debug(out, f0, f1, rp, dv)
+            if keep_debug:
+                res["debug"] = self._debug(out, f0, f1, rp, dv, times)
+            if keep_filt:
+                xf = out["x_td"][s0:s1].copy()
+                res["x_filt"] = xf
+                res["y"] = xf if bool(cfg.classifier_only_mode) else None
+                if not bool(cfg.classifier_only_mode):
+                    res["y_suppressed"] = None
+            if keep_spectra:
+                S = np.asfortranarray(out["S"][f0:f1].view(np.complex64).reshape(T, rp.F).T)
+                res["S"] = S
+                res["S_hat"] = S if (bool(cfg.classifier_only_mode) or bool(cfg.suppressor_bypass)) else None
+            if keep_noise and not bool(cfg.classifier_only_mode):
+                res["noise_psd"] = self._embed(out["noise_psd"][f0:f1], rp)
+            if with_stats:
+                res["_clip_stats"] = out["clip_stats"][c].copy()
+                n = int(out["event_count"][c])
+                res["_event_idx"] = out["event_idx"][f0:f0 + n].copy()
+            results.append(res)
+        return results
+
+    @staticmethod
+    def _embed(plane_tk: np.ndarray, rp) -> np.ndarray:
+        """[T][K] band plane -> (F, T) float32 with exact zeros off-band (Fortran order like the reference)."""
+        T = plane_tk.shape[0]
+        full = np.zeros((rp.F, T), dtype=np.float32, order="F")
+        full[rp.c.band_lo:rp.c.band_hi + 1, :] = plane_tk.T
+        return full
+
+    def _det_debug(self, out, f0, f1, rp, dv) -> Dict[str, Any]:
+        nf = out["norm_flux"][:, f0:f1]
+        gate = out["gate"][f0:f1].astype(bool)
+        gs = gate.astype(np.float32)
+        score = out["score"][f0:f1].copy()
+        d: Dict[str, Any] = {
+            "mode_flux_score": score,
+            "mode_flux_score_gated": score * gs,
+            "primary_mode_flux": nf[0].copy(),
+            "support_mode_flux_1": nf[1].copy(),
+            "support_mode_flux_2": nf[2].copy(),
+            "support_mode_flux_3": nf[3].copy(),
+            "support_mode_flux_4": nf[4].copy() if nf.shape[0] > 4 else np.zeros_like(nf[0]),
+            "rain_conf": out["rain_conf"][f0:f1].copy(),
+            "noise_conf": out["noise_conf"][f0:f1].copy(),
+            "frame_class": out["frame_class"][f0:f1].copy(),
+            "td_gate_mask": gate,
+            "td_gate_threshold": float(dv.get("td_gate_threshold", 2.5)),
+            "td_kurtosis_upper_threshold": dv.get("td_kurtosis_upper_threshold", None),
+            "peak_features_enable": False,
+        }
+        for i in range(1, 4):
+            d[f"support_mode_flux_{i}_gated"] = d[f"support_mode_flux_{i}"] * gs
+        d["primary_mode_flux_gated"] = d["primary_mode_flux"] * gs
+        for i, name in enumerate(TD_FEATURE_ROWS):
+            d[name] = out["td"][i, f0:f1].copy()
+        if "raw" in out:
+            for i, name in enumerate(RAW_SPECTRAL_FEATURE_NAMES):
+                d[name] = out["raw"][i, f0:f1].copy()
+        return d
+
+    def _debug(self, out, f0, f1, rp, dv, times) -> Dict[str, Any]:
+        cfg = self.cfg
+        fc = out["frame_class"][f0:f1]
+        use = fc == FrameClass.NOISE
+        return {
+            "detector_params": dict(cfg.detector or {}),
+            "suppressor_params": dict(cfg.suppressor or {}),
+            "times_s": times,
+            "freqs": rp.freqs.copy(),
+            "detector_noise_psd": self._embed(out["det_noise_psd"][f0:f1], rp),
+            "detector_noise_psd_lag": self._embed(out["det_noise_lag"][f0:f1], rp),
+            "detector_use_noise_norm": bool(dv.get("detector_use_noise_norm", True)),
+            "detector_noise_norm_mode": str(cfg.detector_noise_norm_mode).lower(),
+            "suppressor_bypass": bool(cfg.suppressor_bypass),
+            "classifier_only_mode": bool(cfg.classifier_only_mode),
+            "use_for_noise_psd": use,
+            "is_rain_for_psd": ~use,
+            "noise_psd": self._embed(out["noise_psd"][f0:f1], rp),
+            "operating_band": (float(cfg.operating_band[0]), float(cfg.operating_band[1])),
+            "band_mask": rp.band_mask.copy(),
+            "pre_filter_mode": str(cfg.pre_filter_mode).lower(),
+            "noise_psd_max_ratio": float(cfg.noise_psd_max_ratio),
+        }
+
+
+class RainDetectorProcessor(BaseProcessor):
+    """Framework-facing processor for rain-frame detection (GPU).  ``run`` keeps the reference's
+    per-file contract; ``run_batch`` processes a whole batch of clips in one GPU pass."""
+
+    def __init__(self, name: str = "rain_detector", *, device: int = 0, fft_f64: bool = True):
+        self.name = name
+        self._device = device
+        self._fft_f64 = fft_f64
+        self._proc_cache: Dict[str, SpectralNoiseProcessor] = {}
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_proc_cache"] = {}
+        return d
+
+    def _params_cache_key(self, params: Dict[str, Any]) -> str:
+        try:
+            return json.dumps(params, sort_keys=True, default=str)
+        except Exception:
+            return repr(sorted(params.items(), key=lambda kv: kv[0]))
+
+    def _prepare(self, params: Dict[str, Any]):
+        p = dict(params)
+        keep_audio = bool(p.get("keep_state_audio", False))
+        keep_spectra = bool(p.get("keep_state_spectra", False))
+        keep_debug = bool(p.get("keep_state_debug", False))
+        p.setdefault("compute_output_audio", keep_audio)
+        p.setdefault("return_filtered_audio", keep_audio)
+        p.setdefault("return_spectra", keep_spectra)
+        p.setdefault("return_debug", keep_debug)
+        p.setdefault("return_detector_debug", keep_debug)
+        p.setdefault("return_noise_psd", keep_debug)
+        key = self._params_cache_key(p)
+        proc = self._proc_cache.get(key)
+        if proc is None:
+            proc = SpectralNoiseProcessor(device=self._device, fft_f64=self._fft_f64)
+            proc.setup(p)
+            self._proc_cache[key] = proc
+        return p, proc
+
+    def run(self, audio_data: np.ndarray, params: Dict[str, Any]) -> Tuple[Dict[str, Any], Dict[str, Any]]:
+        self._validate_audio(audio_data, params)
+        return self.run_batch([audio_data], params, _validated=True)[0]
+
+    def run_batch(self, audio_list: Sequence[np.ndarray], params: Dict[str, Any], _validated: bool = False
+                  ) -> List[Tuple[Dict[str, Any], Dict[str, Any]]]:
+        if not _validated:
+            for a in audio_list:
+                self._validate_audio(a, params)
+        p, proc = self._prepare(params)
+        cfg = proc.cfg
+        sr = int(p.get("sample_rate", 11162))
+        min_frames = max(1, int(p.get("clip_rain_min_frames", 1)))
+        t0 = time.perf_counter()
+        outs = proc.process_batch(audio_list, sr=sr, clip_rain_min_frames=min_frames, with_stats=True)
+        latency = (time.perf_counter() - t0) / max(1, len(audio_list))
+        keep_features = bool(p.get("keep_state_features", True))
+        results = []
+        for audio, out in zip(audio_list, outs):
+            stats = out.pop("_clip_stats")
+            out.pop("_event_idx")
+            fc = out["frame_class"]
+            count = int(stats[1])
+            frac = float(count / fc.size) if fc.size else 0.0
+            median_conf = float(stats[5])
+            metrics: Dict[str, Any] = {
+                "rain_frame_fraction": frac,
+                "clip_rain_fraction": frac,
+                "rain_frame_count": count,
+                "clip_is_rain": bool(stats[3] > 0.5),
+                "clip_rain_conf": float(stats[4]),
+                "median_rain_conf": median_conf,
+                "clip_rain_min_frames": min_frames,
+                "latency_s": latency,
+            }
+            if out.get("noise_psd") is not None:
+                metrics["mean_noise_floor_db"] = float(stats[6])
+                metrics["median_noise_floor_db"] = float(stats[7])
+            state: Dict[str, Any] = {
+                "frame_class": out["frame_class"], "times": out["times"],
+                "rain_conf": out["rain_conf"], "noise_conf": out["noise_conf"],
+                "rain_frame_count": count, "clip_rain_fraction": frac,
+                "clip_is_rain": metrics["clip_is_rain"], "clip_rain_conf": metrics["clip_rain_conf"],
+                "median_rain_conf": median_conf, "clip_rain_min_frames": min_frames,
+                "latency_s": latency, "processor": self.name,
+            }
+            if keep_features:
+                state["features"] = out.get("features")
+            if bool(p.get("keep_state_debug", False)):
+                for k in ("debug", "det_debug", "freqs", "noise_psd"):
+                    if k in out:
+                        state[k] = out[k]
+            if bool(p.get("keep_state_spectra", False)):
+                state["S"] = out.get("S")
+                state["S_hat"] = out.get("S_hat")
+            if bool(p.get("keep_state_audio", False)):
+                state["input_audio"] = audio
+                if "x_filt" in out:
+                    state["filtered_audio"] = out["x_filt"]
+                if "y" in out:
+                    state["output_audio"] = out["y"]
+            if bool(p.get("keep_state_config", False)):
+                state["config"] = cfg
+            results.append((metrics, state))
+        return results

@@ -1,0 +1,176 @@
+/*
+ * apt_b200.h -- C ABI of libapt_b200.so: the B200 (sm_100a) implementation of the
+ * audio_processing_tools hot path (framing/windowing -> STFT -> band powers -> noise-PSD tracking
+ * -> rain-frame detection -> clip statistics), batched over many clips.
+ *
+ * The boundary replaces ONE call of the reference:
+ *     results, state = proc.run(audio, proc_params)
+ *         audio_processing_tools/audio_processing_framework.py:190
+ * i.e. everything RainDetectorProcessor.run / SpectralNoiseProcessor.process compute
+ *         audio_processing_tools/edge/rain_signal_processor.py:1223-1344, :788-1198
+ * for a whole batch of clips at once.  The shape of the ABI follows the reference's own FFI
+ * precedent (edge/parameter_tuning/call_c_fun.py:20-58,193-236): POD structs passed by pointer,
+ * `int` status return, caller-owned buffers, no library-owned results.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; apt_last_error() describes the last error
+ *     of a context.  The library never aborts and never computes on the CPU instead of the GPU.
+ *   - one apt_ctx per GPU; a ctx and its plans are not thread-safe.
+ *   - apt_run_* enqueue work on the given CUDA stream (cudaStream_t as void*; NULL = default
+ *     stream) and return without synchronising.  All *device* buffers are caller-owned
+ *     (PyTorch tensors are used only as carriers of such buffers); the plan owns scratch only.
+ *   - per-frame arrays of all clips are concatenated; clip c owns frames
+ *     [frame_offsets[c], frame_offsets[c+1]) with T_c = 1 + len_c / hop  (librosa center=True,
+ *     rain_signal_processor.py:818-825).  Per-sample arrays are concatenated the same way
+ *     (sample_offsets).
+ */
+#ifndef APT_B200_H
+#define APT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APT_MAX_MODES 8
+#define APT_MAX_SOS 4
+#define APT_N_RAW_FEATURES 21 /* feature_extraction.py:9-31 RAW_SPECTRAL_FEATURE_NAMES */
+#define APT_N_TD_FEATURES 5   /* crest, kurtosis, block crest, block width50, block post/pre */
+#define APT_N_CLIP_STATS 8
+#define APT_ABI_VERSION 1
+
+typedef struct apt_ctx apt_ctx;
+typedef struct apt_plan apt_plan_t;
+
+/*
+ * Resolved configuration: the POD image of NoiseProcessorConfig + the detector dict
+ * (rain_signal_processor.py:19-188, rain_frame_classifier.py:314-459) after the host applied the
+ * reference's precedence rules (build_noise_config, :202-255; _dget, rain_frame_classifier.py:135-148)
+ * and the casts numpy applies to Python scalars (float32 where the reference multiplies float32
+ * arrays by Python floats).  Bin ranges are inclusive rfft bin indices; lo > hi means "empty".
+ */
+typedef struct apt_params_t {
+    int32_t abi_version;
+    int32_t fs, n_fft, hop;
+    int32_t band_lo, band_hi;                  /* operating band (rain_signal_processor.py:832-833) */
+    int32_t n_modes;                           /* >= 4 (rain_frame_classifier.py:379-383) */
+    int32_t mode_lo[APT_MAX_MODES], mode_hi[APT_MAX_MODES];            /* over all rfft bins */
+    int32_t mode_band_lo[APT_MAX_MODES], mode_band_hi[APT_MAX_MODES];  /* relative to band_lo */
+    double  mode_weight[APT_MAX_MODES];        /* 1.0 when mode_weights is None */
+    /* noise-PSD tracker, rain_signal_processor.py:555-666 */
+    float   trk_eta, trk_scale_alpha, trk_one_minus_alpha, trk_step_floor;
+    float   trk_q, trk_neg_one_minus_q, trk_maxr;
+    double  ema_up, ema_down;
+    int32_t warmup_need;
+    float   eps_f32;
+    int32_t detector_use_noise_norm;           /* rain_signal_processor.py:862 */
+    int32_t norm_ratio_db;                     /* :884 */
+    /* flux baseline, rain_frame_classifier.py:31-82 (Python doubles) */
+    double  bl_q, bl_eta, bl_scale_alpha, bl_floor;
+    int32_t norm_enable;
+    float   norm_min_f32;
+    /* decision, rain_frame_classifier.py:230-284, :914-998 */
+    float   thr_primary, thr_m1, thr_m2, thr_m3;
+    int32_t min_support;
+    float   td_gate_thr;
+    int32_t has_kurt_upper;
+    float   kurt_upper;
+    float   noise_hi, mode_flux_noise_max;
+    /* zero-phase TD prefilter (scipy butter SOS + sosfilt_zi), rain_frame_classifier.py:472-481 */
+    int32_t n_sos, padlen;
+    double  sos[APT_MAX_SOS][6];
+    double  zi[APT_MAX_SOS][2];
+    double  eps_f64;
+    /* TD block-energy features, feature_extraction.py:253-366 */
+    int32_t blk_len, blk_hop, blk_post_pre, blk_smooth;
+    /* raw spectral features, feature_extraction.py:542-747 */
+    int32_t low_lo, low_hi, rain_lo, rain_hi;
+    double  rolloff_fraction;
+    int32_t suppressor_bypass;
+    int32_t clip_rain_min_frames;              /* rain_signal_processor.py:1256-1257 */
+    /* arithmetic of the STFT: 1 = float64 FFT rounded to complex64 (the reference's arithmetic,
+       librosa/scipy.fft on float64), 0 = float32 FFT (faster, spectra within 1e-6 of frame max) */
+    int32_t fft_f64;
+    int32_t reserved0;
+    /* host pointers, copied at plan creation */
+    const double* window;                      /* n_fft analysis window (scipy get_window) */
+    const float*  freqs;                       /* n_fft/2+1 bin frequencies as float32 */
+} apt_params_t;
+
+/*
+ * Output buffers (device pointers, caller-owned; NULL = do not produce).
+ * nF = total frames of the batch, K = band_hi-band_lo+1, F = n_fft/2+1, M = n_modes.
+ */
+typedef struct apt_out_t {
+    /* always-required detector outputs */
+    int8_t*  frame_class;     /* [nF]  FrameClass NOISE=0 / UNCERTAIN=1 / RAIN=2 */
+    float*   rain_conf;       /* [nF] */
+    float*   noise_conf;      /* [nF] */
+    int32_t* event_idx;       /* [nF]  clip-local frame indices of RAIN frames, ascending, packed at
+                                        frame_offsets[c] .. + event_count[c] */
+    int32_t* event_count;     /* [n_clips] */
+    float*   clip_stats;      /* [n_clips][8]: clip id, rain_frame_count, clip_rain_fraction,
+                                 clip_is_rain, clip_rain_conf, median_rain_conf,
+                                 mean_noise_floor_db, median_noise_floor_db */
+    /* optional planes */
+    float*   S;               /* [nF][F][2] complex64 spectrum (state["S"]) */
+    float*   P;               /* [nF][F]    power */
+    float*   det_noise_psd;   /* [nF][K]    debug["detector_noise_psd"][band] */
+    float*   det_noise_lag;   /* [nF][K]    debug["detector_noise_psd_lag"][band] */
+    float*   D;               /* [nF][K]    detector input (dB above lagged noise) */
+    float*   noise_psd;       /* [nF][K]    state["noise_psd"][band] */
+    float*   mode_flux;       /* [M][nF]    raw per-mode flux */
+    float*   norm_flux;       /* [M][nF]    primary_mode_flux, support_mode_flux_1.. */
+    float*   score;           /* [nF]       mode_flux_score */
+    float*   td;              /* [5][nF]    TD features (zero-filled to T) */
+    float*   raw;             /* [21][nF]   raw spectral features */
+    float*   band_energy;     /* [M+1][nF]  mode-band powers + operating-band energy (float64 sums) */
+    uint8_t* gate;            /* [nF]       td_gate_mask */
+    float*   x_td;            /* [nS]       zero-phase prefiltered waveform */
+} apt_out_t;
+
+/* which stages a run executes */
+#define APT_STAGE_FEATURES 1  /* K1-K3: framing, STFT, power, band energies (BASELINE config 2) */
+#define APT_STAGE_FULL     2  /* K1-K9: + TD features, tracker, detection, clip statistics */
+
+int  apt_init(int device_ordinal, apt_ctx** out);
+void apt_destroy(apt_ctx* ctx);
+const char* apt_last_error(apt_ctx* ctx);
+int  apt_abi_version(void);
+int  apt_sizeof_params(void);
+int  apt_sizeof_out(void);
+
+/* Fills *p with the reference's defaults for fs=11162 except the fields that have no default
+   (mode bands, window, freqs, SOS): the host must set those.  */
+int  apt_params_default(apt_params_t* p);
+
+/* clip_len_samples: host array [n_clips].  The plan owns device scratch sized for the batch. */
+int  apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips,
+                     const int64_t* clip_len_samples, apt_plan_t** out);
+void apt_plan_destroy(apt_plan_t* plan);
+/* host copies of the prefix arrays, each [n_clips+1] */
+int  apt_plan_offsets(const apt_plan_t* plan, int64_t* sample_offsets, int64_t* frame_offsets);
+int64_t apt_plan_total_frames(const apt_plan_t* plan);
+int64_t apt_plan_total_samples(const apt_plan_t* plan);
+int64_t apt_plan_scratch_bytes(const apt_plan_t* plan);
+
+/* dev_pcm: concatenated clips on the device (int16 little-endian PCM as on the Mark-3 wire, or the
+   float32 waveform the reference's loader hands to processors). */
+int  apt_run_i16(apt_plan_t* plan, int stages, const int16_t* dev_pcm, const apt_out_t* out, void* cuda_stream);
+int  apt_run_f32(apt_plan_t* plan, int stages, const float* dev_pcm, const apt_out_t* out, void* cuda_stream);
+
+/* number of kernel launches the last apt_run_* call of this plan enqueued */
+int  apt_plan_last_launches(const apt_plan_t* plan);
+
+/* End-to-end convenience path with HOST buffers: copies PCM host->device in clip groups on a copy
+   stream while earlier groups compute, runs the full pipeline, and copies frame_class / rain_conf /
+   noise_conf / event_idx / event_count / clip_stats back to the given HOST buffers (any may be NULL).
+   Synchronises before returning.  Host buffers should be pinned for full PCIe bandwidth. */
+int  apt_run_host_i16(apt_plan_t* plan, const int16_t* host_pcm, int8_t* frame_class, float* rain_conf,
+                      float* noise_conf, int32_t* event_idx, int32_t* event_count, float* clip_stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APT_B200_H */

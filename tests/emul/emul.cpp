@@ -1,0 +1,30 @@
+// Host-side emulation of kernel math (tests only): compiles csrc/apt_math.cuh with g++ so the
+// lane-level functions the CUDA kernels call can be checked on a CPU-only box.
+#include "../../audio_processing_tools_b200/csrc/apt_math.cuh"
+#include <vector>
+using namespace apt;
+
+template <typename T>
+static void rfft256(const float* x, const double* win, double* out) {
+    std::vector<T> w(256);
+    std::vector<cx<T>> tw128(128), tw256(129), ex(kExSize);
+    for (int i = 0; i < 256; i++) w[i] = (T)win[i];
+    for (int m = 0; m < 128; m++) tw128[m] = {(T)cos(2.0 * M_PI * m / 128.0), (T)-sin(2.0 * M_PI * m / 128.0)};
+    for (int k = 0; k <= 128; k++) tw256[k] = {(T)cos(2.0 * M_PI * k / 256.0), (T)-sin(2.0 * M_PI * k / 256.0)};
+    auto ldx = [&](int n) { return x[n]; };
+    for (int j = 0; j < 8; j++) rfft256_passA<T>(j, ldx, w.data(), tw128.data(), ex.data());
+    for (int t = 0; t < 8; t++)
+        rfft256_passB<T>(t, ex.data(), tw256.data(), [&](int k, T re, T im) { out[2 * k] = (double)re; out[2 * k + 1] = (double)im; });
+}
+extern "C" {
+void emul_rfft256_f64(const float* x, const double* win, double* out) { rfft256<double>(x, win, out); }
+void emul_rfft256_f32(const float* x, const double* win, double* out) { rfft256<float>(x, win, out); }
+void emul_log10f(const float* x, float* y, long n) {
+    const float* tab = (const float*)kSvmlLog10TabHost.t;
+    for (long i = 0; i < n; i++) y[i] = svml_log10f(x[i], tab);
+}
+void emul_log1pf(const float* x, float* y, long n) { for (long i = 0; i < n; i++) y[i] = svml_log1pf(x[i]); }
+void emul_cabsf(const float* z, float* y, long n) { for (long i = 0; i < n; i++) y[i] = np_cabsf(z[2 * i], z[2 * i + 1]); }
+void emul_pcm(float* y) { for (int i = -32768; i < 32768; i++) y[i + 32768] = pcm_to_f32((int16_t)i); }
+float emul_pairwise_f32(const float* a, int n) { return 0.0f + np_pairwise<float>([&](int i) { return a[i]; }, 0, n); }
+}

@@ -1,0 +1,208 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors produced by the
+reference and against the CPU oracle on the same seeded inputs.
+
+Bars (north_star): frame classes, event indices and counts bit-exact; float planes within the
+stated tolerance (<= 1e-4 relative; spectra relative to the frame maximum).  With the default
+float64 FFT the integer outputs AND the float32 planes that feed decisions are expected to be
+bit-equal to the oracle; the asserted float tolerances are the ones written next to each check.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from audio_processing_tools_b200.synth import default_params, pcm_to_f32, synth_clip_i16
+
+pytestmark = pytest.mark.gpu
+
+ALL_PLANES = ("S", "P", "det_noise_psd", "det_noise_lag", "D", "noise_psd", "mode_flux", "norm_flux",
+              "score", "td", "raw", "band_energy", "gate", "x_td")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch
+
+
+def make_engine(params, **kw):
+    from audio_processing_tools_b200.config import build_noise_config
+    from audio_processing_tools_b200.engine import BatchEngine
+    cfg = build_noise_config(int(params.get("sample_rate", 11162)), params)
+    return BatchEngine(cfg, int(params.get("sample_rate", 11162)),
+                       clip_rain_min_frames=int(params.get("clip_rain_min_frames", 1)), **kw)
+
+
+def frame_rel_err(a, b):
+    """max |a-b| per frame relative to the frame's max |b| (spectra tolerance of SURVEY 7.2)."""
+    num = np.abs(a - b).reshape(a.shape[0], -1).max(axis=1)
+    den = np.abs(b).reshape(b.shape[0], -1).max(axis=1) + 1e-30
+    return float((num / den).max())
+
+
+@pytest.mark.parametrize("name", golden_names(min_level=2))
+def test_full_planes_match_reference_golden(torch_cuda, name):
+    g, meta, pcm, params = load_golden(name)
+    eng = make_engine(params)
+    plan, out = eng.run_clips([pcm], ALL_PLANES)
+    T = plan.nF
+    S = out["S"].view(np.complex64).reshape(T, -1)
+    # spectra: <= 1e-6 of the frame maximum (float64 FFT rounded to complex64; bit-equal in practice)
+    assert frame_rel_err(S, g["S"]) <= 1e-6
+    mism = int((S != g["S"]).sum())
+    assert mism <= max(2, S.size // 100000), f"{mism} complex64 bins differ from the reference"
+    # noise PSD planes: <= 1e-4 relative (bit-equal when S is)
+    np.testing.assert_allclose(out["det_noise_psd"], g["detector_noise_psd_band"], rtol=1e-4, atol=1e-12)
+    np.testing.assert_allclose(out["det_noise_lag"], g["detector_noise_psd_lag_band"], rtol=1e-4, atol=1e-12)
+    np.testing.assert_allclose(out["noise_psd"], g["noise_psd_band"], rtol=1e-4, atol=1e-12)
+    # labels / events: bit-exact
+    assert np.array_equal(out["frame_class"], g["frame_class"])
+    n = int(out["event_count"][0])
+    assert np.array_equal(out["event_idx"][:n], g["event_idx"])
+    assert np.array_equal(out["rain_conf"], g["rain_conf"])
+    assert np.array_equal(out["noise_conf"], g["noise_conf"])
+    # detector features: <= 1e-4 relative
+    for i, k in enumerate(("primary_mode_flux", "support_mode_flux_1", "support_mode_flux_2",
+                           "support_mode_flux_3", "support_mode_flux_4")):
+        np.testing.assert_allclose(out["norm_flux"][i], g["det_" + k], rtol=1e-4, atol=1e-5, err_msg=k)
+    np.testing.assert_allclose(out["score"], g["det_mode_flux_score"], rtol=1e-4, atol=1e-5)
+    assert np.array_equal(out["gate"].astype(bool), g["det_td_gate_mask"])
+    for i, k in enumerate(("td_crest_factor", "td_kurtosis", "td_block_energy_crest",
+                           "td_block_peak_width_50", "td_block_post_pre_energy_ratio")):
+        np.testing.assert_allclose(out["td"][i], g["det_" + k], rtol=1e-4, atol=1e-5, err_msg=k)
+    from audio_processing_tools_b200.edge.rain_signal_processor import RAW_SPECTRAL_FEATURE_NAMES
+    for i, k in enumerate(RAW_SPECTRAL_FEATURE_NAMES):
+        np.testing.assert_allclose(out["raw"][i], g["det_" + k], rtol=1e-4, atol=1e-6, err_msg=k)
+    st = out["clip_stats"][0]
+    assert int(st[1]) == int(g["metric_rain_frame_count"])
+    assert st[6] == pytest.approx(float(g["metric_mean_noise_floor_db"]), rel=1e-5)
+    assert st[7] == pytest.approx(float(g["metric_median_noise_floor_db"]), rel=1e-6)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n not in golden_names(min_level=2)])
+def test_events_match_reference_golden(torch_cuda, name):
+    """Through the reference-facing processor API (RainDetectorProcessor.run), int16-derived float32 input."""
+    from audio_processing_tools_b200.edge.rain_signal_processor import RainDetectorProcessor
+    g, meta, pcm, params = load_golden(name)
+    params["keep_state_debug"] = True
+    proc = RainDetectorProcessor()
+    m, s = proc.run(pcm_to_f32(pcm), params)
+    assert np.array_equal(s["frame_class"], g["frame_class"])
+    assert np.array_equal(np.flatnonzero(s["frame_class"] == 2).astype(np.int32), g["event_idx"])
+    assert np.array_equal(s["rain_conf"], g["rain_conf"])
+    assert np.array_equal(s["noise_conf"], g["noise_conf"])
+    assert np.array_equal(s["times"], g["times"])
+    for k in ("rain_frame_count", "clip_is_rain", "clip_rain_conf", "median_rain_conf",
+              "clip_rain_fraction", "clip_rain_min_frames"):
+        assert m[k] == g["metric_" + k].item(), k
+    assert m["mean_noise_floor_db"] == pytest.approx(float(g["metric_mean_noise_floor_db"]), rel=1e-5)
+    assert m["median_noise_floor_db"] == pytest.approx(float(g["metric_median_noise_floor_db"]), rel=1e-6)
+    if "det_primary_mode_flux" in g:
+        dd = s["det_debug"]
+        for k in ("primary_mode_flux", "support_mode_flux_1", "support_mode_flux_2", "support_mode_flux_3",
+                  "mode_flux_score", "td_crest_factor", "td_kurtosis", "td_block_energy_crest",
+                  "td_block_peak_width_50", "td_block_post_pre_energy_ratio"):
+            np.testing.assert_allclose(dd[k], g["det_" + k], rtol=1e-4, atol=1e-5, err_msg=k)
+        assert np.array_equal(dd["td_gate_mask"], g["det_td_gate_mask"])
+
+
+def test_ragged_batch_matches_oracle_i16(torch_cuda, oracle_mod):
+    """Ragged multi-clip batch, int16 wire input, every plane against the CPU oracle."""
+    specs = [(7.3, 201, 3.0), (5.0, 202, 0.0), (11.9, 203, 10.0), (6.02, 204, 0.5), (9.5, 205, 10.0)]
+    clips = [synth_clip_i16(s, seed, lam) for s, seed, lam in specs]
+    params = default_params(check_duration=5)
+    eng = make_engine(params)
+    plan, out = eng.run_clips(clips, ALL_PLANES)
+    flips = 0
+    for c, pcm in enumerate(clips):
+        p2 = dict(params, keep_state_debug=True)
+        m, s = oracle_mod.run(pcm_to_f32(pcm), p2)
+        f0, f1 = int(plan.frame_off[c]), int(plan.frame_off[c + 1])
+        s0, s1 = int(plan.sample_off[c]), int(plan.sample_off[c + 1])
+        T = f1 - f0
+        assert T == s["frame_class"].size
+        flips += int((out["frame_class"][f0:f1] != s["frame_class"]).sum())
+        n = int(out["event_count"][c])
+        assert np.array_equal(out["event_idx"][f0:f0 + n], s["event_idx"])
+        S = out["S"][f0:f1].view(np.complex64).reshape(T, -1)
+        assert frame_rel_err(S, s["S"]) <= 1e-6
+        np.testing.assert_allclose(out["P"][f0:f1][:, 10:81], s["P_band"], rtol=1e-4, atol=1e-12)
+        np.testing.assert_allclose(out["D"][f0:f1], s["D_band"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(out["det_noise_psd"][f0:f1], s["N1_band"], rtol=1e-4, atol=1e-12)
+        np.testing.assert_allclose(out["noise_psd"][f0:f1], s["N2_band"], rtol=1e-4, atol=1e-12)
+        np.testing.assert_allclose(out["mode_flux"][:, f0:f1], s["mode_flux"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(out["norm_flux"][:, f0:f1], s["norm_flux"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(out["x_td"][s0:s1], s["x_td"], rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(out["td"][:, f0:f1], s["td"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(out["raw"][:, f0:f1], s["raw"], rtol=1e-4, atol=1e-6)
+        st = out["clip_stats"][c]
+        assert int(st[1]) == m["rain_frame_count"]
+        assert st[6] == pytest.approx(m["mean_noise_floor_db"], rel=1e-5)
+        assert st[7] == pytest.approx(m["median_noise_floor_db"], rel=1e-6)
+    assert flips == 0, f"{flips} frame labels differ from the oracle"
+    eng.close()
+
+
+def test_f32_fft_mode_events(torch_cuda, oracle_mod):
+    """float32 FFT variant (north_star subsystem 2): spectra within 1e-6 of frame max, labels equal."""
+    clips = [synth_clip_i16(20, 300 + i, (0.0, 3.0, 10.0)[i]) for i in range(3)]
+    params = default_params(check_duration=20)
+    eng = make_engine(params, fft_f64=False)
+    plan, out = eng.run_clips(clips, ("S",))
+    flips = 0
+    for c, pcm in enumerate(clips):
+        m, s = oracle_mod.run(pcm_to_f32(pcm), dict(params, keep_state_debug=True))
+        f0, f1 = int(plan.frame_off[c]), int(plan.frame_off[c + 1])
+        S = out["S"][f0:f1].view(np.complex64).reshape(f1 - f0, -1)
+        assert frame_rel_err(S, s["S"]) <= 2e-6
+        flips += int((out["frame_class"][f0:f1] != s["frame_class"]).sum())
+    assert flips == 0
+    eng.close()
+
+
+def test_features_only_stage(torch_cuda, oracle_mod):
+    """BASELINE config 2 path: STFT + band energies only (no detector buffers needed)."""
+    pcm = synth_clip_i16(30, 400, 3.0)
+    params = default_params(check_duration=30)
+    eng = make_engine(params)
+    plan, out = eng.run_clips([pcm], ("band_energy", "P"), full=False)
+    s = oracle_mod.process(pcm_to_f32(pcm), dict(params))
+    P = out["P"]
+    np.testing.assert_allclose(P[:, 10:81], s["P_band"], rtol=1e-4, atol=1e-12)
+    be = out["band_energy"]
+    P64 = P.astype(np.float64)
+    for i, (lo, hi) in enumerate(((11, 14), (19, 24), (35, 41), (54, 58), (73, 76))):
+        np.testing.assert_allclose(be[i], P64[:, lo:hi + 1].sum(axis=1), rtol=1e-6)
+    np.testing.assert_allclose(be[5], P64[:, 10:81].sum(axis=1) + 1e-9, rtol=1e-6)
+    eng.close()
+
+
+def test_host_path_and_errors(torch_cuda):
+    """apt_run_host_i16 (e2e path) equals the device path; bad inputs fail loudly."""
+    from audio_processing_tools_b200.engine import AptError
+    from audio_processing_tools_b200.edge.rain_signal_processor import RainDetectorProcessor
+    clips = [synth_clip_i16(6 + i, 500 + i, 3.0) for i in range(10)]
+    params = default_params(check_duration=6)
+    eng = make_engine(params)
+    plan, out = eng.run_clips(clips, ())
+    cat = np.concatenate(clips)
+    host = {"frame_class": np.zeros(plan.nF, np.int8), "rain_conf": np.zeros(plan.nF, np.float32),
+            "noise_conf": np.zeros(plan.nF, np.float32), "event_idx": np.zeros(plan.nF, np.int32),
+            "event_count": np.zeros(plan.n_clips, np.int32), "clip_stats": np.zeros((plan.n_clips, 8), np.float32)}
+    eng.run_host_i16(plan, cat, host)
+    assert np.array_equal(host["frame_class"], out["frame_class"])
+    assert np.array_equal(host["event_count"], out["event_count"])
+    assert np.array_equal(host["clip_stats"], out["clip_stats"])
+    with pytest.raises(AptError):
+        eng.plan_for([100])          # shorter than one frame
+    eng.close()
+    proc = RainDetectorProcessor()
+    with pytest.raises(TypeError):
+        proc.run([0.0] * 1000, params)
+    with pytest.raises(ValueError):
+        proc.run(np.zeros(1000, np.float32), params)
+    with pytest.raises(AttributeError):
+        proc.run(np.zeros(6 * 11162, np.float32), {"sample_rate": 11162, "check_duration": 6})
+    with pytest.raises(NotImplementedError):
+        proc.run(np.zeros(6 * 11162, np.float32), dict(params, adaptive_q_enable=True))
