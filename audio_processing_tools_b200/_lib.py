@@ -17,6 +17,7 @@ CSRC = os.path.join(_PKG, "csrc")
 MAX_MODES, MAX_SOS, N_RAW, N_TD, N_STATS = 8, 4, 21, 5, 8
 ABI_VERSION = 1
 STAGE_FEATURES, STAGE_FULL = 1, 2
+KERNEL_NAMES = ("stft256_kernel", "td_features_kernel", "clip_seq_kernel", "select_kernels", "finalize_kernel")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
@@ -66,7 +67,7 @@ EXPORTS = ("apt_init", "apt_destroy", "apt_last_error", "apt_abi_version", "apt_
            "apt_sizeof_out", "apt_params_default", "apt_plan_create", "apt_plan_destroy",
            "apt_plan_offsets", "apt_plan_total_frames", "apt_plan_total_samples",
            "apt_plan_scratch_bytes", "apt_run_i16", "apt_run_f32", "apt_plan_last_launches",
-           "apt_run_host_i16")
+           "apt_run_host_i16", "apt_plan_enable_timing", "apt_plan_kernel_ms")
 
 
 def build(force=False, verbose=False):
@@ -112,6 +113,8 @@ def load():
     L.apt_run_i16.argtypes = [vp, C.c_int, vp, C.POINTER(AptOut), vp]
     L.apt_run_f32.argtypes = [vp, C.c_int, vp, C.POINTER(AptOut), vp]
     L.apt_run_host_i16.argtypes = [vp] * 8
+    L.apt_plan_enable_timing.argtypes = [vp, C.c_int]
+    L.apt_plan_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     if L.apt_abi_version() != ABI_VERSION:
         raise RuntimeError("libapt_b200.so ABI version mismatch")
     if L.apt_sizeof_params() != C.sizeof(AptParams) or L.apt_sizeof_out() != C.sizeof(AptOut):

@@ -76,6 +76,17 @@ struct apt_plan {
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_back = nullptr;
     int last_launches = 0;
     size_t scratch_bytes = 0;
+    // optional per-kernel timing (CUDA events on the launch stream)
+    bool timing = false;
+    std::vector<std::pair<int, cudaEvent_t>> marks;   // (kernel id, event recorded BEFORE that kernel); id -1 = end
+    float kernel_ms[APT_N_KERNELS] = {0};
+    void mark(int id, cudaStream_t st) {
+        if (!timing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks.emplace_back(id, e);
+    }
 };
 
 static void build_td_tables(const apt_params_t& prm, int ns, const double sos[][6], int chunk,
@@ -325,6 +336,30 @@ int64_t apt_plan_total_samples(const apt_plan_t* plan) { return plan ? plan->nS 
 int64_t apt_plan_scratch_bytes(const apt_plan_t* plan) { return plan ? (int64_t)plan->scratch_bytes : -1; }
 int apt_plan_last_launches(const apt_plan_t* plan) { return plan ? plan->last_launches : -1; }
 
+int apt_plan_enable_timing(apt_plan_t* plan, int enable) {
+    if (!plan) return -1;
+    plan->timing = enable != 0;
+    for (auto& m : plan->marks) cudaEventDestroy(m.second);
+    plan->marks.clear();
+    for (int i = 0; i < APT_N_KERNELS; i++) plan->kernel_ms[i] = 0.0f;
+    return 0;
+}
+
+int apt_plan_kernel_ms(apt_plan_t* plan, float* out_ms) {
+    if (!plan || !out_ms) return -1;
+    // caller has synchronised the stream; accumulate the intervals between consecutive marks
+    for (size_t i = 0; i + 1 < plan->marks.size(); i++) {
+        const int id = plan->marks[i].first;
+        if (id < 0) continue;
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, plan->marks[i].second, plan->marks[i + 1].second) == cudaSuccess) plan->kernel_ms[id] += ms;
+    }
+    for (auto& m : plan->marks) cudaEventDestroy(m.second);
+    plan->marks.clear();
+    for (int i = 0; i < APT_N_KERNELS; i++) { out_ms[i] = plan->kernel_ms[i]; plan->kernel_ms[i] = 0.0f; }
+    return 0;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
@@ -383,13 +418,15 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     StftOut so;
     so.S = out->S; so.P = out->P; so.P_band = full ? pl->d_Pband.p : nullptr; so.band_energy = out->band_energy;
     so.raw = out->raw; so.freqs = pl->d_freqs.p; so.nF = pl->nF;
+    pl->mark(APT_KERNEL_STFT, st);
     cudaError_t e = pl->prm.fft_f64 ? launch_stft<double, PCM>(pl, b, pcm, so, st) : launch_stft<float, PCM>(pl, b, pcm, so, st);
     if (e != cudaSuccess) return fail(ctx, -11, "stft launch failed: %s", cudaGetErrorString(e));
-    if (!full) return 0;
+    if (!full) { pl->mark(-1, st); return 0; }
 
     TdOut to;
     to.td = out->td ? out->td : pl->d_td.p; to.x_td = out->x_td; to.nF = pl->nF;
     to.want_block = out->td != nullptr; to.want_kurt = (out->td != nullptr) || d.has_ku;
+    pl->mark(APT_KERNEL_TD, st);
     e = launch_td<PCM>(pl, b, pcm, to, st);
     if (e != cudaSuccess) return fail(ctx, -11, "td launch failed: %s", cudaGetErrorString(e));
 
@@ -400,6 +437,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     io.det_noise_psd = out->det_noise_psd; io.det_noise_lag = out->det_noise_lag; io.D = out->D; io.noise_psd = out->noise_psd;
     io.mode_flux = out->mode_flux; io.norm_flux = out->norm_flux; io.score = out->score; io.gate = out->gate;
     io.db_plane = pl->d_db.p; io.db_sum = pl->d_dbsum.p; io.clip_counter = pl->d_counter.p + counter_slot; io.nF = pl->nF;
+    pl->mark(APT_KERNEL_SEQ, st);
     CUDA_OK(ctx, cudaMemsetAsync(io.clip_counter, 0, sizeof(int), st));
     int occ = 0;
     const size_t seq_smem = seq_smem_bytes(d.K);
@@ -412,6 +450,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     CUDA_OK(ctx, cudaGetLastError());
 
     // exact median of the dB plane
+    pl->mark(APT_KERNEL_SELECT, st);
     if (!d.suppressor_bypass) {
         select_init_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(b, d.K, pl->d_sel.p);
         pl->last_launches++;
@@ -425,9 +464,11 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         }
         CUDA_OK(ctx, cudaGetLastError());
     }
+    pl->mark(APT_KERNEL_FINALIZE, st);
     finalize_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(pl->dp, b, pl->d_sel.p, pl->d_dbsum.p, out->event_count, out->clip_stats, 0);
     pl->last_launches++;
     CUDA_OK(ctx, cudaGetLastError());
+    pl->mark(-1, st);
     return 0;
 }
 

@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (contract: prints ONE JSON line on rank 0).
+
+Workload (BASELINE.json configs[2], the N=1 point of the 1/2/4/8-GPU series the metric is quoted on):
+the full pipeline (STFT -> noise floor -> rain-event detection) on 1,000 x 10-min synthetic clips
+PER GPU (weak scaling: clips shard by file, no data-path collective; one NCCL all-gather of the
+per-clip statistics rows at the end of each step).  A "step" is one pass of the hot path over the
+whole batch.  `value` is device-timed with the int16 PCM already resident in HBM; `e2e` goes through
+the C ABI's host-buffer entry point with the PCIe copies inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--clips C] [--clip-seconds S]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+FS = 11162
+HOP = 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--clips", type=int, default=1000)
+    ap.add_argument("--clip-seconds", type=float, default=600.0)
+    ap.add_argument("--base-clips", type=int, default=16, help="distinct synthetic clips tiled to --clips")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--fft", default="f64", choices=("f64", "f32"))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def make_base_clips(n_base, seconds, seed0):
+    from audio_processing_tools_b200.synth import batch_clip_spec, synth_clip_i16
+    clips = []
+    for i in range(n_base):
+        seed, lam = batch_clip_spec(seed0 + i)
+        clips.append(synth_clip_i16(seconds, seed, lam))
+    return clips
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_baseline(params, seconds, n_threads, target_clips=None):
+    """Times the CPU oracle (C port of the reference's algorithm) on a bounded sample of the workload."""
+    from oracle import oracle
+    from audio_processing_tools_b200.synth import batch_clip_spec, synth_clip_i16
+    oracle.build()
+    n_clips = target_clips or max(2, min(2 * n_threads, 64))
+    distinct = [synth_clip_i16(seconds, *batch_clip_spec(900 + i)) for i in range(min(n_clips, 4))]
+    clips = [distinct[i % len(distinct)] for i in range(n_clips)]
+    t0 = time.perf_counter()
+    oracle.process_batch_i16(clips, params, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    return n_clips * seconds / dt, n_clips, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU arm (oracle port; the reference itself is Python and cannot travel)."""
+    if rank != 0:
+        return
+    from audio_processing_tools_b200.synth import default_params
+    params = default_params(check_duration=args.clip_seconds)
+    cores = os.cpu_count() or 1
+    n_clips = max(2, min(2 * cores, 64))
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_baseline(params, min(args.clip_seconds, 60.0), cores, target_clips=cores)
+    vals, times = [], []
+    for _ in range(max(1, args.steps)):
+        v, n, dt = cpu_baseline(params, args.clip_seconds, cores, target_clips=n_clips)
+        vals.append(v)
+        times.append(dt)
+    value = float(np.mean(vals))
+    sample = (f"{n_clips} x {args.clip_seconds:g}s clips per step (bounded sample of the {args.clips}-clip batch), "
+              f"full pipeline, C port of the reference algorithm (oracle/apt_oracle.c), {cores} threads; the "
+              f"reference's own Python runs ~13.7-15.9 audio-s/s per core (BASELINE.md)")
+    print(json.dumps({
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": f"full pipeline, {args.clips} x {args.clip_seconds:g}s synthetic clips per GPU "
+                               f"(BASELINE configs[2]); CPU arm runs a bounded sample per step"},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from audio_processing_tools_b200 import _lib
+    from audio_processing_tools_b200.config import build_noise_config
+    from audio_processing_tools_b200.engine import BatchEngine
+    from audio_processing_tools_b200.synth import default_params
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    params = default_params(check_duration=args.clip_seconds)
+    cfg = build_noise_config(FS, params)
+    eng = BatchEngine(cfg, FS, device=local_rank, fft_f64=(args.fft == "f64"))
+    N = int(FS * args.clip_seconds)
+    n_clips = args.clips
+    n_base = max(1, min(args.base_clips, n_clips))
+    base = make_base_clips(n_base, args.clip_seconds, seed0=rank * 100000)
+    plan = eng.plan_for([N] * n_clips)
+    T = 1 + N // HOP
+
+    # device-resident batch: base clips tiled to n_clips (13.4 GB int16 at the default size, >> L2)
+    base_dev = torch.from_numpy(np.stack(base)).to(dev)
+    reps = (n_clips + n_base - 1) // n_base
+    pcm_dev = base_dev.repeat(reps, 1)[:n_clips].contiguous().reshape(-1)
+    del base_dev
+    bufs = eng.alloc_outputs(plan, (), full=True)
+    gathered = torch.empty((world, n_clips, 8), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step():
+        eng.run_device(plan, pcm_dev, bufs, full=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, bufs["clip_stats"])
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    launches_per_step = eng.last_launches
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.L.apt_plan_enable_timing(plan.h, 1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    import ctypes as C
+    kms = (C.c_float * 5)()
+    eng.L.apt_plan_kernel_ms(plan.h, kms)
+    eng.L.apt_plan_enable_timing(plan.h, 0)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    clocks = sampler.summary()
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    audio_s = n_clips * args.clip_seconds * world
+    value = audio_s / (ms_step * 1e-3)
+
+    # rooflines: per kernel (device events inside the library) and for the whole pipeline
+    K = eng.rp.K
+    nF = plan.nF
+    bytes_algo = n_clips * (N * 2 + T * 9) + n_clips * 32                       # SURVEY 8(d) formula, int16 in
+    kernel_bytes = {   # algorithmic bytes each kernel must move in this decomposition
+        "stft256_kernel": plan.nS * 2 + nF * K * 4,
+        "td_features_kernel": plan.nS * 2 + nF * 4,
+        "clip_seq_kernel": nF * K * 4 + nF * 4 + nF * 9 + nF * K * 4,
+        "select_kernels": 3 * nF * K * 4,
+        "finalize_kernel": n_clips * 64,
+    }
+    kms_step = {name: float(kms[i]) / args.steps for i, name in enumerate(_lib.KERNEL_NAMES)}
+    dom = max(kms_step, key=lambda k: kms_step[k])
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    ach = kernel_bytes[dom] / (kms_step[dom] * 1e-3) / 1e9 if kms_step[dom] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms_per_step": kms_step,
+                "kernel_gbs": {k: (kernel_bytes[k] / (v * 1e-3) / 1e9 if v > 0 else None) for k, v in kms_step.items()},
+                "pipeline": {"bytes_algo": bytes_algo, "achieved_gbs": bytes_algo / (ms_step * 1e-3) / 1e9,
+                             "frac": bytes_algo / (ms_step * 1e-3) / 1e9 / peak},
+                "note": "the pipeline is issue-bound on fp32/fp64 pipes at n_fft=256 (SURVEY 8(d)); HBM fraction reported as required"}
+
+    result = {
+        "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64" if args.fft == "f64" else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"full pipeline (STFT -> noise floor -> rain events), {n_clips} x {args.clip_seconds:g}s "
+                               f"clips per GPU, fs=11162 n_fft=256 hop=128 (BASELINE configs[2]/[3])",
+                   "clips_per_gpu": n_clips, "clip_seconds": args.clip_seconds, "input": "int16 PCM",
+                   "fft": args.fft, "distinct_clips": n_base,
+                   "l2": "inputs (%.1f GB per step) are far larger than the 126 MB L2" % (plan.nS * 2 / 1e9),
+                   "collective": "all_gather of per-clip stats (32 B/clip)" if world > 1 else "none (1 GPU)"},
+        "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
+    }
+
+    if rank == 0 and not args.no_e2e:
+        # end to end: pinned host PCM -> C ABI host entry point -> results back in host memory
+        host = torch.empty(plan.nS, dtype=torch.int16, pin_memory=True)
+        hv = host.numpy().reshape(n_clips, N)
+        for i in range(n_clips):
+            hv[i] = base[i % n_base]
+        outs = {"frame_class": torch.empty(nF, dtype=torch.int8, pin_memory=True).numpy(),
+                "event_count": torch.empty(n_clips, dtype=torch.int32, pin_memory=True).numpy(),
+                "clip_stats": torch.empty((n_clips, 8), dtype=torch.float32, pin_memory=True).numpy(),
+                "rain_conf": None, "noise_conf": None, "event_idx": torch.empty(nF, dtype=torch.int32, pin_memory=True).numpy()}
+        del pcm_dev
+        torch.cuda.empty_cache()
+        eng.run_host_i16(plan, host.numpy(), outs)      # warm (allocates the staging buffers)
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            eng.run_host_i16(plan, host.numpy(), outs)
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        result["e2e"] = {"value": n_clips * args.clip_seconds / dt, "unit": "audio-s/s",
+                         "h2d_bytes_per_step": int(plan.nS * 2),
+                         "d2h_bytes_per_step": int(nF * (1 + 4) + n_clips * (4 + 32)),
+                         "ms_per_step": dt * 1e3, "n_gpus": 1,
+                         "note": "apt_run_host_i16: pinned host PCM, 8 clip groups pipelined H2D/compute/D2H"}
+    if rank == 0 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, n, dt = cpu_baseline(params, args.clip_seconds, cores)
+        result["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                  "sample": f"{n} x {args.clip_seconds:g}s clips, full pipeline, C port of the reference "
+                                            f"algorithm on {cores} threads ({dt:.1f}s wall); the reference's Python path "
+                                            f"runs ~13.7-15.9 audio-s/s per core (BASELINE.md)"}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(result))
+
+
+if __name__ == "__main__":
+    main()

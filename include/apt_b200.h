@@ -163,6 +163,18 @@ int  apt_run_f32(apt_plan_t* plan, int stages, const float* dev_pcm, const apt_o
 /* number of kernel launches the last apt_run_* call of this plan enqueued */
 int  apt_plan_last_launches(const apt_plan_t* plan);
 
+/* Optional per-kernel device timing for benchmarks: when enabled, apt_run_* records CUDA events on
+   the launch stream around each kernel group.  After synchronising the stream, apt_plan_kernel_ms
+   returns the accumulated milliseconds per group since the last call (and resets them). */
+#define APT_KERNEL_STFT 0      /* stft256_kernel */
+#define APT_KERNEL_TD 1        /* td_features_kernel */
+#define APT_KERNEL_SEQ 2       /* clip_seq_kernel */
+#define APT_KERNEL_SELECT 3    /* select_init/hist/scan (median) */
+#define APT_KERNEL_FINALIZE 4  /* finalize_kernel */
+#define APT_N_KERNELS 5
+int  apt_plan_enable_timing(apt_plan_t* plan, int enable);
+int  apt_plan_kernel_ms(apt_plan_t* plan, float* out_ms /* [APT_N_KERNELS] */);
+
 /* End-to-end convenience path with HOST buffers: copies PCM host->device in clip groups on a copy
    stream while earlier groups compute, runs the full pipeline, and copies frame_class / rain_conf /
    noise_conf / event_idx / event_count / clip_stats back to the given HOST buffers (any may be NULL).
