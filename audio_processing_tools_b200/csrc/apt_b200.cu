@@ -290,13 +290,24 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     {
         const int halo = (p->blk_post_pre + 2) * p->blk_hop + p->blk_len;
         const int lb = TD_FT * p->hop + p->n_fft + 2 * halo + 2 * TD_WARM + 2 * 64;
-        const int chunk = (lb + TD_NT - 1) / TD_NT;
+        int chunk = (lb + TD_NT - 1) / TD_NT;
+        chunk |= 1;   // odd stride: conflict-free 64-bit shared-memory walks
         std::vector<double> Apow, H;
         build_td_tables(*p, ns, sos, chunk, Apow, H);
         PL_OK(upload(pl->d_Apow, Apow)); PL_OK(upload(pl->d_H, H));
         pl->tdt.Apow = pl->d_Apow.p; pl->tdt.H = pl->d_H.p; pl->tdt.chunk = chunk; pl->tdt.lb_max = chunk * TD_NT; pl->tdt.halo = halo;
+        {   // scan rounds: stop once the transition matrix power is numerically zero
+            const int dim = 2 * ns;
+            int rounds = 8;
+            for (int k = 0; k < 8; k++) {
+                double mx = 0.0;
+                for (int i = 0; i < dim * dim; i++) mx = std::max(mx, fabs(Apow[(size_t)k * dim * dim + i]));
+                if (mx < 1e-20) { rounds = k; break; }
+            }
+            pl->tdt.rounds = rounds;
+        }
         const int env_cap = (TD_FT * p->hop + p->n_fft + 2 * halo) / std::max(1, p->blk_hop) + 4;
-        pl->td_smem = sizeof(double) * ((size_t)pl->tdt.lb_max + 2 * TD_NT * 2 * ns + env_cap) +
+        pl->td_smem = sizeof(double) * ((size_t)pl->tdt.lb_max + 2 * TD_NT * 2 * ns + env_cap + 8 * 4 * ns * ns + (size_t)chunk * 2 * ns) +
                       sizeof(float) * (size_t)(TD_FT * p->hop + p->n_fft + 2 * halo + 64);
     }
     // scratch
@@ -441,11 +452,13 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     CUDA_OK(ctx, cudaMemsetAsync(io.clip_counter, 0, sizeof(int), st));
     int occ = 0;
     const size_t seq_smem = seq_smem_bytes(d.K);
+    const int ntrk = seq_tracker_threads(d.K);
+    const int seq_nt = ntrk + SEQ_DET;
     CUDA_OK(ctx, cudaFuncSetAttribute(clip_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem));
-    CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clip_seq_kernel, SEQ_NT, seq_smem));
+    CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clip_seq_kernel, seq_nt, seq_smem));
     if (occ < 1) occ = 1;
-    const int grid = std::min(n_clips, ctx->sm_count * occ);
-    clip_seq_kernel<<<grid, SEQ_NT, seq_smem, st>>>(pl->dp, b, io);
+    const int grid = std::max(1, std::min((n_clips + SEQ_CPB - 1) / SEQ_CPB, ctx->sm_count * occ));
+    clip_seq_kernel<<<grid, seq_nt, seq_smem, st>>>(pl->dp, b, io, ntrk);
     pl->last_launches++;
     CUDA_OK(ctx, cudaGetLastError());
 

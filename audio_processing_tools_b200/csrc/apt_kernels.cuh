@@ -202,7 +202,10 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
     if (fr < nfr) {
         float* Pt = s_P + fr * STFT_PS;
         float* Sg = o.S ? o.S + ((f0 + t0 + fr) * (int64_t)p.F) * 2 : nullptr;
+        const bool need_full = o.S || o.P || o.raw || o.band_energy;
+        const int klo = need_full ? 0 : p.band_lo, khi = need_full ? p.F - 1 : p.band_lo + p.K - 1;
         rfft256_passB<T>(lane, ex, s_tw256, [&](int k, T re, T im) {
+            if (k < klo || k > khi) return;
             float sr = d2f((double)re), si = d2f((double)im);
             if (Sg) { Sg[2 * k] = sr; Sg[2 * k + 1] = si; }
             float a = np_cabsf(sr, si);
@@ -326,7 +329,8 @@ struct TdTables {
     // block-parallel IIR tables, computed at plan time for chunk length `chunk` (state dim = 2*n_sos):
     const double* Apow;  // [8][dim][dim]  A^(2^k), A = transition over one chunk
     const double* H;     // [chunk][dim]   output response at step n to a unit initial state
-    int chunk;           // samples per thread
+    int chunk;           // samples per thread (odd: conflict-free 64-bit shared accesses)
+    int rounds;          // scan rounds needed: max|A^(2^k)| is below 1e-20 for k >= rounds
     int lb_max;          // capacity of the float64 buffer (samples)
     int halo;            // extra valid samples each side of the frames (block features)
 };
@@ -355,7 +359,8 @@ __device__ __forceinline__ double sos_step(const double (&c)[NS][6], double (&z)
 // In-place block-parallel filtering of buf[0..len) (forward if !rev, else over reversed positions).
 // Thread i owns positions [i*chunk, (i+1)*chunk).  init: state entering position 0 (or nullptr = zero).
 template <int NS>
-__device__ void block_iir(const DevParams& p, const TdTables& tb, double* __restrict__ buf, int len, bool rev,
+__device__ void block_iir(const DevParams& p, const TdTables& tb, const double* __restrict__ s_A,
+                          const double* __restrict__ s_H, double* __restrict__ buf, int len, bool rev,
                           const double* init, double* __restrict__ s_state /*[TD_NT][2*NS] x2*/) {
     constexpr int DIM = 2 * NS;
     const int tid = threadIdx.x;
@@ -385,20 +390,20 @@ __device__ void block_iir(const DevParams& p, const TdTables& tb, double* __rest
     double* src = v0;
     double* dst = v1;
 #pragma unroll 1
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < tb.rounds; k++) {
         const int d = 1 << k;
         double acc[DIM];
 #pragma unroll
         for (int r = 0; r < DIM; r++) acc[r] = src[tid * DIM + r];
         if (tid >= d) {
-            const double* A = tb.Apow + k * DIM * DIM;
+            const double* A = s_A + k * DIM * DIM;
             double u[DIM];
 #pragma unroll
             for (int r = 0; r < DIM; r++) u[r] = src[(tid - d) * DIM + r];
 #pragma unroll
             for (int r = 0; r < DIM; r++)
 #pragma unroll
-                for (int q = 0; q < DIM; q++) acc[r] = d_fma(__ldg(A + r * DIM + q), u[q], acc[r]);
+                for (int q = 0; q < DIM; q++) acc[r] = d_fma(A[r * DIM + q], u[q], acc[r]);
         }
 #pragma unroll
         for (int r = 0; r < DIM; r++) dst[tid * DIM + r] = acc[r];
@@ -412,10 +417,10 @@ __device__ void block_iir(const DevParams& p, const TdTables& tb, double* __rest
         for (int r = 0; r < DIM; r++) sin_[r] = src[(tid - 1) * DIM + r];
         for (int i = a; i < e; i++) {
             const int pos = rev ? len - 1 - i : i;
-            const double* h = tb.H + (i - a) * DIM;
+            const double* h = s_H + (i - a) * DIM;
             double y = buf[pos];
 #pragma unroll
-            for (int r = 0; r < DIM; r++) y = d_fma(__ldg(h + r), sin_[r], y);
+            for (int r = 0; r < DIM; r++) y = d_fma(h[r], sin_[r], y);
             buf[pos] = y;
         }
     }
@@ -476,7 +481,9 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
     double* s_env = s_state + 2 * TD_NT * DIM;                      // block envelope (want_block)
     const int L = p.n_fft, hop = p.hop;
     const int env_cap = (TD_FT * hop + L + 2 * tb.halo) / max(1, p.blk_hop) + 4;
-    float* s_xf = reinterpret_cast<float*>(s_env + env_cap);        // valid x_td range as float32
+    double* s_A = s_env + env_cap;                                  // [8][DIM][DIM]
+    double* s_H = s_A + 8 * DIM * DIM;                              // [chunk][DIM]
+    float* s_xf = reinterpret_cast<float*>(s_H + tb.chunk * DIM);   // valid x_td range as float32
     __shared__ double s_init[TD_MAXDIM];
 
     const int tid = threadIdx.x;
@@ -501,6 +508,8 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
     const int len = (int)(be - bs);
     const bool exact_l = bs == -pad, exact_r = be == N + pad;
 
+    for (int i = tid; i < 8 * DIM * DIM; i += TD_NT) s_A[i] = __ldg(tb.Apow + i);
+    for (int i = tid; i < tb.chunk * DIM; i += TD_NT) s_H[i] = __ldg(tb.H + i);
     // stage the odd-extended signal in float64 (scipy odd_ext: 2*x[0]-x[i], 2*x[N-1]-x[N-1-i])
     for (int i = tid; i < len; i += TD_NT) {
         const int64_t s = bs + i;
@@ -514,10 +523,10 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
     if (NS > 0) {
         if (tid < DIM) s_init[tid] = p.zi[tid >> 1][tid & 1] * s_buf[0];
         __syncthreads();
-        block_iir<NS>(p, tb, s_buf, len, false, exact_l ? s_init : nullptr, s_state);
+        block_iir<NS>(p, tb, s_A, s_H, s_buf, len, false, exact_l ? s_init : nullptr, s_state);
         if (tid < DIM) s_init[tid] = p.zi[tid >> 1][tid & 1] * s_buf[len - 1];
         __syncthreads();
-        block_iir<NS>(p, tb, s_buf, len, true, exact_r ? s_init : nullptr, s_state);
+        block_iir<NS>(p, tb, s_A, s_H, s_buf, len, true, exact_r ? s_init : nullptr, s_state);
     }
     // float32 x_td over the valid range
     const int nv = (int)(ve - vs), voff = (int)(vs - bs);
@@ -653,13 +662,31 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4+K5+K8+K9: per-clip time recursions.  One CTA walks one clip at a time (clips are pulled from a
-// global counter); the time axis is processed in tiles of SEQ_TF frames held in shared memory.
+// K4+K5+K8+K9: per-clip time recursions, software-pipelined and warp-specialised.
+//
+// A CTA owns SEQ_CPB clip "slots".  Each slot walks its clips (pulled from a global counter) tile by
+// tile (SEQ_TF frames); consecutive tiles of a slot form a stream of items flowing through three
+// stages that run CONCURRENTLY inside one iteration (one __syncthreads per iteration):
+//   stage B (tracker lanes, item it)   : noise-PSD tracker pass 1 -> lagged dB normalisation -> positive
+//                                        t-vs-(t-2) flux per bin            (one lane per clip x bin)
+//   stage D (detector warps, item it-1): per-mode flux sums (numpy order) -> float64 quantile baselines
+//                                        -> TD gate -> fixed-band decision -> labels + event compaction
+//   stage F (tracker lanes, item it-2) : tracker pass 2 gated by the labels -> noise-floor dB plane
+// Stage B and F run in the same loop of the same lanes (two independent recursion chains per lane);
+// power tiles arrive through a 4-deep cp.async ring, one tile ahead.
 // ---------------------------------------------------------------------------------------------
-constexpr int SEQ_NT = 128;
-constexpr int SEQ_TF = 32;
-constexpr int SEQ_KMAX = 128;  // operating-band bins supported by this kernel (n_fft = 256 -> 71)
-inline size_t seq_smem_bytes(int K) { return sizeof(float) * (size_t)(3 * SEQ_TF + 2) * K; }
+constexpr int SEQ_CPB = 4;       // clip slots per CTA
+constexpr int SEQ_TF = 8;        // frames per tile
+constexpr int SEQ_DET = 32;      // detector group: one warp (SEQ_CPB * SEQ_TF lanes = (slot, frame))
+constexpr int SEQ_KMAX = 128;    // operating-band bins supported (n_fft = 256 -> 71)
+constexpr int SEQ_RING = 8;      // item descriptor ring
+
+struct SeqItem {
+    int clip, t0, nt, T;
+    long long f0;
+    int flags;       // 1 valid, 2 first tile of the clip, 4 last tile of the clip
+    int pad;
+};
 
 struct SeqIO {
     const float* P_band;   // [nF][K]
@@ -673,6 +700,12 @@ struct SeqIO {
     int* clip_counter;     // dynamic clip scheduler
     int64_t nF;
 };
+
+inline int seq_tracker_threads(int K) { return ((SEQ_CPB * K + 31) / 32) * 32; }
+inline size_t seq_smem_bytes(int K) {
+    // P ring [4][CPB][TF][K] + flux [2][CPB][TF][K] floats + dB partials [2][CPB][K] doubles
+    return sizeof(float) * (size_t)6 * SEQ_CPB * SEQ_TF * K + sizeof(double) * (size_t)2 * SEQ_CPB * K;
+}
 
 struct Tracker {
     float trk, ts, nprev;
@@ -702,168 +735,254 @@ __device__ __forceinline__ float tracker_first(const DevParams& p, Tracker& s, f
     return s.nprev;
 }
 
-__global__ void __launch_bounds__(SEQ_NT) clip_seq_kernel(const __grid_constant__ DevParams p, Batch b, SeqIO io) {
-    // dynamic: s_P[2][SEQ_TF*K] power tiles (double buffer), s_D[(SEQ_TF+2)*K] dB rows (2 history rows)
-    extern __shared__ __align__(16) float seq_smem[];
-    float* const s_P0 = seq_smem;
-    float* const s_P1 = seq_smem + SEQ_TF * p.K;
-    float* const s_D = seq_smem + 2 * SEQ_TF * p.K;
-    __shared__ float s_mf[(APT_MAX_MODES + 1) * SEQ_TF];   // raw flux per mode, row M = weighted total
-    __shared__ float s_nf[(APT_MAX_MODES + 1) * SEQ_TF];   // normalised (row 0 = total score, 1.. = modes)
-    __shared__ uint8_t s_excl[SEQ_TF];
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+static_assert(SEQ_CPB * SEQ_TF == SEQ_DET && SEQ_DET == 32, "detector group is exactly one warp");
+__device__ __forceinline__ void det_barrier() { __syncwarp(); }
+
+__global__ void __launch_bounds__(640) clip_seq_kernel(const __grid_constant__ DevParams p, Batch b, SeqIO io, int ntrk) {
+    extern __shared__ __align__(16) unsigned char seq_raw[];
+    const int K = p.K, M = p.M;
+    const int tileK = SEQ_TF * K;
+    double* s_dbl = reinterpret_cast<double*>(seq_raw);                         // [2][CPB][K]
+    float* s_Pring = reinterpret_cast<float*>(s_dbl + 2 * SEQ_CPB * K);         // [4][CPB][TF*K]
+    float* s_flux = s_Pring + 4 * SEQ_CPB * tileK;                              // [2][CPB][TF*K]
+    __shared__ SeqItem s_item[SEQ_CPB][SEQ_RING];
+    __shared__ float s_mf[SEQ_CPB][APT_MAX_MODES + 1][SEQ_TF];   // raw flux per mode, row M = weighted total
+    __shared__ float s_nf[SEQ_CPB][APT_MAX_MODES + 1][SEQ_TF];   // normalised: row 0 total score, 1.. modes
+    __shared__ uint8_t s_excl[2][SEQ_CPB][SEQ_TF];
+    __shared__ int s_dbl_clip[2][SEQ_CPB];
     __shared__ float s_ltab[64];
-    __shared__ double s_red[SEQ_NT];
-    __shared__ int s_clip;
 
     const int tid = threadIdx.x;
-    const int K = p.K, M = p.M;
+    const bool is_trk = tid < ntrk;
+    const int dt = tid - ntrk;                       // detector-group index
+    const int slot = is_trk ? tid / K : 0;
+    const int k = is_trk ? tid - slot * K : 0;
+    const bool trk_active = is_trk && slot < SEQ_CPB;
     if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
+    if (tid < 2 * SEQ_CPB) s_dbl_clip[tid / SEQ_CPB][tid % SEQ_CPB] = -1;
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_clip = atomicAdd(io.clip_counter, 1);
-        __syncthreads();
-        if (s_clip >= b.n_clips) break;
-        const int c = b.clip0 + s_clip;
-        const int64_t f0 = __ldg(b.frame_off + c);
-        const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
-        const float* Pg = io.P_band + f0 * K;
-        const int n_tiles = (T + SEQ_TF - 1) / SEQ_TF;
-
-        Tracker tr1 = {0, 0, 0}, tr2 = {0, 0, 0};
-        int warm2 = 0;
-        double bl_base = 0.0, bl_scale = 0.0;   // lanes 0..M
-        double dbsum = 0.0;
-        int rain_count = 0;                     // warp 0 lanes keep it uniform
-
-        // preload tile 0
-        for (int i = tid; i < min(SEQ_TF, T) * K; i += SEQ_NT) s_P0[i] = __ldg(Pg + i);
-        if (tid < K) { s_D[tid] = 0.0f; s_D[K + tid] = 0.0f; }
-        __syncthreads();
-
-        for (int tile = 0; tile < n_tiles; tile++) {
-            const int t0 = tile * SEQ_TF;
-            const int nt = min(SEQ_TF, T - t0);
-            const float* sP = (tile & 1) ? s_P1 : s_P0;
-            // prefetch the next tile into registers (stored to the other buffer at the end)
-            constexpr int PF = (SEQ_TF * SEQ_KMAX + SEQ_NT - 1) / SEQ_NT;
-            float pf[PF];
-            const int nnext = (tile + 1 < n_tiles) ? min(SEQ_TF, T - t0 - SEQ_TF) * K : 0;
-            {
-                const float* src = Pg + (int64_t)(t0 + SEQ_TF) * K;
-#pragma unroll
-                for (int r = 0; r < PF; r++) {
-                    const int i = tid + r * SEQ_NT;
-                    pf[r] = (i < nnext) ? __ldg(src + i) : 0.0f;
-                }
+    // ---- item generator state (detector threads dt < CPB, one per slot)
+    int g_clip = -1, g_T = 0, g_next = 0;
+    long long g_f0 = 0;
+    auto gen_item = [&](int s, int ring_idx) {
+        SeqItem itx;
+        itx.flags = 0; itx.clip = -1; itx.t0 = 0; itx.nt = 0; itx.T = 0; itx.f0 = 0; itx.pad = 0;
+        if (g_clip < 0 || g_next >= g_T) {
+            const int ci = atomicAdd(io.clip_counter, 1);
+            if (ci < b.n_clips) {
+                g_clip = b.clip0 + ci;
+                g_f0 = __ldg(b.frame_off + g_clip);
+                g_T = (int)(__ldg(b.frame_off + g_clip + 1) - g_f0);
+                g_next = 0;
+            } else {
+                g_clip = -1;
             }
+        }
+        if (g_clip >= 0) {
+            itx.clip = g_clip; itx.t0 = g_next; itx.T = g_T; itx.f0 = g_f0;
+            itx.nt = min(SEQ_TF, g_T - g_next);
+            itx.flags = 1 | (g_next == 0 ? 2 : 0) | (g_next + SEQ_TF >= g_T ? 4 : 0);
+            g_next += SEQ_TF;
+        }
+        s_item[s][ring_idx] = itx;
+    };
+    if (!is_trk && dt < SEQ_CPB) { gen_item(dt, 0); gen_item(dt, 1); }
+    __syncthreads();
+    if (trk_active) {
+        const SeqItem i0 = s_item[slot][0];
+        if (i0.flags & 1) {
+            const float* src = io.P_band + (i0.f0 + i0.t0) * K + k;
+            float* dst = s_Pring + (0 * SEQ_CPB + slot) * tileK + k;
+            for (int t = 0; t < i0.nt; t++) cp_async4(dst + t * K, src + (size_t)t * K);
+        }
+        cp_async_commit_wait_all();
+    }
+    __syncthreads();
 
-            // ---- phase B: tracker pass 1 + detector normalisation (rain_signal_processor.py:862-888)
-            if (tid < K) {
-                const int k = tid;
-                for (int t = 0; t < nt; t++) {
-                    const float pk = sP[t * K + k];
-                    float dval;
-                    if (p.use_norm) {
-                        const float nlag_src = (t0 + t == 0) ? 0.0f : tr1.nprev;   // N1[t-1]
-                        const float n1 = (t0 + t == 0) ? tracker_first(p, tr1, pk) : tracker_step(p, tr1, pk, true);
-                        float nl = (t0 + t == 0) ? n1 : nlag_src;
-                        nl = f_min(nl, p.trk_maxr * pk);
-                        if (p.ratio_db)
-                            dval = 10.0f * svml_log10f(f_div(pk, nl + p.eps32) + p.eps32, s_ltab);
-                        else
-                            dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab) - 10.0f * svml_log10f(nl + p.eps32, s_ltab);
-                        const int64_t gi = (f0 + t0 + t) * K + k;
-                        if (io.det_noise_psd) io.det_noise_psd[gi] = n1;
-                        if (io.det_noise_lag) io.det_noise_lag[gi] = nl;
-                    } else {
-                        dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab);
+    // ---- per-lane recursion state
+    Tracker tr1 = {0, 0, 0}, tr2 = {0, 0, 0};
+    float dm1 = 0.0f, dm2 = 0.0f;
+    int warm2 = 0;
+    double dbsum = 0.0;
+    double bl_base = 0.0, bl_scale = 0.0;   // detector warp 0 lanes: (slot, row)
+    int rain_count = 0;                     // detector E lanes
+
+    for (int it = 0;; it++) {
+        if (is_trk) {
+            if (trk_active) {
+                const SeqItem iB = s_item[slot][it & (SEQ_RING - 1)];
+                const SeqItem iN = s_item[slot][(it + 1) & (SEQ_RING - 1)];
+                SeqItem iF; iF.flags = 0;
+                if (it >= 2) iF = s_item[slot][(it - 2) & (SEQ_RING - 1)];
+                // prefetch the next item's power tile (one tile ahead)
+                if (iN.flags & 1) {
+                    const float* src = io.P_band + (iN.f0 + iN.t0) * K + k;
+                    float* dst = s_Pring + (((it + 1) & 3) * SEQ_CPB + slot) * tileK + k;
+                    for (int t = 0; t < iN.nt; t++) cp_async4(dst + t * K, src + (size_t)t * K);
+                }
+                const bool vB = iB.flags & 1, vF = iF.flags & 1;
+                const float* PB = s_Pring + ((it & 3) * SEQ_CPB + slot) * tileK + k;
+                const float* PF = s_Pring + (((it - 2) & 3) * SEQ_CPB + slot) * tileK + k;
+                float* FB = s_flux + ((it & 1) * SEQ_CPB + slot) * tileK + k;
+                const uint8_t* EX = s_excl[it & 1][slot];
+                const int ntB = vB ? iB.nt : 0, ntF = vF ? iF.nt : 0;
+                if (vF && (iF.flags & 2)) { warm2 = 0; dbsum = 0.0; }
+#pragma unroll 2
+                for (int t = 0; t < SEQ_TF; t++) {
+                    if (t < ntB) {
+                        // stage B: tracker pass 1 + detector normalisation (rain_signal_processor.py:862-888)
+                        const int tg = iB.t0 + t;
+                        const float pk = PB[t * K];
+                        float dval;
+                        if (p.use_norm) {
+                            const float nprev = tr1.nprev;   // N1[t-1]
+                            const float n1 = (tg == 0) ? tracker_first(p, tr1, pk) : tracker_step(p, tr1, pk, true);
+                            float nl = (tg == 0) ? n1 : nprev;
+                            nl = f_min(nl, p.trk_maxr * pk);
+                            if (p.ratio_db)
+                                dval = 10.0f * svml_log10f(f_div(pk, nl + p.eps32) + p.eps32, s_ltab);
+                            else
+                                dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab) - 10.0f * svml_log10f(nl + p.eps32, s_ltab);
+                            if (io.det_noise_psd) io.det_noise_psd[(iB.f0 + tg) * K + k] = n1;
+                            if (io.det_noise_lag) io.det_noise_lag[(iB.f0 + tg) * K + k] = nl;
+                        } else {
+                            dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab);
+                        }
+                        if (io.D) io.D[(iB.f0 + tg) * K + k] = dval;
+                        // positive t-vs-(t-2) flux, lane-local history (rain_frame_classifier.py:721-746)
+                        float fx = 0.0f;
+                        if (tg >= 2) { const float d = dval - dm2; fx = d > 0.0f ? d : (d != d ? d : 0.0f); }
+                        dm2 = dm1; dm1 = dval;
+                        FB[t * K] = fx;
                     }
-                    s_D[(t + 2) * K + k] = dval;
-                    if (io.D) io.D[(f0 + t0 + t) * K + k] = dval;
+                    if (t < ntF) {
+                        // stage F: tracker pass 2 gated by the labels (:1006-1028) + noise-floor dB
+                        const int tg = iF.t0 + t;
+                        const float pk = PF[t * K];
+                        const bool allow = (warm2 < p.warm_need) || !EX[t];
+                        const float n2 = (tg == 0) ? tracker_first(p, tr2, pk) : tracker_step(p, tr2, pk, allow);
+                        if (allow) warm2++;
+                        const float db = 10.0f * svml_log10f(n2 + p.eps32, s_ltab);
+                        dbsum += (double)db;
+                        const int64_t gi = (iF.f0 + tg) * K + k;
+                        if (io.noise_psd) io.noise_psd[gi] = n2;
+                        if (io.db_plane) io.db_plane[gi] = db;
+                    }
+                }
+                if (vF && (iF.flags & 4)) {
+                    s_dbl[((it & 1) * SEQ_CPB + slot) * K + k] = dbsum;
+                    if (k == 0) s_dbl_clip[it & 1][slot] = iF.clip;
                 }
             }
-            __syncthreads();
-
-            // ---- phase C1: positive t-vs-(t-2) flux summed per mode (rain_frame_classifier.py:741-755)
-            for (int i = tid; i < nt * M; i += SEQ_NT) {
-                const int m = i / nt, t = i - m * nt;
-                float s = 0.0f;
-                if (t0 + t >= 2) {
-                    const int lo = p.mode_blo[m], n = p.mode_bhi[m] - lo + 1;
-                    const float* d2 = s_D + (t + 2) * K;
-                    const float* d0 = s_D + t * K;
-                    if (n > 0)
-                        s = 0.0f + np_pairwise<float>([&](int kk) { float d = d2[kk] - d0[kk]; return d > 0.0f ? d : (d != d ? d : 0.0f); }, lo, n);
+            cp_async_commit_wait_all();
+        } else {
+            // ------------------------------ detector group ------------------------------
+            // fixed-order reduction of the per-bin dB sums published in the previous iteration
+            if (dt < SEQ_CPB && it >= 1) {
+                const int pb = (it - 1) & 1;
+                const int c = s_dbl_clip[pb][dt];
+                if (c >= 0) {
+                    double s = 0.0;
+                    const double* src = s_dbl + (pb * SEQ_CPB + dt) * K;
+                    for (int kk = 0; kk < K; kk++) s += src[kk];
+                    io.db_sum[c] = s;
+                    s_dbl_clip[pb][dt] = -1;
                 }
-                s_mf[m * SEQ_TF + t] = s;
             }
-            __syncthreads();
-            // ---- phase C2: weighted total in float64 (Python float accumulation, :752-759)
-            if (tid < nt) {
+            if (dt < SEQ_CPB) gen_item(dt, (it + 2) & (SEQ_RING - 1));
+            const int dslot = dt / SEQ_TF, dtt = dt % SEQ_TF;   // (slot, frame) mapping for C and E
+            SeqItem iD; iD.flags = 0;
+            if (it >= 1 && dslot < SEQ_CPB) iD = s_item[dslot][(it - 1) & (SEQ_RING - 1)];
+            const bool vD = (iD.flags & 1) && dslot < SEQ_CPB;
+            // TD features of this item's frames: issue the loads now, consume them in stage E
+            float crest_pf = 0.0f, kurt_pf = 0.0f;
+            if (vD && dtt < iD.nt) {
+                crest_pf = __ldg(io.td + iD.f0 + iD.t0 + dtt);
+                if (p.has_ku) kurt_pf = __ldg(io.td + io.nF + iD.f0 + iD.t0 + dtt);
+            }
+            // ---- C: per-mode sums of the flux row in numpy order + float64 weighted total (:749-759)
+            if (vD && dtt < iD.nt) {
+                const float* fr = s_flux + (((it - 1) & 1) * SEQ_CPB + dslot) * tileK + dtt * K;
+                const int tg = iD.t0 + dtt;
                 double tot = 0.0;
-                for (int m = 0; m < M; m++) tot += p.mode_w[m] * (double)s_mf[m * SEQ_TF + tid];
-                s_mf[M * SEQ_TF + tid] = (t0 + tid >= 2) ? d2f(tot) : 0.0f;
-            }
-            __syncthreads();
-            if (io.mode_flux)
-                for (int i = tid; i < nt * M; i += SEQ_NT) {
-                    const int m = i / nt, t = i - m * nt;
-                    io.mode_flux[(int64_t)m * io.nF + f0 + t0 + t] = s_mf[m * SEQ_TF + t];
-                }
-
-            // ---- phase D: causal stochastic low-quantile baselines in float64 (:31-82, :873-893)
-            if (tid <= M) {
-                const float* x = s_mf + ((tid == 0) ? M : tid - 1) * SEQ_TF;
-                const float ffloor = d2f(p.bl_floor);
-                for (int t = 0; t < nt; t++) {
-                    const double xt = (double)x[t];
-                    if (t0 + t == 0) {
-                        bl_base = xt > p.bl_floor ? xt : p.bl_floor;
-                        bl_scale = fabs(xt) > p.bl_floor ? fabs(xt) : p.bl_floor;
+                for (int m = 0; m < M; m++) {
+                    float s = 0.0f;
+                    const int lo = p.mode_blo[m], n = p.mode_bhi[m] - lo + 1;
+                    if (tg >= 2 && n > 0) {
+                        if (n < 8) {
+                            float r = -0.0f;
+                            for (int i = 0; i < n; i++) r += fr[lo + i];
+                            s = 0.0f + r;
+                        } else {
+                            s = 0.0f + np_pairwise<float>([&](int kk) { return fr[kk]; }, lo, n);
+                        }
                     }
-                    float ob = d2f(bl_base);
-                    if (isnan(ob) || isinf(ob)) ob = ffloor;
-                    ob = f_max(ob, ffloor);
-                    const double err = xt - bl_base;
-                    bl_scale = p.bl_alpha * bl_scale + (1.0 - p.bl_alpha) * fabs(err);
-                    const double step = p.bl_eta * (bl_scale > p.bl_floor ? bl_scale : p.bl_floor);
-                    const double delta = (xt >= bl_base) ? p.bl_q * step : -(1.0 - p.bl_q) * step;
-                    const double nb = bl_base + delta;
-                    bl_base = nb > p.bl_floor ? nb : p.bl_floor;
-                    const float ex = f_max(x[t] - ob, 0.0f);
-                    float sc = p.norm_enable ? f_div(ex, ob + p.norm_min) : ex;
-                    if (isnan(sc) || isinf(sc)) sc = 0.0f;
-                    s_nf[tid * SEQ_TF + t] = sc;
+                    s_mf[dslot][m][dtt] = s;
+                    tot += p.mode_w[m] * (double)s;
+                    if (io.mode_flux) io.mode_flux[(int64_t)m * io.nF + iD.f0 + tg] = s;
+                }
+                s_mf[dslot][M][dtt] = (tg >= 2) ? d2f(tot) : 0.0f;
+            }
+            det_barrier();
+            // ---- D: causal stochastic low-quantile baselines in float64 (:31-82, :873-893)
+            if (dt < SEQ_CPB * (M + 1)) {
+                const int bs = dt / (M + 1), row = dt - bs * (M + 1);
+                SeqItem jD; jD.flags = 0;
+                if (it >= 1) jD = s_item[bs][(it - 1) & (SEQ_RING - 1)];
+                if (jD.flags & 1) {
+                    const float* x = s_mf[bs][(row == 0) ? M : row - 1];
+                    const float ffloor = d2f(p.bl_floor);
+                    for (int t = 0; t < jD.nt; t++) {
+                        const double xt = (double)x[t];
+                        if (jD.t0 + t == 0) {
+                            bl_base = xt > p.bl_floor ? xt : p.bl_floor;
+                            bl_scale = fabs(xt) > p.bl_floor ? fabs(xt) : p.bl_floor;
+                        }
+                        float ob = d2f(bl_base);
+                        if (isnan(ob) || isinf(ob)) ob = ffloor;
+                        ob = f_max(ob, ffloor);
+                        const double err = xt - bl_base;
+                        bl_scale = p.bl_alpha * bl_scale + (1.0 - p.bl_alpha) * fabs(err);
+                        const double step = p.bl_eta * (bl_scale > p.bl_floor ? bl_scale : p.bl_floor);
+                        const double delta = (xt >= bl_base) ? p.bl_q * step : -(1.0 - p.bl_q) * step;
+                        const double nb = bl_base + delta;
+                        bl_base = nb > p.bl_floor ? nb : p.bl_floor;
+                        const float ex = f_max(x[t] - ob, 0.0f);
+                        float sc = p.norm_enable ? f_div(ex, ob + p.norm_min) : ex;
+                        if (isnan(sc) || isinf(sc)) sc = 0.0f;
+                        s_nf[bs][row][t] = sc;
+                        if (io.norm_flux && row > 0) io.norm_flux[(int64_t)(row - 1) * io.nF + jD.f0 + jD.t0 + t] = sc;
+                    }
                 }
             }
-            __syncthreads();
-            if (io.norm_flux)
-                for (int i = tid; i < nt * M; i += SEQ_NT) {
-                    const int m = i / nt, t = i - m * nt;
-                    io.norm_flux[(int64_t)m * io.nF + f0 + t0 + t] = s_nf[(m + 1) * SEQ_TF + t];
-                }
-
-            // ---- phase E: TD gate, fixed-band decision, labels, event compaction (warp 0: lane = frame)
-            if (tid < 32) {
-                const int t = tid;
+            det_barrier();
+            // ---- E: TD gate, fixed-band decision, labels, event compaction (16 lanes per slot)
+            if (dslot < SEQ_CPB) {
                 bool is_rain = false;
-                if (t < nt) {
-                    const int64_t g = f0 + t0 + t;
-                    const float crest = __ldg(io.td + g);
-                    bool gate = crest > p.gate_thr;
-                    if (p.has_ku) gate = gate && (__ldg(io.td + io.nF + g) <= p.ku);
+                if (vD && (iD.flags & 2)) rain_count = 0;
+                if (vD && dtt < iD.nt) {
+                    const int tg = iD.t0 + dtt;
+                    const int64_t g = iD.f0 + tg;
+                    bool gate = crest_pf > p.gate_thr;
+                    if (p.has_ku) gate = gate && (kurt_pf <= p.ku);
                     const float gs = gate ? 1.0f : 0.0f;
-                    const float l0 = svml_log1pf(f_max(s_nf[1 * SEQ_TF + t] * gs, 0.0f));
-                    const float l1 = svml_log1pf(f_max(s_nf[2 * SEQ_TF + t] * gs, 0.0f));
-                    const float l2 = svml_log1pf(f_max(s_nf[3 * SEQ_TF + t] * gs, 0.0f));
-                    const float l3 = svml_log1pf(f_max(s_nf[4 * SEQ_TF + t] * gs, 0.0f));
+                    const float l0 = svml_log1pf(f_max(s_nf[dslot][1][dtt] * gs, 0.0f));
+                    const float l1 = svml_log1pf(f_max(s_nf[dslot][2][dtt] * gs, 0.0f));
+                    const float l2 = svml_log1pf(f_max(s_nf[dslot][3][dtt] * gs, 0.0f));
+                    const float l3 = svml_log1pf(f_max(s_nf[dslot][4][dtt] * gs, 0.0f));
                     const int hits = (l1 >= p.thr1) + (l2 >= p.thr2) + (l3 >= p.thr3);
                     is_rain = (l0 >= p.thr0) && (hits >= max(1, p.min_support));
                     const float rc = is_rain ? 1.0f : 0.0f;
                     float nc = 1.0f - rc;
                     nc = nc < 0.0f ? 0.0f : (nc > 1.0f ? 1.0f : nc);
-                    const float score = s_nf[t];
+                    const float score = s_nf[dslot][0][dtt];
                     const bool weak = (score * gs) <= p.mf_noise_max;
                     int8_t cls = 1;
                     if (nc >= p.noise_hi && weak && !is_rain) cls = 0;
@@ -871,55 +990,38 @@ __global__ void __launch_bounds__(SEQ_NT) clip_seq_kernel(const __grid_constant_
                     io.frame_class[g] = cls; io.rain_conf[g] = rc; io.noise_conf[g] = nc;
                     if (io.score) io.score[g] = score;
                     if (io.gate) io.gate[g] = gate ? 1 : 0;
-                    s_excl[t] = cls != 0;
+                    s_excl[(it - 1) & 1][dslot][dtt] = cls != 0;
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, is_rain);
-                if (is_rain) io.event_idx[f0 + rain_count + __popc(m & ((1u << t) - 1u))] = t0 + t;
+                // the SEQ_TF lanes of a slot sit in one half-warp
+                const unsigned full = __ballot_sync(0xffffffffu, is_rain);
+                const int shift = ((tid & 31) / SEQ_TF) * SEQ_TF;
+                const unsigned m = (full >> shift) & ((1u << SEQ_TF) - 1u);
+                if (is_rain) io.event_idx[iD.f0 + rain_count + __popc(m & ((1u << dtt) - 1u))] = iD.t0 + dtt;
                 rain_count += __popc(m);
+                if (vD && (iD.flags & 4) && dtt == 0) io.event_count[iD.clip] = rain_count;
             }
-            __syncthreads();
-
-            // ---- phase F: tracker pass 2 gated by the labels (:1006-1028) + noise-floor dB
-            if (tid < K && !p.suppressor_bypass) {
-                const int k = tid;
-                for (int t = 0; t < nt; t++) {
-                    const float pk = sP[t * K + k];
-                    const bool allow = (warm2 < p.warm_need) || !s_excl[t];
-                    const float n2 = (t0 + t == 0) ? tracker_first(p, tr2, pk) : tracker_step(p, tr2, pk, allow);
-                    if (allow) warm2++;
-                    const float db = 10.0f * svml_log10f(n2 + p.eps32, s_ltab);
-                    dbsum += (double)db;
-                    const int64_t gi = (f0 + t0 + t) * K + k;
-                    if (io.noise_psd) io.noise_psd[gi] = n2;
-                    if (io.db_plane) io.db_plane[gi] = db;
-                }
-            }
-            // publish the prefetched tile and roll the D history
-            {
-                float* dstP = ((tile + 1) & 1) ? s_P1 : s_P0;
-#pragma unroll
-                for (int r = 0; r < PF; r++) {
-                    const int i = tid + r * SEQ_NT;
-                    if (i < nnext) dstP[i] = pf[r];
-                }
-            }
-            __syncthreads();
-            if (tid < K) {
-                const float a = s_D[(nt) * K + tid], bb = s_D[(nt + 1) * K + tid];
-                s_D[tid] = a; s_D[K + tid] = bb;
-            }
-            __syncthreads();
         }
-        // clip epilogue
-        s_red[tid] = (tid < K) ? dbsum : 0.0;
         __syncthreads();
-        if (tid == 0) {
-            double s = 0.0;
-            for (int k = 0; k < K; k++) s += s_red[k];
-            io.db_sum[c] = s;
-            io.event_count[c] = rain_count;
-        }
+        // stop when nothing is in flight: items it+1 (next B), it (next D), it-1 (next F) all invalid
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < SEQ_CPB; s++)
+            any = any || (s_item[s][(it + 1) & (SEQ_RING - 1)].flags & 1) || (s_item[s][it & (SEQ_RING - 1)].flags & 1) ||
+                  (it >= 1 && (s_item[s][(it - 1) & (SEQ_RING - 1)].flags & 1));
+        if (!any) break;
     }
+    // dB sums published in the very last iteration
+    __syncthreads();
+    if (!is_trk && dt < SEQ_CPB)
+        for (int pb = 0; pb < 2; pb++) {
+            const int c = s_dbl_clip[pb][dt];
+            if (c >= 0) {
+                double s = 0.0;
+                const double* src = s_dbl + (pb * SEQ_CPB + dt) * K;
+                for (int kk = 0; kk < K; kk++) s += src[kk];
+                io.db_sum[c] = s;
+            }
+        }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -971,8 +1073,16 @@ __global__ void __launch_bounds__(128) select_hist_kernel(Batch b, int K, const 
     int run_bin[2] = {-1, -1};
     uint32_t run_cnt[2] = {0, 0};
     const float* src = db + (f0 + ta) * K + k;
-    for (int t = ta; t < tb; t++, src += K) {
-        const uint32_t key = db_key(__ldg(src));
+    constexpr int U = 8;
+    float vbuf[U];
+    for (int tbase = ta; tbase < tb; tbase += U) {
+#pragma unroll
+      for (int u = 0; u < U; u++) vbuf[u] = (tbase + u < tb) ? __ldg(src + (size_t)u * K) : 0.0f;
+      src += (size_t)U * K;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (tbase + u >= tb) break;
+        const uint32_t key = db_key(vbuf[u]);
         const uint32_t hi = (level == 0) ? 0u : (key >> shp);
         const int bin = (int)((key >> sh) & mask);
 #pragma unroll
@@ -986,6 +1096,7 @@ __global__ void __launch_bounds__(128) select_hist_kernel(Batch b, int K, const 
                 run_bin[w] = bin; run_cnt[w] = 1;
             }
         }
+      }
     }
     if (run_cnt[0]) atomicAdd(h0 + run_bin[0], run_cnt[0]);
     if (run_cnt[1]) atomicAdd(h1 + run_bin[1], run_cnt[1]);
