@@ -87,6 +87,48 @@ __device__ __forceinline__ int tile_clip(const Batch& b, const int64_t* __restri
 __device__ __forceinline__ float load_sample(const int16_t* p, int64_t i) { return pcm_to_f32(__ldg(p + i)); }
 __device__ __forceinline__ float load_sample(const float* p, int64_t i) { return __ldg(p + i); }
 
+// Loads the n samples that start at absolute element index g (all inside the PCM buffer) and hands
+// them to put(i, value).  128-bit loads on 16-byte aligned addresses; every load of a thread is issued
+// before the first conversion so the misses overlap (MAXV = vectors per thread upper bound).
+template <int MAXV, typename PCM, typename Put>
+__device__ __forceinline__ void load_run(const PCM* __restrict__ pcm, int64_t g, int n, Put put) {
+    constexpr int VEC = 16 / (int)sizeof(PCM);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int head = (int)((VEC - (g % VEC)) % VEC);
+    if (head > n) head = n;
+    const int nvec = (n - head) / VEC;
+    const int tail0 = head + nvec * VEC;
+    int4 raw[MAXV];
+#pragma unroll
+    for (int r = 0; r < MAXV; r++) {
+        const int v = tid + r * nt;
+        if (v < nvec) raw[r] = __ldg(reinterpret_cast<const int4*>(pcm + g + head + (int64_t)v * VEC));
+    }
+    if (tid < head) put(tid, load_sample(pcm, g + tid));
+    if (tail0 + tid < n) put(tail0 + tid, load_sample(pcm, g + tail0 + tid));
+#pragma unroll
+    for (int r = 0; r < MAXV; r++) {
+        const int v = tid + r * nt;
+        if (v < nvec) {
+            const int i = head + v * VEC;
+            if constexpr (sizeof(PCM) == 2) {
+                const int16_t* h = reinterpret_cast<const int16_t*>(&raw[r]);
+#pragma unroll
+                for (int e = 0; e < 8; e++) put(i + e, pcm_to_f32(h[e]));
+            } else {
+                const float* f = reinterpret_cast<const float*>(&raw[r]);
+#pragma unroll
+                for (int e = 0; e < 4; e++) put(i + e, f[e]);
+            }
+        }
+    }
+    // vectors beyond MAXV per thread (never for the tile sizes in this file)
+    for (int v = tid + MAXV * nt; v < nvec; v += nt) {
+        const int i = head + v * VEC;
+        for (int e = 0; e < VEC; e++) put(i + e, load_sample(pcm, g + i + e));
+    }
+}
+
 // Stages samples [s0, s0+n) of a clip (clip-relative indices, zero outside [0, N)) into shared memory
 // as float32.  The body uses 128-bit global loads on 16-byte aligned addresses.
 template <typename PCM>
@@ -191,7 +233,14 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
     for (int i = tid; i < 256; i += STFT_NT) s_win[i] = tab.win[i];
     for (int i = tid; i < 128; i += STFT_NT) s_tw128[i] = tab.tw128[i];
     for (int i = tid; i < 129; i += STFT_NT) s_tw256[i] = tab.tw256[i];
-    stage_clip_f32(pcm, base, N, (int64_t)t0 * 128 - 128, (STFT_TF + 1) * 128, s_x);
+    {
+        const int64_t s0 = (int64_t)t0 * 128 - 128;
+        constexpr int NS_ = (STFT_TF + 1) * 128;
+        if (s0 >= 0 && s0 + NS_ <= N)
+            load_run<(NS_ * (int)sizeof(PCM) / 16 + STFT_NT - 1) / STFT_NT + 1>(pcm, base + s0, NS_, [&](int i, float v) { s_x[i] = v; });
+        else
+            stage_clip_f32(pcm, base, N, s0, NS_, s_x);
+    }
     __syncthreads();
 
     const int fr = tid >> 3, lane = tid & 7;
@@ -341,7 +390,15 @@ struct TdOut {
     int64_t nF;
     int want_kurt;   // compute kurtosis
     int want_block;  // compute block features
+#ifdef APT_PROFILE_PHASES
+    long long* dbg;  // [16] per-phase clock64 deltas of one interior tile (profiling builds only)
+#endif
 };
+#ifdef APT_PROFILE_PHASES
+#define APT_STAMP(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 777) o.dbg[i] = clock64(); } while (0)
+#else
+#define APT_STAMP(i) do { } while (0)
+#endif
 
 // one biquad cascade step (DF2T), float64, FMAs allowed (not bit-compared; 1e-16 level)
 template <int NS>
@@ -415,13 +472,14 @@ __device__ void block_iir(const DevParams& p, const TdTables& tb, const double* 
         double sin_[DIM];
 #pragma unroll
         for (int r = 0; r < DIM; r++) sin_[r] = src[(tid - 1) * DIM + r];
+#pragma unroll 4
         for (int i = a; i < e; i++) {
             const int pos = rev ? len - 1 - i : i;
             const double* h = s_H + (i - a) * DIM;
-            double y = buf[pos];
+            double acc = h[0] * sin_[0];
 #pragma unroll
-            for (int r = 0; r < DIM; r++) y = d_fma(h[r], sin_[r], y);
-            buf[pos] = y;
+            for (int r = 1; r < DIM; r++) acc = d_fma(h[r], sin_[r], acc);
+            buf[pos] += acc;
         }
     }
     __syncthreads();
@@ -508,9 +566,13 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
     const int len = (int)(be - bs);
     const bool exact_l = bs == -pad, exact_r = be == N + pad;
 
+    APT_STAMP(0);
     for (int i = tid; i < 8 * DIM * DIM; i += TD_NT) s_A[i] = __ldg(tb.Apow + i);
     for (int i = tid; i < tb.chunk * DIM; i += TD_NT) s_H[i] = __ldg(tb.H + i);
     // stage the odd-extended signal in float64 (scipy odd_ext: 2*x[0]-x[i], 2*x[N-1]-x[N-1-i])
+    if (bs >= 0 && be <= N) {
+        load_run<6>(pcm, base + bs, len, [&](int i, float v) { s_buf[i] = (double)v; });
+    } else
     for (int i = tid; i < len; i += TD_NT) {
         const int64_t s = bs + i;
         double v;
@@ -520,14 +582,17 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
         s_buf[i] = v;
     }
     __syncthreads();
+    APT_STAMP(1);
     if (NS > 0) {
         if (tid < DIM) s_init[tid] = p.zi[tid >> 1][tid & 1] * s_buf[0];
         __syncthreads();
         block_iir<NS>(p, tb, s_A, s_H, s_buf, len, false, exact_l ? s_init : nullptr, s_state);
+        APT_STAMP(2);
         if (tid < DIM) s_init[tid] = p.zi[tid >> 1][tid & 1] * s_buf[len - 1];
         __syncthreads();
         block_iir<NS>(p, tb, s_A, s_H, s_buf, len, true, exact_r ? s_init : nullptr, s_state);
     }
+    APT_STAMP(3);
     // float32 x_td over the valid range
     const int nv = (int)(ve - vs), voff = (int)(vs - bs);
     for (int i = tid; i < nv; i += TD_NT) s_xf[i] = d2f(s_buf[voff + i]);
@@ -539,6 +604,7 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
         for (int64_t s = w0 + tid; s < w1; s += TD_NT) o.x_td[base + s] = s_xf[s - vs];
     }
 
+    APT_STAMP(4);
     // crest factor / kurtosis: 8 lanes per frame, numpy float32 summation order
     const int grp = tid >> 3, lane = tid & 7;
     const unsigned gmask = 0xffu << ((tid & 31) & ~7);
@@ -577,6 +643,7 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
             kurt_o[t] = kv;
         }
     }
+    APT_STAMP(5);
     // frames beyond the TD grid are zero (rain_frame_classifier.py:178-194 zero-fill alignment)
     if (last)
         for (int t = max(Tloc, 0) + tid; t < T_clip; t += TD_NT) {
