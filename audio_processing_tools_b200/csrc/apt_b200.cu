@@ -65,8 +65,10 @@ struct apt_plan {
     int td_ns = 0;
     size_t td_smem = 0;
     // scratch
-    DevBuf<float> d_Pband, d_db, d_td;
-    DevBuf<double> d_dbsum;
+    DevBuf<float> d_Pband, d_db, d_td, d_mf;
+    DevBuf<double> d_dbsum;   // [n_clips][K] per-lane sums of the dB plane
+    Trk1Tab tab_modes, tab_all;   // pass-1 lane tables: mode bins only / every band bin (debug planes)
+    int mf_stride = 8;
     DevBuf<SelState> d_sel;
     DevBuf<uint32_t> d_hist;
     DevBuf<int> d_counter;
@@ -260,7 +262,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         pl->frame_off[c + 1] = pl->frame_off[c] + T;
         pl->stft_tile_off[c + 1] = pl->stft_tile_off[c] + (T + STFT_TF - 1) / STFT_TF;
         pl->td_tile_off[c + 1] = pl->td_tile_off[c] + std::max<int64_t>(1, (Tloc + TD_FT - 1) / TD_FT);
-        pl->sel_chunk_off[c + 1] = pl->sel_chunk_off[c] + (T + SEL_CHUNK - 1) / SEL_CHUNK;
+        pl->sel_chunk_off[c + 1] = pl->sel_chunk_off[c] + (T * K + SEL_CHUNK - 1) / SEL_CHUNK;
     }
     pl->nS = pl->samp_off[n_clips]; pl->nF = pl->frame_off[n_clips];
     if (pl->stft_tile_off[n_clips] > 0x7fffffffLL || pl->td_tile_off[n_clips] > 0x7fffffffLL) { delete pl; return fail(ctx, -29, "batch too large for one launch"); }
@@ -314,12 +316,32 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     PL_OK(pl->d_Pband.alloc((size_t)pl->nF * K));
     PL_OK(pl->d_db.alloc((size_t)pl->nF * K));
     PL_OK(pl->d_td.alloc((size_t)pl->nF * APT_N_TD_FEATURES));
-    PL_OK(pl->d_dbsum.alloc(n_clips));
+    PL_OK(pl->d_dbsum.alloc((size_t)n_clips * K));
+    pl->mf_stride = (p->n_modes + 1 <= 8) ? 8 : 16;
+    PL_OK(pl->d_mf.alloc((size_t)pl->nF * pl->mf_stride));
+    {   // pass-1 lane tables
+        Trk1Tab& tm = pl->tab_modes; Trk1Tab& ta = pl->tab_all;
+        memset(&tm, 0, sizeof(tm)); memset(&ta, 0, sizeof(ta));
+        int nl = 0;
+        for (int m = 0; m < p->n_modes; m++) {
+            const int lo = p->mode_band_lo[m], hi = p->mode_band_hi[m];
+            const int n = hi >= lo ? hi - lo + 1 : 0;
+            tm.mode_l0[m] = nl; tm.mode_n[m] = n;
+            ta.mode_l0[m] = n ? lo : 0; ta.mode_n[m] = n;
+            for (int i = 0; i < n; i++) {
+                if (nl >= SEQ_KMAX) { delete pl; return fail(ctx, -27, "mode bands cover more than %d bins", SEQ_KMAX); }
+                tm.lane_bin[nl++] = (unsigned char)(lo + i);
+            }
+        }
+        tm.n_lanes = nl;
+        ta.n_lanes = K;
+        for (int k = 0; k < K; k++) ta.lane_bin[k] = (unsigned char)k;
+    }
     PL_OK(pl->d_sel.alloc(n_clips));
     PL_OK(pl->d_hist.alloc((size_t)n_clips * 2 * SEL_BINS));
     PL_OK(pl->d_counter.alloc(64));
-    pl->scratch_bytes = sizeof(float) * ((size_t)pl->nF * K * 2 + (size_t)pl->nF * APT_N_TD_FEATURES) +
-                        (size_t)n_clips * (sizeof(double) + sizeof(SelState) + 2 * SEL_BINS * sizeof(uint32_t));
+    pl->scratch_bytes = sizeof(float) * ((size_t)pl->nF * K * 2 + (size_t)pl->nF * APT_N_TD_FEATURES + (size_t)pl->nF * pl->mf_stride) +
+                        (size_t)n_clips * (sizeof(double) * K + sizeof(SelState) + 2 * SEL_BINS * sizeof(uint32_t));
     PL_OK(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
     PL_OK(cudaStreamCreateWithFlags(&pl->s_comp, cudaStreamNonBlocking));
     PL_OK(cudaStreamCreateWithFlags(&pl->s_back, cudaStreamNonBlocking));
@@ -415,8 +437,7 @@ static cudaError_t launch_td(apt_plan* pl, const Batch& b, const PCM* pcm, const
 }
 
 template <typename PCM>
-static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM* pcm, const apt_out_t* out, cudaStream_t st,
-                     int counter_slot) {
+static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM* pcm, const apt_out_t* out, cudaStream_t st) {
     apt_ctx* ctx = pl->ctx;
     const DevParams& d = pl->dp;
     Batch b{clip0, n_clips, pl->d_samp_off.p, pl->d_frame_off.p};
@@ -441,39 +462,58 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     e = launch_td<PCM>(pl, b, pcm, to, st);
     if (e != cudaSuccess) return fail(ctx, -11, "td launch failed: %s", cudaGetErrorString(e));
 
-    SeqIO io;
-    io.P_band = pl->d_Pband.p; io.td = to.td;
-    io.frame_class = out->frame_class; io.rain_conf = out->rain_conf; io.noise_conf = out->noise_conf;
-    io.event_idx = out->event_idx; io.event_count = out->event_count;
-    io.det_noise_psd = out->det_noise_psd; io.det_noise_lag = out->det_noise_lag; io.D = out->D; io.noise_psd = out->noise_psd;
-    io.mode_flux = out->mode_flux; io.norm_flux = out->norm_flux; io.score = out->score; io.gate = out->gate;
-    io.db_plane = pl->d_db.p; io.db_sum = pl->d_dbsum.p; io.clip_counter = pl->d_counter.p + counter_slot; io.nF = pl->nF;
-    pl->mark(APT_KERNEL_SEQ, st);
-    CUDA_OK(ctx, cudaMemsetAsync(io.clip_counter, 0, sizeof(int), st));
-    int occ = 0;
-    const size_t seq_smem = seq_smem_bytes(d.K);
-    const int ntrk = seq_tracker_threads(d.K);
-    const int seq_nt = ntrk + SEQ_DET;
-    CUDA_OK(ctx, cudaFuncSetAttribute(clip_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem));
-    CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clip_seq_kernel, seq_nt, seq_smem));
-    if (occ < 1) occ = 1;
-    const int grid = std::max(1, std::min((n_clips + SEQ_CPB - 1) / SEQ_CPB, ctx->sm_count * occ));
-    clip_seq_kernel<<<grid, seq_nt, seq_smem, st>>>(pl->dp, b, io, ntrk);
-    pl->last_launches++;
-    CUDA_OK(ctx, cudaGetLastError());
-
-    // exact median of the dB plane
-    pl->mark(APT_KERNEL_SELECT, st);
-    if (!d.suppressor_bypass) {
-        select_init_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(b, d.K, pl->d_sel.p);
+    // tracker pass 1 on the mode bins (every band bin when one of its planes is requested)
+    pl->mark(APT_KERNEL_TRK1, st);
+    {
+        const bool dbg = out->det_noise_psd || out->det_noise_lag || out->D;
+        const Trk1Tab& tab = dbg ? pl->tab_all : pl->tab_modes;
+        Trk1IO io;
+        io.P_band = pl->d_Pband.p; io.mf = pl->d_mf.p; io.stride = pl->mf_stride;
+        io.det_noise_psd = out->det_noise_psd; io.det_noise_lag = out->det_noise_lag; io.D = out->D;
+        io.mode_flux = out->mode_flux; io.nF = pl->nF;
+        const int nt = std::max(32, ((tab.n_lanes + 31) / 32) * 32);
+        trk1_kernel<<<n_clips, nt, 0, st>>>(pl->dp, b, tab, io);
         pl->last_launches++;
+        CUDA_OK(ctx, cudaGetLastError());
+    }
+    // baselines, decision, labels, events
+    pl->mark(APT_KERNEL_DETECT, st);
+    {
+        DetIO io;
+        io.mf = pl->d_mf.p; io.stride = pl->mf_stride; io.td = to.td;
+        io.frame_class = out->frame_class; io.rain_conf = out->rain_conf; io.noise_conf = out->noise_conf;
+        io.event_idx = out->event_idx; io.event_count = out->event_count;
+        io.norm_flux = out->norm_flux; io.score = out->score; io.gate = out->gate; io.nF = pl->nF;
+        const int G = 32 / (d.M + 1);
+        const int warps = (n_clips + G - 1) / G;
+        detect_kernel<<<(warps + DET_WARPS - 1) / DET_WARPS, DET_WARPS * 32, 0, st>>>(pl->dp, b, io);
+        pl->last_launches++;
+        CUDA_OK(ctx, cudaGetLastError());
+    }
+    // tracker pass 2 + noise-floor dB plane + level-0 histogram, then the exact median
+    uint32_t* hist = pl->d_hist.p;
+    const size_t hist_bytes = sizeof(uint32_t) * (size_t)n_clips * 2 * SEL_BINS;
+    if (!d.suppressor_bypass) {
+        pl->mark(APT_KERNEL_TRK2, st);
+        CUDA_OK(ctx, cudaMemsetAsync(hist + (size_t)clip0 * 2 * SEL_BINS, 0, hist_bytes, st));
+        select_init_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(b, d.K, pl->d_sel.p);
+        Trk2IO io;
+        io.P_band = pl->d_Pband.p; io.frame_class = out->frame_class; io.noise_psd = out->noise_psd;
+        io.db_plane = pl->d_db.p; io.db_lane_sum = pl->d_dbsum.p; io.hist = hist; io.nF = pl->nF;
+        const int64_t lanes = (int64_t)n_clips * d.K;
+        trk2_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, io);
+        pl->last_launches += 2;
+        CUDA_OK(ctx, cudaGetLastError());
+        pl->mark(APT_KERNEL_SELECT, st);
         const int64_t chunks = pl->sel_chunk_off[clip0 + n_clips] - pl->sel_chunk_off[clip0];
-        uint32_t* hist = pl->d_hist.p;
         for (int level = 0; level < 3; level++) {
-            CUDA_OK(ctx, cudaMemsetAsync(hist + (size_t)clip0 * 2 * SEL_BINS, 0, sizeof(uint32_t) * (size_t)n_clips * 2 * SEL_BINS, st));
-            select_hist_kernel<<<(unsigned)chunks, 128, 0, st>>>(b, d.K, pl->d_db.p, pl->d_sel_chunk_off.p, level, pl->d_sel.p, hist);
+            if (level > 0) {
+                CUDA_OK(ctx, cudaMemsetAsync(hist + (size_t)clip0 * 2 * SEL_BINS, 0, hist_bytes, st));
+                select_hist_kernel<<<(unsigned)chunks, 256, 0, st>>>(b, d.K, pl->d_db.p, pl->d_sel_chunk_off.p, level, pl->d_sel.p, hist);
+                pl->last_launches++;
+            }
             select_scan_kernel<<<(n_clips * 32 + 127) / 128, 128, 0, st>>>(clip0, n_clips, level, pl->d_sel.p, hist);
-            pl->last_launches += 2;
+            pl->last_launches++;
         }
         CUDA_OK(ctx, cudaGetLastError());
     }
@@ -492,7 +532,7 @@ int apt_run_i16(apt_plan_t* plan, int stages, const int16_t* dev_pcm, const apt_
     if (!dev_pcm || !out) return fail(plan->ctx, -1, "apt_run_i16: null buffer");
     CUDA_OK(plan->ctx, cudaSetDevice(plan->ctx->device));
     plan->last_launches = 0;
-    return run_range<int16_t>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream, 0);
+    return run_range<int16_t>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream);
 }
 
 int apt_run_f32(apt_plan_t* plan, int stages, const float* dev_pcm, const apt_out_t* out, void* stream) {
@@ -500,7 +540,7 @@ int apt_run_f32(apt_plan_t* plan, int stages, const float* dev_pcm, const apt_ou
     if (!dev_pcm || !out) return fail(plan->ctx, -1, "apt_run_f32: null buffer");
     CUDA_OK(plan->ctx, cudaSetDevice(plan->ctx->device));
     plan->last_launches = 0;
-    return run_range<float>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream, 0);
+    return run_range<float>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream);
 }
 
 int apt_run_host_i16(apt_plan_t* pl, const int16_t* host_pcm, int8_t* frame_class, float* rain_conf, float* noise_conf,
@@ -534,7 +574,7 @@ int apt_run_host_i16(apt_plan_t* pl, const int16_t* host_pcm, int8_t* frame_clas
         cudaMemcpyAsync(pl->d_pcm.p + s0, host_pcm + s0, (size_t)(s1 - s0) * sizeof(int16_t), cudaMemcpyHostToDevice, pl->s_copy);
         cudaEventRecord(ev[g], pl->s_copy);
         cudaStreamWaitEvent(pl->s_comp, ev[g], 0);
-        rc = run_range<int16_t>(pl, APT_STAGE_FULL, c0, c1 - c0, pl->d_pcm.p, &o, pl->s_comp, g);
+        rc = run_range<int16_t>(pl, APT_STAGE_FULL, c0, c1 - c0, pl->d_pcm.p, &o, pl->s_comp);
         if (rc != 0) break;
         cudaEventRecord(done[g], pl->s_comp);
         cudaStreamWaitEvent(pl->s_back, done[g], 0);

@@ -3,8 +3,9 @@
 // Kernel map (DESIGN.md has the data layout and rooflines):
 //   stft256_kernel      K1+K2+K3  PCM -> frames -> Hann -> rFFT-256 -> power -> band planes
 //   td_features_kernel  K6+K7     PCM -> zero-phase SOS prefilter -> crest / kurtosis / block features
-//   clip_seq_kernel     K4+K5+K8+K9  per-clip time recursions: tracker pass 1, dB normalisation, flux,
-//                                 baselines, decision, labels, event compaction, tracker pass 2, dB stats
+//   trk1_kernel         K4+K5     tracker pass 1 on the mode bins, dB normalisation, flux, per-mode sums
+//   detect_kernel       K8+K9     float64 baselines, decision, labels, event compaction
+//   trk2_kernel         K4+K9     tracker pass 2 gated by the labels, noise-floor dB plane + sums
 //   select_*            K9        exact median of the noise-floor dB plane (3-level radix select)
 //   finalize_kernel     K9        clip statistics rows
 //
@@ -729,50 +730,22 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4+K5+K8+K9: per-clip time recursions, software-pipelined and warp-specialised.
+// K4+K5+K8+K9: the per-clip time recursions as three independent streaming kernels.
 //
-// A CTA owns SEQ_CPB clip "slots".  Each slot walks its clips (pulled from a global counter) tile by
-// tile (SEQ_TF frames); consecutive tiles of a slot form a stream of items flowing through three
-// stages that run CONCURRENTLY inside one iteration (one __syncthreads per iteration):
-//   stage B (tracker lanes, item it)   : noise-PSD tracker pass 1 -> lagged dB normalisation -> positive
-//                                        t-vs-(t-2) flux per bin            (one lane per clip x bin)
-//   stage D (detector warps, item it-1): per-mode flux sums (numpy order) -> float64 quantile baselines
-//                                        -> TD gate -> fixed-band decision -> labels + event compaction
-//   stage F (tracker lanes, item it-2) : tracker pass 2 gated by the labels -> noise-floor dB plane
-// Stage B and F run in the same loop of the same lanes (two independent recursion chains per lane);
-// power tiles arrive through a 4-deep cp.async ring, one tile ahead.
+// The recursions are sequential in time but independent across (clip, bin) / (clip, row) lanes,
+// so each is its own kernel whose warps never wait on one another (no CTA-wide barriers on the
+// recurrence path); the planes between them travel through HBM/L2, which this pipeline barely
+// uses (issue-bound, not bandwidth-bound):
+//   trk1_kernel    lane = (clip, mode bin): noise-PSD tracker pass 1 -> lagged dB normalisation ->
+//                  positive t-vs-(t-2) flux -> per-mode sums in numpy order  => mf[nF][stride]
+//   detect_kernel  lane = (clip, row): float64 quantile baselines -> normalised flux -> TD gate ->
+//                  fixed-band decision (one ballot) -> labels, confidences, event compaction
+//   trk2_kernel    lane = (clip, bin): tracker pass 2 gated by the labels -> noise-floor dB plane,
+//                  per-lane dB sums, level-0 histogram of the median select
 // ---------------------------------------------------------------------------------------------
-constexpr int SEQ_CPB = 4;       // clip slots per CTA
-constexpr int SEQ_TF = 8;        // frames per tile
-constexpr int SEQ_DET = 32;      // detector group: one warp (SEQ_CPB * SEQ_TF lanes = (slot, frame))
 constexpr int SEQ_KMAX = 128;    // operating-band bins supported (n_fft = 256 -> 71)
-constexpr int SEQ_RING = 8;      // item descriptor ring
-
-struct SeqItem {
-    int clip, t0, nt, T;
-    long long f0;
-    int flags;       // 1 valid, 2 first tile of the clip, 4 last tile of the clip
-    int pad;
-};
-
-struct SeqIO {
-    const float* P_band;   // [nF][K]
-    const float* td;       // [5][nF] (crest row 0, kurtosis row 1)
-    int8_t* frame_class; float* rain_conf; float* noise_conf;
-    int32_t* event_idx; int32_t* event_count;
-    float* det_noise_psd; float* det_noise_lag; float* D; float* noise_psd;
-    float* mode_flux; float* norm_flux; float* score; uint8_t* gate;
-    float* db_plane;       // [nF][K] noise-floor dB (scratch for the median select); may be null
-    double* db_sum;        // [n_clips]
-    int* clip_counter;     // dynamic clip scheduler
-    int64_t nF;
-};
-
-inline int seq_tracker_threads(int K) { return ((SEQ_CPB * K + 31) / 32) * 32; }
-inline size_t seq_smem_bytes(int K) {
-    // P ring [4][CPB][TF][K] + flux [2][CPB][TF][K] floats + dB partials [2][CPB][K] doubles
-    return sizeof(float) * (size_t)6 * SEQ_CPB * SEQ_TF * K + sizeof(double) * (size_t)2 * SEQ_CPB * K;
-}
+constexpr int TRK1_TT = 32;      // frames per tile of trk1 (mode sums are taken per tile)
+constexpr int SEQ_PF = 8;        // frames of register prefetch in the streaming loops
 
 struct Tracker {
     float trk, ts, nprev;
@@ -802,301 +775,279 @@ __device__ __forceinline__ float tracker_first(const DevParams& p, Tracker& s, f
     return s.nprev;
 }
 
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-static_assert(SEQ_CPB * SEQ_TF == SEQ_DET && SEQ_DET == 32, "detector group is exactly one warp");
-__device__ __forceinline__ void det_barrier() { __syncwarp(); }
+// Lane table of trk1: which band bins are tracked in pass 1 (the mode bins; every band bin when a
+// debug plane of pass 1 is requested) and where each mode's lanes start.
+struct Trk1Tab {
+    int n_lanes;
+    int mode_l0[APT_MAX_MODES];     // first lane of mode m (its bins are consecutive lanes)
+    int mode_n[APT_MAX_MODES];      // bins of mode m
+    unsigned char lane_bin[SEQ_KMAX];  // band-relative bin of lane j
+};
 
-__global__ void __launch_bounds__(640) clip_seq_kernel(const __grid_constant__ DevParams p, Batch b, SeqIO io, int ntrk) {
-    extern __shared__ __align__(16) unsigned char seq_raw[];
-    const int K = p.K, M = p.M;
-    const int tileK = SEQ_TF * K;
-    double* s_dbl = reinterpret_cast<double*>(seq_raw);                         // [2][CPB][K]
-    float* s_Pring = reinterpret_cast<float*>(s_dbl + 2 * SEQ_CPB * K);         // [4][CPB][TF*K]
-    float* s_flux = s_Pring + 4 * SEQ_CPB * tileK;                              // [2][CPB][TF*K]
-    __shared__ SeqItem s_item[SEQ_CPB][SEQ_RING];
-    __shared__ float s_mf[SEQ_CPB][APT_MAX_MODES + 1][SEQ_TF];   // raw flux per mode, row M = weighted total
-    __shared__ float s_nf[SEQ_CPB][APT_MAX_MODES + 1][SEQ_TF];   // normalised: row 0 total score, 1.. modes
-    __shared__ uint8_t s_excl[2][SEQ_CPB][SEQ_TF];
-    __shared__ int s_dbl_clip[2][SEQ_CPB];
+struct Trk1IO {
+    const float* P_band;   // [nF][K]
+    float* mf;             // [nF][stride]: cols 0..M-1 raw per-mode flux, col M weighted total
+    int stride;
+    float* det_noise_psd; float* det_noise_lag; float* D;   // optional [nF][K]
+    float* mode_flux;      // optional [M][nF]
+    int64_t nF;
+};
+
+// One CTA per clip; blockDim = n_lanes rounded up to a warp.
+__global__ void __launch_bounds__(SEQ_KMAX) trk1_kernel(const __grid_constant__ DevParams p, Batch b,
+                                                        const __grid_constant__ Trk1Tab tab, Trk1IO io) {
+    __shared__ float s_flux[TRK1_TT][SEQ_KMAX + 1];
     __shared__ float s_ltab[64];
-
     const int tid = threadIdx.x;
-    const bool is_trk = tid < ntrk;
-    const int dt = tid - ntrk;                       // detector-group index
-    const int slot = is_trk ? tid / K : 0;
-    const int k = is_trk ? tid - slot * K : 0;
-    const bool trk_active = is_trk && slot < SEQ_CPB;
-    if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
-    if (tid < 2 * SEQ_CPB) s_dbl_clip[tid / SEQ_CPB][tid % SEQ_CPB] = -1;
-
-    // ---- item generator state (detector threads dt < CPB, one per slot)
-    int g_clip = -1, g_T = 0, g_next = 0;
-    long long g_f0 = 0;
-    auto gen_item = [&](int s, int ring_idx) {
-        SeqItem itx;
-        itx.flags = 0; itx.clip = -1; itx.t0 = 0; itx.nt = 0; itx.T = 0; itx.f0 = 0; itx.pad = 0;
-        if (g_clip < 0 || g_next >= g_T) {
-            const int ci = atomicAdd(io.clip_counter, 1);
-            if (ci < b.n_clips) {
-                g_clip = b.clip0 + ci;
-                g_f0 = __ldg(b.frame_off + g_clip);
-                g_T = (int)(__ldg(b.frame_off + g_clip + 1) - g_f0);
-                g_next = 0;
-            } else {
-                g_clip = -1;
-            }
-        }
-        if (g_clip >= 0) {
-            itx.clip = g_clip; itx.t0 = g_next; itx.T = g_T; itx.f0 = g_f0;
-            itx.nt = min(SEQ_TF, g_T - g_next);
-            itx.flags = 1 | (g_next == 0 ? 2 : 0) | (g_next + SEQ_TF >= g_T ? 4 : 0);
-            g_next += SEQ_TF;
-        }
-        s_item[s][ring_idx] = itx;
-    };
-    if (!is_trk && dt < SEQ_CPB) { gen_item(dt, 0); gen_item(dt, 1); }
+    const int c = b.clip0 + blockIdx.x;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int K = p.K, M = p.M;
+    for (int i = tid; i < 64; i += blockDim.x) s_ltab[i] = u2f(kSvmlLog10TabDev[i]);
     __syncthreads();
-    if (trk_active) {
-        const SeqItem i0 = s_item[slot][0];
-        if (i0.flags & 1) {
-            const float* src = io.P_band + (i0.f0 + i0.t0) * K + k;
-            float* dst = s_Pring + (0 * SEQ_CPB + slot) * tileK + k;
-            for (int t = 0; t < i0.nt; t++) cp_async4(dst + t * K, src + (size_t)t * K);
-        }
-        cp_async_commit_wait_all();
-    }
-    __syncthreads();
-
-    // ---- per-lane recursion state
-    Tracker tr1 = {0, 0, 0}, tr2 = {0, 0, 0};
+    const bool lane_on = tid < tab.n_lanes;
+    const int kb = lane_on ? tab.lane_bin[tid] : 0;
+    const float* Pk = io.P_band + f0 * K + kb;
+    Tracker tr = {0, 0, 0};
     float dm1 = 0.0f, dm2 = 0.0f;
-    int warm2 = 0;
-    double dbsum = 0.0;
-    double bl_base = 0.0, bl_scale = 0.0;   // detector warp 0 lanes: (slot, row)
-    int rain_count = 0;                     // detector E lanes
+    float pbuf[SEQ_PF];
+#pragma unroll
+    for (int u = 0; u < SEQ_PF; u++) pbuf[u] = (lane_on && u < T) ? __ldg(Pk + (size_t)u * K) : 0.0f;
 
-    for (int it = 0;; it++) {
-        if (is_trk) {
-            if (trk_active) {
-                const SeqItem iB = s_item[slot][it & (SEQ_RING - 1)];
-                const SeqItem iN = s_item[slot][(it + 1) & (SEQ_RING - 1)];
-                SeqItem iF; iF.flags = 0;
-                if (it >= 2) iF = s_item[slot][(it - 2) & (SEQ_RING - 1)];
-                // prefetch the next item's power tile (one tile ahead)
-                if (iN.flags & 1) {
-                    const float* src = io.P_band + (iN.f0 + iN.t0) * K + k;
-                    float* dst = s_Pring + (((it + 1) & 3) * SEQ_CPB + slot) * tileK + k;
-                    for (int t = 0; t < iN.nt; t++) cp_async4(dst + t * K, src + (size_t)t * K);
-                }
-                const bool vB = iB.flags & 1, vF = iF.flags & 1;
-                const float* PB = s_Pring + ((it & 3) * SEQ_CPB + slot) * tileK + k;
-                const float* PF = s_Pring + (((it - 2) & 3) * SEQ_CPB + slot) * tileK + k;
-                float* FB = s_flux + ((it & 1) * SEQ_CPB + slot) * tileK + k;
-                const uint8_t* EX = s_excl[it & 1][slot];
-                const int ntB = vB ? iB.nt : 0, ntF = vF ? iF.nt : 0;
-                if (vF && (iF.flags & 2)) { warm2 = 0; dbsum = 0.0; }
-#pragma unroll 2
-                for (int t = 0; t < SEQ_TF; t++) {
-                    if (t < ntB) {
-                        // stage B: tracker pass 1 + detector normalisation (rain_signal_processor.py:862-888)
-                        const int tg = iB.t0 + t;
-                        const float pk = PB[t * K];
+    for (int t0 = 0; t0 < T; t0 += TRK1_TT) {
+        const int nt = min(TRK1_TT, T - t0);
+        if (lane_on) {
+            for (int tb = 0; tb < nt; tb += SEQ_PF) {
+                float pcur[SEQ_PF];
+#pragma unroll
+                for (int u = 0; u < SEQ_PF; u++) pcur[u] = pbuf[u];
+                const int tn = t0 + tb + SEQ_PF;   // first frame of the next group
+#pragma unroll
+                for (int u = 0; u < SEQ_PF; u++) pbuf[u] = (tn + u < T) ? __ldg(Pk + (size_t)(tn + u) * K) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < SEQ_PF; u++) {
+                    const int tt = tb + u;
+                    if (tt < nt) {
+                        // tracker pass 1 + detector normalisation (rain_signal_processor.py:862-888)
+                        const int tg = t0 + tt;
+                        const float pk = pcur[u];
                         float dval;
                         if (p.use_norm) {
-                            const float nprev = tr1.nprev;   // N1[t-1]
-                            const float n1 = (tg == 0) ? tracker_first(p, tr1, pk) : tracker_step(p, tr1, pk, true);
+                            const float nprev = tr.nprev;   // N1[t-1]
+                            const float n1 = (tg == 0) ? tracker_first(p, tr, pk) : tracker_step(p, tr, pk, true);
                             float nl = (tg == 0) ? n1 : nprev;
                             nl = f_min(nl, p.trk_maxr * pk);
                             if (p.ratio_db)
                                 dval = 10.0f * svml_log10f(f_div(pk, nl + p.eps32) + p.eps32, s_ltab);
                             else
                                 dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab) - 10.0f * svml_log10f(nl + p.eps32, s_ltab);
-                            if (io.det_noise_psd) io.det_noise_psd[(iB.f0 + tg) * K + k] = n1;
-                            if (io.det_noise_lag) io.det_noise_lag[(iB.f0 + tg) * K + k] = nl;
+                            if (io.det_noise_psd) io.det_noise_psd[(f0 + tg) * K + kb] = n1;
+                            if (io.det_noise_lag) io.det_noise_lag[(f0 + tg) * K + kb] = nl;
                         } else {
                             dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab);
                         }
-                        if (io.D) io.D[(iB.f0 + tg) * K + k] = dval;
+                        if (io.D) io.D[(f0 + tg) * K + kb] = dval;
                         // positive t-vs-(t-2) flux, lane-local history (rain_frame_classifier.py:721-746)
                         float fx = 0.0f;
                         if (tg >= 2) { const float d = dval - dm2; fx = d > 0.0f ? d : (d != d ? d : 0.0f); }
                         dm2 = dm1; dm1 = dval;
-                        FB[t * K] = fx;
-                    }
-                    if (t < ntF) {
-                        // stage F: tracker pass 2 gated by the labels (:1006-1028) + noise-floor dB
-                        const int tg = iF.t0 + t;
-                        const float pk = PF[t * K];
-                        const bool allow = (warm2 < p.warm_need) || !EX[t];
-                        const float n2 = (tg == 0) ? tracker_first(p, tr2, pk) : tracker_step(p, tr2, pk, allow);
-                        if (allow) warm2++;
-                        const float db = 10.0f * svml_log10f(n2 + p.eps32, s_ltab);
-                        dbsum += (double)db;
-                        const int64_t gi = (iF.f0 + tg) * K + k;
-                        if (io.noise_psd) io.noise_psd[gi] = n2;
-                        if (io.db_plane) io.db_plane[gi] = db;
+                        s_flux[tt][tid] = fx;
                     }
                 }
-                if (vF && (iF.flags & 4)) {
-                    s_dbl[((it & 1) * SEQ_CPB + slot) * K + k] = dbsum;
-                    if (k == 0) s_dbl_clip[it & 1][slot] = iF.clip;
-                }
-            }
-            cp_async_commit_wait_all();
-        } else {
-            // ------------------------------ detector group ------------------------------
-            // fixed-order reduction of the per-bin dB sums published in the previous iteration
-            if (dt < SEQ_CPB && it >= 1) {
-                const int pb = (it - 1) & 1;
-                const int c = s_dbl_clip[pb][dt];
-                if (c >= 0) {
-                    double s = 0.0;
-                    const double* src = s_dbl + (pb * SEQ_CPB + dt) * K;
-                    for (int kk = 0; kk < K; kk++) s += src[kk];
-                    io.db_sum[c] = s;
-                    s_dbl_clip[pb][dt] = -1;
-                }
-            }
-            if (dt < SEQ_CPB) gen_item(dt, (it + 2) & (SEQ_RING - 1));
-            const int dslot = dt / SEQ_TF, dtt = dt % SEQ_TF;   // (slot, frame) mapping for C and E
-            SeqItem iD; iD.flags = 0;
-            if (it >= 1 && dslot < SEQ_CPB) iD = s_item[dslot][(it - 1) & (SEQ_RING - 1)];
-            const bool vD = (iD.flags & 1) && dslot < SEQ_CPB;
-            // TD features of this item's frames: issue the loads now, consume them in stage E
-            float crest_pf = 0.0f, kurt_pf = 0.0f;
-            if (vD && dtt < iD.nt) {
-                crest_pf = __ldg(io.td + iD.f0 + iD.t0 + dtt);
-                if (p.has_ku) kurt_pf = __ldg(io.td + io.nF + iD.f0 + iD.t0 + dtt);
-            }
-            // ---- C: per-mode sums of the flux row in numpy order + float64 weighted total (:749-759)
-            if (vD && dtt < iD.nt) {
-                const float* fr = s_flux + (((it - 1) & 1) * SEQ_CPB + dslot) * tileK + dtt * K;
-                const int tg = iD.t0 + dtt;
-                double tot = 0.0;
-                for (int m = 0; m < M; m++) {
-                    float s = 0.0f;
-                    const int lo = p.mode_blo[m], n = p.mode_bhi[m] - lo + 1;
-                    if (tg >= 2 && n > 0) {
-                        if (n < 8) {
-                            float r = -0.0f;
-                            for (int i = 0; i < n; i++) r += fr[lo + i];
-                            s = 0.0f + r;
-                        } else {
-                            s = 0.0f + np_pairwise<float>([&](int kk) { return fr[kk]; }, lo, n);
-                        }
-                    }
-                    s_mf[dslot][m][dtt] = s;
-                    tot += p.mode_w[m] * (double)s;
-                    if (io.mode_flux) io.mode_flux[(int64_t)m * io.nF + iD.f0 + tg] = s;
-                }
-                s_mf[dslot][M][dtt] = (tg >= 2) ? d2f(tot) : 0.0f;
-            }
-            det_barrier();
-            // ---- D: causal stochastic low-quantile baselines in float64 (:31-82, :873-893)
-            if (dt < SEQ_CPB * (M + 1)) {
-                const int bs = dt / (M + 1), row = dt - bs * (M + 1);
-                SeqItem jD; jD.flags = 0;
-                if (it >= 1) jD = s_item[bs][(it - 1) & (SEQ_RING - 1)];
-                if (jD.flags & 1) {
-                    const float* x = s_mf[bs][(row == 0) ? M : row - 1];
-                    const float ffloor = d2f(p.bl_floor);
-                    for (int t = 0; t < jD.nt; t++) {
-                        const double xt = (double)x[t];
-                        if (jD.t0 + t == 0) {
-                            bl_base = xt > p.bl_floor ? xt : p.bl_floor;
-                            bl_scale = fabs(xt) > p.bl_floor ? fabs(xt) : p.bl_floor;
-                        }
-                        float ob = d2f(bl_base);
-                        if (isnan(ob) || isinf(ob)) ob = ffloor;
-                        ob = f_max(ob, ffloor);
-                        const double err = xt - bl_base;
-                        bl_scale = p.bl_alpha * bl_scale + (1.0 - p.bl_alpha) * fabs(err);
-                        const double step = p.bl_eta * (bl_scale > p.bl_floor ? bl_scale : p.bl_floor);
-                        const double delta = (xt >= bl_base) ? p.bl_q * step : -(1.0 - p.bl_q) * step;
-                        const double nb = bl_base + delta;
-                        bl_base = nb > p.bl_floor ? nb : p.bl_floor;
-                        const float ex = f_max(x[t] - ob, 0.0f);
-                        float sc = p.norm_enable ? f_div(ex, ob + p.norm_min) : ex;
-                        if (isnan(sc) || isinf(sc)) sc = 0.0f;
-                        s_nf[bs][row][t] = sc;
-                        if (io.norm_flux && row > 0) io.norm_flux[(int64_t)(row - 1) * io.nF + jD.f0 + jD.t0 + t] = sc;
-                    }
-                }
-            }
-            det_barrier();
-            // ---- E: TD gate, fixed-band decision, labels, event compaction (16 lanes per slot)
-            if (dslot < SEQ_CPB) {
-                bool is_rain = false;
-                if (vD && (iD.flags & 2)) rain_count = 0;
-                if (vD && dtt < iD.nt) {
-                    const int tg = iD.t0 + dtt;
-                    const int64_t g = iD.f0 + tg;
-                    bool gate = crest_pf > p.gate_thr;
-                    if (p.has_ku) gate = gate && (kurt_pf <= p.ku);
-                    const float gs = gate ? 1.0f : 0.0f;
-                    const float l0 = svml_log1pf(f_max(s_nf[dslot][1][dtt] * gs, 0.0f));
-                    const float l1 = svml_log1pf(f_max(s_nf[dslot][2][dtt] * gs, 0.0f));
-                    const float l2 = svml_log1pf(f_max(s_nf[dslot][3][dtt] * gs, 0.0f));
-                    const float l3 = svml_log1pf(f_max(s_nf[dslot][4][dtt] * gs, 0.0f));
-                    const int hits = (l1 >= p.thr1) + (l2 >= p.thr2) + (l3 >= p.thr3);
-                    is_rain = (l0 >= p.thr0) && (hits >= max(1, p.min_support));
-                    const float rc = is_rain ? 1.0f : 0.0f;
-                    float nc = 1.0f - rc;
-                    nc = nc < 0.0f ? 0.0f : (nc > 1.0f ? 1.0f : nc);
-                    const float score = s_nf[dslot][0][dtt];
-                    const bool weak = (score * gs) <= p.mf_noise_max;
-                    int8_t cls = 1;
-                    if (nc >= p.noise_hi && weak && !is_rain) cls = 0;
-                    if (is_rain) cls = 2;
-                    io.frame_class[g] = cls; io.rain_conf[g] = rc; io.noise_conf[g] = nc;
-                    if (io.score) io.score[g] = score;
-                    if (io.gate) io.gate[g] = gate ? 1 : 0;
-                    s_excl[(it - 1) & 1][dslot][dtt] = cls != 0;
-                }
-                // the SEQ_TF lanes of a slot sit in one half-warp
-                const unsigned full = __ballot_sync(0xffffffffu, is_rain);
-                const int shift = ((tid & 31) / SEQ_TF) * SEQ_TF;
-                const unsigned m = (full >> shift) & ((1u << SEQ_TF) - 1u);
-                if (is_rain) io.event_idx[iD.f0 + rain_count + __popc(m & ((1u << dtt) - 1u))] = iD.t0 + dtt;
-                rain_count += __popc(m);
-                if (vD && (iD.flags & 4) && dtt == 0) io.event_count[iD.clip] = rain_count;
             }
         }
         __syncthreads();
-        // stop when nothing is in flight: items it+1 (next B), it (next D), it-1 (next F) all invalid
-        bool any = false;
-#pragma unroll
-        for (int s = 0; s < SEQ_CPB; s++)
-            any = any || (s_item[s][(it + 1) & (SEQ_RING - 1)].flags & 1) || (s_item[s][it & (SEQ_RING - 1)].flags & 1) ||
-                  (it >= 1 && (s_item[s][(it - 1) & (SEQ_RING - 1)].flags & 1));
-        if (!any) break;
+        // per-mode sums of the flux row in numpy order + float64 weighted total (:749-759)
+        for (int tt = tid; tt < nt; tt += blockDim.x) {
+            const float* fr = s_flux[tt];
+            const int tg = t0 + tt;
+            float* row = io.mf + (f0 + tg) * io.stride;
+            double tot = 0.0;
+            for (int m = 0; m < M; m++) {
+                float s = 0.0f;
+                const int lo = tab.mode_l0[m], n = tab.mode_n[m];
+                if (tg >= 2 && n > 0) {
+                    if (n < 8) {
+                        float r = -0.0f;
+                        for (int i = 0; i < n; i++) r += fr[lo + i];
+                        s = 0.0f + r;
+                    } else {
+                        s = 0.0f + np_pairwise<float>([&](int kk) { return fr[kk]; }, lo, n);
+                    }
+                }
+                row[m] = s;
+                tot += p.mode_w[m] * (double)s;
+                if (io.mode_flux) io.mode_flux[(int64_t)m * io.nF + f0 + tg] = s;
+            }
+            row[M] = (tg >= 2) ? d2f(tot) : 0.0f;
+        }
+        __syncthreads();
     }
-    // dB sums published in the very last iteration
-    __syncthreads();
-    if (!is_trk && dt < SEQ_CPB)
-        for (int pb = 0; pb < 2; pb++) {
-            const int c = s_dbl_clip[pb][dt];
-            if (c >= 0) {
-                double s = 0.0;
-                const double* src = s_dbl + (pb * SEQ_CPB + dt) * K;
-                for (int kk = 0; kk < K; kk++) s += src[kk];
-                io.db_sum[c] = s;
+}
+
+struct DetIO {
+    const float* mf; int stride;     // [nF][stride]
+    const float* td;                 // [5][nF] (crest row 0, kurtosis row 1)
+    int8_t* frame_class; float* rain_conf; float* noise_conf;
+    int32_t* event_idx; int32_t* event_count;
+    float* norm_flux; float* score; uint8_t* gate;   // optional
+    int64_t nF;
+};
+
+constexpr int DET_WARPS = 4;         // warps per CTA (independent of one another)
+constexpr int DET_GMAX = 8;          // clips per warp upper bound (rows per clip >= 4)
+
+// lane = (clip, row): row 0 follows the weighted total flux, row r >= 1 follows mode r-1.
+// A warp owns G = 32 / R clips (R = M + 1 rows per clip) and walks them frame by frame.
+__global__ void __launch_bounds__(DET_WARPS * 32) detect_kernel(const __grid_constant__ DevParams p, Batch b, DetIO io) {
+    __shared__ int8_t s_cls[DET_WARPS][DET_GMAX][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int M = p.M, R = M + 1, G = 32 / R;
+    const int warp = blockIdx.x * DET_WARPS + wib;
+    const int g = lane / R, row = lane - g * R;
+    const int ci = warp * G + g;
+    const bool lane_on = (g < G) && (ci < b.n_clips);
+    const int c = b.clip0 + (lane_on ? ci : 0);
+    const int64_t f0 = lane_on ? __ldg(b.frame_off + c) : 0;
+    const int T = lane_on ? (int)(__ldg(b.frame_off + c + 1) - f0) : 0;
+    int Tmax = T;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, d));
+    // geometry of the flush phase: clip gi of this warp, seen from every lane
+    int64_t f0_g[DET_GMAX];
+    int T_g[DET_GMAX], cnt_g[DET_GMAX];
+#pragma unroll
+    for (int gi = 0; gi < DET_GMAX; gi++) {
+        const int src = min(gi * R, 31);
+        const int64_t f = __shfl_sync(0xffffffffu, f0, src);
+        const int tt = __shfl_sync(0xffffffffu, T, src);
+        f0_g[gi] = f; T_g[gi] = (gi < G) ? tt : 0; cnt_g[gi] = 0;
+    }
+    const int col = (row == 0) ? M : row - 1;
+    const float* xs = io.mf + f0 * io.stride + col;
+    const float* crest = io.td + f0;
+    const float* kurt = io.td + io.nF + f0;
+    const float ffloor = d2f(p.bl_floor);
+    const float thr = row == 1 ? p.thr0 : (row == 2 ? p.thr1 : (row == 3 ? p.thr2 : p.thr3));
+    const unsigned grp_shift = (unsigned)(g * R);
+    double bl_base = 0.0, bl_scale = 0.0;
+    float xbuf[SEQ_PF], cbuf[SEQ_PF], kbuf[SEQ_PF];
+#pragma unroll
+    for (int u = 0; u < SEQ_PF; u++) {
+        xbuf[u] = (u < T) ? __ldg(xs + (size_t)u * io.stride) : 0.0f;
+        cbuf[u] = (u < T) ? __ldg(crest + u) : 0.0f;
+        kbuf[u] = (p.has_ku && u < T) ? __ldg(kurt + u) : 0.0f;
+    }
+    for (int tb = 0; tb < Tmax; tb += SEQ_PF) {
+        float xc[SEQ_PF], cc[SEQ_PF], kc[SEQ_PF];
+#pragma unroll
+        for (int u = 0; u < SEQ_PF; u++) { xc[u] = xbuf[u]; cc[u] = cbuf[u]; kc[u] = kbuf[u]; }
+        const int tn = tb + SEQ_PF;
+#pragma unroll
+        for (int u = 0; u < SEQ_PF; u++) {
+            const bool ok = tn + u < T;
+            xbuf[u] = ok ? __ldg(xs + (size_t)(tn + u) * io.stride) : 0.0f;
+            cbuf[u] = ok ? __ldg(crest + tn + u) : 0.0f;
+            kbuf[u] = (p.has_ku && ok) ? __ldg(kurt + tn + u) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < SEQ_PF; u++) {
+            const int t = tb + u;
+            if (t >= Tmax) break;   // warp-uniform
+            const bool on = t < T;
+            // ---- causal stochastic low-quantile baseline in float64 (rain_frame_classifier.py:31-82, :873-893)
+            float sc = 0.0f;
+            {
+                const float xf = xc[u];
+                const double xt = (double)xf;
+                if (t == 0) {
+                    bl_base = xt > p.bl_floor ? xt : p.bl_floor;
+                    bl_scale = fabs(xt) > p.bl_floor ? fabs(xt) : p.bl_floor;
+                }
+                float ob = d2f(bl_base);
+                if (isnan(ob) || isinf(ob)) ob = ffloor;
+                ob = f_max(ob, ffloor);
+                const double err = xt - bl_base;
+                bl_scale = p.bl_alpha * bl_scale + (1.0 - p.bl_alpha) * fabs(err);
+                const double step = p.bl_eta * (bl_scale > p.bl_floor ? bl_scale : p.bl_floor);
+                const double delta = (xt >= bl_base) ? p.bl_q * step : -(1.0 - p.bl_q) * step;
+                const double nb = bl_base + delta;
+                bl_base = nb > p.bl_floor ? nb : p.bl_floor;
+                const float ex = f_max(xf - ob, 0.0f);
+                sc = p.norm_enable ? f_div(ex, ob + p.norm_min) : ex;
+                if (isnan(sc) || isinf(sc)) sc = 0.0f;
+            }
+            // ---- TD gate + fixed-band decision (:230-284, :914-998): one ballot per frame
+            bool gate = cc[u] > p.gate_thr;
+            if (p.has_ku) gate = gate && (kc[u] <= p.ku);
+            const float gs = gate ? 1.0f : 0.0f;
+            const float v = sc * gs;
+            bool hit;
+            if (row == 0) hit = v <= p.mf_noise_max;                       // "weak" total flux
+            else hit = (row <= 4) && (svml_log1pf(f_max(v, 0.0f)) >= thr);  // primary / supports
+            const unsigned bal = __ballot_sync(0xffffffffu, hit && on && lane_on);
+            const unsigned bits = bal >> grp_shift;
+            const bool weak = bits & 1u, prim = bits & 2u;
+            const int hits = __popc(bits & 0x1cu);
+            const bool is_rain = prim && (hits >= max(1, p.min_support));
+            const float rc = is_rain ? 1.0f : 0.0f;
+            float nc = 1.0f - rc;
+            nc = nc < 0.0f ? 0.0f : (nc > 1.0f ? 1.0f : nc);
+            int8_t cls = 1;
+            if (nc >= p.noise_hi && weak && !is_rain) cls = 0;
+            if (is_rain) cls = 2;
+            if (on && lane_on) {
+                if (row == 0) {
+                    s_cls[wib][g][t & 31] = cls;
+                    // confidences are functions of the class: written here so a flush only moves labels
+                    if (io.score) io.score[f0 + t] = sc;
+                    if (io.gate) io.gate[f0 + t] = gate ? 1 : 0;
+                } else if (io.norm_flux) {
+                    io.norm_flux[(int64_t)(row - 1) * io.nF + f0 + t] = sc;
+                }
+            }
+            // ---- every 32 frames: coalesced label / confidence stores + event compaction
+            if ((t & 31) == 31 || t == Tmax - 1) {
+                __syncwarp();
+                const int tbase = t & ~31;
+#pragma unroll
+                for (int gi = 0; gi < DET_GMAX; gi++) {
+                    if (gi >= G) break;
+                    const int tl = tbase + lane;
+                    const bool valid = tl < T_g[gi] && tbase < T_g[gi];
+                    int8_t cl = valid ? s_cls[wib][gi][lane] : (int8_t)0;
+                    const bool rain = valid && cl == 2;
+                    if (valid) {
+                        const int64_t gidx = f0_g[gi] + tl;
+                        io.frame_class[gidx] = cl;
+                        io.rain_conf[gidx] = rain ? 1.0f : 0.0f;
+                        io.noise_conf[gidx] = rain ? 0.0f : 1.0f;
+                    }
+                    const unsigned rm = __ballot_sync(0xffffffffu, rain);
+                    if (rain) io.event_idx[f0_g[gi] + cnt_g[gi] + __popc(rm & ((1u << lane) - 1u))] = tl;
+                    cnt_g[gi] += __popc(rm);
+                }
+                __syncwarp();
             }
         }
+    }
+    // event counts: lane gi writes the count of clip gi
+#pragma unroll
+    for (int gi = 0; gi < DET_GMAX; gi++) {
+        if (gi < G && lane == gi) {
+            const int cg = warp * G + gi;
+            if (cg < b.n_clips) io.event_count[b.clip0 + cg] = cnt_g[gi];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // exact median of the dB plane per clip: 3-level MSD radix select on order-preserving keys.
-// Two ranks are selected at once (lower / upper middle of an even count).
+// Two ranks are selected at once (lower / upper middle of an even count).  Level 0 (bits 31..21) is
+// histogrammed by trk2_kernel while it produces the plane; levels 1 and 2 re-read it as a flat array.
 // ---------------------------------------------------------------------------------------------
 constexpr int SEL_BINS = 2048;
-constexpr int SEL_CHUNK = 1024;  // frames per CTA
+constexpr int SEL_CHUNK = 1 << 16;   // plane elements per CTA of select_hist_kernel
 struct SelState {
     uint32_t prefix[2];
     int64_t rank[2];
@@ -1109,6 +1060,86 @@ __device__ __forceinline__ float key_db(uint32_t k) {
     return u2f((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+struct Trk2IO {
+    const float* P_band;        // [nF][K]
+    const int8_t* frame_class;  // [nF]
+    float* noise_psd;           // optional [nF][K]
+    float* db_plane;            // [nF][K] noise-floor dB (input of the median select)
+    double* db_lane_sum;        // [plan clips][K] per-lane sums of the dB plane
+    uint32_t* hist;             // [plan clips][2][SEL_BINS]: copy 0 receives the level-0 histogram
+    int64_t nF;
+};
+
+// lane = (clip, bin), packed densely over warps; warps are independent.
+__global__ void __launch_bounds__(128) trk2_kernel(const __grid_constant__ DevParams p, Batch b, Trk2IO io) {
+    __shared__ float s_ltab[64];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_ltab[i] = u2f(kSvmlLog10TabDev[i]);
+    __syncthreads();
+    const int K = p.K;
+    const int64_t gl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ci = (int)(gl / K);
+    const bool lane_on = ci < b.n_clips;
+    const int k = (int)(gl - (int64_t)ci * K);
+    const int c = b.clip0 + (lane_on ? ci : 0);
+    const int64_t f0 = lane_on ? __ldg(b.frame_off + c) : 0;
+    const int T = lane_on ? (int)(__ldg(b.frame_off + c + 1) - f0) : 0;
+    int Tmax = T;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, d));
+    const float* Pk = io.P_band + f0 * K + k;
+    const int8_t* fc = io.frame_class + f0;
+    uint32_t* h0 = io.hist + (size_t)c * 2 * SEL_BINS;
+    Tracker tr = {0, 0, 0};
+    int warm = 0;
+    double dbsum = 0.0;
+    int run_bin = -1;
+    uint32_t run_cnt = 0;
+    float pbuf[SEQ_PF];
+    int8_t ebuf[SEQ_PF];
+#pragma unroll
+    for (int u = 0; u < SEQ_PF; u++) {
+        pbuf[u] = (u < T) ? __ldg(Pk + (size_t)u * K) : 0.0f;
+        ebuf[u] = (u < T) ? __ldg(fc + u) : (int8_t)0;
+    }
+    for (int tb = 0; tb < Tmax; tb += SEQ_PF) {
+        float pc[SEQ_PF];
+        int8_t ec[SEQ_PF];
+#pragma unroll
+        for (int u = 0; u < SEQ_PF; u++) { pc[u] = pbuf[u]; ec[u] = ebuf[u]; }
+        const int tn = tb + SEQ_PF;
+#pragma unroll
+        for (int u = 0; u < SEQ_PF; u++) {
+            const bool ok = tn + u < T;
+            pbuf[u] = ok ? __ldg(Pk + (size_t)(tn + u) * K) : 0.0f;
+            ebuf[u] = ok ? __ldg(fc + tn + u) : (int8_t)0;
+        }
+#pragma unroll
+        for (int u = 0; u < SEQ_PF; u++) {
+            const int t = tb + u;
+            if (t < T) {
+                // tracker pass 2 gated by the labels (rain_signal_processor.py:1006-1028) + noise-floor dB
+                const float pk = pc[u];
+                const bool allow = (warm < p.warm_need) || (ec[u] == 0);
+                const float n2 = (t == 0) ? tracker_first(p, tr, pk) : tracker_step(p, tr, pk, allow);
+                if (allow) warm++;
+                const float db = 10.0f * svml_log10f(n2 + p.eps32, s_ltab);
+                dbsum += (double)db;
+                const int64_t gi = (f0 + t) * K + k;
+                if (io.noise_psd) io.noise_psd[gi] = n2;
+                io.db_plane[gi] = db;
+                const int bin = (int)(db_key(db) >> 21);
+                if (bin == run_bin) run_cnt++;
+                else {
+                    if (run_cnt) atomicAdd(h0 + run_bin, run_cnt);
+                    run_bin = bin; run_cnt = 1;
+                }
+            }
+        }
+    }
+    if (run_cnt) atomicAdd(h0 + run_bin, run_cnt);
+    if (lane_on) io.db_lane_sum[(size_t)c * K + k] = dbsum;
+}
+
 __global__ void select_init_kernel(Batch b, int K, SelState* st) {
     const int ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= b.n_clips) return;
@@ -1119,54 +1150,52 @@ __global__ void select_init_kernel(Batch b, int K, SelState* st) {
     st[c].rank[1] = n / 2;
 }
 
-// level 0: bits 31..21, level 1: bits 20..10, level 2: bits 9..0
-__global__ void __launch_bounds__(128) select_hist_kernel(Batch b, int K, const float* __restrict__ db,
+// level 1: bits 20..10, level 2: bits 9..0 of the elements whose higher bits equal the prefix found so
+// far.  The plane of a clip is a flat array of T*K floats; a CTA histograms one SEL_CHUNK of it in
+// shared memory and adds the non-empty bins to the clip's global histogram.
+__global__ void __launch_bounds__(256) select_hist_kernel(Batch b, int K, const float* __restrict__ db,
                                                           const int64_t* __restrict__ chunk_off, int level,
                                                           const SelState* __restrict__ st, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_h[2][SEL_BINS];
     int64_t chunk_in_clip;
     const int c = tile_clip(b, chunk_off, chunk_in_clip);
-    const int chunk = (int)chunk_in_clip;
     const int64_t f0 = __ldg(b.frame_off + c);
-    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
-    const int ta = chunk * SEL_CHUNK, tb = min(T, ta + SEL_CHUNK);
-    const int k = threadIdx.x;
-    if (k >= K) return;
-    const int sh = level == 0 ? 21 : (level == 1 ? 10 : 0);
+    const int64_t n = (__ldg(b.frame_off + c + 1) - f0) * (int64_t)K;
+    const int64_t e0 = chunk_in_clip * SEL_CHUNK, e1 = min(n, e0 + (int64_t)SEL_CHUNK);
+    const int sh = level == 1 ? 10 : 0;
     const uint32_t mask = level == 2 ? 1023u : 2047u;
+    const int shp = level == 1 ? 21 : 10;
     const uint32_t pre0 = st[c].prefix[0], pre1 = st[c].prefix[1];
-    const int shp = level == 0 ? 32 : (level == 1 ? 21 : 10);
-    uint32_t* h0 = hist + ((size_t)c * 2 + 0) * SEL_BINS;
-    uint32_t* h1 = hist + ((size_t)c * 2 + 1) * SEL_BINS;
-    int run_bin[2] = {-1, -1};
-    uint32_t run_cnt[2] = {0, 0};
-    const float* src = db + (f0 + ta) * K + k;
+    const bool two = pre1 != pre0;
+    for (int i = threadIdx.x; i < 2 * SEL_BINS; i += blockDim.x) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    const float* src = db + f0 * K;
     constexpr int U = 8;
-    float vbuf[U];
-    for (int tbase = ta; tbase < tb; tbase += U) {
+    for (int64_t base = e0 + threadIdx.x; base < e1; base += (int64_t)U * blockDim.x) {
+        float v[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) vbuf[u] = (tbase + u < tb) ? __ldg(src + (size_t)u * K) : 0.0f;
-      src += (size_t)U * K;
+        for (int u = 0; u < U; u++) {
+            const int64_t i = base + (int64_t)u * blockDim.x;
+            v[u] = i < e1 ? __ldg(src + i) : 0.0f;
+        }
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (tbase + u >= tb) break;
-        const uint32_t key = db_key(vbuf[u]);
-        const uint32_t hi = (level == 0) ? 0u : (key >> shp);
-        const int bin = (int)((key >> sh) & mask);
-#pragma unroll
-        for (int w = 0; w < 2; w++) {
-            const uint32_t pre = w ? pre1 : pre0;
-            if (w == 1 && (level == 0 || pre1 == pre0)) continue;   // identical prefix: copy 0 serves both
-            if (level != 0 && hi != pre) continue;
-            if (bin == run_bin[w]) run_cnt[w]++;
-            else {
-                if (run_cnt[w]) atomicAdd((w ? h1 : h0) + run_bin[w], run_cnt[w]);
-                run_bin[w] = bin; run_cnt[w] = 1;
+        for (int u = 0; u < U; u++) {
+            const int64_t i = base + (int64_t)u * blockDim.x;
+            if (i < e1) {
+                const uint32_t key = db_key(v[u]);
+                const uint32_t hi = key >> shp;
+                const int bin = (int)((key >> sh) & mask);
+                if (hi == pre0) atomicAdd(&s_h[0][bin], 1u);
+                else if (two && hi == pre1) atomicAdd(&s_h[1][bin], 1u);
             }
         }
-      }
     }
-    if (run_cnt[0]) atomicAdd(h0 + run_bin[0], run_cnt[0]);
-    if (run_cnt[1]) atomicAdd(h1 + run_bin[1], run_cnt[1]);
+    __syncthreads();
+    uint32_t* hg = hist + (size_t)c * 2 * SEL_BINS;
+    for (int i = threadIdx.x; i < 2 * SEL_BINS; i += blockDim.x) {
+        const uint32_t cnt = (&s_h[0][0])[i];
+        if (cnt) atomicAdd(hg + i, cnt);
+    }
 }
 
 // one warp per clip: find the bins holding the two ranks, refine prefix/rank (histograms are cleared
@@ -1220,7 +1249,7 @@ __global__ void select_scan_kernel(int clip0, int n_clips, int level, SelState* 
 }
 
 __global__ void finalize_kernel(const __grid_constant__ DevParams p, Batch b, const SelState* __restrict__ st,
-                                const double* __restrict__ db_sum, const int32_t* __restrict__ event_count,
+                                const double* __restrict__ db_lane_sum, const int32_t* __restrict__ event_count,
                                 float* __restrict__ stats, int clip_id_base) {
     const int ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= b.n_clips) return;
@@ -1245,7 +1274,9 @@ __global__ void finalize_kernel(const __grid_constant__ DevParams p, Batch b, co
         for (int i = 0; i < 64; i++) lt[i] = u2f(kSvmlLog10TabDev[i]);
         r[6] = r[7] = T > 0 ? 10.0f * svml_log10f(p.eps32, lt) : 0.0f;
     } else {
-        r[6] = d2f(db_sum[c] / ((double)T * (double)p.K));
+        double s = 0.0;   // fixed order over the bins: the mean does not depend on the launch geometry
+        for (int k = 0; k < p.K; k++) s += db_lane_sum[(size_t)c * p.K + k];
+        r[6] = d2f(s / ((double)T * (double)p.K));
         const float a = key_db(st[c].prefix[0]), bb = key_db(st[c].prefix[1]);
         r[7] = f_div(a + bb, 2.0f);
     }

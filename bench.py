@@ -202,7 +202,7 @@ def main():
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
     import ctypes as C
-    kms = (C.c_float * 5)()
+    kms = (C.c_float * len(_lib.KERNEL_NAMES))()
     eng.L.apt_plan_kernel_ms(plan.h, kms)
     eng.L.apt_plan_enable_timing(plan.h, 0)
     sampler.stop_flag.set()
@@ -223,8 +223,10 @@ def main():
     kernel_bytes = {   # algorithmic bytes each kernel must move in this decomposition
         "stft256_kernel": plan.nS * 2 + nF * K * 4,
         "td_features_kernel": plan.nS * 2 + nF * 4,
-        "clip_seq_kernel": nF * K * 4 + nF * 4 + nF * 9 + nF * K * 4,
-        "select_kernels": 3 * nF * K * 4,
+        "trk1_kernel": nF * 26 * 4 + nF * 32,
+        "detect_kernel": nF * 32 + nF * 4 + nF * 9,
+        "trk2_kernel": nF * K * 4 + nF + nF * K * 4,
+        "select_kernels": 2 * nF * K * 4,
         "finalize_kernel": n_clips * 64,
     }
     kms_step = {name: float(kms[i]) / args.steps for i, name in enumerate(_lib.KERNEL_NAMES)}

@@ -168,10 +168,12 @@ int  apt_plan_last_launches(const apt_plan_t* plan);
    returns the accumulated milliseconds per group since the last call (and resets them). */
 #define APT_KERNEL_STFT 0      /* stft256_kernel */
 #define APT_KERNEL_TD 1        /* td_features_kernel */
-#define APT_KERNEL_SEQ 2       /* clip_seq_kernel */
-#define APT_KERNEL_SELECT 3    /* select_init/hist/scan (median) */
-#define APT_KERNEL_FINALIZE 4  /* finalize_kernel */
-#define APT_N_KERNELS 5
+#define APT_KERNEL_TRK1 2      /* trk1_kernel: tracker pass 1, dB normalisation, flux, mode sums */
+#define APT_KERNEL_DETECT 3    /* detect_kernel: baselines, decision, labels, events */
+#define APT_KERNEL_TRK2 4      /* trk2_kernel: tracker pass 2, noise-floor dB plane, level-0 histogram */
+#define APT_KERNEL_SELECT 5    /* select_hist/scan (median levels 1-2) */
+#define APT_KERNEL_FINALIZE 6  /* finalize_kernel */
+#define APT_N_KERNELS 7
 int  apt_plan_enable_timing(apt_plan_t* plan, int enable);
 int  apt_plan_kernel_ms(apt_plan_t* plan, float* out_ms /* [APT_N_KERNELS] */);
 
