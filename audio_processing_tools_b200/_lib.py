@@ -17,8 +17,8 @@ CSRC = os.path.join(_PKG, "csrc")
 MAX_MODES, MAX_SOS, N_RAW, N_TD, N_STATS = 8, 4, 21, 5, 8
 ABI_VERSION = 1
 STAGE_FEATURES, STAGE_FULL = 1, 2
-KERNEL_NAMES = ("stft256_kernel", "td_features_kernel", "trk1_kernel", "detect_kernel", "trk2_kernel",
-                "select_kernels", "finalize_kernel")
+KERNEL_NAMES = ("stft256_kernel", "td_features_kernel", "trk1_kernel", "flux_kernel", "base_kernel",
+                "decide_kernels", "trk2_kernel", "db_kernel", "select_kernels", "finalize_kernel")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]

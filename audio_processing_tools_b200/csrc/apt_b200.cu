@@ -53,9 +53,9 @@ struct apt_plan {
     apt_params_t prm;
     DevParams dp;
     int n_clips = 0;
-    std::vector<int64_t> len, samp_off, frame_off, stft_tile_off, td_tile_off, sel_chunk_off;
+    std::vector<int64_t> len, samp_off, frame_off, stft_tile_off, td_tile_off, sel_chunk_off, flux_tile_off;
     int64_t nS = 0, nF = 0;
-    DevBuf<int64_t> d_samp_off, d_frame_off, d_stft_tile_off, d_td_tile_off, d_sel_chunk_off;
+    DevBuf<int64_t> d_samp_off, d_frame_off, d_stft_tile_off, d_td_tile_off, d_sel_chunk_off, d_flux_tile_off;
     // tables
     DevBuf<double> d_win64; DevBuf<cx<double>> d_tw128_64, d_tw256_64;
     DevBuf<float> d_win32;  DevBuf<cx<float>> d_tw128_32, d_tw256_32;
@@ -65,8 +65,8 @@ struct apt_plan {
     int td_ns = 0;
     size_t td_smem = 0;
     // scratch
-    DevBuf<float> d_Pband, d_db, d_td, d_mf;
-    DevBuf<double> d_dbsum;   // [n_clips][K] per-lane sums of the dB plane
+    DevBuf<float> d_Pband, d_db, d_td, d_mf, d_nl, d_nl_all;
+    DevBuf<double> d_dbsum;   // [select chunks] float64 sums of the dB plane
     Trk1Tab tab_modes, tab_all;   // pass-1 lane tables: mode bins only / every band bin (debug planes)
     int mf_stride = 8;
     DevBuf<SelState> d_sel;
@@ -252,7 +252,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     // offsets
     pl->len.assign(clip_len, clip_len + n_clips);
     pl->samp_off.assign(n_clips + 1, 0); pl->frame_off.assign(n_clips + 1, 0);
-    pl->stft_tile_off.assign(n_clips + 1, 0); pl->td_tile_off.assign(n_clips + 1, 0); pl->sel_chunk_off.assign(n_clips + 1, 0);
+    pl->stft_tile_off.assign(n_clips + 1, 0); pl->td_tile_off.assign(n_clips + 1, 0); pl->sel_chunk_off.assign(n_clips + 1, 0); pl->flux_tile_off.assign(n_clips + 1, 0);
     for (int c = 0; c < n_clips; c++) {
         const int64_t N = clip_len[c];
         if (N < p->n_fft || N <= d.padlen + 1) { delete pl; return fail(ctx, -28, "clip %d too short (%lld samples)", c, (long long)N); }
@@ -263,6 +263,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         pl->stft_tile_off[c + 1] = pl->stft_tile_off[c] + (T + STFT_TF - 1) / STFT_TF;
         pl->td_tile_off[c + 1] = pl->td_tile_off[c] + std::max<int64_t>(1, (Tloc + TD_FT - 1) / TD_FT);
         pl->sel_chunk_off[c + 1] = pl->sel_chunk_off[c] + (T * K + SEL_CHUNK - 1) / SEL_CHUNK;
+        pl->flux_tile_off[c + 1] = pl->flux_tile_off[c] + (T + FLUX_FT - 1) / FLUX_FT;
     }
     pl->nS = pl->samp_off[n_clips]; pl->nF = pl->frame_off[n_clips];
     if (pl->stft_tile_off[n_clips] > 0x7fffffffLL || pl->td_tile_off[n_clips] > 0x7fffffffLL) { delete pl; return fail(ctx, -29, "batch too large for one launch"); }
@@ -273,6 +274,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     PL_OK(upload(pl->d_stft_tile_off, pl->stft_tile_off));
     PL_OK(upload(pl->d_td_tile_off, pl->td_tile_off));
     PL_OK(upload(pl->d_sel_chunk_off, pl->sel_chunk_off));
+    PL_OK(upload(pl->d_flux_tile_off, pl->flux_tile_off));
 
     // FFT tables
     {
@@ -316,7 +318,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     PL_OK(pl->d_Pband.alloc((size_t)pl->nF * K));
     PL_OK(pl->d_db.alloc((size_t)pl->nF * K));
     PL_OK(pl->d_td.alloc((size_t)pl->nF * APT_N_TD_FEATURES));
-    PL_OK(pl->d_dbsum.alloc((size_t)n_clips * K));
+    PL_OK(pl->d_dbsum.alloc((size_t)pl->sel_chunk_off[n_clips]));
     pl->mf_stride = (p->n_modes + 1 <= 8) ? 8 : 16;
     PL_OK(pl->d_mf.alloc((size_t)pl->nF * pl->mf_stride));
     {   // pass-1 lane tables
@@ -333,15 +335,18 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
                 tm.lane_bin[nl++] = (unsigned char)(lo + i);
             }
         }
-        tm.n_lanes = nl;
-        ta.n_lanes = K;
+        tm.n_lanes = nl; tm.nls = std::max(8, (nl + 7) / 8 * 8);
+        ta.n_lanes = K;  ta.nls = (K + 7) / 8 * 8;
+        PL_OK(pl->d_nl.alloc((size_t)pl->nF * tm.nls));   // the all-bins plane (debug outputs) is allocated on first use
         for (int k = 0; k < K; k++) ta.lane_bin[k] = (unsigned char)k;
     }
     PL_OK(pl->d_sel.alloc(n_clips));
     PL_OK(pl->d_hist.alloc((size_t)n_clips * 2 * SEL_BINS));
     PL_OK(pl->d_counter.alloc(64));
-    pl->scratch_bytes = sizeof(float) * ((size_t)pl->nF * K * 2 + (size_t)pl->nF * APT_N_TD_FEATURES + (size_t)pl->nF * pl->mf_stride) +
-                        (size_t)n_clips * (sizeof(double) * K + sizeof(SelState) + 2 * SEL_BINS * sizeof(uint32_t));
+    pl->scratch_bytes = sizeof(float) * ((size_t)pl->nF * K * 2 + (size_t)pl->nF * APT_N_TD_FEATURES + (size_t)pl->nF * pl->mf_stride +
+                                         (size_t)pl->nF * pl->tab_modes.nls) +
+                        sizeof(double) * (size_t)pl->sel_chunk_off[n_clips] +
+                        (size_t)n_clips * (sizeof(SelState) + 2 * SEL_BINS * sizeof(uint32_t));
     PL_OK(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
     PL_OK(cudaStreamCreateWithFlags(&pl->s_comp, cudaStreamNonBlocking));
     PL_OK(cudaStreamCreateWithFlags(&pl->s_back, cudaStreamNonBlocking));
@@ -462,50 +467,72 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     e = launch_td<PCM>(pl, b, pcm, to, st);
     if (e != cudaSuccess) return fail(ctx, -11, "td launch failed: %s", cudaGetErrorString(e));
 
+    const int64_t fbeg = pl->frame_off[clip0], fend = pl->frame_off[clip0 + n_clips];
     // tracker pass 1 on the mode bins (every band bin when one of its planes is requested)
+    const bool dbg = out->det_noise_psd || out->det_noise_lag || out->D;
+    const Trk1Tab& tab = dbg ? pl->tab_all : pl->tab_modes;
+    if (dbg && !pl->d_nl_all.p) CUDA_OK(ctx, pl->d_nl_all.alloc((size_t)pl->nF * pl->tab_all.nls));
+    float* nl_plane = dbg ? pl->d_nl_all.p : pl->d_nl.p;
     pl->mark(APT_KERNEL_TRK1, st);
-    {
-        const bool dbg = out->det_noise_psd || out->det_noise_lag || out->D;
-        const Trk1Tab& tab = dbg ? pl->tab_all : pl->tab_modes;
+    if (d.use_norm) {
         Trk1IO io;
-        io.P_band = pl->d_Pband.p; io.mf = pl->d_mf.p; io.stride = pl->mf_stride;
-        io.det_noise_psd = out->det_noise_psd; io.det_noise_lag = out->det_noise_lag; io.D = out->D;
-        io.mode_flux = out->mode_flux; io.nF = pl->nF;
-        const int nt = std::max(32, ((tab.n_lanes + 31) / 32) * 32);
-        trk1_kernel<<<n_clips, nt, 0, st>>>(pl->dp, b, tab, io);
+        io.P_band = pl->d_Pband.p; io.NL = nl_plane; io.det_noise_psd = out->det_noise_psd; io.nF = pl->nF;
+        const int64_t lanes = (int64_t)n_clips * tab.n_lanes;
+        trk1_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, tab, io);
         pl->last_launches++;
         CUDA_OK(ctx, cudaGetLastError());
     }
-    // baselines, decision, labels, events
-    pl->mark(APT_KERNEL_DETECT, st);
+    pl->mark(APT_KERNEL_FLUX, st);
     {
-        DetIO io;
+        FluxIO io;
+        io.P_band = pl->d_Pband.p; io.NL = nl_plane; io.nls = tab.nls; io.mf = pl->d_mf.p; io.stride = pl->mf_stride;
+        io.det_noise_lag = out->det_noise_lag; io.D = out->D; io.mode_flux = out->mode_flux; io.nF = pl->nF;
+        const int64_t tiles = pl->flux_tile_off[clip0 + n_clips] - pl->flux_tile_off[clip0];
+        flux_kernel<<<(unsigned)tiles, 256, 0, st>>>(pl->dp, b, pl->d_flux_tile_off.p, tab, io);
+        pl->last_launches++;
+        CUDA_OK(ctx, cudaGetLastError());
+    }
+    // float64 baselines + normalisation, then the decision and the event lists
+    pl->mark(APT_KERNEL_BASE, st);
+    {
+        const int64_t lanes = (int64_t)n_clips * (d.M + 1);
+        base_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, pl->d_mf.p, pl->mf_stride);
+        pl->last_launches++;
+        CUDA_OK(ctx, cudaGetLastError());
+    }
+    pl->mark(APT_KERNEL_DECIDE, st);
+    {
+        DecIO io;
         io.mf = pl->d_mf.p; io.stride = pl->mf_stride; io.td = to.td;
         io.frame_class = out->frame_class; io.rain_conf = out->rain_conf; io.noise_conf = out->noise_conf;
-        io.event_idx = out->event_idx; io.event_count = out->event_count;
         io.norm_flux = out->norm_flux; io.score = out->score; io.gate = out->gate; io.nF = pl->nF;
-        const int G = 32 / (d.M + 1);
-        const int warps = (n_clips + G - 1) / G;
-        detect_kernel<<<(warps + DET_WARPS - 1) / DET_WARPS, DET_WARPS * 32, 0, st>>>(pl->dp, b, io);
-        pl->last_launches++;
+        decide_kernel<<<(unsigned)((fend - fbeg + 255) / 256), 256, 0, st>>>(pl->dp, fbeg, fend, io);
+        compact_kernel<<<(n_clips * 32 + 127) / 128, 128, 0, st>>>(b, out->frame_class, out->event_idx, out->event_count);
+        pl->last_launches += 2;
         CUDA_OK(ctx, cudaGetLastError());
     }
-    // tracker pass 2 + noise-floor dB plane + level-0 histogram, then the exact median
+    // tracker pass 2, noise-floor dB plane + level-0 histogram, then the exact median
     uint32_t* hist = pl->d_hist.p;
     const size_t hist_bytes = sizeof(uint32_t) * (size_t)n_clips * 2 * SEL_BINS;
     if (!d.suppressor_bypass) {
         pl->mark(APT_KERNEL_TRK2, st);
+        float* n2_plane = out->noise_psd ? out->noise_psd : pl->d_db.p;   // dB plane is produced in place otherwise
+        {
+            Trk2IO io;
+            io.P_band = pl->d_Pband.p; io.frame_class = out->frame_class; io.N2 = n2_plane; io.nF = pl->nF;
+            const int64_t lanes = (int64_t)n_clips * d.K;
+            trk2_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, io);
+            pl->last_launches++;
+            CUDA_OK(ctx, cudaGetLastError());
+        }
+        pl->mark(APT_KERNEL_DB, st);
+        const int64_t chunks = pl->sel_chunk_off[clip0 + n_clips] - pl->sel_chunk_off[clip0];
         CUDA_OK(ctx, cudaMemsetAsync(hist + (size_t)clip0 * 2 * SEL_BINS, 0, hist_bytes, st));
         select_init_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(b, d.K, pl->d_sel.p);
-        Trk2IO io;
-        io.P_band = pl->d_Pband.p; io.frame_class = out->frame_class; io.noise_psd = out->noise_psd;
-        io.db_plane = pl->d_db.p; io.db_lane_sum = pl->d_dbsum.p; io.hist = hist; io.nF = pl->nF;
-        const int64_t lanes = (int64_t)n_clips * d.K;
-        trk2_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, io);
+        db_kernel<<<(unsigned)chunks, 256, 0, st>>>(pl->dp, b, n2_plane, pl->d_db.p, pl->d_sel_chunk_off.p, hist, pl->d_dbsum.p);
         pl->last_launches += 2;
         CUDA_OK(ctx, cudaGetLastError());
         pl->mark(APT_KERNEL_SELECT, st);
-        const int64_t chunks = pl->sel_chunk_off[clip0 + n_clips] - pl->sel_chunk_off[clip0];
         for (int level = 0; level < 3; level++) {
             if (level > 0) {
                 CUDA_OK(ctx, cudaMemsetAsync(hist + (size_t)clip0 * 2 * SEL_BINS, 0, hist_bytes, st));
@@ -518,7 +545,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         CUDA_OK(ctx, cudaGetLastError());
     }
     pl->mark(APT_KERNEL_FINALIZE, st);
-    finalize_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(pl->dp, b, pl->d_sel.p, pl->d_dbsum.p, out->event_count, out->clip_stats, 0);
+    finalize_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(pl->dp, b, pl->d_sel.p, pl->d_dbsum.p, pl->d_sel_chunk_off.p, out->event_count, out->clip_stats, 0);
     pl->last_launches++;
     CUDA_OK(ctx, cudaGetLastError());
     pl->mark(-1, st);

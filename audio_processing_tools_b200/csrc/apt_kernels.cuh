@@ -3,9 +3,12 @@
 // Kernel map (DESIGN.md has the data layout and rooflines):
 //   stft256_kernel      K1+K2+K3  PCM -> frames -> Hann -> rFFT-256 -> power -> band planes
 //   td_features_kernel  K6+K7     PCM -> zero-phase SOS prefilter -> crest / kurtosis / block features
-//   trk1_kernel         K4+K5     tracker pass 1 on the mode bins, dB normalisation, flux, per-mode sums
-//   detect_kernel       K8+K9     float64 baselines, decision, labels, event compaction
-//   trk2_kernel         K4+K9     tracker pass 2 gated by the labels, noise-floor dB plane + sums
+//   trk1_kernel         K4        tracker pass 1 on the mode bins (serial in time)
+//   flux_kernel         K5        dB normalisation, flux, per-mode sums (parallel)
+//   base_kernel         K8        float64 quantile baselines + normalisation (serial in time)
+//   decide/compact      K8+K9     decision, labels, confidences; ordered event indices
+//   trk2_kernel         K4        tracker pass 2 gated by the labels (serial in time)
+//   db_kernel           K9        noise-floor dB plane, sums, level-0 histogram (parallel)
 //   select_*            K9        exact median of the noise-floor dB plane (3-level radix select)
 //   finalize_kernel     K9        clip statistics rows
 //
@@ -730,43 +733,47 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4+K5+K8+K9: the per-clip time recursions as three independent streaming kernels.
+// K4+K5+K8+K9: the per-clip time recursions.
 //
-// The recursions are sequential in time but independent across (clip, bin) / (clip, row) lanes,
-// so each is its own kernel whose warps never wait on one another (no CTA-wide barriers on the
-// recurrence path); the planes between them travel through HBM/L2, which this pipeline barely
-// uses (issue-bound, not bandwidth-bound):
-//   trk1_kernel    lane = (clip, mode bin): noise-PSD tracker pass 1 -> lagged dB normalisation ->
-//                  positive t-vs-(t-2) flux -> per-mode sums in numpy order  => mf[nF][stride]
-//   detect_kernel  lane = (clip, row): float64 quantile baselines -> normalised flux -> TD gate ->
-//                  fixed-band decision (one ballot) -> labels, confidences, event compaction
-//   trk2_kernel    lane = (clip, bin): tracker pass 2 gated by the labels -> noise-floor dB plane,
-//                  per-lane dB sums, level-0 histogram of the median select
+// Everything that is sequential in time is kept in three SERIAL kernels whose instruction streams
+// hold only the loop-carried arithmetic (their run time is chain latency x frames, so every extra
+// instruction costs wall time), and everything element-wise around them runs in fully PARALLEL
+// kernels; the planes in between travel through HBM/L2:
+//   trk1_kernel   serial    lane = (clip, mode bin): noise-PSD tracker pass 1 -> lagged, clamped noise NL
+//   flux_kernel   parallel  (clip, frame tile): dB normalisation, positive t-vs-(t-2) flux, per-mode sums
+//   base_kernel   serial    lane = (clip, row): float64 quantile baselines -> normalised flux (in place)
+//   decide_kernel parallel  frame: TD gate, fixed-band decision, labels and confidences
+//   compact_kernel          warp per clip: ordered event indices + counts
+//   trk2_kernel   serial    lane = (clip, bin): tracker pass 2 gated by the labels -> noise PSD N2
+//   db_kernel     parallel  flat: noise-floor dB plane, its sums, level-0 histogram of the median select
 // ---------------------------------------------------------------------------------------------
 constexpr int SEQ_KMAX = 128;    // operating-band bins supported (n_fft = 256 -> 71)
-constexpr int TRK1_TT = 32;      // frames per tile of trk1 (mode sums are taken per tile)
-constexpr int SEQ_PF = 8;        // frames of register prefetch in the streaming loops
+constexpr int SEQ_PF = 8;        // frames per straight-line group of the serial loops (register prefetch)
 
 struct Tracker {
     float trk, ts, nprev;
 };
 
-// one step of _update_noise_psd_frame for one bin (rain_signal_processor.py:594-666); t > 0
+// one step of _update_noise_psd_frame for one bin (rain_signal_processor.py:594-666); t > 0.  Branch-free.
 __device__ __forceinline__ float tracker_step(const DevParams& p, Tracker& s, float pk, bool allow) {
     const float err = pk - s.trk;
     s.ts = p.trk_alpha * s.ts + p.trk_1m_alpha * fabsf(err);
     const float step = p.trk_eta * f_max(s.ts, p.trk_floor);
     const float delta = (pk >= s.trk) ? p.trk_q * step : p.trk_nq * step;
     const float cand = f_max(s.trk + delta, 0.0f);
-    if (allow) s.trk = cand;
+    s.trk = allow ? cand : s.trk;
     const float raw = s.trk;
-    const double lam = (raw > s.nprev) ? p.ema_up : p.ema_down;
-    double nb = lam * (double)s.nprev + (1.0 - lam) * (double)raw;
-    const double cap = (double)(p.trk_maxr * pk);
-    nb = cap < nb ? cap : nb;
-    nb = nb < 0.0 ? 0.0 : nb;
-    s.nprev = d2f(nb);
-    return s.nprev;
+    const bool up = raw > s.nprev;
+    const double lam = up ? p.ema_up : p.ema_down;
+    const double oml = up ? (1.0 - p.ema_up) : (1.0 - p.ema_down);
+    const double nb = lam * (double)s.nprev + oml * (double)raw;
+    // the reference clamps in float64 before rounding: max(min(nb, cap), 0).  cap and 0 are float32
+    // values and rounding is monotone, so clamping after the rounding gives the same float32.
+    float nf = d2f(nb);
+    nf = f_min(nf, p.trk_maxr * pk);     // (cap < nf) ? cap : nf
+    nf = f_max(nf, 0.0f);
+    s.nprev = nf;
+    return nf;
 }
 __device__ __forceinline__ float tracker_first(const DevParams& p, Tracker& s, float pk) {
     s.trk = f_max(pk, 0.0f);
@@ -775,268 +782,366 @@ __device__ __forceinline__ float tracker_first(const DevParams& p, Tracker& s, f
     return s.nprev;
 }
 
-// Lane table of trk1: which band bins are tracked in pass 1 (the mode bins; every band bin when a
-// debug plane of pass 1 is requested) and where each mode's lanes start.
+// Lane table of pass 1: which band bins are tracked (the mode bins; every band bin when a debug plane
+// of pass 1 is requested) and where each mode's lanes start.
 struct Trk1Tab {
     int n_lanes;
+    int nls;                        // row stride of the NL plane (n_lanes rounded up to 8)
     int mode_l0[APT_MAX_MODES];     // first lane of mode m (its bins are consecutive lanes)
     int mode_n[APT_MAX_MODES];      // bins of mode m
     unsigned char lane_bin[SEQ_KMAX];  // band-relative bin of lane j
 };
 
+// Serial-lane bookkeeping shared by the three serial kernels: global lane -> (clip, sub-lane).  Lanes past
+// the end of the batch repeat the last real lane's arithmetic with their stores switched off, so that
+// every lane of a warp always has a valid clip (no divergence in the main loop).
+struct SerialLane {
+    int c, sub, T, Tmin, Tmax;
+    int64_t f0;
+    bool store;
+};
+__device__ __forceinline__ SerialLane serial_lane(const Batch& b, int per_clip) {
+    SerialLane L;
+    const int64_t total = (int64_t)b.n_clips * per_clip;
+    int64_t gl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    L.store = gl < total;
+    if (gl >= total) gl = total - 1;
+    const int ci = (int)(gl / per_clip);
+    L.sub = (int)(gl - (int64_t)ci * per_clip);
+    L.c = b.clip0 + ci;
+    L.f0 = __ldg(b.frame_off + L.c);
+    L.T = (int)(__ldg(b.frame_off + L.c + 1) - L.f0);
+    int mn = L.T, mx = L.T;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    L.Tmin = mn; L.Tmax = mx;
+    return L;
+}
+
 struct Trk1IO {
     const float* P_band;   // [nF][K]
-    float* mf;             // [nF][stride]: cols 0..M-1 raw per-mode flux, col M weighted total
-    int stride;
-    float* det_noise_psd; float* det_noise_lag; float* D;   // optional [nF][K]
-    float* mode_flux;      // optional [M][nF]
+    float* NL;             // [nF][nls] lagged, clamped pass-1 noise of the tracked bins
+    float* det_noise_psd;  // optional [nF][K]
     int64_t nF;
 };
 
-// One CTA per clip; blockDim = n_lanes rounded up to a warp.
-__global__ void __launch_bounds__(SEQ_KMAX) trk1_kernel(const __grid_constant__ DevParams p, Batch b,
-                                                        const __grid_constant__ Trk1Tab tab, Trk1IO io) {
-    __shared__ float s_flux[TRK1_TT][SEQ_KMAX + 1];
-    __shared__ float s_ltab[64];
-    const int tid = threadIdx.x;
-    const int c = b.clip0 + blockIdx.x;
-    const int64_t f0 = __ldg(b.frame_off + c);
-    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
-    const int K = p.K, M = p.M;
-    for (int i = tid; i < 64; i += blockDim.x) s_ltab[i] = u2f(kSvmlLog10TabDev[i]);
-    __syncthreads();
-    const bool lane_on = tid < tab.n_lanes;
-    const int kb = lane_on ? tab.lane_bin[tid] : 0;
-    const float* Pk = io.P_band + f0 * K + kb;
+__global__ void __launch_bounds__(128) trk1_kernel(const __grid_constant__ DevParams p, Batch b,
+                                                   const __grid_constant__ Trk1Tab tab, Trk1IO io) {
+    const SerialLane L = serial_lane(b, tab.n_lanes);
+    const int K = p.K, nls = tab.nls;
+    const int kb = tab.lane_bin[L.sub];
+    const float* Pk = io.P_band + L.f0 * K + kb;
+    float* NLk = io.NL + L.f0 * nls + L.sub;
+    float* N1k = io.det_noise_psd ? io.det_noise_psd + L.f0 * K + kb : nullptr;
+    const int T = L.T;
     Tracker tr = {0, 0, 0};
-    float dm1 = 0.0f, dm2 = 0.0f;
+    // frame 0 (rain_signal_processor.py:700-703): N = P
+    {
+        const float pk = __ldg(Pk);
+        const float n1 = tracker_first(p, tr, pk);
+        if (L.store) { NLk[0] = f_min(n1, p.trk_maxr * pk); if (N1k) N1k[0] = n1; }
+    }
     float pbuf[SEQ_PF];
 #pragma unroll
-    for (int u = 0; u < SEQ_PF; u++) pbuf[u] = (lane_on && u < T) ? __ldg(Pk + (size_t)u * K) : 0.0f;
-
-    for (int t0 = 0; t0 < T; t0 += TRK1_TT) {
-        const int nt = min(TRK1_TT, T - t0);
-        if (lane_on) {
-            for (int tb = 0; tb < nt; tb += SEQ_PF) {
-                float pcur[SEQ_PF];
+    for (int u = 0; u < SEQ_PF; u++) pbuf[u] = __ldg(Pk + (size_t)min(1 + u, T - 1) * K);
+    int t = 1;
+    for (; t + SEQ_PF <= L.Tmin; t += SEQ_PF) {
+        float pc[SEQ_PF];
 #pragma unroll
-                for (int u = 0; u < SEQ_PF; u++) pcur[u] = pbuf[u];
-                const int tn = t0 + tb + SEQ_PF;   // first frame of the next group
+        for (int u = 0; u < SEQ_PF; u++) pc[u] = pbuf[u];
 #pragma unroll
-                for (int u = 0; u < SEQ_PF; u++) pbuf[u] = (tn + u < T) ? __ldg(Pk + (size_t)(tn + u) * K) : 0.0f;
+        for (int u = 0; u < SEQ_PF; u++) pbuf[u] = __ldg(Pk + (size_t)min(t + SEQ_PF + u, T - 1) * K);
 #pragma unroll
-                for (int u = 0; u < SEQ_PF; u++) {
-                    const int tt = tb + u;
-                    if (tt < nt) {
-                        // tracker pass 1 + detector normalisation (rain_signal_processor.py:862-888)
-                        const int tg = t0 + tt;
-                        const float pk = pcur[u];
-                        float dval;
-                        if (p.use_norm) {
-                            const float nprev = tr.nprev;   // N1[t-1]
-                            const float n1 = (tg == 0) ? tracker_first(p, tr, pk) : tracker_step(p, tr, pk, true);
-                            float nl = (tg == 0) ? n1 : nprev;
-                            nl = f_min(nl, p.trk_maxr * pk);
-                            if (p.ratio_db)
-                                dval = 10.0f * svml_log10f(f_div(pk, nl + p.eps32) + p.eps32, s_ltab);
-                            else
-                                dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab) - 10.0f * svml_log10f(nl + p.eps32, s_ltab);
-                            if (io.det_noise_psd) io.det_noise_psd[(f0 + tg) * K + kb] = n1;
-                            if (io.det_noise_lag) io.det_noise_lag[(f0 + tg) * K + kb] = nl;
-                        } else {
-                            dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab);
-                        }
-                        if (io.D) io.D[(f0 + tg) * K + kb] = dval;
-                        // positive t-vs-(t-2) flux, lane-local history (rain_frame_classifier.py:721-746)
-                        float fx = 0.0f;
-                        if (tg >= 2) { const float d = dval - dm2; fx = d > 0.0f ? d : (d != d ? d : 0.0f); }
-                        dm2 = dm1; dm1 = dval;
-                        s_flux[tt][tid] = fx;
-                    }
-                }
-            }
+        for (int u = 0; u < SEQ_PF; u++) {
+            const float pk = pc[u];
+            const float nprev = tr.nprev;                       // N1[t-1]
+            const float n1 = tracker_step(p, tr, pk, true);
+            const float nl = f_min(nprev, p.trk_maxr * pk);     // lag by one frame, clamp (:874-882)
+            if (L.store) { NLk[(size_t)(t + u) * nls] = nl; if (N1k) N1k[(size_t)(t + u) * K] = n1; }
         }
-        __syncthreads();
-        // per-mode sums of the flux row in numpy order + float64 weighted total (:749-759)
-        for (int tt = tid; tt < nt; tt += blockDim.x) {
-            const float* fr = s_flux[tt];
-            const int tg = t0 + tt;
-            float* row = io.mf + (f0 + tg) * io.stride;
-            double tot = 0.0;
-            for (int m = 0; m < M; m++) {
-                float s = 0.0f;
-                const int lo = tab.mode_l0[m], n = tab.mode_n[m];
-                if (tg >= 2 && n > 0) {
-                    if (n < 8) {
-                        float r = -0.0f;
-                        for (int i = 0; i < n; i++) r += fr[lo + i];
-                        s = 0.0f + r;
-                    } else {
-                        s = 0.0f + np_pairwise<float>([&](int kk) { return fr[kk]; }, lo, n);
-                    }
-                }
-                row[m] = s;
-                tot += p.mode_w[m] * (double)s;
-                if (io.mode_flux) io.mode_flux[(int64_t)m * io.nF + f0 + tg] = s;
-            }
-            row[M] = (tg >= 2) ? d2f(tot) : 0.0f;
+    }
+    for (; t < L.Tmax; t++) {   // ragged tail
+        if (t < T) {
+            const float pk = __ldg(Pk + (size_t)t * K);
+            const float nprev = tr.nprev;
+            const float n1 = tracker_step(p, tr, pk, true);
+            const float nl = f_min(nprev, p.trk_maxr * pk);
+            if (L.store) { NLk[(size_t)t * nls] = nl; if (N1k) N1k[(size_t)t * K] = n1; }
         }
-        __syncthreads();
     }
 }
 
-struct DetIO {
-    const float* mf; int stride;     // [nF][stride]
+struct FluxIO {
+    const float* P_band;   // [nF][K]
+    const float* NL; int nls;
+    float* mf; int stride; // [nF][stride]: cols 0..M-1 raw per-mode flux, col M weighted total
+    float* det_noise_lag; float* D;   // optional [nF][K]
+    float* mode_flux;      // optional [M][nF]
+    int64_t nF;
+};
+constexpr int FLUX_FT = 64;   // frames per tile
+
+__global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevParams p, Batch b,
+                                                   const int64_t* __restrict__ tile_off,
+                                                   const __grid_constant__ Trk1Tab tab, FluxIO io) {
+    __shared__ float s_D[FLUX_FT + 2][SEQ_KMAX + 1];
+    __shared__ float s_mf[FLUX_FT][APT_MAX_MODES];
+    __shared__ float s_ltab[64];
+    const int tid = threadIdx.x;
+    int64_t tile_in_clip;
+    const int c = tile_clip(b, tile_off, tile_in_clip);
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int t0 = (int)tile_in_clip * FLUX_FT, nt = min(FLUX_FT, T - t0);
+    const int K = p.K, M = p.M, nl_ = tab.n_lanes;
+    if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
+    __syncthreads();
+    // detector input D = dB above the lagged noise (rain_signal_processor.py:859-888) for frames t0-2 .. t0+nt-1
+    for (int idx = tid; idx < (nt + 2) * nl_; idx += 256) {
+        const int r = idx / nl_, j = idx - r * nl_;
+        const int tg = t0 - 2 + r;
+        if (tg < 0) continue;
+        const int kb = tab.lane_bin[j];
+        const float pk = __ldg(io.P_band + (f0 + tg) * K + kb);
+        float dval, nl = 0.0f;
+        if (p.use_norm) {
+            nl = __ldg(io.NL + (f0 + tg) * io.nls + j);
+            if (p.ratio_db)
+                dval = 10.0f * svml_log10f(f_div(pk, nl + p.eps32) + p.eps32, s_ltab);
+            else
+                dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab) - 10.0f * svml_log10f(nl + p.eps32, s_ltab);
+        } else {
+            dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab);
+        }
+        s_D[r][j] = dval;
+        if (r >= 2) {
+            if (io.D) io.D[(f0 + tg) * K + kb] = dval;
+            if (io.det_noise_lag) io.det_noise_lag[(f0 + tg) * K + kb] = nl;
+        }
+    }
+    __syncthreads();
+    // positive t-vs-(t-2) flux summed per mode in numpy order (rain_frame_classifier.py:721-759)
+    for (int idx = tid; idx < nt * M; idx += 256) {
+        const int m = idx / nt, tt = idx - m * nt;
+        const int tg = t0 + tt;
+        const int lo = tab.mode_l0[m], n = tab.mode_n[m];
+        const float* d2 = s_D[tt + 2];
+        const float* d0 = s_D[tt];
+        auto fx = [&](int l) { const float d = d2[l] - d0[l]; return d > 0.0f ? d : (d != d ? d : 0.0f); };
+        float s = 0.0f;
+        if (tg >= 2 && n > 0) {
+            if (n < 8) {
+                float r = -0.0f;
+                for (int i = 0; i < n; i++) r += fx(lo + i);
+                s = 0.0f + r;
+            } else {
+                s = 0.0f + np_pairwise<float>(fx, lo, n);
+            }
+        }
+        s_mf[tt][m] = s;
+        if (io.mode_flux) io.mode_flux[(int64_t)m * io.nF + f0 + tg] = s;
+    }
+    __syncthreads();
+    for (int tt = tid; tt < nt; tt += 256) {
+        const int tg = t0 + tt;
+        float* row = io.mf + (f0 + tg) * io.stride;
+        double tot = 0.0;
+        for (int m = 0; m < M; m++) { row[m] = s_mf[tt][m]; tot += p.mode_w[m] * (double)s_mf[tt][m]; }
+        row[M] = (tg >= 2) ? d2f(tot) : 0.0f;   // weighted total accumulated in a Python double (:755-759)
+    }
+}
+
+// lane = (clip, row): row 0 follows the weighted total flux (column M), row r >= 1 follows mode r-1.
+// causal_stochastic_low_quantile_baseline in float64 (rain_frame_classifier.py:31-82) and the
+// normalisation max(x - b, 0) / (b + norm_min) (:874-893); the column is overwritten with the result.
+__device__ __forceinline__ float baseline_step(const DevParams& p, double& bl_base, double& bl_scale, float xf, float ffloor) {
+    const double xt = (double)xf;
+    float ob = d2f(bl_base);
+    if (isnan(ob) || isinf(ob)) ob = ffloor;
+    ob = f_max(ob, ffloor);
+    const double err = xt - bl_base;
+    bl_scale = p.bl_alpha * bl_scale + (1.0 - p.bl_alpha) * fabs(err);
+    const double step = p.bl_eta * (bl_scale > p.bl_floor ? bl_scale : p.bl_floor);
+    const double delta = (xt >= bl_base) ? p.bl_q * step : -(1.0 - p.bl_q) * step;
+    const double nb = bl_base + delta;
+    bl_base = nb > p.bl_floor ? nb : p.bl_floor;
+    const float ex = f_max(xf - ob, 0.0f);
+    float sc = ex;
+    if (p.norm_enable) {
+        // 0 / den is 0 for the finite positive denominators that occur here; dividing 1 instead keeps
+        // __fdiv_rn off its slow path (a zero numerator is the common case)
+        // (0 or NaN) / den ends up 0 after the nan_to_num below either way
+        const bool pos = ex > 0.0f;
+        const float q = f_div(pos ? ex : 1.0f, ob + p.norm_min);
+        sc = pos ? q : 0.0f;
+    }
+    if (isnan(sc) || isinf(sc)) sc = 0.0f;
+    return sc;
+}
+
+__global__ void __launch_bounds__(128) base_kernel(const __grid_constant__ DevParams p, Batch b, float* mf, int stride) {
+    const int M = p.M;
+    const SerialLane L = serial_lane(b, M + 1);
+    const int col = (L.sub == 0) ? M : L.sub - 1;
+    float* xs = mf + L.f0 * stride + col;
+    const int T = L.T;
+    const float ffloor = d2f(p.bl_floor);
+    double bl_base, bl_scale;
+    {
+        const double x0 = (double)__ldg(xs);
+        bl_base = x0 > p.bl_floor ? x0 : p.bl_floor;
+        bl_scale = fabs(x0) > p.bl_floor ? fabs(x0) : p.bl_floor;
+    }
+    float xbuf[SEQ_PF];
+#pragma unroll
+    for (int u = 0; u < SEQ_PF; u++) xbuf[u] = __ldg(xs + (size_t)min(u, T - 1) * stride);
+    int t = 0;
+    for (; t + SEQ_PF <= L.Tmin; t += SEQ_PF) {
+        float xc[SEQ_PF];
+#pragma unroll
+        for (int u = 0; u < SEQ_PF; u++) xc[u] = xbuf[u];
+#pragma unroll
+        for (int u = 0; u < SEQ_PF; u++) xbuf[u] = __ldg(xs + (size_t)min(t + SEQ_PF + u, T - 1) * stride);
+#pragma unroll
+        for (int u = 0; u < SEQ_PF; u++) {
+            const float sc = baseline_step(p, bl_base, bl_scale, xc[u], ffloor);
+            if (L.store) xs[(size_t)(t + u) * stride] = sc;
+        }
+    }
+    for (; t < L.Tmax; t++) {
+        if (t < T) {
+            const float sc = baseline_step(p, bl_base, bl_scale, __ldg(xs + (size_t)t * stride), ffloor);
+            if (L.store) xs[(size_t)t * stride] = sc;
+        }
+    }
+}
+
+struct DecIO {
+    const float* mf; int stride;     // [nF][stride] normalised flux: cols 0..M-1 modes, col M total score
     const float* td;                 // [5][nF] (crest row 0, kurtosis row 1)
     int8_t* frame_class; float* rain_conf; float* noise_conf;
-    int32_t* event_idx; int32_t* event_count;
     float* norm_flux; float* score; uint8_t* gate;   // optional
     int64_t nF;
 };
 
-constexpr int DET_WARPS = 4;         // warps per CTA (independent of one another)
-constexpr int DET_GMAX = 8;          // clips per warp upper bound (rows per clip >= 4)
+// one thread per frame of the launch's clip range: TD gate + fixed-band decision + labels
+// (rain_frame_classifier.py:230-284, :914-998)
+__global__ void __launch_bounds__(256) decide_kernel(const __grid_constant__ DevParams p, int64_t g0, int64_t g1, DecIO io) {
+    const int64_t g = g0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g1) return;
+    const float* row = io.mf + g * io.stride;
+    const int M = p.M;
+    const float score = __ldg(row + M);
+    const float f0 = __ldg(row + 0), f1 = __ldg(row + 1), f2 = __ldg(row + 2), f3 = __ldg(row + 3);
+    bool gate = __ldg(io.td + g) > p.gate_thr;
+    if (p.has_ku) gate = gate && (__ldg(io.td + io.nF + g) <= p.ku);
+    const float gs = gate ? 1.0f : 0.0f;
+    const float l0 = svml_log1pf(f_max(f0 * gs, 0.0f));
+    const float l1 = svml_log1pf(f_max(f1 * gs, 0.0f));
+    const float l2 = svml_log1pf(f_max(f2 * gs, 0.0f));
+    const float l3 = svml_log1pf(f_max(f3 * gs, 0.0f));
+    const int hits = (l1 >= p.thr1) + (l2 >= p.thr2) + (l3 >= p.thr3);
+    const bool is_rain = (l0 >= p.thr0) && (hits >= max(1, p.min_support));
+    const float rc = is_rain ? 1.0f : 0.0f;
+    float nc = 1.0f - rc;
+    nc = nc < 0.0f ? 0.0f : (nc > 1.0f ? 1.0f : nc);
+    const bool weak = (score * gs) <= p.mf_noise_max;
+    int8_t cls = 1;
+    if (nc >= p.noise_hi && weak && !is_rain) cls = 0;
+    if (is_rain) cls = 2;
+    io.frame_class[g] = cls; io.rain_conf[g] = rc; io.noise_conf[g] = nc;
+    if (io.score) io.score[g] = score;
+    if (io.gate) io.gate[g] = gate ? 1 : 0;
+    if (io.norm_flux)
+        for (int m = 0; m < M; m++) io.norm_flux[(int64_t)m * io.nF + g] = __ldg(row + m);
+}
 
-// lane = (clip, row): row 0 follows the weighted total flux, row r >= 1 follows mode r-1.
-// A warp owns G = 32 / R clips (R = M + 1 rows per clip) and walks them frame by frame.
-__global__ void __launch_bounds__(DET_WARPS * 32) detect_kernel(const __grid_constant__ DevParams p, Batch b, DetIO io) {
-    __shared__ int8_t s_cls[DET_WARPS][DET_GMAX][32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int M = p.M, R = M + 1, G = 32 / R;
-    const int warp = blockIdx.x * DET_WARPS + wib;
-    const int g = lane / R, row = lane - g * R;
-    const int ci = warp * G + g;
-    const bool lane_on = (g < G) && (ci < b.n_clips);
-    const int c = b.clip0 + (lane_on ? ci : 0);
-    const int64_t f0 = lane_on ? __ldg(b.frame_off + c) : 0;
-    const int T = lane_on ? (int)(__ldg(b.frame_off + c + 1) - f0) : 0;
-    int Tmax = T;
+// one warp per clip: ascending clip-local indices of the RAIN frames + their count
+__global__ void __launch_bounds__(128) compact_kernel(Batch b, const int8_t* __restrict__ frame_class,
+                                                      int32_t* __restrict__ event_idx, int32_t* __restrict__ event_count) {
+    const int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (ci >= b.n_clips) return;
+    const int c = b.clip0 + ci;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int8_t* fc = frame_class + f0;
+    int32_t* ev = event_idx + f0;
+    int cnt = 0;
+    constexpr int U = 4;
+    for (int tb = 0; tb < T; tb += 32 * U) {
+        int8_t v[U];
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, d));
-    // geometry of the flush phase: clip gi of this warp, seen from every lane
-    int64_t f0_g[DET_GMAX];
-    int T_g[DET_GMAX], cnt_g[DET_GMAX];
+        for (int u = 0; u < U; u++) { const int t = tb + u * 32 + lane; v[u] = t < T ? __ldg(fc + t) : (int8_t)0; }
 #pragma unroll
-    for (int gi = 0; gi < DET_GMAX; gi++) {
-        const int src = min(gi * R, 31);
-        const int64_t f = __shfl_sync(0xffffffffu, f0, src);
-        const int tt = __shfl_sync(0xffffffffu, T, src);
-        f0_g[gi] = f; T_g[gi] = (gi < G) ? tt : 0; cnt_g[gi] = 0;
+        for (int u = 0; u < U; u++) {
+            const bool rain = v[u] == 2;
+            const unsigned m = __ballot_sync(0xffffffffu, rain);
+            if (rain) ev[cnt + __popc(m & ((1u << lane) - 1u))] = tb + u * 32 + lane;
+            cnt += __popc(m);
+        }
     }
-    const int col = (row == 0) ? M : row - 1;
-    const float* xs = io.mf + f0 * io.stride + col;
-    const float* crest = io.td + f0;
-    const float* kurt = io.td + io.nF + f0;
-    const float ffloor = d2f(p.bl_floor);
-    const float thr = row == 1 ? p.thr0 : (row == 2 ? p.thr1 : (row == 3 ? p.thr2 : p.thr3));
-    const unsigned grp_shift = (unsigned)(g * R);
-    double bl_base = 0.0, bl_scale = 0.0;
-    float xbuf[SEQ_PF], cbuf[SEQ_PF], kbuf[SEQ_PF];
+    if (lane == 0) event_count[c] = cnt;
+}
+
+struct Trk2IO {
+    const float* P_band;        // [nF][K]
+    const int8_t* frame_class;  // [nF]
+    float* N2;                  // [nF][K] noise PSD of pass 2
+    int64_t nF;
+};
+
+__global__ void __launch_bounds__(128) trk2_kernel(const __grid_constant__ DevParams p, Batch b, Trk2IO io) {
+    const int K = p.K;
+    const SerialLane L = serial_lane(b, K);
+    const float* Pk = io.P_band + L.f0 * K + L.sub;
+    float* Nk = io.N2 + L.f0 * K + L.sub;
+    const int8_t* fc = io.frame_class + L.f0;
+    const int T = L.T;
+    Tracker tr = {0, 0, 0};
+    // frame 0 counts as an update when it is allowed (rain_signal_processor.py:700-703)
+    int warm = ((0 < p.warm_need) || (__ldg(fc) == 0)) ? 1 : 0;
+    {
+        const float n2 = tracker_first(p, tr, __ldg(Pk));
+        if (L.store) Nk[0] = n2;
+    }
+    float pbuf[SEQ_PF];
+    int8_t ebuf[SEQ_PF];
 #pragma unroll
     for (int u = 0; u < SEQ_PF; u++) {
-        xbuf[u] = (u < T) ? __ldg(xs + (size_t)u * io.stride) : 0.0f;
-        cbuf[u] = (u < T) ? __ldg(crest + u) : 0.0f;
-        kbuf[u] = (p.has_ku && u < T) ? __ldg(kurt + u) : 0.0f;
+        const int ti = min(1 + u, T - 1);
+        pbuf[u] = __ldg(Pk + (size_t)ti * K);
+        ebuf[u] = __ldg(fc + ti);
     }
-    for (int tb = 0; tb < Tmax; tb += SEQ_PF) {
-        float xc[SEQ_PF], cc[SEQ_PF], kc[SEQ_PF];
+    int t = 1;
+    for (; t + SEQ_PF <= L.Tmin; t += SEQ_PF) {
+        float pc[SEQ_PF];
+        int8_t ec[SEQ_PF];
 #pragma unroll
-        for (int u = 0; u < SEQ_PF; u++) { xc[u] = xbuf[u]; cc[u] = cbuf[u]; kc[u] = kbuf[u]; }
-        const int tn = tb + SEQ_PF;
+        for (int u = 0; u < SEQ_PF; u++) { pc[u] = pbuf[u]; ec[u] = ebuf[u]; }
 #pragma unroll
         for (int u = 0; u < SEQ_PF; u++) {
-            const bool ok = tn + u < T;
-            xbuf[u] = ok ? __ldg(xs + (size_t)(tn + u) * io.stride) : 0.0f;
-            cbuf[u] = ok ? __ldg(crest + tn + u) : 0.0f;
-            kbuf[u] = (p.has_ku && ok) ? __ldg(kurt + tn + u) : 0.0f;
+            const int ti = min(t + SEQ_PF + u, T - 1);
+            pbuf[u] = __ldg(Pk + (size_t)ti * K);
+            ebuf[u] = __ldg(fc + ti);
         }
 #pragma unroll
         for (int u = 0; u < SEQ_PF; u++) {
-            const int t = tb + u;
-            if (t >= Tmax) break;   // warp-uniform
-            const bool on = t < T;
-            // ---- causal stochastic low-quantile baseline in float64 (rain_frame_classifier.py:31-82, :873-893)
-            float sc = 0.0f;
-            {
-                const float xf = xc[u];
-                const double xt = (double)xf;
-                if (t == 0) {
-                    bl_base = xt > p.bl_floor ? xt : p.bl_floor;
-                    bl_scale = fabs(xt) > p.bl_floor ? fabs(xt) : p.bl_floor;
-                }
-                float ob = d2f(bl_base);
-                if (isnan(ob) || isinf(ob)) ob = ffloor;
-                ob = f_max(ob, ffloor);
-                const double err = xt - bl_base;
-                bl_scale = p.bl_alpha * bl_scale + (1.0 - p.bl_alpha) * fabs(err);
-                const double step = p.bl_eta * (bl_scale > p.bl_floor ? bl_scale : p.bl_floor);
-                const double delta = (xt >= bl_base) ? p.bl_q * step : -(1.0 - p.bl_q) * step;
-                const double nb = bl_base + delta;
-                bl_base = nb > p.bl_floor ? nb : p.bl_floor;
-                const float ex = f_max(xf - ob, 0.0f);
-                sc = p.norm_enable ? f_div(ex, ob + p.norm_min) : ex;
-                if (isnan(sc) || isinf(sc)) sc = 0.0f;
-            }
-            // ---- TD gate + fixed-band decision (:230-284, :914-998): one ballot per frame
-            bool gate = cc[u] > p.gate_thr;
-            if (p.has_ku) gate = gate && (kc[u] <= p.ku);
-            const float gs = gate ? 1.0f : 0.0f;
-            const float v = sc * gs;
-            bool hit;
-            if (row == 0) hit = v <= p.mf_noise_max;                       // "weak" total flux
-            else hit = (row <= 4) && (svml_log1pf(f_max(v, 0.0f)) >= thr);  // primary / supports
-            const unsigned bal = __ballot_sync(0xffffffffu, hit && on && lane_on);
-            const unsigned bits = bal >> grp_shift;
-            const bool weak = bits & 1u, prim = bits & 2u;
-            const int hits = __popc(bits & 0x1cu);
-            const bool is_rain = prim && (hits >= max(1, p.min_support));
-            const float rc = is_rain ? 1.0f : 0.0f;
-            float nc = 1.0f - rc;
-            nc = nc < 0.0f ? 0.0f : (nc > 1.0f ? 1.0f : nc);
-            int8_t cls = 1;
-            if (nc >= p.noise_hi && weak && !is_rain) cls = 0;
-            if (is_rain) cls = 2;
-            if (on && lane_on) {
-                if (row == 0) {
-                    s_cls[wib][g][t & 31] = cls;
-                    // confidences are functions of the class: written here so a flush only moves labels
-                    if (io.score) io.score[f0 + t] = sc;
-                    if (io.gate) io.gate[f0 + t] = gate ? 1 : 0;
-                } else if (io.norm_flux) {
-                    io.norm_flux[(int64_t)(row - 1) * io.nF + f0 + t] = sc;
-                }
-            }
-            // ---- every 32 frames: coalesced label / confidence stores + event compaction
-            if ((t & 31) == 31 || t == Tmax - 1) {
-                __syncwarp();
-                const int tbase = t & ~31;
-#pragma unroll
-                for (int gi = 0; gi < DET_GMAX; gi++) {
-                    if (gi >= G) break;
-                    const int tl = tbase + lane;
-                    const bool valid = tl < T_g[gi] && tbase < T_g[gi];
-                    int8_t cl = valid ? s_cls[wib][gi][lane] : (int8_t)0;
-                    const bool rain = valid && cl == 2;
-                    if (valid) {
-                        const int64_t gidx = f0_g[gi] + tl;
-                        io.frame_class[gidx] = cl;
-                        io.rain_conf[gidx] = rain ? 1.0f : 0.0f;
-                        io.noise_conf[gidx] = rain ? 0.0f : 1.0f;
-                    }
-                    const unsigned rm = __ballot_sync(0xffffffffu, rain);
-                    if (rain) io.event_idx[f0_g[gi] + cnt_g[gi] + __popc(rm & ((1u << lane) - 1u))] = tl;
-                    cnt_g[gi] += __popc(rm);
-                }
-                __syncwarp();
-            }
+            // tracker pass 2: the quantile tracker only moves on warm-up frames and NOISE frames (:1006-1028)
+            const bool allow = (warm < p.warm_need) || (ec[u] == 0);
+            const float n2 = tracker_step(p, tr, pc[u], allow);
+            warm += allow ? 1 : 0;
+            if (L.store) Nk[(size_t)(t + u) * K] = n2;
         }
     }
-    // event counts: lane gi writes the count of clip gi
-#pragma unroll
-    for (int gi = 0; gi < DET_GMAX; gi++) {
-        if (gi < G && lane == gi) {
-            const int cg = warp * G + gi;
-            if (cg < b.n_clips) io.event_count[b.clip0 + cg] = cnt_g[gi];
+    for (; t < L.Tmax; t++) {
+        if (t < T) {
+            const bool allow = (warm < p.warm_need) || (__ldg(fc + t) == 0);
+            const float n2 = tracker_step(p, tr, __ldg(Pk + (size_t)t * K), allow);
+            warm += allow ? 1 : 0;
+            if (L.store) Nk[(size_t)t * K] = n2;
         }
     }
 }
@@ -1044,10 +1149,10 @@ __global__ void __launch_bounds__(DET_WARPS * 32) detect_kernel(const __grid_con
 // ---------------------------------------------------------------------------------------------
 // exact median of the dB plane per clip: 3-level MSD radix select on order-preserving keys.
 // Two ranks are selected at once (lower / upper middle of an even count).  Level 0 (bits 31..21) is
-// histogrammed by trk2_kernel while it produces the plane; levels 1 and 2 re-read it as a flat array.
+// histogrammed by db_kernel while it produces the plane; levels 1 and 2 re-read it as a flat array.
 // ---------------------------------------------------------------------------------------------
 constexpr int SEL_BINS = 2048;
-constexpr int SEL_CHUNK = 1 << 16;   // plane elements per CTA of select_hist_kernel
+constexpr int SEL_CHUNK = 1 << 16;   // plane elements per CTA of db_kernel / select_hist_kernel
 struct SelState {
     uint32_t prefix[2];
     int64_t rank[2];
@@ -1060,84 +1165,69 @@ __device__ __forceinline__ float key_db(uint32_t k) {
     return u2f((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-struct Trk2IO {
-    const float* P_band;        // [nF][K]
-    const int8_t* frame_class;  // [nF]
-    float* noise_psd;           // optional [nF][K]
-    float* db_plane;            // [nF][K] noise-floor dB (input of the median select)
-    double* db_lane_sum;        // [plan clips][K] per-lane sums of the dB plane
-    uint32_t* hist;             // [plan clips][2][SEL_BINS]: copy 0 receives the level-0 histogram
-    int64_t nF;
-};
-
-// lane = (clip, bin), packed densely over warps; warps are independent.
-__global__ void __launch_bounds__(128) trk2_kernel(const __grid_constant__ DevParams p, Batch b, Trk2IO io) {
+// noise-floor dB plane 10*log10(N2 + eps) (rain_signal_processor.py:1286-1298) over one chunk of a clip's
+// flat plane; the plane may be produced in place.  Also: the chunk's float64 sum (fixed summation order)
+// and the level-0 histogram of the median select.
+__global__ void __launch_bounds__(256) db_kernel(const __grid_constant__ DevParams p, Batch b, const float* N2,
+                                                 float* db, const int64_t* __restrict__ chunk_off,
+                                                 uint32_t* __restrict__ hist, double* __restrict__ chunk_sum) {
+    __shared__ uint32_t s_h[SEL_BINS];
     __shared__ float s_ltab[64];
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_ltab[i] = u2f(kSvmlLog10TabDev[i]);
+    __shared__ double s_part[8];
+    const int tid = threadIdx.x;
+    int64_t chunk_in_clip;
+    const int c = tile_clip(b, chunk_off, chunk_in_clip);
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int64_t n = (__ldg(b.frame_off + c + 1) - f0) * (int64_t)p.K;
+    const int64_t e0 = chunk_in_clip * SEL_CHUNK, e1 = min(n, e0 + (int64_t)SEL_CHUNK);
+    if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
+    for (int i = tid; i < SEL_BINS; i += 256) s_h[i] = 0;
     __syncthreads();
-    const int K = p.K;
-    const int64_t gl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int ci = (int)(gl / K);
-    const bool lane_on = ci < b.n_clips;
-    const int k = (int)(gl - (int64_t)ci * K);
-    const int c = b.clip0 + (lane_on ? ci : 0);
-    const int64_t f0 = lane_on ? __ldg(b.frame_off + c) : 0;
-    const int T = lane_on ? (int)(__ldg(b.frame_off + c + 1) - f0) : 0;
-    int Tmax = T;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, d));
-    const float* Pk = io.P_band + f0 * K + k;
-    const int8_t* fc = io.frame_class + f0;
-    uint32_t* h0 = io.hist + (size_t)c * 2 * SEL_BINS;
-    Tracker tr = {0, 0, 0};
-    int warm = 0;
-    double dbsum = 0.0;
+    const float* src = N2 + f0 * p.K;
+    float* dst = db + f0 * p.K;
+    double acc = 0.0;
     int run_bin = -1;
     uint32_t run_cnt = 0;
-    float pbuf[SEQ_PF];
-    int8_t ebuf[SEQ_PF];
+    constexpr int U = 8;
+    for (int64_t base = e0 + tid; base < e1; base += (int64_t)U * 256) {
+        float v[U];
 #pragma unroll
-    for (int u = 0; u < SEQ_PF; u++) {
-        pbuf[u] = (u < T) ? __ldg(Pk + (size_t)u * K) : 0.0f;
-        ebuf[u] = (u < T) ? __ldg(fc + u) : (int8_t)0;
-    }
-    for (int tb = 0; tb < Tmax; tb += SEQ_PF) {
-        float pc[SEQ_PF];
-        int8_t ec[SEQ_PF];
-#pragma unroll
-        for (int u = 0; u < SEQ_PF; u++) { pc[u] = pbuf[u]; ec[u] = ebuf[u]; }
-        const int tn = tb + SEQ_PF;
-#pragma unroll
-        for (int u = 0; u < SEQ_PF; u++) {
-            const bool ok = tn + u < T;
-            pbuf[u] = ok ? __ldg(Pk + (size_t)(tn + u) * K) : 0.0f;
-            ebuf[u] = ok ? __ldg(fc + tn + u) : (int8_t)0;
+        for (int u = 0; u < U; u++) {
+            const int64_t i = base + (int64_t)u * 256;
+            v[u] = i < e1 ? src[i] : 1.0f;
         }
 #pragma unroll
-        for (int u = 0; u < SEQ_PF; u++) {
-            const int t = tb + u;
-            if (t < T) {
-                // tracker pass 2 gated by the labels (rain_signal_processor.py:1006-1028) + noise-floor dB
-                const float pk = pc[u];
-                const bool allow = (warm < p.warm_need) || (ec[u] == 0);
-                const float n2 = (t == 0) ? tracker_first(p, tr, pk) : tracker_step(p, tr, pk, allow);
-                if (allow) warm++;
-                const float db = 10.0f * svml_log10f(n2 + p.eps32, s_ltab);
-                dbsum += (double)db;
-                const int64_t gi = (f0 + t) * K + k;
-                if (io.noise_psd) io.noise_psd[gi] = n2;
-                io.db_plane[gi] = db;
-                const int bin = (int)(db_key(db) >> 21);
+        for (int u = 0; u < U; u++) {
+            const int64_t i = base + (int64_t)u * 256;
+            if (i < e1) {
+                const float d = 10.0f * svml_log10f(v[u] + p.eps32, s_ltab);
+                dst[i] = d;
+                acc += (double)d;
+                const int bin = (int)(db_key(d) >> 21);
                 if (bin == run_bin) run_cnt++;
                 else {
-                    if (run_cnt) atomicAdd(h0 + run_bin, run_cnt);
+                    if (run_cnt) atomicAdd(&s_h[run_bin], run_cnt);
                     run_bin = bin; run_cnt = 1;
                 }
             }
         }
     }
-    if (run_cnt) atomicAdd(h0 + run_bin, run_cnt);
-    if (lane_on) io.db_lane_sum[(size_t)c * K + k] = dbsum;
+    if (run_cnt) atomicAdd(&s_h[run_bin], run_cnt);
+    // fixed-order block sum: shuffle tree inside the warp, then warps in order
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((tid & 31) == 0) s_part[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; w++) s += s_part[w];
+        chunk_sum[(int64_t)blockIdx.x + __ldg(chunk_off + b.clip0)] = s;
+    }
+    uint32_t* hg = hist + (size_t)c * 2 * SEL_BINS;
+    for (int i = tid; i < SEL_BINS; i += 256) {
+        const uint32_t cnt = s_h[i];
+        if (cnt) atomicAdd(hg + i, cnt);
+    }
 }
 
 __global__ void select_init_kernel(Batch b, int K, SelState* st) {
@@ -1249,7 +1339,8 @@ __global__ void select_scan_kernel(int clip0, int n_clips, int level, SelState* 
 }
 
 __global__ void finalize_kernel(const __grid_constant__ DevParams p, Batch b, const SelState* __restrict__ st,
-                                const double* __restrict__ db_lane_sum, const int32_t* __restrict__ event_count,
+                                const double* __restrict__ chunk_sum, const int64_t* __restrict__ chunk_off,
+                                const int32_t* __restrict__ event_count,
                                 float* __restrict__ stats, int clip_id_base) {
     const int ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= b.n_clips) return;
@@ -1274,8 +1365,8 @@ __global__ void finalize_kernel(const __grid_constant__ DevParams p, Batch b, co
         for (int i = 0; i < 64; i++) lt[i] = u2f(kSvmlLog10TabDev[i]);
         r[6] = r[7] = T > 0 ? 10.0f * svml_log10f(p.eps32, lt) : 0.0f;
     } else {
-        double s = 0.0;   // fixed order over the bins: the mean does not depend on the launch geometry
-        for (int k = 0; k < p.K; k++) s += db_lane_sum[(size_t)c * p.K + k];
+        double s = 0.0;   // chunk sums in chunk order: independent of the launch geometry
+        for (int64_t q = chunk_off[c]; q < chunk_off[c + 1]; q++) s += chunk_sum[q];
         r[6] = d2f(s / ((double)T * (double)p.K));
         const float a = key_db(st[c].prefix[0]), bb = key_db(st[c].prefix[1]);
         r[7] = f_div(a + bb, 2.0f);

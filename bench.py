@@ -223,9 +223,12 @@ def main():
     kernel_bytes = {   # algorithmic bytes each kernel must move in this decomposition
         "stft256_kernel": plan.nS * 2 + nF * K * 4,
         "td_features_kernel": plan.nS * 2 + nF * 4,
-        "trk1_kernel": nF * 26 * 4 + nF * 32,
-        "detect_kernel": nF * 32 + nF * 4 + nF * 9,
+        "trk1_kernel": nF * 26 * 4 + nF * 32 * 4,
+        "flux_kernel": nF * 26 * 4 + nF * 32 * 4 + nF * 32,
+        "base_kernel": 2 * nF * 32,
+        "decide_kernels": nF * 32 + nF * 4 + nF * 9 + nF,
         "trk2_kernel": nF * K * 4 + nF + nF * K * 4,
+        "db_kernel": 2 * nF * K * 4,
         "select_kernels": 2 * nF * K * 4,
         "finalize_kernel": n_clips * 64,
     }

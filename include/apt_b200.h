@@ -168,12 +168,15 @@ int  apt_plan_last_launches(const apt_plan_t* plan);
    returns the accumulated milliseconds per group since the last call (and resets them). */
 #define APT_KERNEL_STFT 0      /* stft256_kernel */
 #define APT_KERNEL_TD 1        /* td_features_kernel */
-#define APT_KERNEL_TRK1 2      /* trk1_kernel: tracker pass 1, dB normalisation, flux, mode sums */
-#define APT_KERNEL_DETECT 3    /* detect_kernel: baselines, decision, labels, events */
-#define APT_KERNEL_TRK2 4      /* trk2_kernel: tracker pass 2, noise-floor dB plane, level-0 histogram */
-#define APT_KERNEL_SELECT 5    /* select_hist/scan (median levels 1-2) */
-#define APT_KERNEL_FINALIZE 6  /* finalize_kernel */
-#define APT_N_KERNELS 7
+#define APT_KERNEL_TRK1 2      /* trk1_kernel: tracker pass 1 (serial in time) */
+#define APT_KERNEL_FLUX 3      /* flux_kernel: dB normalisation, flux, per-mode sums */
+#define APT_KERNEL_BASE 4      /* base_kernel: float64 baselines + normalisation (serial in time) */
+#define APT_KERNEL_DECIDE 5    /* decide_kernel + compact_kernel: labels, confidences, event lists */
+#define APT_KERNEL_TRK2 6      /* trk2_kernel: tracker pass 2 (serial in time) */
+#define APT_KERNEL_DB 7        /* db_kernel: noise-floor dB plane, sums, level-0 histogram */
+#define APT_KERNEL_SELECT 8    /* select_hist/scan: median levels 1-2 */
+#define APT_KERNEL_FINALIZE 9  /* finalize_kernel */
+#define APT_N_KERNELS 10
 int  apt_plan_enable_timing(apt_plan_t* plan, int enable);
 int  apt_plan_kernel_ms(apt_plan_t* plan, float* out_ms /* [APT_N_KERNELS] */);
 

@@ -144,6 +144,38 @@ def test_ragged_batch_matches_oracle_i16(torch_cuda, oracle_mod):
     eng.close()
 
 
+def test_default_planes_mode_lane_path(torch_cuda, oracle_mod):
+    """Default flag set (no pass-1 debug planes): pass 1 tracks the mode bins only.  Labels, events and the
+    flux planes must equal the oracle bit for bit; ragged lengths exercise the serial kernels' tails."""
+    specs = [(20.0, 300, 0.0), (13.37, 301, 3.0), (20.0, 302, 10.0), (5.5, 303, 10.0), (9.0, 304, 0.5),
+             (20.0, 305, 3.0), (6.1, 306, 3.0)]
+    clips = [synth_clip_i16(s, seed, lam) for s, seed, lam in specs]
+    params = default_params(check_duration=5)
+    eng = make_engine(params)
+    plan, out = eng.run_clips(clips, ("mode_flux", "norm_flux", "score", "noise_psd"))
+    for c, pcm in enumerate(clips):
+        m, s = oracle_mod.run(pcm_to_f32(pcm), dict(params, keep_state_debug=True))
+        f0, f1 = int(plan.frame_off[c]), int(plan.frame_off[c + 1])
+        assert np.array_equal(out["frame_class"][f0:f1], s["frame_class"])
+        assert np.array_equal(out["rain_conf"][f0:f1], s["rain_conf"])
+        assert np.array_equal(out["noise_conf"][f0:f1], s["noise_conf"])
+        n = int(out["event_count"][c])
+        assert n == m["rain_frame_count"] and np.array_equal(out["event_idx"][f0:f0 + n], s["event_idx"])
+        assert np.array_equal(out["mode_flux"][:, f0:f1], s["mode_flux"])
+        assert np.array_equal(out["norm_flux"][:, f0:f1], s["norm_flux"])
+        assert np.array_equal(out["score"][f0:f1], s["score"])
+        assert np.array_equal(out["noise_psd"][f0:f1], s["N2_band"])
+        st = out["clip_stats"][c]
+        assert st[6] == pytest.approx(m["mean_noise_floor_db"], rel=1e-6)
+        assert st[7] == m["median_noise_floor_db"]
+    # the same batch without any optional plane (dB plane produced in place) gives the same statistics
+    plan2, out2 = eng.run_clips(clips, ())
+    assert np.array_equal(out2["frame_class"], out["frame_class"])
+    assert np.array_equal(out2["clip_stats"], out["clip_stats"])
+    assert np.array_equal(out2["event_count"], out["event_count"])
+    eng.close()
+
+
 def test_f32_fft_mode_events(torch_cuda, oracle_mod):
     """float32 FFT variant (north_star subsystem 2): spectra within 1e-6 of frame max, labels equal."""
     clips = [synth_clip_i16(20, 300 + i, (0.0, 3.0, 10.0)[i]) for i in range(3)]
