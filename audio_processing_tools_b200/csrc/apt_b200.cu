@@ -293,13 +293,12 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     // TD tables
     {
         const int halo = (p->blk_post_pre + 2) * p->blk_hop + p->blk_len;
-        const int lb = TD_FT * p->hop + p->n_fft + 2 * halo + 2 * TD_WARM + 2 * 64;
-        int chunk = (lb + TD_NT - 1) / TD_NT;
-        chunk |= 1;   // odd stride: conflict-free 64-bit shared-memory walks
+        const int lb = TD_FT * p->hop + p->n_fft + 2 * halo + 2 * TD_WARM + p->hop;
+        if (halo > 128 || lb > TD_LB) { delete pl; return fail(ctx, -26, "block-energy geometry needs a %d-sample tile buffer (max %d)", lb, TD_LB); }
         std::vector<double> Apow, H;
-        build_td_tables(*p, ns, sos, chunk, Apow, H);
+        build_td_tables(*p, ns, sos, TD_CHUNK, Apow, H);
         PL_OK(upload(pl->d_Apow, Apow)); PL_OK(upload(pl->d_H, H));
-        pl->tdt.Apow = pl->d_Apow.p; pl->tdt.H = pl->d_H.p; pl->tdt.chunk = chunk; pl->tdt.lb_max = chunk * TD_NT; pl->tdt.halo = halo;
+        pl->tdt.Apow = pl->d_Apow.p; pl->tdt.H = pl->d_H.p; pl->tdt.chunk = TD_CHUNK; pl->tdt.lb_max = TD_LB; pl->tdt.halo = halo;
         {   // scan rounds: stop once the transition matrix power is numerically zero
             const int dim = 2 * ns;
             int rounds = 8;
@@ -310,9 +309,8 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
             }
             pl->tdt.rounds = rounds;
         }
-        const int env_cap = (TD_FT * p->hop + p->n_fft + 2 * halo) / std::max(1, p->blk_hop) + 4;
-        pl->td_smem = sizeof(double) * ((size_t)pl->tdt.lb_max + 2 * TD_NT * 2 * ns + env_cap + 8 * 4 * ns * ns + (size_t)chunk * 2 * ns) +
-                      sizeof(float) * (size_t)(TD_FT * p->hop + p->n_fft + 2 * halo + 64);
+        pl->tdt.env_cap = (TD_FT * p->hop + p->n_fft + 2 * halo) / std::max(1, p->blk_hop) + 8;
+        pl->td_smem = td_smem_bytes(ns, pl->tdt.env_cap);
     }
     // scratch
     PL_OK(pl->d_Pband.alloc((size_t)pl->nF * K));

@@ -373,19 +373,28 @@ __device__ void raw_features_frame(const DevParams& p, const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 // K6+K7: zero-phase SOS prefilter (scipy.signal.sosfiltfilt, float64) + TD frame features
 // ---------------------------------------------------------------------------------------------
+// A CTA filters one tile of TD_FT frames plus warm-up on both sides.  Every thread keeps its TD_CHUNK
+// consecutive samples in REGISTERS through both filter directions (block-parallel IIR: direct pass from
+// a zero state, Kogge-Stone scan of the chunk-final states with the chunk transition matrix, then the
+// homogeneous response to the incoming state is added); shared memory only carries the staged PCM, the
+// scan states and the float32 result.  The float64 pipe (64 FMA/clk/SM) is the bound of this kernel.
 constexpr int TD_NT = 256;
 constexpr int TD_FT = 32;       // TD frames per tile
 constexpr int TD_WARM = 512;    // warm-up samples each side (pole radius 0.928 -> < 2^-53 after 490)
+constexpr int TD_CHUNK = 23;    // samples per thread (odd: conflict-free shared-memory walks)
+constexpr int TD_LB = TD_NT * TD_CHUNK;   // filter buffer capacity of a tile
+constexpr int TD_XF = TD_LB + TD_LB / 16 + 160;   // float32 staging / result area (padded layout)
 constexpr int TD_MAXDIM = 2 * APT_MAX_SOS;
 
 struct TdTables {
-    // block-parallel IIR tables, computed at plan time for chunk length `chunk` (state dim = 2*n_sos):
+    // block-parallel IIR tables, computed at plan time for chunk length TD_CHUNK (state dim = 2*n_sos):
     const double* Apow;  // [8][dim][dim]  A^(2^k), A = transition over one chunk
     const double* H;     // [chunk][dim]   output response at step n to a unit initial state
-    int chunk;           // samples per thread (odd: conflict-free 64-bit shared accesses)
+    int chunk;           // == TD_CHUNK
     int rounds;          // scan rounds needed: max|A^(2^k)| is below 1e-20 for k >= rounds
-    int lb_max;          // capacity of the float64 buffer (samples)
-    int halo;            // extra valid samples each side of the frames (block features)
+    int lb_max;          // == TD_LB
+    int halo;            // extra valid samples each side of the frames (block features); <= 128
+    int env_cap;         // capacity of the block-envelope scratch (doubles)
 };
 
 struct TdOut {
@@ -394,15 +403,11 @@ struct TdOut {
     int64_t nF;
     int want_kurt;   // compute kurtosis
     int want_block;  // compute block features
-#ifdef APT_PROFILE_PHASES
-    long long* dbg;  // [16] per-phase clock64 deltas of one interior tile (profiling builds only)
-#endif
 };
-#ifdef APT_PROFILE_PHASES
-#define APT_STAMP(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 777) o.dbg[i] = clock64(); } while (0)
-#else
-#define APT_STAMP(i) do { } while (0)
-#endif
+
+inline size_t td_smem_bytes(int ns, int env_cap) {
+    return sizeof(float) * TD_XF + sizeof(double) * ((size_t)2 * TD_NT * 2 * ns + 8 * 4 * ns * ns + (size_t)TD_CHUNK * 2 * ns + env_cap);
+}
 
 // one biquad cascade step (DF2T), float64, FMAs allowed (not bit-compared; 1e-16 level)
 template <int NS>
@@ -417,73 +422,88 @@ __device__ __forceinline__ double sos_step(const double (&c)[NS][6], double (&z)
     return x;
 }
 
-// In-place block-parallel filtering of buf[0..len) (forward if !rev, else over reversed positions).
-// Thread i owns positions [i*chunk, (i+1)*chunk).  init: state entering position 0 (or nullptr = zero).
+// One filter direction over the register-resident chunks.  `rank` is the thread's position in the
+// direction's chunk order (0 = the chunk the sequence starts in, < 0 = no samples); rank 0 starts from
+// `zi * (its first sample)` when has_init, else from rest; every rank >= 1 chunk is full.
 template <int NS>
-__device__ void block_iir(const DevParams& p, const TdTables& tb, const double* __restrict__ s_A,
-                          const double* __restrict__ s_H, double* __restrict__ buf, int len, bool rev,
-                          const double* init, double* __restrict__ s_state /*[TD_NT][2*NS] x2*/) {
+__device__ __forceinline__ void iir_pass(const DevParams& p, const TdTables& tb, const double* __restrict__ s_A,
+                                         const double* __restrict__ s_H, double (&y)[TD_CHUNK], int n_mine, bool rev,
+                                         bool has_init, int rank, double* __restrict__ s_state) {
     constexpr int DIM = 2 * NS;
-    const int tid = threadIdx.x;
-    const int c = tb.chunk;
-    const int a = tid * c, e = min(len, a + c);
     double coef[NS][6];
 #pragma unroll
     for (int s = 0; s < NS; s++)
 #pragma unroll
         for (int j = 0; j < 6; j++) coef[s][j] = p.sos[s][j];
     double z[NS][2];
+    {
+        double xe = 0.0;
+        if (has_init && rank == 0) {
+            if (!rev) xe = y[0];
+            else {
 #pragma unroll
-    for (int s = 0; s < NS; s++) { z[s][0] = (tid == 0 && init) ? init[2 * s] : 0.0; z[s][1] = (tid == 0 && init) ? init[2 * s + 1] : 0.0; }
-    for (int i = a; i < e; i++) {
-        const int pos = rev ? len - 1 - i : i;
-        buf[pos] = sos_step<NS>(coef, z, buf[pos]);
+                for (int j = 0; j < TD_CHUNK; j++) if (j == n_mine - 1) xe = y[j];
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) { z[s][0] = p.zi[s][0] * xe; z[s][1] = p.zi[s][1] * xe; }
     }
-    // a partial (or empty) chunk still has to carry its state across the missing samples so that the
-    // scan below can use one transition matrix; only the last active chunk can be partial and nothing
-    // follows it, so its outgoing state is irrelevant.
-    double* v0 = s_state;
-    double* v1 = s_state + TD_NT * DIM;
+    if (rank >= 0) {
+        if (!rev) {
 #pragma unroll
-    for (int s = 0; s < NS; s++) { v0[tid * DIM + 2 * s] = z[s][0]; v0[tid * DIM + 2 * s + 1] = z[s][1]; }
+            for (int j = 0; j < TD_CHUNK; j++) if (j < n_mine) y[j] = sos_step<NS>(coef, z, y[j]);
+        } else {
+#pragma unroll
+            for (int j = TD_CHUNK - 1; j >= 0; j--) if (j < n_mine) y[j] = sos_step<NS>(coef, z, y[j]);
+        }
+    }
+    // chunk-final states, component-major so that lanes touch consecutive doubles
+    double* src = s_state;
+    double* dst = s_state + TD_NT * DIM;
+    if (rank >= 0) {
+#pragma unroll
+        for (int r = 0; r < DIM; r++) src[r * TD_NT + rank] = z[r >> 1][r & 1];
+    }
     __syncthreads();
-    // Kogge-Stone: v_i <- v_i + A^(2^k) v_{i-2^k}
-    double* src = v0;
-    double* dst = v1;
+    // Kogge-Stone over ranks: v_i <- v_i + A^(2^k) v_{i-2^k}
 #pragma unroll 1
     for (int k = 0; k < tb.rounds; k++) {
         const int d = 1 << k;
-        double acc[DIM];
+        if (rank >= 0) {
+            double acc[DIM];
 #pragma unroll
-        for (int r = 0; r < DIM; r++) acc[r] = src[tid * DIM + r];
-        if (tid >= d) {
-            const double* A = s_A + k * DIM * DIM;
-            double u[DIM];
+            for (int r = 0; r < DIM; r++) acc[r] = src[r * TD_NT + rank];
+            if (rank >= d) {
+                const double* A = s_A + k * DIM * DIM;
+                double u[DIM];
 #pragma unroll
-            for (int r = 0; r < DIM; r++) u[r] = src[(tid - d) * DIM + r];
+                for (int q = 0; q < DIM; q++) u[q] = src[q * TD_NT + rank - d];
 #pragma unroll
-            for (int r = 0; r < DIM; r++)
+                for (int r = 0; r < DIM; r++)
 #pragma unroll
-                for (int q = 0; q < DIM; q++) acc[r] = d_fma(A[r * DIM + q], u[q], acc[r]);
+                    for (int q = 0; q < DIM; q++) acc[r] = d_fma(A[r * DIM + q], u[q], acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < DIM; r++) dst[r * TD_NT + rank] = acc[r];
         }
-#pragma unroll
-        for (int r = 0; r < DIM; r++) dst[tid * DIM + r] = acc[r];
         __syncthreads();
         double* t = src; src = dst; dst = t;
     }
-    // incoming state of thread i (i >= 1) is the scanned value of thread i-1; add its homogeneous response
-    if (tid >= 1 && a < len) {
+    // incoming state of rank i >= 1 is the scanned state of rank i-1: add its homogeneous response
+    if (rank >= 1) {
         double sin_[DIM];
 #pragma unroll
-        for (int r = 0; r < DIM; r++) sin_[r] = src[(tid - 1) * DIM + r];
-#pragma unroll 4
-        for (int i = a; i < e; i++) {
-            const int pos = rev ? len - 1 - i : i;
-            const double* h = s_H + (i - a) * DIM;
-            double acc = h[0] * sin_[0];
+        for (int r = 0; r < DIM; r++) sin_[r] = src[r * TD_NT + rank - 1];
 #pragma unroll
-            for (int r = 1; r < DIM; r++) acc = d_fma(h[r], sin_[r], acc);
-            buf[pos] += acc;
+        for (int j = 0; j < TD_CHUNK; j++) {
+            const int m = rev ? TD_CHUNK - 1 - j : j;
+            if (j < n_mine) {
+                const double* h = s_H + m * DIM;
+                double acc = h[0] * sin_[0];
+#pragma unroll
+                for (int r = 1; r < DIM; r++) acc = d_fma(h[r], sin_[r], acc);
+                y[j] += acc;
+            }
         }
     }
     __syncthreads();
@@ -513,40 +533,44 @@ __device__ __forceinline__ float group8_np_sum(Load ld, int n, int lane, unsigne
     return 0.0f + part[0];
 }
 
-__device__ double td_peak_width_half(const double* x, int n, int peak) {
+template <typename X>
+__device__ double td_peak_width_half(X x, int n, int peak) {
     int i = peak, lb = peak, rb = peak;
-    double lmin = x[peak], rmin = x[peak];
-    while (0 <= i && x[i] <= x[peak]) { if (x[i] < lmin) { lmin = x[i]; lb = i; } i--; }
+    double lmin = x(peak), rmin = x(peak);
+    while (0 <= i && x(i) <= x(peak)) { if (x(i) < lmin) { lmin = x(i); lb = i; } i--; }
     i = peak;
-    while (i <= n - 1 && x[i] <= x[peak]) { if (x[i] < rmin) { rmin = x[i]; rb = i; } i++; }
-    const double prom = x[peak] - (lmin > rmin ? lmin : rmin);
-    const double height = x[peak] - prom * 0.5;
+    while (i <= n - 1 && x(i) <= x(peak)) { if (x(i) < rmin) { rmin = x(i); rb = i; } i++; }
+    const double prom = x(peak) - (lmin > rmin ? lmin : rmin);
+    const double height = x(peak) - prom * 0.5;
     i = peak;
-    while (lb < i && height < x[i]) i--;
+    while (lb < i && height < x(i)) i--;
     double lip = (double)i;
-    if (x[i] < height) lip += (height - x[i]) / (x[i + 1] - x[i]);
+    if (x(i) < height) lip += (height - x(i)) / (x(i + 1) - x(i));
     i = peak;
-    while (i < rb && height < x[i]) i++;
+    while (i < rb && height < x(i)) i++;
     double rip = (double)i;
-    if (x[i] < height) rip -= (height - x[i]) / (x[i - 1] - x[i]);
+    if (x(i) < height) rip -= (height - x(i)) / (x(i - 1) - x(i));
     return rip - lip;
 }
 
+// float32 result layout: sample u (counted from 128 samples before the tile's first frame) lives at
+// u + 8 * (u / 128): consecutive 128-sample blocks start 136 floats apart, so the 4 blocks a warp sums at
+// once fall into different banks.
+__device__ __forceinline__ int td_xf_pos(int u) { return u + ((u >> 7) << 3); }
+
 template <int NS, typename PCM>
-__global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constant__ DevParams p, Batch b,
-                                                            const PCM* __restrict__ pcm,
-                                                            const int64_t* __restrict__ tile_off, TdTables tb, TdOut o) {
+__global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_constant__ DevParams p, Batch b,
+                                                               const PCM* __restrict__ pcm,
+                                                               const int64_t* __restrict__ tile_off, TdTables tb, TdOut o) {
     constexpr int DIM = 2 * NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_buf = reinterpret_cast<double*>(smem_raw);            // [lb_max]
-    double* s_state = s_buf + tb.lb_max;                            // [2][TD_NT][DIM]
-    double* s_env = s_state + 2 * TD_NT * DIM;                      // block envelope (want_block)
-    const int L = p.n_fft, hop = p.hop;
-    const int env_cap = (TD_FT * hop + L + 2 * tb.halo) / max(1, p.blk_hop) + 4;
-    double* s_A = s_env + env_cap;                                  // [8][DIM][DIM]
-    double* s_H = s_A + 8 * DIM * DIM;                              // [chunk][DIM]
-    float* s_xf = reinterpret_cast<float*>(s_H + tb.chunk * DIM);   // valid x_td range as float32
-    __shared__ double s_init[TD_MAXDIM];
+    double* s_state = reinterpret_cast<double*>(smem_raw);          // [2][DIM][TD_NT]
+    double* s_A = s_state + 2 * TD_NT * DIM;                        // [8][DIM][DIM]
+    double* s_H = s_A + 8 * DIM * DIM;                              // [TD_CHUNK][DIM]
+    double* s_env = s_H + TD_CHUNK * DIM;                           // block envelope (want_block)
+    float* s_x = reinterpret_cast<float*>(s_env + tb.env_cap);      // [TD_XF] staged PCM, then the float32 result
+    __shared__ float s_bsum[TD_FT + 1], s_bmax[TD_FT + 1];
+    const int L = p.n_fft, hop = p.hop;   // 256 / 128 (enforced by the plan)
 
     const int tid = threadIdx.x;
     int64_t tile_in_clip;
@@ -570,65 +594,105 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
     const int len = (int)(be - bs);
     const bool exact_l = bs == -pad, exact_r = be == N + pad;
 
-    APT_STAMP(0);
     for (int i = tid; i < 8 * DIM * DIM; i += TD_NT) s_A[i] = __ldg(tb.Apow + i);
-    for (int i = tid; i < tb.chunk * DIM; i += TD_NT) s_H[i] = __ldg(tb.H + i);
-    // stage the odd-extended signal in float64 (scipy odd_ext: 2*x[0]-x[i], 2*x[N-1]-x[N-1-i])
+    for (int i = tid; i < TD_CHUNK * DIM; i += TD_NT) s_H[i] = __ldg(tb.H + i);
+    // stage the in-clip part of the buffer as float32 (coalesced 128-bit loads)
     if (bs >= 0 && be <= N) {
-        load_run<6>(pcm, base + bs, len, [&](int i, float v) { s_buf[i] = (double)v; });
-    } else
-    for (int i = tid; i < len; i += TD_NT) {
-        const int64_t s = bs + i;
-        double v;
-        if (s < 0) v = 2.0 * (double)load_sample(pcm, base) - (double)load_sample(pcm, base - s);
-        else if (s >= N) v = 2.0 * (double)load_sample(pcm, base + N - 1) - (double)load_sample(pcm, base + 2 * (N - 1) - s);
-        else v = (double)load_sample(pcm, base + s);
-        s_buf[i] = v;
+        load_run<4>(pcm, base + bs, len, [&](int i, float v) { s_x[i] = v; });
+    } else {
+        for (int i = tid; i < len; i += TD_NT) {
+            const int64_t s = bs + i;
+            if (s >= 0 && s < N) s_x[i] = load_sample(pcm, base + s);
+        }
     }
     __syncthreads();
-    APT_STAMP(1);
-    if (NS > 0) {
-        if (tid < DIM) s_init[tid] = p.zi[tid >> 1][tid & 1] * s_buf[0];
-        __syncthreads();
-        block_iir<NS>(p, tb, s_A, s_H, s_buf, len, false, exact_l ? s_init : nullptr, s_state);
-        APT_STAMP(2);
-        if (tid < DIM) s_init[tid] = p.zi[tid >> 1][tid & 1] * s_buf[len - 1];
-        __syncthreads();
-        block_iir<NS>(p, tb, s_A, s_H, s_buf, len, true, exact_r ? s_init : nullptr, s_state);
+    // my chunk -> registers (float64); samples beyond the clip ends are scipy's odd extension
+    // 2*x[0]-x[i], 2*x[N-1]-x[N-1-i] (evaluated in float64)
+    const int a0 = tid * TD_CHUNK;
+    const int n_mine = max(0, min(TD_CHUNK, len - a0));
+    double y[TD_CHUNK];
+#pragma unroll
+    for (int j = 0; j < TD_CHUNK; j++) {
+        double v = 0.0;
+        if (j < n_mine) {
+            const int64_t s = bs + a0 + j;
+            if (s < 0) v = 2.0 * (double)load_sample(pcm, base) - (double)load_sample(pcm, base - s);
+            else if (s >= N) v = 2.0 * (double)load_sample(pcm, base + N - 1) - (double)load_sample(pcm, base + 2 * (N - 1) - s);
+            else v = (double)s_x[a0 + j];
+        }
+        y[j] = v;
     }
-    APT_STAMP(3);
-    // float32 x_td over the valid range
-    const int nv = (int)(ve - vs), voff = (int)(vs - bs);
-    for (int i = tid; i < nv; i += TD_NT) s_xf[i] = d2f(s_buf[voff + i]);
+    __syncthreads();   // s_x is reused for the result below
+    const int ia = (len - 1) / TD_CHUNK;   // last thread holding samples
+    iir_pass<NS>(p, tb, s_A, s_H, y, n_mine, false, exact_l, tid <= ia ? tid : -1, s_state);
+    iir_pass<NS>(p, tb, s_A, s_H, y, n_mine, true, exact_r, tid <= ia ? ia - tid : -1, s_state);
+
+    // float32 x_td over the valid range, padded layout
+    const int u_off = (int)(bs - (int64_t)t0 * hop) + 128;   // u of buffer index 0
+    const int voff = (int)(vs - bs), vend = (int)(ve - bs);
+#pragma unroll
+    for (int j = 0; j < TD_CHUNK; j++) {
+        const int i = a0 + j;
+        if (j < n_mine && i >= voff && i < vend) s_x[td_xf_pos(i + u_off)] = d2f(y[j]);
+    }
     __syncthreads();
+    const int u_vs = voff + u_off;   // u of clip sample vs
+    auto xf = [&](int64_t s_clip) -> float { return s_x[td_xf_pos((int)(s_clip - vs) + u_vs)]; };
     if (o.x_td) {
         // each tile owns samples [t0*hop, (t0+TD_FT)*hop), the last tile through N
         int64_t w0 = (int64_t)t0 * hop, w1 = last ? N : (int64_t)(t0 + TD_FT) * hop;
         if (w1 > N) w1 = N;
-        for (int64_t s = w0 + tid; s < w1; s += TD_NT) o.x_td[base + s] = s_xf[s - vs];
+        for (int64_t s = w0 + tid; s < w1; s += TD_NT) o.x_td[base + s] = xf(s);
     }
 
-    APT_STAMP(4);
-    // crest factor / kurtosis: 8 lanes per frame, numpy float32 summation order
+    // crest factor (feature_extraction.py:514-523): frame t = 128-sample blocks t and t+1 (hop = 128, L = 256);
+    // numpy's pairwise float32 sum of a 256-vector is exactly blocksum(first half) + blocksum(second half),
+    // each block summed with 8 strided accumulators, so every block is summed once and shared by two frames.
     const int grp = tid >> 3, lane = tid & 7;
     const unsigned gmask = 0xffu << ((tid & 31) & ~7);
     float* crest_o = o.td + f0;
     float* kurt_o = o.td + o.nF + f0;
-    for (int fr = grp; fr < TD_FT; fr += TD_NT / 8) {
-        const int t = t0 + fr;
-        if (t >= t1) continue;   // uniform per group
-        const float* seg = s_xf + ((int64_t)t * hop - vs);
-        const float sumsq = group8_np_sum([&](int i) { float v = seg[i]; return v * v; }, L, lane, gmask);
-        float pk = 0.0f;
-        for (int i = lane; i < L; i += 8) pk = fmaxf(pk, fabsf(seg[i]));
+    const int nfr = max(0, t1 - t0);
+    for (int blk = grp; blk < nfr + 1 && nfr > 0; blk += TD_NT / 8) {
+        const float* seg = s_x + (blk + 1) * 136;   // u = 128 * (blk + 1)
+        float v = seg[lane];
+        float r = v * v, pk = fabsf(v);
+#pragma unroll
+        for (int i = 1; i < 16; i++) { v = seg[8 * i + lane]; r += v * v; pk = fmaxf(pk, fabsf(v)); }
+        const float o1 = __shfl_xor_sync(gmask, r, 1);
+        const float s1 = (lane & 1) ? o1 + r : r + o1;
+        const float o2 = __shfl_xor_sync(gmask, s1, 2);
+        const float s2 = (lane & 2) ? o2 + s1 : s1 + o2;
+        const float o4 = __shfl_xor_sync(gmask, s2, 4);
+        const float bsum = (lane & 4) ? o4 + s2 : s2 + o4;
         pk = fmaxf(pk, __shfl_xor_sync(gmask, pk, 1));
         pk = fmaxf(pk, __shfl_xor_sync(gmask, pk, 2));
         pk = fmaxf(pk, __shfl_xor_sync(gmask, pk, 4));
-        float kv = 0.0f;
-        if (o.want_kurt) {
-            const float mean = f_div(group8_np_sum([&](int i) { return seg[i]; }, L, lane, gmask), (float)L);
-            const float m2 = f_div(group8_np_sum([&](int i) { float d = seg[i] - mean; return d * d; }, L, lane, gmask), (float)L);
-            const float m4 = f_div(group8_np_sum([&](int i) { double d = (double)(seg[i] - mean); return d2f((d * d) * (d * d)); }, L, lane, gmask), (float)L);
+        if (lane == 0) { s_bsum[blk] = bsum; s_bmax[blk] = pk; }
+    }
+    __syncthreads();
+    if (tid < nfr) {
+        const int t = t0 + tid;
+        const float sumsq = 0.0f + (s_bsum[tid] + s_bsum[tid + 1]);
+        const float pk = fmaxf(s_bmax[tid], s_bmax[tid + 1]);
+        const float mean_sq = f_div(sumsq, (float)L);
+        const float rms = f_sqrt(mean_sq + d2f(p.eps64));
+        const double r = (double)rms;
+        float cf = d2f((double)pk / (r > p.eps64 ? r : p.eps64));
+        if (isnan(cf) || isinf(cf)) cf = 0.0f;
+        crest_o[t] = cf;
+        if (!o.want_kurt) kurt_o[t] = 0.0f;
+    }
+    if (o.want_kurt) {
+        // unbiased Pearson kurtosis (scipy.stats.kurtosis(fisher=False, bias=False)), numpy float32 sums
+        for (int fr = grp; fr < nfr; fr += TD_NT / 8) {
+            const int t = t0 + fr;
+            const int ub = 128 * (fr + 1);
+            auto seg = [&](int i) { return s_x[td_xf_pos(ub + i)]; };
+            const float mean = f_div(group8_np_sum([&](int i) { return seg(i); }, L, lane, gmask), (float)L);
+            const float m2 = f_div(group8_np_sum([&](int i) { float d = seg(i) - mean; return d * d; }, L, lane, gmask), (float)L);
+            const float m4 = f_div(group8_np_sum([&](int i) { double d = (double)(seg(i) - mean); return d2f((d * d) * (d * d)); }, L, lane, gmask), (float)L);
+            float kv = 0.0f;
             const float lim = 1.1920929e-07f * mean;
             if (!(m2 <= lim * lim)) {
                 const double nn = (double)L;
@@ -636,18 +700,9 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
                 kv = d2f(1.0 / (nn - 2.0) / (nn - 3.0)) * a + 3.0f;
                 if (isnan(kv) || isinf(kv)) kv = 0.0f;
             }
-        }
-        if (lane == 0) {
-            const float mean_sq = f_div(sumsq, (float)L);
-            const float rms = f_sqrt(mean_sq + d2f(p.eps64));
-            const double r = (double)rms;
-            float cf = d2f((double)pk / (r > p.eps64 ? r : p.eps64));
-            if (isnan(cf) || isinf(cf)) cf = 0.0f;
-            crest_o[t] = cf;
-            kurt_o[t] = kv;
+            if (lane == 0) kurt_o[t] = kv;
         }
     }
-    APT_STAMP(5);
     // frames beyond the TD grid are zero (rain_frame_classifier.py:178-194 zero-fill alignment)
     if (last)
         for (int t = max(Tloc, 0) + tid; t < T_clip; t += TD_NT) {
@@ -668,12 +723,11 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
         int64_t bq1 = (int64_t)(t1 - 1) * bstep + bpf + pp + 1; if (bq1 > nb_total) bq1 = nb_total;
         const int64_t br0 = bq0 > 0 ? bq0 - 1 : 0, br1 = bq1 < nb_total ? bq1 + 1 : nb_total;
         const int nraw = (int)(br1 - br0);
-        double* raw_env = s_buf;            // reuse (filter buffer is dead now)
-        __syncthreads();
+        double* raw_env = s_state;            // reuse (scan states are dead now)
         for (int i = tid; i < nraw; i += TD_NT) {
-            const int64_t s = (br0 + i) * H - vs;
+            const int64_t s = (br0 + i) * H;
             double acc = 0.0;
-            for (int e = 0; e < B; e++) { double v = (double)s_xf[s + e]; acc += v * v; }
+            for (int e = 0; e < B; e++) { double v = (double)xf(s + e); acc += v * v; }
             const double en = acc / (double)B;
             raw_env[i] = sqrt(en > 0.0 ? en : 0.0);
         }
@@ -710,7 +764,7 @@ __global__ void __launch_bounds__(TD_NT) td_features_kernel(const __grid_constan
                 if (pv > p.eps64 && m >= 3 && pi > 0 && pi < m - 1) {
                     const double lv = fe[pi - 1], rv = fe[pi + 1];
                     if (pv - (lv > rv ? lv : rv) > p.eps64) {
-                        const double wv = td_peak_width_half(fe, m, pi);
+                        const double wv = td_peak_width_half([&](int i) { return fe[i]; }, m, pi);
                         if (isfinite(wv) && wv > 0.0) ow = d2f(wv);
                     }
                 }
