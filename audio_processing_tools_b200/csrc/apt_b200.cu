@@ -112,19 +112,28 @@ static void build_td_tables(const apt_params_t& prm, int ns, const double sos[][
         }
         for (int q = 0; q < dim; q++) A[q * dim + r] = z[q];
     }
-    Apow.assign((size_t)8 * dim * dim, 0.0);
-    std::vector<double> cur = A, nxt(dim * dim);
-    for (int k = 0; k < 8; k++) {
-        std::copy(cur.begin(), cur.end(), Apow.begin() + (size_t)k * dim * dim);
+    // A^e for e = 0..31, component-major: Alin[(i*dim+j)*32 + e]
+    Apow.assign((size_t)32 * dim * dim, 0.0);
+    std::vector<double> cur(dim * dim, 0.0), nxt(dim * dim);
+    for (int i = 0; i < dim; i++) cur[i * dim + i] = 1.0;
+    for (int e = 0; e < 32; e++) {
+        for (int i = 0; i < dim * dim; i++) Apow[(size_t)i * 32 + e] = cur[i];
         for (int i = 0; i < dim; i++)
             for (int j = 0; j < dim; j++) {
                 double s = 0.0;
-                for (int q = 0; q < dim; q++) s += cur[i * dim + q] * cur[q * dim + j];
+                for (int q = 0; q < dim; q++) s += A[i * dim + q] * cur[q * dim + j];
                 nxt[i * dim + j] = s;
             }
         cur = nxt;
     }
     (void)prm;
+}
+
+// 2-D launch grid of a tiled kernel over clips [clip0, clip0+n): x = largest tile count, y = clips
+static dim3 tile_grid(const std::vector<int64_t>& off, int clip0, int n) {
+    int64_t mx = 1;
+    for (int c = clip0; c < clip0 + n; c++) mx = std::max(mx, off[c + 1] - off[c]);
+    return dim3((unsigned)mx, (unsigned)n, 1);
 }
 
 template <typename T>
@@ -190,6 +199,7 @@ int apt_params_default(apt_params_t* p) {
 int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int64_t* clip_len, apt_plan_t** out) {
     if (!ctx) return -1;
     if (!p || !out || !clip_len || n_clips <= 0) return fail(ctx, -1, "apt_plan_create: bad arguments");
+    if (n_clips > 65535) return fail(ctx, -1, "apt_plan_create: at most 65535 clips per plan (grid.y limit), got %d", n_clips);
     *out = nullptr;
     if (p->abi_version != APT_ABI_VERSION) return fail(ctx, -20, "params abi_version %d != %d", p->abi_version, APT_ABI_VERSION);
     if (p->n_fft != 256 || p->hop < 1 || p->hop > 256 || 256 % p->hop != 0 || p->hop != 128)
@@ -298,16 +308,13 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         std::vector<double> Apow, H;
         build_td_tables(*p, ns, sos, TD_CHUNK, Apow, H);
         PL_OK(upload(pl->d_Apow, Apow)); PL_OK(upload(pl->d_H, H));
-        pl->tdt.Apow = pl->d_Apow.p; pl->tdt.H = pl->d_H.p; pl->tdt.chunk = TD_CHUNK; pl->tdt.lb_max = TD_LB; pl->tdt.halo = halo;
-        {   // scan rounds: stop once the transition matrix power is numerically zero
-            const int dim = 2 * ns;
-            int rounds = 8;
-            for (int k = 0; k < 8; k++) {
-                double mx = 0.0;
-                for (int i = 0; i < dim * dim; i++) mx = std::max(mx, fabs(Apow[(size_t)k * dim * dim + i]));
-                if (mx < 1e-20) { rounds = k; break; }
-            }
-            pl->tdt.rounds = rounds;
+        pl->tdt.Alin = pl->d_Apow.p; pl->tdt.H = pl->d_H.p; pl->tdt.chunk = TD_CHUNK; pl->tdt.lb_max = TD_LB; pl->tdt.halo = halo;
+        {   // the tile warm-up (TD_WARM samples) and the one-level warp scan both rely on the filter's memory
+            // being numerically gone after TD_WARM samples: check A^(TD_WARM / TD_CHUNK)
+            const int dim = 2 * ns, e = TD_WARM / TD_CHUNK;
+            double mx = 0.0;
+            for (int i = 0; i < dim * dim; i++) mx = std::max(mx, fabs(Apow[(size_t)i * 32 + e]));
+            if (mx > 1e-15) { delete pl; return fail(ctx, -26, "TD prefilter decays too slowly for the %d-sample tile warm-up (|A^%d| = %.3g)", TD_WARM, e, mx); }
         }
         pl->tdt.env_cap = (TD_FT * p->hop + p->n_fft + 2 * halo) / std::max(1, p->blk_hop) + 8;
         pl->td_smem = td_smem_bytes(ns, pl->tdt.env_cap);
@@ -412,7 +419,7 @@ static cudaError_t launch_stft(apt_plan* pl, const Batch& b, const PCM* pcm, con
     auto kern = stft256_kernel<T, PCM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)tiles, STFT_NT, smem, st>>>(pl->dp, b, pcm, pl->d_stft_tile_off.p, tab, so);
+    kern<<<tile_grid(pl->stft_tile_off, b.clip0, b.n_clips), STFT_NT, smem, st>>>(pl->dp, b, pcm, pl->d_stft_tile_off.p, tab, so);
     pl->last_launches++;
     return cudaGetLastError();
 }
@@ -424,7 +431,7 @@ static cudaError_t launch_td_ns(apt_plan* pl, const Batch& b, const PCM* pcm, co
     auto kern = td_features_kernel<NS, PCM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->td_smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)tiles, TD_NT, pl->td_smem, st>>>(pl->dp, b, pcm, pl->d_td_tile_off.p, pl->tdt, to);
+    kern<<<tile_grid(pl->td_tile_off, b.clip0, b.n_clips), TD_NT, pl->td_smem, st>>>(pl->dp, b, pcm, pl->d_td_tile_off.p, pl->tdt, to);
     pl->last_launches++;
     return cudaGetLastError();
 }
@@ -486,7 +493,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         io.P_band = pl->d_Pband.p; io.NL = nl_plane; io.nls = tab.nls; io.mf = pl->d_mf.p; io.stride = pl->mf_stride;
         io.det_noise_lag = out->det_noise_lag; io.D = out->D; io.mode_flux = out->mode_flux; io.nF = pl->nF;
         const int64_t tiles = pl->flux_tile_off[clip0 + n_clips] - pl->flux_tile_off[clip0];
-        flux_kernel<<<(unsigned)tiles, 256, 0, st>>>(pl->dp, b, pl->d_flux_tile_off.p, tab, io);
+        flux_kernel<<<tile_grid(pl->flux_tile_off, clip0, n_clips), 256, 0, st>>>(pl->dp, b, pl->d_flux_tile_off.p, tab, io);
         pl->last_launches++;
         CUDA_OK(ctx, cudaGetLastError());
     }
@@ -527,14 +534,14 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         const int64_t chunks = pl->sel_chunk_off[clip0 + n_clips] - pl->sel_chunk_off[clip0];
         CUDA_OK(ctx, cudaMemsetAsync(hist + (size_t)clip0 * 2 * SEL_BINS, 0, hist_bytes, st));
         select_init_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(b, d.K, pl->d_sel.p);
-        db_kernel<<<(unsigned)chunks, 256, 0, st>>>(pl->dp, b, n2_plane, pl->d_db.p, pl->d_sel_chunk_off.p, hist, pl->d_dbsum.p);
+        db_kernel<<<tile_grid(pl->sel_chunk_off, clip0, n_clips), 256, 0, st>>>(pl->dp, b, n2_plane, pl->d_db.p, pl->d_sel_chunk_off.p, hist, pl->d_dbsum.p);
         pl->last_launches += 2;
         CUDA_OK(ctx, cudaGetLastError());
         pl->mark(APT_KERNEL_SELECT, st);
         for (int level = 0; level < 3; level++) {
             if (level > 0) {
                 CUDA_OK(ctx, cudaMemsetAsync(hist + (size_t)clip0 * 2 * SEL_BINS, 0, hist_bytes, st));
-                select_hist_kernel<<<(unsigned)chunks, 256, 0, st>>>(b, d.K, pl->d_db.p, pl->d_sel_chunk_off.p, level, pl->d_sel.p, hist);
+                select_hist_kernel<<<tile_grid(pl->sel_chunk_off, clip0, n_clips), 256, 0, st>>>(b, d.K, pl->d_db.p, pl->d_sel_chunk_off.p, level, pl->d_sel.p, hist);
                 pl->last_launches++;
             }
             select_scan_kernel<<<(n_clips * 32 + 127) / 128, 128, 0, st>>>(clip0, n_clips, level, pl->d_sel.p, hist);

@@ -68,21 +68,13 @@ struct Batch {
     const int64_t* frame_off;  // [plan clips + 1]
 };
 
-// tile -> clip: tile_off is the plan's absolute prefix array of tiles per clip
-__device__ __forceinline__ int find_clip(const int64_t* __restrict__ off, int n_clips, int64_t x) {
-    // largest c with off[c] <= x
-    int lo = 0, hi = n_clips;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (__ldg(off + mid) <= x) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-__device__ __forceinline__ int tile_clip(const Batch& b, const int64_t* __restrict__ tile_off, int64_t& tile_in_clip) {
-    const int64_t x = (int64_t)blockIdx.x + __ldg(tile_off + b.clip0);
-    const int c = b.clip0 + find_clip(tile_off + b.clip0, b.n_clips, x);
-    tile_in_clip = x - __ldg(tile_off + c);
-    return c;
+// tile -> clip: tiled kernels launch a 2-D grid, blockIdx.y = clip of the launch's range, blockIdx.x = tile
+// inside the clip (grid.x = the largest tile count of the range; surplus CTAs of shorter clips exit at
+// once).  tile_off is the plan's absolute prefix array of tiles per clip.  No search, no per-tile table.
+__device__ __forceinline__ bool tile_clip(const Batch& b, const int64_t* __restrict__ tile_off, int& c, int64_t& tile_in_clip) {
+    c = b.clip0 + (int)blockIdx.y;
+    tile_in_clip = blockIdx.x;
+    return tile_in_clip < __ldg(tile_off + c + 1) - __ldg(tile_off + c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -226,7 +218,8 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
 
     const int tid = threadIdx.x;
     int64_t tile_in_clip;
-    const int c = tile_clip(b, tile_off, tile_in_clip);
+    int c;
+    if (!tile_clip(b, tile_off, c, tile_in_clip)) return;
     const int t0 = (int)tile_in_clip * STFT_TF;
     const int64_t base = __ldg(b.samp_off + c);
     const int64_t N = __ldg(b.samp_off + c + 1) - base;
@@ -388,10 +381,9 @@ constexpr int TD_MAXDIM = 2 * APT_MAX_SOS;
 
 struct TdTables {
     // block-parallel IIR tables, computed at plan time for chunk length TD_CHUNK (state dim = 2*n_sos):
-    const double* Apow;  // [8][dim][dim]  A^(2^k), A = transition over one chunk
+    const double* Alin;  // [dim*dim][32]  A^e for e = 0..31 (component-major), A = transition over one chunk
     const double* H;     // [chunk][dim]   output response at step n to a unit initial state
     int chunk;           // == TD_CHUNK
-    int rounds;          // scan rounds needed: max|A^(2^k)| is below 1e-20 for k >= rounds
     int lb_max;          // == TD_LB
     int halo;            // extra valid samples each side of the frames (block features); <= 128
     int env_cap;         // capacity of the block-envelope scratch (doubles)
@@ -403,10 +395,18 @@ struct TdOut {
     int64_t nF;
     int want_kurt;   // compute kurtosis
     int want_block;  // compute block features
+#ifdef APT_PROFILE_PHASES
+    long long* dbg;  // [16] clock64 stamps of one interior tile (profiling builds only)
+#endif
 };
+#ifdef APT_PROFILE_PHASES
+#define APT_STAMP(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 777) o.dbg[i] = clock64(); } while (0)
+#else
+#define APT_STAMP(i) do { } while (0)
+#endif
 
 inline size_t td_smem_bytes(int ns, int env_cap) {
-    return sizeof(float) * TD_XF + sizeof(double) * ((size_t)2 * TD_NT * 2 * ns + 8 * 4 * ns * ns + (size_t)TD_CHUNK * 2 * ns + env_cap);
+    return sizeof(float) * TD_XF + sizeof(double) * ((size_t)2 * ns * (TD_NT / 32) + 32 * 4 * ns * ns + (size_t)TD_CHUNK * 2 * ns + 2 * (size_t)env_cap);
 }
 
 // one biquad cascade step (DF2T), float64, FMAs allowed (not bit-compared; 1e-16 level)
@@ -422,14 +422,36 @@ __device__ __forceinline__ double sos_step(const double (&c)[NS][6], double (&z)
     return x;
 }
 
-// One filter direction over the register-resident chunks.  `rank` is the thread's position in the
-// direction's chunk order (0 = the chunk the sequence starts in, < 0 = no samples); rank 0 starts from
-// `zi * (its first sample)` when has_init, else from rest; every rank >= 1 chunk is full.
-template <int NS>
-__device__ __forceinline__ void iir_pass(const DevParams& p, const TdTables& tb, const double* __restrict__ s_A,
-                                         const double* __restrict__ s_H, double (&y)[TD_CHUNK], int n_mine, bool rev,
-                                         bool has_init, int rank, double* __restrict__ s_state) {
+__device__ __forceinline__ double shfl_up_d(double v, int d) {
+    return __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(v), d), __shfl_up_sync(0xffffffffu, __double2loint(v), d));
+}
+__device__ __forceinline__ double shfl_down_d(double v, int d) {
+    return __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(v), d), __shfl_down_sync(0xffffffffu, __double2loint(v), d));
+}
+
+// One filter direction over the register-resident chunks.  Chunks are ordered by thread index (forward)
+// or reverse thread index (REV); `ia` is the last thread holding samples.  The first chunk of the order
+// starts from `zi * xe` when has_init, else from rest; every later chunk is full except the last chunk
+// of the forward order.  Steps: (1) direct pass from a zero state, straight-line for full chunks;
+// (2) scan of the chunk-final states over the chunk order: Kogge-Stone with shuffles inside each warp
+// (v <- v + A^d v[pos-d]), then ONE shared-memory exchange adds A^(pos) times the previous warp's final
+// state (older warps contribute A^32 and beyond, below 1e-20 by the plan-time decay check);
+// (3) the homogeneous response to the incoming state is added to the chunk.
+// s_Alin: [DIM*DIM][32] powers A^e, e = 0..31, component-major.  s_vend: [DIM][TD_NT/32].
+template <int NS, bool REV>
+__device__ __forceinline__ void iir_pass(const DevParams& p, const double* __restrict__ s_Alin,
+                                         const double* __restrict__ s_H, double (&y)[TD_CHUNK], int n_mine,
+                                         bool has_init, double xe, int ia, double* __restrict__ s_vend) {
     constexpr int DIM = 2 * NS;
+    constexpr int NW = TD_NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wa = ia >> 5;
+    const bool active = tid <= ia;
+    // position inside the warp in chunk order, and whether an earlier warp exists
+    const int la = min(31, ia - 32 * w);                 // last active lane of this warp (< 0: none)
+    const int pos = REV ? la - lane : lane;
+    const bool first_chunk = REV ? (tid == ia) : (tid == 0);
+    const bool has_prev_warp = REV ? (w < wa) : (w > 0);
     double coef[NS][6];
 #pragma unroll
     for (int s = 0; s < NS; s++)
@@ -437,76 +459,93 @@ __device__ __forceinline__ void iir_pass(const DevParams& p, const TdTables& tb,
         for (int j = 0; j < 6; j++) coef[s][j] = p.sos[s][j];
     double z[NS][2];
     {
-        double xe = 0.0;
-        if (has_init && rank == 0) {
-            if (!rev) xe = y[0];
-            else {
+        const double x0 = (has_init && first_chunk) ? xe : 0.0;
 #pragma unroll
-                for (int j = 0; j < TD_CHUNK; j++) if (j == n_mine - 1) xe = y[j];
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < NS; s++) { z[s][0] = p.zi[s][0] * xe; z[s][1] = p.zi[s][1] * xe; }
+        for (int s = 0; s < NS; s++) { z[s][0] = p.zi[s][0] * x0; z[s][1] = p.zi[s][1] * x0; }
     }
-    if (rank >= 0) {
-        if (!rev) {
+    if (n_mine == TD_CHUNK) {
 #pragma unroll
-            for (int j = 0; j < TD_CHUNK; j++) if (j < n_mine) y[j] = sos_step<NS>(coef, z, y[j]);
-        } else {
+        for (int jj = 0; jj < TD_CHUNK; jj++) {
+            const int j = REV ? TD_CHUNK - 1 - jj : jj;
+            y[j] = sos_step<NS>(coef, z, y[j]);
+        }
+    } else if (n_mine > 0) {
 #pragma unroll
-            for (int j = TD_CHUNK - 1; j >= 0; j--) if (j < n_mine) y[j] = sos_step<NS>(coef, z, y[j]);
+        for (int jj = 0; jj < TD_CHUNK; jj++) {
+            const int j = REV ? TD_CHUNK - 1 - jj : jj;
+            if (j < n_mine) y[j] = sos_step<NS>(coef, z, y[j]);
         }
     }
-    // chunk-final states, component-major so that lanes touch consecutive doubles
-    double* src = s_state;
-    double* dst = s_state + TD_NT * DIM;
-    if (rank >= 0) {
+    // (2) scan.  v = chunk-final state (zero for threads without samples)
+    double v[DIM];
 #pragma unroll
-        for (int r = 0; r < DIM; r++) src[r * TD_NT + rank] = z[r >> 1][r & 1];
+    for (int r = 0; r < DIM; r++) v[r] = active ? z[r >> 1][r & 1] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int d = 1 << k;
+        double u[DIM];
+#pragma unroll
+        for (int q = 0; q < DIM; q++) u[q] = REV ? shfl_down_d(v[q], d) : shfl_up_d(v[q], d);
+        if (active && pos >= d) {
+#pragma unroll
+            for (int r = 0; r < DIM; r++)
+#pragma unroll
+                for (int q = 0; q < DIM; q++) v[r] = d_fma(s_Alin[(r * DIM + q) * 32 + d], u[q], v[r]);
+        }
+    }
+    // final state of this warp's last chunk in order, for the next warp
+    if (REV ? (lane == 0) : (lane == 31)) {
+#pragma unroll
+        for (int r = 0; r < DIM; r++) s_vend[r * NW + w] = v[r];
+    }
+    // scanned state of the previous chunk inside the warp
+    double sin_[DIM];
+#pragma unroll
+    for (int r = 0; r < DIM; r++) {
+        const double nb = REV ? shfl_down_d(v[r], 1) : shfl_up_d(v[r], 1);
+        sin_[r] = (pos >= 1) ? nb : 0.0;
     }
     __syncthreads();
-    // Kogge-Stone over ranks: v_i <- v_i + A^(2^k) v_{i-2^k}
-#pragma unroll 1
-    for (int k = 0; k < tb.rounds; k++) {
-        const int d = 1 << k;
-        if (rank >= 0) {
-            double acc[DIM];
+    if (active && has_prev_warp && pos >= 0) {
+        double ve[DIM];
 #pragma unroll
-            for (int r = 0; r < DIM; r++) acc[r] = src[r * TD_NT + rank];
-            if (rank >= d) {
-                const double* A = s_A + k * DIM * DIM;
-                double u[DIM];
+        for (int q = 0; q < DIM; q++) ve[q] = s_vend[q * NW + (REV ? w + 1 : w - 1)];
 #pragma unroll
-                for (int q = 0; q < DIM; q++) u[q] = src[q * TD_NT + rank - d];
+        for (int r = 0; r < DIM; r++)
 #pragma unroll
-                for (int r = 0; r < DIM; r++)
-#pragma unroll
-                    for (int q = 0; q < DIM; q++) acc[r] = d_fma(A[r * DIM + q], u[q], acc[r]);
-            }
-#pragma unroll
-            for (int r = 0; r < DIM; r++) dst[r * TD_NT + rank] = acc[r];
-        }
-        __syncthreads();
-        double* t = src; src = dst; dst = t;
+            for (int q = 0; q < DIM; q++) sin_[r] = d_fma(s_Alin[(r * DIM + q) * 32 + pos], ve[q], sin_[r]);
     }
-    // incoming state of rank i >= 1 is the scanned state of rank i-1: add its homogeneous response
-    if (rank >= 1) {
-        double sin_[DIM];
+    // (3) add the homogeneous response to the incoming state (every chunk but the first of the order)
+    if (active && !first_chunk) {
+        const double2* H2 = reinterpret_cast<const double2*>(s_H);
+        if (n_mine == TD_CHUNK) {
 #pragma unroll
-        for (int r = 0; r < DIM; r++) sin_[r] = src[r * TD_NT + rank - 1];
+            for (int j = 0; j < TD_CHUNK; j++) {
+                const int m = REV ? TD_CHUNK - 1 - j : j;
+                double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < TD_CHUNK; j++) {
-            const int m = rev ? TD_CHUNK - 1 - j : j;
-            if (j < n_mine) {
-                const double* h = s_H + m * DIM;
-                double acc = h[0] * sin_[0];
-#pragma unroll
-                for (int r = 1; r < DIM; r++) acc = d_fma(h[r], sin_[r], acc);
+                for (int r = 0; r < DIM; r += 2) {
+                    const double2 h2 = H2[(m * DIM + r) >> 1];
+                    acc = (r == 0) ? h2.x * sin_[0] : d_fma(h2.x, sin_[r], acc);
+                    acc = d_fma(h2.y, sin_[r + 1], acc);
+                }
                 y[j] += acc;
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < TD_CHUNK; j++) {
+                const int m = REV ? TD_CHUNK - 1 - j : j;
+                if (j < n_mine) {
+                    const double* h = s_H + m * DIM;
+                    double acc = h[0] * sin_[0];
+#pragma unroll
+                    for (int r = 1; r < DIM; r++) acc = d_fma(h[r], sin_[r], acc);
+                    y[j] += acc;
+                }
+            }
         }
     }
-    __syncthreads();
+    __syncthreads();   // s_vend is reused by the next pass
 }
 
 // numpy pairwise sum of n = 128 * 2^m contiguous float32 values spread over 8 lanes (lane j = accumulator j).
@@ -564,17 +603,19 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
                                                                const int64_t* __restrict__ tile_off, TdTables tb, TdOut o) {
     constexpr int DIM = 2 * NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_state = reinterpret_cast<double*>(smem_raw);          // [2][DIM][TD_NT]
-    double* s_A = s_state + 2 * TD_NT * DIM;                        // [8][DIM][DIM]
-    double* s_H = s_A + 8 * DIM * DIM;                              // [TD_CHUNK][DIM]
-    double* s_env = s_H + TD_CHUNK * DIM;                           // block envelope (want_block)
+    double* s_vend = reinterpret_cast<double*>(smem_raw);           // [DIM][TD_NT/32] warp-final scan states
+    double* s_A = s_vend + DIM * (TD_NT / 32);                      // [DIM*DIM][32] powers of the chunk transition
+    double* s_H = s_A + 32 * DIM * DIM;                             // [TD_CHUNK][DIM]
+    double* s_renv = s_H + TD_CHUNK * DIM;                          // [env_cap] raw block envelope (want_block)
+    double* s_env = s_renv + tb.env_cap;                            // [env_cap] smoothed block envelope
     float* s_x = reinterpret_cast<float*>(s_env + tb.env_cap);      // [TD_XF] staged PCM, then the float32 result
     __shared__ float s_bsum[TD_FT + 1], s_bmax[TD_FT + 1];
     const int L = p.n_fft, hop = p.hop;   // 256 / 128 (enforced by the plan)
 
     const int tid = threadIdx.x;
     int64_t tile_in_clip;
-    const int c = tile_clip(b, tile_off, tile_in_clip);
+    int c;
+    if (!tile_clip(b, tile_off, c, tile_in_clip)) return;
     const int tile = (int)tile_in_clip;
     const int64_t base = __ldg(b.samp_off + c);
     const int64_t N = __ldg(b.samp_off + c + 1) - base;
@@ -594,7 +635,8 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
     const int len = (int)(be - bs);
     const bool exact_l = bs == -pad, exact_r = be == N + pad;
 
-    for (int i = tid; i < 8 * DIM * DIM; i += TD_NT) s_A[i] = __ldg(tb.Apow + i);
+    APT_STAMP(0);
+    for (int i = tid; i < 32 * DIM * DIM; i += TD_NT) s_A[i] = __ldg(tb.Alin + i);
     for (int i = tid; i < TD_CHUNK * DIM; i += TD_NT) s_H[i] = __ldg(tb.H + i);
     // stage the in-clip part of the buffer as float32 (coalesced 128-bit loads)
     if (bs >= 0 && be <= N) {
@@ -606,27 +648,41 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
         }
     }
     __syncthreads();
+    APT_STAMP(1);
     // my chunk -> registers (float64); samples beyond the clip ends are scipy's odd extension
     // 2*x[0]-x[i], 2*x[N-1]-x[N-1-i] (evaluated in float64)
     const int a0 = tid * TD_CHUNK;
     const int n_mine = max(0, min(TD_CHUNK, len - a0));
     double y[TD_CHUNK];
+    if (n_mine == TD_CHUNK && bs + a0 >= 0 && bs + a0 + TD_CHUNK <= N) {
 #pragma unroll
-    for (int j = 0; j < TD_CHUNK; j++) {
-        double v = 0.0;
-        if (j < n_mine) {
-            const int64_t s = bs + a0 + j;
-            if (s < 0) v = 2.0 * (double)load_sample(pcm, base) - (double)load_sample(pcm, base - s);
-            else if (s >= N) v = 2.0 * (double)load_sample(pcm, base + N - 1) - (double)load_sample(pcm, base + 2 * (N - 1) - s);
-            else v = (double)s_x[a0 + j];
+        for (int j = 0; j < TD_CHUNK; j++) y[j] = (double)s_x[a0 + j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < TD_CHUNK; j++) {
+            double v = 0.0;
+            if (j < n_mine) {
+                const int64_t s = bs + a0 + j;
+                if (s < 0) v = 2.0 * (double)load_sample(pcm, base) - (double)load_sample(pcm, base - s);
+                else if (s >= N) v = 2.0 * (double)load_sample(pcm, base + N - 1) - (double)load_sample(pcm, base + 2 * (N - 1) - s);
+                else v = (double)s_x[a0 + j];
+            }
+            y[j] = v;
         }
-        y[j] = v;
     }
     __syncthreads();   // s_x is reused for the result below
+    APT_STAMP(2);
     const int ia = (len - 1) / TD_CHUNK;   // last thread holding samples
-    iir_pass<NS>(p, tb, s_A, s_H, y, n_mine, false, exact_l, tid <= ia ? tid : -1, s_state);
-    iir_pass<NS>(p, tb, s_A, s_H, y, n_mine, true, exact_r, tid <= ia ? ia - tid : -1, s_state);
+    iir_pass<NS, false>(p, s_A, s_H, y, n_mine, exact_l, y[0], ia, s_vend);
+    APT_STAMP(3);
+    double xe = 0.0;
+    if (exact_r && tid == ia) {   // scipy seeds the backward pass with zi * (last forward output)
+#pragma unroll
+        for (int j = 0; j < TD_CHUNK; j++) if (j == n_mine - 1) xe = y[j];
+    }
+    iir_pass<NS, true>(p, s_A, s_H, y, n_mine, exact_r, xe, ia, s_vend);
 
+    APT_STAMP(4);
     // float32 x_td over the valid range, padded layout
     const int u_off = (int)(bs - (int64_t)t0 * hop) + 128;   // u of buffer index 0
     const int voff = (int)(vs - bs), vend = (int)(ve - bs);
@@ -636,6 +692,7 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
         if (j < n_mine && i >= voff && i < vend) s_x[td_xf_pos(i + u_off)] = d2f(y[j]);
     }
     __syncthreads();
+    APT_STAMP(5);
     const int u_vs = voff + u_off;   // u of clip sample vs
     auto xf = [&](int64_t s_clip) -> float { return s_x[td_xf_pos((int)(s_clip - vs) + u_vs)]; };
     if (o.x_td) {
@@ -683,6 +740,7 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
         crest_o[t] = cf;
         if (!o.want_kurt) kurt_o[t] = 0.0f;
     }
+    APT_STAMP(6);
     if (o.want_kurt) {
         // unbiased Pearson kurtosis (scipy.stats.kurtosis(fisher=False, bias=False)), numpy float32 sums
         for (int fr = grp; fr < nfr; fr += TD_NT / 8) {
@@ -723,7 +781,7 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
         int64_t bq1 = (int64_t)(t1 - 1) * bstep + bpf + pp + 1; if (bq1 > nb_total) bq1 = nb_total;
         const int64_t br0 = bq0 > 0 ? bq0 - 1 : 0, br1 = bq1 < nb_total ? bq1 + 1 : nb_total;
         const int nraw = (int)(br1 - br0);
-        double* raw_env = s_state;            // reuse (scan states are dead now)
+        double* raw_env = s_renv;
         for (int i = tid; i < nraw; i += TD_NT) {
             const int64_t s = (br0 + i) * H;
             double acc = 0.0;
@@ -946,7 +1004,8 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevPa
     __shared__ float s_ltab[64];
     const int tid = threadIdx.x;
     int64_t tile_in_clip;
-    const int c = tile_clip(b, tile_off, tile_in_clip);
+    int c;
+    if (!tile_clip(b, tile_off, c, tile_in_clip)) return;
     const int64_t f0 = __ldg(b.frame_off + c);
     const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
     const int t0 = (int)tile_in_clip * FLUX_FT, nt = min(FLUX_FT, T - t0);
@@ -1230,7 +1289,8 @@ __global__ void __launch_bounds__(256) db_kernel(const __grid_constant__ DevPara
     __shared__ double s_part[8];
     const int tid = threadIdx.x;
     int64_t chunk_in_clip;
-    const int c = tile_clip(b, chunk_off, chunk_in_clip);
+    int c;
+    if (!tile_clip(b, chunk_off, c, chunk_in_clip)) return;
     const int64_t f0 = __ldg(b.frame_off + c);
     const int64_t n = (__ldg(b.frame_off + c + 1) - f0) * (int64_t)p.K;
     const int64_t e0 = chunk_in_clip * SEL_CHUNK, e1 = min(n, e0 + (int64_t)SEL_CHUNK);
@@ -1275,7 +1335,7 @@ __global__ void __launch_bounds__(256) db_kernel(const __grid_constant__ DevPara
     if (tid == 0) {
         double s = 0.0;
         for (int w = 0; w < 8; w++) s += s_part[w];
-        chunk_sum[(int64_t)blockIdx.x + __ldg(chunk_off + b.clip0)] = s;
+        chunk_sum[__ldg(chunk_off + c) + chunk_in_clip] = s;
     }
     uint32_t* hg = hist + (size_t)c * 2 * SEL_BINS;
     for (int i = tid; i < SEL_BINS; i += 256) {
@@ -1302,7 +1362,8 @@ __global__ void __launch_bounds__(256) select_hist_kernel(Batch b, int K, const 
                                                           const SelState* __restrict__ st, uint32_t* __restrict__ hist) {
     __shared__ uint32_t s_h[2][SEL_BINS];
     int64_t chunk_in_clip;
-    const int c = tile_clip(b, chunk_off, chunk_in_clip);
+    int c;
+    if (!tile_clip(b, chunk_off, c, chunk_in_clip)) return;
     const int64_t f0 = __ldg(b.frame_off + c);
     const int64_t n = (__ldg(b.frame_off + c + 1) - f0) * (int64_t)K;
     const int64_t e0 = chunk_in_clip * SEL_CHUNK, e1 = min(n, e0 + (int64_t)SEL_CHUNK);

@@ -27,8 +27,8 @@ int main() {
     TdOut to; to.td = pl->d_td.p; to.x_td = nullptr; to.nF = pl->nF; to.want_block = 0; to.want_kurt = 0; to.dbg = dbg;
     for (int rep = 0; rep < 2; rep++) { launch_td<int16_t>(pl, b, pcm, to, 0); cudaDeviceSynchronize(); }
     long long hd[16]; cudaMemcpy(hd, dbg, 128, cudaMemcpyDeviceToHost);
-    const char* nm[5] = {"stage(load+cvt)", "forward iir", "backward iir", "f64->f32 xf", "crest"};
-    for (int i = 0; i < 5; i++) printf("%-16s %lld cycles\n", nm[i], hd[i + 1] - hd[i]);
+    const char* nm[6] = {"stage(load+cvt)", "smem->regs f64", "forward iir", "backward iir", "f64->f32 xf", "crest"};
+    for (int i = 0; i < 6; i++) printf("%-16s %lld cycles\n", nm[i], hd[i + 1] - hd[i]);
     printf("chunk=%d rounds=%d lb_max=%d smem=%zu tiles=%lld\n", pl->tdt.chunk, pl->tdt.rounds, pl->tdt.lb_max, pl->td_smem, (long long)pl->td_tile_off[n_clips]);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
