@@ -316,6 +316,12 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
             for (int i = 0; i < dim * dim; i++) mx = std::max(mx, fabs(Apow[(size_t)i * 32 + e]));
             if (mx > 1e-15) { delete pl; return fail(ctx, -26, "TD prefilter decays too slowly for the %d-sample tile warm-up (|A^%d| = %.3g)", TD_WARM, e, mx); }
         }
+        memset(pl->tdt.Hc, 0, sizeof(pl->tdt.Hc)); memset(pl->tdt.Adc, 0, sizeof(pl->tdt.Adc));
+        if (ns <= 2) {
+            const int dim = 2 * ns;
+            for (int m = 0; m < TD_CHUNK; m++) for (int r = 0; r < dim; r++) pl->tdt.Hc[m * dim + r] = H[(size_t)m * dim + r];
+            for (int k = 0; k < 5; k++) for (int i = 0; i < dim * dim; i++) pl->tdt.Adc[k * 16 + i] = Apow[(size_t)i * 32 + (1 << k)];
+        }
         pl->tdt.env_cap = (TD_FT * p->hop + p->n_fft + 2 * halo) / std::max(1, p->blk_hop) + 8;
         pl->td_smem = td_smem_bytes(ns, pl->tdt.env_cap);
     }

@@ -387,6 +387,10 @@ struct TdTables {
     int lb_max;          // == TD_LB
     int halo;            // extra valid samples each side of the frames (block features); <= 128
     int env_cap;         // capacity of the block-envelope scratch (doubles)
+    // copies for state dimension <= 4 (n_sos <= 2) that travel in the kernel-parameter constant bank, so the
+    // scan and the response pass use them as FMA operands without any load on the dependent path
+    double Hc[TD_CHUNK * 4];   // [chunk][4]
+    double Adc[5 * 16];        // [k][4][4]  A^(2^k), k = 0..4
 };
 
 struct TdOut {
@@ -400,9 +404,12 @@ struct TdOut {
 #endif
 };
 #ifdef APT_PROFILE_PHASES
-#define APT_STAMP(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 777) o.dbg[i] = clock64(); } while (0)
+__device__ long long g_stamp[64];
+#define APT_STAMP(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 77 && blockIdx.y == 7) o.dbg[i] = clock64(); } while (0)
+#define APT_STAMP2(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 77 && blockIdx.y == 7) g_stamp[i] = clock64(); } while (0)
 #else
 #define APT_STAMP(i) do { } while (0)
+#define APT_STAMP2(i) do { } while (0)
 #endif
 
 inline size_t td_smem_bytes(int ns, int env_cap) {
@@ -439,7 +446,7 @@ __device__ __forceinline__ double shfl_down_d(double v, int d) {
 // (3) the homogeneous response to the incoming state is added to the chunk.
 // s_Alin: [DIM*DIM][32] powers A^e, e = 0..31, component-major.  s_vend: [DIM][TD_NT/32].
 template <int NS, bool REV>
-__device__ __forceinline__ void iir_pass(const DevParams& p, const double* __restrict__ s_Alin,
+__device__ __forceinline__ void iir_pass(const DevParams& p, const TdTables& tb, const double* __restrict__ s_Alin,
                                          const double* __restrict__ s_H, double (&y)[TD_CHUNK], int n_mine,
                                          bool has_init, double xe, int ia, double* __restrict__ s_vend) {
     constexpr int DIM = 2 * NS;
@@ -476,6 +483,7 @@ __device__ __forceinline__ void iir_pass(const DevParams& p, const double* __res
             if (j < n_mine) y[j] = sos_step<NS>(coef, z, y[j]);
         }
     }
+    APT_STAMP2(REV ? 10 : 0);
     // (2) scan.  v = chunk-final state (zero for threads without samples)
     double v[DIM];
 #pragma unroll
@@ -490,9 +498,13 @@ __device__ __forceinline__ void iir_pass(const DevParams& p, const double* __res
 #pragma unroll
             for (int r = 0; r < DIM; r++)
 #pragma unroll
-                for (int q = 0; q < DIM; q++) v[r] = d_fma(s_Alin[(r * DIM + q) * 32 + d], u[q], v[r]);
+                for (int q = 0; q < DIM; q++) {
+                    const double a = (NS <= 2) ? tb.Adc[k * 16 + r * DIM + q] : s_Alin[(r * DIM + q) * 32 + d];
+                    v[r] = d_fma(a, u[q], v[r]);
+                }
         }
     }
+    APT_STAMP2(REV ? 11 : 1);
     // final state of this warp's last chunk in order, for the next warp
     if (REV ? (lane == 0) : (lane == 31)) {
 #pragma unroll
@@ -511,23 +523,26 @@ __device__ __forceinline__ void iir_pass(const DevParams& p, const double* __res
 #pragma unroll
         for (int q = 0; q < DIM; q++) ve[q] = s_vend[q * NW + (REV ? w + 1 : w - 1)];
 #pragma unroll
-        for (int r = 0; r < DIM; r++)
+        for (int r = 0; r < DIM; r++) {
+            double arow[DIM];   // the row's loads are issued together, ahead of its FMA chain
 #pragma unroll
-            for (int q = 0; q < DIM; q++) sin_[r] = d_fma(s_Alin[(r * DIM + q) * 32 + pos], ve[q], sin_[r]);
+            for (int q = 0; q < DIM; q++) arow[q] = s_Alin[(r * DIM + q) * 32 + pos];
+#pragma unroll
+            for (int q = 0; q < DIM; q++) sin_[r] = d_fma(arow[q], ve[q], sin_[r]);
+        }
     }
+    APT_STAMP2(REV ? 12 : 2);
     // (3) add the homogeneous response to the incoming state (every chunk but the first of the order)
     if (active && !first_chunk) {
-        const double2* H2 = reinterpret_cast<const double2*>(s_H);
         if (n_mine == TD_CHUNK) {
 #pragma unroll
             for (int j = 0; j < TD_CHUNK; j++) {
                 const int m = REV ? TD_CHUNK - 1 - j : j;
                 double acc = 0.0;
 #pragma unroll
-                for (int r = 0; r < DIM; r += 2) {
-                    const double2 h2 = H2[(m * DIM + r) >> 1];
-                    acc = (r == 0) ? h2.x * sin_[0] : d_fma(h2.x, sin_[r], acc);
-                    acc = d_fma(h2.y, sin_[r + 1], acc);
+                for (int r = 0; r < DIM; r++) {
+                    const double h = (NS <= 2) ? tb.Hc[m * DIM + r] : s_H[m * DIM + r];
+                    acc = (r == 0) ? h * sin_[0] : d_fma(h, sin_[r], acc);
                 }
                 y[j] += acc;
             }
@@ -546,6 +561,7 @@ __device__ __forceinline__ void iir_pass(const DevParams& p, const double* __res
         }
     }
     __syncthreads();   // s_vend is reused by the next pass
+    APT_STAMP2(REV ? 13 : 3);
 }
 
 // numpy pairwise sum of n = 128 * 2^m contiguous float32 values spread over 8 lanes (lane j = accumulator j).
@@ -598,9 +614,9 @@ __device__ double td_peak_width_half(X x, int n, int peak) {
 __device__ __forceinline__ int td_xf_pos(int u) { return u + ((u >> 7) << 3); }
 
 template <int NS, typename PCM>
-__global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_constant__ DevParams p, Batch b,
+__global__ void __launch_bounds__(TD_NT, 3) td_features_kernel(const __grid_constant__ DevParams p, Batch b,
                                                                const PCM* __restrict__ pcm,
-                                                               const int64_t* __restrict__ tile_off, TdTables tb, TdOut o) {
+                                                               const int64_t* __restrict__ tile_off, const __grid_constant__ TdTables tb, TdOut o) {
     constexpr int DIM = 2 * NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_vend = reinterpret_cast<double*>(smem_raw);           // [DIM][TD_NT/32] warp-final scan states
@@ -638,8 +654,9 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
     APT_STAMP(0);
     for (int i = tid; i < 32 * DIM * DIM; i += TD_NT) s_A[i] = __ldg(tb.Alin + i);
     for (int i = tid; i < TD_CHUNK * DIM; i += TD_NT) s_H[i] = __ldg(tb.H + i);
-    // stage the in-clip part of the buffer as float32 (coalesced 128-bit loads)
-    if (bs >= 0 && be <= N) {
+    // stage the in-clip part of the buffer as float32 (coalesced 128-bit loads); zeros behind it
+    const bool interior = bs >= 0 && be <= N;
+    if (interior) {
         load_run<4>(pcm, base + bs, len, [&](int i, float v) { s_x[i] = v; });
     } else {
         for (int i = tid; i < len; i += TD_NT) {
@@ -647,21 +664,25 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
             if (s >= 0 && s < N) s_x[i] = load_sample(pcm, base + s);
         }
     }
+    for (int i = len + tid; i < TD_LB; i += TD_NT) s_x[i] = 0.0f;
     __syncthreads();
     APT_STAMP(1);
-    // my chunk -> registers (float64); samples beyond the clip ends are scipy's odd extension
-    // 2*x[0]-x[i], 2*x[N-1]-x[N-1-i] (evaluated in float64)
+    // my chunk -> registers (float64).  Every tile but the last of a clip runs all TD_NT chunks full
+    // length: the samples behind the buffer end are zeros (a filter at rest stays at rest on zeros, so the
+    // backward pass reaches the real data in the same state), which keeps every warp on straight-line
+    // code; one partial warp on a predicated path would stall the whole CTA at each barrier.
+    // Samples beyond the clip ends are scipy's odd extension 2*x[0]-x[i], 2*x[N-1]-x[N-1-i] (float64).
     const int a0 = tid * TD_CHUNK;
-    const int n_mine = max(0, min(TD_CHUNK, len - a0));
+    const int n_mine = exact_r ? max(0, min(TD_CHUNK, len - a0)) : TD_CHUNK;
     double y[TD_CHUNK];
-    if (n_mine == TD_CHUNK && bs + a0 >= 0 && bs + a0 + TD_CHUNK <= N) {
+    if (interior) {
 #pragma unroll
         for (int j = 0; j < TD_CHUNK; j++) y[j] = (double)s_x[a0 + j];
     } else {
 #pragma unroll
         for (int j = 0; j < TD_CHUNK; j++) {
             double v = 0.0;
-            if (j < n_mine) {
+            if (a0 + j < len) {
                 const int64_t s = bs + a0 + j;
                 if (s < 0) v = 2.0 * (double)load_sample(pcm, base) - (double)load_sample(pcm, base - s);
                 else if (s >= N) v = 2.0 * (double)load_sample(pcm, base + N - 1) - (double)load_sample(pcm, base + 2 * (N - 1) - s);
@@ -672,15 +693,20 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
     }
     __syncthreads();   // s_x is reused for the result below
     APT_STAMP(2);
-    const int ia = (len - 1) / TD_CHUNK;   // last thread holding samples
-    iir_pass<NS, false>(p, s_A, s_H, y, n_mine, exact_l, y[0], ia, s_vend);
+    const int ia = exact_r ? (len - 1) / TD_CHUNK : TD_NT - 1;   // last thread holding samples
+    iir_pass<NS, false>(p, tb, s_A, s_H, y, n_mine, exact_l, y[0], ia, s_vend);
     APT_STAMP(3);
     double xe = 0.0;
-    if (exact_r && tid == ia) {   // scipy seeds the backward pass with zi * (last forward output)
+    if (exact_r) {
+        if (tid == ia) {   // scipy seeds the backward pass with zi * (last forward output)
 #pragma unroll
-        for (int j = 0; j < TD_CHUNK; j++) if (j == n_mine - 1) xe = y[j];
+            for (int j = 0; j < TD_CHUNK; j++) if (j == n_mine - 1) xe = y[j];
+        }
+    } else if (a0 + TD_CHUNK > len) {   // forward ringing behind the buffer end must not enter the backward pass
+#pragma unroll
+        for (int j = 0; j < TD_CHUNK; j++) if (a0 + j >= len) y[j] = 0.0;
     }
-    iir_pass<NS, true>(p, s_A, s_H, y, n_mine, exact_r, xe, ia, s_vend);
+    iir_pass<NS, true>(p, tb, s_A, s_H, y, n_mine, exact_r, xe, ia, s_vend);
 
     APT_STAMP(4);
     // float32 x_td over the valid range, padded layout
@@ -689,7 +715,7 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
 #pragma unroll
     for (int j = 0; j < TD_CHUNK; j++) {
         const int i = a0 + j;
-        if (j < n_mine && i >= voff && i < vend) s_x[td_xf_pos(i + u_off)] = d2f(y[j]);
+        if (i >= voff && i < vend) s_x[td_xf_pos(i + u_off)] = d2f(y[j]);
     }
     __syncthreads();
     APT_STAMP(5);

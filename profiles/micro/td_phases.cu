@@ -25,11 +25,18 @@ int main() {
     long long* dbg; cudaMalloc(&dbg, 16 * 8); cudaMemset(dbg, 0, 128);
     Batch b{0, n_clips, pl->d_samp_off.p, pl->d_frame_off.p};
     TdOut to; to.td = pl->d_td.p; to.x_td = nullptr; to.nF = pl->nF; to.want_block = 0; to.want_kurt = 0; to.dbg = dbg;
+  for (int solo = 0; solo < 2; solo++) {
+    if (solo) pl->td_smem = 120 * 1024;   // one CTA per SM: phase latencies without a co-resident CTA
     for (int rep = 0; rep < 2; rep++) { launch_td<int16_t>(pl, b, pcm, to, 0); cudaDeviceSynchronize(); }
     long long hd[16]; cudaMemcpy(hd, dbg, 128, cudaMemcpyDeviceToHost);
+    printf(solo ? "--- 1 CTA/SM\n" : "--- default occupancy\n");
     const char* nm[6] = {"stage(load+cvt)", "smem->regs f64", "forward iir", "backward iir", "f64->f32 xf", "crest"};
     for (int i = 0; i < 6; i++) printf("%-16s %lld cycles\n", nm[i], hd[i + 1] - hd[i]);
-    printf("chunk=%d rounds=%d lb_max=%d smem=%zu tiles=%lld\n", pl->tdt.chunk, pl->tdt.rounds, pl->tdt.lb_max, pl->td_smem, (long long)pl->td_tile_off[n_clips]);
+    long long gs[64]; cudaMemcpyFromSymbol(gs, apt::g_stamp, sizeof(gs));
+    printf("  fwd: direct %lld, scan %lld, exchange %lld, correction %lld\n", gs[0] - hd[2], gs[1] - gs[0], gs[2] - gs[1], gs[3] - gs[2]);
+    printf("  bwd: direct %lld, scan %lld, exchange %lld, correction %lld\n", gs[10] - hd[3], gs[11] - gs[10], gs[12] - gs[11], gs[13] - gs[12]);
+  }
+    printf("chunk=%d lb_max=%d smem=%zu tiles=%lld\n", pl->tdt.chunk, pl->tdt.lb_max, pl->td_smem, (long long)pl->td_tile_off[n_clips]);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
