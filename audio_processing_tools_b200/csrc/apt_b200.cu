@@ -75,7 +75,8 @@ struct apt_plan {
     // host-path staging
     DevBuf<int16_t> d_pcm;
     DevBuf<int8_t> d_fc; DevBuf<float> d_rc, d_nc, d_stats; DevBuf<int32_t> d_ev, d_evc;
-    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_back = nullptr;
+    static constexpr int N_COMP = 3;
+    cudaStream_t s_copy = nullptr, s_comp[N_COMP] = {nullptr, nullptr, nullptr};
     int last_launches = 0;
     size_t scratch_bytes = 0;
     // optional per-kernel timing (CUDA events on the launch stream)
@@ -359,8 +360,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
                         sizeof(double) * (size_t)pl->sel_chunk_off[n_clips] +
                         (size_t)n_clips * (sizeof(SelState) + 2 * SEL_BINS * sizeof(uint32_t));
     PL_OK(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
-    PL_OK(cudaStreamCreateWithFlags(&pl->s_comp, cudaStreamNonBlocking));
-    PL_OK(cudaStreamCreateWithFlags(&pl->s_back, cudaStreamNonBlocking));
+    for (int i = 0; i < apt_plan::N_COMP; i++) PL_OK(cudaStreamCreateWithFlags(&pl->s_comp[i], cudaStreamNonBlocking));
 #undef PL_OK
     *out = pl;
     return 0;
@@ -369,8 +369,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
 void apt_plan_destroy(apt_plan_t* plan) {
     if (!plan) return;
     if (plan->s_copy) cudaStreamDestroy(plan->s_copy);
-    if (plan->s_comp) cudaStreamDestroy(plan->s_comp);
-    if (plan->s_back) cudaStreamDestroy(plan->s_back);
+    for (int i = 0; i < apt_plan::N_COMP; i++) if (plan->s_comp[i]) cudaStreamDestroy(plan->s_comp[i]);
     delete plan;
 }
 
@@ -499,7 +498,9 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         io.P_band = pl->d_Pband.p; io.NL = nl_plane; io.nls = tab.nls; io.mf = pl->d_mf.p; io.stride = pl->mf_stride;
         io.det_noise_lag = out->det_noise_lag; io.D = out->D; io.mode_flux = out->mode_flux; io.nF = pl->nF;
         const int64_t tiles = pl->flux_tile_off[clip0 + n_clips] - pl->flux_tile_off[clip0];
-        flux_kernel<<<tile_grid(pl->flux_tile_off, clip0, n_clips), 256, 0, st>>>(pl->dp, b, pl->d_flux_tile_off.p, tab, io);
+        const size_t fsm = flux_smem_bytes(d.K, tab.n_lanes, tab.nls);
+        CUDA_OK(ctx, cudaFuncSetAttribute(flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+        flux_kernel<<<tile_grid(pl->flux_tile_off, clip0, n_clips), 256, fsm, st>>>(pl->dp, b, pl->d_flux_tile_off.p, tab, io);
         pl->last_launches++;
         CUDA_OK(ctx, cudaGetLastError());
     }
@@ -598,35 +599,38 @@ int apt_run_host_i16(apt_plan_t* pl, const int16_t* host_pcm, int8_t* frame_clas
     memset(&o, 0, sizeof(o));
     o.frame_class = pl->d_fc.p; o.rain_conf = pl->d_rc.p; o.noise_conf = pl->d_nc.p;
     o.event_idx = pl->d_ev.p; o.event_count = pl->d_evc.p; o.clip_stats = pl->d_stats.p;
-    // clip groups: group g+1 is copied in (copy stream) while group g computes (compute stream) and
-    // group g-1's results travel back (return stream)
+    // Clip groups: group g+1 travels host->device on the copy stream while earlier groups compute.  Groups
+    // alternate over N_COMP compute streams so that the latency-bound serial kernels of one group (few warps,
+    // fixed duration whatever the group size) overlap the wide kernels of its neighbours; each group's results
+    // go back on its own compute stream (the device->host copy engine is separate from the host->device one).
     const int n_groups = std::min(pl->n_clips, 8);
-    std::vector<cudaEvent_t> ev(n_groups, nullptr), done(n_groups, nullptr);
+    std::vector<cudaEvent_t> ev(n_groups, nullptr);
+    const bool was_timing = pl->timing;
+    pl->timing = false;   // per-kernel event marks assume one stream
     int rc = 0;
     for (int g = 0; g < n_groups && rc == 0; g++) {
         const int c0 = (int)((int64_t)pl->n_clips * g / n_groups), c1 = (int)((int64_t)pl->n_clips * (g + 1) / n_groups);
         const int64_t s0 = pl->samp_off[c0], s1 = pl->samp_off[c1];
         const int64_t f0 = pl->frame_off[c0], f1 = pl->frame_off[c1];
+        cudaStream_t sc = pl->s_comp[g % apt_plan::N_COMP];
         cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming);
         cudaMemcpyAsync(pl->d_pcm.p + s0, host_pcm + s0, (size_t)(s1 - s0) * sizeof(int16_t), cudaMemcpyHostToDevice, pl->s_copy);
         cudaEventRecord(ev[g], pl->s_copy);
-        cudaStreamWaitEvent(pl->s_comp, ev[g], 0);
-        rc = run_range<int16_t>(pl, APT_STAGE_FULL, c0, c1 - c0, pl->d_pcm.p, &o, pl->s_comp);
+        cudaStreamWaitEvent(sc, ev[g], 0);
+        rc = run_range<int16_t>(pl, APT_STAGE_FULL, c0, c1 - c0, pl->d_pcm.p, &o, sc);
         if (rc != 0) break;
-        cudaEventRecord(done[g], pl->s_comp);
-        cudaStreamWaitEvent(pl->s_back, done[g], 0);
-        if (frame_class) cudaMemcpyAsync(frame_class + f0, pl->d_fc.p + f0, (size_t)(f1 - f0), cudaMemcpyDeviceToHost, pl->s_back);
-        if (rain_conf) cudaMemcpyAsync(rain_conf + f0, pl->d_rc.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, pl->s_back);
-        if (noise_conf) cudaMemcpyAsync(noise_conf + f0, pl->d_nc.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, pl->s_back);
-        if (event_idx) cudaMemcpyAsync(event_idx + f0, pl->d_ev.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, pl->s_back);
-        if (event_count) cudaMemcpyAsync(event_count + c0, pl->d_evc.p + c0, (size_t)(c1 - c0) * 4, cudaMemcpyDeviceToHost, pl->s_back);
+        if (frame_class) cudaMemcpyAsync(frame_class + f0, pl->d_fc.p + f0, (size_t)(f1 - f0), cudaMemcpyDeviceToHost, sc);
+        if (rain_conf) cudaMemcpyAsync(rain_conf + f0, pl->d_rc.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, sc);
+        if (noise_conf) cudaMemcpyAsync(noise_conf + f0, pl->d_nc.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, sc);
+        if (event_idx) cudaMemcpyAsync(event_idx + f0, pl->d_ev.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, sc);
+        if (event_count) cudaMemcpyAsync(event_count + c0, pl->d_evc.p + c0, (size_t)(c1 - c0) * 4, cudaMemcpyDeviceToHost, sc);
         if (clip_stats) cudaMemcpyAsync(clip_stats + (size_t)c0 * APT_N_CLIP_STATS, pl->d_stats.p + (size_t)c0 * APT_N_CLIP_STATS,
-                                        (size_t)(c1 - c0) * APT_N_CLIP_STATS * 4, cudaMemcpyDeviceToHost, pl->s_back);
+                                        (size_t)(c1 - c0) * APT_N_CLIP_STATS * 4, cudaMemcpyDeviceToHost, sc);
     }
-    cudaError_t e0 = cudaStreamSynchronize(pl->s_copy), e1 = cudaStreamSynchronize(pl->s_comp), e2 = cudaStreamSynchronize(pl->s_back);
+    cudaError_t e0 = cudaStreamSynchronize(pl->s_copy), e1 = cudaSuccess, e2 = cudaSuccess;
+    for (int i = 0; i < apt_plan::N_COMP; i++) { cudaError_t e = cudaStreamSynchronize(pl->s_comp[i]); if (e != cudaSuccess) e1 = e; }
     for (auto& e : ev) if (e) cudaEventDestroy(e);
-    for (auto& e : done) if (e) cudaEventDestroy(e);
+    pl->timing = was_timing;
     if (rc != 0) return rc;
     if (e0 != cudaSuccess) return fail(ctx, -12, "copy stream: %s", cudaGetErrorString(e0));
     if (e1 != cudaSuccess) return fail(ctx, -12, "compute stream: %s", cudaGetErrorString(e1));

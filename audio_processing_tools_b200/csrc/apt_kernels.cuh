@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(TD_NT, 3) td_features_kernel(const __grid_cons
 //   db_kernel     parallel  flat: noise-floor dB plane, its sums, level-0 histogram of the median select
 // ---------------------------------------------------------------------------------------------
 constexpr int SEQ_KMAX = 128;    // operating-band bins supported (n_fft = 256 -> 71)
-constexpr int SEQ_PF = 8;        // frames per straight-line group of the serial loops (register prefetch)
+constexpr int SEQ_PF = 16;       // frames per straight-line group of the serial loops (register prefetch)
 
 struct Tracker {
     float trk, ts, nprev;
@@ -1022,10 +1022,15 @@ struct FluxIO {
 };
 constexpr int FLUX_FT = 64;   // frames per tile
 
+inline size_t flux_smem_bytes(int K, int n_lanes, int nls) {
+    (void)K; (void)nls;
+    return sizeof(float) * (size_t)(FLUX_FT + 2) * (n_lanes + 1);
+}
+
 __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevParams p, Batch b,
                                                    const int64_t* __restrict__ tile_off,
                                                    const __grid_constant__ Trk1Tab tab, FluxIO io) {
-    __shared__ float s_D[FLUX_FT + 2][SEQ_KMAX + 1];
+    extern __shared__ __align__(16) float s_D[];   // [(FT+2)][n_lanes+1]
     __shared__ float s_mf[FLUX_FT][APT_MAX_MODES];
     __shared__ float s_ltab[64];
     const int tid = threadIdx.x;
@@ -1035,30 +1040,48 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevPa
     const int64_t f0 = __ldg(b.frame_off + c);
     const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
     const int t0 = (int)tile_in_clip * FLUX_FT, nt = min(FLUX_FT, T - t0);
-    const int K = p.K, M = p.M, nl_ = tab.n_lanes;
+    const int K = p.K, M = p.M, nl_ = tab.n_lanes, nls = io.nls, ds = nl_ + 1;
     if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
     __syncthreads();
-    // detector input D = dB above the lagged noise (rain_signal_processor.py:859-888) for frames t0-2 .. t0+nt-1
-    for (int idx = tid; idx < (nt + 2) * nl_; idx += 256) {
-        const int r = idx / nl_, j = idx - r * nl_;
-        const int tg = t0 - 2 + r;
-        if (tg < 0) continue;
+    // detector input D = dB above the lagged noise (rain_signal_processor.py:859-888) for frames t0-2 .. t0+nt-1.
+    // Thread = (row group, lane): the lane's bin is fixed, rows advance by 256/LP, three rows' loads in flight.
+    const int r0 = t0 >= 2 ? 0 : 2 - t0;           // first row that exists (frames before the clip start do not)
+    const int LP = (nl_ + 31) & ~31;               // lanes padded to whole warps
+    const int j = tid % LP, rg = tid / LP, RP = 256 / LP;
+    if (j < nl_ && rg < RP) {
         const int kb = tab.lane_bin[j];
-        const float pk = __ldg(io.P_band + (f0 + tg) * K + kb);
-        float dval, nl = 0.0f;
-        if (p.use_norm) {
-            nl = __ldg(io.NL + (f0 + tg) * io.nls + j);
-            if (p.ratio_db)
-                dval = 10.0f * svml_log10f(f_div(pk, nl + p.eps32) + p.eps32, s_ltab);
-            else
-                dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab) - 10.0f * svml_log10f(nl + p.eps32, s_ltab);
-        } else {
-            dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab);
-        }
-        s_D[r][j] = dval;
-        if (r >= 2) {
-            if (io.D) io.D[(f0 + tg) * K + kb] = dval;
-            if (io.det_noise_lag) io.det_noise_lag[(f0 + tg) * K + kb] = nl;
+        const float* Pp = io.P_band + (f0 + t0 - 2) * K + kb;
+        const float* Np = io.NL + (f0 + t0 - 2) * nls + j;
+        constexpr int U = 3;
+        for (int rb = r0 + rg; rb < nt + 2; rb += RP * U) {
+            float pk[U], nl[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int r = min(rb + u * RP, nt + 1);
+                pk[u] = __ldg(Pp + (size_t)r * K);
+                nl[u] = p.use_norm ? __ldg(Np + (size_t)r * nls) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int r = rb + u * RP;
+                if (r < nt + 2) {
+                    float dval;
+                    if (p.use_norm) {
+                        if (p.ratio_db)
+                            dval = 10.0f * svml_log10f(f_div(pk[u], nl[u] + p.eps32) + p.eps32, s_ltab);
+                        else
+                            dval = 10.0f * svml_log10f(pk[u] + p.eps32, s_ltab) - 10.0f * svml_log10f(nl[u] + p.eps32, s_ltab);
+                    } else {
+                        dval = 10.0f * svml_log10f(pk[u] + p.eps32, s_ltab);
+                    }
+                    s_D[r * ds + j] = dval;
+                    if (r >= 2) {
+                        const int64_t gi = (f0 + t0 - 2 + r) * K + kb;
+                        if (io.D) io.D[gi] = dval;
+                        if (io.det_noise_lag) io.det_noise_lag[gi] = nl[u];
+                    }
+                }
+            }
         }
     }
     __syncthreads();
@@ -1067,8 +1090,8 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevPa
         const int m = idx / nt, tt = idx - m * nt;
         const int tg = t0 + tt;
         const int lo = tab.mode_l0[m], n = tab.mode_n[m];
-        const float* d2 = s_D[tt + 2];
-        const float* d0 = s_D[tt];
+        const float* d2 = s_D + (tt + 2) * ds;
+        const float* d0 = s_D + tt * ds;
         auto fx = [&](int l) { const float d = d2[l] - d0[l]; return d > 0.0f ? d : (d != d ? d : 0.0f); };
         float s = 0.0f;
         if (tg >= 2 && n > 0) {
