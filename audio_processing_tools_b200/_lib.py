@@ -15,10 +15,11 @@ LIB_PATH = os.path.join(_PKG, "libapt_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 MAX_MODES, MAX_SOS, N_RAW, N_TD, N_STATS = 8, 4, 21, 5, 8
-ABI_VERSION = 1
+ABI_VERSION = 2
+MAX_GAIN_TAPS = 9
 STAGE_FEATURES, STAGE_FULL = 1, 2
 KERNEL_NAMES = ("stft256_kernel", "td_features_kernel", "trk1_kernel", "flux_kernel", "base_kernel",
-                "decide_kernels", "trk2_kernel", "db_kernel", "select_kernels", "finalize_kernel")
+                "decide_kernels", "trk2_kernel", "db_kernel", "select_kernels", "finalize_kernel", "gain_kernels")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
@@ -49,14 +50,20 @@ class AptParams(C.Structure):
         ("low_lo", C.c_int32), ("low_hi", C.c_int32), ("rain_lo", C.c_int32), ("rain_hi", C.c_int32),
         ("rolloff_fraction", C.c_double),
         ("suppressor_bypass", C.c_int32), ("clip_rain_min_frames", C.c_int32),
-        ("fft_f64", C.c_int32), ("reserved0", C.c_int32),
+        ("fft_f64", C.c_int32),
+        ("gain_mode", C.c_int32), ("adaptive_gain", C.c_int32), ("gain_freq_smooth", C.c_int32),
+        ("n_gain_taps", C.c_int32), ("use_lagged_noise_psd", C.c_int32),
+        ("oversub_noise", C.c_float), ("oversub_rain", C.c_float), ("gain_floor", C.c_float), ("gain_ceil", C.c_float),
+        ("gain_taps", C.c_float * MAX_GAIN_TAPS),
+        ("alpha_noise", C.c_float), ("one_minus_alpha_noise", C.c_float),
+        ("alpha_base", C.c_float), ("one_minus_alpha_base", C.c_float), ("gain_eps_f32", C.c_float),
         ("window", C.c_void_p), ("freqs", C.c_void_p),
     ]
 
 
 OUT_FIELDS = ("frame_class", "rain_conf", "noise_conf", "event_idx", "event_count", "clip_stats",
               "S", "P", "det_noise_psd", "det_noise_lag", "D", "noise_psd", "mode_flux", "norm_flux",
-              "score", "td", "raw", "band_energy", "gate", "x_td")
+              "score", "td", "raw", "band_energy", "gate", "x_td", "G", "ratio_med", "S_hat")
 
 
 class AptOut(C.Structure):

@@ -317,6 +317,43 @@ class ResolvedParams:
         P.suppressor_bypass = int(bool(cfg.suppressor_bypass))
         P.clip_rain_min_frames = int(max(1, int(clip_rain_min_frames)))
         P.fft_f64 = int(bool(fft_f64))
+
+        # --- suppressor gain (_compute_gain, rain_signal_processor.py:400-533).  noise_conf is binary on this
+        # path (1 - rain_conf), so the per-frame scalars take two values; they are formed here with the same
+        # numpy float32 / Python-float promotions the reference applies.
+        if bool(cfg.snr_gating_enable):
+            raise NotImplementedError("snr_gating_enable=True is not implemented on the CUDA path")
+        mode = str(cfg.gain_mode).lower()
+        P.gain_mode = 1 if mode == "wiener" else 0
+        P.adaptive_gain = int(bool(cfg.adaptive_gain_enable))
+        P.gain_freq_smooth = int(bool(cfg.gain_freq_smooth_enable))
+        P.use_lagged_noise_psd = int(bool(cfg.use_lagged_noise_psd))
+        th = 0.7
+        denom = max(1e-9, 1.0 - th)
+        nc = np.array([1.0, 0.0], dtype=np.float32)
+        if P.adaptive_gain:
+            eff = np.clip((nc - th) / denom, 0.0, 1.0)
+            oversub = cfg.oversub_base + eff * (cfg.oversub_max - cfg.oversub_base)
+        else:
+            eff = np.zeros(2, dtype=np.float32)
+            oversub = np.full(2, float(cfg.oversub_base), dtype=np.float32)
+        P.oversub_noise, P.oversub_rain = f32(oversub[0]), f32(oversub[1])
+        P.gain_floor, P.gain_ceil = f32(cfg.gain_floor), f32(cfg.gain_ceil)
+        kernel = np.asarray(cfg.gain_freq_kernel, dtype=np.float32).reshape(-1)
+        if kernel.size < 1:
+            kernel = np.array([1.0], dtype=np.float32)
+        kernel = kernel / (kernel.sum() + 1e-12)
+        if kernel.size > _lib.MAX_GAIN_TAPS or kernel.size % 2 == 0:
+            raise NotImplementedError("gain_freq_kernel must have an odd number of taps, at most %d" % _lib.MAX_GAIN_TAPS)
+        P.n_gain_taps = int(kernel.size)
+        for i in range(_lib.MAX_GAIN_TAPS):
+            P.gain_taps[i] = f32(kernel[i]) if i < kernel.size else f32(0.0)
+        alpha_base = float(np.clip(cfg.gain_smooth_alpha, 0.0, 1.0))
+        eff_nc = (np.float32(1.0) - th) / denom                  # np.float32, as for noise_conf[t] = 1
+        a_noise = alpha_base * eff_nc
+        P.alpha_noise, P.one_minus_alpha_noise = f32(a_noise), f32(1.0 - a_noise)
+        P.alpha_base, P.one_minus_alpha_base = f32(alpha_base), f32(1.0 - alpha_base)
+        P.gain_eps_f32 = f32(cfg.eps)
         P.window = self.window.ctypes.data_as(C.c_void_p)
         P.freqs = self.freqs.ctypes.data_as(C.c_void_p)
         self.c = P

@@ -194,6 +194,11 @@ int apt_params_default(apt_params_t* p) {
     p->blk_len = 8; p->blk_hop = 8; p->blk_post_pre = 4; p->blk_smooth = 1;
     p->low_lo = 2; p->low_hi = 4; p->rain_lo = 10; p->rain_hi = 18; p->rolloff_fraction = 0.85;
     p->suppressor_bypass = 0; p->clip_rain_min_frames = 1; p->fft_f64 = 1;
+    p->gain_mode = 0; p->adaptive_gain = 1; p->gain_freq_smooth = 1; p->n_gain_taps = 3; p->use_lagged_noise_psd = 0;
+    p->oversub_noise = 3.0f; p->oversub_rain = 1.0f; p->gain_floor = 0.0f; p->gain_ceil = 1.0f;
+    p->gain_taps[0] = 0.2f; p->gain_taps[1] = 0.6f; p->gain_taps[2] = 0.2f;
+    p->alpha_noise = 0.7f; p->one_minus_alpha_noise = 0.3f; p->alpha_base = 0.7f; p->one_minus_alpha_base = 0.3f;
+    p->gain_eps_f32 = 1e-9f;
     return 0;
 }
 
@@ -243,6 +248,15 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     d.blk_len = p->blk_len; d.blk_hop = p->blk_hop; d.blk_pp = p->blk_post_pre; d.blk_smooth = p->blk_smooth;
     d.low_lo = p->low_lo; d.low_hi = p->low_hi; d.rain_lo = p->rain_lo; d.rain_hi = p->rain_hi; d.rolloff = p->rolloff_fraction;
     d.suppressor_bypass = p->suppressor_bypass; d.min_frames = p->clip_rain_min_frames;
+    d.gain_mode = p->gain_mode; d.adaptive_gain = p->adaptive_gain; d.gain_freq_smooth = p->gain_freq_smooth;
+    d.n_gain_taps = p->n_gain_taps; d.use_lagged = p->use_lagged_noise_psd;
+    d.oversub_noise = p->oversub_noise; d.oversub_rain = p->oversub_rain; d.gain_floor = p->gain_floor; d.gain_ceil = p->gain_ceil;
+    for (int i = 0; i < APT_MAX_GAIN_TAPS; i++) d.gain_taps[i] = p->gain_taps[i];
+    d.alpha_noise = p->alpha_noise; d.om_noise = p->one_minus_alpha_noise; d.alpha_base = p->alpha_base; d.om_base = p->one_minus_alpha_base;
+    d.gain_eps = p->gain_eps_f32;
+    if (p->n_gain_taps < 1 || p->n_gain_taps > APT_MAX_GAIN_TAPS || (p->n_gain_taps & 1) == 0) {
+        delete pl; return fail(ctx, -32, "n_gain_taps=%d must be odd and <= %d", p->n_gain_taps, APT_MAX_GAIN_TAPS);
+    }
     // TD prefilter: n_sos == 0 is run as one identity section
     double sos[APT_MAX_SOS][6];
     int ns = p->n_sos;
@@ -535,6 +549,24 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             const int64_t lanes = (int64_t)n_clips * d.K;
             trk2_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, io);
             pl->last_launches++;
+            CUDA_OK(ctx, cudaGetLastError());
+        }
+        if (out->G || out->S_hat) {
+            pl->mark(APT_KERNEL_GAIN, st);
+            if (!out->G) return fail(ctx, -33, "S_hat requires the G buffer");
+            if (out->S_hat && !out->S) return fail(ctx, -33, "S_hat requires the S buffer");
+            GainIO gio;
+            gio.P_band = pl->d_Pband.p; gio.N2 = n2_plane; gio.frame_class = out->frame_class; gio.G = out->G;
+            gio.ratio_med = out->ratio_med; gio.nF = pl->nF;
+            gain_kernel<<<tile_grid(pl->flux_tile_off, clip0, n_clips), 256, 0, st>>>(pl->dp, b, pl->d_flux_tile_off.p, gio);
+            const int64_t lanes = (int64_t)n_clips * d.K;
+            gain_time_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, out->frame_class, out->G);
+            pl->last_launches += 2;
+            if (out->S_hat) {
+                const int64_t n = (fend - fbeg) * d.F;
+                shat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pl->dp, fbeg, fend, out->G, out->S, out->S_hat);
+                pl->last_launches++;
+            }
             CUDA_OK(ctx, cudaGetLastError());
         }
         pl->mark(APT_KERNEL_DB, st);

@@ -58,6 +58,11 @@ struct DevParams {
     double rolloff;
     int suppressor_bypass;
     int min_frames;
+    // suppressor gain
+    int gain_mode, adaptive_gain, gain_freq_smooth, n_gain_taps, use_lagged;
+    float oversub_noise, oversub_rain, gain_floor, gain_ceil;
+    float gain_taps[APT_MAX_GAIN_TAPS];
+    float alpha_noise, om_noise, alpha_base, om_base, gain_eps;
 };
 
 // A launch covers clips [clip0, clip0 + n_clips) of the plan; the offset arrays are the plan's
@@ -1306,6 +1311,129 @@ __global__ void __launch_bounds__(128) trk2_kernel(const __grid_constant__ DevPa
             if (L.store) Nk[(size_t)t * K] = n2;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K10: suppressor gain (rain_signal_processor.py:400-533 _compute_gain, :1028-1091).  Runs only when the
+// caller asks for G / S_hat (the reference computes it always and discards it under default flags).
+// noise_conf is binary on this path (1 - rain_conf): RAIN frames are "rain-like", all others noise-like.
+//   gain_kernel       parallel: N_eff = min(N2[lag], maxr P), ratio, raw gain, clip, frequency smoothing
+//                     (np.convolve 'same'), per-frame median of the ratio
+//   gain_time_kernel  serial in time, lane = (clip, bin): confidence-dependent temporal smoothing, clip
+//   shat_kernel       parallel: S_hat = G * S
+// ---------------------------------------------------------------------------------------------
+struct GainIO {
+    const float* P_band; const float* N2; const int8_t* frame_class;
+    float* G;            // [nF][K]
+    float* ratio_med;    // optional [nF]
+    int64_t nF;
+};
+constexpr int GAIN_FT = 8;        // frames per inner batch (one warp per frame for the median)
+constexpr int GAIN_HALF = APT_MAX_GAIN_TAPS / 2;
+
+__global__ void __launch_bounds__(256) gain_kernel(const __grid_constant__ DevParams p, Batch b,
+                                                   const int64_t* __restrict__ tile_off, GainIO io) {
+    __shared__ float s_g[GAIN_FT][SEQ_KMAX + 2 * GAIN_HALF];
+    __shared__ float s_r[GAIN_FT][SEQ_KMAX];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int64_t tile_in_clip;
+    int c;
+    if (!tile_clip(b, tile_off, c, tile_in_clip)) return;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int t0 = (int)tile_in_clip * FLUX_FT, t1 = min(T, t0 + FLUX_FT);
+    const int K = p.K, nt = p.n_gain_taps, h = nt / 2;
+    for (int i = tid; i < GAIN_FT * (SEQ_KMAX + 2 * GAIN_HALF); i += 256) (&s_g[0][0])[i] = 0.0f;
+    for (int tb = t0; tb < t1; tb += GAIN_FT) {
+        __syncthreads();
+        for (int idx = tid; idx < GAIN_FT * K; idx += 256) {
+            const int tt = idx / K, k = idx - tt * K;
+            const int t = tb + tt;
+            if (t >= t1) continue;
+            const float pk = __ldg(io.P_band + (f0 + t) * K + k);
+            const int tl = (p.use_lagged && t > 0) ? t - 1 : t;
+            const float n = __ldg(io.N2 + (f0 + tl) * K + k);
+            const float neff = f_min(n, p.trk_maxr * pk);
+            const float ratio = f_div(neff, pk + p.gain_eps);
+            s_r[tt][k] = ratio;
+            const bool rain = __ldg(io.frame_class + f0 + t) == 2;
+            const float osub = rain ? p.oversub_rain : p.oversub_noise;
+            float g;
+            if (p.gain_mode == 0) {
+                const float r = f_min(f_max(ratio, 0.0f), 1.0f);
+                g = 1.0f - osub * f_sqrt(r);
+            } else {
+                g = f_div(f_max(pk - osub * neff, 0.0f), pk + p.gain_eps);
+            }
+            s_g[tt][GAIN_HALF + k] = f_min(f_max(g, p.gain_floor), p.gain_ceil);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < GAIN_FT * K; idx += 256) {
+            const int tt = idx / K, k = idx - tt * K;
+            const int t = tb + tt;
+            if (t >= t1) continue;
+            const bool rain = __ldg(io.frame_class + f0 + t) == 2;
+            const bool smooth = p.gain_freq_smooth && nt > 1 && (!p.adaptive_gain || !rain);
+            float g = s_g[tt][GAIN_HALF + k];
+            if (smooth) {
+                // np.convolve(g, v, 'same') == correlate with the reversed kernel: sum_i g[k-h+i] * v[nt-1-i]
+                float acc = 0.0f;
+                for (int i = 0; i < nt; i++) acc += s_g[tt][GAIN_HALF + k - h + i] * p.gain_taps[nt - 1 - i];
+                g = acc;
+            }
+            io.G[(f0 + t) * K + k] = g;
+        }
+        if (io.ratio_med && w < GAIN_FT && tb + w < t1) {
+            // np.median over the band: element(s) of rank (K-1)/2 and K/2 by counting
+            const float* r = s_r[w];
+            float lo = 0.0f, hi = 0.0f;
+            for (int k = lane; k < K; k += 32) {
+                const float v = r[k];
+                int rank = 0;
+                for (int j = 0; j < K; j++) rank += (r[j] < v) || (r[j] == v && j < k);
+                if (rank == (K - 1) / 2) lo = v;
+                if (rank == K / 2) hi = v;
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, d); hi += __shfl_xor_sync(0xffffffffu, hi, d); }
+            if (lane == 0) io.ratio_med[f0 + tb + w] = (K & 1) ? lo : f_div(lo + hi, 2.0f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) gain_time_kernel(const __grid_constant__ DevParams p, Batch b,
+                                                        const int8_t* __restrict__ frame_class, float* __restrict__ G) {
+    const int K = p.K;
+    const SerialLane L = serial_lane(b, K);
+    float* Gk = G + L.f0 * K + L.sub;
+    const int8_t* fc = frame_class + L.f0;
+    float gt = 0.0f;
+    for (int t = 0; t < L.T; t++) {
+        const float gf = Gk[(size_t)t * K];
+        if (t == 0) gt = gf;
+        else if (p.adaptive_gain) {
+            // rain-like frames (noise_conf < 0.7): no temporal smoothing; others: alpha = alpha_base * eff_nc
+            gt = (__ldg(fc + t) == 2) ? gf : p.alpha_noise * gt + p.om_noise * gf;
+        } else {
+            gt = p.alpha_base * gt + p.om_base * gf;
+        }
+        if (L.store) Gk[(size_t)t * K] = f_min(f_max(gt, p.gain_floor), p.gain_ceil);
+    }
+}
+
+__global__ void __launch_bounds__(256) shat_kernel(const __grid_constant__ DevParams p, int64_t g0, int64_t g1,
+                                                   const float* __restrict__ G, const float* __restrict__ S,
+                                                   float* __restrict__ S_hat) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (frame, bin) flat over the launch's frames
+    const int64_t n = (g1 - g0) * p.F;
+    if (i >= n) return;
+    const int64_t fr = g0 + i / p.F;
+    const int f = (int)(i % p.F);
+    const int k = f - p.band_lo;
+    const float g = (k >= 0 && k < p.K) ? G[fr * p.K + k] : 1.0f;
+    const int64_t o = (fr * p.F + f) * 2;
+    S_hat[o] = g * S[o];
+    S_hat[o + 1] = g * S[o + 1];
 }
 
 // ---------------------------------------------------------------------------------------------

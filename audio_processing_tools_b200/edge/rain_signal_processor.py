@@ -95,8 +95,11 @@ class SpectralNoiseProcessor:
         keep_noise = bool(cfg.return_noise_psd)
         keep_filt = bool(cfg.return_filtered_audio)
         want = []
+        suppress = not (bool(cfg.suppressor_bypass) or bool(cfg.classifier_only_mode))
         if keep_debug:
             want += ["det_noise_psd", "det_noise_lag", "noise_psd"]
+            if suppress:
+                want += ["G", "ratio_med"]
         if keep_noise and "noise_psd" not in want:
             want.append("noise_psd")
         if keep_det:
@@ -105,6 +108,8 @@ class SpectralNoiseProcessor:
                 want.append("raw")
         if keep_spectra:
             want.append("S")
+            if suppress:
+                want += ["S_hat"] + ([] if "G" in want else ["G"])
         if keep_filt:
             want.append("x_td")
         arrays = []
@@ -141,7 +146,10 @@ class SpectralNoiseProcessor:
             if keep_spectra:
                 S = np.asfortranarray(out["S"][f0:f1].view(np.complex64).reshape(T, rp.F).T)
                 res["S"] = S
-                res["S_hat"] = S if (bool(cfg.classifier_only_mode) or bool(cfg.suppressor_bypass)) else None
+                if suppress:
+                    res["S_hat"] = np.asfortranarray(out["S_hat"][f0:f1].view(np.complex64).reshape(T, rp.F).T)
+                else:
+                    res["S_hat"] = S.copy()
             if keep_noise and not bool(cfg.classifier_only_mode):
                 res["noise_psd"] = self._embed(out["noise_psd"][f0:f1], rp)
             if with_stats:
@@ -152,10 +160,10 @@ class SpectralNoiseProcessor:
         return results
 
     @staticmethod
-    def _embed(plane_tk: np.ndarray, rp) -> np.ndarray:
-        """[T][K] band plane -> (F, T) float32 with exact zeros off-band (Fortran order like the reference)."""
+    def _embed(plane_tk: np.ndarray, rp, fill: float = 0.0) -> np.ndarray:
+        """[T][K] band plane -> (F, T) float32 with `fill` off-band (Fortran order like the reference)."""
         T = plane_tk.shape[0]
-        full = np.zeros((rp.F, T), dtype=np.float32, order="F")
+        full = np.full((rp.F, T), fill, dtype=np.float32, order="F")
         full[rp.c.band_lo:rp.c.band_hi + 1, :] = plane_tk.T
         return full
 
@@ -208,6 +216,11 @@ class SpectralNoiseProcessor:
             "use_for_noise_psd": use,
             "is_rain_for_psd": ~use,
             "noise_psd": self._embed(out["noise_psd"][f0:f1], rp),
+            "G": (self._embed(out["G"][f0:f1], rp, fill=1.0) if "G" in out
+                  else np.ones((rp.F, f1 - f0), dtype=np.float32, order="F")),
+            "np_ratio_median_t": (out["ratio_med"][f0:f1].copy() if "ratio_med" in out
+                                  else np.zeros(f1 - f0, dtype=np.float32)),
+            "use_lagged_noise_psd": bool(cfg.use_lagged_noise_psd),
             "operating_band": (float(cfg.operating_band[0]), float(cfg.operating_band[1])),
             "band_mask": rp.band_mask.copy(),
             "pre_filter_mode": str(cfg.pre_filter_mode).lower(),

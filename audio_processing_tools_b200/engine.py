@@ -30,6 +30,9 @@ _PLANES = {
     "band_energy": ("float32", lambda nF, nS, rp: (rp.M + 1, nF)),
     "gate": ("uint8", lambda nF, nS, rp: (nF,)),
     "x_td": ("float32", lambda nF, nS, rp: (nS,)),
+    "G": ("float32", lambda nF, nS, rp: (nF, rp.K)),
+    "ratio_med": ("float32", lambda nF, nS, rp: (nF,)),
+    "S_hat": ("float32", lambda nF, nS, rp: (nF, rp.F, 2)),
 }
 _CORE = {
     "frame_class": ("int8", lambda nF, nC: (nF,)),

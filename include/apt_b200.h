@@ -38,7 +38,8 @@ extern "C" {
 #define APT_N_RAW_FEATURES 21 /* feature_extraction.py:9-31 RAW_SPECTRAL_FEATURE_NAMES */
 #define APT_N_TD_FEATURES 5   /* crest, kurtosis, block crest, block width50, block post/pre */
 #define APT_N_CLIP_STATS 8
-#define APT_ABI_VERSION 1
+#define APT_MAX_GAIN_TAPS 9
+#define APT_ABI_VERSION 2
 
 typedef struct apt_ctx apt_ctx;
 typedef struct apt_plan apt_plan_t;
@@ -92,7 +93,16 @@ typedef struct apt_params_t {
     /* arithmetic of the STFT: 1 = float64 FFT rounded to complex64 (the reference's arithmetic,
        librosa/scipy.fft on float64), 0 = float32 FFT (faster, spectra within 1e-6 of frame max) */
     int32_t fft_f64;
-    int32_t reserved0;
+    /* suppressor gain, rain_signal_processor.py:400-533 (_compute_gain) and :1028-1091; float32 values are
+       the ones numpy forms when the reference mixes Python floats with float32 arrays */
+    int32_t gain_mode;                         /* 0 = sqrt_sub (default), 1 = wiener */
+    int32_t adaptive_gain, gain_freq_smooth, n_gain_taps, use_lagged_noise_psd;
+    float   oversub_noise, oversub_rain;       /* oversubtraction at noise_conf = 1 / 0 (:436-437) */
+    float   gain_floor, gain_ceil;
+    float   gain_taps[APT_MAX_GAIN_TAPS];      /* normalised frequency-smoothing kernel (:484-487) */
+    float   alpha_noise, one_minus_alpha_noise;/* temporal smoothing on noise-like frames (:508-516) */
+    float   alpha_base, one_minus_alpha_base;  /* non-adaptive mode (:522-523) */
+    float   gain_eps_f32;
     /* host pointers, copied at plan creation */
     const double* window;                      /* n_fft analysis window (scipy get_window) */
     const float*  freqs;                       /* n_fft/2+1 bin frequencies as float32 */
@@ -128,6 +138,9 @@ typedef struct apt_out_t {
     float*   band_energy;     /* [M+1][nF]  mode-band powers + operating-band energy (float64 sums) */
     uint8_t* gate;            /* [nF]       td_gate_mask */
     float*   x_td;            /* [nS]       zero-phase prefiltered waveform */
+    float*   G;               /* [nF][K]    suppressor gain over the band (debug["G"][band]) */
+    float*   ratio_med;       /* [nF]       debug["np_ratio_median_t"] */
+    float*   S_hat;           /* [nF][F][2] gain-weighted spectrum (state["S_hat"]); needs S */
 } apt_out_t;
 
 /* which stages a run executes */
@@ -176,7 +189,8 @@ int  apt_plan_last_launches(const apt_plan_t* plan);
 #define APT_KERNEL_DB 7        /* db_kernel: noise-floor dB plane, sums, level-0 histogram */
 #define APT_KERNEL_SELECT 8    /* select_hist/scan: median levels 1-2 */
 #define APT_KERNEL_FINALIZE 9  /* finalize_kernel */
-#define APT_N_KERNELS 10
+#define APT_KERNEL_GAIN 10     /* gain_kernel + gain_time_kernel (+ shat_kernel): only when G / S_hat is requested */
+#define APT_N_KERNELS 11
 int  apt_plan_enable_timing(apt_plan_t* plan, int enable);
 int  apt_plan_kernel_ms(apt_plan_t* plan, float* out_ms /* [APT_N_KERNELS] */);
 

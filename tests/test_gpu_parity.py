@@ -15,7 +15,7 @@ from audio_processing_tools_b200.synth import default_params, pcm_to_f32, synth_
 pytestmark = pytest.mark.gpu
 
 ALL_PLANES = ("S", "P", "det_noise_psd", "det_noise_lag", "D", "noise_psd", "mode_flux", "norm_flux",
-              "score", "td", "raw", "band_energy", "gate", "x_td")
+              "score", "td", "raw", "band_energy", "gate", "x_td", "G", "ratio_med", "S_hat")
 
 
 @pytest.fixture(scope="module")
@@ -77,6 +77,13 @@ def test_full_planes_match_reference_golden(torch_cuda, name):
     assert int(st[1]) == int(g["metric_rain_frame_count"])
     assert st[6] == pytest.approx(float(g["metric_mean_noise_floor_db"]), rel=1e-5)
     assert st[7] == pytest.approx(float(g["metric_median_noise_floor_db"]), rel=1e-6)
+    # suppressor gain (rain_signal_processor.py:400-533): <= 1e-5 (float32 sums of a 3-tap kernel in another order)
+    np.testing.assert_allclose(out["G"], g["G_band"], rtol=1e-5, atol=2e-7)
+    np.testing.assert_allclose(out["ratio_med"], g["np_ratio_median_t"], rtol=1e-6, atol=1e-12)
+    G_full = np.ones((T, S.shape[1]), np.float32)
+    G_full[:, 10:81] = g["G_band"]
+    S_hat = out["S_hat"].view(np.complex64).reshape(T, -1)
+    np.testing.assert_allclose(S_hat, G_full * g["S"], rtol=1e-5, atol=1e-9)
     eng.close()
 
 
