@@ -69,14 +69,16 @@ struct apt_plan {
     DevBuf<double> d_dbsum;   // [select chunks] float64 sums of the dB plane
     Trk1Tab tab_modes, tab_all;   // pass-1 lane tables: mode bins only / every band bin (debug planes)
     int mf_stride = 8;
+    bool generic = false;   // features stage only, generic frame size
+    DevBuf<double> d_gwin64; DevBuf<cx<double>> d_gtw64; DevBuf<float> d_gwin32; DevBuf<cx<float>> d_gtw32;
     DevBuf<SelState> d_sel;
     DevBuf<uint32_t> d_hist;
     DevBuf<int> d_counter;
     // host-path staging
     DevBuf<int16_t> d_pcm;
     DevBuf<int8_t> d_fc; DevBuf<float> d_rc, d_nc, d_stats; DevBuf<int32_t> d_ev, d_evc;
-    static constexpr int N_COMP = 3;
-    cudaStream_t s_copy = nullptr, s_comp[N_COMP] = {nullptr, nullptr, nullptr};
+    static constexpr int N_COMP = 4;
+    cudaStream_t s_copy = nullptr, s_comp[N_COMP] = {nullptr, nullptr, nullptr, nullptr};
     int last_launches = 0;
     size_t scratch_bytes = 0;
     // optional per-kernel timing (CUDA events on the launch stream)
@@ -208,11 +210,14 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     if (n_clips > 65535) return fail(ctx, -1, "apt_plan_create: at most 65535 clips per plan (grid.y limit), got %d", n_clips);
     *out = nullptr;
     if (p->abi_version != APT_ABI_VERSION) return fail(ctx, -20, "params abi_version %d != %d", p->abi_version, APT_ABI_VERSION);
-    if (p->n_fft != 256 || p->hop < 1 || p->hop > 256 || 256 % p->hop != 0 || p->hop != 128)
-        return fail(ctx, -21, "unsupported STFT geometry n_fft=%d hop=%d (this build: n_fft=256, hop=128)", p->n_fft, p->hop);
+    // (256, 128) runs the full pipeline on the specialised kernels; any other power-of-two frame size up to 4096
+    // with 1 <= hop <= n_fft runs the features stage (STFT, power, band energies, raw features) on the generic kernel
+    if (p->n_fft < 256 || p->n_fft > 4096 || (p->n_fft & (p->n_fft - 1)) != 0 || p->hop < 1 || p->hop > p->n_fft)
+        return fail(ctx, -21, "unsupported STFT geometry n_fft=%d hop=%d (power of two 256..4096, 1 <= hop <= n_fft)", p->n_fft, p->hop);
+    const bool generic = !(p->n_fft == 256 && p->hop == 128);
     const int F = p->n_fft / 2 + 1;
     const int K = p->band_hi - p->band_lo + 1;
-    if (p->band_lo < 0 || p->band_hi >= F || K < 1 || K > SEQ_KMAX) return fail(ctx, -22, "operating band bins [%d,%d] unsupported", p->band_lo, p->band_hi);
+    if (p->band_lo < 0 || p->band_hi >= F || K < 1 || (!generic && K > SEQ_KMAX)) return fail(ctx, -22, "operating band bins [%d,%d] unsupported", p->band_lo, p->band_hi);
     if (p->n_modes < 4 || p->n_modes > APT_MAX_MODES) return fail(ctx, -23, "n_modes=%d outside [4,%d]", p->n_modes, APT_MAX_MODES);
     if (p->n_sos < 0 || p->n_sos > APT_MAX_SOS) return fail(ctx, -24, "n_sos=%d outside [0,%d]", p->n_sos, APT_MAX_SOS);
     if (!p->window || !p->freqs) return fail(ctx, -25, "window / freqs tables missing");
@@ -223,6 +228,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     apt_plan* pl = new apt_plan();
     pl->ctx = ctx;
     pl->prm = *p;
+    pl->generic = generic;
     pl->n_clips = n_clips;
     DevParams& d = pl->dp;
     memset(&d, 0, sizeof(d));
@@ -285,7 +291,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         const int64_t Tloc = 1 + (N - p->n_fft) / p->hop;
         pl->samp_off[c + 1] = pl->samp_off[c] + N;
         pl->frame_off[c + 1] = pl->frame_off[c] + T;
-        pl->stft_tile_off[c + 1] = pl->stft_tile_off[c] + (T + STFT_TF - 1) / STFT_TF;
+        pl->stft_tile_off[c + 1] = pl->stft_tile_off[c] + (generic ? T : (T + STFT_TF - 1) / STFT_TF);
         pl->td_tile_off[c + 1] = pl->td_tile_off[c] + std::max<int64_t>(1, (Tloc + TD_FT - 1) / TD_FT);
         pl->sel_chunk_off[c + 1] = pl->sel_chunk_off[c] + (T * K + SEL_CHUNK - 1) / SEL_CHUNK;
         pl->flux_tile_off[c + 1] = pl->flux_tile_off[c] + (T + FLUX_FT - 1) / FLUX_FT;
@@ -301,6 +307,22 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     PL_OK(upload(pl->d_sel_chunk_off, pl->sel_chunk_off));
     PL_OK(upload(pl->d_flux_tile_off, pl->flux_tile_off));
 
+    if (generic) {
+        const int N = p->n_fft;
+        std::vector<double> w64(p->window, p->window + N);
+        std::vector<float> w32(N);
+        for (int i = 0; i < N; i++) w32[i] = (float)w64[i];
+        std::vector<cx<double>> tw(N / 2 + 1);
+        std::vector<cx<float>> twf(N / 2 + 1);
+        for (int k = 0; k <= N / 2; k++) { tw[k] = {cos(2.0 * M_PI * k / N), -sin(2.0 * M_PI * k / N)}; twf[k] = {(float)tw[k].x, (float)tw[k].y}; }
+        PL_OK(upload(pl->d_gwin64, w64)); PL_OK(upload(pl->d_gtw64, tw)); PL_OK(upload(pl->d_gwin32, w32)); PL_OK(upload(pl->d_gtw32, twf));
+        std::vector<float> fr(p->freqs, p->freqs + F);
+        PL_OK(upload(pl->d_freqs, fr));
+        PL_OK(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < apt_plan::N_COMP; i++) PL_OK(cudaStreamCreateWithFlags(&pl->s_comp[i], cudaStreamNonBlocking));
+        *out = pl;
+        return 0;
+    }
     // FFT tables
     {
         std::vector<double> w64(p->window, p->window + 256);
@@ -443,6 +465,20 @@ static cudaError_t launch_stft(apt_plan* pl, const Batch& b, const PCM* pcm, con
     return cudaGetLastError();
 }
 
+template <typename T, typename PCM>
+static cudaError_t launch_stft_generic(apt_plan* pl, const Batch& b, const PCM* pcm, const StftOut& so, cudaStream_t st) {
+    FftTablesG<T> tab;
+    if constexpr (sizeof(T) == 8) { tab.win = pl->d_gwin64.p; tab.tw = pl->d_gtw64.p; }
+    else { tab.win = pl->d_gwin32.p; tab.tw = pl->d_gtw32.p; }
+    const size_t smem = stftg_smem_bytes<T>(pl->dp.n_fft);
+    auto kern = stft_generic_kernel<T, PCM>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<tile_grid(pl->stft_tile_off, b.clip0, b.n_clips), STFTG_NT, smem, st>>>(pl->dp, b, pcm, tab, so);
+    pl->last_launches++;
+    return cudaGetLastError();
+}
+
 template <int NS, typename PCM>
 static cudaError_t launch_td_ns(apt_plan* pl, const Batch& b, const PCM* pcm, const TdOut& to, cudaStream_t st) {
     const int64_t tiles = pl->td_tile_off[b.clip0 + b.n_clips] - pl->td_tile_off[b.clip0];
@@ -475,6 +511,17 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         return fail(ctx, -30, "full pipeline requires frame_class, rain_conf, noise_conf, event_idx, event_count, clip_stats buffers");
     if (!full && !(out->band_energy || out->P || out->S || out->raw))
         return fail(ctx, -31, "features stage requires at least one of band_energy / P / S / raw");
+    if (pl->generic) {
+        if (full) return fail(ctx, -34, "the full pipeline runs at n_fft=256 / hop=128 only; n_fft=%d hop=%d supports the features stage", d.n_fft, d.hop);
+        StftOut sg;
+        sg.S = out->S; sg.P = out->P; sg.P_band = nullptr; sg.band_energy = out->band_energy;
+        sg.raw = out->raw; sg.freqs = pl->d_freqs.p; sg.nF = pl->nF;
+        pl->mark(APT_KERNEL_STFT, st);
+        cudaError_t eg = pl->prm.fft_f64 ? launch_stft_generic<double, PCM>(pl, b, pcm, sg, st) : launch_stft_generic<float, PCM>(pl, b, pcm, sg, st);
+        if (eg != cudaSuccess) return fail(ctx, -11, "stft launch failed: %s", cudaGetErrorString(eg));
+        pl->mark(-1, st);
+        return 0;
+    }
 
     StftOut so;
     so.S = out->S; so.P = out->P; so.P_band = full ? pl->d_Pband.p : nullptr; so.band_energy = out->band_energy;
@@ -635,7 +682,9 @@ int apt_run_host_i16(apt_plan_t* pl, const int16_t* host_pcm, int8_t* frame_clas
     // alternate over N_COMP compute streams so that the latency-bound serial kernels of one group (few warps,
     // fixed duration whatever the group size) overlap the wide kernels of its neighbours; each group's results
     // go back on its own compute stream (the device->host copy engine is separate from the host->device one).
-    const int n_groups = std::min(pl->n_clips, 8);
+    int want_groups = 24;
+    if (const char* e = getenv("APT_HOST_GROUPS")) want_groups = std::max(1, atoi(e));
+    const int n_groups = std::min(pl->n_clips, want_groups);
     std::vector<cudaEvent_t> ev(n_groups, nullptr);
     const bool was_timing = pl->timing;
     pl->timing = false;   // per-kernel event marks assume one stream

@@ -300,6 +300,96 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1+K2+K3 for any power-of-two frame size 256..4096 and any hop (BASELINE config 5, features stage):
+// one CTA per frame.  The real frame is packed into n_fft/2 complex points, transformed by a
+// shared-memory radix-2 Stockham FFT (autosort, ping-pong buffers, twiddles W_N^k from a table), and
+// unpacked to the n_fft/2+1 rfft bins.  Arithmetic type T as in stft256_kernel (float64 = reference).
+// ---------------------------------------------------------------------------------------------
+constexpr int STFTG_NT = 256;
+template <typename T>
+struct FftTablesG {
+    const T* win;        // [n_fft]
+    const cx<T>* tw;     // [n_fft/2 + 1]  W_N^k
+};
+template <typename T>
+inline size_t stftg_smem_bytes(int n_fft) {
+    return sizeof(cx<T>) * (size_t)n_fft + sizeof(float) * (size_t)(n_fft / 2 + 4);
+}
+
+template <typename T, typename PCM>
+__global__ void __launch_bounds__(STFTG_NT) stft_generic_kernel(const __grid_constant__ DevParams p, Batch b,
+                                                                const PCM* __restrict__ pcm, FftTablesG<T> tab, StftOut o) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = p.n_fft, H = N >> 1, F = H + 1;
+    cx<T>* bufA = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* bufB = bufA + H;
+    float* s_P = reinterpret_cast<float*>(bufB + H);
+    const int tid = threadIdx.x;
+    const int c = b.clip0 + (int)blockIdx.y;
+    const int64_t base = __ldg(b.samp_off + c);
+    const int64_t Ns = __ldg(b.samp_off + c + 1) - base;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T_clip = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int t = blockIdx.x;
+    if (t >= T_clip) return;
+    // windowed frame, centre-padded with zeros (librosa center=True, pad_mode="constant")
+    const int64_t s0 = (int64_t)t * p.hop - H;
+    for (int n = tid; n < H; n += STFTG_NT) {
+        const int64_t sa = s0 + 2 * n, sb = sa + 1;
+        const T xa = (sa >= 0 && sa < Ns) ? (T)load_sample(pcm, base + sa) : (T)0;
+        const T xb = (sb >= 0 && sb < Ns) ? (T)load_sample(pcm, base + sb) : (T)0;
+        bufA[n] = {tab.win[2 * n] * xa, tab.win[2 * n + 1] * xb};
+    }
+    __syncthreads();
+    cx<T>* x = bufA;
+    cx<T>* y = bufB;
+    for (int q = 1; q < H; q <<= 1) {   // radix-2 Stockham passes, q = 1, 2, ..., H/2
+        const int tstep = H / q;        // W_{2q}^k = W_N^{k * N / (2q)} = W_N^{k * H / q}
+        for (int i = tid; i < (H >> 1); i += STFTG_NT) {
+            const int k = i & (q - 1);
+            const int j = ((i - k) << 1) + k;
+            const cx<T> u0 = x[i];
+            const cx<T> xv = x[i + (H >> 1)];
+            const cx<T> u1 = (k == 0) ? xv : cmul(xv, tab.tw[k * tstep]);
+            y[j] = cadd(u0, u1);
+            y[j + q] = csub(u0, u1);
+        }
+        __syncthreads();
+        cx<T>* tmp = x; x = y; y = tmp;
+    }
+    // real-FFT unpack: X[k] = E + W_N^k O with E = (Z[k] + conj(Z[H-k]))/2, O = (Z[k] - conj(Z[H-k]))/(2i)
+    float* Sg = o.S ? o.S + ((f0 + t) * (int64_t)F) * 2 : nullptr;
+    const T half = (T)0.5;
+    for (int k = tid; k < F; k += STFTG_NT) {
+        T re, im;
+        if (k == 0) { re = x[0].x + x[0].y; im = (T)0; }
+        else if (k == H) { re = x[0].x - x[0].y; im = (T)0; }
+        else {
+            const cx<T> zk = x[k], cn = cconj(x[H - k]);
+            const cx<T> e = {(zk.x + cn.x) * half, (zk.y + cn.y) * half};
+            const cx<T> d = csub(zk, cn);
+            const cx<T> od = {d.y * half, -d.x * half};
+            const cx<T> wo = cmul(od, tab.tw[k]);
+            re = e.x + wo.x; im = e.y + wo.y;
+        }
+        const float sr = d2f((double)re), si = d2f((double)im);
+        if (Sg) { Sg[2 * k] = sr; Sg[2 * k + 1] = si; }
+        const float a = np_cabsf(sr, si);
+        s_P[k] = a * a;
+    }
+    __syncthreads();
+    const int64_t fr = f0 + t;
+    if (o.P) for (int k = tid; k < F; k += STFTG_NT) o.P[fr * F + k] = s_P[k];
+    if (o.band_energy && tid <= p.M) {
+        double s = 0.0;
+        if (tid < p.M) { for (int k = p.mode_lo[tid]; k <= p.mode_hi[tid]; k++) s += (double)s_P[k]; }
+        else { for (int k = 0; k < p.K; k++) s += (double)s_P[p.band_lo + k]; s += p.eps64; }
+        o.band_energy[(int64_t)tid * o.nF + fr] = d2f(s);
+    }
+    if (o.raw && tid == 0) raw_features_frame(p, s_P, o.freqs, o.raw + fr, o.nF);
+}
+
 // raw spectral features of one frame in float64 (feature_extraction.py:610-747)
 __device__ void raw_features_frame(const DevParams& p, const float* __restrict__ Pt, const float* __restrict__ freqs,
                                    float* __restrict__ out, int64_t stride) {

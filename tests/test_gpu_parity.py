@@ -245,3 +245,32 @@ def test_host_path_and_errors(torch_cuda):
         proc.run(np.zeros(6 * 11162, np.float32), {"sample_rate": 11162, "check_duration": 6})
     with pytest.raises(NotImplementedError):
         proc.run(np.zeros(6 * 11162, np.float32), dict(params, adaptive_q_enable=True))
+
+
+@pytest.mark.parametrize("n_fft,hop", [(256, 64), (512, 256), (1024, 256), (2048, 1024), (4096, 1024)])
+@pytest.mark.parametrize("fft_f64", [True, False])
+def test_frame_size_sweep_features(torch_cuda, n_fft, hop, fft_f64):
+    """BASELINE config 5 (features stage): generic power-of-two STFT against the reference's spectra and
+    band-energy features; the float32 FFT variant within 1e-5 of the frame maximum."""
+    from test_oracle_golden import load_sweep
+    from audio_processing_tools_b200.edge.rain_signal_processor import RAW_SPECTRAL_FEATURE_NAMES
+    from audio_processing_tools_b200.engine import AptError
+    g, meta, params = load_sweep(n_fft, hop)
+    eng = make_engine(params, fft_f64=fft_f64)
+    plan, out = eng.run_clips([g["pcm"]], ("S", "P", "raw", "band_energy"), full=False)
+    T, F = g["S"].shape
+    assert plan.nF == T
+    S = out["S"].view(np.complex64).reshape(T, F)
+    assert frame_rel_err(S, g["S"]) <= (1e-6 if fft_f64 else 1e-5)
+    if fft_f64:
+        assert (S != g["S"]).mean() < 2e-3
+    P_ref = (np.abs(g["S"]).astype(np.float32)) ** 2
+    np.testing.assert_allclose(out["P"], P_ref, rtol=1e-4, atol=1e-6 * float(P_ref.max()))
+    if fft_f64:
+        for i, k in enumerate(RAW_SPECTRAL_FEATURE_NAMES):
+            np.testing.assert_allclose(out["raw"][i], g["det_" + k], rtol=1e-4, atol=1e-6, err_msg=k)
+    band = g["band_mask"]
+    np.testing.assert_allclose(out["band_energy"][-1], out["P"][:, band].astype(np.float64).sum(axis=1) + 1e-9, rtol=1e-6)
+    with pytest.raises(AptError):      # the full pipeline is planned for 256/128 only
+        eng.run_clips([g["pcm"]], ())
+    eng.close()

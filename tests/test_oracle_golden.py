@@ -100,3 +100,32 @@ def test_oracle_batch_driver_matches_single(oracle_mod):
         m, s = oracle_mod.run(pcm_to_f32(c), params)
         assert np.array_equal(fc, s["frame_class"])
         assert n == m["rain_frame_count"]
+
+
+SWEEP = ((256, 64), (512, 256), (1024, 256), (2048, 1024), (4096, 1024))
+
+
+def load_sweep(n_fft, hop):
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from audio_processing_tools_b200.synth import default_params
+    g = dict(np.load(os.path.join(GOLDEN_DIR, f"sweep_nfft{n_fft}_hop{hop}.npz"), allow_pickle=False))
+    meta = json.loads(str(g["meta"]))
+    assert hashlib.sha1(g["pcm"].tobytes()).hexdigest() == meta["pcm_sha1"]
+    params = default_params(check_duration=meta["seconds"], n_fft=n_fft, hop=hop)
+    return g, meta, params
+
+
+@pytest.mark.parametrize("n_fft,hop", SWEEP)
+def test_oracle_frame_size_sweep(oracle_mod, n_fft, hop):
+    """BASELINE config 5: the oracle's STFT and band-energy features at other frame sizes against the reference."""
+    g, meta, params = load_sweep(n_fft, hop)
+    s = oracle_mod.process(pcm_to_f32(g["pcm"]), dict(params, keep_state_debug=True))
+    assert s["S"].shape == g["S"].shape
+    err = np.abs(s["S"] - g["S"]).max(axis=1) / np.abs(g["S"]).max(axis=1)
+    assert err.max() <= 1e-6                      # float64 FFT rounded to complex64: other algorithm, same values
+    assert (s["S"] != g["S"]).mean() < 2e-3
+    for i, k in enumerate(oracle_mod.RAW_NAMES):
+        np.testing.assert_allclose(s["raw"][i], g["det_" + k], rtol=1e-4, atol=1e-6, err_msg=k)
