@@ -75,7 +75,7 @@ EXPORTS = ("apt_init", "apt_destroy", "apt_last_error", "apt_abi_version", "apt_
            "apt_sizeof_out", "apt_params_default", "apt_plan_create", "apt_plan_destroy",
            "apt_plan_offsets", "apt_plan_total_frames", "apt_plan_total_samples",
            "apt_plan_scratch_bytes", "apt_run_i16", "apt_run_f32", "apt_plan_last_launches",
-           "apt_run_host_i16", "apt_plan_enable_timing", "apt_plan_kernel_ms")
+           "apt_run_host_i16", "apt_plan_enable_timing", "apt_plan_kernel_ms", "apt_selftest")
 
 
 def build(force=False, verbose=False):
@@ -121,6 +121,7 @@ def load():
     L.apt_run_i16.argtypes = [vp, C.c_int, vp, C.POINTER(AptOut), vp]
     L.apt_run_f32.argtypes = [vp, C.c_int, vp, C.POINTER(AptOut), vp]
     L.apt_run_host_i16.argtypes = [vp] * 8
+    L.apt_selftest.argtypes = [vp, C.c_int, C.c_int64, i64p]
     L.apt_plan_enable_timing.argtypes = [vp, C.c_int]
     L.apt_plan_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     if L.apt_abi_version() != ABI_VERSION:

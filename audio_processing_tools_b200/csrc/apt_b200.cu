@@ -174,6 +174,23 @@ void apt_destroy(apt_ctx* ctx) { delete ctx; }
 
 const char* apt_last_error(apt_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (is a CUDA device visible?)"; }
 
+int apt_selftest(apt_ctx* ctx, int which, int64_t n, int64_t* mismatches) {
+    if (!ctx || !mismatches) return -1;
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    unsigned long long* d = nullptr;
+    CUDA_OK(ctx, cudaMalloc((void**)&d, 8));
+    CUDA_OK(ctx, cudaMemset(d, 0, 8));
+    if (which == 0) selftest_sqrt_kernel<<<ctx->sm_count * 8, 256>>>(d);
+    else if (which == 1) selftest_div_kernel<<<ctx->sm_count * 8, 256>>>(d, (unsigned long long)n);
+    else { cudaFree(d); return fail(ctx, -1, "apt_selftest: unknown test %d", which); }
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, -10, "apt_selftest: %s", cudaGetErrorString(e));
+    *mismatches = (int64_t)h;
+    return 0;
+}
+
 int apt_params_default(apt_params_t* p) {
     if (!p) return -1;
     memset(p, 0, sizeof(*p));

@@ -30,6 +30,16 @@ __constant__ uint32_t kSvmlLog10TabDev[64] = {
     0x3ede5bd8, 0x3ede5b45, 0x3ede57d8, 0x3ede4eb1, 0x3ede3d37, 0x3ede2166, 0x3eddf9d9, 0x3eddc5bb,
     0x3ede08ed, 0x3ede32e7, 0x3ede4967, 0x3ede5490, 0x3ede597f, 0x3ede5b50, 0x3ede5bca, 0x3ede5bd9};
 
+#ifdef APT_PROFILE_PHASES
+// phase stamps of one interior tile (profiling builds only: profiles/micro/*_phases.cu)
+__device__ long long g_stamp[64];
+#define APT_STAMP(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 77 && blockIdx.y == 7) o.dbg[i] = clock64(); } while (0)
+#define APT_STAMP2(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 77 && blockIdx.y == 7) g_stamp[i] = clock64(); } while (0)
+#else
+#define APT_STAMP(i) do { } while (0)
+#define APT_STAMP2(i) do { } while (0)
+#endif
+
 struct DevParams {
     int n_fft, hop, F, band_lo, K, M;
     int mode_lo[APT_MAX_MODES], mode_hi[APT_MAX_MODES];
@@ -232,6 +242,7 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
     const int T_clip = (int)(__ldg(b.frame_off + c + 1) - f0);
     const int nfr = min(STFT_TF, T_clip - t0);
 
+    APT_STAMP2(20);
     for (int i = tid; i < 256; i += STFT_NT) s_win[i] = tab.win[i];
     for (int i = tid; i < 128; i += STFT_NT) s_tw128[i] = tab.tw128[i];
     for (int i = tid; i < 129; i += STFT_NT) s_tw256[i] = tab.tw256[i];
@@ -244,26 +255,28 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
             stage_clip_f32(pcm, base, N, s0, NS_, s_x);
     }
     __syncthreads();
+    APT_STAMP2(21);
 
     const int fr = tid >> 3, lane = tid & 7;
     const float* xs = s_x + fr * 128;
     cx<T>* ex = s_ex + (size_t)fr * kExSize;
     if (fr < nfr) rfft256_passA<T>(lane, [&](int n) { return xs[n]; }, s_win, s_tw128, ex);
     __syncthreads();
+    APT_STAMP2(22);
     if (fr < nfr) {
         float* Pt = s_P + fr * STFT_PS;
         float* Sg = o.S ? o.S + ((f0 + t0 + fr) * (int64_t)p.F) * 2 : nullptr;
         const bool need_full = o.S || o.P || o.raw || o.band_energy;
         const int klo = need_full ? 0 : p.band_lo, khi = need_full ? p.F - 1 : p.band_lo + p.K - 1;
         rfft256_passB<T>(lane, ex, s_tw256, [&](int k, T re, T im) {
-            if (k < klo || k > khi) return;
-            float sr = d2f((double)re), si = d2f((double)im);
+            const float sr = d2f((double)re), si = d2f((double)im);
             if (Sg) { Sg[2 * k] = sr; Sg[2 * k + 1] = si; }
-            float a = np_cabsf(sr, si);
-            Pt[k] = a * a;
+            const float a = np_cabsf_fast(sr, si);
+            if (k >= klo && k <= khi) Pt[k] = a * a;
         });
     }
     __syncthreads();
+    APT_STAMP2(23);
 
     // coalesced plane writes
     const int64_t fbase = f0 + t0;
@@ -298,6 +311,7 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
     if (o.raw) {
         if (tid < nfr) raw_features_frame(p, s_P + tid * STFT_PS, o.freqs, o.raw + fbase + tid, o.nF);
     }
+    APT_STAMP2(24);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -498,14 +512,7 @@ struct TdOut {
     long long* dbg;  // [16] clock64 stamps of one interior tile (profiling builds only)
 #endif
 };
-#ifdef APT_PROFILE_PHASES
-__device__ long long g_stamp[64];
-#define APT_STAMP(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 77 && blockIdx.y == 7) o.dbg[i] = clock64(); } while (0)
-#define APT_STAMP2(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 77 && blockIdx.y == 7) g_stamp[i] = clock64(); } while (0)
-#else
-#define APT_STAMP(i) do { } while (0)
-#define APT_STAMP2(i) do { } while (0)
-#endif
+
 
 inline size_t td_smem_bytes(int ns, int env_cap) {
     return sizeof(float) * TD_XF + sizeof(double) * ((size_t)2 * ns * (TD_NT / 32) + 32 * 4 * ns * ns + (size_t)TD_CHUNK * 2 * ns + 2 * (size_t)env_cap);
@@ -1232,7 +1239,10 @@ __device__ __forceinline__ float baseline_step(const DevParams& p, double& bl_ba
         // __fdiv_rn off its slow path (a zero numerator is the common case)
         // (0 or NaN) / den ends up 0 after the nan_to_num below either way
         const bool pos = ex > 0.0f;
-        const float q = f_div(pos ? ex : 1.0f, ob + p.norm_min);
+        // exact branch-free division: the operands are clamped into its contract (|log2| < 60); flux values are
+        // dB differences, so the clamps never act on meaningful data
+        const float den = f_min(f_max(ob + p.norm_min, 1e-18f), 1e18f);
+        const float q = f_div_nr(pos ? f_min(ex, 1e18f) : 1.0f, den);
         sc = pos ? q : 0.0f;
     }
     if (isnan(sc) || isinf(sc)) sc = 0.0f;
@@ -1752,6 +1762,29 @@ __global__ void finalize_kernel(const __grid_constant__ DevParams p, Batch b, co
         r[6] = d2f(s / ((double)T * (double)p.K));
         const float a = key_db(st[c].prefix[0]), bb = key_db(st[c].prefix[1]);
         r[7] = f_div(a + bb, 2.0f);
+    }
+}
+
+// exactness self-tests of the branch-free float32 division / square root (apt_selftest)
+__global__ void selftest_sqrt_kernel(unsigned long long* bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t u = 0x3f800000u + i; u <= 0x40000000u; u += gridDim.x * blockDim.x) {
+        const float v = __uint_as_float(u);
+        if (__float_as_uint(f_sqrt_12(v)) != __float_as_uint(__fsqrt_rn(v))) atomicAdd(bad, 1ull);
+    }
+}
+__global__ void selftest_div_kernel(unsigned long long* bad, unsigned long long n) {
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned long long i = i0; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        // two hashed operands: magnitudes log-uniform over 2^-60 .. 2^20, full mantissas, a <= b (the cabs
+        // use) for even i, arbitrary order (the baseline normalisation) for odd i
+        unsigned long long h = i * 0x9E3779B97F4A7C15ull; h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+        const uint32_t ma = (uint32_t)h & 0x7fffffu, mb = (uint32_t)(h >> 23) & 0x7fffffu;
+        const uint32_t ea = 67u + (uint32_t)((h >> 46) % 80u), eb = 67u + (uint32_t)((h >> 54) % 80u);
+        float a = __uint_as_float((ea << 23) | ma), b = __uint_as_float((eb << 23) | mb);
+        if (!(i & 1) && a > b) { const float t = a; a = b; b = t; }
+        if (fabsf(__log2f(a) - __log2f(b)) > 100.0f) continue;   // quotient outside the exact path's contract
+        if (__float_as_uint(f_div_nr(a, b)) != __float_as_uint(__fdiv_rn(a, b))) atomicAdd(bad, 1ull);
     }
 }
 

@@ -154,6 +154,11 @@ int  apt_abi_version(void);
 int  apt_sizeof_params(void);
 int  apt_sizeof_out(void);
 
+/* Device self-tests of the branch-free exact float32 primitives the kernels use instead of the IEEE
+   division / square root intrinsics: which = 0 square root over every float32 in [1, 2]; which = 1 division on
+   n hashed operand pairs.  *mismatches = results that differ from __fsqrt_rn / __fdiv_rn (must be 0). */
+int  apt_selftest(apt_ctx* ctx, int which, int64_t n, int64_t* mismatches);
+
 /* Fills *p with the reference's defaults for fs=11162 except the fields that have no default
    (mode bands, window, freqs, SOS): the host must set those.  */
 int  apt_params_default(apt_params_t* p);

@@ -36,6 +36,15 @@ int main() {
     printf("  fwd: direct %lld, scan %lld, exchange %lld, correction %lld\n", gs[0] - hd[2], gs[1] - gs[0], gs[2] - gs[1], gs[3] - gs[2]);
     printf("  bwd: direct %lld, scan %lld, exchange %lld, correction %lld\n", gs[10] - hd[3], gs[11] - gs[10], gs[12] - gs[11], gs[13] - gs[12]);
   }
+    {   // STFT kernel phases (same batch)
+        StftOut so; memset(&so, 0, sizeof(so)); so.P_band = pl->d_Pband.p; so.freqs = pl->d_freqs.p; so.nF = pl->nF;
+        for (int rep = 0; rep < 2; rep++) { launch_stft<double, int16_t>(pl, b, pcm, so, 0); cudaDeviceSynchronize(); }
+        long long gs[64]; cudaMemcpyFromSymbol(gs, apt::g_stamp, sizeof(gs));
+        printf("stft256<f64>: stage %lld, pass A %lld, pass B + power %lld, plane writes %lld cycles\n", gs[21] - gs[20], gs[22] - gs[21], gs[23] - gs[22], gs[24] - gs[23]);
+        for (int rep = 0; rep < 2; rep++) { launch_stft<float, int16_t>(pl, b, pcm, so, 0); cudaDeviceSynchronize(); }
+        cudaMemcpyFromSymbol(gs, apt::g_stamp, sizeof(gs));
+        printf("stft256<f32>: stage %lld, pass A %lld, pass B + power %lld, plane writes %lld cycles\n", gs[21] - gs[20], gs[22] - gs[21], gs[23] - gs[22], gs[24] - gs[23]);
+    }
     printf("chunk=%d lb_max=%d smem=%zu tiles=%lld\n", pl->tdt.chunk, pl->tdt.lb_max, pl->td_smem, (long long)pl->td_tile_off[n_clips]);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;

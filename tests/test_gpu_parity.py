@@ -274,3 +274,18 @@ def test_frame_size_sweep_features(torch_cuda, n_fft, hop, fft_f64):
     with pytest.raises(AptError):      # the full pipeline is planned for 256/128 only
         eng.run_clips([g["pcm"]], ())
     eng.close()
+
+
+def test_exact_div_sqrt(torch_cuda):
+    """The branch-free float32 division / square root used in the power and normalisation paths are
+    bit-identical to the IEEE intrinsics: exhaustive for sqrt on [1, 2], 2^30 hashed pairs for division."""
+    import ctypes as C
+    from audio_processing_tools_b200 import _lib
+    L = _lib.load()
+    ctx = C.c_void_p()
+    assert L.apt_init(0, C.byref(ctx)) == 0
+    bad = C.c_int64(-1)
+    assert L.apt_selftest(ctx, 0, 0, C.byref(bad)) == 0 and bad.value == 0
+    bad = C.c_int64(-1)
+    assert L.apt_selftest(ctx, 1, 1 << 30, C.byref(bad)) == 0 and bad.value == 0
+    L.apt_destroy(ctx)
