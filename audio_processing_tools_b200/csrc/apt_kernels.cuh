@@ -260,33 +260,58 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
     const int fr = tid >> 3, lane = tid & 7;
     const float* xs = s_x + fr * 128;
     cx<T>* ex = s_ex + (size_t)fr * kExSize;
-    if (fr < nfr) rfft256_passA<T>(lane, [&](int n) { return xs[n]; }, s_win, s_tw128, ex);
+    // all STFT_TF frame slots run both passes (slots past the clip end transform zero padding and are never
+    // written out): the warp barrier inside pass B needs every lane
+    rfft256_passA<T>(lane, [&](int n) { return xs[n]; }, s_win, s_tw128, ex);
     __syncthreads();
     APT_STAMP2(22);
-    if (fr < nfr) {
-        float* Pt = s_P + fr * STFT_PS;
-        float* Sg = o.S ? o.S + ((f0 + t0 + fr) * (int64_t)p.F) * 2 : nullptr;
-        const bool need_full = o.S || o.P || o.raw || o.band_energy;
-        const int klo = need_full ? 0 : p.band_lo, khi = need_full ? p.F - 1 : p.band_lo + p.K - 1;
-        rfft256_passB<T>(lane, ex, s_tw256, [&](int k, T re, T im) {
-            const float sr = d2f((double)re), si = d2f((double)im);
-            if (Sg) { Sg[2 * k] = sr; Sg[2 * k + 1] = si; }
-            const float a = np_cabsf_fast(sr, si);
-            if (k >= klo && k <= khi) Pt[k] = a * a;
-        });
+    // pass B: every lane emits its bins as complex64 into the frame's own (now consumed) exchange area
+    {
+        float2* sS = reinterpret_cast<float2*>(ex);
+        rfft256_passB<T>(lane, ex, s_tw256,
+                         [&](int k, T re, T im) { sS[k] = make_float2(d2f((double)re), d2f((double)im)); },
+                         [&]() { __syncwarp(); });
     }
     __syncthreads();
     APT_STAMP2(23);
 
-    // coalesced plane writes
+    // power |S|^2 with numpy's complex64 abs, all threads over (frame, bin): independent evaluations that the
+    // scheduler interleaves; the band plane goes straight to HBM (consecutive threads = consecutive bins)
     const int64_t fbase = f0 + t0;
-    if (o.P_band) {
-        float* dst = o.P_band + fbase * p.K;
-        for (int i = tid; i < nfr * p.K; i += STFT_NT) {
-            int t = i / p.K, k = i - t * p.K;
-            dst[i] = s_P[t * STFT_PS + p.band_lo + k];
+    const bool need_full = o.P || o.raw || o.band_energy;
+    {
+        const int klo = need_full ? 0 : p.band_lo, nk = need_full ? p.F : p.K;
+        float* dstb = o.P_band ? o.P_band + fbase * p.K : nullptr;
+        // warp w takes frames w, w+8, ...; lanes run over the bins: no index division, and the (up to 20)
+        // evaluations of a thread are independent straight-line code
+        const int w = tid >> 5, ln = tid & 31;
+#pragma unroll
+        for (int tt = 0; tt < STFT_TF / 8; tt++) {
+            const int t = w + 8 * tt;
+            const float2* sS = reinterpret_cast<const float2*>(s_ex + (size_t)t * kExSize);
+#pragma unroll
+            for (int kk = 0; kk < 5; kk++) {
+                const int ki = ln + 32 * kk;
+                if (t < nfr && ki < nk) {
+                    const int k = klo + ki;
+                    const float2 z = sS[k];
+                    const float a = np_cabsf_fast(z.x, z.y);
+                    const float pw = a * a;
+                    if (need_full) s_P[t * STFT_PS + k] = pw;
+                    const int kb = k - p.band_lo;
+                    if (dstb && kb >= 0 && kb < p.K) dstb[t * p.K + kb] = pw;
+                }
+            }
+        }
+        if (o.S) {
+            float2* dstS = reinterpret_cast<float2*>(o.S) + fbase * p.F;
+            for (int i = tid; i < nfr * p.F; i += STFT_NT) {
+                const int t = i / p.F, k = i - t * p.F;
+                dstS[i] = reinterpret_cast<const float2*>(s_ex + (size_t)t * kExSize)[k];
+            }
         }
     }
+    __syncthreads();
     if (o.P) {
         float* dst = o.P + fbase * p.F;
         for (int i = tid; i < nfr * p.F; i += STFT_NT) {
@@ -1239,10 +1264,7 @@ __device__ __forceinline__ float baseline_step(const DevParams& p, double& bl_ba
         // __fdiv_rn off its slow path (a zero numerator is the common case)
         // (0 or NaN) / den ends up 0 after the nan_to_num below either way
         const bool pos = ex > 0.0f;
-        // exact branch-free division: the operands are clamped into its contract (|log2| < 60); flux values are
-        // dB differences, so the clamps never act on meaningful data
-        const float den = f_min(f_max(ob + p.norm_min, 1e-18f), 1e18f);
-        const float q = f_div_nr(pos ? f_min(ex, 1e18f) : 1.0f, den);
+        const float q = f_div(pos ? ex : 1.0f, ob + p.norm_min);
         sc = pos ? q : 0.0f;
     }
     if (isnan(sc) || isinf(sc)) sc = 0.0f;
