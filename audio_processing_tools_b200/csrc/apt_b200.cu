@@ -79,6 +79,8 @@ struct apt_plan {
     DevBuf<int8_t> d_fc; DevBuf<float> d_rc, d_nc, d_stats; DevBuf<int32_t> d_ev, d_evc;
     static constexpr int N_COMP = 4;
     cudaStream_t s_copy = nullptr, s_comp[N_COMP] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t s_aux = nullptr;            // high-priority side stream for the STFT -> baseline chain (the TD kernel stays on the caller's)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int last_launches = 0;
     size_t scratch_bytes = 0;
     // optional per-kernel timing (CUDA events on the launch stream)
@@ -414,6 +416,13 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
                         (size_t)n_clips * (sizeof(SelState) + 2 * SEL_BINS * sizeof(uint32_t));
     PL_OK(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
     for (int i = 0; i < apt_plan::N_COMP; i++) PL_OK(cudaStreamCreateWithFlags(&pl->s_comp[i], cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        PL_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PL_OK(cudaStreamCreateWithPriority(&pl->s_aux, cudaStreamNonBlocking, hi));   // hi = greatest priority
+        PL_OK(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+        PL_OK(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+    }
 #undef PL_OK
     *out = pl;
     return 0;
@@ -423,6 +432,9 @@ void apt_plan_destroy(apt_plan_t* plan) {
     if (!plan) return;
     if (plan->s_copy) cudaStreamDestroy(plan->s_copy);
     for (int i = 0; i < apt_plan::N_COMP; i++) if (plan->s_comp[i]) cudaStreamDestroy(plan->s_comp[i]);
+    if (plan->s_aux) cudaStreamDestroy(plan->s_aux);
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    if (plan->ev_join) cudaEventDestroy(plan->ev_join);
     delete plan;
 }
 
@@ -519,7 +531,8 @@ static cudaError_t launch_td(apt_plan* pl, const Batch& b, const PCM* pcm, const
 }
 
 template <typename PCM>
-static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM* pcm, const apt_out_t* out, cudaStream_t st) {
+static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM* pcm, const apt_out_t* out, cudaStream_t st,
+                     bool fork_td = false) {
     apt_ctx* ctx = pl->ctx;
     const DevParams& d = pl->dp;
     Batch b{clip0, n_clips, pl->d_samp_off.p, pl->d_frame_off.p};
@@ -540,11 +553,22 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         return 0;
     }
 
+    // The TD kernel depends only on the PCM and is first needed by decide_kernel; the STFT -> trk1 -> flux -> base
+    // chain is independent of it.  Unless per-kernel timing is on, the chain runs on a high-priority side stream
+    // so that its serial kernels (few warps, latency-bound) are scheduled ahead of the TD kernel's queued CTAs and
+    // hide behind them; the caller's stream carries the TD kernel and joins the chain before decide_kernel.
+    const bool forked = fork_td && full && !pl->timing && pl->s_aux;
+    cudaStream_t sc = st;   // stream of the chain
+    if (forked) {
+        CUDA_OK(ctx, cudaEventRecord(pl->ev_fork, st));
+        CUDA_OK(ctx, cudaStreamWaitEvent(pl->s_aux, pl->ev_fork, 0));
+        sc = pl->s_aux;
+    }
     StftOut so;
     so.S = out->S; so.P = out->P; so.P_band = full ? pl->d_Pband.p : nullptr; so.band_energy = out->band_energy;
     so.raw = out->raw; so.freqs = pl->d_freqs.p; so.nF = pl->nF;
     pl->mark(APT_KERNEL_STFT, st);
-    cudaError_t e = pl->prm.fft_f64 ? launch_stft<double, PCM>(pl, b, pcm, so, st) : launch_stft<float, PCM>(pl, b, pcm, so, st);
+    cudaError_t e = pl->prm.fft_f64 ? launch_stft<double, PCM>(pl, b, pcm, so, sc) : launch_stft<float, PCM>(pl, b, pcm, so, sc);
     if (e != cudaSuccess) return fail(ctx, -11, "stft launch failed: %s", cudaGetErrorString(e));
     if (!full) { pl->mark(-1, st); return 0; }
 
@@ -566,7 +590,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         Trk1IO io;
         io.P_band = pl->d_Pband.p; io.NL = nl_plane; io.det_noise_psd = out->det_noise_psd; io.nF = pl->nF;
         const int64_t lanes = (int64_t)n_clips * tab.n_lanes;
-        trk1_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, tab, io);
+        trk1_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, sc>>>(pl->dp, b, tab, io);
         pl->last_launches++;
         CUDA_OK(ctx, cudaGetLastError());
     }
@@ -578,7 +602,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         const int64_t tiles = pl->flux_tile_off[clip0 + n_clips] - pl->flux_tile_off[clip0];
         const size_t fsm = flux_smem_bytes(d.K, tab.n_lanes, tab.nls);
         CUDA_OK(ctx, cudaFuncSetAttribute(flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-        flux_kernel<<<tile_grid(pl->flux_tile_off, clip0, n_clips), 256, fsm, st>>>(pl->dp, b, pl->d_flux_tile_off.p, tab, io);
+        flux_kernel<<<tile_grid(pl->flux_tile_off, clip0, n_clips), 256, fsm, sc>>>(pl->dp, b, pl->d_flux_tile_off.p, tab, io);
         pl->last_launches++;
         CUDA_OK(ctx, cudaGetLastError());
     }
@@ -586,9 +610,13 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     pl->mark(APT_KERNEL_BASE, st);
     {
         const int64_t lanes = (int64_t)n_clips * (d.M + 1);
-        base_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, pl->d_mf.p, pl->mf_stride);
+        base_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, sc>>>(pl->dp, b, pl->d_mf.p, pl->mf_stride);
         pl->last_launches++;
         CUDA_OK(ctx, cudaGetLastError());
+    }
+    if (forked) {
+        CUDA_OK(ctx, cudaEventRecord(pl->ev_join, sc));
+        CUDA_OK(ctx, cudaStreamWaitEvent(st, pl->ev_join, 0));
     }
     pl->mark(APT_KERNEL_DECIDE, st);
     {
@@ -667,7 +695,7 @@ int apt_run_i16(apt_plan_t* plan, int stages, const int16_t* dev_pcm, const apt_
     if (!dev_pcm || !out) return fail(plan->ctx, -1, "apt_run_i16: null buffer");
     CUDA_OK(plan->ctx, cudaSetDevice(plan->ctx->device));
     plan->last_launches = 0;
-    return run_range<int16_t>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream);
+    return run_range<int16_t>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream, true);
 }
 
 int apt_run_f32(apt_plan_t* plan, int stages, const float* dev_pcm, const apt_out_t* out, void* stream) {
@@ -675,7 +703,7 @@ int apt_run_f32(apt_plan_t* plan, int stages, const float* dev_pcm, const apt_ou
     if (!dev_pcm || !out) return fail(plan->ctx, -1, "apt_run_f32: null buffer");
     CUDA_OK(plan->ctx, cudaSetDevice(plan->ctx->device));
     plan->last_launches = 0;
-    return run_range<float>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream);
+    return run_range<float>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream, true);
 }
 
 int apt_run_host_i16(apt_plan_t* pl, const int16_t* host_pcm, int8_t* frame_class, float* rain_conf, float* noise_conf,
