@@ -90,18 +90,27 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_baseline(params, seconds, n_threads, target_clips=None):
-    """Times the CPU oracle (C port of the reference's algorithm) on a bounded sample of the workload."""
+def cpu_baseline(params, seconds, n_threads, target_clips=None, target_wall=12.0):
+    """Times the CPU oracle (C port of the reference's algorithm) on a bounded sample of the workload:
+    a short calibration pass sizes the sample to about `target_wall` seconds of wall time on all threads."""
     from oracle import oracle
     from audio_processing_tools_b200.synth import batch_clip_spec, synth_clip_i16
     oracle.build()
-    n_clips = target_clips or max(2, min(2 * n_threads, 64))
-    distinct = [synth_clip_i16(seconds, *batch_clip_spec(900 + i)) for i in range(min(n_clips, 4))]
-    clips = [distinct[i % len(distinct)] for i in range(n_clips)]
-    t0 = time.perf_counter()
-    oracle.process_batch_i16(clips, params, n_threads=n_threads)
-    dt = time.perf_counter() - t0
-    return n_clips * seconds / dt, n_clips, dt
+    distinct = [synth_clip_i16(seconds, *batch_clip_spec(900 + i)) for i in range(4)]
+
+    def run(n):
+        clips = [distinct[i % len(distinct)] for i in range(n)]
+        t0 = time.perf_counter()
+        oracle.process_batch_i16(clips, params, n_threads=n_threads)
+        return time.perf_counter() - t0
+
+    if target_clips is None:
+        n0 = max(2, 2 * n_threads)
+        dt0 = run(n0)
+        target_clips = int(min(4096, max(n0, round(n0 * target_wall / max(dt0, 1e-3)))))
+        target_clips = max(n_threads, target_clips // n_threads * n_threads)
+    dt = run(target_clips)
+    return target_clips * seconds / dt, target_clips, dt
 
 
 def run_reference(args, rank, world):
@@ -111,9 +120,7 @@ def run_reference(args, rank, world):
     from audio_processing_tools_b200.synth import default_params
     params = default_params(check_duration=args.clip_seconds)
     cores = os.cpu_count() or 1
-    n_clips = max(2, min(2 * cores, 64))
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_baseline(params, min(args.clip_seconds, 60.0), cores, target_clips=cores)
+    _, n_clips, _ = cpu_baseline(params, args.clip_seconds, cores, target_wall=10.0)   # warm-up + sample sizing
     vals, times = [], []
     for _ in range(max(1, args.steps)):
         v, n, dt = cpu_baseline(params, args.clip_seconds, cores, target_clips=n_clips)
@@ -224,12 +231,14 @@ def main():
     # rooflines: per kernel (device events inside the library) and for the whole pipeline
     K = eng.rp.K
     nF = plan.nF
+    n_mode_bins = sum(max(0, eng.rp.c.mode_band_hi[i] - eng.rp.c.mode_band_lo[i] + 1) for i in range(eng.rp.M))
+    nls = max(8, (n_mode_bins + 7) // 8 * 8)
     bytes_algo = n_clips * (N * 2 + T * 9) + n_clips * 32                       # SURVEY 8(d) formula, int16 in
     kernel_bytes = {   # algorithmic bytes each kernel must move in this decomposition
         "stft256_kernel": plan.nS * 2 + nF * K * 4,
         "td_features_kernel": plan.nS * 2 + nF * 4,
-        "trk1_kernel": nF * 26 * 4 + nF * 32 * 4,
-        "flux_kernel": nF * 26 * 4 + nF * 32 * 4 + nF * 32,
+        "trk1_kernel": nF * n_mode_bins * 4 + nF * nls * 4,
+        "flux_kernel": nF * n_mode_bins * 4 + nF * nls * 4 + nF * 32,
         "base_kernel": 2 * nF * 32,
         "decide_kernels": nF * 32 + nF * 4 + nF * 9 + nF,
         "trk2_kernel": nF * K * 4 + nF + nF * K * 4,
@@ -245,13 +254,27 @@ def main():
     except Exception:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     ach = kernel_bytes[dom] / (kms_step[dom] * 1e-3) / 1e9 if kms_step[dom] > 0 else 0.0
+    # DRAM traffic of the dominant kernel: ncu (dram__bytes_read + write) on the small profiling workload
+    # (profiles/r1/kernel_traffic_r1.json), per frame, scaled to this launch's frames
+    traffic, traffic_note = None, None
+    try:
+        tj = json.load(open(os.path.join(REPO, "profiles", "r1", "kernel_traffic_r1.json")))
+        key = {"decide_kernels": "decide_kernel", "select_kernels": "select_hist_kernel"}.get(dom, dom)
+        traffic = tj["kernels"][key]["dram_bytes_per_frame"] * nF
+        traffic_note = "ncu dram bytes per frame on %s, scaled by frames" % tj["workload"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "frac": ach / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                "algorithmic_bytes": kernel_bytes[dom],
                 "kernel_ms_per_step": kms_step,
                 "kernel_gbs": {k: (kernel_bytes[k] / (v * 1e-3) / 1e9 if v > 0 else None) for k, v in kms_step.items()},
                 "pipeline": {"bytes_algo": bytes_algo, "achieved_gbs": bytes_algo / (ms_step * 1e-3) / 1e9,
                              "frac": bytes_algo / (ms_step * 1e-3) / 1e9 / peak},
-                "note": "the pipeline is issue-bound on fp32/fp64 pipes at n_fft=256 (SURVEY 8(d)); HBM fraction reported as required"}
+                "note": "HBM fraction reported as the contract requires, but neither the dominant kernel nor the pipeline is "
+                        "HBM-bound at n_fft=256: td_features / stft256 are bound by the FP64 pipe (62 FMA/clk/SM measured; "
+                        "ncu: fp64 pipe 29-33 % busy, DRAM 3-6 %) and the serial kernels by dependent-issue latency "
+                        "(DESIGN.md section 4, profiles/r1/ncu_summary_r1_final.txt)"}
 
     result = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,

@@ -10,7 +10,7 @@ def g(r, k):
     return r[ix[k]] if k in ix else "n/a"
 for r in rows[2:]:
     print("----", g(r, "Kernel Name")[:70])
-    print("   time %s ms  grid %s block %s regs %s  dyn smem %s" % (g(r, "gpu__time_duration.sum"), g(r, "launch__grid_size"), g(r, "launch__block_size"),
+    print("   time %s %s  grid %s block %s regs %s  dyn smem %s" % (g(r, "gpu__time_duration.sum"), units[ix["gpu__time_duration.sum"]], g(r, "launch__grid_size"), g(r, "launch__block_size"),
           g(r, "launch__registers_per_thread"), g(r, "launch__shared_mem_per_block_dynamic")))
     print("   dram read %s %s write %s %s  dram%% %s" % (g(r, "dram__bytes_read.sum"), units[ix["dram__bytes_read.sum"]], g(r, "dram__bytes_write.sum"),
           units[ix["dram__bytes_write.sum"]], g(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")))
