@@ -66,6 +66,11 @@ OUT_FIELDS = ("frame_class", "rain_conf", "noise_conf", "event_idx", "event_coun
               "score", "td", "raw", "band_energy", "gate", "x_td", "G", "ratio_med", "S_hat")
 
 
+class AptDsdParams(C.Structure):
+    _fields_ = [("fs", C.c_int32), ("frame_length", C.c_int32), ("hop_length", C.c_int32), ("apply_window", C.c_int32),
+                ("window", C.c_void_p)]
+
+
 class AptOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in OUT_FIELDS]
 
@@ -75,7 +80,8 @@ EXPORTS = ("apt_init", "apt_destroy", "apt_last_error", "apt_abi_version", "apt_
            "apt_sizeof_out", "apt_params_default", "apt_plan_create", "apt_plan_destroy",
            "apt_plan_offsets", "apt_plan_total_frames", "apt_plan_total_samples",
            "apt_plan_scratch_bytes", "apt_run_i16", "apt_run_f32", "apt_plan_last_launches",
-           "apt_run_host_i16", "apt_plan_enable_timing", "apt_plan_kernel_ms", "apt_selftest")
+           "apt_run_host_i16", "apt_plan_enable_timing", "apt_plan_kernel_ms", "apt_selftest",
+           "apt_dsd_run_i16")
 
 
 def build(force=False, verbose=False):
@@ -122,6 +128,7 @@ def load():
     L.apt_run_f32.argtypes = [vp, C.c_int, vp, C.POINTER(AptOut), vp]
     L.apt_run_host_i16.argtypes = [vp] * 8
     L.apt_selftest.argtypes = [vp, C.c_int, C.c_int64, i64p]
+    L.apt_dsd_run_i16.argtypes = [vp, C.POINTER(AptDsdParams), C.c_int, i64p, C.POINTER(C.c_double), vp, vp, vp, C.c_int, vp]
     L.apt_plan_enable_timing.argtypes = [vp, C.c_int]
     L.apt_plan_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     if L.apt_abi_version() != ABI_VERSION:

@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "apt_kernels.cuh"
+#include "apt_dsd.cuh"
 
 using namespace apt;
 
@@ -765,3 +766,57 @@ int apt_run_host_i16(apt_plan_t* pl, const int16_t* host_pcm, int8_t* frame_clas
 }
 
 }  // extern "C"
+
+extern "C" int apt_dsd_run_i16(apt_ctx* ctx, const apt_dsd_params_t* p, int n_clips, const int64_t* clip_len, const double* ts,
+                               const int16_t* dev_pcm, double* dev_out, int32_t* dev_n_minutes, int max_minutes, void* stream) {
+    if (!ctx) return -1;
+    if (!p || !clip_len || !ts || !dev_pcm || !dev_out || !dev_n_minutes || n_clips <= 0 || n_clips > 65535)
+        return fail(ctx, -1, "apt_dsd_run_i16: bad arguments");
+    const int L = p->frame_length;
+    if (L < 64 || L > 4096 || (L & (L - 1)) != 0 || p->hop_length < 1 || p->fs < 1)
+        return fail(ctx, -21, "apt_dsd_run_i16: frame_length=%d must be a power of two in 64..4096, hop >= 1", L);
+    if (p->apply_window && !p->window) return fail(ctx, -25, "apt_dsd_run_i16: window table missing");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DsdDev d;
+    memset(&d, 0, sizeof(d));
+    d.fs = p->fs; d.L = L; d.hop = p->hop_length; d.window = p->apply_window;
+    // index constants exactly as the reference constructor computes them (:33-71)
+    const double dF = (double)p->fs / (double)L;
+    auto fdiv = [&](double f) { return (int)floor(f / dF); };
+    d.n_bins = L / 2;
+    d.rain_lo = fdiv(400) + 1; d.rain_hi = fdiv(700);
+    d.pft_lo = fdiv(100) + 1; d.pft_hi = fdiv(1500) - 1;
+    d.lwin0 = fdiv(300); d.lwin1 = d.lwin0 + 19 - 1;
+    d.hwin0 = fdiv(1000); d.hwin1 = d.hwin0 + 19 - 1;
+    d.rain_thr = 0.6; d.rain_log_factor = 0.6; d.rain_log_base = 1.13;
+    d.max_minutes = max_minutes;
+    if (d.pft_hi > d.n_bins || d.rain_hi >= d.n_bins || d.hwin1 >= d.n_bins || d.pft_lo >= d.pft_hi || d.n_bins > 2048)
+        return fail(ctx, -22, "apt_dsd_run_i16: fs=%d / frame_length=%d put the analysis bands outside the spectrum", p->fs, L);
+    std::vector<int64_t> so(n_clips + 1, 0), fo(n_clips + 1, 0);
+    int64_t max_fr = 1;
+    for (int c = 0; c < n_clips; c++) {
+        const int64_t n = clip_len[c];
+        const int64_t nf = n < L ? 0 : (n - L) / p->hop_length + 1;
+        if ((int64_t)ceil((double)n / ((double)p->fs * 60.0)) > max_minutes) return fail(ctx, -28, "clip %d needs more than max_minutes=%d rows", c, max_minutes);
+        so[c + 1] = so[c] + n; fo[c + 1] = fo[c] + nf;
+        max_fr = std::max(max_fr, nf);
+    }
+    DevBuf<int64_t> d_so, d_fo; DevBuf<double> d_ts, d_drop, d_pkv, d_win; DevBuf<int> d_pki; DevBuf<cx<double>> d_tw;
+    CUDA_OK(ctx, upload(d_so, so)); CUDA_OK(ctx, upload(d_fo, fo));
+    CUDA_OK(ctx, upload(d_ts, std::vector<double>(ts, ts + n_clips)));
+    std::vector<cx<double>> tw(L / 2 + 1);
+    for (int k = 0; k <= L / 2; k++) tw[k] = {cos(2.0 * M_PI * k / L), -sin(2.0 * M_PI * k / L)};
+    CUDA_OK(ctx, upload(d_tw, tw));
+    if (p->apply_window) CUDA_OK(ctx, upload(d_win, std::vector<double>(p->window, p->window + L)));
+    const size_t nf_tot = (size_t)std::max<int64_t>(1, fo[n_clips]);
+    CUDA_OK(ctx, d_drop.alloc(nf_tot)); CUDA_OK(ctx, d_pkv.alloc(nf_tot)); CUDA_OK(ctx, d_pki.alloc(nf_tot));
+    const size_t smem = sizeof(cx<double>) * (size_t)L + sizeof(double) * (size_t)(L / 2);
+    CUDA_OK(ctx, cudaFuncSetAttribute(dsd_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dsd_frame_kernel<<<dim3((unsigned)max_fr, (unsigned)n_clips), DSD_NT, smem, st>>>(d, 0, d_so.p, d_fo.p, dev_pcm, d_win.p, d_tw.p,
+                                                                                       d_drop.p, d_pki.p, d_pkv.p);
+    dsd_minutes_kernel<<<(n_clips + 63) / 64, 64, 0, st>>>(d, n_clips, d_so.p, d_fo.p, d_ts.p, d_drop.p, d_pki.p, d_pkv.p, dev_out, dev_n_minutes);
+    CUDA_OK(ctx, cudaGetLastError());
+    CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return 0;
+}

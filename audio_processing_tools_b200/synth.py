@@ -35,6 +35,19 @@ def synth_clip_i16(seconds, seed, lam, noise_rms=0.01, fs=FS):
     return np.round(np.clip(x, -1, 1) * 32767).astype(np.int16)
 
 
+def quiet_clip_i16(seconds, seed, burst_at=(), fs=FS):
+    """Near-silent clip (far below the DSD emulator's 0.6 rain-energy threshold) with optional loud
+    550 Hz bursts at the given times (seconds): exercises the emulator's not-raining / rain-check branches."""
+    rng = np.random.default_rng(seed)
+    n = int(fs * seconds)
+    x = rng.standard_normal(n) * 0.0002
+    for t0 in burst_at:
+        i = int(t0 * fs)
+        tt = np.arange(int(0.05 * fs)) / fs
+        x[i:i + tt.size] += 0.3 * np.sin(2 * np.pi * 550.0 * tt) * np.exp(-tt / 0.01)
+    return np.round(np.clip(x, -1, 1) * 32767).astype(np.int16)
+
+
 def pcm_to_f32(i16):
     """audio_io.safe_to_float semantics (reference audio_io.py:71-72)."""
     return np.asarray(i16, dtype=np.int16).astype(np.float32) / np.float32(32767.0)

@@ -206,6 +206,24 @@ int  apt_plan_kernel_ms(apt_plan_t* plan, float* out_ms /* [APT_N_KERNELS] */);
 int  apt_run_host_i16(apt_plan_t* plan, const int16_t* host_pcm, int8_t* frame_class, float* rain_conf,
                       float* noise_conf, int32_t* event_idx, int32_t* event_count, float* clip_stats);
 
+/* ---------------------------------------------------------------------------------------------
+ * Drop-size-distribution emulator: replaces DsdProcessingEmualtor.process_audio_data
+ * (host_analysis/device_dsd_processing_emulator.py:257-314), the compute path of
+ * transform.process_audio_file_dsd (transform.py:251-313), for a batch of clips.
+ * ------------------------------------------------------------------------------------------- */
+#define APT_DSD_OUT 100   /* 32 drop-size bins + 30 peak-frequency slots + 38 FFT energies per minute */
+typedef struct apt_dsd_params_t {
+    int32_t fs, frame_length, hop_length, apply_window;   /* constructor arguments (:16-31) */
+    const double* window;                                  /* frame_length values when apply_window (host) */
+} apt_dsd_params_t;
+/* clip_len / ts: host arrays [n_clips] (ts = start time of each clip in seconds, as process_audio_data's ts).
+   dev_pcm: concatenated int16 clips on the device (scaled /32768 as parse.pcm_to_float, :670).
+   dev_out: [n_clips][max_minutes][100] float64, dev_n_minutes: [n_clips] int32 (rows actually produced).
+   max_minutes must be >= ceil(len / (fs * 60)) of the longest clip.  Runs on the given stream; synchronises it
+   before returning (per-frame scratch is released). */
+int  apt_dsd_run_i16(apt_ctx* ctx, const apt_dsd_params_t* p, int n_clips, const int64_t* clip_len, const double* ts,
+                     const int16_t* dev_pcm, double* dev_out, int32_t* dev_n_minutes, int max_minutes, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -289,3 +289,41 @@ def test_exact_div_sqrt(torch_cuda):
     bad = C.c_int64(-1)
     assert L.apt_selftest(ctx, 1, 1 << 30, C.byref(bad)) == 0 and bad.value == 0
     L.apt_destroy(ctx)
+
+
+def test_dsd_emulator_matches_reference(torch_cuda):
+    """the GPU drop-size-distribution emulator against the unmodified reference's per-minute
+    100-vectors (integer histograms: bit-exact), one batch holding every case with the same windowing."""
+    from test_dsd_oracle import case_pcm, dsd_cases
+    from audio_processing_tools_b200.host_analysis.device_dsd_processing_emulator import DsdProcessingEmualtor
+    cases = dsd_cases()
+    for win in (False, True):
+        sel = [(m, ref) for m, ref in cases if m["window"] == win]
+        em = DsdProcessingEmualtor(fs=11162, frame_length=512, hop_length=512, bwindow=win)
+        outs = em.process_audio_batch([case_pcm(m) for m, _ in sel], [m["ts"] for m, _ in sel])
+        for (m, ref), out in zip(sel, outs):
+            assert len(out) == ref.shape[0], m["name"]
+            assert np.array_equal(np.asarray(out).reshape(ref.shape), ref), m["name"]
+    # float input scaled as parse.pcm_to_float is accepted, anything else is refused
+    m, ref = cases[0]
+    pcm = case_pcm(m)
+    one = DsdProcessingEmualtor().process_audio_data(pcm.astype(np.float64) / 32768.0, m["ts"])
+    assert np.array_equal(np.asarray(one), ref)
+    with pytest.raises(ValueError):
+        DsdProcessingEmualtor().process_audio_data(pcm.astype(np.float64) / 32767.0, 0)
+
+
+def test_transform_dsd_entry_points(torch_cuda):
+    import datetime as dt
+    from test_dsd_oracle import case_pcm, dsd_cases
+    from audio_processing_tools_b200 import transform
+    m, ref = dsd_cases()[3]          # 150 s clip: transform processes its first 60 s
+    pcm = case_pcm(m)
+    meta = {"sample_rate": 11162, "device_id": "C00001", "time": dt.datetime(2024, 5, 1, 12, 0, 0)}
+    df = transform.process_audio_file_dsd("k0", pcm, meta)
+    assert len(df) == 1 and df["device"].iloc[0] == "C00001" and df["key"].iloc[0] == "k0"
+    assert np.array_equal(df[[f"dsd{i}" for i in range(32)]].to_numpy()[0], ref[0, :32])
+    assert np.array_equal(df[[f"pft{i}" for i in range(30)]].to_numpy()[0], ref[0, 32:62])
+    assert np.array_equal(df[[f"fft{i}" for i in range(38)]].to_numpy()[0], ref[0, 62:])
+    assert df["weighted_dsd_sum"].iloc[0] == pytest.approx(float((ref[0, :32] * np.array(list(transform.dsd_weights.values()))).sum()))
+    assert df["time"].iloc[0] == meta["time"] + dt.timedelta(minutes=1)
