@@ -327,3 +327,25 @@ def test_transform_dsd_entry_points(torch_cuda):
     assert np.array_equal(df[[f"fft{i}" for i in range(38)]].to_numpy()[0], ref[0, 62:])
     assert df["weighted_dsd_sum"].iloc[0] == pytest.approx(float((ref[0, :32] * np.array(list(transform.dsd_weights.values()))).sum()))
     assert df["time"].iloc[0] == meta["time"] + dt.timedelta(minutes=1)
+
+
+def test_mark3_loader_feeds_host_path(torch_cuda):
+    """Mark-3 files -> pinned int16 batch -> apt_run_host_i16, equal to the device-resident path."""
+    from audio_processing_tools_b200 import parse
+    clips = [synth_clip_i16(6.0 + 0.5 * i, 700 + i, (0.5, 3.0, 10.0)[i % 3]) for i in range(6)]
+    files = [parse.build_mark_audio_file(c, ts=1700000000 + i, device_id=f"C{i:06d}") for i, c in enumerate(clips)]
+    loader = parse.Mark3BatchLoader(sum(c.size for c in clips))
+    pcm, lengths, metas = loader.load(files)
+    assert loader.pinned and [m["device_id"] for m in metas] == [f"C{i:06d}" for i in range(6)]
+    params = default_params(check_duration=6)
+    eng = make_engine(params)
+    plan = eng.plan_for(list(lengths))
+    host = {"frame_class": np.zeros(plan.nF, np.int8), "rain_conf": None, "noise_conf": None,
+            "event_idx": np.zeros(plan.nF, np.int32), "event_count": np.zeros(plan.n_clips, np.int32),
+            "clip_stats": np.zeros((plan.n_clips, 8), np.float32)}
+    eng.run_host_i16(plan, pcm, host)
+    plan2, out = eng.run_clips(clips, ())
+    assert np.array_equal(host["frame_class"], out["frame_class"])
+    assert np.array_equal(host["event_count"], out["event_count"])
+    assert np.array_equal(host["clip_stats"], out["clip_stats"])
+    eng.close()
