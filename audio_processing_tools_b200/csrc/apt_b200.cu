@@ -70,7 +70,8 @@ struct apt_plan {
     DevBuf<double> d_dbsum;   // [select chunks] float64 sums of the dB plane
     Trk1Tab tab_modes, tab_all;   // pass-1 lane tables: mode bins only / every band bin (debug planes)
     int mf_stride = 8;
-    bool generic = false;   // features stage only, generic frame size
+    bool generic = false;   // generic frame-size STFT kernel
+    bool full_ok = true;    // the full pipeline is planned (n_fft = 256, hop = 128)
     DevBuf<double> d_gwin64; DevBuf<cx<double>> d_gtw64; DevBuf<float> d_gwin32; DevBuf<cx<float>> d_gtw32;
     DevBuf<SelState> d_sel;
     DevBuf<uint32_t> d_hist;
@@ -234,7 +235,9 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     // with 1 <= hop <= n_fft runs the features stage (STFT, power, band energies, raw features) on the generic kernel
     if (p->n_fft < 256 || p->n_fft > 4096 || (p->n_fft & (p->n_fft - 1)) != 0 || p->hop < 1 || p->hop > p->n_fft)
         return fail(ctx, -21, "unsupported STFT geometry n_fft=%d hop=%d (power of two 256..4096, 1 <= hop <= n_fft)", p->n_fft, p->hop);
-    const bool generic = !(p->n_fft == 256 && p->hop == 128);
+    // n_fft = 256 with any hop <= 128 stays on the specialised STFT kernel (features stage unless hop = 128)
+    const bool generic = !(p->n_fft == 256 && p->hop <= 128);
+    const bool full_ok = p->n_fft == 256 && p->hop == 128;
     const int F = p->n_fft / 2 + 1;
     const int K = p->band_hi - p->band_lo + 1;
     if (p->band_lo < 0 || p->band_hi >= F || K < 1 || (!generic && K > SEQ_KMAX)) return fail(ctx, -22, "operating band bins [%d,%d] unsupported", p->band_lo, p->band_hi);
@@ -249,6 +252,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     pl->ctx = ctx;
     pl->prm = *p;
     pl->generic = generic;
+    pl->full_ok = full_ok;
     pl->n_clips = n_clips;
     DevParams& d = pl->dp;
     memset(&d, 0, sizeof(d));
@@ -311,7 +315,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         const int64_t Tloc = 1 + (N - p->n_fft) / p->hop;
         pl->samp_off[c + 1] = pl->samp_off[c] + N;
         pl->frame_off[c + 1] = pl->frame_off[c] + T;
-        pl->stft_tile_off[c + 1] = pl->stft_tile_off[c] + (generic ? T : (T + STFT_TF - 1) / STFT_TF);
+        pl->stft_tile_off[c + 1] = pl->stft_tile_off[c] + (generic ? (T + stftg_frames_per_cta(p->n_fft) - 1) / stftg_frames_per_cta(p->n_fft) : (T + STFT_TF - 1) / STFT_TF);
         pl->td_tile_off[c + 1] = pl->td_tile_off[c] + std::max<int64_t>(1, (Tloc + TD_FT - 1) / TD_FT);
         pl->sel_chunk_off[c + 1] = pl->sel_chunk_off[c] + (T * K + SEL_CHUNK - 1) / SEL_CHUNK;
         pl->flux_tile_off[c + 1] = pl->flux_tile_off[c] + (T + FLUX_FT - 1) / FLUX_FT;
@@ -504,7 +508,7 @@ static cudaError_t launch_stft_generic(apt_plan* pl, const Batch& b, const PCM* 
     auto kern = stft_generic_kernel<T, PCM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<tile_grid(pl->stft_tile_off, b.clip0, b.n_clips), STFTG_NT, smem, st>>>(pl->dp, b, pcm, tab, so);
+    kern<<<tile_grid(pl->stft_tile_off, b.clip0, b.n_clips), STFTG_NT, smem, st>>>(pl->dp, b, pcm, tab, so, stftg_frames_per_cta(pl->dp.n_fft));
     pl->last_launches++;
     return cudaGetLastError();
 }
@@ -542,6 +546,8 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         return fail(ctx, -30, "full pipeline requires frame_class, rain_conf, noise_conf, event_idx, event_count, clip_stats buffers");
     if (!full && !(out->band_energy || out->P || out->S || out->raw))
         return fail(ctx, -31, "features stage requires at least one of band_energy / P / S / raw");
+    if (full && !pl->full_ok)
+        return fail(ctx, -34, "the full pipeline runs at n_fft=256 / hop=128 only; n_fft=%d hop=%d supports the features stage", d.n_fft, d.hop);
     if (pl->generic) {
         if (full) return fail(ctx, -34, "the full pipeline runs at n_fft=256 / hop=128 only; n_fft=%d hop=%d supports the features stage", d.n_fft, d.hop);
         StftOut sg;

@@ -247,10 +247,12 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
     for (int i = tid; i < 128; i += STFT_NT) s_tw128[i] = tab.tw128[i];
     for (int i = tid; i < 129; i += STFT_NT) s_tw256[i] = tab.tw256[i];
     {
-        const int64_t s0 = (int64_t)t0 * 128 - 128;
-        constexpr int NS_ = (STFT_TF + 1) * 128;
+        // frames t0 .. t0+TF-1 of hop p.hop (<= 128) cover samples [t0*hop - 128, (t0+TF-1)*hop + 128)
+        const int64_t s0 = (int64_t)t0 * p.hop - 128;
+        constexpr int NS_MAX = (STFT_TF + 1) * 128;
+        const int NS_ = (STFT_TF - 1) * p.hop + 256;
         if (s0 >= 0 && s0 + NS_ <= N)
-            load_run<(NS_ * (int)sizeof(PCM) / 16 + STFT_NT - 1) / STFT_NT + 1>(pcm, base + s0, NS_, [&](int i, float v) { s_x[i] = v; });
+            load_run<(NS_MAX * (int)sizeof(PCM) / 16 + STFT_NT - 1) / STFT_NT + 1>(pcm, base + s0, NS_, [&](int i, float v) { s_x[i] = v; });
         else
             stage_clip_f32(pcm, base, N, s0, NS_, s_x);
     }
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
     APT_STAMP2(21);
 
     const int fr = tid >> 3, lane = tid & 7;
-    const float* xs = s_x + fr * 128;
+    const float* xs = s_x + fr * p.hop;
     cx<T>* ex = s_ex + (size_t)fr * kExSize;
     // all STFT_TF frame slots run both passes (slots past the clip end transform zero padding and are never
     // written out): the warp barrier inside pass B needs every lane
@@ -351,61 +353,68 @@ struct FftTablesG {
     const T* win;        // [n_fft]
     const cx<T>* tw;     // [n_fft/2 + 1]  W_N^k
 };
+inline int stftg_frames_per_cta(int n_fft) { return n_fft >= 2048 ? 1 : 2048 / n_fft; }   // 512 -> 4, 1024 -> 2
 template <typename T>
 inline size_t stftg_smem_bytes(int n_fft) {
-    return sizeof(cx<T>) * (size_t)n_fft + sizeof(float) * (size_t)(n_fft / 2 + 4);
+    return (size_t)stftg_frames_per_cta(n_fft) * (sizeof(cx<T>) * (size_t)n_fft + sizeof(float) * (size_t)(n_fft / 2 + 4));
 }
 
 template <typename T, typename PCM>
 __global__ void __launch_bounds__(STFTG_NT) stft_generic_kernel(const __grid_constant__ DevParams p, Batch b,
-                                                                const PCM* __restrict__ pcm, FftTablesG<T> tab, StftOut o) {
+                                                                const PCM* __restrict__ pcm, FftTablesG<T> tab, StftOut o, int fpc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = p.n_fft, H = N >> 1, F = H + 1;
-    cx<T>* bufA = reinterpret_cast<cx<T>*>(smem_raw);
-    cx<T>* bufB = bufA + H;
-    float* s_P = reinterpret_cast<float*>(bufB + H);
+    const int N = p.n_fft, H = N >> 1, F = H + 1, PS = H + 4;
+    const int lgH2 = 31 - __clz(H >> 1);                       // log2(H/2)
+    cx<T>* bufA = reinterpret_cast<cx<T>*>(smem_raw);          // [fpc][H]
+    cx<T>* bufB = bufA + (size_t)fpc * H;                      // [fpc][H]
+    float* s_P = reinterpret_cast<float*>(bufB + (size_t)fpc * H);   // [fpc][PS]
     const int tid = threadIdx.x;
     const int c = b.clip0 + (int)blockIdx.y;
     const int64_t base = __ldg(b.samp_off + c);
     const int64_t Ns = __ldg(b.samp_off + c + 1) - base;
     const int64_t f0 = __ldg(b.frame_off + c);
     const int T_clip = (int)(__ldg(b.frame_off + c + 1) - f0);
-    const int t = blockIdx.x;
-    if (t >= T_clip) return;
-    // windowed frame, centre-padded with zeros (librosa center=True, pad_mode="constant")
-    const int64_t s0 = (int64_t)t * p.hop - H;
-    for (int n = tid; n < H; n += STFTG_NT) {
-        const int64_t sa = s0 + 2 * n, sb = sa + 1;
+    const int t0 = blockIdx.x * fpc;
+    if (t0 >= T_clip) return;
+    const int nfr = min(fpc, T_clip - t0);
+    // windowed frames, centre-padded with zeros (librosa center=True, pad_mode="constant")
+    for (int i = tid; i < nfr * H; i += STFTG_NT) {
+        const int f = i / H, n = i - f * H;
+        const int64_t sa = (int64_t)(t0 + f) * p.hop - H + 2 * n, sb = sa + 1;
         const T xa = (sa >= 0 && sa < Ns) ? (T)load_sample(pcm, base + sa) : (T)0;
         const T xb = (sb >= 0 && sb < Ns) ? (T)load_sample(pcm, base + sb) : (T)0;
-        bufA[n] = {tab.win[2 * n] * xa, tab.win[2 * n + 1] * xb};
+        bufA[i] = {tab.win[2 * n] * xa, tab.win[2 * n + 1] * xb};
     }
     __syncthreads();
     cx<T>* x = bufA;
     cx<T>* y = bufB;
     for (int q = 1; q < H; q <<= 1) {   // radix-2 Stockham passes, q = 1, 2, ..., H/2
-        const int tstep = H / q;        // W_{2q}^k = W_N^{k * N / (2q)} = W_N^{k * H / q}
-        for (int i = tid; i < (H >> 1); i += STFTG_NT) {
+        const int tstep = H / q;        // W_{2q}^k = W_N^{k * H / q}
+        for (int ii = tid; ii < nfr * (H >> 1); ii += STFTG_NT) {
+            const int f = ii >> lgH2, i = ii & ((H >> 1) - 1);
+            const cx<T>* xf = x + (size_t)f * H;
+            cx<T>* yf = y + (size_t)f * H;
             const int k = i & (q - 1);
             const int j = ((i - k) << 1) + k;
-            const cx<T> u0 = x[i];
-            const cx<T> xv = x[i + (H >> 1)];
+            const cx<T> u0 = xf[i];
+            const cx<T> xv = xf[i + (H >> 1)];
             const cx<T> u1 = (k == 0) ? xv : cmul(xv, tab.tw[k * tstep]);
-            y[j] = cadd(u0, u1);
-            y[j + q] = csub(u0, u1);
+            yf[j] = cadd(u0, u1);
+            yf[j + q] = csub(u0, u1);
         }
         __syncthreads();
         cx<T>* tmp = x; x = y; y = tmp;
     }
     // real-FFT unpack: X[k] = E + W_N^k O with E = (Z[k] + conj(Z[H-k]))/2, O = (Z[k] - conj(Z[H-k]))/(2i)
-    float* Sg = o.S ? o.S + ((f0 + t) * (int64_t)F) * 2 : nullptr;
     const T half = (T)0.5;
-    for (int k = tid; k < F; k += STFTG_NT) {
+    for (int i = tid; i < nfr * F; i += STFTG_NT) {
+        const int f = i / F, k = i - f * F;
+        const cx<T>* xf = x + (size_t)f * H;
         T re, im;
-        if (k == 0) { re = x[0].x + x[0].y; im = (T)0; }
-        else if (k == H) { re = x[0].x - x[0].y; im = (T)0; }
+        if (k == 0) { re = xf[0].x + xf[0].y; im = (T)0; }
+        else if (k == H) { re = xf[0].x - xf[0].y; im = (T)0; }
         else {
-            const cx<T> zk = x[k], cn = cconj(x[H - k]);
+            const cx<T> zk = xf[k], cn = cconj(xf[H - k]);
             const cx<T> e = {(zk.x + cn.x) * half, (zk.y + cn.y) * half};
             const cx<T> d = csub(zk, cn);
             const cx<T> od = {d.y * half, -d.x * half};
@@ -413,20 +422,25 @@ __global__ void __launch_bounds__(STFTG_NT) stft_generic_kernel(const __grid_con
             re = e.x + wo.x; im = e.y + wo.y;
         }
         const float sr = d2f((double)re), si = d2f((double)im);
-        if (Sg) { Sg[2 * k] = sr; Sg[2 * k + 1] = si; }
+        const int64_t fr = f0 + t0 + f;
+        if (o.S) { float2* Sg = reinterpret_cast<float2*>(o.S) + fr * F; Sg[k] = make_float2(sr, si); }
         const float a = np_cabsf(sr, si);
-        s_P[k] = a * a;
+        const float pw = a * a;
+        s_P[f * PS + k] = pw;
+        if (o.P) o.P[fr * F + k] = pw;
     }
     __syncthreads();
-    const int64_t fr = f0 + t;
-    if (o.P) for (int k = tid; k < F; k += STFTG_NT) o.P[fr * F + k] = s_P[k];
-    if (o.band_energy && tid <= p.M) {
-        double s = 0.0;
-        if (tid < p.M) { for (int k = p.mode_lo[tid]; k <= p.mode_hi[tid]; k++) s += (double)s_P[k]; }
-        else { for (int k = 0; k < p.K; k++) s += (double)s_P[p.band_lo + k]; s += p.eps64; }
-        o.band_energy[(int64_t)tid * o.nF + fr] = d2f(s);
+    if (o.band_energy) {
+        for (int i = tid; i < nfr * (p.M + 1); i += STFTG_NT) {
+            const int f = i / (p.M + 1), m = i - f * (p.M + 1);
+            const float* Pt = s_P + f * PS;
+            double s = 0.0;
+            if (m < p.M) { for (int k = p.mode_lo[m]; k <= p.mode_hi[m]; k++) s += (double)Pt[k]; }
+            else { for (int k = 0; k < p.K; k++) s += (double)Pt[p.band_lo + k]; s += p.eps64; }
+            o.band_energy[(int64_t)m * o.nF + f0 + t0 + f] = d2f(s);
+        }
     }
-    if (o.raw && tid == 0) raw_features_frame(p, s_P, o.freqs, o.raw + fr, o.nF);
+    if (o.raw && tid < nfr) raw_features_frame(p, s_P + tid * PS, o.freqs, o.raw + f0 + t0 + tid, o.nF);
 }
 
 // raw spectral features of one frame in float64 (feature_extraction.py:610-747)
