@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG, "libapt_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 MAX_MODES, MAX_SOS, N_RAW, N_TD, N_STATS = 8, 4, 21, 5, 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_GAIN_TAPS = 9
 STAGE_FEATURES, STAGE_FULL = 1, 2
 KERNEL_NAMES = ("stft256_kernel", "td_features_kernel", "trk1_kernel", "flux_kernel", "base_kernel",
@@ -63,7 +63,7 @@ class AptParams(C.Structure):
 
 OUT_FIELDS = ("frame_class", "rain_conf", "noise_conf", "event_idx", "event_count", "clip_stats",
               "S", "P", "det_noise_psd", "det_noise_lag", "D", "noise_psd", "mode_flux", "norm_flux",
-              "score", "td", "raw", "band_energy", "gate", "x_td", "G", "ratio_med", "S_hat")
+              "score", "td", "raw", "band_energy", "gate", "x_td", "G", "ratio_med", "S_hat", "y")
 
 
 class AptDsdParams(C.Structure):

@@ -650,9 +650,10 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             pl->last_launches++;
             CUDA_OK(ctx, cudaGetLastError());
         }
-        if (out->G || out->S_hat) {
+        if (out->G || out->S_hat || out->y) {
             pl->mark(APT_KERNEL_GAIN, st);
-            if (!out->G) return fail(ctx, -33, "S_hat requires the G buffer");
+            if (!out->G) return fail(ctx, -33, "S_hat / y require the G buffer");
+            if (out->y && !out->S_hat) return fail(ctx, -33, "y requires the S_hat buffer");
             if (out->S_hat && !out->S) return fail(ctx, -33, "S_hat requires the S buffer");
             GainIO gio;
             gio.P_band = pl->d_Pband.p; gio.N2 = n2_plane; gio.frame_class = out->frame_class; gio.G = out->G;
@@ -664,6 +665,13 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             if (out->S_hat) {
                 const int64_t n = (fend - fbeg) * d.F;
                 shat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pl->dp, fbeg, fend, out->G, out->S, out->S_hat);
+                pl->last_launches++;
+            }
+            if (out->y) {
+                int64_t max_n = 1;
+                for (int c = clip0; c < clip0 + n_clips; c++) max_n = std::max(max_n, pl->len[c]);
+                const dim3 grid((unsigned)((max_n + ISTFT_TH * 128 - 1) / (ISTFT_TH * 128)), (unsigned)n_clips);
+                istft256_kernel<<<grid, ISTFT_NT, 0, st>>>(pl->dp, b, out->S_hat, pl->d_win64.p, pl->d_tw256_64.p, out->y);
                 pl->last_launches++;
             }
             CUDA_OK(ctx, cudaGetLastError());

@@ -1573,6 +1573,88 @@ __global__ void __launch_bounds__(256) shat_kernel(const __grid_constant__ DevPa
 }
 
 // ---------------------------------------------------------------------------------------------
+// Inverse STFT of the gain-weighted spectrum (rain_signal_processor.py:1113-1128, librosa.istft with
+// center=True, Hann, length=len(x)): per frame the inverse real FFT (float64, as a 128-point complex
+// transform of the re-packed half spectrum), synthesis window, overlap-add in frame order, division by
+// the window sum-square where it exceeds float32 tiny, float32 output.  n_fft = 256, hop = 128.
+// One CTA per ISTFT_TH output hops; frames h0 .. h0+TH contribute.
+// ---------------------------------------------------------------------------------------------
+constexpr int ISTFT_TH = 8;
+constexpr int ISTFT_NT = 256;
+
+__global__ void __launch_bounds__(ISTFT_NT) istft256_kernel(const __grid_constant__ DevParams p, Batch b,
+                                                            const float* __restrict__ S_hat, const double* __restrict__ win,
+                                                            const cx<double>* __restrict__ tw256, float* __restrict__ y) {
+    constexpr int NF = ISTFT_TH + 1, H = 128;
+    __shared__ cx<double> bufA[NF][H];
+    __shared__ cx<double> bufB[NF][H];
+    const int tid = threadIdx.x;
+    const int c = b.clip0 + (int)blockIdx.y;
+    const int64_t base = __ldg(b.samp_off + c);
+    const int64_t N = __ldg(b.samp_off + c + 1) - base;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int h0 = blockIdx.x * ISTFT_TH;                       // first output hop of this CTA
+    if ((int64_t)h0 * 128 >= N) return;
+    // re-pack: Z[k] = E[k] + i O[k], E = (X[k] + conj(X[128-k]))/2, O = (X[k] - conj(X[128-k]))/2 * conj(W256^k);
+    // the inverse transform is conj(FFT128(conj(Z)))/128, so conj(Z) is what enters the forward passes
+    for (int i = tid; i < NF * H; i += ISTFT_NT) {
+        const int f = i >> 7, k = i & 127;
+        const int t = h0 + f;
+        cx<double> zc = {0.0, 0.0};
+        if (t < T) {
+            const float* X = S_hat + ((f0 + t) * (int64_t)p.F) * 2;
+            const cx<double> xk = {(double)X[2 * k], (double)X[2 * k + 1]};
+            const cx<double> xn = {(double)X[2 * (128 - k)], -(double)X[2 * (128 - k) + 1]};   // conj(X[128-k])
+            const cx<double> e = {(xk.x + xn.x) * 0.5, (xk.y + xn.y) * 0.5};
+            const cx<double> d = {(xk.x - xn.x) * 0.5, (xk.y - xn.y) * 0.5};
+            const cx<double> o = cmul(d, cconj(tw256[k]));
+            zc = {e.x - o.y, -(e.y + o.x)};                      // conj(E + iO)
+        }
+        bufA[f][k] = zc;
+    }
+    __syncthreads();
+    cx<double>(*x)[H] = bufA;
+    cx<double>(*yb)[H] = bufB;
+    for (int q = 1; q < H; q <<= 1) {
+        const int tstep = 2 * (H / q);                           // W_{2q}^k = W256^(k * 256 / (2q))
+        for (int ii = tid; ii < NF * (H >> 1); ii += ISTFT_NT) {
+            const int f = ii >> 6, i = ii & 63;
+            const int k = i & (q - 1);
+            const int j = ((i - k) << 1) + k;
+            const cx<double> u0 = x[f][i];
+            const cx<double> xv = x[f][i + (H >> 1)];
+            const cx<double> u1 = (k == 0) ? xv : cmul(xv, tw256[k * tstep >> 1]);
+            yb[f][j] = cadd(u0, u1);
+            yb[f][j + q] = csub(u0, u1);
+        }
+        __syncthreads();
+        cx<double>(*tmp)[H] = x; x = yb; yb = tmp;
+    }
+    // x[f][n] now holds 128 * conj(z[n]):  frame sample 2n = Re / 128, sample 2n+1 = -Im / 128
+    for (int i = tid; i < ISTFT_TH * 128; i += ISTFT_NT) {
+        const int64_t n = (int64_t)h0 * 128 + i;                 // output sample
+        if (n >= N) continue;
+        const int64_t pidx = n + 128;                            // index in the centre-padded signal
+        const int tb = (int)(pidx >> 7);                         // frames tb-1 and tb cover it
+        double acc = 0.0, wss = 0.0;
+#pragma unroll
+        for (int dt = -1; dt <= 0; dt++) {
+            const int t = tb + dt;
+            if (t < 0 || t >= T) continue;
+            const int m = (int)(pidx - (int64_t)t * 128);        // sample inside frame t
+            const cx<double> v = x[t - h0][m >> 1];
+            const double fs = ((m & 1) ? -v.y : v.x) * (1.0 / 128.0);
+            const double w = win[m];
+            acc += w * fs;
+            wss += w * w;
+        }
+        if (wss > 1.1754943508222875e-38) acc /= wss;
+        y[base + n] = d2f(acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // exact median of the dB plane per clip: 3-level MSD radix select on order-preserving keys.
 // Two ranks are selected at once (lower / upper middle of an even count).  Level 0 (bits 31..21) is
 // histogrammed by db_kernel while it produces the plane; levels 1 and 2 re-read it as a flat array.

@@ -85,9 +85,7 @@ class SpectralNoiseProcessor:
         cfg = self.cfg
         if sr is None:
             sr = cfg.fs
-        if bool(cfg.compute_output_audio):
-            raise NotImplementedError("compute_output_audio=True (ISTFT of the suppressed spectrum) is not "
-                                      "implemented on the CUDA path")
+        want_audio = bool(cfg.compute_output_audio)
         dv = DetectorView(cfg)
         keep_debug = bool(cfg.return_debug) or bool(cfg.debug_enable)
         keep_det = bool(cfg.return_detector_debug) or bool(cfg.debug_enable)
@@ -110,8 +108,10 @@ class SpectralNoiseProcessor:
             want.append("S")
             if suppress:
                 want += ["S_hat"] + ([] if "G" in want else ["G"])
-        if keep_filt:
+        if keep_filt or want_audio:
             want.append("x_td")
+        if want_audio and suppress:
+            want += [w for w in ("S", "G", "S_hat", "y") if w not in want]
         arrays = []
         for x in clips:
             a = np.asarray(x)
@@ -140,9 +140,13 @@ class SpectralNoiseProcessor:
             if keep_filt:
                 xf = out["x_td"][s0:s1].copy()
                 res["x_filt"] = xf
-                res["y"] = xf if bool(cfg.classifier_only_mode) else None
-                if not bool(cfg.classifier_only_mode):
-                    res["y_suppressed"] = None
+                if bool(cfg.classifier_only_mode):
+                    res["y"] = xf
+                else:
+                    # suppressed waveform (rain_signal_processor.py:1113-1128); bypass returns the prefiltered input
+                    yh = (out["y"][s0:s1].copy() if suppress else xf.copy()) if want_audio else None
+                    res["y"] = yh
+                    res["y_suppressed"] = yh
             if keep_spectra:
                 S = np.asfortranarray(out["S"][f0:f1].view(np.complex64).reshape(T, rp.F).T)
                 res["S"] = S

@@ -33,6 +33,7 @@ _PLANES = {
     "G": ("float32", lambda nF, nS, rp: (nF, rp.K)),
     "ratio_med": ("float32", lambda nF, nS, rp: (nF,)),
     "S_hat": ("float32", lambda nF, nS, rp: (nF, rp.F, 2)),
+    "y": ("float32", lambda nF, nS, rp: (nS,)),
 }
 _CORE = {
     "frame_class": ("int8", lambda nF, nC: (nF,)),

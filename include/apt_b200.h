@@ -39,7 +39,7 @@ extern "C" {
 #define APT_N_TD_FEATURES 5   /* crest, kurtosis, block crest, block width50, block post/pre */
 #define APT_N_CLIP_STATS 8
 #define APT_MAX_GAIN_TAPS 9
-#define APT_ABI_VERSION 2
+#define APT_ABI_VERSION 3
 
 typedef struct apt_ctx apt_ctx;
 typedef struct apt_plan apt_plan_t;
@@ -141,6 +141,7 @@ typedef struct apt_out_t {
     float*   G;               /* [nF][K]    suppressor gain over the band (debug["G"][band]) */
     float*   ratio_med;       /* [nF]       debug["np_ratio_median_t"] */
     float*   S_hat;           /* [nF][F][2] gain-weighted spectrum (state["S_hat"]); needs S */
+    float*   y;               /* [nS]       suppressed output audio = ISTFT(S_hat) (state["output_audio"]); needs S_hat */
 } apt_out_t;
 
 /* which stages a run executes */
@@ -194,7 +195,7 @@ int  apt_plan_last_launches(const apt_plan_t* plan);
 #define APT_KERNEL_DB 7        /* db_kernel: noise-floor dB plane, sums, level-0 histogram */
 #define APT_KERNEL_SELECT 8    /* select_hist/scan: median levels 1-2 */
 #define APT_KERNEL_FINALIZE 9  /* finalize_kernel */
-#define APT_KERNEL_GAIN 10     /* gain_kernel + gain_time_kernel (+ shat_kernel): only when G / S_hat is requested */
+#define APT_KERNEL_GAIN 10     /* gain_kernel + gain_time_kernel (+ shat_kernel, istft256_kernel): only when G / S_hat / y is requested */
 #define APT_N_KERNELS 11
 int  apt_plan_enable_timing(apt_plan_t* plan, int enable);
 int  apt_plan_kernel_ms(apt_plan_t* plan, float* out_ms /* [APT_N_KERNELS] */);

@@ -349,3 +349,23 @@ def test_mark3_loader_feeds_host_path(torch_cuda):
     assert np.array_equal(host["event_count"], out["event_count"])
     assert np.array_equal(host["clip_stats"], out["clip_stats"])
     eng.close()
+
+
+@pytest.mark.parametrize("name,seconds,seed,lam", [("audio_s14_l3_6s", 6.0, 14, 3.0), ("audio_s15_l10_5s", 5.03, 15, 10.0)])
+def test_output_audio_matches_reference(torch_cuda, name, seconds, seed, lam):
+    """compute_output_audio: gain -> S_hat -> inverse STFT (rain_signal_processor.py:1113-1128) through the
+    processor API, against the reference run (its ISTFT is the harness' librosa stand-in: unpinned link).
+    Tolerance: 2e-6 absolute on a waveform of amplitude <= 1 (float32 output of float64 overlap-add)."""
+    import os
+    from conftest import GOLDEN_DIR
+    from audio_processing_tools_b200.edge.rain_signal_processor import RainDetectorProcessor
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    pcm = synth_clip_i16(seconds, seed, lam)
+    params = default_params(check_duration=int(seconds), keep_state_audio=True, keep_state_spectra=True, keep_state_debug=True)
+    m, s = RainDetectorProcessor().run(pcm_to_f32(pcm), params)
+    assert np.array_equal(s["frame_class"], g["frame_class"])
+    assert s["output_audio"].dtype == np.float32 and s["output_audio"].shape == g["output_audio"].shape
+    np.testing.assert_allclose(s["filtered_audio"], g["filtered_audio"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(s["output_audio"], g["output_audio"], rtol=1e-5, atol=2e-6)
+    # (not bit-equal: scipy's irfft runs in float32 on complex64 input, the kernel inverts in float64)
+    assert float(np.abs(s["output_audio"] - g["output_audio"]).max()) < 2e-6
