@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG, "libapt_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 MAX_MODES, MAX_SOS, N_RAW, N_TD, N_STATS = 8, 4, 21, 5, 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_GAIN_TAPS = 9
 STAGE_FEATURES, STAGE_FULL = 1, 2
 KERNEL_NAMES = ("stft256_kernel", "td_features_kernel", "trk1_kernel", "flux_kernel", "base_kernel",
@@ -57,13 +57,17 @@ class AptParams(C.Structure):
         ("gain_taps", C.c_float * MAX_GAIN_TAPS),
         ("alpha_noise", C.c_float), ("one_minus_alpha_noise", C.c_float),
         ("alpha_base", C.c_float), ("one_minus_alpha_base", C.c_float), ("gain_eps_f32", C.c_float),
+        ("peak_top_p", C.c_int32), ("primary_top_m", C.c_int32),
+        ("peak_prominence_db", C.c_double), ("peak_min_db_above_floor", C.c_double), ("peak_ratio_min", C.c_double),
+        ("peak_valid_prom_min_db", C.c_float), ("peak_valid_prom_max_db", C.c_float),
         ("window", C.c_void_p), ("freqs", C.c_void_p),
     ]
 
 
 OUT_FIELDS = ("frame_class", "rain_conf", "noise_conf", "event_idx", "event_count", "clip_stats",
               "S", "P", "det_noise_psd", "det_noise_lag", "D", "noise_psd", "mode_flux", "norm_flux",
-              "score", "td", "raw", "band_energy", "gate", "x_td", "G", "ratio_med", "S_hat", "y")
+              "score", "td", "raw", "band_energy", "gate", "x_td", "G", "ratio_med", "S_hat",
+              "peak_ratio", "peak_gate_score", "peak_valid_count", "peak_count_by_mode", "y")
 
 
 class AptDsdParams(C.Structure):

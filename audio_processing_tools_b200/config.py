@@ -156,7 +156,7 @@ def _contiguous_bins(mask):
     return int(idx[0]), int(idx[-1])
 
 
-_UNSUPPORTED_DETECTOR_FLAGS = ("peak_features_enable", "flux_modes_winsor_enable",
+_UNSUPPORTED_DETECTOR_FLAGS = ("feature_dump_include_peak_payload", "flux_modes_winsor_enable",
                                "td_envelope_features_enable", "bypass_classifier",
                                "clip_spectral_occupancy_enable")
 
@@ -354,6 +354,17 @@ class ResolvedParams:
         P.alpha_noise, P.one_minus_alpha_noise = f32(a_noise), f32(1.0 - a_noise)
         P.alpha_base, P.one_minus_alpha_base = f32(alpha_base), f32(1.0 - alpha_base)
         P.gain_eps_f32 = f32(cfg.eps)
+
+        # --- optional peak-structure features (rain_frame_classifier.py:670-683)
+        self.peak_features = bool(dv.get("peak_features_enable", False))
+        P.peak_top_p = max(1, int(dv.get("peak_top_p", 6)))
+        P.primary_top_m = max(1, int(dv.get("primary_top_m", 3)))
+        P.peak_prominence_db = float(dv.get("peak_prominence_db", 3.0))
+        P.peak_min_db_above_floor = float(dv.get("peak_min_db_above_floor", 6.0))
+        P.peak_ratio_min = float(np.clip(float(dv.get("peak_ratio_min", 0.50)), 0.0, 1.0))
+        vmin = float(dv.get("peak_valid_prom_min_db", 3.0))
+        vmax = max(vmin, float(dv.get("peak_valid_prom_max_db", 6.0)))
+        P.peak_valid_prom_min_db, P.peak_valid_prom_max_db = f32(vmin), f32(vmax)
         P.window = self.window.ctypes.data_as(C.c_void_p)
         P.freqs = self.freqs.ctypes.data_as(C.c_void_p)
         self.c = P

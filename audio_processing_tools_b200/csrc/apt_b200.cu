@@ -66,7 +66,7 @@ struct apt_plan {
     int td_ns = 0;
     size_t td_smem = 0;
     // scratch
-    DevBuf<float> d_Pband, d_db, d_td, d_mf, d_nl, d_nl_all;
+    DevBuf<float> d_Pband, d_db, d_td, d_mf, d_nl, d_nl_all, d_Dscr;
     DevBuf<double> d_dbsum;   // [select chunks] float64 sums of the dB plane
     Trk1Tab tab_modes, tab_all;   // pass-1 lane tables: mode bins only / every band bin (debug planes)
     int mf_stride = 8;
@@ -222,6 +222,8 @@ int apt_params_default(apt_params_t* p) {
     p->gain_taps[0] = 0.2f; p->gain_taps[1] = 0.6f; p->gain_taps[2] = 0.2f;
     p->alpha_noise = 0.7f; p->one_minus_alpha_noise = 0.3f; p->alpha_base = 0.7f; p->one_minus_alpha_base = 0.3f;
     p->gain_eps_f32 = 1e-9f;
+    p->peak_top_p = 6; p->primary_top_m = 3; p->peak_prominence_db = 3.0; p->peak_min_db_above_floor = 6.0; p->peak_ratio_min = 0.5;
+    p->peak_valid_prom_min_db = 3.0f; p->peak_valid_prom_max_db = 6.0f;
     return 0;
 }
 
@@ -284,6 +286,9 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     for (int i = 0; i < APT_MAX_GAIN_TAPS; i++) d.gain_taps[i] = p->gain_taps[i];
     d.alpha_noise = p->alpha_noise; d.om_noise = p->one_minus_alpha_noise; d.alpha_base = p->alpha_base; d.om_base = p->one_minus_alpha_base;
     d.gain_eps = p->gain_eps_f32;
+    d.peak_top_p = p->peak_top_p; d.primary_top_m = p->primary_top_m; d.peak_prom_db = p->peak_prominence_db;
+    d.peak_min_above_floor = p->peak_min_db_above_floor; d.peak_ratio_min = p->peak_ratio_min;
+    d.peak_valid_prom_min = p->peak_valid_prom_min_db; d.peak_valid_prom_max = p->peak_valid_prom_max_db;
     if (p->n_gain_taps < 1 || p->n_gain_taps > APT_MAX_GAIN_TAPS || (p->n_gain_taps & 1) == 0) {
         delete pl; return fail(ctx, -32, "n_gain_taps=%d must be odd and <= %d", p->n_gain_taps, APT_MAX_GAIN_TAPS);
     }
@@ -588,7 +593,15 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
 
     const int64_t fbeg = pl->frame_off[clip0], fend = pl->frame_off[clip0 + n_clips];
     // tracker pass 1 on the mode bins (every band bin when one of its planes is requested)
-    const bool dbg = out->det_noise_psd || out->det_noise_lag || out->D;
+    const bool want_peaks = out->peak_ratio || out->peak_gate_score || out->peak_valid_count || out->peak_count_by_mode;
+    if (want_peaks && !(out->peak_ratio && out->peak_gate_score && out->peak_valid_count && out->peak_count_by_mode))
+        return fail(ctx, -35, "the four peak-feature buffers must be given together");
+    float* D_plane = out->D;
+    if (want_peaks && !D_plane) {   // the peak features read the detector input of every band bin
+        if (!pl->d_Dscr.p) CUDA_OK(ctx, pl->d_Dscr.alloc((size_t)pl->nF * d.K));
+        D_plane = pl->d_Dscr.p;
+    }
+    const bool dbg = out->det_noise_psd || out->det_noise_lag || D_plane;
     const Trk1Tab& tab = dbg ? pl->tab_all : pl->tab_modes;
     if (dbg && !pl->d_nl_all.p) CUDA_OK(ctx, pl->d_nl_all.alloc((size_t)pl->nF * pl->tab_all.nls));
     float* nl_plane = dbg ? pl->d_nl_all.p : pl->d_nl.p;
@@ -605,11 +618,21 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     {
         FluxIO io;
         io.P_band = pl->d_Pband.p; io.NL = nl_plane; io.nls = tab.nls; io.mf = pl->d_mf.p; io.stride = pl->mf_stride;
-        io.det_noise_lag = out->det_noise_lag; io.D = out->D; io.mode_flux = out->mode_flux; io.nF = pl->nF;
+        io.det_noise_lag = out->det_noise_lag; io.D = D_plane; io.mode_flux = out->mode_flux; io.nF = pl->nF;
         const int64_t tiles = pl->flux_tile_off[clip0 + n_clips] - pl->flux_tile_off[clip0];
         const size_t fsm = flux_smem_bytes(d.K, tab.n_lanes, tab.nls);
         CUDA_OK(ctx, cudaFuncSetAttribute(flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
         flux_kernel<<<tile_grid(pl->flux_tile_off, clip0, n_clips), 256, fsm, sc>>>(pl->dp, b, pl->d_flux_tile_off.p, tab, io);
+        pl->last_launches++;
+        CUDA_OK(ctx, cudaGetLastError());
+    }
+    if (want_peaks) {
+        PeakIO pio;
+        pio.D = D_plane; pio.ratio = out->peak_ratio; pio.gate_score = out->peak_gate_score;
+        pio.valid_count = out->peak_valid_count; pio.count_by_mode = out->peak_count_by_mode; pio.nF = pl->nF;
+        int64_t maxT = 1;
+        for (int c = clip0; c < clip0 + n_clips; c++) maxT = std::max(maxT, pl->frame_off[c + 1] - pl->frame_off[c]);
+        peak_kernel<<<dim3((unsigned)((maxT + 127) / 128), (unsigned)n_clips), 128, 0, sc>>>(pl->dp, b, pio);
         pl->last_launches++;
         CUDA_OK(ctx, cudaGetLastError());
     }

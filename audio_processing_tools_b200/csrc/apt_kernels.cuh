@@ -73,6 +73,10 @@ struct DevParams {
     float oversub_noise, oversub_rain, gain_floor, gain_ceil;
     float gain_taps[APT_MAX_GAIN_TAPS];
     float alpha_noise, om_noise, alpha_base, om_base, gain_eps;
+    // optional peak-structure features
+    int peak_top_p, primary_top_m;
+    double peak_prom_db, peak_min_above_floor, peak_ratio_min;
+    float peak_valid_prom_min, peak_valid_prom_max;
 };
 
 // A launch covers clips [clip0, clip0 + n_clips) of the plan; the offset arrays are the plan's
@@ -1447,6 +1451,115 @@ __global__ void __launch_bounds__(128) trk2_kernel(const __grid_constant__ DevPa
             if (L.store) Nk[(size_t)t * K] = n2;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Optional peak-structure features (rain_frame_classifier.py:761-843; peak_features_enable, default off;
+// debug outputs only).  One thread per frame on the detector input D (dB above the lagged noise):
+// scipy.signal.find_peaks(D, prominence=, height=median + min_above_floor) in float64 -- local maxima with
+// plateau midpoints (_local_maxima_1d), height filter, prominences over the whole row (_peak_prominences,
+// wlen=None) -- then the reference's valid-prominence range in float32, per-mode counts, and the top-P
+// gate (strongest peaks: share inside any mode band, primary band among the first top_m).
+// ---------------------------------------------------------------------------------------------
+struct PeakIO {
+    const float* D;            // [nF][K]
+    float* ratio; float* gate_score; int32_t* valid_count; int32_t* count_by_mode;   // [nF], [nF], [nF], [M][nF]
+    int64_t nF;
+};
+
+__global__ void __launch_bounds__(128) peak_kernel(const __grid_constant__ DevParams p, Batch b, PeakIO io) {
+    const int c = b.clip0 + (int)blockIdx.y;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int K = p.K, M = p.M;
+    const int64_t g = f0 + t;
+    int cnt_mode[APT_MAX_MODES];
+    for (int m = 0; m < M; m++) cnt_mode[m] = 0;
+    float ratio_o = 0.0f, gate_o = 0.0f;
+    int valid_o = 0;
+    if (t >= 1) {
+        float xf[SEQ_KMAX];
+        const float* row = io.D + g * K;
+        for (int k = 0; k < K; k++) xf[k] = row[k];
+        // np.median of the float32 row: middle element, or the float32 mean of the two middle ones
+        float lo = 0.0f, hi = 0.0f;
+        for (int k = 0; k < K; k++) {
+            int rank = 0;
+            for (int j = 0; j < K; j++) rank += (xf[j] < xf[k]) || (xf[j] == xf[k] && j < k);
+            if (rank == (K - 1) / 2) lo = xf[k];
+            if (rank == K / 2) hi = xf[k];
+        }
+        const float med = (K & 1) ? lo : f_div(lo + hi, 2.0f);
+        const double hthr = (double)med + p.peak_min_above_floor;
+        // peaks surviving the height and prominence filters: index, height (float32), prominence (float32)
+        unsigned char pk_i[SEQ_KMAX / 2 + 1];
+        float pk_h[SEQ_KMAX / 2 + 1];
+        int npk = 0;
+        int i = 1;
+        const int imax = K - 1;
+        while (i < imax) {
+            if (xf[i - 1] < xf[i]) {
+                int ia = i + 1;
+                while (ia < imax && xf[ia] == xf[i]) ia++;
+                if (xf[ia] < xf[i]) {
+                    const int pk = (i + ia - 1) / 2;                 // plateau midpoint
+                    const double xp = (double)xf[pk];
+                    if (hthr <= xp) {
+                        // prominence over the whole row
+                        double lmin = xp, rmin = xp;
+                        for (int j = pk; j >= 0 && xf[j] <= xf[pk]; j--) if ((double)xf[j] < lmin) lmin = (double)xf[j];
+                        for (int j = pk; j <= K - 1 && xf[j] <= xf[pk]; j++) if ((double)xf[j] < rmin) rmin = (double)xf[j];
+                        const double prom = xp - (lmin > rmin ? lmin : rmin);
+                        if (p.peak_prom_db <= prom) {
+                            const float pf = d2f(prom);
+                            if (pf >= p.peak_valid_prom_min && pf <= p.peak_valid_prom_max) {   // valid_prom_mask, float32
+                                pk_i[npk] = (unsigned char)pk; pk_h[npk] = xf[pk]; npk++;
+                            }
+                        }
+                    }
+                    i = ia;
+                    continue;
+                }
+                i = ia;
+                continue;
+            }
+            i++;
+        }
+        valid_o = npk;
+        for (int q = 0; q < npk; q++) {
+            const int kb = pk_i[q];
+            for (int m = 0; m < M; m++) if (kb >= p.mode_blo[m] && kb <= p.mode_bhi[m]) cnt_mode[m]++;
+        }
+        if (npk > 0) {
+            // strongest top-P valid peaks, tallest first (ties: higher bin first, as a reversed stable argsort)
+            const int nsel = min(p.peak_top_p, npk);
+            unsigned long long used = 0ull, used_hi = 0ull;
+            int in_any = 0;
+            bool primary_ok = false;
+            const int top_m = min(p.primary_top_m, nsel);
+            for (int s_ = 0; s_ < nsel; s_++) {
+                int best = -1;
+                for (int q = 0; q < npk; q++) {
+                    const bool u = q < 64 ? ((used >> q) & 1ull) : ((used_hi >> (q - 64)) & 1ull);
+                    if (u) continue;
+                    if (best < 0 || pk_h[q] > pk_h[best] || (pk_h[q] == pk_h[best] && pk_i[q] > pk_i[best])) best = q;
+                }
+                if (best < 64) used |= 1ull << best; else used_hi |= 1ull << (best - 64);
+                const int kb = pk_i[best];
+                bool any = false;
+                for (int m = 0; m < M; m++) any = any || (kb >= p.mode_blo[m] && kb <= p.mode_bhi[m]);
+                in_any += any ? 1 : 0;
+                if (s_ < top_m && kb >= p.mode_blo[0] && kb <= p.mode_bhi[0]) primary_ok = true;
+            }
+            const double ratio = (double)in_any / (double)max(1, nsel);
+            ratio_o = d2f(ratio);
+            gate_o = (primary_ok && ratio >= p.peak_ratio_min) ? 1.0f : 0.0f;
+        }
+    }
+    io.ratio[g] = ratio_o; io.gate_score[g] = gate_o; io.valid_count[g] = valid_o;
+    for (int m = 0; m < M; m++) io.count_by_mode[(int64_t)m * io.nF + g] = cnt_mode[m];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -100,6 +100,9 @@ class SpectralNoiseProcessor:
                 want += ["G", "ratio_med"]
         if keep_noise and "noise_psd" not in want:
             want.append("noise_psd")
+        peaks = keep_det and bool(dv.get("peak_features_enable", False))
+        if peaks:
+            want += ["peak_ratio", "peak_gate_score", "peak_valid_count", "peak_count_by_mode"]
         if keep_det:
             want += ["norm_flux", "score", "td", "gate"]
             if dv.get("raw_spectral_shape_enable", True):
@@ -190,8 +193,13 @@ class SpectralNoiseProcessor:
             "td_gate_mask": gate,
             "td_gate_threshold": float(dv.get("td_gate_threshold", 2.5)),
             "td_kurtosis_upper_threshold": dv.get("td_kurtosis_upper_threshold", None),
-            "peak_features_enable": False,
+            "peak_features_enable": "peak_ratio" in out,
         }
+        if "peak_ratio" in out:
+            d["peak_ratio"] = out["peak_ratio"][f0:f1].copy()
+            d["peak_gate_score"] = out["peak_gate_score"][f0:f1].copy()
+            d["peak_valid_count"] = out["peak_valid_count"][f0:f1].copy()
+            d["peak_count_by_mode"] = out["peak_count_by_mode"][:, f0:f1].copy()
         for i in range(1, 4):
             d[f"support_mode_flux_{i}_gated"] = d[f"support_mode_flux_{i}"] * gs
         d["primary_mode_flux_gated"] = d["primary_mode_flux"] * gs

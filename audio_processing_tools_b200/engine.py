@@ -34,6 +34,10 @@ _PLANES = {
     "ratio_med": ("float32", lambda nF, nS, rp: (nF,)),
     "S_hat": ("float32", lambda nF, nS, rp: (nF, rp.F, 2)),
     "y": ("float32", lambda nF, nS, rp: (nS,)),
+    "peak_ratio": ("float32", lambda nF, nS, rp: (nF,)),
+    "peak_gate_score": ("float32", lambda nF, nS, rp: (nF,)),
+    "peak_valid_count": ("int32", lambda nF, nS, rp: (nF,)),
+    "peak_count_by_mode": ("int32", lambda nF, nS, rp: (rp.M, nF)),
 }
 _CORE = {
     "frame_class": ("int8", lambda nF, nC: (nF,)),

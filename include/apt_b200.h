@@ -39,7 +39,7 @@ extern "C" {
 #define APT_N_TD_FEATURES 5   /* crest, kurtosis, block crest, block width50, block post/pre */
 #define APT_N_CLIP_STATS 8
 #define APT_MAX_GAIN_TAPS 9
-#define APT_ABI_VERSION 3
+#define APT_ABI_VERSION 4
 
 typedef struct apt_ctx apt_ctx;
 typedef struct apt_plan apt_plan_t;
@@ -103,6 +103,10 @@ typedef struct apt_params_t {
     float   alpha_noise, one_minus_alpha_noise;/* temporal smoothing on noise-like frames (:508-516) */
     float   alpha_base, one_minus_alpha_base;  /* non-adaptive mode (:522-523) */
     float   gain_eps_f32;
+    /* optional peak-structure features, rain_frame_classifier.py:670-683, :761-843 (debug outputs only) */
+    int32_t peak_top_p, primary_top_m;
+    double  peak_prominence_db, peak_min_db_above_floor, peak_ratio_min;
+    float   peak_valid_prom_min_db, peak_valid_prom_max_db;
     /* host pointers, copied at plan creation */
     const double* window;                      /* n_fft analysis window (scipy get_window) */
     const float*  freqs;                       /* n_fft/2+1 bin frequencies as float32 */
@@ -141,6 +145,10 @@ typedef struct apt_out_t {
     float*   G;               /* [nF][K]    suppressor gain over the band (debug["G"][band]) */
     float*   ratio_med;       /* [nF]       debug["np_ratio_median_t"] */
     float*   S_hat;           /* [nF][F][2] gain-weighted spectrum (state["S_hat"]); needs S */
+    float*   peak_ratio;      /* [nF]       det_debug["peak_ratio"]        (peak_features_enable) */
+    float*   peak_gate_score; /* [nF]       det_debug["peak_gate_score"]   (all four or none) */
+    int32_t* peak_valid_count;/* [nF]       det_debug["peak_valid_count"] */
+    int32_t* peak_count_by_mode; /* [M][nF] det_debug["peak_count_by_mode"] */
     float*   y;               /* [nS]       suppressed output audio = ISTFT(S_hat) (state["output_audio"]); needs S_hat */
 } apt_out_t;
 

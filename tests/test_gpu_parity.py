@@ -369,3 +369,26 @@ def test_output_audio_matches_reference(torch_cuda, name, seconds, seed, lam):
     np.testing.assert_allclose(s["output_audio"], g["output_audio"], rtol=1e-5, atol=2e-6)
     # (not bit-equal: scipy's irfft runs in float32 on complex64 input, the kernel inverts in float64)
     assert float(np.abs(s["output_audio"] - g["output_audio"]).max()) < 2e-6
+
+
+@pytest.mark.parametrize("name", ["peaks_s16_l10_20s", "peaks_s17_l3_15s_alt"])
+def test_peak_features_match_reference(torch_cuda, name):
+    """Optional peak-structure features (rain_frame_classifier.py:761-843, peak_features_enable): integer counts and
+    the binary gate bit-exact, the top-P ratio equal as float32, against the unmodified reference."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from audio_processing_tools_b200.edge.rain_signal_processor import RainDetectorProcessor
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(str(g["meta"]))
+    pcm = synth_clip_i16(meta["seconds"], meta["seed"], meta["lam"])
+    params = default_params(check_duration=int(meta["seconds"]), keep_state_debug=True)
+    params["detector"].update({"peak_features_enable": True, **meta["detector_extra"]})
+    m, s = RainDetectorProcessor().run(pcm_to_f32(pcm), params)
+    dd = s["det_debug"]
+    assert np.array_equal(s["frame_class"], g["frame_class"])
+    assert dd["peak_features_enable"] is True
+    assert np.array_equal(dd["peak_valid_count"], g["peak_valid_count"])
+    assert np.array_equal(dd["peak_count_by_mode"], g["peak_count_by_mode"])
+    assert np.array_equal(dd["peak_gate_score"], g["peak_gate_score"])
+    assert np.array_equal(dd["peak_ratio"], g["peak_ratio"])
