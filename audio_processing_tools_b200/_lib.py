@@ -75,6 +75,28 @@ class AptDsdParams(C.Structure):
                 ("window", C.c_void_p)]
 
 
+BNE_MAX_SOS, BNE_MAX_S, BNE_MAX_BANDS, BNE_FRAME_F, BNE_STATS = 8, 8, 8, 12, 16
+
+
+class AptBneParams(C.Structure):
+    _fields_ = [
+        ("fs", C.c_int32), ("N", C.c_int32), ("sub_len", C.c_int32), ("S", C.c_int32),
+        ("ns_h", C.c_int32), ("ns_b", C.c_int32), ("warm", C.c_int32), ("pad0", C.c_int32),
+        ("sos_h", (C.c_double * 6) * BNE_MAX_SOS), ("zi_h", (C.c_double * 2) * BNE_MAX_SOS),
+        ("sos_b", (C.c_double * 6) * BNE_MAX_SOS), ("zi_b", (C.c_double * 2) * BNE_MAX_SOS),
+        ("n_bands", C.c_int32), ("band_b0", C.c_int32 * BNE_MAX_BANDS), ("band_b1", C.c_int32 * BNE_MAX_BANDS),
+        ("prim_b0", C.c_int32), ("prim_b1", C.c_int32), ("mask_b0", C.c_int32), ("mask_b1", C.c_int32), ("pad1", C.c_int32),
+        ("M_ratio", C.c_double), ("N_ratio", C.c_double), ("D_ratio", C.c_double), ("band_rise_db", C.c_double),
+        ("excess_rise_db", C.c_double), ("min_Ehpf", C.c_double), ("min_Eband", C.c_double), ("dE_thr", C.c_double),
+        ("k_subframes", C.c_int32), ("use_dE", C.c_int32), ("use_D", C.c_int32), ("pad2", C.c_int32),
+        ("W", C.c_int32), ("W_min", C.c_int32), ("ttl", C.c_int32), ("smooth", C.c_int32), ("learn_all", C.c_int32),
+        ("replenish", C.c_int32), ("replenish_only_not_full", C.c_int32), ("q_adapt", C.c_int32),
+        ("q", C.c_double), ("ema_alpha", C.c_double), ("beta", C.c_double), ("gain_floor", C.c_double), ("eps", C.c_double),
+        ("att_dry", C.c_double), ("att_wet", C.c_double), ("release", C.c_double), ("repl_q", C.c_double),
+        ("q_repl_alpha", C.c_double), ("q_norm_alpha", C.c_double),
+    ]
+
+
 class AptOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in OUT_FIELDS]
 
@@ -85,7 +107,7 @@ EXPORTS = ("apt_init", "apt_destroy", "apt_last_error", "apt_abi_version", "apt_
            "apt_plan_offsets", "apt_plan_total_frames", "apt_plan_total_samples",
            "apt_plan_scratch_bytes", "apt_run_i16", "apt_run_f32", "apt_plan_last_launches",
            "apt_run_host_i16", "apt_plan_enable_timing", "apt_plan_kernel_ms", "apt_selftest",
-           "apt_dsd_run_i16")
+           "apt_dsd_run_i16", "apt_sizeof_bne_params", "apt_bne_run")
 
 
 def build(force=False, verbose=False):
@@ -132,6 +154,9 @@ def load():
     L.apt_run_f32.argtypes = [vp, C.c_int, vp, C.POINTER(AptOut), vp]
     L.apt_run_host_i16.argtypes = [vp] * 8
     L.apt_selftest.argtypes = [vp, C.c_int, C.c_int64, i64p]
+    L.apt_bne_run.argtypes = [vp, C.POINTER(AptBneParams), C.c_int, i64p, vp, C.c_int, vp, vp, vp, vp, vp]
+    if L.apt_sizeof_bne_params() != C.sizeof(AptBneParams):
+        raise RuntimeError("libapt_b200.so apt_bne_params_t layout differs from the Python binding")
     L.apt_dsd_run_i16.argtypes = [vp, C.POINTER(AptDsdParams), C.c_int, i64p, C.POINTER(C.c_double), vp, vp, vp, C.c_int, vp]
     L.apt_plan_enable_timing.argtypes = [vp, C.c_int]
     L.apt_plan_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]

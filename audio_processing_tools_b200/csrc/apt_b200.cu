@@ -11,6 +11,7 @@
 
 #include "apt_kernels.cuh"
 #include "apt_dsd.cuh"
+#include "apt_bne.cuh"
 
 using namespace apt;
 
@@ -853,6 +854,51 @@ extern "C" int apt_dsd_run_i16(apt_ctx* ctx, const apt_dsd_params_t* p, int n_cl
     dsd_frame_kernel<<<dim3((unsigned)max_fr, (unsigned)n_clips), DSD_NT, smem, st>>>(d, 0, d_so.p, d_fo.p, dev_pcm, d_win.p, d_tw.p,
                                                                                        d_drop.p, d_pki.p, d_pkv.p);
     dsd_minutes_kernel<<<(n_clips + 63) / 64, 64, 0, st>>>(d, n_clips, d_so.p, d_fo.p, d_ts.p, d_drop.p, d_pki.p, d_pkv.p, dev_out, dev_n_minutes);
+    CUDA_OK(ctx, cudaGetLastError());
+    CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int apt_sizeof_bne_params(void) { return (int)sizeof(apt_bne_params_t); }
+
+extern "C" int apt_bne_run(apt_ctx* ctx, const apt_bne_params_t* p, int n_clips, const int64_t* clip_len, const void* dev_pcm, int is_f32,
+                           double* dev_frame_out, uint8_t* dev_mask, double* dev_subE, double* dev_stats, void* stream) {
+    if (!ctx) return -1;
+    if (!p || !clip_len || !dev_pcm || !dev_frame_out || !dev_mask || !dev_subE || !dev_stats || n_clips <= 0 || n_clips > 65535)
+        return fail(ctx, -1, "apt_bne_run: bad arguments");
+    const int N = p->N;
+    if (N < 64 || N > 4096 || (N & (N - 1)) != 0) return fail(ctx, -21, "apt_bne_run: frame_len=%d must be a power of two in 64..4096", N);
+    if (p->sub_len < 8 || p->sub_len > 128 || p->sub_len % 8 != 0 || N % p->sub_len != 0 || p->S != N / p->sub_len || p->S > BNE_MAX_S)
+        return fail(ctx, -26, "apt_bne_run: subframes of %d samples (need a multiple of 8 up to 128 tiling the frame, at most %d per frame)", p->sub_len, BNE_MAX_S);
+    if (p->ns_h < 0 || p->ns_h > BNE_MAX_SOS || p->ns_b < 1 || p->ns_b > BNE_MAX_SOS) return fail(ctx, -24, "apt_bne_run: filter sections out of range");
+    if (p->W < 1 || p->W > BNE_MAX_W || p->W_min < 0 || p->W_min > p->W) return fail(ctx, -26, "apt_bne_run: W=%d outside [1,%d]", p->W, BNE_MAX_W);
+    if (p->n_bands < 0 || p->n_bands > BNE_MAX_BANDS || p->warm < 0) return fail(ctx, -26, "apt_bne_run: bad band table / warm-up");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int64_t> so(n_clips + 1, 0), fo(n_clips + 1, 0), sg(n_clips + 1, 0);
+    int64_t max_fr = 1;
+    for (int c = 0; c < n_clips; c++) {
+        const int64_t nf = clip_len[c] / N;
+        so[c + 1] = so[c] + clip_len[c]; fo[c + 1] = fo[c] + nf; sg[c + 1] = sg[c] + (nf + BNE_SEG - 1) / BNE_SEG;
+        max_fr = std::max(max_fr, nf);
+    }
+    DevBuf<int64_t> d_so, d_fo, d_sg; DevBuf<double> d_xhp, d_subEh, d_fftq; DevBuf<cx<double>> d_tw;
+    CUDA_OK(ctx, upload(d_so, so)); CUDA_OK(ctx, upload(d_fo, fo)); CUDA_OK(ctx, upload(d_sg, sg));
+    std::vector<cx<double>> tw(N / 2 + 1);
+    for (int k = 0; k <= N / 2; k++) tw[k] = {cos(2.0 * M_PI * k / N), -sin(2.0 * M_PI * k / N)};
+    CUDA_OK(ctx, upload(d_tw, tw));
+    const size_t nf_tot = (size_t)std::max<int64_t>(1, fo[n_clips]);
+    CUDA_OK(ctx, d_xhp.alloc((size_t)std::max<int64_t>(1, so[n_clips])));
+    CUDA_OK(ctx, d_subEh.alloc(nf_tot * BNE_MAX_S)); CUDA_OK(ctx, d_fftq.alloc(nf_tot * 4));
+    const int64_t nseg = sg[n_clips];
+    if (nseg > 0) {
+        if (is_f32) bne_filter_kernel<float><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, (const float*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
+        else bne_filter_kernel<int16_t><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, (const int16_t*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
+        const size_t smem = sizeof(cx<double>) * (size_t)N + sizeof(double) * (size_t)(N + 2);
+        CUDA_OK(ctx, cudaFuncSetAttribute(bne_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bne_fft_kernel<<<dim3((unsigned)max_fr, (unsigned)n_clips), BNE_NT, smem, st>>>(*p, d_so.p, d_fo.p, d_xhp.p, d_tw.p, d_fftq.p);
+    }
+    bne_state_kernel<<<(n_clips + 63) / 64, 64, 0, st>>>(*p, n_clips, d_fo.p, d_subEh.p, dev_subE, d_fftq.p, dev_frame_out, dev_mask, dev_stats);
     CUDA_OK(ctx, cudaGetLastError());
     CUDA_OK(ctx, cudaStreamSynchronize(st));
     return 0;

@@ -233,6 +233,37 @@ typedef struct apt_dsd_params_t {
 int  apt_dsd_run_i16(apt_ctx* ctx, const apt_dsd_params_t* p, int n_clips, const int64_t* clip_len, const double* ts,
                      const int16_t* dev_pcm, double* dev_out, int32_t* dev_n_minutes, int max_minutes, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Band noise estimator: replaces the per-frame loop of BandNoiseEstimatorProcessor.run
+ * (edge/band_noise_processor.py:82-281) over BandNoiseEstimator.process_frame
+ * (edge/band_noise_estimator.py:770-986) for a batch of clips; float64 configuration, hop == frame_len.
+ * The host resolves the configuration (filter design, bins, ratios) exactly as the reference's constructors do.
+ * ------------------------------------------------------------------------------------------- */
+#define APT_BNE_MAX_SOS 8
+#define APT_BNE_MAX_S 8
+#define APT_BNE_MAX_BANDS 8
+#define APT_BNE_FRAME_F 12   /* M_band, E_band, N_E, N_E_raw, G_mag, M_clean, noise_effective_q, M_band_fft, E_band_fft,
+                                E_hpf, N_sub, fft_rain_frame */
+#define APT_BNE_STATS 16     /* noise/rain/total energy sums, noise/rain/total frame counts, buffer valid / min valid /
+                                underflow counts, frames_since_noise_update, learned, replenished, noise_effective_q */
+typedef struct apt_bne_params_t {
+    int32_t fs, N, sub_len, S;
+    int32_t ns_h, ns_b, warm, pad0;            /* sections of the HPF / BPF, warm-up samples of a filter segment */
+    double  sos_h[APT_BNE_MAX_SOS][6], zi_h[APT_BNE_MAX_SOS][2];   /* scipy butter(...,"sos"), sosfilt_zi */
+    double  sos_b[APT_BNE_MAX_SOS][6], zi_b[APT_BNE_MAX_SOS][2];
+    int32_t n_bands, band_b0[APT_BNE_MAX_BANDS], band_b1[APT_BNE_MAX_BANDS], prim_b0, prim_b1, mask_b0, mask_b1, pad1;
+    double  M_ratio, N_ratio, D_ratio, band_rise_db, excess_rise_db, min_Ehpf, min_Eband, dE_thr;
+    int32_t k_subframes, use_dE, use_D, pad2;
+    int32_t W, W_min, ttl, smooth, learn_all, replenish, replenish_only_not_full, q_adapt;
+    double  q, ema_alpha, beta, gain_floor, eps, att_dry, att_wet, release, repl_q, q_repl_alpha, q_norm_alpha;
+} apt_bne_params_t;
+int  apt_sizeof_bne_params(void);
+/* dev_pcm: concatenated clips (int16 scaled /32767 as audio_io.safe_to_float when is_f32 == 0, else float32).
+   dev_frame_out [nF][APT_BNE_FRAME_F] f64, dev_mask [nF] u8 (bit s = rain_submask[s]), dev_subE [nF][APT_BNE_MAX_S] f64,
+   dev_stats [n_clips][APT_BNE_STATS] f64; nF = sum over clips of len / N.  Synchronises the stream before returning. */
+int  apt_bne_run(apt_ctx* ctx, const apt_bne_params_t* p, int n_clips, const int64_t* clip_len, const void* dev_pcm, int is_f32,
+                 double* dev_frame_out, uint8_t* dev_mask, double* dev_subE, double* dev_stats, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -392,3 +392,42 @@ def test_peak_features_match_reference(torch_cuda, name):
     assert np.array_equal(dd["peak_count_by_mode"], g["peak_count_by_mode"])
     assert np.array_equal(dd["peak_gate_score"], g["peak_gate_score"])
     assert np.array_equal(dd["peak_ratio"], g["peak_ratio"])
+
+
+@pytest.mark.parametrize("idx", range(6))
+def test_band_noise_estimator_matches_reference(torch_cuda, idx):
+    """the GPU band noise estimator through BandNoiseEstimatorProcessor.run against the unmodified
+    reference: rain masks / FFT rain flags / counters bit-exact, float64 series within 1e-9 relative
+    (block-wise streaming filters and another FFT algorithm: 1e-13-level differences before accumulation)."""
+    from test_band_noise_oracle import band_cases, case_pcm, check_against_golden
+    from audio_processing_tools_b200.edge.band_noise_processor import BandNoiseEstimatorProcessor
+    g, meta = band_cases()
+    m = meta[idx]
+    params = {"sample_rate": 11162, "check_duration": m["seconds"], **m["extra"]}
+    res, st = BandNoiseEstimatorProcessor().run(pcm_to_f32(case_pcm(m)), params)
+    check_against_golden(st, g, m["name"], rtol=1e-9)
+    import json
+    ref = json.loads(str(g[m["name"] + "__results"]))
+    for k, v in ref.items():
+        if isinstance(v, str):
+            assert res[k] == v, k
+        elif isinstance(v, int):
+            assert res[k] == v, k
+        else:
+            assert res[k] == pytest.approx(v, rel=1e-9, nan_ok=True), k
+
+
+def test_band_noise_batch_and_int16(torch_cuda):
+    """A ragged batch (int16 wire input) equals the per-clip runs; clips shorter than one frame give empty outputs."""
+    from audio_processing_tools_b200.edge.band_noise_processor import BandNoiseEstimatorProcessor
+    clips = [synth_clip_i16(20.0, 81, 3.0), synth_clip_i16(0.03, 82, 3.0), synth_clip_i16(31.4, 83, 10.0)]
+    proc = BandNoiseEstimatorProcessor()
+    params = {"sample_rate": 11162}
+    batch = proc.run_batch(clips, params)
+    assert batch[1][0]["n_frames"] == 0 and np.isnan(batch[1][0]["gain_med"])
+    for c, (res, st) in zip(clips, batch):
+        r1, s1 = proc.run(pcm_to_f32(c), params)
+        assert r1["n_frames"] == res["n_frames"]
+        for k in ("M_clean", "N_E", "G_mag", "subE"):
+            assert np.array_equal(s1[k], st[k]), k
+        assert np.array_equal(s1["rain_submask"], st["rain_submask"])
