@@ -844,8 +844,12 @@ __global__ void __launch_bounds__(TD_NT, 3) td_features_kernel(const __grid_cons
     double xe = 0.0;
     if (exact_r) {
         if (tid == ia) {   // scipy seeds the backward pass with zi * (last forward output)
+            // through shared memory (s_x is free between the passes): a run-time index into y[] would
+            // move the whole register array to local memory
+            double* tmp = reinterpret_cast<double*>(s_x);
 #pragma unroll
-            for (int j = 0; j < TD_CHUNK; j++) if (j == n_mine - 1) xe = y[j];
+            for (int j = 0; j < TD_CHUNK; j++) tmp[j] = y[j];
+            xe = tmp[n_mine - 1];
         }
     } else if (a0 + TD_CHUNK > len) {   // forward ringing behind the buffer end must not enter the backward pass
 #pragma unroll
