@@ -102,14 +102,24 @@ __device__ __forceinline__ bool tile_clip(const Batch& b, const int64_t* __restr
 __device__ __forceinline__ float load_sample(const int16_t* p, int64_t i) { return pcm_to_f32(__ldg(p + i)); }
 __device__ __forceinline__ float load_sample(const float* p, int64_t i) { return __ldg(p + i); }
 
+// First i >= 0 such that element g + i of the PCM buffer sits on a 16-byte boundary.
+template <typename PCM>
+__device__ __forceinline__ int run_head(int64_t g) {
+    constexpr int VEC = 16 / (int)sizeof(PCM);
+    return (int)((VEC - (g % VEC + VEC) % VEC) % VEC);
+}
+
 // Loads the n samples that start at absolute element index g (all inside the PCM buffer) and hands
-// them to put(i, value).  128-bit loads on 16-byte aligned addresses; every load of a thread is issued
-// before the first conversion so the misses overlap (MAXV = vectors per thread upper bound).
-template <int MAXV, typename PCM, typename Put>
-__device__ __forceinline__ void load_run(const PCM* __restrict__ pcm, int64_t g, int n, Put put) {
+// them to put(i, value) / put4(i, four values i..i+3).  128-bit loads on 16-byte aligned addresses; every
+// load of a thread is issued before the first conversion so the misses overlap (MAXV = vectors per thread
+// upper bound).  put4 is called with i = run_head(g) (mod 4) only, so a destination shifted by
+// (4 - run_head % 4) % 4 floats takes aligned 128-bit shared-memory stores (scalar stores from a thread
+// that owns 8 consecutive samples are an 8-way bank conflict).
+template <int MAXV, typename PCM, typename Put, typename Put4>
+__device__ __forceinline__ void load_run(const PCM* __restrict__ pcm, int64_t g, int n, Put put, Put4 put4) {
     constexpr int VEC = 16 / (int)sizeof(PCM);
     const int tid = threadIdx.x, nt = blockDim.x;
-    int head = (int)((VEC - (g % VEC)) % VEC);
+    int head = run_head<PCM>(g);
     if (head > n) head = n;
     const int nvec = (n - head) / VEC;
     const int tail0 = head + nvec * VEC;
@@ -127,13 +137,14 @@ __device__ __forceinline__ void load_run(const PCM* __restrict__ pcm, int64_t g,
         if (v < nvec) {
             const int i = head + v * VEC;
             if constexpr (sizeof(PCM) == 2) {
-                const int16_t* h = reinterpret_cast<const int16_t*>(&raw[r]);
-#pragma unroll
-                for (int e = 0; e < 8; e++) put(i + e, pcm_to_f32(h[e]));
+                const int4 q = raw[r];
+                put4(i, make_float4(pcm_to_f32((int16_t)(q.x & 0xffff)), pcm_to_f32((int16_t)(q.x >> 16)),
+                                    pcm_to_f32((int16_t)(q.y & 0xffff)), pcm_to_f32((int16_t)(q.y >> 16))));
+                put4(i + 4, make_float4(pcm_to_f32((int16_t)(q.z & 0xffff)), pcm_to_f32((int16_t)(q.z >> 16)),
+                                        pcm_to_f32((int16_t)(q.w & 0xffff)), pcm_to_f32((int16_t)(q.w >> 16))));
             } else {
-                const float* f = reinterpret_cast<const float*>(&raw[r]);
-#pragma unroll
-                for (int e = 0; e < 4; e++) put(i + e, f[e]);
+                const int4 q = raw[r];
+                put4(i, make_float4(__int_as_float(q.x), __int_as_float(q.y), __int_as_float(q.z), __int_as_float(q.w)));
             }
         }
     }
@@ -146,9 +157,10 @@ __device__ __forceinline__ void load_run(const PCM* __restrict__ pcm, int64_t g,
 
 // Stages samples [s0, s0+n) of a clip (clip-relative indices, zero outside [0, N)) into shared memory
 // as float32.  The body uses 128-bit global loads on 16-byte aligned addresses.
-template <typename PCM>
+struct IdentityPos { __device__ __forceinline__ int operator()(int i) const { return i; } };
+template <typename PCM, typename Pos = IdentityPos>
 __device__ __forceinline__ void stage_clip_f32(const PCM* __restrict__ pcm, int64_t clip_base, int64_t N,
-                                               int64_t s0, int n, float* __restrict__ dst) {
+                                               int64_t s0, int n, float* __restrict__ dst, Pos pos = Pos()) {
     constexpr int VEC = 16 / (int)sizeof(PCM);
     const int tid = threadIdx.x, nt = blockDim.x;
     // global element index of dst[0]
@@ -158,7 +170,7 @@ __device__ __forceinline__ void stage_clip_f32(const PCM* __restrict__ pcm, int6
     if (head > n) head = n;
     for (int i = tid; i < head; i += nt) {
         int64_t s = s0 + i;
-        dst[i] = (s >= 0 && s < N) ? load_sample(pcm, clip_base + s) : 0.0f;
+        dst[pos(i)] = (s >= 0 && s < N) ? load_sample(pcm, clip_base + s) : 0.0f;
     }
     const int nvec = (n - head) / VEC;
     for (int v = tid; v < nvec; v += nt) {
@@ -169,23 +181,23 @@ __device__ __forceinline__ void stage_clip_f32(const PCM* __restrict__ pcm, int6
             if constexpr (sizeof(PCM) == 2) {
                 const int16_t* h = reinterpret_cast<const int16_t*>(&raw);
 #pragma unroll
-                for (int e = 0; e < 8; e++) dst[i + e] = pcm_to_f32(h[e]);
+                for (int e = 0; e < 8; e++) dst[pos(i + e)] = pcm_to_f32(h[e]);
             } else {
                 const float* f = reinterpret_cast<const float*>(&raw);
 #pragma unroll
-                for (int e = 0; e < 4; e++) dst[i + e] = f[e];
+                for (int e = 0; e < 4; e++) dst[pos(i + e)] = f[e];
             }
         } else {
 #pragma unroll
             for (int e = 0; e < VEC; e++) {
                 int64_t se = s + e;
-                dst[i + e] = (se >= 0 && se < N) ? load_sample(pcm, clip_base + se) : 0.0f;
+                dst[pos(i + e)] = (se >= 0 && se < N) ? load_sample(pcm, clip_base + se) : 0.0f;
             }
         }
     }
     for (int i = head + nvec * VEC + tid; i < n; i += nt) {
         int64_t s = s0 + i;
-        dst[i] = (s >= 0 && s < N) ? load_sample(pcm, clip_base + s) : 0.0f;
+        dst[pos(i)] = (s >= 0 && s < N) ? load_sample(pcm, clip_base + s) : 0.0f;
     }
 }
 
@@ -195,6 +207,10 @@ __device__ __forceinline__ void stage_clip_f32(const PCM* __restrict__ pcm, int6
 constexpr int STFT_TF = 32;          // frames per tile
 constexpr int STFT_NT = STFT_TF * 8; // 8 lanes per frame
 constexpr int STFT_PS = 132;         // row stride of the power tile (F = 129)
+constexpr int STFT_XS = (STFT_TF + 1) * 136 + 8;   // staged samples: 8 floats of padding per 128, + alignment shift
+// exchange area of one frame in complex elements: 32 bytes more than the FFT needs, so the four frames of a
+// warp start 32 bytes apart modulo 128 and their complex64 output stores do not fall on the same banks
+template <typename T> struct ExFrame { static constexpr int value = kExSize + 32 / (int)sizeof(cx<T>); };
 
 template <typename T>
 struct FftTables {
@@ -215,8 +231,8 @@ struct StftOut {
 
 template <typename T>
 constexpr size_t stft_smem_bytes() {
-    return sizeof(float) * ((STFT_TF + 1) * 128) + sizeof(cx<T>) * (size_t)STFT_TF * kExSize + sizeof(T) * 256 +
-           sizeof(cx<T>) * (128 + 129) + sizeof(float) * STFT_TF * STFT_PS + 64;
+    return sizeof(float) * STFT_XS + sizeof(cx<T>) * (size_t)STFT_TF * ExFrame<T>::value + sizeof(T) * 256 +
+           sizeof(cx<T>) * (128 + 130) + 64;
 }
 
 __device__ void raw_features_frame(const DevParams& p, const float* __restrict__ Pt, const float* __restrict__ freqs,
@@ -229,11 +245,13 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
                                                           StftOut o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* s_ex = reinterpret_cast<cx<T>*>(smem_raw);
-    cx<T>* s_tw128 = s_ex + (size_t)STFT_TF * kExSize;
+    constexpr int EXF = ExFrame<T>::value;
+    cx<T>* s_tw128 = s_ex + (size_t)STFT_TF * EXF;   // pass-A twiddles, [k1][lane]: W128^(lane * k1)
     cx<T>* s_tw256 = s_tw128 + 128;
-    T* s_win = reinterpret_cast<T*>(s_tw256 + 129);
+    T* s_win = reinterpret_cast<T*>(s_tw256 + 130);   // 130: keeps what follows 16-byte aligned for T = float
     float* s_x = reinterpret_cast<float*>(s_win + 256);
-    float* s_P = s_x + (STFT_TF + 1) * 128;
+    float* s_P = s_x;   // the power tile reuses the staged samples, dead after pass A (STFT_TF * STFT_PS <= STFT_XS)
+    static_assert(STFT_TF * STFT_PS <= STFT_XS, "power tile must fit the sample area");
 
     const int tid = threadIdx.x;
     int64_t tile_in_clip;
@@ -248,27 +266,40 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
 
     APT_STAMP2(20);
     for (int i = tid; i < 256; i += STFT_NT) s_win[i] = tab.win[i];
-    for (int i = tid; i < 128; i += STFT_NT) s_tw128[i] = tab.tw128[i];
+    for (int i = tid; i < 128; i += STFT_NT) s_tw128[i] = tab.tw128[((i & 7) * (i >> 3)) & 127];
     for (int i = tid; i < 129; i += STFT_NT) s_tw256[i] = tab.tw256[i];
+    // Sample u of the tile (u = 0 is 128 samples before the first frame) lives at u + sh + padk * (u / 128):
+    // at hop 128 the four frames of a warp then read different banks (padk = 8); sh aligns the 128-bit
+    // staging stores.
+    const int padk = p.hop == 128 ? 8 : 0;
+    int sh = 0;
     {
         // frames t0 .. t0+TF-1 of hop p.hop (<= 128) cover samples [t0*hop - 128, (t0+TF-1)*hop + 128)
         const int64_t s0 = (int64_t)t0 * p.hop - 128;
         constexpr int NS_MAX = (STFT_TF + 1) * 128;
         const int NS_ = (STFT_TF - 1) * p.hop + 256;
-        if (s0 >= 0 && s0 + NS_ <= N)
-            load_run<(NS_MAX * (int)sizeof(PCM) / 16 + STFT_NT - 1) / STFT_NT + 1>(pcm, base + s0, NS_, [&](int i, float v) { s_x[i] = v; });
-        else
-            stage_clip_f32(pcm, base, N, s0, NS_, s_x);
+        if (s0 >= 0 && s0 + NS_ <= N) {
+            sh = (4 - (run_head<PCM>(base + s0) & 3)) & 3;
+            auto xpos = [&](int u) { return u + sh + padk * (u >> 7); };
+            load_run<(NS_MAX * (int)sizeof(PCM) / 16 + STFT_NT - 1) / STFT_NT + 1>(
+                pcm, base + s0, NS_, [&](int i, float v) { s_x[xpos(i)] = v; },
+                [&](int i, float4 v) {
+                    if ((i & 127) > 124) { s_x[xpos(i)] = v.x; s_x[xpos(i + 1)] = v.y; s_x[xpos(i + 2)] = v.z; s_x[xpos(i + 3)] = v.w; }
+                    else *reinterpret_cast<float4*>(s_x + xpos(i)) = v;
+                });
+        } else {
+            stage_clip_f32(pcm, base, N, s0, NS_, s_x, [&](int u) { return u + padk * (u >> 7); });
+        }
     }
     __syncthreads();
     APT_STAMP2(21);
 
     const int fr = tid >> 3, lane = tid & 7;
-    const float* xs = s_x + fr * p.hop;
-    cx<T>* ex = s_ex + (size_t)fr * kExSize;
+    const float* xs = s_x + sh + fr * (p.hop + padk);   // sample n of the frame: xs[n + (n >= 128 ? padk : 0)]
+    cx<T>* ex = s_ex + (size_t)fr * EXF;
     // all STFT_TF frame slots run both passes (slots past the clip end transform zero padding and are never
     // written out): the warp barrier inside pass B needs every lane
-    rfft256_passA<T>(lane, [&](int n) { return xs[n]; }, s_win, s_tw128, ex);
+    rfft256_passA<T>(lane, [&](int n) { return xs[n + (n >= 128 ? padk : 0)]; }, s_win, s_tw128, ex);
     __syncthreads();
     APT_STAMP2(22);
     // pass B: every lane emits its bins as complex64 into the frame's own (now consumed) exchange area
@@ -294,7 +325,7 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
 #pragma unroll
         for (int tt = 0; tt < STFT_TF / 8; tt++) {
             const int t = w + 8 * tt;
-            const float2* sS = reinterpret_cast<const float2*>(s_ex + (size_t)t * kExSize);
+            const float2* sS = reinterpret_cast<const float2*>(s_ex + (size_t)t * EXF);
 #pragma unroll
             for (int kk = 0; kk < 5; kk++) {
                 const int ki = ln + 32 * kk;
@@ -313,7 +344,7 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
             float2* dstS = reinterpret_cast<float2*>(o.S) + fbase * p.F;
             for (int i = tid; i < nfr * p.F; i += STFT_NT) {
                 const int t = i / p.F, k = i - t * p.F;
-                dstS[i] = reinterpret_cast<const float2*>(s_ex + (size_t)t * kExSize)[k];
+                dstS[i] = reinterpret_cast<const float2*>(s_ex + (size_t)t * EXF)[k];
             }
         }
     }
@@ -801,15 +832,18 @@ __global__ void __launch_bounds__(TD_NT, 3) td_features_kernel(const __grid_cons
     for (int i = tid; i < TD_CHUNK * DIM; i += TD_NT) s_H[i] = __ldg(tb.H + i);
     // stage the in-clip part of the buffer as float32 (coalesced 128-bit loads); zeros behind it
     const bool interior = bs >= 0 && be <= N;
+    int sh = 0;   // shift of the staged samples that makes the 128-bit staging stores aligned
     if (interior) {
-        load_run<4>(pcm, base + bs, len, [&](int i, float v) { s_x[i] = v; });
+        sh = (4 - (run_head<PCM>(base + bs) & 3)) & 3;
+        load_run<4>(pcm, base + bs, len, [&](int i, float v) { s_x[i + sh] = v; },
+                    [&](int i, float4 v) { *reinterpret_cast<float4*>(s_x + i + sh) = v; });
     } else {
         for (int i = tid; i < len; i += TD_NT) {
             const int64_t s = bs + i;
             if (s >= 0 && s < N) s_x[i] = load_sample(pcm, base + s);
         }
     }
-    for (int i = len + tid; i < TD_LB; i += TD_NT) s_x[i] = 0.0f;
+    for (int i = len + tid; i < TD_LB; i += TD_NT) s_x[i + sh] = 0.0f;
     __syncthreads();
     APT_STAMP(1);
     // my chunk -> registers (float64).  Every tile but the last of a clip runs all TD_NT chunks full
@@ -822,7 +856,7 @@ __global__ void __launch_bounds__(TD_NT, 3) td_features_kernel(const __grid_cons
     double y[TD_CHUNK];
     if (interior) {
 #pragma unroll
-        for (int j = 0; j < TD_CHUNK; j++) y[j] = (double)s_x[a0 + j];
+        for (int j = 0; j < TD_CHUNK; j++) y[j] = (double)s_x[sh + a0 + j];
     } else {
 #pragma unroll
         for (int j = 0; j < TD_CHUNK; j++) {

@@ -7,12 +7,13 @@ using namespace apt;
 template <typename T>
 static void rfft256(const float* x, const double* win, double* out) {
     std::vector<T> w(256);
-    std::vector<cx<T>> tw128(128), tw256(129), ex(kExSize);
+    std::vector<cx<T>> tw128(128), twA(128), tw256(129), ex(kExSize);
     for (int i = 0; i < 256; i++) w[i] = (T)win[i];
     for (int m = 0; m < 128; m++) tw128[m] = {(T)cos(2.0 * M_PI * m / 128.0), (T)-sin(2.0 * M_PI * m / 128.0)};
+    for (int i = 0; i < 128; i++) twA[i] = tw128[((i & 7) * (i >> 3)) & 127];   // [k1][lane] layout of the kernel
     for (int k = 0; k <= 128; k++) tw256[k] = {(T)cos(2.0 * M_PI * k / 256.0), (T)-sin(2.0 * M_PI * k / 256.0)};
     auto ldx = [&](int n) { return x[n]; };
-    for (int j = 0; j < 8; j++) rfft256_passA<T>(j, ldx, w.data(), tw128.data(), ex.data());
+    for (int j = 0; j < 8; j++) rfft256_passA<T>(j, ldx, w.data(), twA.data(), ex.data());
     for (int t = 0; t < 8; t++)
         rfft256_passB<T>(t, ex.data(), tw256.data(), [&](int k, T re, T im) { out[2 * k] = (double)re; out[2 * k + 1] = (double)im; });
 }
