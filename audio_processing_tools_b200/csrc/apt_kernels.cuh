@@ -102,50 +102,56 @@ __device__ __forceinline__ bool tile_clip(const Batch& b, const int64_t* __restr
 __device__ __forceinline__ float load_sample(const int16_t* p, int64_t i) { return pcm_to_f32(__ldg(p + i)); }
 __device__ __forceinline__ float load_sample(const float* p, int64_t i) { return __ldg(p + i); }
 
-// First i >= 0 such that element g + i of the PCM buffer sits on a 16-byte boundary.
+// Vector width of the staging loads in samples: 4 either way (8-byte loads of int16, 16-byte loads of float32),
+// so that one load feeds exactly one 128-bit shared-memory store and the stores of a warp are contiguous.
+// First i >= 0 such that element g + i of the PCM buffer sits on that vector's boundary:
 template <typename PCM>
-__device__ __forceinline__ int run_head(int64_t g) {
-    constexpr int VEC = 16 / (int)sizeof(PCM);
-    return (int)((VEC - (g % VEC + VEC) % VEC) % VEC);
-}
+__device__ __forceinline__ int run_head(int64_t g) { return (int)((4 - (g % 4 + 4) % 4) % 4); }
 
 // Loads the n samples that start at absolute element index g (all inside the PCM buffer) and hands
-// them to put(i, value) / put4(i, four values i..i+3).  128-bit loads on 16-byte aligned addresses; every
-// load of a thread is issued before the first conversion so the misses overlap (MAXV = vectors per thread
-// upper bound).  put4 is called with i = run_head(g) (mod 4) only, so a destination shifted by
-// (4 - run_head % 4) % 4 floats takes aligned 128-bit shared-memory stores (scalar stores from a thread
-// that owns 8 consecutive samples are an 8-way bank conflict).
+// them to put(i, value) / put4(i, four values i..i+3).  Aligned vector loads; every load of a thread is
+// issued before the first conversion so the misses overlap (MAXV = vectors per thread upper bound).
+// put4 is called with i = run_head(g) (mod 4) only, so a destination shifted by (4 - run_head % 4) % 4
+// floats takes aligned 128-bit shared-memory stores.
 template <int MAXV, typename PCM, typename Put, typename Put4>
 __device__ __forceinline__ void load_run(const PCM* __restrict__ pcm, int64_t g, int n, Put put, Put4 put4) {
-    constexpr int VEC = 16 / (int)sizeof(PCM);
+    constexpr int VEC = 4;
     const int tid = threadIdx.x, nt = blockDim.x;
     int head = run_head<PCM>(g);
     if (head > n) head = n;
     const int nvec = (n - head) / VEC;
     const int tail0 = head + nvec * VEC;
-    int4 raw[MAXV];
+    if constexpr (sizeof(PCM) == 2) {
+        int2 raw[MAXV];
 #pragma unroll
-    for (int r = 0; r < MAXV; r++) {
-        const int v = tid + r * nt;
-        if (v < nvec) raw[r] = __ldg(reinterpret_cast<const int4*>(pcm + g + head + (int64_t)v * VEC));
-    }
-    if (tid < head) put(tid, load_sample(pcm, g + tid));
-    if (tail0 + tid < n) put(tail0 + tid, load_sample(pcm, g + tail0 + tid));
+        for (int r = 0; r < MAXV; r++) {
+            const int v = tid + r * nt;
+            if (v < nvec) raw[r] = __ldg(reinterpret_cast<const int2*>(pcm + g + head + (int64_t)v * VEC));
+        }
+        if (tid < head) put(tid, load_sample(pcm, g + tid));
+        if (tail0 + tid < n) put(tail0 + tid, load_sample(pcm, g + tail0 + tid));
 #pragma unroll
-    for (int r = 0; r < MAXV; r++) {
-        const int v = tid + r * nt;
-        if (v < nvec) {
-            const int i = head + v * VEC;
-            if constexpr (sizeof(PCM) == 2) {
-                const int4 q = raw[r];
-                put4(i, make_float4(pcm_to_f32((int16_t)(q.x & 0xffff)), pcm_to_f32((int16_t)(q.x >> 16)),
-                                    pcm_to_f32((int16_t)(q.y & 0xffff)), pcm_to_f32((int16_t)(q.y >> 16))));
-                put4(i + 4, make_float4(pcm_to_f32((int16_t)(q.z & 0xffff)), pcm_to_f32((int16_t)(q.z >> 16)),
-                                        pcm_to_f32((int16_t)(q.w & 0xffff)), pcm_to_f32((int16_t)(q.w >> 16))));
-            } else {
-                const int4 q = raw[r];
-                put4(i, make_float4(__int_as_float(q.x), __int_as_float(q.y), __int_as_float(q.z), __int_as_float(q.w)));
+        for (int r = 0; r < MAXV; r++) {
+            const int v = tid + r * nt;
+            if (v < nvec) {
+                const int2 q = raw[r];
+                put4(head + v * VEC, make_float4(pcm_to_f32((int16_t)(q.x & 0xffff)), pcm_to_f32((int16_t)(q.x >> 16)),
+                                                 pcm_to_f32((int16_t)(q.y & 0xffff)), pcm_to_f32((int16_t)(q.y >> 16))));
             }
+        }
+    } else {
+        float4 raw[MAXV];
+#pragma unroll
+        for (int r = 0; r < MAXV; r++) {
+            const int v = tid + r * nt;
+            if (v < nvec) raw[r] = __ldg(reinterpret_cast<const float4*>(pcm + g + head + (int64_t)v * VEC));
+        }
+        if (tid < head) put(tid, load_sample(pcm, g + tid));
+        if (tail0 + tid < n) put(tail0 + tid, load_sample(pcm, g + tail0 + tid));
+#pragma unroll
+        for (int r = 0; r < MAXV; r++) {
+            const int v = tid + r * nt;
+            if (v < nvec) put4(head + v * VEC, raw[r]);
         }
     }
     // vectors beyond MAXV per thread (never for the tile sizes in this file)
@@ -208,9 +214,9 @@ constexpr int STFT_TF = 32;          // frames per tile
 constexpr int STFT_NT = STFT_TF * 8; // 8 lanes per frame
 constexpr int STFT_PS = 132;         // row stride of the power tile (F = 129)
 constexpr int STFT_XS = (STFT_TF + 1) * 136 + 8;   // staged samples: 8 floats of padding per 128, + alignment shift
-// exchange area of one frame in complex elements: 32 bytes more than the FFT needs, so the four frames of a
-// warp start 32 bytes apart modulo 128 and their complex64 output stores do not fall on the same banks
-template <typename T> struct ExFrame { static constexpr int value = kExSize + 32 / (int)sizeof(cx<T>); };
+// exchange area of one frame in complex elements: 64 bytes more than the FFT needs, so the two frames of a
+// half-warp start 64 bytes apart modulo 128 and their 64-byte runs of complex64 output fill one wavefront
+template <typename T> struct ExFrame { static constexpr int value = kExSize + 64 / (int)sizeof(cx<T>); };
 
 template <typename T>
 struct FftTables {
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
         if (s0 >= 0 && s0 + NS_ <= N) {
             sh = (4 - (run_head<PCM>(base + s0) & 3)) & 3;
             auto xpos = [&](int u) { return u + sh + padk * (u >> 7); };
-            load_run<(NS_MAX * (int)sizeof(PCM) / 16 + STFT_NT - 1) / STFT_NT + 1>(
+            load_run<(NS_MAX / 4 + STFT_NT - 1) / STFT_NT + 1>(
                 pcm, base + s0, NS_, [&](int i, float v) { s_x[xpos(i)] = v; },
                 [&](int i, float4 v) {
                     if ((i & 127) > 124) { s_x[xpos(i)] = v.x; s_x[xpos(i + 1)] = v.y; s_x[xpos(i + 2)] = v.z; s_x[xpos(i + 3)] = v.w; }
@@ -835,7 +841,7 @@ __global__ void __launch_bounds__(TD_NT, 3) td_features_kernel(const __grid_cons
     int sh = 0;   // shift of the staged samples that makes the 128-bit staging stores aligned
     if (interior) {
         sh = (4 - (run_head<PCM>(base + bs) & 3)) & 3;
-        load_run<4>(pcm, base + bs, len, [&](int i, float v) { s_x[i + sh] = v; },
+        load_run<(TD_LB / 4 + TD_NT - 1) / TD_NT + 1>(pcm, base + bs, len, [&](int i, float v) { s_x[i + sh] = v; },
                     [&](int i, float4 v) { *reinterpret_cast<float4*>(s_x + i + sh) = v; });
     } else {
         for (int i = tid; i < len; i += TD_NT) {
