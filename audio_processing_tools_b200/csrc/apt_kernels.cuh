@@ -214,9 +214,13 @@ constexpr int STFT_TF = 32;          // frames per tile
 constexpr int STFT_NT = STFT_TF * 8; // 8 lanes per frame
 constexpr int STFT_PS = 132;         // row stride of the power tile (F = 129)
 constexpr int STFT_XS = (STFT_TF + 1) * 136 + 8;   // staged samples: 8 floats of padding per 128, + alignment shift
-// exchange area of one frame in complex elements: 64 bytes more than the FFT needs, so the two frames of a
-// half-warp start 64 bytes apart modulo 128 and their 64-byte runs of complex64 output fill one wavefront
-template <typename T> struct ExFrame { static constexpr int value = kExSize + 64 / (int)sizeof(cx<T>); };
+// Shared-memory area of one frame, in complex elements of the working precision.  It is used three times:
+// (1) all areas together first hold the staged samples of the tile (dead once pass A has them in registers),
+// (2) the frame's 128-element exchange buffer between the FFT passes, (3) the frame's complex64 spectrum
+// (129 x 8 bytes from byte (t & 1) * 64: the two frames of a half-warp store their 64-byte runs into one
+// wavefront) and, from byte STFT_POFF, its float32 power row.  Strides are multiples of 128 bytes.
+template <typename T> struct ExFrame { static constexpr int value = sizeof(T) == 8 ? 128 : 224; };
+constexpr int STFT_POFF = 1152;      // byte offset of the power row inside a frame area (after 64 + 129 * 8)
 
 template <typename T>
 struct FftTables {
@@ -237,15 +241,16 @@ struct StftOut {
 
 template <typename T>
 constexpr size_t stft_smem_bytes() {
-    return sizeof(float) * STFT_XS + sizeof(cx<T>) * (size_t)STFT_TF * ExFrame<T>::value + sizeof(T) * 256 +
-           sizeof(cx<T>) * (128 + 130) + 64;
+    static_assert(sizeof(float) * STFT_XS <= sizeof(cx<T>) * (size_t)STFT_TF * ExFrame<T>::value, "samples must fit the frame areas");
+    static_assert(STFT_POFF + sizeof(float) * STFT_PS <= sizeof(cx<T>) * ExFrame<T>::value, "power row must fit the frame area");
+    return sizeof(cx<T>) * (size_t)STFT_TF * ExFrame<T>::value + sizeof(T) * 256 + sizeof(cx<T>) * (128 + 130) + 64;
 }
 
 __device__ void raw_features_frame(const DevParams& p, const float* __restrict__ Pt, const float* __restrict__ freqs,
                                    float* __restrict__ out, int64_t stride);
 
 template <typename T, typename PCM>
-__global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant__ DevParams p, Batch b,
+__global__ void __launch_bounds__(STFT_NT, 3) stft256_kernel(const __grid_constant__ DevParams p, Batch b,
                                                           const PCM* __restrict__ pcm,
                                                           const int64_t* __restrict__ tile_off, FftTables<T> tab,
                                                           StftOut o) {
@@ -254,10 +259,10 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
     constexpr int EXF = ExFrame<T>::value;
     cx<T>* s_tw128 = s_ex + (size_t)STFT_TF * EXF;   // pass-A twiddles, [k1][lane]: W128^(lane * k1)
     cx<T>* s_tw256 = s_tw128 + 128;
-    T* s_win = reinterpret_cast<T*>(s_tw256 + 130);   // 130: keeps what follows 16-byte aligned for T = float
-    float* s_x = reinterpret_cast<float*>(s_win + 256);
-    float* s_P = s_x;   // the power tile reuses the staged samples, dead after pass A (STFT_TF * STFT_PS <= STFT_XS)
-    static_assert(STFT_TF * STFT_PS <= STFT_XS, "power tile must fit the sample area");
+    T* s_win = reinterpret_cast<T*>(s_tw256 + 130);
+    float* s_x = reinterpret_cast<float*>(smem_raw);   // staged samples overlay the frame areas until pass A holds them
+    auto S_row = [&](int t) { return reinterpret_cast<float2*>(s_ex + (size_t)t * EXF) + (t & 1) * 8; };
+    auto P_row = [&](int t) { return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_ex + (size_t)t * EXF) + STFT_POFF); };
 
     const int tid = threadIdx.x;
     int64_t tile_in_clip;
@@ -305,12 +310,12 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
     cx<T>* ex = s_ex + (size_t)fr * EXF;
     // all STFT_TF frame slots run both passes (slots past the clip end transform zero padding and are never
     // written out): the warp barrier inside pass B needs every lane
-    rfft256_passA<T>(lane, [&](int n) { return xs[n + (n >= 128 ? padk : 0)]; }, s_win, s_tw128, ex);
+    rfft256_passA<T>(lane, [&](int n) { return xs[n + (n >= 128 ? padk : 0)]; }, s_win, s_tw128, ex, [&]() { __syncthreads(); });
     __syncthreads();
     APT_STAMP2(22);
     // pass B: every lane emits its bins as complex64 into the frame's own (now consumed) exchange area
     {
-        float2* sS = reinterpret_cast<float2*>(ex);
+        float2* sS = S_row(fr);
         rfft256_passB<T>(lane, ex, s_tw256,
                          [&](int k, T re, T im) { sS[k] = make_float2(d2f((double)re), d2f((double)im)); },
                          [&]() { __syncwarp(); });
@@ -331,7 +336,8 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
 #pragma unroll
         for (int tt = 0; tt < STFT_TF / 8; tt++) {
             const int t = w + 8 * tt;
-            const float2* sS = reinterpret_cast<const float2*>(s_ex + (size_t)t * EXF);
+            const float2* sS = S_row(t);
+            float* sP = P_row(t);
 #pragma unroll
             for (int kk = 0; kk < 5; kk++) {
                 const int ki = ln + 32 * kk;
@@ -340,7 +346,7 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
                     const float2 z = sS[k];
                     const float a = np_cabsf_fast(z.x, z.y);
                     const float pw = a * a;
-                    if (need_full) s_P[t * STFT_PS + k] = pw;
+                    if (need_full) sP[k] = pw;
                     const int kb = k - p.band_lo;
                     if (dstb && kb >= 0 && kb < p.K) dstb[t * p.K + kb] = pw;
                 }
@@ -350,7 +356,7 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
             float2* dstS = reinterpret_cast<float2*>(o.S) + fbase * p.F;
             for (int i = tid; i < nfr * p.F; i += STFT_NT) {
                 const int t = i / p.F, k = i - t * p.F;
-                dstS[i] = reinterpret_cast<const float2*>(s_ex + (size_t)t * EXF)[k];
+                dstS[i] = S_row(t)[k];
             }
         }
     }
@@ -359,13 +365,13 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
         float* dst = o.P + fbase * p.F;
         for (int i = tid; i < nfr * p.F; i += STFT_NT) {
             int t = i / p.F, k = i - t * p.F;
-            dst[i] = s_P[t * STFT_PS + k];
+            dst[i] = P_row(t)[k];
         }
     }
     if (o.band_energy) {
         for (int i = tid; i < nfr * (p.M + 1); i += STFT_NT) {
             int m = i / nfr, t = i - m * nfr;
-            const float* Pt = s_P + t * STFT_PS;
+            const float* Pt = P_row(t);
             double s = 0.0;
             if (m < p.M) {
                 for (int k = p.mode_lo[m]; k <= p.mode_hi[m]; k++) s += (double)Pt[k];
@@ -377,7 +383,7 @@ __global__ void __launch_bounds__(STFT_NT) stft256_kernel(const __grid_constant_
         }
     }
     if (o.raw) {
-        if (tid < nfr) raw_features_frame(p, s_P + tid * STFT_PS, o.freqs, o.raw + fbase + tid, o.nF);
+        if (tid < nfr) raw_features_frame(p, P_row(tid), o.freqs, o.raw + fbase + tid, o.nF);
     }
     APT_STAMP2(24);
 }
