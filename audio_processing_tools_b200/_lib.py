@@ -97,6 +97,22 @@ class AptBneParams(C.Structure):
     ]
 
 
+ROE_FRAME_F, ROE_PART_F, ROE_CLIP_F = 8, 5, 5
+
+
+class AptRoeParams(C.Structure):
+    _fields_ = [
+        ("n_fft", C.c_int32), ("hop", C.c_int32), ("M", C.c_int32), ("wl", C.c_int32), ("max_peaks", C.c_int32), ("want_td", C.c_int32),
+        ("ns_in", C.c_int32), ("ns_td", C.c_int32),
+        ("sos_in", (C.c_double * 6) * 8), ("sos_td", (C.c_double * 6) * 4), ("window", C.c_double * 256), ("fs", C.c_double),
+        ("f_natural", C.c_double), ("op_lo", C.c_double), ("op_hi", C.c_double), ("nat_lo", C.c_double), ("nat_hi", C.c_double),
+        ("search0_lo", C.c_double), ("search0_hi", C.c_double), ("rain_thr", C.c_double * 6), ("rain_thr_hn", C.c_double),
+        ("kurtosis_thr", C.c_double), ("crest_thr", C.c_double), ("diff_energy_thr", C.c_double),
+        ("handle_fp", C.c_int32), ("handle_fn", C.c_int32), ("rain_drop_threshold", C.c_int32), ("rain_drop_max_thr", C.c_int32),
+        ("rain_peaks_min_thr", C.c_int32), ("rain_peaks_max_thr", C.c_int32),
+    ]
+
+
 class AptOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in OUT_FIELDS]
 
@@ -107,7 +123,8 @@ EXPORTS = ("apt_init", "apt_destroy", "apt_last_error", "apt_abi_version", "apt_
            "apt_plan_offsets", "apt_plan_total_frames", "apt_plan_total_samples",
            "apt_plan_scratch_bytes", "apt_run_i16", "apt_run_f32", "apt_plan_last_launches",
            "apt_run_host_i16", "apt_plan_enable_timing", "apt_plan_kernel_ms", "apt_selftest",
-           "apt_dsd_run_i16", "apt_sizeof_bne_params", "apt_bne_run")
+           "apt_dsd_run_i16", "apt_sizeof_bne_params", "apt_bne_run",
+           "apt_sizeof_roe_params", "apt_roe_run")
 
 
 def build(force=False, verbose=False):
@@ -155,6 +172,11 @@ def load():
     L.apt_run_host_i16.argtypes = [vp] * 8
     L.apt_selftest.argtypes = [vp, C.c_int, C.c_int64, i64p]
     L.apt_bne_run.argtypes = [vp, C.POINTER(AptBneParams), C.c_int, i64p, vp, C.c_int, vp, vp, vp, vp, vp]
+    i32p = C.POINTER(C.c_int32)
+    L.apt_roe_run.argtypes = [vp, C.POINTER(AptRoeParams), C.c_int, vp, C.c_int, C.c_int, i32p, i64p, i32p, C.c_int, vp, vp, vp,
+                              C.POINTER(C.c_int), vp]
+    if L.apt_sizeof_roe_params() != C.sizeof(AptRoeParams):
+        raise RuntimeError("libapt_b200.so apt_roe_params_t layout differs from the Python binding")
     if L.apt_sizeof_bne_params() != C.sizeof(AptBneParams):
         raise RuntimeError("libapt_b200.so apt_bne_params_t layout differs from the Python binding")
     L.apt_dsd_run_i16.argtypes = [vp, C.POINTER(AptDsdParams), C.c_int, i64p, C.POINTER(C.c_double), vp, vp, vp, C.c_int, vp]

@@ -12,6 +12,7 @@
 #include "apt_kernels.cuh"
 #include "apt_dsd.cuh"
 #include "apt_bne.cuh"
+#include "apt_roe.cuh"
 
 using namespace apt;
 
@@ -901,5 +902,67 @@ extern "C" int apt_bne_run(apt_ctx* ctx, const apt_bne_params_t* p, int n_clips,
     bne_state_kernel<<<(n_clips + 63) / 64, 64, 0, st>>>(*p, n_clips, d_fo.p, d_subEh.p, dev_subE, d_fftq.p, dev_frame_out, dev_mask, dev_stats);
     CUDA_OK(ctx, cudaGetLastError());
     CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int apt_sizeof_roe_params(void) { return (int)sizeof(apt_roe_params_t); }
+
+extern "C" int apt_roe_run(apt_ctx* ctx, const apt_roe_params_t* p, int n_clips, const void* dev_pcm, int is_f32, int n_parts,
+                           const int32_t* part_clip, const int64_t* part_start, const int32_t* part_len, int max_harmonics_in,
+                           double* dev_frame_out, double* dev_part_out, double* dev_clip_out, int* max_harmonics_out, void* stream) {
+    if (!ctx) return -1;
+    if (!p || !dev_pcm || !dev_frame_out || !dev_part_out || !dev_clip_out || !max_harmonics_out || n_clips <= 0 || n_parts < 0 ||
+        (n_parts > 0 && (!part_clip || !part_start || !part_len)))
+        return fail(ctx, -1, "apt_roe_run: bad arguments");
+    if (p->n_fft != 256 || p->hop != 128) return fail(ctx, -21, "apt_roe_run: frame %d / hop %d (the CUDA path is built for 256 / 128)", p->n_fft, p->hop);
+    if (p->ns_in < 1 || p->ns_in > 8 || p->ns_td < 0 || p->ns_td > 4 || p->ns_in + p->ns_td > 32) return fail(ctx, -24, "apt_roe_run: filter sections out of range");
+    if (p->M < 2 || p->wl < 1 || p->wl > 8 || p->max_peaks < 1) return fail(ctx, -26, "apt_roe_run: local-average window out of range (M=%d, wl=%d)", p->M, p->wl);
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int64_t> fo(n_parts + 1, 0), yo(n_parts + 1, 0);
+    std::vector<int> cp0(n_clips + 1, 0);
+    int max_T = 1;
+    for (int q = 0; q < n_parts; q++) {
+        if (part_len[q] < 256 || part_len[q] > 254 * 128) return fail(ctx, -22, "apt_roe_run: part %d has %d samples (256..%d)", q, part_len[q], 254 * 128);
+        if (part_clip[q] < 0 || part_clip[q] >= n_clips || (q && part_clip[q] < part_clip[q - 1])) return fail(ctx, -22, "apt_roe_run: parts must be listed clip by clip");
+        const int T = 1 + part_len[q] / 128;
+        fo[q + 1] = fo[q] + T + 1; yo[q + 1] = yo[q] + part_len[q];
+        cp0[part_clip[q] + 1]++;
+        max_T = std::max(max_T, T);
+    }
+    for (int c = 0; c < n_clips; c++) cp0[c + 1] += cp0[c];
+    CUDA_OK(ctx, cudaMemsetAsync(dev_clip_out, 0, sizeof(double) * (size_t)n_clips * APT_ROE_CLIP_F, st));
+    *max_harmonics_out = max_harmonics_in;
+    DevBuf<int> d_cp0; CUDA_OK(ctx, upload(d_cp0, cp0));
+    if (n_parts > 0) {
+        DevBuf<int64_t> d_fo, d_yo, d_start; DevBuf<int32_t> d_clip, d_len; DevBuf<int> d_mh;
+        DevBuf<double> d_y, d_t, d_mag, d_harm; DevBuf<cx<double>> d_twA, d_tw256;
+        CUDA_OK(ctx, upload(d_fo, fo)); CUDA_OK(ctx, upload(d_yo, yo));
+        CUDA_OK(ctx, upload(d_start, std::vector<int64_t>(part_start, part_start + n_parts)));
+        CUDA_OK(ctx, upload(d_clip, std::vector<int32_t>(part_clip, part_clip + n_parts)));
+        CUDA_OK(ctx, upload(d_len, std::vector<int32_t>(part_len, part_len + n_parts)));
+        std::vector<cx<double>> twA(128), tw256(129);
+        for (int i = 0; i < 128; i++) { const int m = ((i & 7) * (i >> 3)) & 127; twA[i] = {cos(2.0 * M_PI * m / 128.0), -sin(2.0 * M_PI * m / 128.0)}; }
+        for (int k = 0; k <= 128; k++) tw256[k] = {cos(2.0 * M_PI * k / 256.0), -sin(2.0 * M_PI * k / 256.0)};
+        CUDA_OK(ctx, upload(d_twA, twA)); CUDA_OK(ctx, upload(d_tw256, tw256));
+        CUDA_OK(ctx, d_y.alloc((size_t)yo[n_parts])); CUDA_OK(ctx, d_t.alloc((size_t)yo[n_parts] + (size_t)256 * n_parts));
+        CUDA_OK(ctx, d_mag.alloc((size_t)(fo[n_parts] - n_parts) * 129)); CUDA_OK(ctx, d_harm.alloc((size_t)fo[n_parts] * 5));
+        CUDA_OK(ctx, d_mh.alloc((size_t)n_parts + 1));
+        const RoeParts pt{n_parts, d_clip.p, d_start.p, d_len.p, d_fo.p, d_yo.p};
+        if (is_f32) roe_filter_kernel<float><<<n_parts, 32, 0, st>>>(*p, pt, (const float*)dev_pcm, d_y.p, d_t.p);
+        else roe_filter_kernel<int16_t><<<n_parts, 32, 0, st>>>(*p, pt, (const int16_t*)dev_pcm, d_y.p, d_t.p);
+        const size_t smem = sizeof(cx<double>) * (32 * kExSize + 128 + 130) + sizeof(double) * 256;
+        CUDA_OK(ctx, cudaFuncSetAttribute(roe_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roe_frame_kernel<<<dim3((unsigned)((max_T + 31) / 32), (unsigned)n_parts), ROE_NT, smem, st>>>(*p, pt, d_y.p, d_t.p, d_twA.p, d_tw256.p, d_mag.p, dev_frame_out);
+        roe_part_kernel<<<n_parts, ROE_NT, 0, st>>>(*p, pt, d_mag.p, dev_frame_out, d_harm.p, dev_part_out);
+        roe_state_kernel<<<1, 32, 0, st>>>(pt, dev_part_out, max_harmonics_in, d_mh.p, d_mh.p + n_parts);
+        roe_combine_kernel<<<n_parts, ROE_NT, 0, st>>>(*p, pt, d_mh.p, d_harm.p, dev_frame_out, dev_part_out);
+        roe_clip_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(*p, n_clips, d_cp0.p, dev_part_out, dev_clip_out);
+        CUDA_OK(ctx, cudaGetLastError());
+        CUDA_OK(ctx, cudaMemcpyAsync(max_harmonics_out, d_mh.p + n_parts, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(ctx, cudaStreamSynchronize(st));
+    } else {
+        CUDA_OK(ctx, cudaStreamSynchronize(st));
+    }
     return 0;
 }

@@ -264,6 +264,42 @@ int  apt_sizeof_bne_params(void);
 int  apt_bne_run(apt_ctx* ctx, const apt_bne_params_t* p, int n_clips, const int64_t* clip_len, const void* dev_pcm, int is_f32,
                  double* dev_frame_out, uint8_t* dev_mask, double* dev_subE, double* dev_stats, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Legacy "RoE" rain detector.  Replaces, for a batch of clips, the compute of
+ * `rain_detection_algo` (edge/dsp_rain_detection.py:2566-2575): `analyse_raw_audio` per 2-second part
+ * (:2230-2562, :2603-2636) with `calculate_pulse_characteristics` (:657-767), `compute_novelty_spectrum_new`
+ * (:1924-1955), `find_peaks_in_frequency_range` (:1649-1698), and the clip-level FP / FN combination
+ * (:2638-2731).  The host resolves `configure_parameters` (:1298-1391) into apt_roe_params_t (filter design by
+ * scipy.signal.butter stays on the host) and lists the parts; `max_harmonics` -- module state of the reference
+ * that survives between calls (:1141, :1394-1403) -- goes in and comes out explicitly.
+ * ------------------------------------------------------------------------------------------- */
+#define APT_ROE_FRAME_F 8   /* per frame slot: raining, kurtosis, crest_factor, diff_energy, energy, min_energy, Nov0, novt */
+#define APT_ROE_PART_F 5    /* per part: frain_mean, natural-range flag, max_harmonics set by the part (0: none), drops, td peaks */
+#define APT_ROE_CLIP_F 5    /* per clip: returned rain_drops, rain_drop_count, rain_peaks_count, rain_drop_count_mod, raining */
+typedef struct apt_roe_params_t {
+    int32_t n_fft, hop;                 /* 256 / 128 */
+    int32_t M, wl;                      /* local-average half window (min_average_len), values averaged = max(3, M / 6) */
+    int32_t max_peaks, want_td;         /* want_td = handle_fp || handle_fn */
+    int32_t ns_in, ns_td;               /* biquad sections of the two band-pass filters */
+    double  sos_in[8][6];               /* butter(8, op_freq_range, "bandpass") */
+    double  sos_td[4][6];               /* butter(4, [400, 900], "band") */
+    double  window[256];                /* scipy get_window("hann", 256) */
+    double  fs;                         /* 11162: analyse_raw_audio's own default, whatever sample_rate says (:2236) */
+    double  f_natural, op_lo, op_hi, nat_lo, nat_hi, search0_lo, search0_hi;
+    double  rain_thr[6], rain_thr_hn;
+    double  kurtosis_thr, crest_thr, diff_energy_thr;
+    int32_t handle_fp, handle_fn, rain_drop_threshold, rain_drop_max_thr, rain_peaks_min_thr, rain_peaks_max_thr;
+} apt_roe_params_t;
+int  apt_sizeof_roe_params(void);
+/* Parts are listed clip by clip in time order: part_clip ascending, part_start = first sample (absolute index into
+   dev_pcm), part_len >= fs samples and <= 254 * hop.  A part has T = 1 + part_len / hop frames and T + 1 frame slots
+   (the reference appends one zero per part); slots of all parts are concatenated.
+   dev_frame_out [sum(T + 1)][APT_ROE_FRAME_F] f64, dev_part_out [n_parts][APT_ROE_PART_F] f64,
+   dev_clip_out [n_clips][APT_ROE_CLIP_F] f64 (a clip without parts gets zeros).  Synchronises the stream. */
+int  apt_roe_run(apt_ctx* ctx, const apt_roe_params_t* p, int n_clips, const void* dev_pcm, int is_f32, int n_parts,
+                 const int32_t* part_clip, const int64_t* part_start, const int32_t* part_len, int max_harmonics_in,
+                 double* dev_frame_out, double* dev_part_out, double* dev_clip_out, int* max_harmonics_out, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -431,3 +431,42 @@ def test_band_noise_batch_and_int16(torch_cuda):
         for k in ("M_clean", "N_E", "G_mag", "subE"):
             assert np.array_equal(s1[k], st[k]), k
         assert np.array_equal(s1["rain_submask"], st["rain_submask"])
+
+
+def test_legacy_roe_matches_reference(torch_cuda):
+    """the legacy RoE detector on the GPU against ten runs of the unmodified reference, in the
+    reference's call order (its `max_harmonics` module state carries over): drop / peak counts and the per-frame rain
+    status bit-exact, float64 series within 1e-9 relative."""
+    import json
+    from test_roe_oracle import roe_cases, case_pcm, check_roe
+    from audio_processing_tools_b200.edge import dsp_rain_detection as roe
+    g, meta, defaults = roe_cases()
+    roe.max_harmonics = defaults["num_harmonics"]
+    for m in meta:
+        sc = json.loads(str(g[m["name"] + "__scalars"]))
+        assert roe.max_harmonics == sc["max_harmonics_in"], m["name"]
+        params = dict(defaults)
+        params.update(m["extra"])
+        drops, frain_mean, st = roe.rain_detection_algo(pcm_to_f32(case_pcm(m)), **params)
+        check_roe((drops, frain_mean, st, roe.max_harmonics), g, m["name"], rtol=1e-9)
+
+
+def test_legacy_roe_batch_and_rain_processor(torch_cuda):
+    """A ragged int16 batch equals the per-clip calls (module state included), and the function is a drop-in `fn`
+    for RainProcessor (processors.py:84-142)."""
+    from audio_processing_tools_b200.edge import dsp_rain_detection as roe
+    from audio_processing_tools_b200.processors import RainProcessor
+    clips = [synth_clip_i16(10.0, 91, 10.0), synth_clip_i16(7.5, 92, 3.0), synth_clip_i16(10.0, 93, 30.0)]
+    roe.max_harmonics = 6
+    single = [roe.rain_detection_algo(pcm_to_f32(c), **roe.default_params) for c in clips]
+    mh = roe.max_harmonics
+    roe.max_harmonics = 6
+    batch = roe.rain_detection_algo_batch(clips, **roe.default_params)
+    assert roe.max_harmonics == mh
+    for (d1, f1, s1), (d2, f2, s2) in zip(single, batch):
+        assert d1 == d2 and f1 == f2
+        for k in ("raining", "kurtosis", "crest_factor", "diff_energy", "Nov0"):
+            assert np.array_equal(s1[k], s2[k], equal_nan=True), k
+    res, st = RainProcessor(name="rain", fn=roe.rain_detection_algo).run(pcm_to_f32(clips[0]), dict(roe.default_params))
+    assert res["rain_drops"] == single[0][0] and res["rain_drop_count"] == single[0][2]["rain_drop_count"]
+    assert st["processor"] == "rain"
