@@ -566,8 +566,8 @@ __device__ void raw_features_frame(const DevParams& p, const float* __restrict__
 // a zero state, Kogge-Stone scan of the chunk-final states with the chunk transition matrix, then the
 // homogeneous response to the incoming state is added); shared memory only carries the staged PCM, the
 // scan states and the float32 result.  The float64 pipe (64 FMA/clk/SM) is the bound of this kernel.
-constexpr int TD_NT = 256;
-constexpr int TD_FT = 32;       // TD frames per tile
+constexpr int TD_NT = 384;
+constexpr int TD_FT = 56;       // TD frames per tile (fills the 384 x 23 sample buffer with 2 x 512 warm-up and the block-feature halo)
 constexpr int TD_WARM = 512;    // warm-up samples each side (pole radius 0.928 -> < 2^-53 after 490)
 constexpr int TD_CHUNK = 23;    // samples per thread (odd: conflict-free shared-memory walks)
 constexpr int TD_LB = TD_NT * TD_CHUNK;   // filter buffer capacity of a tile
@@ -802,7 +802,7 @@ __device__ double td_peak_width_half(X x, int n, int peak) {
 __device__ __forceinline__ int td_xf_pos(int u) { return u + ((u >> 7) << 3); }
 
 template <int NS, typename PCM>
-__global__ void __launch_bounds__(TD_NT, 3) td_features_kernel(const __grid_constant__ DevParams p, Batch b,
+__global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_constant__ DevParams p, Batch b,
                                                                const PCM* __restrict__ pcm,
                                                                const int64_t* __restrict__ tile_off, const __grid_constant__ TdTables tb, TdOut o) {
     constexpr int DIM = 2 * NS;
