@@ -278,7 +278,7 @@ def main():
                              "compute_frac_fp32_peak": 17000.0 * nF / (ms_step * 1e-3) / 74.4e12},
                 "note": "HBM fraction reported as the contract requires, but neither the dominant kernel nor the pipeline is "
                         "HBM-bound at n_fft=256: td_features / stft256 are bound by the FP64 pipe (62 FMA/clk/SM measured; "
-                        "ncu: fp64 pipe 41-47 % busy, issue slots 64-66 %, DRAM 4-8 %) and the serial kernels by dependent-issue latency "
+                        "ncu: fp64 pipe 41-47 % busy, issue slots 64-67 %, DRAM 4-8 %) and the serial kernels by dependent-issue latency "
                         "(DESIGN.md section 4, profiles/r1/ncu_summary_r1_final.txt)"}
 
     result = {
