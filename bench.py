@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--fft", default="f64", choices=("f64", "f32"))
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--operating-band", type=float, nargs=2, default=None,
+                    help="experiment knob: another operating band (the BASELINE workload uses the default 400..3500 Hz = 71 bins)")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -118,7 +120,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from audio_processing_tools_b200.synth import default_params
-    params = default_params(check_duration=args.clip_seconds)
+    params = default_params(check_duration=args.clip_seconds, **({"operating_band": tuple(args.operating_band)} if args.operating_band else {}))
     cores = os.cpu_count() or 1
     _, n_clips, _ = cpu_baseline(params, args.clip_seconds, cores, target_wall=10.0)   # warm-up + sample sizing
     vals, times = [], []
@@ -165,7 +167,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    params = default_params(check_duration=args.clip_seconds)
+    params = default_params(check_duration=args.clip_seconds, **({"operating_band": tuple(args.operating_band)} if args.operating_band else {}))
     cfg = build_noise_config(FS, params)
     eng = BatchEngine(cfg, FS, device=local_rank, fft_f64=(args.fft == "f64"))
     N = int(FS * args.clip_seconds)
