@@ -1215,7 +1215,7 @@ struct FluxIO {
     float* mode_flux;      // optional [M][nF]
     int64_t nF;
 };
-constexpr int FLUX_FT = 64;   // frames per tile
+constexpr int FLUX_FT = 256;  // frames per tile (the per-CTA set-up is a large share of a 64-frame tile's instructions)
 
 inline size_t flux_smem_bytes(int K, int n_lanes, int nls) {
     (void)K; (void)nls;
@@ -1281,8 +1281,8 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevPa
     }
     __syncthreads();
     // positive t-vs-(t-2) flux summed per mode in numpy order (rain_frame_classifier.py:721-759)
-    for (int idx = tid; idx < nt * M; idx += 256) {
-        const int m = idx / nt, tt = idx - m * nt;
+    for (int m = 0; m < M; m++)
+    for (int tt = tid; tt < nt; tt += 256) {       // (mode, frame) without an index division
         const int tg = t0 + tt;
         const int lo = tab.mode_l0[m], n = tab.mode_n[m];
         const float* d2 = s_D + (tt + 2) * ds;
