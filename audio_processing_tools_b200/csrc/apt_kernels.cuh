@@ -1253,8 +1253,8 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevPa
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int r = min(rb + u * RP, nt + 1);
-                pk[u] = __ldg(Pp + (size_t)r * K);
-                nl[u] = p.use_norm ? __ldg(Np + (size_t)r * nls) : 0.0f;
+                pk[u] = __ldg(Pp + r * K);          // row offsets inside a tile fit 32 bits
+                nl[u] = p.use_norm ? __ldg(Np + r * nls) : 0.0f;
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
