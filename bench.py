@@ -299,6 +299,8 @@ def main():
 
     if not args.no_e2e:
         # end to end on every rank at once: pinned host PCM -> C ABI host entry point -> results back in host memory
+        from audio_processing_tools_b200.parallel import bind_near_gpu
+        prev_affinity = bind_near_gpu(dev.index) if world > 1 else None   # pinned buffers on the GPU's own NUMA node
         host = torch.empty(plan.nS, dtype=torch.int16, pin_memory=True)
         hv = host.numpy().reshape(n_clips, N)
         for i in range(n_clips):
@@ -323,12 +325,15 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        if prev_affinity is not None:
+            os.sched_setaffinity(0, prev_affinity)      # the CPU baseline below uses every host thread
         result["e2e"] = {"value": world * n_clips * args.clip_seconds / dt, "unit": "audio-s/s",
                          "h2d_bytes_per_step": int(plan.nS * 2) * world,
                          "d2h_bytes_per_step": int(nF * (1 + 4) + n_clips * (4 + 32)) * world,
                          "ms_per_step": dt * 1e3, "n_gpus": world,
                          "note": "apt_run_host_i16 on every rank: pinned host PCM, clip groups pipelined H2D/compute/D2H over "
-                                 "one copy stream and several compute streams; wall clock, max over ranks"}
+                                 "one copy stream and several compute streams; wall clock, max over ranks"
+                                 + ("; each rank bound to its GPU's NUMA node" if prev_affinity is not None else "")}
     if rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
         v, n, dt = cpu_baseline(params, args.clip_seconds, cores)
