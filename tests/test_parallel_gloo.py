@@ -60,3 +60,12 @@ def test_shard_helpers():
     assert parts[0][0] == 0 and parts[-1][1] == len(lengths) and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
     tot = [sum(lengths[a:b]) for a, b in parts]
     assert max(tot) <= 80
+
+
+def test_bind_near_gpu_is_harmless_without_a_gpu():
+    """No NVML device here: the call must leave the affinity alone and say so."""
+    import os
+    from audio_processing_tools_b200.parallel import bind_near_gpu
+    before = os.sched_getaffinity(0)
+    assert bind_near_gpu(0) is None
+    assert os.sched_getaffinity(0) == before
