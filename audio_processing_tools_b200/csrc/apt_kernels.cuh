@@ -330,27 +330,21 @@ __global__ void __launch_bounds__(STFT_NT, 3) stft256_kernel(const __grid_consta
     {
         const int klo = need_full ? 0 : p.band_lo, nk = need_full ? p.F : p.K;
         float* dstb = o.P_band ? o.P_band + fbase * p.K : nullptr;
-        // warp w takes frames w, w+8, ...; lanes run over the bins: no index division, and the (up to 20)
+        // all (frame, bin) pairs of the tile, flattened over the CTA (no idle lanes when nk is not a multiple of
+        // 32): element e -> frame e / nk by a multiply with ceil(2^24 / nk) (exact for e < 2^12, nk <= 129); the
         // evaluations of a thread are independent straight-line code
-        const int w = tid >> 5, ln = tid & 31;
-#pragma unroll
-        for (int tt = 0; tt < STFT_TF / 8; tt++) {
-            const int t = w + 8 * tt;
-            const float2* sS = S_row(t);
-            float* sP = P_row(t);
-#pragma unroll
-            for (int kk = 0; kk < 5; kk++) {
-                const int ki = ln + 32 * kk;
-                if (t < nfr && ki < nk) {
-                    const int k = klo + ki;
-                    const float2 z = sS[k];
-                    const float a = np_cabsf_fast(z.x, z.y);
-                    const float pw = a * a;
-                    if (need_full) sP[k] = pw;
-                    const int kb = k - p.band_lo;
-                    if (dstb && kb >= 0 && kb < p.K) dstb[t * p.K + kb] = pw;
-                }
-            }
+        const unsigned inv = (1u << 24) / (unsigned)nk + 1u;
+        const int n_el = nfr * nk;
+#pragma unroll 4
+        for (int e = tid; e < n_el; e += STFT_NT) {
+            const int t = (int)(((unsigned long long)(unsigned)e * inv) >> 24);
+            const int k = klo + (e - t * nk);
+            const float2 z = S_row(t)[k];
+            const float a = np_cabsf_fast(z.x, z.y);
+            const float pw = a * a;
+            if (need_full) P_row(t)[k] = pw;
+            const int kb = k - p.band_lo;
+            if (dstb && kb >= 0 && kb < p.K) dstb[t * p.K + kb] = pw;
         }
         if (o.S) {
             float2* dstS = reinterpret_cast<float2*>(o.S) + fbase * p.F;
