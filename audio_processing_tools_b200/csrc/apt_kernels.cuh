@@ -1849,23 +1849,24 @@ __global__ void __launch_bounds__(256) db_kernel(const __grid_constant__ DevPara
     if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
     for (int i = tid; i < SEL_BINS; i += 256) s_h[i] = 0;
     __syncthreads();
-    const float* src = N2 + f0 * p.K;
-    float* dst = db + f0 * p.K;
+    const float* src = N2 + f0 * p.K + e0;      // the chunk: 32-bit indices from here on
+    float* dst = db + f0 * p.K + e0;
+    const int ne = (int)(e1 - e0);
     double acc = 0.0;
     int run_bin = -1;
     uint32_t run_cnt = 0;
     constexpr int U = 8;
-    for (int64_t base = e0 + tid; base < e1; base += (int64_t)U * 256) {
+    for (int base = tid; base < ne; base += U * 256) {
         float v[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int64_t i = base + (int64_t)u * 256;
-            v[u] = i < e1 ? src[i] : 1.0f;
+            const int i = base + u * 256;
+            v[u] = i < ne ? src[i] : 1.0f;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int64_t i = base + (int64_t)u * 256;
-            if (i < e1) {
+            const int i = base + u * 256;
+            if (i < ne) {
                 const float d = 10.0f * svml_log10f(v[u] + p.eps32, s_ltab);
                 dst[i] = d;
                 acc += (double)d;
@@ -1926,19 +1927,20 @@ __global__ void __launch_bounds__(256) select_hist_kernel(Batch b, int K, const 
     const bool two = pre1 != pre0;
     for (int i = threadIdx.x; i < 2 * SEL_BINS; i += blockDim.x) (&s_h[0][0])[i] = 0;
     __syncthreads();
-    const float* src = db + f0 * K;
+    const float* src = db + f0 * K + e0;        // the chunk: 32-bit indices from here on
+    const int ne = (int)(e1 - e0);
     constexpr int U = 8;
-    for (int64_t base = e0 + threadIdx.x; base < e1; base += (int64_t)U * blockDim.x) {
+    for (int base = threadIdx.x; base < ne; base += U * 256) {
         float v[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int64_t i = base + (int64_t)u * blockDim.x;
-            v[u] = i < e1 ? __ldg(src + i) : 0.0f;
+            const int i = base + u * 256;
+            v[u] = i < ne ? __ldg(src + i) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int64_t i = base + (int64_t)u * blockDim.x;
-            if (i < e1) {
+            const int i = base + u * 256;
+            if (i < ne) {
                 const uint32_t key = db_key(v[u]);
                 const uint32_t hi = key >> shp;
                 const int bin = (int)((key >> sh) & mask);
