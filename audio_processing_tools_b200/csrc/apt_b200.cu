@@ -320,6 +320,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         if (N < p->n_fft || N <= d.padlen + 1) { delete pl; return fail(ctx, -28, "clip %d too short (%lld samples)", c, (long long)N); }
         const int64_t T = 1 + N / p->hop;
         const int64_t Tloc = 1 + (N - p->n_fft) / p->hop;
+        if (T * (int64_t)std::max(K, 128) >= (int64_t)1 << 31) { delete pl; return fail(ctx, -28, "clip %d too long (%lld frames): per-clip plane offsets are 32-bit", c, (long long)T); }
         pl->samp_off[c + 1] = pl->samp_off[c] + N;
         pl->frame_off[c + 1] = pl->frame_off[c] + T;
         pl->stft_tile_off[c + 1] = pl->stft_tile_off[c] + (generic ? (T + stftg_frames_per_cta(p->n_fft) - 1) / stftg_frames_per_cta(p->n_fft) : (T + STFT_TF - 1) / STFT_TF);

@@ -1074,6 +1074,9 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
 //   trk2_kernel   serial    lane = (clip, bin): tracker pass 2 gated by the labels -> noise PSD N2
 //   db_kernel     parallel  flat: noise-floor dB plane, its sums, level-0 histogram of the median select
 // ---------------------------------------------------------------------------------------------
+// trk1 / base address their planes with 32-bit offsets inside a clip (frames x row stride < 2^31, checked by the
+// plan): the 64-bit multiply per element costs instructions these loops are made of.  trk2 keeps 64-bit offsets: with
+// fewer registers all its CTAs become co-resident and it runs slower.
 constexpr int SEQ_KMAX = 128;    // operating-band bins supported (n_fft = 256 -> 71)
 constexpr int SEQ_PF = 16;       // frames per straight-line group of the serial loops (register prefetch)
 
@@ -1173,30 +1176,30 @@ __global__ void __launch_bounds__(128) trk1_kernel(const __grid_constant__ DevPa
     }
     float pbuf[SEQ_PF];
 #pragma unroll
-    for (int u = 0; u < SEQ_PF; u++) pbuf[u] = __ldg(Pk + (size_t)min(1 + u, T - 1) * K);
+    for (int u = 0; u < SEQ_PF; u++) pbuf[u] = __ldg(Pk + (uint32_t)(min(1 + u, T - 1) * K));
     int t = 1;
     for (; t + SEQ_PF <= L.Tmin; t += SEQ_PF) {
         float pc[SEQ_PF];
 #pragma unroll
         for (int u = 0; u < SEQ_PF; u++) pc[u] = pbuf[u];
 #pragma unroll
-        for (int u = 0; u < SEQ_PF; u++) pbuf[u] = __ldg(Pk + (size_t)min(t + SEQ_PF + u, T - 1) * K);
+        for (int u = 0; u < SEQ_PF; u++) pbuf[u] = __ldg(Pk + (uint32_t)(min(t + SEQ_PF + u, T - 1) * K));
 #pragma unroll
         for (int u = 0; u < SEQ_PF; u++) {
             const float pk = pc[u];
             const float nprev = tr.nprev;                       // N1[t-1]
             const float n1 = tracker_step(p, tr, pk, true);
             const float nl = f_min(nprev, p.trk_maxr * pk);     // lag by one frame, clamp (:874-882)
-            if (L.store) { NLk[(size_t)(t + u) * nls] = nl; if (N1k) N1k[(size_t)(t + u) * K] = n1; }
+            if (L.store) { NLk[(uint32_t)((t + u) * nls)] = nl; if (N1k) N1k[(uint32_t)((t + u) * K)] = n1; }
         }
     }
     for (; t < L.Tmax; t++) {   // ragged tail
         if (t < T) {
-            const float pk = __ldg(Pk + (size_t)t * K);
+            const float pk = __ldg(Pk + (uint32_t)(t * K));
             const float nprev = tr.nprev;
             const float n1 = tracker_step(p, tr, pk, true);
             const float nl = f_min(nprev, p.trk_maxr * pk);
-            if (L.store) { NLk[(size_t)t * nls] = nl; if (N1k) N1k[(size_t)t * K] = n1; }
+            if (L.store) { NLk[(uint32_t)(t * nls)] = nl; if (N1k) N1k[(uint32_t)(t * K)] = n1; }
         }
     }
 }
@@ -1348,24 +1351,24 @@ __global__ void __launch_bounds__(128) base_kernel(const __grid_constant__ DevPa
     }
     float xbuf[SEQ_PF];
 #pragma unroll
-    for (int u = 0; u < SEQ_PF; u++) xbuf[u] = __ldg(xs + (size_t)min(u, T - 1) * stride);
+    for (int u = 0; u < SEQ_PF; u++) xbuf[u] = __ldg(xs + (uint32_t)(min(u, T - 1) * stride));
     int t = 0;
     for (; t + SEQ_PF <= L.Tmin; t += SEQ_PF) {
         float xc[SEQ_PF];
 #pragma unroll
         for (int u = 0; u < SEQ_PF; u++) xc[u] = xbuf[u];
 #pragma unroll
-        for (int u = 0; u < SEQ_PF; u++) xbuf[u] = __ldg(xs + (size_t)min(t + SEQ_PF + u, T - 1) * stride);
+        for (int u = 0; u < SEQ_PF; u++) xbuf[u] = __ldg(xs + (uint32_t)(min(t + SEQ_PF + u, T - 1) * stride));
 #pragma unroll
         for (int u = 0; u < SEQ_PF; u++) {
             const float sc = baseline_step(p, bl_base, bl_scale, xc[u], ffloor);
-            if (L.store) xs[(size_t)(t + u) * stride] = sc;
+            if (L.store) xs[(uint32_t)((t + u) * stride)] = sc;
         }
     }
     for (; t < L.Tmax; t++) {
         if (t < T) {
-            const float sc = baseline_step(p, bl_base, bl_scale, __ldg(xs + (size_t)t * stride), ffloor);
-            if (L.store) xs[(size_t)t * stride] = sc;
+            const float sc = baseline_step(p, bl_base, bl_scale, __ldg(xs + (uint32_t)(t * stride)), ffloor);
+            if (L.store) xs[(uint32_t)(t * stride)] = sc;
         }
     }
 }
