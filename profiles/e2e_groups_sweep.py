@@ -1,3 +1,4 @@
+"""End-to-end time of apt_run_host_i16 as a function of the clip-group count (APT_HOST_GROUPS); prints one line per setting."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
