@@ -672,7 +672,19 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             Trk2IO io;
             io.P_band = pl->d_Pband.p; io.frame_class = out->frame_class; io.N2 = n2_plane; io.nF = pl->nF;
             const int64_t lanes = (int64_t)n_clips * d.K;
-            trk2_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, io);
+            // Every lane runs the whole time chain, so the kernel's time is (waves of CTAs) x (chain time at that
+            // residency); measured per frame step: ~170 cycles up to 4 warps/SM, 185 at 8, 228 at 12, and a cliff
+            // beyond (profiles/r1).  The default is 128-thread CTAs, three per SM (registers).
+            // When the launch holds 12..16 warps per SM that leaves a short second wave after a full first one;
+            // two even waves of one 256-thread CTA per SM (unused dynamic shared memory as the occupancy limiter)
+            // are faster there (1 000 x 71 lanes: 10.8 -> 9.7 ms).
+            const double warps_per_sm = (double)((lanes + 31) / 32) / (double)std::max(1, ctx->sm_count);
+            if (warps_per_sm > 12.0 && warps_per_sm <= 16.0) {
+                CUDA_OK(ctx, cudaFuncSetAttribute(trk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+                trk2_kernel<<<(unsigned)((lanes + 255) / 256), 256, 120 * 1024, st>>>(pl->dp, b, io);
+            } else {
+                trk2_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, io);
+            }
             pl->last_launches++;
             CUDA_OK(ctx, cudaGetLastError());
         }
