@@ -208,6 +208,9 @@ def rain_detection_algo(audio_data, **kwargs):
     return rain_detection_algo_batch([audio_data], **kwargs)[0]
 
 
+rain_detection_algo.batch = rain_detection_algo_batch      # RainProcessor.run_batch picks this up
+
+
 def python_classifier_boolean_wrapper(audio_signal: np.ndarray, **kwargs):
     """python_classifier_boolean_wrapper (:2577-2598)."""
     rain_drop_count, _, _ = rain_detection_algo(audio_signal, **kwargs)

@@ -55,5 +55,31 @@ class RainProcessor(BaseProcessor):
         return results, state_out
 
 
+    def run_batch(self, audio_list, params: Dict[str, Any]):
+        """Additive batch hook of the framework twin: when the wrapped function carries a `batch` companion
+        (`fn.batch(list_of_audio, **params) -> list of fn results`, as the GPU RoE detector does) the whole list is one
+        call; otherwise the files go through `run` one by one.  Same results / state as `run` per file; `latency_s` is
+        the batch time divided by the number of files."""
+        batch_fn = getattr(self.fn, "batch", None)
+        if batch_fn is None:
+            return [self.run(a, params) for a in audio_list]
+        for a in audio_list:
+            self._validate_audio(a, params)
+        outs, latency = self._with_timing(batch_fn, list(audio_list), **params)
+        per_file = latency / max(1, len(audio_list))
+        packed = []
+        for rain_drops, frain_mean, state in outs:
+            results: Dict[str, Any] = {"rain_drops": rain_drops, "frain_mean": frain_mean, "latency_s": per_file}
+            if isinstance(state, dict):
+                for key in ("rain_drop_count", "rain_peaks_count", "rain_drop_count_mod"):
+                    if key in state:
+                        results[key] = state[key]
+            state_out: Dict[str, Any] = dict(state) if isinstance(state, dict) else {"state": state}
+            state_out["processor"] = self.name
+            state_out["latency_s"] = per_file
+            packed.append((results, state_out))
+        return packed
+
+
 def has_processor(processors, name: str) -> bool:
     return any(p.name == name for p in processors)

@@ -63,3 +63,29 @@ def test_band_noise_config_resolution():
 def test_band_noise_rejects_hop_other_than_frame():
     with pytest.raises(ValueError, match="hop == frame_len"):
         BandNoiseEstimatorProcessor().run_batch([np.zeros(4096, np.float32)], {"hop": 256})
+
+
+def test_rain_processor_batch_hook_uses_the_companion():
+    """RainProcessor.run_batch: one call of fn.batch for the list, the same packaging as run() per file."""
+    from audio_processing_tools_b200.processors import RainProcessor
+    calls = []
+
+    def fn(audio, **params):
+        return int(audio.size), 1.5, {"rain_drop_count": int(audio.size), "extra": params.get("k")}
+
+    def fn_batch(audios, **params):
+        calls.append(len(audios))
+        return [fn(a, **params) for a in audios]
+
+    clips = [np.zeros(n, np.float32) for n in (20, 30)]
+    params = {"sample_rate": 10, "check_duration": 2, "k": 7}
+    plain = RainProcessor(name="rain", fn=fn).run_batch(clips, params)          # no companion: per-file run()
+    fn.batch = fn_batch
+    batched = RainProcessor(name="rain", fn=fn).run_batch(clips, params)
+    assert calls == [2]
+    for (r1, s1), (r2, s2) in zip(plain, batched):
+        assert {k: v for k, v in r1.items() if k != "latency_s"} == {k: v for k, v in r2.items() if k != "latency_s"}
+        assert s1["processor"] == s2["processor"] == "rain" and s1["extra"] == s2["extra"] == 7
+    with pytest.raises(ValueError):
+        RainProcessor(name="rain", fn=fn).run_batch([np.zeros(5, np.float32)], params)     # shorter than check_duration
+    assert roe.rain_detection_algo.batch is roe.rain_detection_algo_batch
