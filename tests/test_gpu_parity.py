@@ -470,3 +470,18 @@ def test_legacy_roe_batch_and_rain_processor(torch_cuda):
     res, st = RainProcessor(name="rain", fn=roe.rain_detection_algo).run(pcm_to_f32(clips[0]), dict(roe.default_params))
     assert res["rain_drops"] == single[0][0] and res["rain_drop_count"] == single[0][2]["rain_drop_count"]
     assert st["processor"] == "rain"
+
+
+def test_rain_processor_run_batch_uses_the_gpu_batch(torch_cuda):
+    """RainProcessor.run_batch over the legacy RoE fn: one GPU pass for the list, same results as run() per file."""
+    from audio_processing_tools_b200.edge import dsp_rain_detection as roe
+    from audio_processing_tools_b200.processors import RainProcessor
+    clips = [pcm_to_f32(synth_clip_i16(10.0, 91 + i, 10.0)) for i in range(3)]
+    proc = RainProcessor(name="rain", fn=roe.rain_detection_algo)
+    roe.max_harmonics = 6
+    single = [proc.run(c, dict(roe.default_params)) for c in clips]
+    roe.max_harmonics = 6
+    batch = proc.run_batch(clips, dict(roe.default_params))
+    for (r1, s1), (r2, s2) in zip(single, batch):
+        assert r1["rain_drops"] == r2["rain_drops"] and r1["rain_drop_count"] == r2["rain_drop_count"]
+        assert np.array_equal(s1["raining"], s2["raining"])
