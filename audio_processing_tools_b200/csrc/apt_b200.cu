@@ -680,10 +680,10 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             // are faster there (1 000 x 71 lanes: 10.8 -> 9.7 ms).
             const double warps_per_sm = (double)((lanes + 31) / 32) / (double)std::max(1, ctx->sm_count);
             if (warps_per_sm > 12.0 && warps_per_sm <= 16.0) {
-                CUDA_OK(ctx, cudaFuncSetAttribute(trk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-                trk2_kernel<<<(unsigned)((lanes + 255) / 256), 256, 120 * 1024, st>>>(pl->dp, b, io);
+                CUDA_OK(ctx, cudaFuncSetAttribute(trk2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+                trk2_kernel<256><<<(unsigned)((lanes + 255) / 256), 256, 120 * 1024, st>>>(pl->dp, b, io);
             } else {
-                trk2_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, io);
+                trk2_kernel<128><<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, io);
             }
             pl->last_launches++;
             CUDA_OK(ctx, cudaGetLastError());

@@ -1447,7 +1447,9 @@ struct Trk2IO {
     int64_t nF;
 };
 
-__global__ void __launch_bounds__(256) trk2_kernel(const __grid_constant__ DevParams p, Batch b, Trk2IO io) {
+// NT = CTA size of the launch (128: the compiler takes ~130 registers, three CTAs fit an SM; 256: see the launch site)
+template <int NT>
+__global__ void __launch_bounds__(NT) trk2_kernel(const __grid_constant__ DevParams p, Batch b, Trk2IO io) {
     const int K = p.K;
     const SerialLane L = serial_lane(b, K);
     const float* Pk = io.P_band + L.f0 * K + L.sub;
