@@ -75,3 +75,28 @@ def test_numpy_float32_kernels(emul):
     if feats.get("AVX512_SKX"):   # numpy takes the SVML path there: bit-equal
         assert np.array_equal(y, np.log10(x))
         assert np.array_equal(y1, np.log1p(x1))
+
+
+def test_power_phase_reciprocal_is_exact():
+    """stft256_kernel maps element e of the (frame, bin) tile to frame e // nk with (e * (2^24 // nk + 1)) >> 24;
+    exact for every nk the kernel can see (1..129 bins) and every e of a 32-frame tile."""
+    for nk in range(1, 130):
+        inv = (1 << 24) // nk + 1
+        e = np.arange(32 * 129, dtype=np.uint64)
+        assert np.array_equal((e * np.uint64(inv)) >> np.uint64(24), e // np.uint64(nk)), nk
+
+
+def test_exchange_swizzle_is_conflict_free():
+    """Exchange layout ex[k1 * 8 + (j ^ (k1 & 7))] (apt_math.cuh): a pass-A store (8 lanes j, one row k1) fills one
+    128-byte row, and a pass-B gather (8 lanes t, rows t or 16 - t, one column j) touches 8 different 16-byte bank
+    groups, so neither needs more than one shared-memory wavefront per quarter warp."""
+    def idx(k1, j):
+        return k1 * 8 + (j ^ (k1 & 7))
+    for k1 in range(16):
+        assert sorted(idx(k1, j) for j in range(8)) == list(range(k1 * 8, k1 * 8 + 8))
+    for j in range(8):
+        rows_a = [t for t in range(8)]                       # ka = t (lane 0 reads row 0)
+        rows_b = [8 if t == 0 else 16 - t for t in range(8)]
+        for rows in (rows_a, rows_b):
+            groups = [(idx(r, j) * 16 // 16) % 8 for r in rows]      # 16-byte slot inside the 128-byte bank window
+            assert sorted(groups) == list(range(8)), (j, rows)
