@@ -6,6 +6,8 @@ device is visible every entry point raises.
 from __future__ import annotations
 
 import ctypes as C
+import glob
+import hashlib
 import os
 import subprocess
 
@@ -122,22 +124,56 @@ EXPORTS = ("apt_init", "apt_destroy", "apt_last_error", "apt_abi_version", "apt_
            "apt_sizeof_out", "apt_params_default", "apt_plan_create", "apt_plan_destroy",
            "apt_plan_offsets", "apt_plan_total_frames", "apt_plan_total_samples",
            "apt_plan_scratch_bytes", "apt_run_i16", "apt_run_f32", "apt_plan_last_launches",
-           "apt_run_host_i16", "apt_plan_enable_timing", "apt_plan_kernel_ms", "apt_selftest",
+           "apt_run_host_i16", "apt_run_host_clips", "apt_source_hash", "apt_plan_enable_timing", "apt_plan_kernel_ms", "apt_selftest",
            "apt_dsd_run_i16", "apt_sizeof_bne_params", "apt_bne_run",
            "apt_sizeof_roe_params", "apt_roe_run")
 
 
+def source_files():
+    """Every file the library is compiled from: all of csrc/ plus the public header(s)."""
+    files = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                   glob.glob(os.path.join(_REPO, "include", "*.h")))
+    return files
+
+
+def source_hash():
+    """sha256 over the sources and the compiler flags; compiled into the library (apt_source_hash) so that a
+    stale binary is detected by content, not by file times (the .so is git-ignored and travels prebuilt)."""
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for f in source_files():
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:32]
+
+
+def built_hash():
+    """Hash recorded in the built library, or None.  Read from the file's bytes (the library carries the string
+    "APT_SRC_HASH=<hash>"), not through dlopen: a library loaded once stays mapped under its path for the life of
+    the process, so a rebuild could not be checked that way."""
+    if not os.path.exists(LIB_PATH):
+        return None
+    data = open(LIB_PATH, "rb").read()
+    i = data.find(b"APT_SRC_HASH=")
+    if i < 0:
+        return None
+    return data[i + 13:i + 13 + 32].decode("ascii", "replace")
+
+
 def build(force=False, verbose=False):
-    """Compile csrc/apt_b200.cu for sm_100a into the package directory (in-tree .so)."""
-    srcs = [os.path.join(CSRC, f) for f in ("apt_b200.cu", "apt_kernels.cuh", "apt_math.cuh")]
-    srcs.append(os.path.join(_REPO, "include", "apt_b200.h"))
-    if not force and os.path.exists(LIB_PATH) and all(
-            os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+    """Compile csrc/apt_b200.cu for sm_100a into the package directory (in-tree .so).  Rebuilds whenever the
+    hash of the sources differs from the one compiled into the existing library."""
+    want = source_hash()
+    if not force and built_hash() == want:
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "apt_b200.cu")]
+    tmp = LIB_PATH + ".tmp"
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-DAPT_SRC_HASH=\"%s\"" % want, "-o", tmp, os.path.join(CSRC, "apt_b200.cu")]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd, cwd=CSRC)
+    os.replace(tmp, LIB_PATH)
+    global _lib
+    _lib = None
     return LIB_PATH
 
 
@@ -154,6 +190,12 @@ def load():
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`."
             " There is no CPU fallback for this path.")
     L = C.CDLL(LIB_PATH)
+    L.apt_source_hash.restype = C.c_char_p
+    if os.path.isdir(CSRC) and L.apt_source_hash().decode() != source_hash():
+        raise RuntimeError(
+            f"{LIB_PATH} was built from other sources than the ones in {CSRC} (hash "
+            f"{L.apt_source_hash().decode()} != {source_hash()}): rebuild with "
+            "`python -c 'import __graft_entry__ as g; g.build()'`")
     vp, i64p = C.c_void_p, C.POINTER(C.c_int64)
     L.apt_init.argtypes = [C.c_int, C.POINTER(vp)]
     L.apt_destroy.argtypes = [vp]
@@ -170,6 +212,7 @@ def load():
     L.apt_run_i16.argtypes = [vp, C.c_int, vp, C.POINTER(AptOut), vp]
     L.apt_run_f32.argtypes = [vp, C.c_int, vp, C.POINTER(AptOut), vp]
     L.apt_run_host_i16.argtypes = [vp] * 8
+    L.apt_run_host_clips.argtypes = [vp, C.POINTER(vp), C.c_int] + [vp] * 6
     L.apt_selftest.argtypes = [vp, C.c_int, C.c_int64, i64p]
     L.apt_bne_run.argtypes = [vp, C.POINTER(AptBneParams), C.c_int, i64p, vp, C.c_int, vp, vp, vp, vp, vp]
     i32p = C.POINTER(C.c_int32)

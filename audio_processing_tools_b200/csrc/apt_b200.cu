@@ -8,6 +8,10 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 #include "apt_kernels.cuh"
 #include "apt_dsd.cuh"
@@ -68,10 +72,18 @@ struct apt_plan {
     int td_ns = 0;
     size_t td_smem = 0;
     // scratch
-    DevBuf<float> d_Pband, d_db, d_td, d_mf, d_nl, d_nl_all, d_Dscr;
-    DevBuf<double> d_dbsum;   // [select chunks] float64 sums of the dB plane
+    DevBuf<float> d_Pband, d_n2, d_td, d_mf, d_nl, d_nl_all, d_Dscr;
+    DevBuf<double> d_dbsum;   // [dB chunks] float64 sums of the noise-floor dB values
+    // state carried between the time segments of the pipelined run
+    DevBuf<float4> d_st_trk1, d_st_trk2;   // [clips][K]
+    DevBuf<double2> d_st_base;             // [clips][APT_MAX_MODES + 1]
+    // candidate lists of the median select
+    std::vector<int64_t> cand_off;
+    DevBuf<int64_t> d_cand_off;
+    DevBuf<uint32_t> d_cand;
     Trk1Tab tab_modes, tab_all;   // pass-1 lane tables: mode bins only / every band bin (debug planes)
     int mf_stride = 8;
+    int st_stride = 0;      // lanes per clip in the carried-state arrays
     bool generic = false;   // generic frame-size STFT kernel
     bool full_ok = true;    // the full pipeline is planned (n_fft = 256, hop = 128)
     DevBuf<double> d_gwin64; DevBuf<cx<double>> d_gtw64; DevBuf<float> d_gwin32; DevBuf<cx<float>> d_gtw32;
@@ -80,11 +92,22 @@ struct apt_plan {
     DevBuf<int> d_counter;
     // host-path staging
     DevBuf<int16_t> d_pcm;
+    DevBuf<float> d_pcm_f32;
+    static constexpr int N_RING = 3;          // pinned slots of the pageable-clips path (apt_run_host_clips)
+    void* ring[N_RING] = {nullptr, nullptr, nullptr};
+    size_t ring_bytes = 0;
     DevBuf<int8_t> d_fc; DevBuf<float> d_rc, d_nc, d_stats; DevBuf<int32_t> d_ev, d_evc;
     static constexpr int N_COMP = 4;
     cudaStream_t s_copy = nullptr, s_comp[N_COMP] = {nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t s_aux = nullptr;            // high-priority side stream for the STFT -> baseline chain (the TD kernel stays on the caller's)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // Pipelined run: one stream per kernel kind, so that kernel k of time segment s+1 overlaps kernel k+1 of segment s;
+    // events chain the kinds inside a segment.  The bulk kernels (STFT, TD) run at the lowest priority, everything
+    // on the latency-bound chain behind them at the highest.
+    enum { SK_STFT, SK_TD, SK_TRK1, SK_FLUX, SK_BASE, SK_DEC, SK_TRK2, SK_DBS, SK_N };
+    static constexpr int MAX_SEG = 64;
+    cudaStream_t s_kind[SK_N] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_seg[SK_N][MAX_SEG] = {};
+    cudaEvent_t ev_fork = nullptr;
+    int pipeline = 1;                        // 0: everything on the caller's stream in one segment
     int last_launches = 0;
     size_t scratch_bytes = 0;
     // optional per-kernel timing (CUDA events on the launch stream)
@@ -138,13 +161,6 @@ static void build_td_tables(const apt_params_t& prm, int ns, const double sos[][
     (void)prm;
 }
 
-// 2-D launch grid of a tiled kernel over clips [clip0, clip0+n): x = largest tile count, y = clips
-static dim3 tile_grid(const std::vector<int64_t>& off, int clip0, int n) {
-    int64_t mx = 1;
-    for (int c = clip0; c < clip0 + n; c++) mx = std::max(mx, off[c + 1] - off[c]);
-    return dim3((unsigned)mx, (unsigned)n, 1);
-}
-
 template <typename T>
 static cudaError_t upload(DevBuf<T>& b, const std::vector<T>& h) {
     cudaError_t e = b.alloc(h.size());
@@ -155,6 +171,13 @@ static cudaError_t upload(DevBuf<T>& b, const std::vector<T>& h) {
 
 extern "C" {
 
+void apt_plan_destroy(apt_plan_t* plan);
+
+#ifndef APT_SRC_HASH
+#define APT_SRC_HASH "unhashed"
+#endif
+static const char kSrcHashTag[] = "APT_SRC_HASH=" APT_SRC_HASH;   // found by the loader in the file's bytes
+const char* apt_source_hash(void) { return kSrcHashTag + 13; }
 int apt_abi_version(void) { return APT_ABI_VERSION; }
 int apt_sizeof_params(void) { return (int)sizeof(apt_params_t); }
 int apt_sizeof_out(void) { return (int)sizeof(apt_out_t); }
@@ -266,7 +289,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         d.mode_blo[i] = p->mode_band_lo[i]; d.mode_bhi[i] = p->mode_band_hi[i];
         d.mode_w[i] = p->mode_weight[i];
         if (i < p->n_modes && (p->mode_hi[i] >= F || (p->mode_band_hi[i] >= K && p->mode_band_lo[i] <= p->mode_band_hi[i]))) {
-            delete pl; return fail(ctx, -27, "mode band %d out of range", i);
+            apt_plan_destroy(pl); return fail(ctx, -27, "mode band %d out of range", i);
         }
     }
     d.trk_eta = p->trk_eta; d.trk_alpha = p->trk_scale_alpha; d.trk_1m_alpha = p->trk_one_minus_alpha; d.trk_floor = p->trk_step_floor;
@@ -292,7 +315,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     d.peak_min_above_floor = p->peak_min_db_above_floor; d.peak_ratio_min = p->peak_ratio_min;
     d.peak_valid_prom_min = p->peak_valid_prom_min_db; d.peak_valid_prom_max = p->peak_valid_prom_max_db;
     if (p->n_gain_taps < 1 || p->n_gain_taps > APT_MAX_GAIN_TAPS || (p->n_gain_taps & 1) == 0) {
-        delete pl; return fail(ctx, -32, "n_gain_taps=%d must be odd and <= %d", p->n_gain_taps, APT_MAX_GAIN_TAPS);
+        apt_plan_destroy(pl); return fail(ctx, -32, "n_gain_taps=%d must be odd and <= %d", p->n_gain_taps, APT_MAX_GAIN_TAPS);
     }
     // TD prefilter: n_sos == 0 is run as one identity section
     double sos[APT_MAX_SOS][6];
@@ -317,21 +340,21 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     pl->stft_tile_off.assign(n_clips + 1, 0); pl->td_tile_off.assign(n_clips + 1, 0); pl->sel_chunk_off.assign(n_clips + 1, 0); pl->flux_tile_off.assign(n_clips + 1, 0);
     for (int c = 0; c < n_clips; c++) {
         const int64_t N = clip_len[c];
-        if (N < p->n_fft || N <= d.padlen + 1) { delete pl; return fail(ctx, -28, "clip %d too short (%lld samples)", c, (long long)N); }
+        if (N < p->n_fft || N <= d.padlen + 1) { apt_plan_destroy(pl); return fail(ctx, -28, "clip %d too short (%lld samples)", c, (long long)N); }
         const int64_t T = 1 + N / p->hop;
         const int64_t Tloc = 1 + (N - p->n_fft) / p->hop;
-        if (T * (int64_t)std::max(K, 128) >= (int64_t)1 << 31) { delete pl; return fail(ctx, -28, "clip %d too long (%lld frames): per-clip plane offsets are 32-bit", c, (long long)T); }
+        if (T * (int64_t)std::max(K, 128) >= (int64_t)1 << 31) { apt_plan_destroy(pl); return fail(ctx, -28, "clip %d too long (%lld frames): per-clip plane offsets are 32-bit", c, (long long)T); }
         pl->samp_off[c + 1] = pl->samp_off[c] + N;
         pl->frame_off[c + 1] = pl->frame_off[c] + T;
         pl->stft_tile_off[c + 1] = pl->stft_tile_off[c] + (generic ? (T + stftg_frames_per_cta(p->n_fft) - 1) / stftg_frames_per_cta(p->n_fft) : (T + STFT_TF - 1) / STFT_TF);
         pl->td_tile_off[c + 1] = pl->td_tile_off[c] + std::max<int64_t>(1, (Tloc + TD_FT - 1) / TD_FT);
-        pl->sel_chunk_off[c + 1] = pl->sel_chunk_off[c] + (T * K + SEL_CHUNK - 1) / SEL_CHUNK;
+        pl->sel_chunk_off[c + 1] = pl->sel_chunk_off[c] + (T + DB_CF - 1) / DB_CF;
         pl->flux_tile_off[c + 1] = pl->flux_tile_off[c] + (T + FLUX_FT - 1) / FLUX_FT;
     }
     pl->nS = pl->samp_off[n_clips]; pl->nF = pl->frame_off[n_clips];
-    if (pl->stft_tile_off[n_clips] > 0x7fffffffLL || pl->td_tile_off[n_clips] > 0x7fffffffLL) { delete pl; return fail(ctx, -29, "batch too large for one launch"); }
+    if (pl->stft_tile_off[n_clips] > 0x7fffffffLL || pl->td_tile_off[n_clips] > 0x7fffffffLL) { apt_plan_destroy(pl); return fail(ctx, -29, "batch too large for one launch"); }
 
-#define PL_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int r_ = fail(ctx, -10, "%s failed: %s", #call, cudaGetErrorString(e_)); delete pl; return r_; } } while (0)
+#define PL_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int r_ = fail(ctx, -10, "%s failed: %s", #call, cudaGetErrorString(e_)); apt_plan_destroy(pl); return r_; } } while (0)
     PL_OK(upload(pl->d_samp_off, pl->samp_off));
     PL_OK(upload(pl->d_frame_off, pl->frame_off));
     PL_OK(upload(pl->d_stft_tile_off, pl->stft_tile_off));
@@ -373,7 +396,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     {
         const int halo = (p->blk_post_pre + 2) * p->blk_hop + p->blk_len;
         const int lb = TD_FT * p->hop + p->n_fft + 2 * halo + 2 * TD_WARM + p->hop;
-        if (halo > 128 || lb > TD_LB) { delete pl; return fail(ctx, -26, "block-energy geometry needs a %d-sample tile buffer (max %d)", lb, TD_LB); }
+        if (halo > 128 || lb > TD_LB) { apt_plan_destroy(pl); return fail(ctx, -26, "block-energy geometry needs a %d-sample tile buffer (max %d)", lb, TD_LB); }
         std::vector<double> Apow, H;
         build_td_tables(*p, ns, sos, TD_CHUNK, Apow, H);
         PL_OK(upload(pl->d_Apow, Apow)); PL_OK(upload(pl->d_H, H));
@@ -383,7 +406,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
             const int dim = 2 * ns, e = TD_WARM / TD_CHUNK;
             double mx = 0.0;
             for (int i = 0; i < dim * dim; i++) mx = std::max(mx, fabs(Apow[(size_t)i * 32 + e]));
-            if (mx > 1e-15) { delete pl; return fail(ctx, -26, "TD prefilter decays too slowly for the %d-sample tile warm-up (|A^%d| = %.3g)", TD_WARM, e, mx); }
+            if (mx > 1e-15) { apt_plan_destroy(pl); return fail(ctx, -26, "TD prefilter decays too slowly for the %d-sample tile warm-up (|A^%d| = %.3g)", TD_WARM, e, mx); }
         }
         memset(pl->tdt.Hc, 0, sizeof(pl->tdt.Hc)); memset(pl->tdt.Adc, 0, sizeof(pl->tdt.Adc));
         if (ns <= 2) {
@@ -396,7 +419,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     }
     // scratch
     PL_OK(pl->d_Pband.alloc((size_t)pl->nF * K));
-    PL_OK(pl->d_db.alloc((size_t)pl->nF * K));
+    PL_OK(pl->d_n2.alloc((size_t)pl->nF * K));
     PL_OK(pl->d_td.alloc((size_t)pl->nF * APT_N_TD_FEATURES));
     PL_OK(pl->d_dbsum.alloc((size_t)pl->sel_chunk_off[n_clips]));
     pl->mf_stride = (p->n_modes + 1 <= 8) ? 8 : 16;
@@ -411,7 +434,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
             tm.mode_l0[m] = nl; tm.mode_n[m] = n;
             ta.mode_l0[m] = n ? lo : 0; ta.mode_n[m] = n;
             for (int i = 0; i < n; i++) {
-                if (nl >= SEQ_KMAX) { delete pl; return fail(ctx, -27, "mode bands cover more than %d bins", SEQ_KMAX); }
+                if (nl >= SEQ_KMAX) { apt_plan_destroy(pl); return fail(ctx, -27, "mode bands cover more than %d bins", SEQ_KMAX); }
                 tm.lane_bin[nl++] = (unsigned char)(lo + i);
             }
         }
@@ -422,19 +445,37 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     }
     PL_OK(pl->d_sel.alloc(n_clips));
     PL_OK(pl->d_hist.alloc((size_t)n_clips * 2 * SEL_BINS));
+    pl->st_stride = std::max(K, pl->tab_modes.n_lanes);
+    PL_OK(pl->d_st_trk1.alloc((size_t)n_clips * pl->st_stride));
+    PL_OK(pl->d_st_trk2.alloc((size_t)n_clips * pl->st_stride));
+    PL_OK(pl->d_st_base.alloc((size_t)n_clips * (APT_MAX_MODES + 1)));
+    {   // candidate lists of the median select: an eighth of the plane per clip (a 1/16 dB bin holds ~1 % of a clip's
+        // values; clips that overflow fall back to the full radix select)
+        pl->cand_off.assign(n_clips + 1, 0);
+        for (int c = 0; c < n_clips; c++) {
+            const int64_t n = (pl->frame_off[c + 1] - pl->frame_off[c]) * (int64_t)K;
+            pl->cand_off[c + 1] = pl->cand_off[c] + std::max<int64_t>(1024, (n / 8 + 31) / 32 * 32);
+        }
+        PL_OK(upload(pl->d_cand_off, pl->cand_off));
+        PL_OK(pl->d_cand.alloc((size_t)pl->cand_off[n_clips]));
+    }
     PL_OK(pl->d_counter.alloc(64));
     pl->scratch_bytes = sizeof(float) * ((size_t)pl->nF * K * 2 + (size_t)pl->nF * APT_N_TD_FEATURES + (size_t)pl->nF * pl->mf_stride +
-                                         (size_t)pl->nF * pl->tab_modes.nls) +
+                                         (size_t)pl->nF * pl->tab_modes.nls + (size_t)pl->cand_off[n_clips] + (size_t)n_clips * K * 8) +
                         sizeof(double) * (size_t)pl->sel_chunk_off[n_clips] +
                         (size_t)n_clips * (sizeof(SelState) + 2 * SEL_BINS * sizeof(uint32_t));
     PL_OK(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
     for (int i = 0; i < apt_plan::N_COMP; i++) PL_OK(cudaStreamCreateWithFlags(&pl->s_comp[i], cudaStreamNonBlocking));
     {
         int lo = 0, hi = 0;
-        PL_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        PL_OK(cudaStreamCreateWithPriority(&pl->s_aux, cudaStreamNonBlocking, hi));   // hi = greatest priority
+        PL_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least, hi = greatest priority
+        for (int k = 0; k < apt_plan::SK_N; k++) {
+            const int prio = (k == apt_plan::SK_STFT || k == apt_plan::SK_TD) ? lo : hi;
+            PL_OK(cudaStreamCreateWithPriority(&pl->s_kind[k], cudaStreamNonBlocking, prio));
+            for (int i = 0; i < apt_plan::MAX_SEG; i++) PL_OK(cudaEventCreateWithFlags(&pl->ev_seg[k][i], cudaEventDisableTiming));
+        }
         PL_OK(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
-        PL_OK(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+        if (const char* e = getenv("APT_PIPELINE")) pl->pipeline = atoi(e);
     }
 #undef PL_OK
     *out = pl;
@@ -445,9 +486,13 @@ void apt_plan_destroy(apt_plan_t* plan) {
     if (!plan) return;
     if (plan->s_copy) cudaStreamDestroy(plan->s_copy);
     for (int i = 0; i < apt_plan::N_COMP; i++) if (plan->s_comp[i]) cudaStreamDestroy(plan->s_comp[i]);
-    if (plan->s_aux) cudaStreamDestroy(plan->s_aux);
+    for (int k = 0; k < apt_plan::SK_N; k++) {
+        if (plan->s_kind[k]) cudaStreamDestroy(plan->s_kind[k]);
+        for (int i = 0; i < apt_plan::MAX_SEG; i++) if (plan->ev_seg[k][i]) cudaEventDestroy(plan->ev_seg[k][i]);
+    }
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
-    if (plan->ev_join) cudaEventDestroy(plan->ev_join);
+    for (int i = 0; i < apt_plan::N_RING; i++) if (plan->ring[i]) cudaFreeHost(plan->ring[i]);
+    for (auto& m : plan->marks) cudaEventDestroy(m.second);
     delete plan;
 }
 
@@ -491,10 +536,18 @@ int apt_plan_kernel_ms(apt_plan_t* plan, float* out_ms) {
 // ---------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------
+// grid of a tiled kernel over the tiles [tile0, tile0 + per_seg) of clips [clip0, clip0 + n): x = tiles of the
+// longest clip that fall into the range, y = clips.  x == 0: nothing to launch.
+static dim3 seg_grid(const std::vector<int64_t>& off, int clip0, int n, int64_t tile0, int64_t per_seg) {
+    int64_t mx = 0;
+    for (int c = clip0; c < clip0 + n; c++) mx = std::max(mx, off[c + 1] - off[c]);
+    const int64_t x = std::max<int64_t>(0, std::min(per_seg, mx - tile0));
+    return dim3((unsigned)x, (unsigned)n, 1);
+}
+
 template <typename T, typename PCM>
-static cudaError_t launch_stft(apt_plan* pl, const Batch& b, const PCM* pcm, const StftOut& so, cudaStream_t st) {
-    const int64_t tiles = pl->stft_tile_off[b.clip0 + b.n_clips] - pl->stft_tile_off[b.clip0];
-    if (tiles <= 0) return cudaSuccess;
+static cudaError_t launch_stft(apt_plan* pl, const Batch& b, dim3 grid, const PCM* pcm, const StftOut& so, cudaStream_t st) {
+    if (grid.x == 0) return cudaSuccess;
     FftTables<T> tab;
     if constexpr (sizeof(T) == 8) { tab.win = pl->d_win64.p; tab.tw128 = pl->d_tw128_64.p; tab.tw256 = pl->d_tw256_64.p; }
     else { tab.win = pl->d_win32.p; tab.tw128 = pl->d_tw128_32.p; tab.tw256 = pl->d_tw256_32.p; }
@@ -502,7 +555,7 @@ static cudaError_t launch_stft(apt_plan* pl, const Batch& b, const PCM* pcm, con
     auto kern = stft256_kernel<T, PCM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<tile_grid(pl->stft_tile_off, b.clip0, b.n_clips), STFT_NT, smem, st>>>(pl->dp, b, pcm, pl->d_stft_tile_off.p, tab, so);
+    kern<<<grid, STFT_NT, smem, st>>>(pl->dp, b, pcm, pl->d_stft_tile_off.p, tab, so);
     pl->last_launches++;
     return cudaGetLastError();
 }
@@ -516,191 +569,303 @@ static cudaError_t launch_stft_generic(apt_plan* pl, const Batch& b, const PCM* 
     auto kern = stft_generic_kernel<T, PCM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<tile_grid(pl->stft_tile_off, b.clip0, b.n_clips), STFTG_NT, smem, st>>>(pl->dp, b, pcm, tab, so, stftg_frames_per_cta(pl->dp.n_fft));
+    kern<<<seg_grid(pl->stft_tile_off, b.clip0, b.n_clips, 0, INT64_MAX), STFTG_NT, smem, st>>>(pl->dp, b, pcm, tab, so, stftg_frames_per_cta(pl->dp.n_fft));
     pl->last_launches++;
     return cudaGetLastError();
 }
 
 template <int NS, typename PCM>
-static cudaError_t launch_td_ns(apt_plan* pl, const Batch& b, const PCM* pcm, const TdOut& to, cudaStream_t st) {
-    const int64_t tiles = pl->td_tile_off[b.clip0 + b.n_clips] - pl->td_tile_off[b.clip0];
-    if (tiles <= 0) return cudaSuccess;
+static cudaError_t launch_td_ns(apt_plan* pl, const Batch& b, dim3 grid, const PCM* pcm, const TdOut& to, cudaStream_t st) {
+    if (grid.x == 0) return cudaSuccess;
     auto kern = td_features_kernel<NS, PCM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->td_smem);
     if (e != cudaSuccess) return e;
-    kern<<<tile_grid(pl->td_tile_off, b.clip0, b.n_clips), TD_NT, pl->td_smem, st>>>(pl->dp, b, pcm, pl->d_td_tile_off.p, pl->tdt, to);
+    kern<<<grid, TD_NT, pl->td_smem, st>>>(pl->dp, b, pcm, pl->d_td_tile_off.p, pl->tdt, to);
     pl->last_launches++;
     return cudaGetLastError();
 }
 template <typename PCM>
-static cudaError_t launch_td(apt_plan* pl, const Batch& b, const PCM* pcm, const TdOut& to, cudaStream_t st) {
+static cudaError_t launch_td(apt_plan* pl, const Batch& b, dim3 grid, const PCM* pcm, const TdOut& to, cudaStream_t st) {
     switch (pl->td_ns) {
-        case 1: return launch_td_ns<1, PCM>(pl, b, pcm, to, st);
-        case 2: return launch_td_ns<2, PCM>(pl, b, pcm, to, st);
-        case 3: return launch_td_ns<3, PCM>(pl, b, pcm, to, st);
-        case 4: return launch_td_ns<4, PCM>(pl, b, pcm, to, st);
+        case 1: return launch_td_ns<1, PCM>(pl, b, grid, pcm, to, st);
+        case 2: return launch_td_ns<2, PCM>(pl, b, grid, pcm, to, st);
+        case 3: return launch_td_ns<3, PCM>(pl, b, grid, pcm, to, st);
+        case 4: return launch_td_ns<4, PCM>(pl, b, grid, pcm, to, st);
     }
     return cudaErrorInvalidValue;
 }
 
+// Frames per time segment of the pipelined run: a common multiple of every tile size on the path (STFT 32, TD 56,
+// flux 256, dB chunk 896 frames -> 1792), sized for about `want` segments over the longest clip.
+constexpr int SEG_UNIT = 1792;
+static_assert(SEG_UNIT % STFT_TF == 0 && SEG_UNIT % TD_FT == 0 && SEG_UNIT % FLUX_FT == 0 && SEG_UNIT % DB_CF == 0, "segment unit");
+
 template <typename PCM>
 static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM* pcm, const apt_out_t* out, cudaStream_t st,
-                     bool fork_td = false) {
+                     int want_seg = 16) {
     apt_ctx* ctx = pl->ctx;
     const DevParams& d = pl->dp;
-    Batch b{clip0, n_clips, pl->d_samp_off.p, pl->d_frame_off.p};
     const bool full = (stages & APT_STAGE_FULL) != 0;
+    // ---- every argument check and lazy allocation happens before the first launch
     if (full && (!out->frame_class || !out->rain_conf || !out->noise_conf || !out->event_idx || !out->event_count || !out->clip_stats))
         return fail(ctx, -30, "full pipeline requires frame_class, rain_conf, noise_conf, event_idx, event_count, clip_stats buffers");
     if (!full && !(out->band_energy || out->P || out->S || out->raw))
         return fail(ctx, -31, "features stage requires at least one of band_energy / P / S / raw");
-    if (full && !pl->full_ok)
+    if (full && (!pl->full_ok || pl->generic))
         return fail(ctx, -34, "the full pipeline runs at n_fft=256 / hop=128 only; n_fft=%d hop=%d supports the features stage", d.n_fft, d.hop);
+    const bool want_peaks = out->peak_ratio || out->peak_gate_score || out->peak_valid_count || out->peak_count_by_mode;
+    const bool want_gain = out->G || out->S_hat || out->y;
+    if (full) {
+        if (want_peaks && !(out->peak_ratio && out->peak_gate_score && out->peak_valid_count && out->peak_count_by_mode))
+            return fail(ctx, -35, "the four peak-feature buffers must be given together");
+        if (want_gain && !d.suppressor_bypass) {
+            if (!out->G) return fail(ctx, -33, "S_hat / y require the G buffer");
+            if (out->y && !out->S_hat) return fail(ctx, -33, "y requires the S_hat buffer");
+            if (out->S_hat && !out->S) return fail(ctx, -33, "S_hat requires the S buffer");
+        }
+    }
+    float* D_plane = out->D;
+    if (full && want_peaks && !D_plane) {   // the peak features read the detector input of every band bin
+        if (!pl->d_Dscr.p) CUDA_OK(ctx, pl->d_Dscr.alloc((size_t)pl->nF * d.K));
+        D_plane = pl->d_Dscr.p;
+    }
+    const bool dbg = full && (out->det_noise_psd || out->det_noise_lag || D_plane);
+    if (dbg && !pl->d_nl_all.p) CUDA_OK(ctx, pl->d_nl_all.alloc((size_t)pl->nF * pl->tab_all.nls));
+
+    Batch b{clip0, n_clips, pl->d_samp_off.p, pl->d_frame_off.p, 0, 0, INT32_MAX};
+    StftOut so;
+    so.S = out->S; so.P = out->P; so.P_band = full ? pl->d_Pband.p : nullptr; so.band_energy = out->band_energy;
+    so.raw = out->raw; so.freqs = pl->d_freqs.p; so.nF = pl->nF;
     if (pl->generic) {
-        if (full) return fail(ctx, -34, "the full pipeline runs at n_fft=256 / hop=128 only; n_fft=%d hop=%d supports the features stage", d.n_fft, d.hop);
-        StftOut sg;
-        sg.S = out->S; sg.P = out->P; sg.P_band = nullptr; sg.band_energy = out->band_energy;
-        sg.raw = out->raw; sg.freqs = pl->d_freqs.p; sg.nF = pl->nF;
         pl->mark(APT_KERNEL_STFT, st);
-        cudaError_t eg = pl->prm.fft_f64 ? launch_stft_generic<double, PCM>(pl, b, pcm, sg, st) : launch_stft_generic<float, PCM>(pl, b, pcm, sg, st);
+        cudaError_t eg = pl->prm.fft_f64 ? launch_stft_generic<double, PCM>(pl, b, pcm, so, st) : launch_stft_generic<float, PCM>(pl, b, pcm, so, st);
         if (eg != cudaSuccess) return fail(ctx, -11, "stft launch failed: %s", cudaGetErrorString(eg));
         pl->mark(-1, st);
         return 0;
     }
-
-    // The TD kernel depends only on the PCM and is first needed by decide_kernel; the STFT -> trk1 -> flux -> base
-    // chain is independent of it.  Unless per-kernel timing is on, the chain runs on a high-priority side stream
-    // so that its serial kernels (few warps, latency-bound) are scheduled ahead of the TD kernel's queued CTAs and
-    // hide behind them; the caller's stream carries the TD kernel and joins the chain before decide_kernel.
-    const bool forked = fork_td && full && !pl->timing && pl->s_aux;
-    cudaStream_t sc = st;   // stream of the chain
-    if (forked) {
-        CUDA_OK(ctx, cudaEventRecord(pl->ev_fork, st));
-        CUDA_OK(ctx, cudaStreamWaitEvent(pl->s_aux, pl->ev_fork, 0));
-        sc = pl->s_aux;
+    if (!full) {
+        pl->mark(APT_KERNEL_STFT, st);
+        const dim3 g = seg_grid(pl->stft_tile_off, clip0, n_clips, 0, INT64_MAX);
+        cudaError_t e = pl->prm.fft_f64 ? launch_stft<double, PCM>(pl, b, g, pcm, so, st) : launch_stft<float, PCM>(pl, b, g, pcm, so, st);
+        if (e != cudaSuccess) return fail(ctx, -11, "stft launch failed: %s", cudaGetErrorString(e));
+        pl->mark(-1, st);
+        return 0;
     }
-    StftOut so;
-    so.S = out->S; so.P = out->P; so.P_band = full ? pl->d_Pband.p : nullptr; so.band_energy = out->band_energy;
-    so.raw = out->raw; so.freqs = pl->d_freqs.p; so.nF = pl->nF;
-    pl->mark(APT_KERNEL_STFT, st);
-    cudaError_t e = pl->prm.fft_f64 ? launch_stft<double, PCM>(pl, b, pcm, so, sc) : launch_stft<float, PCM>(pl, b, pcm, so, sc);
-    if (e != cudaSuccess) return fail(ctx, -11, "stft launch failed: %s", cudaGetErrorString(e));
-    if (!full) { pl->mark(-1, st); return 0; }
 
+    // ---- the full pipeline.  The time axis of every clip is cut into segments; all kernels of one kind run on their
+    // own stream in segment order (the serial kernels carry their state from segment to segment), and events chain
+    // the kinds inside a segment:  stft -> trk1 -> flux -> base -> decide (<- td) -> trk2 -> dbsum.
+    // So the latency-bound serial kernels of segment s overlap each other's neighbours and the wide kernels of the
+    // segments behind them, instead of each paying its whole chain (frames x dependent-issue latency) alone.
+    // With per-kernel timing on (or APT_PIPELINE=0) everything runs on the caller's stream in one segment.
+    int64_t maxT = 1;
+    for (int c = clip0; c < clip0 + n_clips; c++) maxT = std::max(maxT, pl->frame_off[c + 1] - pl->frame_off[c]);
+    const bool piped = want_seg > 1 && pl->pipeline && !pl->timing;
+    int seg_frames, n_seg;
+    if (piped) {
+        int want = want_seg;
+        if (const char* e = getenv("APT_SEGMENTS")) want = std::max(1, std::min((int)apt_plan::MAX_SEG, atoi(e)));
+        const int64_t units = (maxT + SEG_UNIT - 1) / SEG_UNIT;
+        const int64_t upseg = std::max<int64_t>(1, (units + want - 1) / want);
+        seg_frames = (int)std::min<int64_t>(upseg * SEG_UNIT, INT32_MAX / 2);
+        n_seg = (int)((maxT + seg_frames - 1) / seg_frames);
+        if (n_seg > apt_plan::MAX_SEG) return fail(ctx, -29, "internal: %d time segments", n_seg);
+    } else {
+        seg_frames = (int)std::min<int64_t>((maxT + SEG_UNIT - 1) / SEG_UNIT * SEG_UNIT, INT32_MAX / 2);
+        n_seg = 1;
+    }
+    cudaStream_t S[apt_plan::SK_N];
+    for (int k = 0; k < apt_plan::SK_N; k++) S[k] = piped ? pl->s_kind[k] : st;
+    // record on the producing kind's stream / wait on the consuming kind's stream (no-ops on one stream)
+    auto rec = [&](int kind, int sg) -> cudaError_t { return piped ? cudaEventRecord(pl->ev_seg[kind][sg], S[kind]) : cudaSuccess; };
+    auto wait = [&](int kind, int on, int sg) -> cudaError_t { return piped ? cudaStreamWaitEvent(S[kind], pl->ev_seg[on][sg], 0) : cudaSuccess; };
+
+    const Trk1Tab& tab = dbg ? pl->tab_all : pl->tab_modes;
+    float* nl_plane = dbg ? pl->d_nl_all.p : pl->d_nl.p;
+    float* n2_plane = out->noise_psd ? out->noise_psd : pl->d_n2.p;
+    uint32_t* hist = pl->d_hist.p;
+    const size_t hist_bytes = sizeof(uint32_t) * (size_t)n_clips * 2 * SEL_BINS;
     TdOut to;
     to.td = out->td ? out->td : pl->d_td.p; to.x_td = out->x_td; to.nF = pl->nF;
     to.want_block = out->td != nullptr; to.want_kurt = (out->td != nullptr) || d.has_ku;
-    pl->mark(APT_KERNEL_TD, st);
-    e = launch_td<PCM>(pl, b, pcm, to, st);
-    if (e != cudaSuccess) return fail(ctx, -11, "td launch failed: %s", cudaGetErrorString(e));
 
-    const int64_t fbeg = pl->frame_off[clip0], fend = pl->frame_off[clip0 + n_clips];
-    // tracker pass 1 on the mode bins (every band bin when one of its planes is requested)
-    const bool want_peaks = out->peak_ratio || out->peak_gate_score || out->peak_valid_count || out->peak_count_by_mode;
-    if (want_peaks && !(out->peak_ratio && out->peak_gate_score && out->peak_valid_count && out->peak_count_by_mode))
-        return fail(ctx, -35, "the four peak-feature buffers must be given together");
-    float* D_plane = out->D;
-    if (want_peaks && !D_plane) {   // the peak features read the detector input of every band bin
-        if (!pl->d_Dscr.p) CUDA_OK(ctx, pl->d_Dscr.alloc((size_t)pl->nF * d.K));
-        D_plane = pl->d_Dscr.p;
-    }
-    const bool dbg = out->det_noise_psd || out->det_noise_lag || D_plane;
-    const Trk1Tab& tab = dbg ? pl->tab_all : pl->tab_modes;
-    if (dbg && !pl->d_nl_all.p) CUDA_OK(ctx, pl->d_nl_all.alloc((size_t)pl->nF * pl->tab_all.nls));
-    float* nl_plane = dbg ? pl->d_nl_all.p : pl->d_nl.p;
-    pl->mark(APT_KERNEL_TRK1, st);
-    if (d.use_norm) {
-        Trk1IO io;
-        io.P_band = pl->d_Pband.p; io.NL = nl_plane; io.det_noise_psd = out->det_noise_psd; io.nF = pl->nF;
-        const int64_t lanes = (int64_t)n_clips * tab.n_lanes;
-        trk1_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, sc>>>(pl->dp, b, tab, io);
-        pl->last_launches++;
-        CUDA_OK(ctx, cudaGetLastError());
-    }
-    pl->mark(APT_KERNEL_FLUX, st);
-    {
-        FluxIO io;
-        io.P_band = pl->d_Pband.p; io.NL = nl_plane; io.nls = tab.nls; io.mf = pl->d_mf.p; io.stride = pl->mf_stride;
-        io.det_noise_lag = out->det_noise_lag; io.D = D_plane; io.mode_flux = out->mode_flux; io.nF = pl->nF;
-        const int64_t tiles = pl->flux_tile_off[clip0 + n_clips] - pl->flux_tile_off[clip0];
-        const size_t fsm = flux_smem_bytes(d.K, tab.n_lanes, tab.nls);
-        CUDA_OK(ctx, cudaFuncSetAttribute(flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-        flux_kernel<<<tile_grid(pl->flux_tile_off, clip0, n_clips), 256, fsm, sc>>>(pl->dp, b, pl->d_flux_tile_off.p, tab, io);
-        pl->last_launches++;
-        CUDA_OK(ctx, cudaGetLastError());
-    }
-    if (want_peaks) {
-        PeakIO pio;
-        pio.D = D_plane; pio.ratio = out->peak_ratio; pio.gate_score = out->peak_gate_score;
-        pio.valid_count = out->peak_valid_count; pio.count_by_mode = out->peak_count_by_mode; pio.nF = pl->nF;
-        int64_t maxT = 1;
-        for (int c = clip0; c < clip0 + n_clips; c++) maxT = std::max(maxT, pl->frame_off[c + 1] - pl->frame_off[c]);
-        peak_kernel<<<dim3((unsigned)((maxT + 127) / 128), (unsigned)n_clips), 128, 0, sc>>>(pl->dp, b, pio);
-        pl->last_launches++;
-        CUDA_OK(ctx, cudaGetLastError());
-    }
-    // float64 baselines + normalisation, then the decision and the event lists
-    pl->mark(APT_KERNEL_BASE, st);
-    {
-        const int64_t lanes = (int64_t)n_clips * (d.M + 1);
-        base_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, sc>>>(pl->dp, b, pl->d_mf.p, pl->mf_stride);
-        pl->last_launches++;
-        CUDA_OK(ctx, cudaGetLastError());
-    }
-    if (forked) {
-        CUDA_OK(ctx, cudaEventRecord(pl->ev_join, sc));
-        CUDA_OK(ctx, cudaStreamWaitEvent(st, pl->ev_join, 0));
-    }
-    pl->mark(APT_KERNEL_DECIDE, st);
-    {
-        DecIO io;
-        io.mf = pl->d_mf.p; io.stride = pl->mf_stride; io.td = to.td;
-        io.frame_class = out->frame_class; io.rain_conf = out->rain_conf; io.noise_conf = out->noise_conf;
-        io.norm_flux = out->norm_flux; io.score = out->score; io.gate = out->gate; io.nF = pl->nF;
-        decide_kernel<<<(unsigned)((fend - fbeg + 255) / 256), 256, 0, st>>>(pl->dp, fbeg, fend, io);
-        compact_kernel<<<(n_clips * 32 + 127) / 128, 128, 0, st>>>(b, out->frame_class, out->event_idx, out->event_count);
-        pl->last_launches += 2;
-        CUDA_OK(ctx, cudaGetLastError());
-    }
-    // tracker pass 2, noise-floor dB plane + level-0 histogram, then the exact median
-    uint32_t* hist = pl->d_hist.p;
-    const size_t hist_bytes = sizeof(uint32_t) * (size_t)n_clips * 2 * SEL_BINS;
+    // start of the run on the caller's stream: selection state and histograms, then the fork
     if (!d.suppressor_bypass) {
-        pl->mark(APT_KERNEL_TRK2, st);
-        float* n2_plane = out->noise_psd ? out->noise_psd : pl->d_db.p;   // dB plane is produced in place otherwise
+        CUDA_OK(ctx, cudaMemsetAsync(hist + (size_t)clip0 * 2 * SEL_BINS, 0, hist_bytes, st));
+        select_init_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(b, d.K, pl->d_sel.p);
+        pl->last_launches++;
+    }
+    if (piped) {
+        CUDA_OK(ctx, cudaEventRecord(pl->ev_fork, st));
+        for (int k = 0; k < apt_plan::SK_N; k++) CUDA_OK(ctx, cudaStreamWaitEvent(S[k], pl->ev_fork, 0));
+    }
+    int rc = 0;
+    cudaError_t e = cudaSuccess;
+    const char* what = "";
+#define RR(...) do { if (e == cudaSuccess) { e = (__VA_ARGS__); if (e != cudaSuccess) what = #__VA_ARGS__; } } while (0)
+    for (int sg = 0; sg < n_seg && e == cudaSuccess; sg++) {
+        Batch bs = b;
+        bs.ta = sg * seg_frames;
+        bs.tb = n_seg == 1 ? INT32_MAX : bs.ta + seg_frames;
+        // STFT
+        pl->mark(APT_KERNEL_STFT, st);
+        bs.tile0 = bs.ta / STFT_TF;
         {
+            const dim3 g = seg_grid(pl->stft_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / STFT_TF);
+            RR(pl->prm.fft_f64 ? launch_stft<double, PCM>(pl, bs, g, pcm, so, S[apt_plan::SK_STFT]) : launch_stft<float, PCM>(pl, bs, g, pcm, so, S[apt_plan::SK_STFT]));
+            RR(rec(apt_plan::SK_STFT, sg));
+        }
+        // TD features
+        pl->mark(APT_KERNEL_TD, st);
+        bs.tile0 = bs.ta / TD_FT;
+        {
+            const dim3 g = seg_grid(pl->td_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / TD_FT);
+            RR(launch_td<PCM>(pl, bs, g, pcm, to, S[apt_plan::SK_TD]));
+            RR(rec(apt_plan::SK_TD, sg));
+        }
+        // tracker pass 1 on the mode bins (every band bin when one of its planes is requested)
+        pl->mark(APT_KERNEL_TRK1, st);
+        if (d.use_norm) {
+            Trk1IO io;
+            io.P_band = pl->d_Pband.p; io.NL = nl_plane; io.det_noise_psd = out->det_noise_psd; io.nF = pl->nF;
+            io.state = pl->d_st_trk1.p; io.state_stride = pl->st_stride;
+            const int64_t lanes = (int64_t)n_clips * tab.n_lanes;
+            RR(wait(apt_plan::SK_TRK1, apt_plan::SK_STFT, sg));
+            if (e == cudaSuccess) {
+                trk1_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, S[apt_plan::SK_TRK1]>>>(pl->dp, bs, tab, io);
+                pl->last_launches++;
+                RR(cudaGetLastError());
+            }
+            RR(rec(apt_plan::SK_TRK1, sg));
+        }
+        // dB normalisation, flux, per-mode sums
+        pl->mark(APT_KERNEL_FLUX, st);
+        {
+            FluxIO io;
+            io.P_band = pl->d_Pband.p; io.NL = nl_plane; io.nls = tab.nls; io.mf = pl->d_mf.p; io.stride = pl->mf_stride;
+            io.det_noise_lag = out->det_noise_lag; io.D = D_plane; io.mode_flux = out->mode_flux; io.nF = pl->nF;
+            bs.tile0 = bs.ta / FLUX_FT;
+            const dim3 g = seg_grid(pl->flux_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / FLUX_FT);
+            const size_t fsm = flux_smem_bytes(d.K, tab.n_lanes, tab.nls);
+            RR(wait(apt_plan::SK_FLUX, d.use_norm ? apt_plan::SK_TRK1 : apt_plan::SK_STFT, sg));
+            if (g.x > 0 && e == cudaSuccess) {
+                RR(cudaFuncSetAttribute(flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+                if (e == cudaSuccess) {
+                    flux_kernel<<<g, 256, fsm, S[apt_plan::SK_FLUX]>>>(pl->dp, bs, pl->d_flux_tile_off.p, tab, io);
+                    pl->last_launches++;
+                    RR(cudaGetLastError());
+                }
+            }
+            RR(rec(apt_plan::SK_FLUX, sg));
+        }
+        // float64 baselines + normalisation
+        pl->mark(APT_KERNEL_BASE, st);
+        {
+            const int64_t lanes = (int64_t)n_clips * (d.M + 1);
+            RR(wait(apt_plan::SK_BASE, apt_plan::SK_FLUX, sg));
+            if (e == cudaSuccess) {
+                base_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, S[apt_plan::SK_BASE]>>>(pl->dp, bs, pl->d_mf.p, pl->mf_stride, pl->d_st_base.p);
+                pl->last_launches++;
+                RR(cudaGetLastError());
+            }
+            RR(rec(apt_plan::SK_BASE, sg));
+        }
+        // decision
+        pl->mark(APT_KERNEL_DECIDE, st);
+        {
+            DecIO io;
+            io.mf = pl->d_mf.p; io.stride = pl->mf_stride; io.td = to.td; io.gate_in = nullptr;
+            io.frame_class = out->frame_class; io.rain_conf = out->rain_conf; io.noise_conf = out->noise_conf;
+            io.norm_flux = out->norm_flux; io.score = out->score; io.gate = out->gate; io.nF = pl->nF;
+            const int64_t fr = std::min<int64_t>(maxT - bs.ta, n_seg == 1 ? maxT : seg_frames);
+            RR(wait(apt_plan::SK_DEC, apt_plan::SK_BASE, sg));
+            RR(wait(apt_plan::SK_DEC, apt_plan::SK_TD, sg));
+            if (fr > 0 && e == cudaSuccess) {
+                decide_kernel<<<dim3((unsigned)((fr + 255) / 256), (unsigned)n_clips), 256, 0, S[apt_plan::SK_DEC]>>>(pl->dp, bs, io);
+                pl->last_launches++;
+                RR(cudaGetLastError());
+            }
+            RR(rec(apt_plan::SK_DEC, sg));
+        }
+        if (!d.suppressor_bypass) {
+            // tracker pass 2, then the noise-floor dB sums and histogram of the segment
+            pl->mark(APT_KERNEL_TRK2, st);
             Trk2IO io;
             io.P_band = pl->d_Pband.p; io.frame_class = out->frame_class; io.N2 = n2_plane; io.nF = pl->nF;
+            io.state = pl->d_st_trk2.p; io.state_stride = pl->st_stride;
             const int64_t lanes = (int64_t)n_clips * d.K;
             // Every lane runs the whole time chain, so the kernel's time is (waves of CTAs) x (chain time at that
             // residency); measured per frame step: ~170 cycles up to 4 warps/SM, 185 at 8, 228 at 12, and a cliff
             // beyond (profiles/r1).  The default is 128-thread CTAs, three per SM (registers).
             // When the launch holds 12..16 warps per SM that leaves a short second wave after a full first one;
             // two even waves of one 256-thread CTA per SM (unused dynamic shared memory as the occupancy limiter)
-            // are faster there (1 000 x 71 lanes: 10.8 -> 9.7 ms).
+            // are faster there when the kernel has the GPU to itself (1 000 x 71 lanes: 10.8 -> 9.7 ms).
             const double warps_per_sm = (double)((lanes + 31) / 32) / (double)std::max(1, ctx->sm_count);
-            if (warps_per_sm > 12.0 && warps_per_sm <= 16.0) {
-                CUDA_OK(ctx, cudaFuncSetAttribute(trk2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-                trk2_kernel<256><<<(unsigned)((lanes + 255) / 256), 256, 120 * 1024, st>>>(pl->dp, b, io);
-            } else {
-                trk2_kernel<128><<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, io);
+            RR(wait(apt_plan::SK_TRK2, apt_plan::SK_DEC, sg));
+            if (e == cudaSuccess) {
+                if (!piped && warps_per_sm > 12.0 && warps_per_sm <= 16.0) {
+                    RR(cudaFuncSetAttribute(trk2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+                    if (e == cudaSuccess) trk2_kernel<256><<<(unsigned)((lanes + 255) / 256), 256, 120 * 1024, S[apt_plan::SK_TRK2]>>>(pl->dp, bs, io);
+                } else {
+                    trk2_kernel<128><<<(unsigned)((lanes + 127) / 128), 128, 0, S[apt_plan::SK_TRK2]>>>(pl->dp, bs, io);
+                }
+                pl->last_launches++;
+                RR(cudaGetLastError());
             }
-            pl->last_launches++;
-            CUDA_OK(ctx, cudaGetLastError());
+            RR(rec(apt_plan::SK_TRK2, sg));
+            pl->mark(APT_KERNEL_DB, st);
+            bs.tile0 = bs.ta / DB_CF;
+            const dim3 g = seg_grid(pl->sel_chunk_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / DB_CF);
+            RR(wait(apt_plan::SK_DBS, apt_plan::SK_TRK2, sg));
+            if (g.x > 0 && e == cudaSuccess) {
+                dbsum_kernel<<<g, 256, 0, S[apt_plan::SK_DBS]>>>(pl->dp, bs, n2_plane, pl->d_sel_chunk_off.p, hist, pl->d_dbsum.p);
+                pl->last_launches++;
+                RR(cudaGetLastError());
+            }
+            RR(rec(apt_plan::SK_DBS, sg));
         }
-        if (out->G || out->S_hat || out->y) {
+    }
+    // join: the last event of the last kind covers everything before it (each kind's stream is in segment order and
+    // waits for its producer kind)
+    if (piped) {
+        const int last_kind = d.suppressor_bypass ? apt_plan::SK_DEC : apt_plan::SK_DBS;
+        cudaError_t ej = cudaStreamWaitEvent(st, pl->ev_seg[last_kind][n_seg - 1], 0);
+        if (e != cudaSuccess || ej != cudaSuccess) {
+            // something failed after the fork: drain the side streams before reporting, so that nothing of this call is
+            // still writing the caller's buffers when the error reaches it
+            for (int k = 0; k < apt_plan::SK_N; k++) cudaStreamSynchronize(S[k]);
+            if (e == cudaSuccess) { e = ej; what = "cudaStreamWaitEvent(join)"; }
+        }
+    }
+    if (e != cudaSuccess) return fail(ctx, -11, "%s failed: %s", what, cudaGetErrorString(e));
+#undef RR
+    (void)rc;
+    // ---- tail on the caller's stream, whole clips
+    Batch bw = b;
+    if (want_peaks) {
+        PeakIO pio;
+        pio.D = D_plane; pio.ratio = out->peak_ratio; pio.gate_score = out->peak_gate_score;
+        pio.valid_count = out->peak_valid_count; pio.count_by_mode = out->peak_count_by_mode; pio.nF = pl->nF;
+        peak_kernel<<<dim3((unsigned)((maxT + 127) / 128), (unsigned)n_clips), 128, 0, st>>>(pl->dp, bw, pio);
+        pl->last_launches++;
+        CUDA_OK(ctx, cudaGetLastError());
+    }
+    pl->mark(APT_KERNEL_DECIDE, st);
+    compact_kernel<<<(n_clips * 32 + 127) / 128, 128, 0, st>>>(bw, out->frame_class, out->event_idx, out->event_count);
+    pl->last_launches++;
+    CUDA_OK(ctx, cudaGetLastError());
+    if (!d.suppressor_bypass) {
+        if (want_gain) {
             pl->mark(APT_KERNEL_GAIN, st);
-            if (!out->G) return fail(ctx, -33, "S_hat / y require the G buffer");
-            if (out->y && !out->S_hat) return fail(ctx, -33, "y requires the S_hat buffer");
-            if (out->S_hat && !out->S) return fail(ctx, -33, "S_hat requires the S buffer");
             GainIO gio;
             gio.P_band = pl->d_Pband.p; gio.N2 = n2_plane; gio.frame_class = out->frame_class; gio.G = out->G;
             gio.ratio_med = out->ratio_med; gio.nF = pl->nF;
-            gain_kernel<<<tile_grid(pl->flux_tile_off, clip0, n_clips), 256, 0, st>>>(pl->dp, b, pl->d_flux_tile_off.p, gio);
+            gain_kernel<<<seg_grid(pl->flux_tile_off, clip0, n_clips, 0, INT64_MAX), 256, 0, st>>>(pl->dp, bw, pl->d_flux_tile_off.p, gio);
             const int64_t lanes = (int64_t)n_clips * d.K;
-            gain_time_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, b, out->frame_class, out->G);
+            gain_time_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, bw, out->frame_class, out->G);
             pl->last_launches += 2;
             if (out->S_hat) {
+                const int64_t fbeg = pl->frame_off[clip0], fend = pl->frame_off[clip0 + n_clips];
                 const int64_t n = (fend - fbeg) * d.F;
                 shat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pl->dp, fbeg, fend, out->G, out->S, out->S_hat);
                 pl->last_launches++;
@@ -709,32 +874,30 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
                 int64_t max_n = 1;
                 for (int c = clip0; c < clip0 + n_clips; c++) max_n = std::max(max_n, pl->len[c]);
                 const dim3 grid((unsigned)((max_n + ISTFT_TH * 128 - 1) / (ISTFT_TH * 128)), (unsigned)n_clips);
-                istft256_kernel<<<grid, ISTFT_NT, 0, st>>>(pl->dp, b, out->S_hat, pl->d_win64.p, pl->d_tw256_64.p, out->y);
+                istft256_kernel<<<grid, ISTFT_NT, 0, st>>>(pl->dp, bw, out->S_hat, pl->d_win64.p, pl->d_tw256_64.p, out->y);
                 pl->last_launches++;
             }
             CUDA_OK(ctx, cudaGetLastError());
         }
-        pl->mark(APT_KERNEL_DB, st);
-        const int64_t chunks = pl->sel_chunk_off[clip0 + n_clips] - pl->sel_chunk_off[clip0];
-        CUDA_OK(ctx, cudaMemsetAsync(hist + (size_t)clip0 * 2 * SEL_BINS, 0, hist_bytes, st));
-        select_init_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(b, d.K, pl->d_sel.p);
-        db_kernel<<<tile_grid(pl->sel_chunk_off, clip0, n_clips), 256, 0, st>>>(pl->dp, b, n2_plane, pl->d_db.p, pl->d_sel_chunk_off.p, hist, pl->d_dbsum.p);
-        pl->last_launches += 2;
-        CUDA_OK(ctx, cudaGetLastError());
+        // exact median: bins of the two middle ranks, candidates of those bins, select inside the candidates;
+        // clips whose candidates overflow go through the full 3-level radix select (no-ops for the others)
         pl->mark(APT_KERNEL_SELECT, st);
+        const dim3 gall = seg_grid(pl->sel_chunk_off, clip0, n_clips, 0, INT64_MAX);
+        sel_scan0_kernel<<<(n_clips * 32 + 127) / 128, 128, 0, st>>>(clip0, n_clips, pl->d_sel.p, hist);
+        sel_collect_kernel<<<gall, 256, 0, st>>>(pl->dp, bw, n2_plane, pl->d_sel_chunk_off.p, pl->d_sel.p, pl->d_cand_off.p, pl->d_cand.p);
+        sel_final_kernel<<<n_clips, 256, 0, st>>>(clip0, pl->d_sel.p, pl->d_cand_off.p, pl->d_cand.p);
+        pl->last_launches += 3;
+        CUDA_OK(ctx, cudaGetLastError());
         for (int level = 0; level < 3; level++) {
-            if (level > 0) {
-                CUDA_OK(ctx, cudaMemsetAsync(hist + (size_t)clip0 * 2 * SEL_BINS, 0, hist_bytes, st));
-                select_hist_kernel<<<tile_grid(pl->sel_chunk_off, clip0, n_clips), 256, 0, st>>>(b, d.K, pl->d_db.p, pl->d_sel_chunk_off.p, level, pl->d_sel.p, hist);
-                pl->last_launches++;
-            }
+            CUDA_OK(ctx, cudaMemsetAsync(hist + (size_t)clip0 * 2 * SEL_BINS, 0, hist_bytes, st));
+            select_hist_kernel<<<gall, 256, 0, st>>>(pl->dp, bw, n2_plane, pl->d_sel_chunk_off.p, level, pl->d_sel.p, hist);
             select_scan_kernel<<<(n_clips * 32 + 127) / 128, 128, 0, st>>>(clip0, n_clips, level, pl->d_sel.p, hist);
-            pl->last_launches++;
+            pl->last_launches += 2;
         }
         CUDA_OK(ctx, cudaGetLastError());
     }
     pl->mark(APT_KERNEL_FINALIZE, st);
-    finalize_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(pl->dp, b, pl->d_sel.p, pl->d_dbsum.p, pl->d_sel_chunk_off.p, out->event_count, out->clip_stats, 0);
+    finalize_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(pl->dp, bw, pl->d_sel.p, pl->d_dbsum.p, pl->d_sel_chunk_off.p, out->event_count, out->clip_stats, 0);
     pl->last_launches++;
     CUDA_OK(ctx, cudaGetLastError());
     pl->mark(-1, st);
@@ -748,7 +911,7 @@ int apt_run_i16(apt_plan_t* plan, int stages, const int16_t* dev_pcm, const apt_
     if (!dev_pcm || !out) return fail(plan->ctx, -1, "apt_run_i16: null buffer");
     CUDA_OK(plan->ctx, cudaSetDevice(plan->ctx->device));
     plan->last_launches = 0;
-    return run_range<int16_t>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream, true);
+    return run_range<int16_t>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream);
 }
 
 int apt_run_f32(apt_plan_t* plan, int stages, const float* dev_pcm, const apt_out_t* out, void* stream) {
@@ -756,18 +919,31 @@ int apt_run_f32(apt_plan_t* plan, int stages, const float* dev_pcm, const apt_ou
     if (!dev_pcm || !out) return fail(plan->ctx, -1, "apt_run_f32: null buffer");
     CUDA_OK(plan->ctx, cudaSetDevice(plan->ctx->device));
     plan->last_launches = 0;
-    return run_range<float>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream, true);
+    return run_range<float>(plan, stages, 0, plan->n_clips, dev_pcm, out, (cudaStream_t)stream);
 }
 
-int apt_run_host_i16(apt_plan_t* pl, const int16_t* host_pcm, int8_t* frame_class, float* rain_conf, float* noise_conf,
-                     int32_t* event_idx, int32_t* event_count, float* clip_stats) {
-    if (!pl) return -1;
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// End-to-end host paths.  Clip groups: group g+1 travels host->device on the copy stream while earlier
+// groups compute; each group's results go back on its own compute stream (the device->host copy engine
+// is separate from the host->device one).  `feed(g, c0, c1, dst_dev, bytes)` enqueues the host->device
+// copy of group g on s_copy (and does whatever host-side staging it needs first).
+// ---------------------------------------------------------------------------------------------
+struct HostOut {
+    int8_t* frame_class; float* rain_conf; float* noise_conf; int32_t* event_idx; int32_t* event_count; float* clip_stats;
+};
+
+static int host_groups(const apt_plan* pl) {
+    int want_groups = 24;
+    if (const char* e = getenv("APT_HOST_GROUPS")) want_groups = std::max(1, atoi(e));
+    return std::min(pl->n_clips, want_groups);
+}
+
+template <typename PCM, typename Feed>
+static int run_host_impl(apt_plan* pl, PCM* d_pcm, Feed feed, const HostOut& ho) {
     apt_ctx* ctx = pl->ctx;
-    if (!host_pcm) return fail(ctx, -1, "apt_run_host_i16: null PCM");
-    CUDA_OK(ctx, cudaSetDevice(ctx->device));
-    pl->last_launches = 0;
-    if (!pl->d_pcm.p) {
-        CUDA_OK(ctx, pl->d_pcm.alloc((size_t)pl->nS));
+    if (!pl->d_fc.p) {
         CUDA_OK(ctx, pl->d_fc.alloc((size_t)pl->nF)); CUDA_OK(ctx, pl->d_rc.alloc((size_t)pl->nF)); CUDA_OK(ctx, pl->d_nc.alloc((size_t)pl->nF));
         CUDA_OK(ctx, pl->d_ev.alloc((size_t)pl->nF)); CUDA_OK(ctx, pl->d_evc.alloc((size_t)pl->n_clips));
         CUDA_OK(ctx, pl->d_stats.alloc((size_t)pl->n_clips * APT_N_CLIP_STATS));
@@ -776,45 +952,197 @@ int apt_run_host_i16(apt_plan_t* pl, const int16_t* host_pcm, int8_t* frame_clas
     memset(&o, 0, sizeof(o));
     o.frame_class = pl->d_fc.p; o.rain_conf = pl->d_rc.p; o.noise_conf = pl->d_nc.p;
     o.event_idx = pl->d_ev.p; o.event_count = pl->d_evc.p; o.clip_stats = pl->d_stats.p;
-    // Clip groups: group g+1 travels host->device on the copy stream while earlier groups compute.  Groups
-    // alternate over N_COMP compute streams so that the latency-bound serial kernels of one group (few warps,
-    // fixed duration whatever the group size) overlap the wide kernels of its neighbours; each group's results
-    // go back on its own compute stream (the device->host copy engine is separate from the host->device one).
-    int want_groups = 24;
-    if (const char* e = getenv("APT_HOST_GROUPS")) want_groups = std::max(1, atoi(e));
-    const int n_groups = std::min(pl->n_clips, want_groups);
+    const int n_groups = host_groups(pl);
     std::vector<cudaEvent_t> ev(n_groups, nullptr);
     const bool was_timing = pl->timing;
     pl->timing = false;   // per-kernel event marks assume one stream
     int rc = 0;
-    for (int g = 0; g < n_groups && rc == 0; g++) {
+    cudaError_t ce = cudaSuccess;
+    const char* what = "";
+#define HP(...) do { if (ce == cudaSuccess) { ce = (__VA_ARGS__); if (ce != cudaSuccess) what = #__VA_ARGS__; } } while (0)
+    for (int g = 0; g < n_groups && rc == 0 && ce == cudaSuccess; g++) {
         const int c0 = (int)((int64_t)pl->n_clips * g / n_groups), c1 = (int)((int64_t)pl->n_clips * (g + 1) / n_groups);
         const int64_t s0 = pl->samp_off[c0], s1 = pl->samp_off[c1];
         const int64_t f0 = pl->frame_off[c0], f1 = pl->frame_off[c1];
         cudaStream_t sc = pl->s_comp[g % apt_plan::N_COMP];
-        cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming);
-        cudaMemcpyAsync(pl->d_pcm.p + s0, host_pcm + s0, (size_t)(s1 - s0) * sizeof(int16_t), cudaMemcpyHostToDevice, pl->s_copy);
-        cudaEventRecord(ev[g], pl->s_copy);
-        cudaStreamWaitEvent(sc, ev[g], 0);
-        rc = run_range<int16_t>(pl, APT_STAGE_FULL, c0, c1 - c0, pl->d_pcm.p, &o, sc);
+        HP(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
+        HP(feed(g, c0, c1, d_pcm + s0, (size_t)(s1 - s0) * sizeof(PCM)));
+        HP(cudaEventRecord(ev[g], pl->s_copy));
+        HP(cudaStreamWaitEvent(sc, ev[g], 0));
+        if (ce != cudaSuccess) break;
+        rc = run_range<PCM>(pl, APT_STAGE_FULL, c0, c1 - c0, d_pcm, &o, sc, 8);
         if (rc != 0) break;
-        if (frame_class) cudaMemcpyAsync(frame_class + f0, pl->d_fc.p + f0, (size_t)(f1 - f0), cudaMemcpyDeviceToHost, sc);
-        if (rain_conf) cudaMemcpyAsync(rain_conf + f0, pl->d_rc.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, sc);
-        if (noise_conf) cudaMemcpyAsync(noise_conf + f0, pl->d_nc.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, sc);
-        if (event_idx) cudaMemcpyAsync(event_idx + f0, pl->d_ev.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, sc);
-        if (event_count) cudaMemcpyAsync(event_count + c0, pl->d_evc.p + c0, (size_t)(c1 - c0) * 4, cudaMemcpyDeviceToHost, sc);
-        if (clip_stats) cudaMemcpyAsync(clip_stats + (size_t)c0 * APT_N_CLIP_STATS, pl->d_stats.p + (size_t)c0 * APT_N_CLIP_STATS,
-                                        (size_t)(c1 - c0) * APT_N_CLIP_STATS * 4, cudaMemcpyDeviceToHost, sc);
+        if (ho.frame_class) HP(cudaMemcpyAsync(ho.frame_class + f0, pl->d_fc.p + f0, (size_t)(f1 - f0), cudaMemcpyDeviceToHost, sc));
+        if (ho.rain_conf) HP(cudaMemcpyAsync(ho.rain_conf + f0, pl->d_rc.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, sc));
+        if (ho.noise_conf) HP(cudaMemcpyAsync(ho.noise_conf + f0, pl->d_nc.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, sc));
+        if (ho.event_idx) HP(cudaMemcpyAsync(ho.event_idx + f0, pl->d_ev.p + f0, (size_t)(f1 - f0) * 4, cudaMemcpyDeviceToHost, sc));
+        if (ho.event_count) HP(cudaMemcpyAsync(ho.event_count + c0, pl->d_evc.p + c0, (size_t)(c1 - c0) * 4, cudaMemcpyDeviceToHost, sc));
+        if (ho.clip_stats) HP(cudaMemcpyAsync(ho.clip_stats + (size_t)c0 * APT_N_CLIP_STATS, pl->d_stats.p + (size_t)c0 * APT_N_CLIP_STATS,
+                                              (size_t)(c1 - c0) * APT_N_CLIP_STATS * 4, cudaMemcpyDeviceToHost, sc));
     }
-    cudaError_t e0 = cudaStreamSynchronize(pl->s_copy), e1 = cudaSuccess, e2 = cudaSuccess;
+#undef HP
+    // always drain every stream this call touched, whatever failed above: the caller's buffers must not be written
+    // to after we return
+    cudaError_t e0 = cudaStreamSynchronize(pl->s_copy), e1 = cudaSuccess;
     for (int i = 0; i < apt_plan::N_COMP; i++) { cudaError_t e = cudaStreamSynchronize(pl->s_comp[i]); if (e != cudaSuccess) e1 = e; }
+    for (int k = 0; k < apt_plan::SK_N; k++) if (pl->s_kind[k]) { cudaError_t e = cudaStreamSynchronize(pl->s_kind[k]); if (e != cudaSuccess) e1 = e; }
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     pl->timing = was_timing;
     if (rc != 0) return rc;
+    if (ce != cudaSuccess) return fail(ctx, -12, "host path: %s failed: %s", what, cudaGetErrorString(ce));
     if (e0 != cudaSuccess) return fail(ctx, -12, "copy stream: %s", cudaGetErrorString(e0));
     if (e1 != cudaSuccess) return fail(ctx, -12, "compute stream: %s", cudaGetErrorString(e1));
-    if (e2 != cudaSuccess) return fail(ctx, -12, "return stream: %s", cudaGetErrorString(e2));
     return 0;
+}
+
+// Staging of pageable clips into the pinned ring: `n_thr` helper threads copy each group's bytes in equal shares
+// (a share may span several clips), one group at a time, released by the main thread (which waits for the slot's
+// previous host->device copy first).
+struct StagePool {
+    const apt_plan* pl;
+    const void* const* clips;
+    size_t esz;
+    int n_groups, n_thr;
+    std::mutex mu;
+    std::condition_variable cv;
+    int go = 0;                       // groups released so far
+    std::vector<int> done;            // helper threads finished with group g
+    std::vector<std::thread> th;
+    bool stop = false;
+
+    void copy_share(int g, int tid) {
+        const int n_clips = pl->n_clips;
+        const int c0 = (int)((int64_t)n_clips * g / n_groups), c1 = (int)((int64_t)n_clips * (g + 1) / n_groups);
+        const int64_t s0 = pl->samp_off[c0], total = pl->samp_off[c1] - s0;
+        // shares are cut on 4 KiB boundaries of the group's byte range
+        const int64_t bytes = total * (int64_t)esz;
+        const int64_t pages = (bytes + 4095) / 4096;
+        const int64_t b0 = std::min(bytes, pages * tid / n_thr * 4096), b1 = std::min(bytes, pages * (tid + 1) / n_thr * 4096);
+        if (b1 <= b0) return;
+        char* dst = (char*)pl->ring[g % apt_plan::N_RING];
+        // first clip whose byte range reaches b0
+        int c = (int)(std::upper_bound(pl->samp_off.begin() + c0, pl->samp_off.begin() + c1 + 1, s0 + b0 / (int64_t)esz) - pl->samp_off.begin()) - 1;
+        int64_t pos = b0;
+        while (pos < b1 && c < c1) {
+            const int64_t cb0 = (pl->samp_off[c] - s0) * (int64_t)esz, cb1 = (pl->samp_off[c + 1] - s0) * (int64_t)esz;
+            const int64_t e = std::min(b1, cb1);
+            if (e > pos) memcpy(dst + pos, (const char*)clips[c] + (pos - cb0), (size_t)(e - pos));
+            pos = e;
+            c++;
+        }
+    }
+    void worker(int tid) {
+        for (int g = 0; g < n_groups; g++) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return go > g || stop; });
+                if (stop) return;
+            }
+            copy_share(g, tid);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                done[g]++;
+            }
+            cv.notify_all();
+        }
+    }
+    void start() {
+        done.assign(n_groups, 0);
+        for (int i = 0; i < n_thr; i++) th.emplace_back([this, i] { worker(i); });
+    }
+    void release_and_wait(int g) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            go = g + 1;
+        }
+        cv.notify_all();
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return done[g] == n_thr; });
+    }
+    void finish() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+        th.clear();
+    }
+};
+
+template <typename PCM>
+static int run_host_clips_impl(apt_plan* pl, const void* const* clips, const HostOut& ho) {
+    apt_ctx* ctx = pl->ctx;
+    const int n_groups = host_groups(pl);
+    size_t max_bytes = 0;
+    for (int g = 0; g < n_groups; g++) {
+        const int c0 = (int)((int64_t)pl->n_clips * g / n_groups), c1 = (int)((int64_t)pl->n_clips * (g + 1) / n_groups);
+        max_bytes = std::max(max_bytes, (size_t)(pl->samp_off[c1] - pl->samp_off[c0]) * sizeof(PCM));
+    }
+    if (pl->ring_bytes < max_bytes) {
+        for (int i = 0; i < apt_plan::N_RING; i++) { if (pl->ring[i]) cudaFreeHost(pl->ring[i]); pl->ring[i] = nullptr; }
+        pl->ring_bytes = 0;
+        for (int i = 0; i < apt_plan::N_RING; i++) CUDA_OK(ctx, cudaHostAlloc(&pl->ring[i], max_bytes, cudaHostAllocDefault));
+        pl->ring_bytes = max_bytes;
+    }
+    PCM* d_pcm;
+    if constexpr (sizeof(PCM) == 2) { if (!pl->d_pcm.p) CUDA_OK(ctx, pl->d_pcm.alloc((size_t)pl->nS)); d_pcm = pl->d_pcm.p; }
+    else { if (!pl->d_pcm_f32.p) CUDA_OK(ctx, pl->d_pcm_f32.alloc((size_t)pl->nS)); d_pcm = pl->d_pcm_f32.p; }
+    int n_thr = (int)std::thread::hardware_concurrency();
+    n_thr = std::max(1, std::min(16, n_thr > 2 ? n_thr / 2 : 1));
+    if (const char* e = getenv("APT_STAGE_THREADS")) n_thr = std::max(1, std::min(64, atoi(e)));
+    StagePool pool;
+    pool.pl = pl; pool.clips = clips; pool.esz = sizeof(PCM); pool.n_groups = n_groups; pool.n_thr = n_thr;
+    pool.start();
+    std::vector<cudaEvent_t> slot_free(n_groups, nullptr);   // recorded after the host->device copy of group g
+    auto feed = [&](int g, int, int, PCM* dst, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaSuccess;
+        if (g >= apt_plan::N_RING) {   // the slot's previous copy must have left the pinned buffer
+            e = cudaEventSynchronize(slot_free[g - apt_plan::N_RING]);
+            if (e != cudaSuccess) return e;
+        }
+        pool.release_and_wait(g);
+        e = cudaMemcpyAsync(dst, pl->ring[g % apt_plan::N_RING], bytes, cudaMemcpyHostToDevice, pl->s_copy);
+        if (e != cudaSuccess) return e;
+        e = cudaEventCreateWithFlags(&slot_free[g], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(slot_free[g], pl->s_copy);
+    };
+    const int rc = run_host_impl<PCM>(pl, d_pcm, feed, ho);
+    pool.finish();
+    for (auto& e : slot_free) if (e) cudaEventDestroy(e);
+    return rc;
+}
+
+extern "C" {
+
+int apt_run_host_i16(apt_plan_t* pl, const int16_t* host_pcm, int8_t* frame_class, float* rain_conf, float* noise_conf,
+                     int32_t* event_idx, int32_t* event_count, float* clip_stats) {
+    if (!pl) return -1;
+    apt_ctx* ctx = pl->ctx;
+    if (!host_pcm) return fail(ctx, -1, "apt_run_host_i16: null PCM");
+    if (!pl->full_ok) return fail(ctx, -34, "apt_run_host_i16: the plan's STFT geometry supports the features stage only");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    pl->last_launches = 0;
+    if (!pl->d_pcm.p) CUDA_OK(ctx, pl->d_pcm.alloc((size_t)pl->nS));
+    const HostOut ho{frame_class, rain_conf, noise_conf, event_idx, event_count, clip_stats};
+    auto feed = [&](int, int c0, int, int16_t* dst, size_t bytes) -> cudaError_t {
+        return cudaMemcpyAsync(dst, host_pcm + pl->samp_off[c0], bytes, cudaMemcpyHostToDevice, pl->s_copy);
+    };
+    return run_host_impl<int16_t>(pl, pl->d_pcm.p, feed, ho);
+}
+
+int apt_run_host_clips(apt_plan_t* pl, const void* const* clip_ptrs, int is_f32, int8_t* frame_class, float* rain_conf,
+                       float* noise_conf, int32_t* event_idx, int32_t* event_count, float* clip_stats) {
+    if (!pl) return -1;
+    apt_ctx* ctx = pl->ctx;
+    if (!clip_ptrs) return fail(ctx, -1, "apt_run_host_clips: null clip table");
+    for (int c = 0; c < pl->n_clips; c++) if (!clip_ptrs[c]) return fail(ctx, -1, "apt_run_host_clips: clip %d is null", c);
+    if (!pl->full_ok) return fail(ctx, -34, "apt_run_host_clips: the plan's STFT geometry supports the features stage only");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    pl->last_launches = 0;
+    const HostOut ho{frame_class, rain_conf, noise_conf, event_idx, event_count, clip_stats};
+    return is_f32 ? run_host_clips_impl<float>(pl, clip_ptrs, ho) : run_host_clips_impl<int16_t>(pl, clip_ptrs, ho);
 }
 
 }  // extern "C"

@@ -85,14 +85,17 @@ struct Batch {
     int clip0, n_clips;
     const int64_t* samp_off;   // [plan clips + 1]
     const int64_t* frame_off;  // [plan clips + 1]
+    int tile0;                 // first tile of every clip this launch covers (tiled kernels)
+    int ta, tb;                // clip-local frame range [ta, tb) this launch covers (serial / per-frame kernels)
 };
 
 // tile -> clip: tiled kernels launch a 2-D grid, blockIdx.y = clip of the launch's range, blockIdx.x = tile
 // inside the clip (grid.x = the largest tile count of the range; surplus CTAs of shorter clips exit at
 // once).  tile_off is the plan's absolute prefix array of tiles per clip.  No search, no per-tile table.
+// A launch may cover only the tiles [b.tile0, b.tile0 + gridDim.x) of every clip (one time segment of the pipelined run).
 __device__ __forceinline__ bool tile_clip(const Batch& b, const int64_t* __restrict__ tile_off, int& c, int64_t& tile_in_clip) {
     c = b.clip0 + (int)blockIdx.y;
-    tile_in_clip = blockIdx.x;
+    tile_in_clip = (int64_t)b.tile0 + blockIdx.x;
     return tile_in_clip < __ldg(tile_off + c + 1) - __ldg(tile_off + c);
 }
 
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(STFTG_NT) stft_generic_kernel(const __grid_con
     const int64_t Ns = __ldg(b.samp_off + c + 1) - base;
     const int64_t f0 = __ldg(b.frame_off + c);
     const int T_clip = (int)(__ldg(b.frame_off + c + 1) - f0);
-    const int t0 = blockIdx.x * fpc;
+    const int t0 = (b.tile0 + (int)blockIdx.x) * fpc;
     if (t0 >= T_clip) return;
     const int nfr = min(fpc, T_clip - t0);
     // windowed frames, centre-padded with zeros (librosa center=True, pad_mode="constant")
@@ -1126,8 +1129,11 @@ struct Trk1Tab {
 // the end of the batch repeat the last real lane's arithmetic with their stores switched off, so that
 // every lane of a warp always has a valid clip (no divergence in the main loop).
 struct SerialLane {
-    int c, sub, T, Tmin, Tmax;
+    int c, sub, T;
+    int t_end;          // min(T, b.tb): this lane's frames of the launch are [max(b.ta, first), t_end)
+    int emin, emax;     // smallest / largest t_end of the warp (uniform loop bounds)
     int64_t f0;
+    int64_t gl;         // global lane index inside the launch's clip range (state slot)
     bool store;
 };
 __device__ __forceinline__ SerialLane serial_lane(const Batch& b, int per_clip) {
@@ -1136,18 +1142,20 @@ __device__ __forceinline__ SerialLane serial_lane(const Batch& b, int per_clip) 
     int64_t gl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     L.store = gl < total;
     if (gl >= total) gl = total - 1;
+    L.gl = gl;
     const int ci = (int)(gl / per_clip);
     L.sub = (int)(gl - (int64_t)ci * per_clip);
     L.c = b.clip0 + ci;
     L.f0 = __ldg(b.frame_off + L.c);
     L.T = (int)(__ldg(b.frame_off + L.c + 1) - L.f0);
-    int mn = L.T, mx = L.T;
+    L.t_end = min(L.T, b.tb);
+    int mn = L.t_end, mx = L.t_end;
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
         mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     }
-    L.Tmin = mn; L.Tmax = mx;
+    L.emin = mn; L.emax = mx;
     return L;
 }
 
@@ -1155,9 +1163,12 @@ struct Trk1IO {
     const float* P_band;   // [nF][K]
     float* NL;             // [nF][nls] lagged, clamped pass-1 noise of the tracked bins
     float* det_noise_psd;  // optional [nF][K]
+    float4* state;         // [plan clips][state_stride]: (trk, ts, nprev, -) carried between time segments
+    int state_stride;
     int64_t nF;
 };
 
+// Frames [b.ta, b.tb) of every lane; ta == 0 starts the recursion (frame 0: N = P), ta > 0 resumes from `state`.
 __global__ void __launch_bounds__(128) trk1_kernel(const __grid_constant__ DevParams p, Batch b,
                                                    const __grid_constant__ Trk1Tab tab, Trk1IO io) {
     const SerialLane L = serial_lane(b, tab.n_lanes);
@@ -1166,24 +1177,29 @@ __global__ void __launch_bounds__(128) trk1_kernel(const __grid_constant__ DevPa
     const float* Pk = io.P_band + L.f0 * K + kb;
     float* NLk = io.NL + L.f0 * nls + L.sub;
     float* N1k = io.det_noise_psd ? io.det_noise_psd + L.f0 * K + kb : nullptr;
-    const int T = L.T;
+    float4* stp = io.state + (size_t)L.c * io.state_stride + L.sub;
+    const int te = L.t_end;
     Tracker tr = {0, 0, 0};
-    // frame 0 (rain_signal_processor.py:700-703): N = P
-    {
+    if (b.ta == 0) {
+        // frame 0 (rain_signal_processor.py:700-703): N = P
         const float pk = __ldg(Pk);
         const float n1 = tracker_first(p, tr, pk);
         if (L.store) { NLk[0] = f_min(n1, p.trk_maxr * pk); if (N1k) N1k[0] = n1; }
+    } else {
+        const float4 st = *stp;
+        tr.trk = st.x; tr.ts = st.y; tr.nprev = st.z;
     }
+    int t = max(b.ta, 1);
+    const int tl = max(te - 1, 0);   // last frame this lane may read
     float pbuf[SEQ_PF];
 #pragma unroll
-    for (int u = 0; u < SEQ_PF; u++) pbuf[u] = __ldg(Pk + (uint32_t)(min(1 + u, T - 1) * K));
-    int t = 1;
-    for (; t + SEQ_PF <= L.Tmin; t += SEQ_PF) {
+    for (int u = 0; u < SEQ_PF; u++) pbuf[u] = __ldg(Pk + (uint32_t)(min(t + u, tl) * K));
+    for (; t + SEQ_PF <= L.emin; t += SEQ_PF) {
         float pc[SEQ_PF];
 #pragma unroll
         for (int u = 0; u < SEQ_PF; u++) pc[u] = pbuf[u];
 #pragma unroll
-        for (int u = 0; u < SEQ_PF; u++) pbuf[u] = __ldg(Pk + (uint32_t)(min(t + SEQ_PF + u, T - 1) * K));
+        for (int u = 0; u < SEQ_PF; u++) pbuf[u] = __ldg(Pk + (uint32_t)(min(t + SEQ_PF + u, tl) * K));
 #pragma unroll
         for (int u = 0; u < SEQ_PF; u++) {
             const float pk = pc[u];
@@ -1193,8 +1209,8 @@ __global__ void __launch_bounds__(128) trk1_kernel(const __grid_constant__ DevPa
             if (L.store) { NLk[(uint32_t)((t + u) * nls)] = nl; if (N1k) N1k[(uint32_t)((t + u) * K)] = n1; }
         }
     }
-    for (; t < L.Tmax; t++) {   // ragged tail
-        if (t < T) {
+    for (; t < L.emax; t++) {   // ragged tail
+        if (t < te) {
             const float pk = __ldg(Pk + (uint32_t)(t * K));
             const float nprev = tr.nprev;
             const float n1 = tracker_step(p, tr, pk, true);
@@ -1202,6 +1218,7 @@ __global__ void __launch_bounds__(128) trk1_kernel(const __grid_constant__ DevPa
             if (L.store) { NLk[(uint32_t)(t * nls)] = nl; if (N1k) N1k[(uint32_t)(t * K)] = n1; }
         }
     }
+    if (L.store) *stp = make_float4(tr.trk, tr.ts, tr.nprev, 0.0f);
 }
 
 struct FluxIO {
@@ -1336,64 +1353,82 @@ __device__ __forceinline__ float baseline_step(const DevParams& p, double& bl_ba
     return sc;
 }
 
-__global__ void __launch_bounds__(128) base_kernel(const __grid_constant__ DevParams p, Batch b, float* mf, int stride) {
+__global__ void __launch_bounds__(128) base_kernel(const __grid_constant__ DevParams p, Batch b, float* mf, int stride,
+                                                   double2* state) {
     const int M = p.M;
     const SerialLane L = serial_lane(b, M + 1);
     const int col = (L.sub == 0) ? M : L.sub - 1;
+    // plain loads: the column is rewritten in place by this very kernel (the non-coherent path is for data that stays
+    // read-only for the kernel's lifetime)
     float* xs = mf + L.f0 * stride + col;
-    const int T = L.T;
+    double2* stp = state + (size_t)L.c * (APT_MAX_MODES + 1) + L.sub;
+    const int te = L.t_end;
     const float ffloor = d2f(p.bl_floor);
     double bl_base, bl_scale;
-    {
-        const double x0 = (double)__ldg(xs);
+    if (b.ta == 0) {
+        const double x0 = (double)xs[0];
         bl_base = x0 > p.bl_floor ? x0 : p.bl_floor;
         bl_scale = fabs(x0) > p.bl_floor ? fabs(x0) : p.bl_floor;
+    } else {
+        const double2 st = *stp;
+        bl_base = st.x; bl_scale = st.y;
     }
+    int t = b.ta;
+    const int tl = max(te - 1, 0);
     float xbuf[SEQ_PF];
 #pragma unroll
-    for (int u = 0; u < SEQ_PF; u++) xbuf[u] = __ldg(xs + (uint32_t)(min(u, T - 1) * stride));
-    int t = 0;
-    for (; t + SEQ_PF <= L.Tmin; t += SEQ_PF) {
+    for (int u = 0; u < SEQ_PF; u++) xbuf[u] = xs[(uint32_t)(min(t + u, tl) * stride)];
+    for (; t + SEQ_PF <= L.emin; t += SEQ_PF) {
         float xc[SEQ_PF];
 #pragma unroll
         for (int u = 0; u < SEQ_PF; u++) xc[u] = xbuf[u];
 #pragma unroll
-        for (int u = 0; u < SEQ_PF; u++) xbuf[u] = __ldg(xs + (uint32_t)(min(t + SEQ_PF + u, T - 1) * stride));
+        for (int u = 0; u < SEQ_PF; u++) xbuf[u] = xs[(uint32_t)(min(t + SEQ_PF + u, tl) * stride)];
 #pragma unroll
         for (int u = 0; u < SEQ_PF; u++) {
             const float sc = baseline_step(p, bl_base, bl_scale, xc[u], ffloor);
             if (L.store) xs[(uint32_t)((t + u) * stride)] = sc;
         }
     }
-    for (; t < L.Tmax; t++) {
-        if (t < T) {
-            const float sc = baseline_step(p, bl_base, bl_scale, __ldg(xs + (uint32_t)(t * stride)), ffloor);
+    for (; t < L.emax; t++) {
+        if (t < te) {
+            const float sc = baseline_step(p, bl_base, bl_scale, xs[(uint32_t)(t * stride)], ffloor);
             if (L.store) xs[(uint32_t)(t * stride)] = sc;
         }
     }
+    if (L.store) *stp = make_double2(bl_base, bl_scale);
 }
 
 struct DecIO {
     const float* mf; int stride;     // [nF][stride] normalised flux: cols 0..M-1 modes, col M total score
     const float* td;                 // [5][nF] (crest row 0, kurtosis row 1)
+    const uint8_t* gate_in;          // [nF] TD gate decided upstream (float32 fast path + exact re-check); NULL: from td
     int8_t* frame_class; float* rain_conf; float* noise_conf;
     float* norm_flux; float* score; uint8_t* gate;   // optional
     int64_t nF;
 };
 
-// one thread per frame of the launch's clip range: TD gate + fixed-band decision + labels
-// (rain_frame_classifier.py:230-284, :914-998)
-__global__ void __launch_bounds__(256) decide_kernel(const __grid_constant__ DevParams p, int64_t g0, int64_t g1, DecIO io) {
-    const int64_t g = g0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= g1) return;
+// one thread per frame: grid.x covers the frames [b.ta, b.tb) of a clip, grid.y the clips.  TD gate + fixed-band
+// decision + labels (rain_frame_classifier.py:230-284, :914-998)
+__global__ void __launch_bounds__(256) decide_kernel(const __grid_constant__ DevParams p, Batch b, DecIO io) {
+    const int c = b.clip0 + (int)blockIdx.y;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int t = b.ta + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (t >= min(T, b.tb)) return;
+    const int64_t g = f0 + t;
     const float* row = io.mf + g * io.stride;
     const int M = p.M;
     const float score = __ldg(row + M);
-    const float f0 = __ldg(row + 0), f1 = __ldg(row + 1), f2 = __ldg(row + 2), f3 = __ldg(row + 3);
-    bool gate = __ldg(io.td + g) > p.gate_thr;
-    if (p.has_ku) gate = gate && (__ldg(io.td + io.nF + g) <= p.ku);
+    const float f0v = __ldg(row + 0), f1 = __ldg(row + 1), f2 = __ldg(row + 2), f3 = __ldg(row + 3);
+    bool gate;
+    if (io.gate_in) gate = __ldg(io.gate_in + g) != 0;
+    else {
+        gate = __ldg(io.td + g) > p.gate_thr;
+        if (p.has_ku) gate = gate && (__ldg(io.td + io.nF + g) <= p.ku);
+    }
     const float gs = gate ? 1.0f : 0.0f;
-    const float l0 = svml_log1pf(f_max(f0 * gs, 0.0f));
+    const float l0 = svml_log1pf(f_max(f0v * gs, 0.0f));
     const float l1 = svml_log1pf(f_max(f1 * gs, 0.0f));
     const float l2 = svml_log1pf(f_max(f2 * gs, 0.0f));
     const float l3 = svml_log1pf(f_max(f3 * gs, 0.0f));
@@ -1444,10 +1479,13 @@ struct Trk2IO {
     const float* P_band;        // [nF][K]
     const int8_t* frame_class;  // [nF]
     float* N2;                  // [nF][K] noise PSD of pass 2
+    float4* state;              // [plan clips][state_stride]: (trk, ts, nprev, warm-up count) between time segments
+    int state_stride;
     int64_t nF;
 };
 
 // NT = CTA size of the launch (128: the compiler takes ~130 registers, three CTAs fit an SM; 256: see the launch site)
+// Frames [b.ta, b.tb) of every lane; ta == 0 starts the recursion, ta > 0 resumes from `state`.
 template <int NT>
 __global__ void __launch_bounds__(NT) trk2_kernel(const __grid_constant__ DevParams p, Batch b, Trk2IO io) {
     const int K = p.K;
@@ -1455,31 +1493,37 @@ __global__ void __launch_bounds__(NT) trk2_kernel(const __grid_constant__ DevPar
     const float* Pk = io.P_band + L.f0 * K + L.sub;
     float* Nk = io.N2 + L.f0 * K + L.sub;
     const int8_t* fc = io.frame_class + L.f0;
-    const int T = L.T;
+    float4* stp = io.state + (size_t)L.c * io.state_stride + L.sub;
+    const int te = L.t_end;
     Tracker tr = {0, 0, 0};
-    // frame 0 counts as an update when it is allowed (rain_signal_processor.py:700-703)
-    int warm = ((0 < p.warm_need) || (__ldg(fc) == 0)) ? 1 : 0;
-    {
+    int warm;
+    if (b.ta == 0) {
+        // frame 0 counts as an update when it is allowed (rain_signal_processor.py:700-703)
+        warm = ((0 < p.warm_need) || (__ldg(fc) == 0)) ? 1 : 0;
         const float n2 = tracker_first(p, tr, __ldg(Pk));
         if (L.store) Nk[0] = n2;
+    } else {
+        const float4 st = *stp;
+        tr.trk = st.x; tr.ts = st.y; tr.nprev = st.z; warm = __float_as_int(st.w);
     }
+    int t = max(b.ta, 1);
+    const int tl = max(te - 1, 0);
     float pbuf[SEQ_PF];
     int8_t ebuf[SEQ_PF];
 #pragma unroll
     for (int u = 0; u < SEQ_PF; u++) {
-        const int ti = min(1 + u, T - 1);
+        const int ti = min(t + u, tl);
         pbuf[u] = __ldg(Pk + (size_t)ti * K);
         ebuf[u] = __ldg(fc + ti);
     }
-    int t = 1;
-    for (; t + SEQ_PF <= L.Tmin; t += SEQ_PF) {
+    for (; t + SEQ_PF <= L.emin; t += SEQ_PF) {
         float pc[SEQ_PF];
         int8_t ec[SEQ_PF];
 #pragma unroll
         for (int u = 0; u < SEQ_PF; u++) { pc[u] = pbuf[u]; ec[u] = ebuf[u]; }
 #pragma unroll
         for (int u = 0; u < SEQ_PF; u++) {
-            const int ti = min(t + SEQ_PF + u, T - 1);
+            const int ti = min(t + SEQ_PF + u, tl);
             pbuf[u] = __ldg(Pk + (size_t)ti * K);
             ebuf[u] = __ldg(fc + ti);
         }
@@ -1492,14 +1536,15 @@ __global__ void __launch_bounds__(NT) trk2_kernel(const __grid_constant__ DevPar
             if (L.store) Nk[(size_t)(t + u) * K] = n2;
         }
     }
-    for (; t < L.Tmax; t++) {
-        if (t < T) {
+    for (; t < L.emax; t++) {
+        if (t < te) {
             const bool allow = (warm < p.warm_need) || (__ldg(fc + t) == 0);
             const float n2 = tracker_step(p, tr, __ldg(Pk + (size_t)t * K), allow);
             warm += allow ? 1 : 0;
             if (L.store) Nk[(size_t)t * K] = n2;
         }
     }
+    if (L.store) *stp = make_float4(tr.trk, tr.ts, tr.nprev, __int_as_float(warm));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1817,15 +1862,30 @@ __global__ void __launch_bounds__(ISTFT_NT) istft256_kernel(const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
-// exact median of the dB plane per clip: 3-level MSD radix select on order-preserving keys.
-// Two ranks are selected at once (lower / upper middle of an even count).  Level 0 (bits 31..21) is
-// histogrammed by db_kernel while it produces the plane; levels 1 and 2 re-read it as a flat array.
+// Noise-floor statistics of a clip: mean and exact median of d = 10*log10(N2 + eps) over its T*K values
+// (rain_signal_processor.py:1286-1298).  The dB values are never stored: every pass recomputes them from the
+// noise PSD plane (log10 is cheap next to the plane's bytes).
+//   dbsum_kernel     per time segment, right behind trk2: float64 chunk sums in a fixed order + a histogram of the
+//                    dB values over 2048 LINEAR bins of 1/16 dB on [-96, +32) dB (a monotone binning, so the bin that
+//                    holds a rank is found by a prefix sum; the values cluster within a few dB, so a 1/16 dB bin holds
+//                    about 1 % of them, where the top radix digit of the float would hold a third)
+//   sel_scan0_kernel warp per clip: the bins holding the two middle ranks (numpy's even-count rule) + ranks inside
+//   sel_collect_kernel  second read of the plane: the order-preserving keys of the values in those bins are
+//                    appended to the clip's candidate list (warp-aggregated)
+//   sel_final_kernel CTA per clip: 4 x 8-bit radix select of both ranks inside the candidate list (L2-resident)
+// A clip whose candidates overflow its list (constant or near-constant planes) is flagged and goes through the
+// 3-level radix select over the whole plane instead (select_hist / select_scan: 11 + 11 + 10 key bits); those
+// kernels return at once for every other clip.
 // ---------------------------------------------------------------------------------------------
 constexpr int SEL_BINS = 2048;
-constexpr int SEL_CHUNK = 1 << 16;   // plane elements per CTA of db_kernel / select_hist_kernel
+constexpr int DB_CF = 896;           // frames per chunk of dbsum / collect / select_hist (chunk = DB_CF * K values)
 struct SelState {
-    uint32_t prefix[2];
-    int64_t rank[2];
+    uint32_t prefix[2];   // fallback: key prefix found so far; finally: the two selected keys
+    int64_t rank[2];      // fallback: rank inside the prefix
+    int64_t brank[2];     // rank inside the linear bin
+    int bin[2];           // linear bins holding the two middle ranks
+    int cnt;              // candidates appended
+    int overflow;         // candidate list too small: fallback
 };
 __device__ __forceinline__ uint32_t db_key(float v) {
     const uint32_t u = f2u(v);
@@ -1834,29 +1894,38 @@ __device__ __forceinline__ uint32_t db_key(float v) {
 __device__ __forceinline__ float key_db(uint32_t k) {
     return u2f((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
+__device__ __forceinline__ int db_bin(float d) {   // monotone non-decreasing in d
+    float x = (d + 96.0f) * 16.0f;
+    x = fminf(fmaxf(x, 0.0f), (float)(SEL_BINS - 1));
+    return (int)x;
+}
 
-// noise-floor dB plane 10*log10(N2 + eps) (rain_signal_processor.py:1286-1298) over one chunk of a clip's
-// flat plane; the plane may be produced in place.  Also: the chunk's float64 sum (fixed summation order)
-// and the level-0 histogram of the median select.
-__global__ void __launch_bounds__(256) db_kernel(const __grid_constant__ DevParams p, Batch b, const float* N2,
-                                                 float* db, const int64_t* __restrict__ chunk_off,
-                                                 uint32_t* __restrict__ hist, double* __restrict__ chunk_sum) {
+// chunk `blockIdx.x + b.tile0` of clip `blockIdx.y`: returns false when the clip has no such chunk
+__device__ __forceinline__ bool db_chunk(const Batch& b, int K, const int64_t* __restrict__ chunk_off, int& c, int64_t& chunk,
+                                         int64_t& f0, int& ne, int64_t& e0) {
+    if (!tile_clip(b, chunk_off, c, chunk)) return false;
+    f0 = __ldg(b.frame_off + c);
+    const int64_t n = (__ldg(b.frame_off + c + 1) - f0) * (int64_t)K;
+    e0 = chunk * (int64_t)DB_CF * K;
+    const int64_t e1 = min(n, e0 + (int64_t)DB_CF * K);
+    ne = (int)(e1 - e0);
+    return ne > 0;
+}
+
+__global__ void __launch_bounds__(256) dbsum_kernel(const __grid_constant__ DevParams p, Batch b, const float* __restrict__ N2,
+                                                    const int64_t* __restrict__ chunk_off, uint32_t* __restrict__ hist,
+                                                    double* __restrict__ chunk_sum) {
     __shared__ uint32_t s_h[SEL_BINS];
     __shared__ float s_ltab[64];
     __shared__ double s_part[8];
     const int tid = threadIdx.x;
-    int64_t chunk_in_clip;
-    int c;
-    if (!tile_clip(b, chunk_off, c, chunk_in_clip)) return;
-    const int64_t f0 = __ldg(b.frame_off + c);
-    const int64_t n = (__ldg(b.frame_off + c + 1) - f0) * (int64_t)p.K;
-    const int64_t e0 = chunk_in_clip * SEL_CHUNK, e1 = min(n, e0 + (int64_t)SEL_CHUNK);
+    int c, ne;
+    int64_t chunk, f0, e0;
+    if (!db_chunk(b, p.K, chunk_off, c, chunk, f0, ne, e0)) return;
     if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
     for (int i = tid; i < SEL_BINS; i += 256) s_h[i] = 0;
     __syncthreads();
     const float* src = N2 + f0 * p.K + e0;      // the chunk: 32-bit indices from here on
-    float* dst = db + f0 * p.K + e0;
-    const int ne = (int)(e1 - e0);
     double acc = 0.0;
     int run_bin = -1;
     uint32_t run_cnt = 0;
@@ -1866,16 +1935,15 @@ __global__ void __launch_bounds__(256) db_kernel(const __grid_constant__ DevPara
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int i = base + u * 256;
-            v[u] = i < ne ? src[i] : 1.0f;
+            v[u] = i < ne ? __ldg(src + i) : 1.0f;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int i = base + u * 256;
             if (i < ne) {
                 const float d = 10.0f * svml_log10f(v[u] + p.eps32, s_ltab);
-                dst[i] = d;
                 acc += (double)d;
-                const int bin = (int)(db_key(d) >> 21);
+                const int bin = db_bin(d);
                 if (bin == run_bin) run_cnt++;
                 else {
                     if (run_cnt) atomicAdd(&s_h[run_bin], run_cnt);
@@ -1891,9 +1959,9 @@ __global__ void __launch_bounds__(256) db_kernel(const __grid_constant__ DevPara
     if ((tid & 31) == 0) s_part[tid >> 5] = acc;
     __syncthreads();
     if (tid == 0) {
-        double s = 0.0;
-        for (int w = 0; w < 8; w++) s += s_part[w];
-        chunk_sum[__ldg(chunk_off + c) + chunk_in_clip] = s;
+        double sm = 0.0;
+        for (int w = 0; w < 8; w++) sm += s_part[w];
+        chunk_sum[__ldg(chunk_off + c) + chunk] = sm;
     }
     uint32_t* hg = hist + (size_t)c * 2 * SEL_BINS;
     for (int i = tid; i < SEL_BINS; i += 256) {
@@ -1907,63 +1975,17 @@ __global__ void select_init_kernel(Batch b, int K, SelState* st) {
     if (ci >= b.n_clips) return;
     const int c = b.clip0 + ci;
     const int64_t n = (b.frame_off[c + 1] - b.frame_off[c]) * (int64_t)K;
-    st[c].prefix[0] = st[c].prefix[1] = 0;
-    st[c].rank[0] = (n - 1) / 2;
-    st[c].rank[1] = n / 2;
+    SelState z;
+    z.prefix[0] = z.prefix[1] = 0;
+    z.rank[0] = (n - 1) / 2;
+    z.rank[1] = n / 2;
+    z.brank[0] = z.brank[1] = 0;
+    z.bin[0] = z.bin[1] = 0;
+    z.cnt = 0; z.overflow = 0;
+    st[c] = z;
 }
 
-// level 1: bits 20..10, level 2: bits 9..0 of the elements whose higher bits equal the prefix found so
-// far.  The plane of a clip is a flat array of T*K floats; a CTA histograms one SEL_CHUNK of it in
-// shared memory and adds the non-empty bins to the clip's global histogram.
-__global__ void __launch_bounds__(256) select_hist_kernel(Batch b, int K, const float* __restrict__ db,
-                                                          const int64_t* __restrict__ chunk_off, int level,
-                                                          const SelState* __restrict__ st, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t s_h[2][SEL_BINS];
-    int64_t chunk_in_clip;
-    int c;
-    if (!tile_clip(b, chunk_off, c, chunk_in_clip)) return;
-    const int64_t f0 = __ldg(b.frame_off + c);
-    const int64_t n = (__ldg(b.frame_off + c + 1) - f0) * (int64_t)K;
-    const int64_t e0 = chunk_in_clip * SEL_CHUNK, e1 = min(n, e0 + (int64_t)SEL_CHUNK);
-    const int sh = level == 1 ? 10 : 0;
-    const uint32_t mask = level == 2 ? 1023u : 2047u;
-    const int shp = level == 1 ? 21 : 10;
-    const uint32_t pre0 = st[c].prefix[0], pre1 = st[c].prefix[1];
-    const bool two = pre1 != pre0;
-    for (int i = threadIdx.x; i < 2 * SEL_BINS; i += blockDim.x) (&s_h[0][0])[i] = 0;
-    __syncthreads();
-    const float* src = db + f0 * K + e0;        // the chunk: 32-bit indices from here on
-    const int ne = (int)(e1 - e0);
-    constexpr int U = 8;
-    for (int base = threadIdx.x; base < ne; base += U * 256) {
-        float v[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int i = base + u * 256;
-            v[u] = i < ne ? __ldg(src + i) : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int i = base + u * 256;
-            if (i < ne) {
-                const uint32_t key = db_key(v[u]);
-                const uint32_t hi = key >> shp;
-                const int bin = (int)((key >> sh) & mask);
-                if (hi == pre0) atomicAdd(&s_h[0][bin], 1u);
-                else if (two && hi == pre1) atomicAdd(&s_h[1][bin], 1u);
-            }
-        }
-    }
-    __syncthreads();
-    uint32_t* hg = hist + (size_t)c * 2 * SEL_BINS;
-    for (int i = threadIdx.x; i < 2 * SEL_BINS; i += blockDim.x) {
-        const uint32_t cnt = (&s_h[0][0])[i];
-        if (cnt) atomicAdd(hg + i, cnt);
-    }
-}
-
-// one warp per clip: find the bins holding the two ranks, refine prefix/rank (histograms are cleared
-// by the host between levels)
+// one warp: the bin of h[0..nb) holding `rank` and the count of elements in lower bins
 __device__ __forceinline__ int warp_find_rank(const uint32_t* __restrict__ h, int nb, int64_t rank, int64_t& before_out) {
     const int lane = threadIdx.x & 31;
     int64_t cum = 0;
@@ -1991,10 +2013,158 @@ __device__ __forceinline__ int warp_find_rank(const uint32_t* __restrict__ h, in
     return found;
 }
 
+__global__ void sel_scan0_kernel(int clip0, int n_clips, SelState* st, const uint32_t* __restrict__ hist) {
+    const int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (ci >= n_clips) return;
+    const int c = clip0 + ci;
+    const uint32_t* h = hist + (size_t)c * 2 * SEL_BINS;
+    int64_t b0, b1;
+    const int f0 = warp_find_rank(h, SEL_BINS, st[c].rank[0], b0);
+    const int f1 = warp_find_rank(h, SEL_BINS, st[c].rank[1], b1);
+    if (lane == 0) {
+        st[c].bin[0] = f0 < 0 ? 0 : f0; st[c].bin[1] = f1 < 0 ? 0 : f1;
+        st[c].brank[0] = st[c].rank[0] - b0; st[c].brank[1] = st[c].rank[1] - b1;
+    }
+}
+
+__global__ void __launch_bounds__(256) sel_collect_kernel(const __grid_constant__ DevParams p, Batch b, const float* __restrict__ N2,
+                                                          const int64_t* __restrict__ chunk_off, SelState* st,
+                                                          const int64_t* __restrict__ cand_off, uint32_t* __restrict__ cand) {
+    __shared__ float s_ltab[64];
+    const int tid = threadIdx.x, lane = tid & 31;
+    int c, ne;
+    int64_t chunk, f0, e0;
+    if (!db_chunk(b, p.K, chunk_off, c, chunk, f0, ne, e0)) return;
+    if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
+    __syncthreads();
+    const int bin0 = st[c].bin[0], bin1 = st[c].bin[1];
+    const int64_t co = __ldg(cand_off + c);
+    const int cap = (int)(__ldg(cand_off + c + 1) - co);
+    uint32_t* dst = cand + co;
+    const float* src = N2 + f0 * p.K + e0;
+    constexpr int U = 8;
+    const int n_iter = (ne + U * 256 - 1) / (U * 256);     // uniform over the CTA: the ballots below need every lane
+    for (int it = 0; it < n_iter; it++) {
+        const int base = it * U * 256 + tid;
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = base + u * 256;
+            v[u] = i < ne ? __ldg(src + i) : 1.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = base + u * 256;
+            bool take = false;
+            float d = 0.0f;
+            if (i < ne) {
+                d = 10.0f * svml_log10f(v[u] + p.eps32, s_ltab);
+                const int bin = db_bin(d);
+                take = bin == bin0 || bin == bin1;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, take);
+            if (m) {
+                int pos0 = 0;
+                if (lane == 0) pos0 = atomicAdd(&st[c].cnt, __popc(m));
+                pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+                if (take) {
+                    const int pos = pos0 + __popc(m & ((1u << lane) - 1u));
+                    if (pos < cap) dst[pos] = db_key(d);
+                }
+            }
+        }
+    }
+}
+
+// one CTA per clip: both ranks inside the candidate list, 8 key bits per pass
+__global__ void __launch_bounds__(256) sel_final_kernel(int clip0, SelState* st, const int64_t* __restrict__ cand_off,
+                                                        const uint32_t* __restrict__ cand) {
+    __shared__ uint32_t s_h[2][256];
+    __shared__ uint32_t s_pre[2];
+    __shared__ int64_t s_rank[2];
+    const int c = clip0 + (int)blockIdx.x;
+    const int tid = threadIdx.x;
+    const int64_t co = __ldg(cand_off + c);
+    const int cap = (int)(__ldg(cand_off + c + 1) - co);
+    const int m = st[c].cnt;
+    if (m > cap) { if (tid == 0) st[c].overflow = 1; return; }
+    const uint32_t* src = cand + co;
+    const int bin0 = st[c].bin[0], bin1 = st[c].bin[1];
+    if (tid == 0) { s_pre[0] = s_pre[1] = 0; s_rank[0] = st[c].brank[0]; s_rank[1] = st[c].brank[1]; }
+    for (int pass = 0; pass < 4; pass++) {
+        const int sh = 24 - 8 * pass;
+        s_h[0][tid] = 0; s_h[1][tid] = 0;
+        __syncthreads();
+        const uint32_t pre0 = s_pre[0], pre1 = s_pre[1];
+        for (int i = tid; i < m; i += 256) {
+            const uint32_t key = src[i];
+            const int bin = db_bin(key_db(key));
+            const uint32_t hi = pass == 0 ? 0u : key >> (sh + 8);
+            const uint32_t dg = (key >> sh) & 255u;
+            if (bin == bin0 && hi == pre0) atomicAdd(&s_h[0][dg], 1u);
+            if (bin == bin1 && hi == pre1) atomicAdd(&s_h[1][dg], 1u);
+        }
+        __syncthreads();
+        if (tid < 2) {
+            int64_t r = s_rank[tid], cum = 0;
+            int dgt = 255;
+            for (int j = 0; j < 256; j++) {
+                const int64_t nx = cum + s_h[tid][j];
+                if (nx > r) { dgt = j; break; }
+                cum = nx;
+            }
+            s_pre[tid] = (s_pre[tid] << 8) | (uint32_t)dgt;
+            s_rank[tid] = r - cum;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { st[c].prefix[0] = s_pre[0]; st[c].prefix[1] = s_pre[1]; }
+}
+
+// Fallback for clips flagged `overflow`: 3-level MSD radix select (11 + 11 + 10 key bits) over the whole plane, both
+// ranks at once.  level 0: bits 31..21, level 1: bits 20..10, level 2: bits 9..0 of the elements whose higher bits
+// equal the prefix found so far.  A CTA histograms one chunk in shared memory and adds the non-empty bins to the
+// clip's global histogram.
+__global__ void __launch_bounds__(256) select_hist_kernel(const __grid_constant__ DevParams p, Batch b, const float* __restrict__ N2,
+                                                          const int64_t* __restrict__ chunk_off, int level,
+                                                          const SelState* __restrict__ st, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_h[2][SEL_BINS];
+    __shared__ float s_ltab[64];
+    int c, ne;
+    int64_t chunk, f0, e0;
+    if (!db_chunk(b, p.K, chunk_off, c, chunk, f0, ne, e0)) return;
+    if (!st[c].overflow) return;
+    const int sh = level == 0 ? 21 : (level == 1 ? 10 : 0);
+    const uint32_t mask = level == 2 ? 1023u : 2047u;
+    const int shp = level == 1 ? 21 : 10;
+    const uint32_t pre0 = st[c].prefix[0], pre1 = st[c].prefix[1];
+    const bool two = pre1 != pre0;
+    if (threadIdx.x < 64) s_ltab[threadIdx.x] = u2f(kSvmlLog10TabDev[threadIdx.x]);
+    for (int i = threadIdx.x; i < 2 * SEL_BINS; i += blockDim.x) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    const float* src = N2 + f0 * p.K + e0;
+    for (int i = threadIdx.x; i < ne; i += 256) {
+        const uint32_t key = db_key(10.0f * svml_log10f(__ldg(src + i) + p.eps32, s_ltab));
+        const uint32_t hi = level == 0 ? 0u : key >> shp;
+        const int bin = (int)((key >> sh) & mask);
+        if (hi == pre0) atomicAdd(&s_h[0][bin], 1u);
+        else if (two && hi == pre1) atomicAdd(&s_h[1][bin], 1u);
+    }
+    __syncthreads();
+    uint32_t* hg = hist + (size_t)c * 2 * SEL_BINS;
+    for (int i = threadIdx.x; i < 2 * SEL_BINS; i += blockDim.x) {
+        const uint32_t cnt = (&s_h[0][0])[i];
+        if (cnt) atomicAdd(hg + i, cnt);
+    }
+}
+
+// one warp per flagged clip: find the bins holding the two ranks, refine prefix / rank (histograms are cleared by
+// the host between levels)
 __global__ void select_scan_kernel(int clip0, int n_clips, int level, SelState* st, const uint32_t* __restrict__ hist) {
     const int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (ci >= n_clips) return;
     const int c = clip0 + ci;
+    if (!st[c].overflow) return;
     const uint32_t pre0 = st[c].prefix[0], pre1 = st[c].prefix[1];
     const int64_t r0 = st[c].rank[0], r1 = st[c].rank[1];
     const bool shared01 = (level == 0) || (pre0 == pre1);

@@ -79,7 +79,8 @@ class SpectralNoiseProcessor:
         return self.process_batch([x], sr=sr)[0]
 
     def process_batch(self, clips: Sequence[np.ndarray], sr: Optional[int] = None,
-                      clip_rain_min_frames: int = 1, with_stats: bool = False) -> List[Dict[str, Any]]:
+                      clip_rain_min_frames: int = 1, with_stats: bool = False,
+                      with_events: bool = True) -> List[Dict[str, Any]]:
         if self.cfg is None:
             self.setup({"sample_rate": sr or 11162})
         cfg = self.cfg
@@ -120,6 +121,12 @@ class SpectralNoiseProcessor:
             a = np.asarray(x)
             arrays.append(a.reshape(-1) if a.dtype == np.int16 else np.asarray(a, dtype=np.float32).reshape(-1))
         eng = self._get_engine(int(sr), clip_rain_min_frames)
+        if not want:
+            # default flags (labels, confidences, clip statistics only): the pipelined host path -- pinned staging
+            # ring, host->device copies overlapped with compute, results straight into the caller's arrays
+            plan, out = eng.run_host_clips(arrays, event_idx=with_events)
+            self.last_host_call_s = eng.last_host_call_s
+            return self._package_core(plan, out, cfg, sr, eng.rp, with_stats)
         plan, out = eng.run_clips(arrays, want)
         rp = eng.rp
         band = rp.band_mask
@@ -163,6 +170,37 @@ class SpectralNoiseProcessor:
                 res["_clip_stats"] = out["clip_stats"][c].copy()
                 n = int(out["event_count"][c])
                 res["_event_idx"] = out["event_idx"][f0:f0 + n].copy()
+            results.append(res)
+        return results
+
+    _times_cache: Dict[tuple, np.ndarray] = {}
+
+    @classmethod
+    def _times(cls, T: int, hop: int, sr: float) -> np.ndarray:
+        """librosa.frames_to_time as float32 (rain_signal_processor.py:828); one array per (T, hop, sr), copied out."""
+        key = (int(T), int(hop), float(sr))
+        t = cls._times_cache.get(key)
+        if t is None:
+            if len(cls._times_cache) > 64:
+                cls._times_cache.clear()
+            t = np.asarray((np.arange(T) * int(hop)).astype(int) / float(sr), dtype=np.float32)
+            cls._times_cache[key] = t
+        return t.copy()
+
+    def _package_core(self, plan, out, cfg, sr, rp, with_stats) -> List[Dict[str, Any]]:
+        """Result dictionaries of the default-flags path: per-clip views of the batch's (caller-owned) host arrays."""
+        results = []
+        fo = plan.frame_off
+        fc, rc, nc = out["frame_class"], out["rain_conf"], out["noise_conf"]
+        ev = out.get("event_idx")
+        for c in range(plan.n_clips):
+            f0, f1 = int(fo[c]), int(fo[c + 1])
+            res: Dict[str, Any] = {"frame_class": fc[f0:f1], "freqs": rp.freqs.copy(),
+                                   "times": self._times(f1 - f0, cfg.hop, sr),
+                                   "rain_conf": rc[f0:f1], "noise_conf": nc[f0:f1]}
+            if with_stats:
+                res["_clip_stats"] = out["clip_stats"][c]
+                res["_event_idx"] = ev[f0:f0 + int(out["event_count"][c])] if ev is not None else None
             results.append(res)
         return results
 
@@ -294,8 +332,9 @@ class RainDetectorProcessor(BaseProcessor):
         sr = int(p.get("sample_rate", 11162))
         min_frames = max(1, int(p.get("clip_rain_min_frames", 1)))
         t0 = time.perf_counter()
-        outs = proc.process_batch(audio_list, sr=sr, clip_rain_min_frames=min_frames, with_stats=True)
+        outs = proc.process_batch(audio_list, sr=sr, clip_rain_min_frames=min_frames, with_stats=True, with_events=False)
         latency = (time.perf_counter() - t0) / max(1, len(audio_list))
+        self.last_host_call_s = getattr(proc, "last_host_call_s", 0.0)    # time inside the C-ABI call of this batch
         keep_features = bool(p.get("keep_state_features", True))
         results = []
         for audio, out in zip(audio_list, outs):

@@ -7,6 +7,7 @@ of clip lengths so repeated batches of the same shape reuse scratch.
 from __future__ import annotations
 
 import ctypes as C
+import time
 from typing import Any, Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -112,6 +113,7 @@ class BatchEngine:
         self._plans: Dict[tuple, Plan] = {}
         self._max_plans = max_plans
         self.last_launches = 0
+        self.last_host_call_s = 0.0      # seconds inside the last apt_run_host_clips call
 
     # ------------------------------------------------------------------
     def plan_for(self, lengths: Sequence[int]) -> Plan:
@@ -188,6 +190,40 @@ class BatchEngine:
             raise AptError(f"apt_run_host_i16 failed ({rc}): {self.L.apt_last_error(self.ctx).decode()}")
         self.last_launches = int(self.L.apt_plan_last_launches(plan.h))
         return outs
+
+    def run_host_clips(self, clips: List[np.ndarray], *, event_idx: bool = False):
+        """The plugin's default-flags path: host clips (all int16 or all float32, pageable memory is fine) ->
+        apt_run_host_clips (pinned staging ring, H2D / compute / D2H pipelined over clip groups) -> results in
+        freshly allocated pinned host arrays that the caller owns.  Returns (plan, outs)."""
+        torch = self.torch
+        first = clips[0]
+        if first.dtype not in (np.int16, np.float32):
+            raise TypeError(f"clip dtype {first.dtype} unsupported on the host path (int16 or float32)")
+        arrs = []
+        for c in clips:
+            if c.dtype != first.dtype or c.ndim != 1:
+                raise TypeError("all clips of a batch must be 1-D arrays of one dtype")
+            arrs.append(c if c.flags.c_contiguous else np.ascontiguousarray(c))
+        plan = self.plan_for([a.size for a in arrs])
+        n, nF = plan.n_clips, plan.nF
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+
+        def pin(shape, dt):
+            return torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+
+        outs = {"frame_class": pin((nF,), torch.int8), "rain_conf": pin((nF,), torch.float32),
+                "noise_conf": pin((nF,), torch.float32), "event_count": pin((n,), torch.int32),
+                "clip_stats": pin((n, _lib.N_STATS), torch.float32),
+                "event_idx": pin((nF,), torch.int32) if event_idx else None}
+        ptr = lambda k: outs[k].ctypes.data if outs.get(k) is not None else None
+        t0 = time.perf_counter()
+        rc = self.L.apt_run_host_clips(plan.h, ptrs, int(first.dtype == np.float32), ptr("frame_class"), ptr("rain_conf"),
+                                       ptr("noise_conf"), ptr("event_idx"), ptr("event_count"), ptr("clip_stats"))
+        self.last_host_call_s = time.perf_counter() - t0
+        if rc != 0:
+            raise AptError(f"apt_run_host_clips failed ({rc}): {self.L.apt_last_error(self.ctx).decode()}")
+        self.last_launches = int(self.L.apt_plan_last_launches(plan.h))
+        return plan, outs
 
     # ------------------------------------------------------------------
     def run_clips(self, clips: List[np.ndarray], want: Iterable[str] = (), *, full: bool = True):

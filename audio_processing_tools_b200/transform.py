@@ -1,9 +1,10 @@
 """Entry points of the reference's transform.py for the DSD path (the reference module cannot even be imported
 as shipped: transform.py:25 imports a module path that does not exist).
 
-Kept with the same names and meaning: ``butter_bandpass`` / ``butter_bandpass_filter`` (:29-36),
-``get_real_fft_df`` (:39-48), ``emulator_output_to_df`` (:51-68), ``reverse_binning_func`` / ``dsd_weights`` /
-``add_weighted_dsd_data`` (:123-145), ``process_audio_file_dsd`` (:251-313).  The compute of
+Kept with the same names and meaning: ``emulator_output_to_df`` (:51-68), ``reverse_binning_func`` / ``dsd_weights`` /
+``add_weighted_dsd_data`` (:123-145), ``process_audio_file_dsd`` (:251-313).  Not carried over: the two scipy
+one-liners ``butter_bandpass_filter`` / ``get_real_fft_df`` (:29-48; plotting helpers that nothing on the DSD path
+calls -- this package computes nothing on the CPU) and ``dsd_from_audio_keys`` (:316-403; S3 fetch + Postgres upsert).  The compute of
 ``process_audio_file_dsd`` runs on the GPU (host_analysis.device_dsd_processing_emulator); fetching from S3,
 Mark-3 container parsing and the database upsert (``dsd_from_audio_keys`` :316-403) are host I/O outside this
 package, so ``process_audio_file_dsd`` takes the decoded int16 signal and its metadata instead of an S3 key,
@@ -16,28 +17,11 @@ from typing import Any, Dict, Sequence
 
 import numpy as np
 import pandas as pd
-from scipy import fft, signal
 
 from .host_analysis.device_dsd_processing_emulator import DsdProcessingEmualtor
 
 RAIN_ENERGY_THRESHOLD = 0.6
 RAIN_LOG_FACTOR = 0.6
-
-
-def butter_bandpass(lowcut, highcut, fs, order=5):
-    return signal.butter(order, [lowcut, highcut], fs=fs, btype="band")
-
-
-def butter_bandpass_filter(data, lowcut, highcut, fs, order=5):
-    b, a = butter_bandpass(lowcut, highcut, fs, order=order)
-    return signal.lfilter(b, a, data)
-
-
-def get_real_fft_df(sig, sample_rate):
-    n = len(sig)
-    y = fft.fft(sig)
-    freqs = fft.fftfreq(n, 1 / sample_rate)[: n // 2]
-    return pd.DataFrame({"frequency": freqs, "amplitude": 2.0 / n * np.abs(y[0: n // 2])})
 
 
 def emulator_output_to_df(output, device_id, audio_start_timestamp, output_interval_min=1):
@@ -89,8 +73,3 @@ def process_audio_signals_dsd(signals: Sequence[np.ndarray], metadata: Sequence[
 def process_audio_file_dsd(key, sig, metadata, verbose=False, reprocess=False, device=0):
     """transform.process_audio_file_dsd (:251-313) for an already fetched and parsed Mark-3 file."""
     return process_audio_signals_dsd([sig], [metadata], [key], verbose=verbose, device=device)[0]
-
-
-def dsd_from_audio_keys(*args, **kwargs):
-    raise NotImplementedError("dsd_from_audio_keys (S3 fetch + Postgres upsert, transform.py:316-403) is host I/O outside "
-                              "this package; fetch and parse the files, then call process_audio_signals_dsd")

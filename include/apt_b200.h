@@ -160,6 +160,9 @@ int  apt_init(int device_ordinal, apt_ctx** out);
 void apt_destroy(apt_ctx* ctx);
 const char* apt_last_error(apt_ctx* ctx);
 int  apt_abi_version(void);
+/* hash of the sources the library was compiled from (set by the build; the Python loader refuses a library whose
+   hash differs from the sources beside it) */
+const char* apt_source_hash(void);
 int  apt_sizeof_params(void);
 int  apt_sizeof_out(void);
 
@@ -214,6 +217,17 @@ int  apt_plan_kernel_ms(apt_plan_t* plan, float* out_ms /* [APT_N_KERNELS] */);
    Synchronises before returning.  Host buffers should be pinned for full PCIe bandwidth. */
 int  apt_run_host_i16(apt_plan_t* plan, const int16_t* host_pcm, int8_t* frame_class, float* rain_conf,
                       float* noise_conf, int32_t* event_idx, int32_t* event_count, float* clip_stats);
+
+/* The same end-to-end path for what a processor's run_batch receives: one HOST pointer per clip (pageable memory
+   is fine), all int16 (is_f32 = 0) or all float32 (is_f32 = 1; the waveform audio_io.get_input_data hands out,
+   audio_io.py:421-432), clip c holding the plan's clip_len_samples[c] samples.  Helper threads stage the clips
+   of each group into a small ring of pinned buffers owned by the plan while the previous group is on the bus and
+   earlier groups compute; results are copied back as in apt_run_host_i16.  This is the entry point behind
+   RainDetectorProcessor.run_batch / NoiseProcessor.run_batch (the replacement of the per-file proc.run loop,
+   audio_processing_framework.py:183-207).  Synchronises before returning.
+   Environment: APT_HOST_GROUPS (clip groups, default 24), APT_STAGE_THREADS (staging threads, default min(16, cores/2)). */
+int  apt_run_host_clips(apt_plan_t* plan, const void* const* clip_ptrs, int is_f32, int8_t* frame_class, float* rain_conf,
+                        float* noise_conf, int32_t* event_idx, int32_t* event_count, float* clip_stats);
 
 /* ---------------------------------------------------------------------------------------------
  * Drop-size-distribution emulator: replaces DsdProcessingEmualtor.process_audio_data

@@ -3,9 +3,10 @@
 `install()` puts a librosa stand-in and import-time stubs for the reference's
 absent third-party modules on sys.path / sys.modules, then makes
 `audio_processing_tools` (the reference package) importable from
-$APT_REFERENCE or /root/reference.  It is used only by oracle/make_golden.py
-(in the build container, where /root/reference is mounted) -- never by the
-product package and never on the GPU box.
+$APT_REFERENCE, <repo>/baseline/_ref (the offline `pip install --target` copy of the
+unmodified reference, git-ignored; it travels to the GPU box) or /root/reference.  It is
+used by oracle/make_golden*.py (build container) and by bench.py's CPU reference legs --
+never by the product package.
 """
 from __future__ import annotations
 
@@ -19,7 +20,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def reference_root():
-    for cand in (os.environ.get("APT_REFERENCE"), "/root/reference"):
+    repo = os.path.dirname(os.path.dirname(_HERE))
+    for cand in (os.environ.get("APT_REFERENCE"), os.path.join(repo, "baseline", "_ref"), "/root/reference"):
         if cand and os.path.isdir(os.path.join(cand, "audio_processing_tools")):
             return cand
     return None

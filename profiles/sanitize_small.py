@@ -8,7 +8,8 @@ from audio_processing_tools_b200.synth import default_params, synth_clip_i16, qu
 from audio_processing_tools_b200.host_analysis.device_dsd_processing_emulator import DsdProcessingEmualtor
 ALL = ("S", "P", "det_noise_psd", "det_noise_lag", "D", "noise_psd", "mode_flux", "norm_flux", "score", "td", "raw",
        "band_energy", "gate", "x_td", "G", "ratio_med", "S_hat")
-clips = [synth_clip_i16(3.0 + 0.71 * i, 900 + i, 10.0) for i in range(3)]
+# ragged: 45 s and 25.3 s clips span several time segments of the pipelined run (1792 frames = 20.5 s each), 3.7 s does not
+clips = [synth_clip_i16(sec, 900 + i, 10.0) for i, sec in enumerate((45.0, 25.3, 3.7))]
 params = default_params(check_duration=3)
 eng = BatchEngine(build_noise_config(11162, params), 11162)
 plan, out = eng.run_clips(clips, ALL)
@@ -19,6 +20,10 @@ host = {"frame_class": np.zeros(plan.nF, np.int8), "rain_conf": np.zeros(plan.nF
         "event_idx": np.zeros(plan.nF, np.int32), "event_count": np.zeros(3, np.int32), "clip_stats": np.zeros((3, 8), np.float32)}
 eng.run_host_i16(plan, np.concatenate(clips), host)
 assert np.array_equal(host["frame_class"], out2["frame_class"])
+plan4, out4 = eng.run_host_clips([c.copy() for c in clips], event_idx=True)
+assert np.array_equal(out4["frame_class"], out2["frame_class"]) and np.array_equal(out4["clip_stats"], out2["clip_stats"])
+plan5, out5 = eng.run_host_clips([c.astype(np.float32) / np.float32(32767) for c in clips])
+assert np.array_equal(out5["frame_class"], out2["frame_class"])
 eng.close()
 for n_fft, hop in ((256, 64), (512, 128), (4096, 1024)):
     p2 = default_params(check_duration=3, n_fft=n_fft, hop=hop)

@@ -1,0 +1,179 @@
+"""GPU tests of the plugin boundary: the processors a reference user instantiates (RainDetectorProcessor,
+NoiseProcessor) and the batch orchestrator that calls them, on the default-flags path that goes through
+apt_run_host_clips (pinned staging ring, pipelined H2D / compute / D2H), against the goldens the unmodified
+reference produced (tests/golden, oracle/make_golden.py).
+
+Reference seams: processor contract audio_processing_framework.py:52-100 / :183-207, NoiseProcessor's intended
+results noise_processor.py:104-127, injected loaders audio_processing_framework.py:653-656."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from audio_processing_tools_b200.synth import FS, default_params, pcm_to_f32, synth_clip_i16
+
+pytestmark = pytest.mark.gpu
+
+DEFAULT_GOLDENS = [n for n in golden_names(max_seconds=60) if not n.startswith("alt_")]
+
+
+@pytest.fixture(scope="module")
+def goldens():
+    out = {}
+    for name in DEFAULT_GOLDENS:
+        g, meta, pcm, params = load_golden(name)
+        out[name] = (g, meta, pcm, params)
+    return out
+
+
+def _check_detector_result(m, s, g):
+    assert np.array_equal(s["frame_class"], g["frame_class"])
+    assert np.array_equal(s["rain_conf"], g["rain_conf"])
+    assert np.array_equal(s["noise_conf"], g["noise_conf"])
+    assert np.array_equal(s["times"], g["times"])
+    for k in ("rain_frame_count", "clip_is_rain", "clip_rain_conf", "median_rain_conf", "clip_rain_fraction",
+              "clip_rain_min_frames"):
+        assert m[k] == g["metric_" + k].item(), k
+    assert m["rain_frame_fraction"] == m["clip_rain_fraction"]
+
+
+def test_detector_run_batch_default_flags_ragged_int16_and_float32(goldens):
+    """RainDetectorProcessor.run_batch under default flags (host path): every golden clip in ONE ragged batch, once as
+    the int16 wire samples and once as the float32 waveform the reference's loader hands out."""
+    from audio_processing_tools_b200.edge.rain_signal_processor import RainDetectorProcessor
+    names = list(goldens)
+    params = dict(goldens[names[0]][3], check_duration=6)
+    proc = RainDetectorProcessor()
+    for conv in (lambda p: p, pcm_to_f32):
+        clips = [conv(goldens[n][2]) for n in names]
+        outs = proc.run_batch(clips, params)
+        assert len(outs) == len(names)
+        for n, (m, s) in zip(names, outs):
+            _check_detector_result(m, s, goldens[n][0])
+            assert "mean_noise_floor_db" not in m          # only with noise_psd returned (rain_signal_processor.py:1286)
+            assert s["processor"] == "rain_detector" and s["features"] is None
+            assert s["frame_class"].dtype == np.int8 and s["rain_conf"].dtype == np.float32
+    # results are caller-owned: a second batch must not overwrite the arrays handed out by the first
+    keep = [s["frame_class"].copy() for _, s in outs]
+    proc.run_batch([pcm_to_f32(goldens[names[-1]][2])] * 3, params)
+    for k, (_, s) in zip(keep, outs):
+        assert np.array_equal(k, s["frame_class"])
+
+
+def test_detector_host_path_equals_planes_path(goldens):
+    """The default-flags host path and the keep_state_debug path (device-resident, optional planes) agree bit for bit."""
+    from audio_processing_tools_b200.edge.rain_signal_processor import RainDetectorProcessor
+    names = list(goldens)[:4]
+    params = dict(goldens[names[0]][3], check_duration=6)
+    proc = RainDetectorProcessor()
+    clips = [pcm_to_f32(goldens[n][2]) for n in names]
+    fast = proc.run_batch(clips, params)
+    full = proc.run_batch(clips, dict(params, keep_state_debug=True))
+    for (m0, s0), (m1, s1) in zip(fast, full):
+        assert np.array_equal(s0["frame_class"], s1["frame_class"])
+        assert np.array_equal(s0["rain_conf"], s1["rain_conf"])
+        for k in ("rain_frame_count", "clip_is_rain", "clip_rain_conf", "clip_rain_fraction"):
+            assert m0[k] == m1[k]
+
+
+@pytest.mark.parametrize("name", DEFAULT_GOLDENS[:6])
+def test_noise_processor_run_matches_reference_metrics(goldens, name):
+    """NoiseProcessor.run (intended contract, noise_processor.py:104-127): the noise-floor statistics and the rain-frame
+    fraction equal what the reference's engine produced for the same clip (RainDetectorProcessor(keep_state_debug=True)
+    goldens: same noise_psd); default flags = host path, no plane leaves the GPU."""
+    from audio_processing_tools_b200.noise_processor import NoiseProcessor
+    g, meta, pcm, params = goldens[name]
+    proc = NoiseProcessor(name="noise")
+    m, s = proc.run(pcm_to_f32(pcm), params)
+    assert set(m) == {"mean_noise_floor_db", "median_noise_floor_db", "rain_frame_fraction", "latency_s"}
+    assert m["mean_noise_floor_db"] == pytest.approx(float(g["metric_mean_noise_floor_db"]), rel=1e-5)
+    assert m["median_noise_floor_db"] == pytest.approx(float(g["metric_median_noise_floor_db"]), rel=1e-6)
+    assert m["rain_frame_fraction"] == float(np.mean(g["frame_class"] == 2))
+    assert np.array_equal(s["is_rain"], g["frame_class"] == 2)
+    assert np.array_equal(s["times"], g["times"])
+    assert s["processor"] == "noise" and "noise_psd" not in s
+
+
+def test_noise_processor_batch_and_full_state(goldens):
+    """run_batch over a ragged batch; keep_state_full returns the arrays the reference's state lists."""
+    from audio_processing_tools_b200.noise_processor import NoiseProcessor
+    names = [n for n in goldens if n.startswith("full_")]
+    params = dict(goldens[names[0]][3], check_duration=6)
+    proc = NoiseProcessor(name="noise")
+    clips = [pcm_to_f32(goldens[n][2]) for n in names]
+    lean = proc.run_batch(clips, params)
+    rich = proc.run_batch(clips, dict(params, keep_state_full=True))
+    for n, (m0, s0), (m1, s1) in zip(names, lean, rich):
+        g = goldens[n][0]
+        for k in ("mean_noise_floor_db", "median_noise_floor_db", "rain_frame_fraction"):
+            assert m0[k] == m1[k], k
+        assert m0["median_noise_floor_db"] == pytest.approx(float(g["metric_median_noise_floor_db"]), rel=1e-6)
+        band = s1["noise_psd"][10:81].T
+        np.testing.assert_allclose(band, g["noise_psd_band"], rtol=1e-4, atol=1e-12)
+        assert s1["noise_psd"].shape == (129, g["frame_class"].size)
+        # the statistics are the reference's formulas applied to the returned plane (noise_processor.py:104-112)
+        db = 10.0 * np.log10(s1["noise_psd"][10:81] + np.float32(1e-9))
+        assert m1["mean_noise_floor_db"] == pytest.approx(float(np.mean(db)), rel=1e-5)
+        assert m1["median_noise_floor_db"] == pytest.approx(float(np.median(db)), rel=1e-6)
+        T = g["frame_class"].size
+        assert s1["S"].shape == (129, T) and s1["S_hat"].shape == (129, T)
+        assert s1["input_audio"].shape == clips[names.index(n)].shape
+        assert s1["denoised_audio"].shape == clips[names.index(n)].shape
+        assert "debug" in s1 and "config" in s1
+    with pytest.raises(ValueError):
+        proc.run(clips[0], dict(params, suppressor_bypass=True))
+    with pytest.raises(ValueError):
+        proc.run(clips[0][:100], params)
+
+
+def test_orchestrator_with_gpu_processors(goldens, tmp_path):
+    """process_audio_batches_v2 with the real GPU processors and an injected synthetic loader: rows equal the goldens;
+    batch_size smaller than the corpus; one file too short (dropped before run, framework :162-169)."""
+    import pandas as pd
+    from audio_processing_tools_b200.audio_processing_framework import process_audio_batches_v2
+    from audio_processing_tools_b200.edge.rain_signal_processor import RainDetectorProcessor
+    from audio_processing_tools_b200.noise_processor import NoiseProcessor
+    names = [n for n in goldens if goldens[n][1]["seconds"] == 60]
+    assert len(names) >= 5
+    base = goldens[names[0]][3]
+
+    def get_keys(InputType, **kw):
+        return [{"source_file": n, "raining": goldens[n][1]["lam"] > 0} for n in names] + \
+               [{"source_file": "zz_short", "raining": False}]
+
+    def loader(keys, InputType, Fs, check_duration, localStatus, local_cache, read_size=None, bytes_per_sample=2, **kw):
+        out = {}
+        for k in keys:
+            n = k["source_file"]
+            audio = np.zeros(1000, np.float32) if n == "zz_short" else pcm_to_f32(goldens[n][2])
+            out[n] = {"file_contents": audio, "raining": k["raining"]}
+        return out
+
+    procs = [RainDetectorProcessor(name="rain_detector"), NoiseProcessor(name="noise")]
+    res, states = process_audio_batches_v2(
+        processors=procs, params_global={"sample_rate": FS, "check_duration": 60, "detector": base["detector"]},
+        batch_size=2, batch_save_dir=str(tmp_path), max_batch_save=3, get_keys_fn=get_keys, get_input_data_fn=loader)
+    # rows are flushed to parquet every >= 3 rows (framework :813-829) and the in-memory frames keep the remainder:
+    # the parts together hold every file once, without the short one (dropped before run)
+    parts = res.attrs["saved_parquet_files"]
+    assert len(parts) == 2
+    rows = pd.concat([pd.read_parquet(p) for p in parts]).sort_values("file_key").reset_index(drop=True)
+    assert list(rows["file_key"]) == sorted(names)
+    assert list(res["file_key"]) == sorted(names)[4:]
+    for _, row in rows.iterrows():
+        g = goldens[row["file_key"]][0]
+        assert row["rain_detector__rain_frame_count"] == int(g["metric_rain_frame_count"])
+        assert bool(row["rain_detector__clip_is_rain"]) == bool(g["metric_clip_is_rain"])
+        assert row["rain_detector__clip_rain_fraction"] == float(g["metric_clip_rain_fraction"])
+        assert row["noise__median_noise_floor_db"] == pytest.approx(float(g["metric_median_noise_floor_db"]), rel=1e-6)
+        assert row["noise__mean_noise_floor_db"] == pytest.approx(float(g["metric_mean_noise_floor_db"]), rel=1e-5)
+        assert row["noise__rain_frame_fraction"] == float(np.mean(g["frame_class"] == 2))
+        assert bool(row["rain_actual"]) == (goldens[row["file_key"]][1]["lam"] > 0)
+    st_parts = states["rain_detector"].attrs["saved_parquet_files"]
+    st_rows = pd.concat([pd.read_parquet(p) for p in st_parts])
+    assert sorted(st_rows["file_key"]) == sorted(names)
+    for _, st in st_rows.iterrows():
+        g = goldens[st["file_key"]][0]
+        assert np.array_equal(np.asarray(st["frame_class"], dtype=np.int8), g["frame_class"])
+    for _, st in states["noise"].iterrows():       # in-memory remainder: numpy arrays, not lists
+        assert np.array_equal(st["is_rain"], goldens[st["file_key"]][0]["frame_class"] == 2)
+    assert res.attrs["num_files_processed_total"] == len(names) + 1
