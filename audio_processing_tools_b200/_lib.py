@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_PKG, "libapt_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 MAX_MODES, MAX_SOS, N_RAW, N_TD, N_STATS = 8, 4, 21, 5, 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_GAIN_TAPS = 9
 STAGE_FEATURES, STAGE_FULL = 1, 2
 KERNEL_NAMES = ("stft256_kernel", "td_features_kernel", "trk1_kernel", "flux_kernel", "base_kernel",
@@ -69,7 +69,7 @@ class AptParams(C.Structure):
 OUT_FIELDS = ("frame_class", "rain_conf", "noise_conf", "event_idx", "event_count", "clip_stats",
               "S", "P", "det_noise_psd", "det_noise_lag", "D", "noise_psd", "mode_flux", "norm_flux",
               "score", "td", "raw", "band_energy", "gate", "x_td", "G", "ratio_med", "S_hat",
-              "peak_ratio", "peak_gate_score", "peak_valid_count", "peak_count_by_mode", "y")
+              "peak_ratio", "peak_gate_score", "peak_valid_count", "peak_count_by_mode", "y", "td_fast_crest")
 
 
 class AptDsdParams(C.Structure):
@@ -124,7 +124,7 @@ EXPORTS = ("apt_init", "apt_destroy", "apt_last_error", "apt_abi_version", "apt_
            "apt_sizeof_out", "apt_params_default", "apt_plan_create", "apt_plan_destroy",
            "apt_plan_offsets", "apt_plan_total_frames", "apt_plan_total_samples",
            "apt_plan_scratch_bytes", "apt_run_i16", "apt_run_f32", "apt_plan_last_launches",
-           "apt_run_host_i16", "apt_run_host_clips", "apt_source_hash", "apt_plan_enable_timing", "apt_plan_kernel_ms", "apt_selftest",
+           "apt_run_host_i16", "apt_run_host_clips", "apt_source_hash", "apt_plan_enable_timing", "apt_plan_enable_trace", "apt_plan_trace", "apt_plan_kernel_ms", "apt_selftest",
            "apt_dsd_run_i16", "apt_sizeof_bne_params", "apt_bne_run",
            "apt_sizeof_roe_params", "apt_roe_run")
 
@@ -224,6 +224,8 @@ def load():
         raise RuntimeError("libapt_b200.so apt_bne_params_t layout differs from the Python binding")
     L.apt_dsd_run_i16.argtypes = [vp, C.POINTER(AptDsdParams), C.c_int, i64p, C.POINTER(C.c_double), vp, vp, vp, C.c_int, vp]
     L.apt_plan_enable_timing.argtypes = [vp, C.c_int]
+    L.apt_plan_enable_trace.argtypes = [vp, C.c_int]
+    L.apt_plan_trace.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float)]
     L.apt_plan_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     if L.apt_abi_version() != ABI_VERSION:
         raise RuntimeError("libapt_b200.so ABI version mismatch")

@@ -70,7 +70,14 @@ struct apt_plan {
     DevBuf<double> d_Apow, d_H;
     TdTables tdt;
     int td_ns = 0;
-    size_t td_smem = 0;
+    size_t td_smem = 0, td_smem_f32 = 0;
+    // float32 fast path of the TD gate: gate bytes, flagged tiles of each time segment, counters
+    DevBuf<uint8_t> d_gate;
+    DevBuf<int2> d_td_list;
+    DevBuf<int> d_td_cnt;
+    int64_t td_list_cap = 0;
+    int td_fast = 1;
+    float td_guard = 1e-3f;
     // scratch
     DevBuf<float> d_Pband, d_n2, d_td, d_mf, d_nl, d_nl_all, d_Dscr;
     DevBuf<double> d_dbsum;   // [dB chunks] float64 sums of the noise-floor dB values
@@ -107,6 +114,10 @@ struct apt_plan {
     cudaStream_t s_kind[SK_N] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_seg[SK_N][MAX_SEG] = {};
     cudaEvent_t ev_fork = nullptr;
+    // optional timeline of the pipelined run (apt_plan_trace): timing events around every launch on its kind's stream
+    bool trace = false;
+    cudaEvent_t tr_origin = nullptr, tr_end = nullptr, tr_ev[SK_N][MAX_SEG][2] = {};
+    int tr_nseg = 0;
     int pipeline = 1;                        // 0: everything on the caller's stream in one segment
     int last_launches = 0;
     size_t scratch_bytes = 0;
@@ -416,6 +427,9 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         }
         pl->tdt.env_cap = (TD_FT * p->hop + p->n_fft + 2 * halo) / std::max(1, p->blk_hop) + 8;
         pl->td_smem = td_smem_bytes(ns, pl->tdt.env_cap);
+        pl->td_smem_f32 = td_smem_bytes(ns, pl->tdt.env_cap, sizeof(float));
+        for (int i = 0; i < TD_CHUNK * 4; i++) pl->tdt.Hcf[i] = (float)pl->tdt.Hc[i];
+        for (int i = 0; i < 5 * 16; i++) pl->tdt.Adcf[i] = (float)pl->tdt.Adc[i];
     }
     // scratch
     PL_OK(pl->d_Pband.alloc((size_t)pl->nF * K));
@@ -445,6 +459,12 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     }
     PL_OK(pl->d_sel.alloc(n_clips));
     PL_OK(pl->d_hist.alloc((size_t)n_clips * 2 * SEL_BINS));
+    PL_OK(pl->d_gate.alloc((size_t)pl->nF));
+    pl->td_list_cap = pl->td_tile_off[n_clips];
+    PL_OK(pl->d_td_list.alloc((size_t)pl->td_list_cap));
+    PL_OK(pl->d_td_cnt.alloc(apt_plan::MAX_SEG));
+    if (const char* e = getenv("APT_TD_FAST")) pl->td_fast = atoi(e);
+    if (const char* e = getenv("APT_TD_GUARD")) pl->td_guard = (float)atof(e);
     pl->st_stride = std::max(K, pl->tab_modes.n_lanes);
     PL_OK(pl->d_st_trk1.alloc((size_t)n_clips * pl->st_stride));
     PL_OK(pl->d_st_trk2.alloc((size_t)n_clips * pl->st_stride));
@@ -491,6 +511,10 @@ void apt_plan_destroy(apt_plan_t* plan) {
         for (int i = 0; i < apt_plan::MAX_SEG; i++) if (plan->ev_seg[k][i]) cudaEventDestroy(plan->ev_seg[k][i]);
     }
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    if (plan->tr_origin) cudaEventDestroy(plan->tr_origin);
+    if (plan->tr_end) cudaEventDestroy(plan->tr_end);
+    for (int k = 0; k < apt_plan::SK_N; k++) for (int i = 0; i < apt_plan::MAX_SEG; i++) for (int j = 0; j < 2; j++)
+        if (plan->tr_ev[k][i][j]) cudaEventDestroy(plan->tr_ev[k][i][j]);
     for (int i = 0; i < apt_plan::N_RING; i++) if (plan->ring[i]) cudaFreeHost(plan->ring[i]);
     for (auto& m : plan->marks) cudaEventDestroy(m.second);
     delete plan;
@@ -513,6 +537,32 @@ int apt_plan_enable_timing(apt_plan_t* plan, int enable) {
     for (auto& m : plan->marks) cudaEventDestroy(m.second);
     plan->marks.clear();
     for (int i = 0; i < APT_N_KERNELS; i++) plan->kernel_ms[i] = 0.0f;
+    return 0;
+}
+
+int apt_plan_enable_trace(apt_plan_t* plan, int enable) {
+    if (!plan) return -1;
+    if (enable && !plan->tr_origin) {
+        if (cudaEventCreate(&plan->tr_origin) != cudaSuccess || cudaEventCreate(&plan->tr_end) != cudaSuccess) return -10;
+        for (int k = 0; k < apt_plan::SK_N; k++) for (int i = 0; i < apt_plan::MAX_SEG; i++) for (int j = 0; j < 2; j++)
+            if (cudaEventCreate(&plan->tr_ev[k][i][j]) != cudaSuccess) return -10;
+    }
+    plan->trace = enable != 0;
+    plan->tr_nseg = 0;
+    return 0;
+}
+
+int apt_plan_trace(apt_plan_t* plan, float* out_ms, int* n_seg, float* total_ms) {
+    if (!plan || !out_ms || !n_seg || !total_ms) return -1;
+    *n_seg = plan->tr_nseg;
+    *total_ms = 0.0f;
+    if (!plan->tr_nseg) return 0;
+    cudaEventElapsedTime(total_ms, plan->tr_origin, plan->tr_end);
+    for (int k = 0; k < apt_plan::SK_N; k++) for (int i = 0; i < plan->tr_nseg; i++) for (int j = 0; j < 2; j++) {
+        float ms = -1.0f;
+        if (cudaEventElapsedTime(&ms, plan->tr_origin, plan->tr_ev[k][i][j]) != cudaSuccess) { ms = -1.0f; cudaGetLastError(); }
+        out_ms[(k * apt_plan::MAX_SEG + i) * 2 + j] = ms;
+    }
     return 0;
 }
 
@@ -574,23 +624,44 @@ static cudaError_t launch_stft_generic(apt_plan* pl, const Batch& b, const PCM* 
     return cudaGetLastError();
 }
 
-template <int NS, typename PCM>
+template <int NS, typename PCM, typename R>
 static cudaError_t launch_td_ns(apt_plan* pl, const Batch& b, dim3 grid, const PCM* pcm, const TdOut& to, cudaStream_t st) {
     if (grid.x == 0) return cudaSuccess;
-    auto kern = td_features_kernel<NS, PCM>;
+    auto kern = td_features_kernel<NS, PCM, R>;
+    const size_t smem = sizeof(R) == 8 ? pl->td_smem : pl->td_smem_f32;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, TD_NT, smem, st>>>(pl->dp, b, pcm, pl->d_td_tile_off.p, pl->tdt, to);
+    pl->last_launches++;
+    return cudaGetLastError();
+}
+template <typename PCM, typename R>
+static cudaError_t launch_td(apt_plan* pl, const Batch& b, dim3 grid, const PCM* pcm, const TdOut& to, cudaStream_t st) {
+    switch (pl->td_ns) {
+        case 1: return launch_td_ns<1, PCM, R>(pl, b, grid, pcm, to, st);
+        case 2: return launch_td_ns<2, PCM, R>(pl, b, grid, pcm, to, st);
+        case 3: return launch_td_ns<3, PCM, R>(pl, b, grid, pcm, to, st);
+        case 4: return launch_td_ns<4, PCM, R>(pl, b, grid, pcm, to, st);
+    }
+    return cudaErrorInvalidValue;
+}
+template <int NS, typename PCM>
+static cudaError_t launch_td_recheck_ns(apt_plan* pl, const Batch& b, const PCM* pcm, const TdOut& to, cudaStream_t st) {
+    auto kern = td_recheck_kernel<NS, PCM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->td_smem);
     if (e != cudaSuccess) return e;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(to.list_cap, 2 * (int64_t)pl->ctx->sm_count));
     kern<<<grid, TD_NT, pl->td_smem, st>>>(pl->dp, b, pcm, pl->d_td_tile_off.p, pl->tdt, to);
     pl->last_launches++;
     return cudaGetLastError();
 }
 template <typename PCM>
-static cudaError_t launch_td(apt_plan* pl, const Batch& b, dim3 grid, const PCM* pcm, const TdOut& to, cudaStream_t st) {
+static cudaError_t launch_td_recheck(apt_plan* pl, const Batch& b, const PCM* pcm, const TdOut& to, cudaStream_t st) {
     switch (pl->td_ns) {
-        case 1: return launch_td_ns<1, PCM>(pl, b, grid, pcm, to, st);
-        case 2: return launch_td_ns<2, PCM>(pl, b, grid, pcm, to, st);
-        case 3: return launch_td_ns<3, PCM>(pl, b, grid, pcm, to, st);
-        case 4: return launch_td_ns<4, PCM>(pl, b, grid, pcm, to, st);
+        case 1: return launch_td_recheck_ns<1, PCM>(pl, b, pcm, to, st);
+        case 2: return launch_td_recheck_ns<2, PCM>(pl, b, pcm, to, st);
+        case 3: return launch_td_recheck_ns<3, PCM>(pl, b, pcm, to, st);
+        case 4: return launch_td_recheck_ns<4, PCM>(pl, b, pcm, to, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -676,8 +747,16 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     }
     cudaStream_t S[apt_plan::SK_N];
     for (int k = 0; k < apt_plan::SK_N; k++) S[k] = piped ? pl->s_kind[k] : st;
+    // The two bulk kernels share ONE stream (STFT of a segment, then its TD kernel): run side by side they take 95 ms
+    // for the 1 000-clip batch, back to back 67 ms (both live on the FP64 pipe and on most of an SM's shared memory;
+    // profiles/r2/trace_*.txt) -- the chain kernels are what overlaps them.
+    S[apt_plan::SK_TD] = S[apt_plan::SK_STFT];
     // record on the producing kind's stream / wait on the consuming kind's stream (no-ops on one stream)
-    auto rec = [&](int kind, int sg) -> cudaError_t { return piped ? cudaEventRecord(pl->ev_seg[kind][sg], S[kind]) : cudaSuccess; };
+    auto rec = [&](int kind, int sg) -> cudaError_t {
+        if (!piped) return cudaSuccess;
+        if (pl->trace) cudaEventRecord(pl->tr_ev[kind][sg][1], S[kind]);
+        return cudaEventRecord(pl->ev_seg[kind][sg], S[kind]);
+    };
     auto wait = [&](int kind, int on, int sg) -> cudaError_t { return piped ? cudaStreamWaitEvent(S[kind], pl->ev_seg[on][sg], 0) : cudaSuccess; };
 
     const Trk1Tab& tab = dbg ? pl->tab_all : pl->tab_modes;
@@ -686,8 +765,13 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     uint32_t* hist = pl->d_hist.p;
     const size_t hist_bytes = sizeof(uint32_t) * (size_t)n_clips * 2 * SEL_BINS;
     TdOut to;
+    memset(&to, 0, sizeof(to));
     to.td = out->td ? out->td : pl->d_td.p; to.x_td = out->x_td; to.nF = pl->nF;
     to.want_block = out->td != nullptr; to.want_kurt = (out->td != nullptr) || d.has_ku;
+    // Default flags consume one bit of the TD features per frame (crest > td_gate_threshold): the float32 filter
+    // decides it wherever the crest factor is outside a guard band around the threshold, and the float64 filter
+    // re-decides the tiles holding a frame inside the band -- the gate plane equals the float64 one bit for bit.
+    const bool fast_td = pl->td_fast && !out->td && !out->x_td && !d.has_ku && d.gate_thr != 0.0f;
 
     // start of the run on the caller's stream: selection state and histograms, then the fork
     if (!d.suppressor_bypass) {
@@ -695,10 +779,14 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         select_init_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(b, d.K, pl->d_sel.p);
         pl->last_launches++;
     }
+    const bool tracing = piped && pl->trace;
+    if (tracing) { CUDA_OK(ctx, cudaEventRecord(pl->tr_origin, st)); pl->tr_nseg = n_seg; }
     if (piped) {
         CUDA_OK(ctx, cudaEventRecord(pl->ev_fork, st));
         for (int k = 0; k < apt_plan::SK_N; k++) CUDA_OK(ctx, cudaStreamWaitEvent(S[k], pl->ev_fork, 0));
     }
+    // trace marks: j = 0 before the launch on its stream (after its waits), j = 1 after it
+    auto tmark = [&](int kind, int sg, int j) { if (tracing) cudaEventRecord(pl->tr_ev[kind][sg][j], S[kind]); };
     int rc = 0;
     cudaError_t e = cudaSuccess;
     const char* what = "";
@@ -712,6 +800,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         bs.tile0 = bs.ta / STFT_TF;
         {
             const dim3 g = seg_grid(pl->stft_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / STFT_TF);
+            tmark(apt_plan::SK_STFT, sg, 0);
             RR(pl->prm.fft_f64 ? launch_stft<double, PCM>(pl, bs, g, pcm, so, S[apt_plan::SK_STFT]) : launch_stft<float, PCM>(pl, bs, g, pcm, so, S[apt_plan::SK_STFT]));
             RR(rec(apt_plan::SK_STFT, sg));
         }
@@ -720,7 +809,23 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         bs.tile0 = bs.ta / TD_FT;
         {
             const dim3 g = seg_grid(pl->td_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / TD_FT);
-            RR(launch_td<PCM>(pl, bs, g, pcm, to, S[apt_plan::SK_TD]));
+            tmark(apt_plan::SK_TD, sg, 0);
+            if (fast_td) {
+                TdOut tf = to;
+                tf.td = nullptr; tf.want_block = 0; tf.want_kurt = 0;
+                tf.gate = pl->d_gate.p; tf.crest_dbg = out->td_fast_crest; tf.guard = pl->td_guard;
+                // flagged tiles of this segment: its own slice of the list (at most every tile of the segment) and counter
+                const int64_t per_seg = n_seg == 1 ? pl->td_list_cap : (int64_t)(seg_frames / TD_FT) * n_clips;
+                const int64_t off = std::min<int64_t>((int64_t)sg * per_seg, pl->td_list_cap);
+                tf.list = pl->d_td_list.p + off;
+                tf.list_cap = (int)std::min<int64_t>(per_seg, pl->td_list_cap - off);
+                tf.list_count = pl->d_td_cnt.p + sg;
+                RR(cudaMemsetAsync(tf.list_count, 0, sizeof(int), S[apt_plan::SK_TD]));
+                RR(launch_td<PCM, float>(pl, bs, g, pcm, tf, S[apt_plan::SK_TD]));
+                if (g.x > 0 && tf.list_cap > 0) RR(launch_td_recheck<PCM>(pl, bs, pcm, tf, S[apt_plan::SK_TD]));
+            } else {
+                RR(launch_td<PCM, double>(pl, bs, g, pcm, to, S[apt_plan::SK_TD]));
+            }
             RR(rec(apt_plan::SK_TD, sg));
         }
         // tracker pass 1 on the mode bins (every band bin when one of its planes is requested)
@@ -731,6 +836,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             io.state = pl->d_st_trk1.p; io.state_stride = pl->st_stride;
             const int64_t lanes = (int64_t)n_clips * tab.n_lanes;
             RR(wait(apt_plan::SK_TRK1, apt_plan::SK_STFT, sg));
+            tmark(apt_plan::SK_TRK1, sg, 0);
             if (e == cudaSuccess) {
                 trk1_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, S[apt_plan::SK_TRK1]>>>(pl->dp, bs, tab, io);
                 pl->last_launches++;
@@ -748,6 +854,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             const dim3 g = seg_grid(pl->flux_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / FLUX_FT);
             const size_t fsm = flux_smem_bytes(d.K, tab.n_lanes, tab.nls);
             RR(wait(apt_plan::SK_FLUX, d.use_norm ? apt_plan::SK_TRK1 : apt_plan::SK_STFT, sg));
+            tmark(apt_plan::SK_FLUX, sg, 0);
             if (g.x > 0 && e == cudaSuccess) {
                 RR(cudaFuncSetAttribute(flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
                 if (e == cudaSuccess) {
@@ -763,6 +870,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         {
             const int64_t lanes = (int64_t)n_clips * (d.M + 1);
             RR(wait(apt_plan::SK_BASE, apt_plan::SK_FLUX, sg));
+            tmark(apt_plan::SK_BASE, sg, 0);
             if (e == cudaSuccess) {
                 base_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, S[apt_plan::SK_BASE]>>>(pl->dp, bs, pl->d_mf.p, pl->mf_stride, pl->d_st_base.p);
                 pl->last_launches++;
@@ -774,12 +882,13 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         pl->mark(APT_KERNEL_DECIDE, st);
         {
             DecIO io;
-            io.mf = pl->d_mf.p; io.stride = pl->mf_stride; io.td = to.td; io.gate_in = nullptr;
+            io.mf = pl->d_mf.p; io.stride = pl->mf_stride; io.td = to.td; io.gate_in = fast_td ? pl->d_gate.p : nullptr;
             io.frame_class = out->frame_class; io.rain_conf = out->rain_conf; io.noise_conf = out->noise_conf;
             io.norm_flux = out->norm_flux; io.score = out->score; io.gate = out->gate; io.nF = pl->nF;
             const int64_t fr = std::min<int64_t>(maxT - bs.ta, n_seg == 1 ? maxT : seg_frames);
             RR(wait(apt_plan::SK_DEC, apt_plan::SK_BASE, sg));
             RR(wait(apt_plan::SK_DEC, apt_plan::SK_TD, sg));
+            tmark(apt_plan::SK_DEC, sg, 0);
             if (fr > 0 && e == cudaSuccess) {
                 decide_kernel<<<dim3((unsigned)((fr + 255) / 256), (unsigned)n_clips), 256, 0, S[apt_plan::SK_DEC]>>>(pl->dp, bs, io);
                 pl->last_launches++;
@@ -802,6 +911,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             // are faster there when the kernel has the GPU to itself (1 000 x 71 lanes: 10.8 -> 9.7 ms).
             const double warps_per_sm = (double)((lanes + 31) / 32) / (double)std::max(1, ctx->sm_count);
             RR(wait(apt_plan::SK_TRK2, apt_plan::SK_DEC, sg));
+            tmark(apt_plan::SK_TRK2, sg, 0);
             if (e == cudaSuccess) {
                 if (!piped && warps_per_sm > 12.0 && warps_per_sm <= 16.0) {
                     RR(cudaFuncSetAttribute(trk2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
@@ -817,6 +927,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             bs.tile0 = bs.ta / DB_CF;
             const dim3 g = seg_grid(pl->sel_chunk_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / DB_CF);
             RR(wait(apt_plan::SK_DBS, apt_plan::SK_TRK2, sg));
+            tmark(apt_plan::SK_DBS, sg, 0);
             if (g.x > 0 && e == cudaSuccess) {
                 dbsum_kernel<<<g, 256, 0, S[apt_plan::SK_DBS]>>>(pl->dp, bs, n2_plane, pl->d_sel_chunk_off.p, hist, pl->d_dbsum.p);
                 pl->last_launches++;
@@ -883,7 +994,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         // clips whose candidates overflow go through the full 3-level radix select (no-ops for the others)
         pl->mark(APT_KERNEL_SELECT, st);
         const dim3 gall = seg_grid(pl->sel_chunk_off, clip0, n_clips, 0, INT64_MAX);
-        sel_scan0_kernel<<<(n_clips * 32 + 127) / 128, 128, 0, st>>>(clip0, n_clips, pl->d_sel.p, hist);
+        sel_scan0_kernel<<<(n_clips * 32 + 127) / 128, 128, 0, st>>>(clip0, n_clips, d.eps32, pl->d_sel.p, hist);
         sel_collect_kernel<<<gall, 256, 0, st>>>(pl->dp, bw, n2_plane, pl->d_sel_chunk_off.p, pl->d_sel.p, pl->d_cand_off.p, pl->d_cand.p);
         sel_final_kernel<<<n_clips, 256, 0, st>>>(clip0, pl->d_sel.p, pl->d_cand_off.p, pl->d_cand.p);
         pl->last_launches += 3;
@@ -901,6 +1012,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     pl->last_launches++;
     CUDA_OK(ctx, cudaGetLastError());
     pl->mark(-1, st);
+    if (tracing) cudaEventRecord(pl->tr_end, st);
     return 0;
 }
 
@@ -1031,14 +1143,25 @@ struct StagePool {
             c++;
         }
     }
+    std::vector<char> skipped;        // groups that need no staging
+    void skip(int g) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            skipped[g] = 1;
+            go = g + 1;
+        }
+        cv.notify_all();
+    }
     void worker(int tid) {
         for (int g = 0; g < n_groups; g++) {
+            bool sk;
             {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return go > g || stop; });
                 if (stop) return;
+                sk = skipped[g] != 0;
             }
-            copy_share(g, tid);
+            if (!sk) copy_share(g, tid);
             {
                 std::lock_guard<std::mutex> lk(mu);
                 done[g]++;
@@ -1048,6 +1171,7 @@ struct StagePool {
     }
     void start() {
         done.assign(n_groups, 0);
+        skipped.assign(n_groups, 0);
         for (int i = 0; i < n_thr; i++) th.emplace_back([this, i] { worker(i); });
     }
     void release_and_wait(int g) {
@@ -1079,28 +1203,54 @@ static int run_host_clips_impl(apt_plan* pl, const void* const* clips, const Hos
         const int c0 = (int)((int64_t)pl->n_clips * g / n_groups), c1 = (int)((int64_t)pl->n_clips * (g + 1) / n_groups);
         max_bytes = std::max(max_bytes, (size_t)(pl->samp_off[c1] - pl->samp_off[c0]) * sizeof(PCM));
     }
-    if (pl->ring_bytes < max_bytes) {
-        for (int i = 0; i < apt_plan::N_RING; i++) { if (pl->ring[i]) cudaFreeHost(pl->ring[i]); pl->ring[i] = nullptr; }
-        pl->ring_bytes = 0;
-        for (int i = 0; i < apt_plan::N_RING; i++) CUDA_OK(ctx, cudaHostAlloc(&pl->ring[i], max_bytes, cudaHostAllocDefault));
-        pl->ring_bytes = max_bytes;
-    }
     PCM* d_pcm;
     if constexpr (sizeof(PCM) == 2) { if (!pl->d_pcm.p) CUDA_OK(ctx, pl->d_pcm.alloc((size_t)pl->nS)); d_pcm = pl->d_pcm.p; }
     else { if (!pl->d_pcm_f32.p) CUDA_OK(ctx, pl->d_pcm_f32.alloc((size_t)pl->nS)); d_pcm = pl->d_pcm_f32.p; }
+    // staging is bound by the host's memory bandwidth, not by cores: every hardware thread helps up to ~24
+    // (16-vCPU box: 8 threads 437 ms, 16 threads 351 ms, 24 threads 340 ms for 13.4 GB; profiles/r2/staging.txt)
     int n_thr = (int)std::thread::hardware_concurrency();
-    n_thr = std::max(1, std::min(16, n_thr > 2 ? n_thr / 2 : 1));
+    n_thr = std::max(1, std::min(24, n_thr));
     if (const char* e = getenv("APT_STAGE_THREADS")) n_thr = std::max(1, std::min(64, atoi(e)));
     StagePool pool;
     pool.pl = pl; pool.clips = clips; pool.esz = sizeof(PCM); pool.n_groups = n_groups; pool.n_thr = n_thr;
-    pool.start();
     std::vector<cudaEvent_t> slot_free(n_groups, nullptr);   // recorded after the host->device copy of group g
-    auto feed = [&](int g, int, int, PCM* dst, size_t bytes) -> cudaError_t {
-        cudaError_t e = cudaSuccess;
-        if (g >= apt_plan::N_RING) {   // the slot's previous copy must have left the pinned buffer
-            e = cudaEventSynchronize(slot_free[g - apt_plan::N_RING]);
-            if (e != cudaSuccess) return e;
+    // a group whose clips already sit back to back in page-locked memory (a loader that filled one pinned buffer, e.g.
+    // parse.Mark3BatchLoader) goes to the device straight from there
+    auto direct = [&](int c0, int c1) -> bool {
+        for (int c = c0; c + 1 < c1; c++)
+            if ((const char*)clips[c + 1] != (const char*)clips[c] + (size_t)pl->len[c] * sizeof(PCM)) return false;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, clips[c0]) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    std::vector<char> is_direct(n_groups, 0);
+    bool any_staged = false;
+    for (int g = 0; g < n_groups; g++) {
+        const int c0 = (int)((int64_t)pl->n_clips * g / n_groups), c1 = (int)((int64_t)pl->n_clips * (g + 1) / n_groups);
+        is_direct[g] = direct(c0, c1) ? 1 : 0;
+        any_staged = any_staged || !is_direct[g];
+    }
+    if (any_staged) {
+        if (pl->ring_bytes < max_bytes) {
+            for (int i = 0; i < apt_plan::N_RING; i++) { if (pl->ring[i]) cudaFreeHost(pl->ring[i]); pl->ring[i] = nullptr; }
+            pl->ring_bytes = 0;
+            for (int i = 0; i < apt_plan::N_RING; i++) CUDA_OK(ctx, cudaHostAlloc(&pl->ring[i], max_bytes, cudaHostAllocDefault));
+            pl->ring_bytes = max_bytes;
         }
+    }
+    auto feed = [&](int g, int c0, int, PCM* dst, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaSuccess;
+        if (is_direct[g]) {
+            pool.skip(g);
+            return cudaMemcpyAsync(dst, clips[c0], bytes, cudaMemcpyHostToDevice, pl->s_copy);
+        }
+        // the slot's previous copy (the latest staged group with the same slot) must have left the pinned buffer
+        for (int j = g - apt_plan::N_RING; j >= 0; j -= apt_plan::N_RING)
+            if (slot_free[j]) {
+                e = cudaEventSynchronize(slot_free[j]);
+                if (e != cudaSuccess) return e;
+                break;
+            }
         pool.release_and_wait(g);
         e = cudaMemcpyAsync(dst, pl->ring[g % apt_plan::N_RING], bytes, cudaMemcpyHostToDevice, pl->s_copy);
         if (e != cudaSuccess) return e;
@@ -1108,6 +1258,7 @@ static int run_host_clips_impl(apt_plan* pl, const void* const* clips, const Hos
         if (e != cudaSuccess) return e;
         return cudaEventRecord(slot_free[g], pl->s_copy);
     };
+    pool.start();            // no early return between here and finish(): the helper threads must be joined
     const int rc = run_host_impl<PCM>(pl, d_pcm, feed, ho);
     pool.finish();
     for (auto& e : slot_free) if (e) cudaEventDestroy(e);

@@ -583,7 +583,15 @@ struct TdTables {
     // scan and the response pass use them as FMA operands without any load on the dependent path
     double Hc[TD_CHUNK * 4];   // [chunk][4]
     double Adc[5 * 16];        // [k][4][4]  A^(2^k), k = 0..4
+    float Hcf[TD_CHUNK * 4];   // the same tables rounded to float32 (float32 fast path)
+    float Adcf[5 * 16];
 };
+template <typename R> __device__ __forceinline__ R td_Hc(const TdTables& tb, int i);
+template <> __device__ __forceinline__ double td_Hc<double>(const TdTables& tb, int i) { return tb.Hc[i]; }
+template <> __device__ __forceinline__ float td_Hc<float>(const TdTables& tb, int i) { return tb.Hcf[i]; }
+template <typename R> __device__ __forceinline__ R td_Adc(const TdTables& tb, int i);
+template <> __device__ __forceinline__ double td_Adc<double>(const TdTables& tb, int i) { return tb.Adc[i]; }
+template <> __device__ __forceinline__ float td_Adc<float>(const TdTables& tb, int i) { return tb.Adcf[i]; }
 
 struct TdOut {
     float* td;       // [5][nF]  (rows: crest, kurtosis, block crest, block width, block post/pre)
@@ -591,24 +599,36 @@ struct TdOut {
     int64_t nF;
     int want_kurt;   // compute kurtosis
     int want_block;  // compute block features
+    // Gate mode (default flags: the decision only consumes `crest > td_gate_threshold`).  gate != NULL: the kernel
+    // writes the gate byte of every frame instead of the feature rows.  The float32 instantiation also appends the
+    // (clip, tile) of every tile holding a frame whose crest factor lies within `guard` (relative) of the threshold
+    // to `list`; the float64 instantiation launched in list mode then recomputes exactly those tiles and overwrites
+    // their gate bytes, so the gate plane equals the float64 one bit for bit.
+    uint8_t* gate;   // [nF]
+    float* crest_dbg;// [nF] optional: the crest factor as the gate-mode kernel computed it (diagnostic plane)
+    float guard;
+    int2* list;      // [list_cap] flagged (clip, tile) pairs of this launch
+    int* list_count;
+    int list_cap;
 #ifdef APT_PROFILE_PHASES
     long long* dbg;  // [16] clock64 stamps of one interior tile (profiling builds only)
 #endif
 };
 
 
-inline size_t td_smem_bytes(int ns, int env_cap) {
-    return sizeof(float) * TD_XF + sizeof(double) * ((size_t)2 * ns * (TD_NT / 32) + 32 * 4 * ns * ns + (size_t)TD_CHUNK * 2 * ns + 2 * (size_t)env_cap);
+inline size_t td_smem_bytes(int ns, int env_cap, size_t real_bytes = sizeof(double)) {
+    return sizeof(float) * TD_XF + real_bytes * ((size_t)2 * ns * (TD_NT / 32) + 32 * 4 * ns * ns + (size_t)TD_CHUNK * 2 * ns) + 8 +
+           sizeof(double) * 2 * (size_t)env_cap;
 }
 
-// one biquad cascade step (DF2T), float64, FMAs allowed (not bit-compared; 1e-16 level)
-template <int NS>
-__device__ __forceinline__ double sos_step(const double (&c)[NS][6], double (&z)[NS][2], double x) {
+// one biquad cascade step (DF2T) in the working precision R, FMAs allowed (not bit-compared; 1e-16 level in float64)
+template <int NS, typename R>
+__device__ __forceinline__ R sos_step(const R (&c)[NS][6], R (&z)[NS][2], R x) {
 #pragma unroll
     for (int s = 0; s < NS; s++) {
-        double y = d_fma(c[s][0], x, z[s][0]);
-        z[s][0] = d_fma(-c[s][4], y, d_fma(c[s][1], x, z[s][1]));
-        z[s][1] = d_fma(-c[s][5], y, c[s][2] * x);
+        R y = t_fma(c[s][0], x, z[s][0]);
+        z[s][0] = t_fma(-c[s][4], y, t_fma(c[s][1], x, z[s][1]));
+        z[s][1] = t_fma(-c[s][5], y, c[s][2] * x);
         x = y;
     }
     return x;
@@ -620,6 +640,10 @@ __device__ __forceinline__ double shfl_up_d(double v, int d) {
 __device__ __forceinline__ double shfl_down_d(double v, int d) {
     return __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(v), d), __shfl_down_sync(0xffffffffu, __double2loint(v), d));
 }
+__device__ __forceinline__ float to_f32(double v) { return d2f(v); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float shfl_up_d(float v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ float shfl_down_d(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 
 // One filter direction over the register-resident chunks.  Chunks are ordered by thread index (forward)
 // or reverse thread index (REV); `ia` is the last thread holding samples.  The first chunk of the order
@@ -630,10 +654,10 @@ __device__ __forceinline__ double shfl_down_d(double v, int d) {
 // state (older warps contribute A^32 and beyond, below 1e-20 by the plan-time decay check);
 // (3) the homogeneous response to the incoming state is added to the chunk.
 // s_Alin: [DIM*DIM][32] powers A^e, e = 0..31, component-major.  s_vend: [DIM][TD_NT/32].
-template <int NS, bool REV>
-__device__ __forceinline__ void iir_pass(const DevParams& p, const TdTables& tb, const double* __restrict__ s_Alin,
-                                         const double* __restrict__ s_H, double (&y)[TD_CHUNK], int n_mine,
-                                         bool has_init, double xe, int ia, double* __restrict__ s_vend) {
+template <int NS, bool REV, typename R>
+__device__ __forceinline__ void iir_pass(const DevParams& p, const TdTables& tb, const R* __restrict__ s_Alin,
+                                         const R* __restrict__ s_H, R (&y)[TD_CHUNK], int n_mine,
+                                         bool has_init, R xe, int ia, R* __restrict__ s_vend) {
     constexpr int DIM = 2 * NS;
     constexpr int NW = TD_NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -644,39 +668,39 @@ __device__ __forceinline__ void iir_pass(const DevParams& p, const TdTables& tb,
     const int pos = REV ? la - lane : lane;
     const bool first_chunk = REV ? (tid == ia) : (tid == 0);
     const bool has_prev_warp = REV ? (w < wa) : (w > 0);
-    double coef[NS][6];
+    R coef[NS][6];
 #pragma unroll
     for (int s = 0; s < NS; s++)
 #pragma unroll
-        for (int j = 0; j < 6; j++) coef[s][j] = p.sos[s][j];
-    double z[NS][2];
+        for (int j = 0; j < 6; j++) coef[s][j] = (R)p.sos[s][j];
+    R z[NS][2];
     {
-        const double x0 = (has_init && first_chunk) ? xe : 0.0;
+        const R x0 = (has_init && first_chunk) ? xe : (R)0;
 #pragma unroll
-        for (int s = 0; s < NS; s++) { z[s][0] = p.zi[s][0] * x0; z[s][1] = p.zi[s][1] * x0; }
+        for (int s = 0; s < NS; s++) { z[s][0] = (R)p.zi[s][0] * x0; z[s][1] = (R)p.zi[s][1] * x0; }
     }
     if (n_mine == TD_CHUNK) {
 #pragma unroll
         for (int jj = 0; jj < TD_CHUNK; jj++) {
             const int j = REV ? TD_CHUNK - 1 - jj : jj;
-            y[j] = sos_step<NS>(coef, z, y[j]);
+            y[j] = sos_step<NS, R>(coef, z, y[j]);
         }
     } else if (n_mine > 0) {
 #pragma unroll
         for (int jj = 0; jj < TD_CHUNK; jj++) {
             const int j = REV ? TD_CHUNK - 1 - jj : jj;
-            if (j < n_mine) y[j] = sos_step<NS>(coef, z, y[j]);
+            if (j < n_mine) y[j] = sos_step<NS, R>(coef, z, y[j]);
         }
     }
     APT_STAMP2(REV ? 10 : 0);
     // (2) scan.  v = chunk-final state (zero for threads without samples)
-    double v[DIM];
+    R v[DIM];
 #pragma unroll
-    for (int r = 0; r < DIM; r++) v[r] = active ? z[r >> 1][r & 1] : 0.0;
+    for (int r = 0; r < DIM; r++) v[r] = active ? z[r >> 1][r & 1] : (R)0;
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         const int d = 1 << k;
-        double u[DIM];
+        R u[DIM];
 #pragma unroll
         for (int q = 0; q < DIM; q++) u[q] = REV ? shfl_down_d(v[q], d) : shfl_up_d(v[q], d);
         if (active && pos >= d) {
@@ -684,8 +708,8 @@ __device__ __forceinline__ void iir_pass(const DevParams& p, const TdTables& tb,
             for (int r = 0; r < DIM; r++)
 #pragma unroll
                 for (int q = 0; q < DIM; q++) {
-                    const double a = (NS <= 2) ? tb.Adc[k * 16 + r * DIM + q] : s_Alin[(r * DIM + q) * 32 + d];
-                    v[r] = d_fma(a, u[q], v[r]);
+                    const R a = (NS <= 2) ? td_Adc<R>(tb, k * 16 + r * DIM + q) : s_Alin[(r * DIM + q) * 32 + d];
+                    v[r] = t_fma(a, u[q], v[r]);
                 }
         }
     }
@@ -696,24 +720,24 @@ __device__ __forceinline__ void iir_pass(const DevParams& p, const TdTables& tb,
         for (int r = 0; r < DIM; r++) s_vend[r * NW + w] = v[r];
     }
     // scanned state of the previous chunk inside the warp
-    double sin_[DIM];
+    R sin_[DIM];
 #pragma unroll
     for (int r = 0; r < DIM; r++) {
-        const double nb = REV ? shfl_down_d(v[r], 1) : shfl_up_d(v[r], 1);
-        sin_[r] = (pos >= 1) ? nb : 0.0;
+        const R nb = REV ? shfl_down_d(v[r], 1) : shfl_up_d(v[r], 1);
+        sin_[r] = (pos >= 1) ? nb : (R)0;
     }
     __syncthreads();
     if (active && has_prev_warp && pos >= 0) {
-        double ve[DIM];
+        R ve[DIM];
 #pragma unroll
         for (int q = 0; q < DIM; q++) ve[q] = s_vend[q * NW + (REV ? w + 1 : w - 1)];
 #pragma unroll
         for (int r = 0; r < DIM; r++) {
-            double arow[DIM];   // the row's loads are issued together, ahead of its FMA chain
+            R arow[DIM];   // the row's loads are issued together, ahead of its FMA chain
 #pragma unroll
             for (int q = 0; q < DIM; q++) arow[q] = s_Alin[(r * DIM + q) * 32 + pos];
 #pragma unroll
-            for (int q = 0; q < DIM; q++) sin_[r] = d_fma(arow[q], ve[q], sin_[r]);
+            for (int q = 0; q < DIM; q++) sin_[r] = t_fma(arow[q], ve[q], sin_[r]);
         }
     }
     APT_STAMP2(REV ? 12 : 2);
@@ -723,11 +747,11 @@ __device__ __forceinline__ void iir_pass(const DevParams& p, const TdTables& tb,
 #pragma unroll
             for (int j = 0; j < TD_CHUNK; j++) {
                 const int m = REV ? TD_CHUNK - 1 - j : j;
-                double acc = 0.0;
+                R acc = (R)0;
 #pragma unroll
                 for (int r = 0; r < DIM; r++) {
-                    const double h = (NS <= 2) ? tb.Hc[m * DIM + r] : s_H[m * DIM + r];
-                    acc = (r == 0) ? h * sin_[0] : d_fma(h, sin_[r], acc);
+                    const R h = (NS <= 2) ? td_Hc<R>(tb, m * DIM + r) : s_H[m * DIM + r];
+                    acc = (r == 0) ? h * sin_[0] : t_fma(h, sin_[r], acc);
                 }
                 y[j] += acc;
             }
@@ -736,10 +760,10 @@ __device__ __forceinline__ void iir_pass(const DevParams& p, const TdTables& tb,
             for (int j = 0; j < TD_CHUNK; j++) {
                 const int m = REV ? TD_CHUNK - 1 - j : j;
                 if (j < n_mine) {
-                    const double* h = s_H + m * DIM;
-                    double acc = h[0] * sin_[0];
+                    const R* h = s_H + m * DIM;
+                    R acc = h[0] * sin_[0];
 #pragma unroll
-                    for (int r = 1; r < DIM; r++) acc = d_fma(h[r], sin_[r], acc);
+                    for (int r = 1; r < DIM; r++) acc = t_fma(h[r], sin_[r], acc);
                     y[j] += acc;
                 }
             }
@@ -798,26 +822,23 @@ __device__ double td_peak_width_half(X x, int n, int peak) {
 // once fall into different banks.
 __device__ __forceinline__ int td_xf_pos(int u) { return u + ((u >> 7) << 3); }
 
-template <int NS, typename PCM>
-__global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_constant__ DevParams p, Batch b,
-                                                               const PCM* __restrict__ pcm,
-                                                               const int64_t* __restrict__ tile_off, const __grid_constant__ TdTables tb, TdOut o) {
+// One tile (clip c, tile index `tile`) in the working precision R of the filter.
+template <int NS, typename PCM, typename R>
+__device__ __forceinline__ void td_tile(const DevParams& p, const Batch& b, const PCM* __restrict__ pcm,
+                                        const int64_t* __restrict__ tile_off, const TdTables& tb, const TdOut& o,
+                                        const int c, const int tile, unsigned char* smem_raw) {
     constexpr int DIM = 2 * NS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_vend = reinterpret_cast<double*>(smem_raw);           // [DIM][TD_NT/32] warp-final scan states
-    double* s_A = s_vend + DIM * (TD_NT / 32);                      // [DIM*DIM][32] powers of the chunk transition
-    double* s_H = s_A + 32 * DIM * DIM;                             // [TD_CHUNK][DIM]
-    double* s_renv = s_H + TD_CHUNK * DIM;                          // [env_cap] raw block envelope (want_block)
+    R* s_vend = reinterpret_cast<R*>(smem_raw);                     // [DIM][TD_NT/32] warp-final scan states
+    R* s_A = s_vend + DIM * (TD_NT / 32);                           // [DIM*DIM][32] powers of the chunk transition
+    R* s_H = s_A + 32 * DIM * DIM;                                  // [TD_CHUNK][DIM]
+    double* s_renv = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_H + TD_CHUNK * DIM) + 7) & ~(uintptr_t)7);   // [env_cap] raw block envelope (want_block)
     double* s_env = s_renv + tb.env_cap;                            // [env_cap] smoothed block envelope
     float* s_x = reinterpret_cast<float*>(s_env + tb.env_cap);      // [TD_XF] staged PCM, then the float32 result
     __shared__ float s_bsum[TD_FT + 1], s_bmax[TD_FT + 1];
+    __shared__ int s_near;
     const int L = p.n_fft, hop = p.hop;   // 256 / 128 (enforced by the plan)
 
     const int tid = threadIdx.x;
-    int64_t tile_in_clip;
-    int c;
-    if (!tile_clip(b, tile_off, c, tile_in_clip)) return;
-    const int tile = (int)tile_in_clip;
     const int64_t base = __ldg(b.samp_off + c);
     const int64_t N = __ldg(b.samp_off + c + 1) - base;
     const int64_t f0 = __ldg(b.frame_off + c);
@@ -827,6 +848,7 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
     const int t0 = tile * TD_FT, t1 = min(Tloc, t0 + TD_FT);
     const bool last = tile == n_tiles - 1;
     const int pad = p.padlen;
+    if (tid == 0) s_near = 0;
 
     // valid x_td range of this tile (clip-relative), then the filter buffer around it
     int64_t vs = (int64_t)t0 * hop - tb.halo; if (vs < 0 || tile == 0) vs = 0;
@@ -837,8 +859,8 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
     const bool exact_l = bs == -pad, exact_r = be == N + pad;
 
     APT_STAMP(0);
-    for (int i = tid; i < 32 * DIM * DIM; i += TD_NT) s_A[i] = __ldg(tb.Alin + i);
-    for (int i = tid; i < TD_CHUNK * DIM; i += TD_NT) s_H[i] = __ldg(tb.H + i);
+    for (int i = tid; i < 32 * DIM * DIM; i += TD_NT) s_A[i] = (R)__ldg(tb.Alin + i);
+    for (int i = tid; i < TD_CHUNK * DIM; i += TD_NT) s_H[i] = (R)__ldg(tb.H + i);
     // stage the in-clip part of the buffer as float32 (coalesced 128-bit loads); zeros behind it
     const bool interior = bs >= 0 && be <= N;
     int sh = 0;   // shift of the staged samples that makes the 128-bit staging stores aligned
@@ -862,19 +884,19 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
     // Samples beyond the clip ends are scipy's odd extension 2*x[0]-x[i], 2*x[N-1]-x[N-1-i] (float64).
     const int a0 = tid * TD_CHUNK;
     const int n_mine = exact_r ? max(0, min(TD_CHUNK, len - a0)) : TD_CHUNK;
-    double y[TD_CHUNK];
+    R y[TD_CHUNK];
     if (interior) {
 #pragma unroll
-        for (int j = 0; j < TD_CHUNK; j++) y[j] = (double)s_x[sh + a0 + j];
+        for (int j = 0; j < TD_CHUNK; j++) y[j] = (R)s_x[sh + a0 + j];
     } else {
 #pragma unroll
         for (int j = 0; j < TD_CHUNK; j++) {
-            double v = 0.0;
+            R v = (R)0;
             if (a0 + j < len) {
                 const int64_t s = bs + a0 + j;
-                if (s < 0) v = 2.0 * (double)load_sample(pcm, base) - (double)load_sample(pcm, base - s);
-                else if (s >= N) v = 2.0 * (double)load_sample(pcm, base + N - 1) - (double)load_sample(pcm, base + 2 * (N - 1) - s);
-                else v = (double)s_x[a0 + j];
+                if (s < 0) v = (R)2 * (R)load_sample(pcm, base) - (R)load_sample(pcm, base - s);
+                else if (s >= N) v = (R)2 * (R)load_sample(pcm, base + N - 1) - (R)load_sample(pcm, base + 2 * (N - 1) - s);
+                else v = (R)s_x[a0 + j];
             }
             y[j] = v;
         }
@@ -882,23 +904,23 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
     __syncthreads();   // s_x is reused for the result below
     APT_STAMP(2);
     const int ia = exact_r ? (len - 1) / TD_CHUNK : TD_NT - 1;   // last thread holding samples
-    iir_pass<NS, false>(p, tb, s_A, s_H, y, n_mine, exact_l, y[0], ia, s_vend);
+    iir_pass<NS, false, R>(p, tb, s_A, s_H, y, n_mine, exact_l, y[0], ia, s_vend);
     APT_STAMP(3);
-    double xe = 0.0;
+    R xe = (R)0;
     if (exact_r) {
         if (tid == ia) {   // scipy seeds the backward pass with zi * (last forward output)
             // through shared memory (s_x is free between the passes): a run-time index into y[] would
             // move the whole register array to local memory
-            double* tmp = reinterpret_cast<double*>(s_x);
+            R* tmp = reinterpret_cast<R*>(s_x);
 #pragma unroll
             for (int j = 0; j < TD_CHUNK; j++) tmp[j] = y[j];
             xe = tmp[n_mine - 1];
         }
     } else if (a0 + TD_CHUNK > len) {   // forward ringing behind the buffer end must not enter the backward pass
 #pragma unroll
-        for (int j = 0; j < TD_CHUNK; j++) if (a0 + j >= len) y[j] = 0.0;
+        for (int j = 0; j < TD_CHUNK; j++) if (a0 + j >= len) y[j] = (R)0;
     }
-    iir_pass<NS, true>(p, tb, s_A, s_H, y, n_mine, exact_r, xe, ia, s_vend);
+    iir_pass<NS, true, R>(p, tb, s_A, s_H, y, n_mine, exact_r, xe, ia, s_vend);
 
     APT_STAMP(4);
     // float32 x_td over the valid range, padded layout
@@ -907,7 +929,7 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
 #pragma unroll
     for (int j = 0; j < TD_CHUNK; j++) {
         const int i = a0 + j;
-        if (i >= voff && i < vend) s_x[td_xf_pos(i + u_off)] = d2f(y[j]);
+        if (i >= voff && i < vend) s_x[td_xf_pos(i + u_off)] = to_f32(y[j]);
     }
     __syncthreads();
     APT_STAMP(5);
@@ -925,7 +947,7 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
     // each block summed with 8 strided accumulators, so every block is summed once and shared by two frames.
     const int grp = tid >> 3, lane = tid & 7;
     const unsigned gmask = 0xffu << ((tid & 31) & ~7);
-    float* crest_o = o.td + f0;
+    float* crest_o = o.td + f0;             // (unused in gate mode)
     float* kurt_o = o.td + o.nF + f0;
     const int nfr = max(0, t1 - t0);
     for (int blk = grp; blk < nfr + 1 && nfr > 0; blk += TD_NT / 8) {
@@ -955,10 +977,30 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
         const double r = (double)rms;
         float cf = d2f((double)pk / (r > p.eps64 ? r : p.eps64));
         if (isnan(cf) || isinf(cf)) cf = 0.0f;
-        crest_o[t] = cf;
-        if (!o.want_kurt) kurt_o[t] = 0.0f;
+        if (o.gate) {
+            o.gate[f0 + t] = cf > p.gate_thr ? 1 : 0;
+            if (o.crest_dbg) o.crest_dbg[f0 + t] = cf;
+            if (o.list && fabsf(cf - p.gate_thr) <= o.guard * fabsf(p.gate_thr)) s_near = 1;   // benign race: all write 1
+        } else {
+            crest_o[t] = cf;
+            if (!o.want_kurt) kurt_o[t] = 0.0f;
+        }
     }
     APT_STAMP(6);
+    if (o.gate) {
+        // frames beyond the TD grid have crest factor 0 (zero-fill alignment, rain_frame_classifier.py:178-194)
+        if (last)
+            for (int t = max(Tloc, 0) + tid; t < T_clip; t += TD_NT) {
+                o.gate[f0 + t] = 0.0f > p.gate_thr ? 1 : 0;
+                if (o.crest_dbg) o.crest_dbg[f0 + t] = 0.0f;
+            }
+        __syncthreads();
+        if (tid == 0 && o.list && s_near) {
+            const int pos = atomicAdd(o.list_count, 1);
+            if (pos < o.list_cap) o.list[pos] = make_int2(c, tile);
+        }
+        return;
+    }
     if (o.want_kurt) {
         // unbiased Pearson kurtosis (scipy.stats.kurtosis(fisher=False, bias=False)), numpy float32 sums
         for (int fr = grp; fr < nfr; fr += TD_NT / 8) {
@@ -1059,6 +1101,36 @@ __global__ void __launch_bounds__(TD_NT, 2) td_features_kernel(const __grid_cons
             o.td[3 * o.nF + f0 + t] = ow;
             o.td[4 * o.nF + f0 + t] = orat;
         }
+    }
+}
+
+
+// grid form: blockIdx.y = clip, blockIdx.x + b.tile0 = tile
+template <int NS, typename PCM, typename R>
+__global__ void __launch_bounds__(TD_NT, (sizeof(R) == 8 ? 2 : 3)) td_features_kernel(const __grid_constant__ DevParams p, Batch b,
+                                                               const PCM* __restrict__ pcm,
+                                                               const int64_t* __restrict__ tile_off, const __grid_constant__ TdTables tb, TdOut o) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int64_t tile_in_clip;
+    int c;
+    if (!tile_clip(b, tile_off, c, tile_in_clip)) return;
+    td_tile<NS, PCM, R>(p, b, pcm, tile_off, tb, o, c, (int)tile_in_clip, smem_raw);
+}
+
+// list form (exact re-check of the float32 fast path): persistent CTAs walk the flagged (clip, tile) pairs
+template <int NS, typename PCM>
+__global__ void __launch_bounds__(TD_NT, 2) td_recheck_kernel(const __grid_constant__ DevParams p, Batch b,
+                                                              const PCM* __restrict__ pcm,
+                                                              const int64_t* __restrict__ tile_off, const __grid_constant__ TdTables tb, TdOut o) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = min(*o.list_count, o.list_cap);
+    TdOut oo = o;
+    oo.list = nullptr;            // the exact pass only rewrites gate bytes
+    oo.crest_dbg = nullptr;       // (the diagnostic plane keeps the float32 values)
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int2 ct = o.list[i];
+        td_tile<NS, PCM, double>(p, b, pcm, tile_off, tb, oo, ct.x, ct.y, smem_raw);
+        __syncthreads();          // shared memory is reused by the next tile
     }
 }
 
@@ -1886,6 +1958,7 @@ struct SelState {
     int bin[2];           // linear bins holding the two middle ranks
     int cnt;              // candidates appended
     int overflow;         // candidate list too small: fallback
+    float v_lo, v_hi;     // noise-PSD range that surely contains every value of those bins (prefilter of the collect pass)
 };
 __device__ __forceinline__ uint32_t db_key(float v) {
     const uint32_t u = f2u(v);
@@ -1982,6 +2055,7 @@ __global__ void select_init_kernel(Batch b, int K, SelState* st) {
     z.brank[0] = z.brank[1] = 0;
     z.bin[0] = z.bin[1] = 0;
     z.cnt = 0; z.overflow = 0;
+    z.v_lo = 0.0f; z.v_hi = 3.0e38f;
     st[c] = z;
 }
 
@@ -2013,7 +2087,7 @@ __device__ __forceinline__ int warp_find_rank(const uint32_t* __restrict__ h, in
     return found;
 }
 
-__global__ void sel_scan0_kernel(int clip0, int n_clips, SelState* st, const uint32_t* __restrict__ hist) {
+__global__ void sel_scan0_kernel(int clip0, int n_clips, float eps32, SelState* st, const uint32_t* __restrict__ hist) {
     const int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (ci >= n_clips) return;
     const int c = clip0 + ci;
@@ -2022,8 +2096,18 @@ __global__ void sel_scan0_kernel(int clip0, int n_clips, SelState* st, const uin
     const int f0 = warp_find_rank(h, SEL_BINS, st[c].rank[0], b0);
     const int f1 = warp_find_rank(h, SEL_BINS, st[c].rank[1], b1);
     if (lane == 0) {
-        st[c].bin[0] = f0 < 0 ? 0 : f0; st[c].bin[1] = f1 < 0 ? 0 : f1;
+        const int q0 = f0 < 0 ? 0 : f0, q1 = f1 < 0 ? 0 : f1;
+        st[c].bin[0] = q0; st[c].bin[1] = q1;
         st[c].brank[0] = st[c].rank[0] - b0; st[c].brank[1] = st[c].rank[1] - b1;
+        // Values of the bins [min, max] have dB values in [lo_db, hi_db): in the noise PSD itself that is
+        // v in [10^(lo_db/10) - eps, 10^(hi_db/10) - eps), widened by 1e-4 relative (0.0004 dB: the float32 log10
+        // polynomial is within 1e-6 dB of the true value).  The end bins are open-ended.
+        const int lo_bin = q0 < q1 ? q0 : q1, hi_bin = q0 < q1 ? q1 : q0;
+        const double lo_db = (double)lo_bin / 16.0 - 96.0, hi_db = (double)(hi_bin + 1) / 16.0 - 96.0;
+        const double vl = (exp10(lo_db / 10.0) - (double)eps32) * (1.0 - 1e-4) - 1e-12;
+        const double vh = (exp10(hi_db / 10.0) - (double)eps32) * (1.0 + 1e-4) + 1e-12;
+        st[c].v_lo = lo_bin <= 0 ? -1.0f : (float)(vl > 0.0 ? vl : -1.0);
+        st[c].v_hi = hi_bin >= SEL_BINS - 1 ? 3.0e38f : (float)vh;
     }
 }
 
@@ -2038,6 +2122,7 @@ __global__ void __launch_bounds__(256) sel_collect_kernel(const __grid_constant_
     if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
     __syncthreads();
     const int bin0 = st[c].bin[0], bin1 = st[c].bin[1];
+    const float v_lo = st[c].v_lo, v_hi = st[c].v_hi;
     const int64_t co = __ldg(cand_off + c);
     const int cap = (int)(__ldg(cand_off + c + 1) - co);
     uint32_t* dst = cand + co;
@@ -2050,14 +2135,18 @@ __global__ void __launch_bounds__(256) sel_collect_kernel(const __grid_constant_
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int i = base + u * 256;
-            v[u] = i < ne ? __ldg(src + i) : 1.0f;
+            v[u] = i < ne ? __ldg(src + i) : -2.0f;        // -2: outside every prefilter range
         }
+        // cheap prefilter on the noise PSD itself; only the ~1 % that pass pay for the log10
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < U; u++) any = any || (v[u] >= v_lo && v[u] <= v_hi);
+        if (!__any_sync(0xffffffffu, any)) continue;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int i = base + u * 256;
             bool take = false;
             float d = 0.0f;
-            if (i < ne) {
+            if (v[u] >= v_lo && v[u] <= v_hi) {
                 d = 10.0f * svml_log10f(v[u] + p.eps32, s_ltab);
                 const int bin = db_bin(d);
                 take = bin == bin0 || bin == bin1;

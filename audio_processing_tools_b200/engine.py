@@ -39,6 +39,7 @@ _PLANES = {
     "peak_gate_score": ("float32", lambda nF, nS, rp: (nF,)),
     "peak_valid_count": ("int32", lambda nF, nS, rp: (nF,)),
     "peak_count_by_mode": ("int32", lambda nF, nS, rp: (rp.M, nF)),
+    "td_fast_crest": ("float32", lambda nF, nS, rp: (nF,)),
 }
 _CORE = {
     "frame_class": ("int8", lambda nF, nC: (nF,)),

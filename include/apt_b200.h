@@ -39,7 +39,7 @@ extern "C" {
 #define APT_N_TD_FEATURES 5   /* crest, kurtosis, block crest, block width50, block post/pre */
 #define APT_N_CLIP_STATS 8
 #define APT_MAX_GAIN_TAPS 9
-#define APT_ABI_VERSION 4
+#define APT_ABI_VERSION 5
 
 typedef struct apt_ctx apt_ctx;
 typedef struct apt_plan apt_plan_t;
@@ -150,6 +150,9 @@ typedef struct apt_out_t {
     int32_t* peak_valid_count;/* [nF]       det_debug["peak_valid_count"] */
     int32_t* peak_count_by_mode; /* [M][nF] det_debug["peak_count_by_mode"] */
     float*   y;               /* [nS]       suppressed output audio = ISTFT(S_hat) (state["output_audio"]); needs S_hat */
+    float*   td_fast_crest;   /* [nF]       diagnostic: crest factor as the float32 fast path of the TD gate computed it
+                                            (the decision uses it only outside the guard band around td_gate_threshold;
+                                            frames inside are re-decided by the float64 filter).  Not with td / x_td. */
 } apt_out_t;
 
 /* which stages a run executes */
@@ -209,6 +212,13 @@ int  apt_plan_last_launches(const apt_plan_t* plan);
 #define APT_KERNEL_GAIN 10     /* gain_kernel + gain_time_kernel (+ shat_kernel, istft256_kernel): only when G / S_hat / y is requested */
 #define APT_N_KERNELS 11
 int  apt_plan_enable_timing(apt_plan_t* plan, int enable);
+/* Timeline of the pipelined run (benchmarks / profiles): with tracing on, apt_run_* records timing events around
+   every launch on its kind's stream.  After synchronising, apt_plan_trace returns for each kernel kind k
+   (0 stft, 1 td, 2 trk1, 3 flux, 4 base, 5 decide, 6 trk2, 7 dbsum) and time segment s the start and end of that
+   launch in ms since the start of the call: out_ms[(k * 64 + s) * 2 + {0, 1}]; *n_seg = segments of the last run
+   (0: it did not run pipelined), *total_ms = duration of the whole call on the caller's stream. */
+int  apt_plan_enable_trace(apt_plan_t* plan, int enable);
+int  apt_plan_trace(apt_plan_t* plan, float* out_ms /* [8][64][2] */, int* n_seg, float* total_ms);
 int  apt_plan_kernel_ms(apt_plan_t* plan, float* out_ms /* [APT_N_KERNELS] */);
 
 /* End-to-end convenience path with HOST buffers: copies PCM host->device in clip groups on a copy
