@@ -177,3 +177,32 @@ def test_orchestrator_with_gpu_processors(goldens, tmp_path):
     for _, st in states["noise"].iterrows():       # in-memory remainder: numpy arrays, not lists
         assert np.array_equal(st["is_rain"], goldens[st["file_key"]][0]["frame_class"] == 2)
     assert res.attrs["num_files_processed_total"] == len(names) + 1
+
+
+def test_td_fast_path_gate_equals_exact(goldens):
+    """Default flags decide the TD gate with the float32 filter + exact float64 re-check of the tiles that hold a frame
+    within the guard band of td_gate_threshold.  The gate plane and the labels must equal the float64 path's bit for bit,
+    and the float32 crest factor must sit far inside the guard band (1e-3 relative) everywhere."""
+    from audio_processing_tools_b200.config import build_noise_config
+    from audio_processing_tools_b200.engine import BatchEngine
+    names = [n for n in goldens if goldens[n][1]["seconds"] == 60][:4]
+    clips = [goldens[n][2] for n in names] + [synth_clip_i16(s, 700 + i, lam) for i, (s, lam) in
+                                               enumerate(((7.3, 3.0), (33.1, 10.0), (20.6, 0.0), (3.2, 10.0)))]
+    params = default_params(check_duration=3)
+    eng = BatchEngine(build_noise_config(FS, params), FS)
+    plan, fast = eng.run_clips(clips, ("gate", "td_fast_crest"))
+    plan, exact = eng.run_clips(clips, ("gate", "td"))
+    assert np.array_equal(fast["gate"], exact["gate"])
+    assert np.array_equal(fast["frame_class"], exact["frame_class"])
+    assert np.array_equal(fast["event_count"], exact["event_count"])
+    assert np.array_equal(fast["clip_stats"], exact["clip_stats"])
+    c64, c32 = exact["td"][0], fast["td_fast_crest"]
+    ok = c64 > 0
+    dev = float(np.max(np.abs(c32[ok] - c64[ok]) / c64[ok]))
+    near = float(np.mean(np.abs(c64[ok] - 2.5) <= 1e-3 * 2.5))
+    print(f"float32 crest factor: max relative deviation {dev:.3e} over {int(ok.sum())} frames; {near:.4%} of frames inside the guard band")
+    assert dev < 1e-4, dev
+    for n, c in zip(names, range(len(names))):
+        f0, f1 = int(plan.frame_off[c]), int(plan.frame_off[c + 1])
+        assert np.array_equal(fast["frame_class"][f0:f1], goldens[n][0]["frame_class"])
+    eng.close()
