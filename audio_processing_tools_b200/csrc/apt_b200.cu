@@ -77,6 +77,9 @@ struct apt_plan {
     DevBuf<int> d_td_cnt;
     int64_t td_list_cap = 0;
     int td_fast = 1;
+    bool tdf_ok = false;                 // the dedicated float32 gate kernel (two biquad sections) is usable
+    DevBuf<float> d_tdf_tab;
+    TdFastParams tdf;
     float td_guard = 1e-3f;
     // scratch
     DevBuf<float> d_Pband, d_n2, d_td, d_mf, d_nl, d_nl_all, d_Dscr;
@@ -426,6 +429,23 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
             for (int k = 0; k < 5; k++) for (int i = 0; i < dim * dim; i++) pl->tdt.Adc[k * 16 + i] = Apow[(size_t)i * 32 + (1 << k)];
         }
         pl->tdt.env_cap = (TD_FT * p->hop + p->n_fft + 2 * halo) / std::max(1, p->blk_hop) + 8;
+        if (ns == 2) {   // tables of the float32 gate kernel (chunk = 32 samples)
+            std::vector<double> Ap32, H32;
+            build_td_tables(*p, ns, sos, TDF_CH, Ap32, H32);
+            std::vector<float> tab(TDF_TAB_N, 0.0f);
+            for (int m = 0; m < TDF_CH; m++) for (int r = 0; r < 4; r++) tab[TDF_TAB_H + m * 4 + r] = (float)H32[(size_t)m * 4 + r];
+            for (int k = 0; k < 5; k++) for (int i = 0; i < 16; i++) tab[TDF_TAB_A2K + k * 16 + i] = (float)Ap32[(size_t)i * 32 + (1 << k)];
+            for (int e = 0; e < 32; e++) for (int i = 0; i < 16; i++) tab[TDF_TAB_APOS + e * 20 + i] = (float)Ap32[(size_t)i * 32 + e];
+            double mx = 0.0;     // what is left of a state after the warm-up (12 chunks) must be far below float32 resolution
+            for (int i = 0; i < 16; i++) mx = std::max(mx, fabs(Ap32[(size_t)i * 32 + TDF_WARM / TDF_CH]));
+            PL_OK(upload(pl->d_tdf_tab, tab));
+            memset(&pl->tdf, 0, sizeof(pl->tdf));
+            for (int s_ = 0; s_ < 2; s_++) for (int j = 0; j < 6; j++) pl->tdf.c[s_][j] = (float)sos[s_][j];
+            pl->tdf.tab = pl->d_tdf_tab.p;
+            pl->tdf.eps = (float)p->eps_f64;
+            pl->tdf.thr = p->td_gate_thr;
+            pl->tdf_ok = mx < 1e-9;
+        }
         pl->td_smem = td_smem_bytes(ns, pl->tdt.env_cap);
         pl->td_smem_f32 = td_smem_bytes(ns, pl->tdt.env_cap, sizeof(float));
         for (int i = 0; i < TD_CHUNK * 4; i++) pl->tdt.Hcf[i] = (float)pl->tdt.Hc[i];
@@ -460,7 +480,12 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     PL_OK(pl->d_sel.alloc(n_clips));
     PL_OK(pl->d_hist.alloc((size_t)n_clips * 2 * SEL_BINS));
     PL_OK(pl->d_gate.alloc((size_t)pl->nF));
-    pl->td_list_cap = pl->td_tile_off[n_clips];
+    {   // flagged-tile lists: one slice of (tiles per segment) x clips per time segment; segments x tiles per segment is
+        // below twice the tiles of the longest clip
+        int64_t mx = 1;
+        for (int c = 0; c < n_clips; c++) mx = std::max(mx, pl->td_tile_off[c + 1] - pl->td_tile_off[c]);
+        pl->td_list_cap = 2 * mx * n_clips + 64;
+    }
     PL_OK(pl->d_td_list.alloc((size_t)pl->td_list_cap));
     PL_OK(pl->d_td_cnt.alloc(apt_plan::MAX_SEG));
     if (const char* e = getenv("APT_TD_FAST")) pl->td_fast = atoi(e);
@@ -595,6 +620,19 @@ static dim3 seg_grid(const std::vector<int64_t>& off, int clip0, int n, int64_t 
     return dim3((unsigned)x, (unsigned)n, 1);
 }
 
+// Tiled kernels (STFT, TD) can walk several tiles of a clip per CTA (grid.x < tiles), which pays the per-CTA set-up once.
+// Measured (profiles/r2): with 8 waves of long-lived CTAs the kernels lose more to lock-step phases (every resident
+// CTA staging, then every CTA in the FFT) than the set-up costs -- issue utilisation 64 % -> 57 % (STFT), 80 % -> 65 %
+// (TD) -- so the default is one tile per CTA; APT_PERSIST_WAVES=n selects n waves of persistent CTAs.
+static dim3 persistent_grid(const apt_plan* pl, dim3 tiles, int ctas_per_sm) {
+    int waves = 0;
+    if (const char* e = getenv("APT_PERSIST_WAVES")) waves = atoi(e);
+    if (tiles.x == 0 || waves <= 0) return tiles;
+    const int64_t want = (int64_t)waves * ctas_per_sm * pl->ctx->sm_count;
+    const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(tiles.x, (want + tiles.y - 1) / tiles.y));
+    return dim3((unsigned)gx, tiles.y, 1);
+}
+
 template <typename T, typename PCM>
 static cudaError_t launch_stft(apt_plan* pl, const Batch& b, dim3 grid, const PCM* pcm, const StftOut& so, cudaStream_t st) {
     if (grid.x == 0) return cudaSuccess;
@@ -703,7 +741,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     const bool dbg = full && (out->det_noise_psd || out->det_noise_lag || D_plane);
     if (dbg && !pl->d_nl_all.p) CUDA_OK(ctx, pl->d_nl_all.alloc((size_t)pl->nF * pl->tab_all.nls));
 
-    Batch b{clip0, n_clips, pl->d_samp_off.p, pl->d_frame_off.p, 0, 0, INT32_MAX};
+    Batch b{clip0, n_clips, pl->d_samp_off.p, pl->d_frame_off.p, 0, 0, INT32_MAX, INT32_MAX};
     StftOut so;
     so.S = out->S; so.P = out->P; so.P_band = full ? pl->d_Pband.p : nullptr; so.band_energy = out->band_energy;
     so.raw = out->raw; so.freqs = pl->d_freqs.p; so.nF = pl->nF;
@@ -716,7 +754,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     }
     if (!full) {
         pl->mark(APT_KERNEL_STFT, st);
-        const dim3 g = seg_grid(pl->stft_tile_off, clip0, n_clips, 0, INT64_MAX);
+        const dim3 g = persistent_grid(pl, seg_grid(pl->stft_tile_off, clip0, n_clips, 0, INT64_MAX), 3);
         cudaError_t e = pl->prm.fft_f64 ? launch_stft<double, PCM>(pl, b, g, pcm, so, st) : launch_stft<float, PCM>(pl, b, g, pcm, so, st);
         if (e != cudaSuccess) return fail(ctx, -11, "stft launch failed: %s", cudaGetErrorString(e));
         pl->mark(-1, st);
@@ -750,7 +788,10 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     // The two bulk kernels share ONE stream (STFT of a segment, then its TD kernel): run side by side they take 95 ms
     // for the 1 000-clip batch, back to back 67 ms (both live on the FP64 pipe and on most of an SM's shared memory;
     // profiles/r2/trace_*.txt) -- the chain kernels are what overlaps them.
-    S[apt_plan::SK_TD] = S[apt_plan::SK_STFT];
+    int td_own = 0, two_phase = 0;     // experiment knobs (profiles/variants.py)
+    if (const char* e = getenv("APT_TD_OWN_STREAM")) td_own = atoi(e);
+    if (const char* e = getenv("APT_TWO_PHASE")) two_phase = atoi(e);
+    if (!td_own) S[apt_plan::SK_TD] = S[apt_plan::SK_STFT];
     // record on the producing kind's stream / wait on the consuming kind's stream (no-ops on one stream)
     auto rec = [&](int kind, int sg) -> cudaError_t {
         if (!piped) return cudaSuccess;
@@ -779,6 +820,9 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         select_init_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(b, d.K, pl->d_sel.p);
         pl->last_launches++;
     }
+    if (out->td_fast_crest)    // diagnostic plane: frames of tiles the float32 kernel leaves to the exact one stay 0
+        CUDA_OK(ctx, cudaMemsetAsync(out->td_fast_crest + pl->frame_off[clip0], 0,
+                                     sizeof(float) * (size_t)(pl->frame_off[clip0 + n_clips] - pl->frame_off[clip0]), st));
     const bool tracing = piped && pl->trace;
     if (tracing) { CUDA_OK(ctx, cudaEventRecord(pl->tr_origin, st)); pl->tr_nseg = n_seg; }
     if (piped) {
@@ -791,15 +835,22 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     cudaError_t e = cudaSuccess;
     const char* what = "";
 #define RR(...) do { if (e == cudaSuccess) { e = (__VA_ARGS__); if (e != cudaSuccess) what = #__VA_ARGS__; } } while (0)
+    // two-phase schedule: every bulk launch (STFT, TD of all segments) is enqueued before the first chain launch, and the
+    // chain waits for the last of them, so that the bulk kernels have the GPU to themselves
+    for (int phase = 0; phase < (two_phase && piped ? 2 : 1); phase++)
     for (int sg = 0; sg < n_seg && e == cudaSuccess; sg++) {
+        const bool do_bulk = !(two_phase && piped) || phase == 0;
+        const bool do_chain = !(two_phase && piped) || phase == 1;
         Batch bs = b;
         bs.ta = sg * seg_frames;
         bs.tb = n_seg == 1 ? INT32_MAX : bs.ta + seg_frames;
+        if (do_bulk) {
         // STFT
         pl->mark(APT_KERNEL_STFT, st);
         bs.tile0 = bs.ta / STFT_TF;
+        bs.ntile = n_seg == 1 ? INT32_MAX : seg_frames / STFT_TF;
         {
-            const dim3 g = seg_grid(pl->stft_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / STFT_TF);
+            const dim3 g = persistent_grid(pl, seg_grid(pl->stft_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / STFT_TF), 3);
             tmark(apt_plan::SK_STFT, sg, 0);
             RR(pl->prm.fft_f64 ? launch_stft<double, PCM>(pl, bs, g, pcm, so, S[apt_plan::SK_STFT]) : launch_stft<float, PCM>(pl, bs, g, pcm, so, S[apt_plan::SK_STFT]));
             RR(rec(apt_plan::SK_STFT, sg));
@@ -807,26 +858,53 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         // TD features
         pl->mark(APT_KERNEL_TD, st);
         bs.tile0 = bs.ta / TD_FT;
+        bs.ntile = n_seg == 1 ? INT32_MAX : seg_frames / TD_FT;
         {
-            const dim3 g = seg_grid(pl->td_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / TD_FT);
+            const dim3 g = persistent_grid(pl, seg_grid(pl->td_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / TD_FT), fast_td ? 3 : 2);
             tmark(apt_plan::SK_TD, sg, 0);
             if (fast_td) {
                 TdOut tf = to;
                 tf.td = nullptr; tf.want_block = 0; tf.want_kurt = 0;
                 tf.gate = pl->d_gate.p; tf.crest_dbg = out->td_fast_crest; tf.guard = pl->td_guard;
                 // flagged tiles of this segment: its own slice of the list (at most every tile of the segment) and counter
-                const int64_t per_seg = n_seg == 1 ? pl->td_list_cap : (int64_t)(seg_frames / TD_FT) * n_clips;
+                int64_t max_tiles = 1;
+                for (int c = clip0; c < clip0 + n_clips; c++) max_tiles = std::max(max_tiles, pl->td_tile_off[c + 1] - pl->td_tile_off[c]);
+                const int64_t per_seg = (n_seg == 1 ? max_tiles : (int64_t)(seg_frames / TD_FT)) * n_clips;
                 const int64_t off = std::min<int64_t>((int64_t)sg * per_seg, pl->td_list_cap);
                 tf.list = pl->d_td_list.p + off;
                 tf.list_cap = (int)std::min<int64_t>(per_seg, pl->td_list_cap - off);
                 tf.list_count = pl->d_td_cnt.p + sg;
                 RR(cudaMemsetAsync(tf.list_count, 0, sizeof(int), S[apt_plan::SK_TD]));
-                RR(launch_td<PCM, float>(pl, bs, g, pcm, tf, S[apt_plan::SK_TD]));
+                if (pl->tdf_ok && pl->td_ns == 2) {
+                    TdFastParams q = pl->tdf;
+                    q.guard = pl->td_guard; q.gate = tf.gate; q.crest_dbg = tf.crest_dbg;
+                    q.list = tf.list; q.list_count = tf.list_count; q.list_cap = tf.list_cap;
+                    const dim3 gt = seg_grid(pl->td_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / TD_FT);
+                    if (gt.x > 0 && e == cudaSuccess) {
+                        auto kern = td_gate_fast_kernel<PCM>;
+                        RR(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tdf_smem_bytes()));
+                        if (e == cudaSuccess) {
+                            kern<<<gt, TDF_NT, tdf_smem_bytes(), S[apt_plan::SK_TD]>>>(bs, pcm, pl->d_td_tile_off.p, q);
+                            pl->last_launches++;
+                            RR(cudaGetLastError());
+                        }
+                    }
+                } else {
+                    RR(launch_td<PCM, float>(pl, bs, g, pcm, tf, S[apt_plan::SK_TD]));
+                }
                 if (g.x > 0 && tf.list_cap > 0) RR(launch_td_recheck<PCM>(pl, bs, pcm, tf, S[apt_plan::SK_TD]));
             } else {
                 RR(launch_td<PCM, double>(pl, bs, g, pcm, to, S[apt_plan::SK_TD]));
             }
             RR(rec(apt_plan::SK_TD, sg));
+        }
+        }
+        if (!do_chain) continue;
+        if (two_phase && piped && sg == 0) {
+            RR(cudaStreamWaitEvent(S[apt_plan::SK_TRK1], pl->ev_seg[apt_plan::SK_TD][n_seg - 1], 0));
+            RR(cudaStreamWaitEvent(S[apt_plan::SK_FLUX], pl->ev_seg[apt_plan::SK_TD][n_seg - 1], 0));
+            RR(cudaStreamWaitEvent(S[apt_plan::SK_FLUX], pl->ev_seg[apt_plan::SK_STFT][n_seg - 1], 0));
+            RR(cudaStreamWaitEvent(S[apt_plan::SK_TRK1], pl->ev_seg[apt_plan::SK_STFT][n_seg - 1], 0));
         }
         // tracker pass 1 on the mode bins (every band bin when one of its planes is requested)
         pl->mark(APT_KERNEL_TRK1, st);

@@ -87,6 +87,8 @@ struct Batch {
     const int64_t* frame_off;  // [plan clips + 1]
     int tile0;                 // first tile of every clip this launch covers (tiled kernels)
     int ta, tb;                // clip-local frame range [ta, tb) this launch covers (serial / per-frame kernels)
+    int ntile;                 // tiles of every clip this launch covers, from tile0 (persistent tiled kernels: a CTA
+                               // walks tile0 + blockIdx.x, + gridDim.x, ... below tile0 + ntile)
 };
 
 // tile -> clip: tiled kernels launch a 2-D grid, blockIdx.y = clip of the launch's range, blockIdx.x = tile
@@ -116,7 +118,12 @@ __device__ __forceinline__ int run_head(int64_t g) { return (int)((4 - (g % 4 + 
 // issued before the first conversion so the misses overlap (MAXV = vectors per thread upper bound).
 // put4 is called with i = run_head(g) (mod 4) only, so a destination shifted by (4 - run_head % 4) % 4
 // floats takes aligned 128-bit shared-memory stores.
-template <int MAXV, typename PCM, typename Put, typename Put4>
+// RAW: int16 samples are handed over unscaled ((float)s instead of s / 32767): for consumers that are invariant to the
+// scale or undo it later (the float32 fast path of the TD gate).
+template <bool RAW> __device__ __forceinline__ float cvt_pcm(int16_t s) { return RAW ? (float)s : pcm_to_f32(s); }
+template <bool RAW> __device__ __forceinline__ float load_in(const int16_t* p, int64_t i) { return cvt_pcm<RAW>(__ldg(p + i)); }
+template <bool RAW> __device__ __forceinline__ float load_in(const float* p, int64_t i) { return __ldg(p + i); }
+template <int MAXV, typename PCM, typename Put, typename Put4, bool RAW = false>
 __device__ __forceinline__ void load_run(const PCM* __restrict__ pcm, int64_t g, int n, Put put, Put4 put4) {
     constexpr int VEC = 4;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -131,15 +138,15 @@ __device__ __forceinline__ void load_run(const PCM* __restrict__ pcm, int64_t g,
             const int v = tid + r * nt;
             if (v < nvec) raw[r] = __ldg(reinterpret_cast<const int2*>(pcm + g + head + (int64_t)v * VEC));
         }
-        if (tid < head) put(tid, load_sample(pcm, g + tid));
-        if (tail0 + tid < n) put(tail0 + tid, load_sample(pcm, g + tail0 + tid));
+        if (tid < head) put(tid, load_in<RAW>(pcm, g + tid));
+        if (tail0 + tid < n) put(tail0 + tid, load_in<RAW>(pcm, g + tail0 + tid));
 #pragma unroll
         for (int r = 0; r < MAXV; r++) {
             const int v = tid + r * nt;
             if (v < nvec) {
                 const int2 q = raw[r];
-                put4(head + v * VEC, make_float4(pcm_to_f32((int16_t)(q.x & 0xffff)), pcm_to_f32((int16_t)(q.x >> 16)),
-                                                 pcm_to_f32((int16_t)(q.y & 0xffff)), pcm_to_f32((int16_t)(q.y >> 16))));
+                put4(head + v * VEC, make_float4(cvt_pcm<RAW>((int16_t)(q.x & 0xffff)), cvt_pcm<RAW>((int16_t)(q.x >> 16)),
+                                                 cvt_pcm<RAW>((int16_t)(q.y & 0xffff)), cvt_pcm<RAW>((int16_t)(q.y >> 16))));
             }
         }
     } else {
@@ -160,7 +167,7 @@ __device__ __forceinline__ void load_run(const PCM* __restrict__ pcm, int64_t g,
     // vectors beyond MAXV per thread (never for the tile sizes in this file)
     for (int v = tid + MAXV * nt; v < nvec; v += nt) {
         const int i = head + v * VEC;
-        for (int e = 0; e < VEC; e++) put(i + e, load_sample(pcm, g + i + e));
+        for (int e = 0; e < VEC; e++) put(i + e, load_in<RAW>(pcm, g + i + e));
     }
 }
 
@@ -268,20 +275,23 @@ __global__ void __launch_bounds__(STFT_NT, 3) stft256_kernel(const __grid_consta
     auto P_row = [&](int t) { return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_ex + (size_t)t * EXF) + STFT_POFF); };
 
     const int tid = threadIdx.x;
-    int64_t tile_in_clip;
-    int c;
-    if (!tile_clip(b, tile_off, c, tile_in_clip)) return;
-    const int t0 = (int)tile_in_clip * STFT_TF;
+    const int c = b.clip0 + (int)blockIdx.y;
+    const int n_tiles = (int)(__ldg(tile_off + c + 1) - __ldg(tile_off + c));
+    const int tile_end = (int)min((int64_t)n_tiles, (int64_t)b.tile0 + (int64_t)b.ntile);
+    if (b.tile0 + (int)blockIdx.x >= tile_end) return;
     const int64_t base = __ldg(b.samp_off + c);
     const int64_t N = __ldg(b.samp_off + c + 1) - base;
     const int64_t f0 = __ldg(b.frame_off + c);
     const int T_clip = (int)(__ldg(b.frame_off + c + 1) - f0);
-    const int nfr = min(STFT_TF, T_clip - t0);
 
     APT_STAMP2(20);
+    // tables once per CTA; the CTA then walks its tiles of the clip
     for (int i = tid; i < 256; i += STFT_NT) s_win[i] = tab.win[i];
     for (int i = tid; i < 128; i += STFT_NT) s_tw128[i] = tab.tw128[((i & 7) * (i >> 3)) & 127];
     for (int i = tid; i < 129; i += STFT_NT) s_tw256[i] = tab.tw256[i];
+    for (int tile = b.tile0 + (int)blockIdx.x; tile < tile_end; tile += (int)gridDim.x) {
+    const int t0 = tile * STFT_TF;
+    const int nfr = min(STFT_TF, T_clip - t0);
     // Sample u of the tile (u = 0 is 128 samples before the first frame) lives at u + sh + padk * (u / 128):
     // at hop 128 the four frames of a warp then read different banks (padk = 8); sh aligns the 128-bit
     // staging stores.
@@ -323,19 +333,43 @@ __global__ void __launch_bounds__(STFT_NT, 3) stft256_kernel(const __grid_consta
                          [&](int k, T re, T im) { sS[k] = make_float2(d2f((double)re), d2f((double)im)); },
                          [&]() { __syncwarp(); });
     }
-    __syncthreads();
     APT_STAMP2(23);
 
-    // power |S|^2 with numpy's complex64 abs, all threads over (frame, bin): independent evaluations that the
-    // scheduler interleaves; the band plane goes straight to HBM (consecutive threads = consecutive bins)
+    // power |S|^2 with numpy's complex64 abs
     const int64_t fbase = f0 + t0;
     const bool need_full = o.P || o.raw || o.band_energy;
+    if (!need_full) {
+        // default path (band plane only): the frame's 8 lanes take its band bins lane, lane + 8, ... -- fixed mapping, no
+        // index arithmetic; the bins were written by other lanes of the same frame (same warp) in pass B
+        __syncwarp();
+        if (fr < nfr && o.P_band) {
+            const float2* sS = S_row(fr) + p.band_lo;
+            float* dst = o.P_band + (fbase + fr) * p.K;
+            const int K = p.K;
+#pragma unroll 3
+            for (int kb = lane; kb < K; kb += 8) {
+                const float2 z = sS[kb];
+                const float a = np_cabsf_fast(z.x, z.y);
+                dst[kb] = a * a;
+            }
+        }
+        if (o.S) {
+            __syncthreads();
+            float2* dstS = reinterpret_cast<float2*>(o.S) + fbase * p.F;
+            for (int i = tid; i < nfr * p.F; i += STFT_NT) {
+                const int t = i / p.F, k = i - t * p.F;
+                dstS[i] = S_row(t)[k];
+            }
+        }
+        __syncthreads();      // the frame areas are restaged by the next tile
+        continue;
+    }
+    __syncthreads();
     {
-        const int klo = need_full ? 0 : p.band_lo, nk = need_full ? p.F : p.K;
+        const int klo = 0, nk = p.F;
         float* dstb = o.P_band ? o.P_band + fbase * p.K : nullptr;
-        // all (frame, bin) pairs of the tile, flattened over the CTA (no idle lanes when nk is not a multiple of
-        // 32): element e -> frame e / nk by a multiply with ceil(2^24 / nk) (exact for e < 2^12, nk <= 129); the
-        // evaluations of a thread are independent straight-line code
+        // all (frame, bin) pairs of the tile, flattened over the CTA: element e -> frame e / nk by a multiply with
+        // ceil(2^24 / nk) (exact for e < 2^12, nk <= 129)
         const unsigned inv = (1u << 24) / (unsigned)nk + 1u;
         const int n_el = nfr * nk;
 #pragma unroll 4
@@ -345,7 +379,7 @@ __global__ void __launch_bounds__(STFT_NT, 3) stft256_kernel(const __grid_consta
             const float2 z = S_row(t)[k];
             const float a = np_cabsf_fast(z.x, z.y);
             const float pw = a * a;
-            if (need_full) P_row(t)[k] = pw;
+            P_row(t)[k] = pw;
             const int kb = k - p.band_lo;
             if (dstb && kb >= 0 && kb < p.K) dstb[t * p.K + kb] = pw;
         }
@@ -382,6 +416,8 @@ __global__ void __launch_bounds__(STFT_NT, 3) stft256_kernel(const __grid_consta
     if (o.raw) {
         if (tid < nfr) raw_features_frame(p, P_row(tid), o.freqs, o.raw + fbase + tid, o.nF);
     }
+    __syncthreads();      // the frame areas are restaged by the next tile
+    }   // tiles of this CTA
     APT_STAMP2(24);
 }
 
@@ -747,13 +783,21 @@ __device__ __forceinline__ void iir_pass(const DevParams& p, const TdTables& tb,
 #pragma unroll
             for (int j = 0; j < TD_CHUNK; j++) {
                 const int m = REV ? TD_CHUNK - 1 - j : j;
-                R acc = (R)0;
+                if constexpr (sizeof(R) == 4) {
+                    // float32 fast path: the response is accumulated straight onto the sample (one operation fewer)
+                    R acc = y[j];
 #pragma unroll
-                for (int r = 0; r < DIM; r++) {
-                    const R h = (NS <= 2) ? td_Hc<R>(tb, m * DIM + r) : s_H[m * DIM + r];
-                    acc = (r == 0) ? h * sin_[0] : t_fma(h, sin_[r], acc);
+                    for (int r = 0; r < DIM; r++) acc = t_fma((NS <= 2) ? td_Hc<R>(tb, m * DIM + r) : s_H[m * DIM + r], sin_[r], acc);
+                    y[j] = acc;
+                } else {
+                    R acc = (R)0;
+#pragma unroll
+                    for (int r = 0; r < DIM; r++) {
+                        const R h = (NS <= 2) ? td_Hc<R>(tb, m * DIM + r) : s_H[m * DIM + r];
+                        acc = (r == 0) ? h * sin_[0] : t_fma(h, sin_[r], acc);
+                    }
+                    y[j] += acc;
                 }
-                y[j] += acc;
             }
         } else {
 #pragma unroll
@@ -836,14 +880,17 @@ __device__ __forceinline__ void td_tile(const DevParams& p, const Batch& b, cons
     float* s_x = reinterpret_cast<float*>(s_env + tb.env_cap);      // [TD_XF] staged PCM, then the float32 result
     __shared__ float s_bsum[TD_FT + 1], s_bmax[TD_FT + 1];
     __shared__ int s_near;
-    const int L = p.n_fft, hop = p.hop;   // 256 / 128 (enforced by the plan)
+    constexpr int L = 256, hop = 128;     // n_fft / hop (enforced by the plan)
+    // float32 fast path on int16 input: unscaled samples through the (linear) filter, the scale is applied to the
+    // frame statistics
+    constexpr bool RAW = sizeof(R) == 4 && sizeof(PCM) == 2;
 
     const int tid = threadIdx.x;
     const int64_t base = __ldg(b.samp_off + c);
     const int64_t N = __ldg(b.samp_off + c + 1) - base;
     const int64_t f0 = __ldg(b.frame_off + c);
     const int T_clip = (int)(__ldg(b.frame_off + c + 1) - f0);
-    const int Tloc = N < L ? 0 : (int)(1 + (N - L) / hop);
+    const int Tloc = N < L ? 0 : (int)(1 + ((N - L) >> 7));
     const int n_tiles = (int)(__ldg(tile_off + c + 1) - __ldg(tile_off + c));
     const int t0 = tile * TD_FT, t1 = min(Tloc, t0 + TD_FT);
     const bool last = tile == n_tiles - 1;
@@ -859,19 +906,19 @@ __device__ __forceinline__ void td_tile(const DevParams& p, const Batch& b, cons
     const bool exact_l = bs == -pad, exact_r = be == N + pad;
 
     APT_STAMP(0);
-    for (int i = tid; i < 32 * DIM * DIM; i += TD_NT) s_A[i] = (R)__ldg(tb.Alin + i);
-    for (int i = tid; i < TD_CHUNK * DIM; i += TD_NT) s_H[i] = (R)__ldg(tb.H + i);
+    // (the callers staged the tables s_A / s_H once per CTA)
     // stage the in-clip part of the buffer as float32 (coalesced 128-bit loads); zeros behind it
     const bool interior = bs >= 0 && be <= N;
     int sh = 0;   // shift of the staged samples that makes the 128-bit staging stores aligned
     if (interior) {
         sh = (4 - (run_head<PCM>(base + bs) & 3)) & 3;
-        load_run<(TD_LB / 4 + TD_NT - 1) / TD_NT + 1>(pcm, base + bs, len, [&](int i, float v) { s_x[i + sh] = v; },
-                    [&](int i, float4 v) { *reinterpret_cast<float4*>(s_x + i + sh) = v; });
+        auto put1 = [&](int i, float v) { s_x[i + sh] = v; };
+        auto put4 = [&](int i, float4 v) { *reinterpret_cast<float4*>(s_x + i + sh) = v; };
+        load_run<(TD_LB / 4 + TD_NT - 1) / TD_NT + 1, PCM, decltype(put1), decltype(put4), RAW>(pcm, base + bs, len, put1, put4);
     } else {
         for (int i = tid; i < len; i += TD_NT) {
             const int64_t s = bs + i;
-            if (s >= 0 && s < N) s_x[i] = load_sample(pcm, base + s);
+            if (s >= 0 && s < N) s_x[i] = load_in<RAW>(pcm, base + s);
         }
     }
     for (int i = len + tid; i < TD_LB; i += TD_NT) s_x[i + sh] = 0.0f;
@@ -894,8 +941,8 @@ __device__ __forceinline__ void td_tile(const DevParams& p, const Batch& b, cons
             R v = (R)0;
             if (a0 + j < len) {
                 const int64_t s = bs + a0 + j;
-                if (s < 0) v = (R)2 * (R)load_sample(pcm, base) - (R)load_sample(pcm, base - s);
-                else if (s >= N) v = (R)2 * (R)load_sample(pcm, base + N - 1) - (R)load_sample(pcm, base + 2 * (N - 1) - s);
+                if (s < 0) v = (R)2 * (R)load_in<RAW>(pcm, base) - (R)load_in<RAW>(pcm, base - s);
+                else if (s >= N) v = (R)2 * (R)load_in<RAW>(pcm, base + N - 1) - (R)load_in<RAW>(pcm, base + 2 * (N - 1) - s);
                 else v = (R)s_x[a0 + j];
             }
             y[j] = v;
@@ -926,10 +973,20 @@ __device__ __forceinline__ void td_tile(const DevParams& p, const Batch& b, cons
     // float32 x_td over the valid range, padded layout
     const int u_off = (int)(bs - (int64_t)t0 * hop) + 128;   // u of buffer index 0
     const int voff = (int)(vs - bs), vend = (int)(ve - bs);
+    if (a0 >= voff && a0 + TD_CHUNK <= vend) {
+        // whole chunk inside the valid range (almost every thread): the padded position u + 8 * (u / 128) of its 23
+        // consecutive samples jumps by 8 at most once, at the 128-sample boundary `bnd` elements in
+        const int u0 = a0 + u_off;
+        float* pa = s_x + td_xf_pos(u0);
+        const int bnd = 128 - (u0 & 127);
 #pragma unroll
-    for (int j = 0; j < TD_CHUNK; j++) {
-        const int i = a0 + j;
-        if (i >= voff && i < vend) s_x[td_xf_pos(i + u_off)] = to_f32(y[j]);
+        for (int j = 0; j < TD_CHUNK; j++) pa[j + (j >= bnd ? 8 : 0)] = to_f32(y[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < TD_CHUNK; j++) {
+            const int i = a0 + j;
+            if (i >= voff && i < vend) s_x[td_xf_pos(i + u_off)] = to_f32(y[j]);
+        }
     }
     __syncthreads();
     APT_STAMP(5);
@@ -970,8 +1027,9 @@ __device__ __forceinline__ void td_tile(const DevParams& p, const Batch& b, cons
     __syncthreads();
     if (tid < nfr) {
         const int t = t0 + tid;
-        const float sumsq = 0.0f + (s_bsum[tid] + s_bsum[tid + 1]);
-        const float pk = fmaxf(s_bmax[tid], s_bmax[tid + 1]);
+        float sumsq = 0.0f + (s_bsum[tid] + s_bsum[tid + 1]);
+        float pk = fmaxf(s_bmax[tid], s_bmax[tid + 1]);
+        if (RAW) { pk *= 3.0518509447574615e-05f; sumsq *= 3.0518509447574615e-05f * 3.0518509447574615e-05f; }   // 1 / 32767
         const float mean_sq = f_div(sumsq, (float)L);
         const float rms = f_sqrt(mean_sq + d2f(p.eps64));
         const double r = (double)rms;
@@ -1105,16 +1163,31 @@ __device__ __forceinline__ void td_tile(const DevParams& p, const Batch& b, cons
 }
 
 
-// grid form: blockIdx.y = clip, blockIdx.x + b.tile0 = tile
+// tables of the block-parallel filter -> shared memory, once per CTA (same carve-up as td_tile)
+template <int NS, typename R>
+__device__ __forceinline__ void td_stage_tables(const TdTables& tb, unsigned char* smem_raw) {
+    constexpr int DIM = 2 * NS;
+    R* s_A = reinterpret_cast<R*>(smem_raw) + DIM * (TD_NT / 32);
+    R* s_H = s_A + 32 * DIM * DIM;
+    for (int i = threadIdx.x; i < 32 * DIM * DIM; i += TD_NT) s_A[i] = (R)__ldg(tb.Alin + i);
+    for (int i = threadIdx.x; i < TD_CHUNK * DIM; i += TD_NT) s_H[i] = (R)__ldg(tb.H + i);
+}
+
+// grid form: blockIdx.y = clip; the CTA walks the tiles b.tile0 + blockIdx.x, + gridDim.x, ... of the launch's range
 template <int NS, typename PCM, typename R>
 __global__ void __launch_bounds__(TD_NT, (sizeof(R) == 8 ? 2 : 3)) td_features_kernel(const __grid_constant__ DevParams p, Batch b,
                                                                const PCM* __restrict__ pcm,
                                                                const int64_t* __restrict__ tile_off, const __grid_constant__ TdTables tb, TdOut o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int64_t tile_in_clip;
-    int c;
-    if (!tile_clip(b, tile_off, c, tile_in_clip)) return;
-    td_tile<NS, PCM, R>(p, b, pcm, tile_off, tb, o, c, (int)tile_in_clip, smem_raw);
+    const int c = b.clip0 + (int)blockIdx.y;
+    const int n_tiles = (int)(__ldg(tile_off + c + 1) - __ldg(tile_off + c));
+    const int tile_end = (int)min((int64_t)n_tiles, (int64_t)b.tile0 + (int64_t)b.ntile);
+    if (b.tile0 + (int)blockIdx.x >= tile_end) return;
+    td_stage_tables<NS, R>(tb, smem_raw);
+    for (int tile = b.tile0 + (int)blockIdx.x; tile < tile_end; tile += (int)gridDim.x) {
+        td_tile<NS, PCM, R>(p, b, pcm, tile_off, tb, o, c, tile, smem_raw);
+        __syncthreads();          // shared memory is reused by the next tile
+    }
 }
 
 // list form (exact re-check of the float32 fast path): persistent CTAs walk the flagged (clip, tile) pairs
@@ -1124,13 +1197,199 @@ __global__ void __launch_bounds__(TD_NT, 2) td_recheck_kernel(const __grid_const
                                                               const int64_t* __restrict__ tile_off, const __grid_constant__ TdTables tb, TdOut o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = min(*o.list_count, o.list_cap);
+    if ((int)blockIdx.x >= n) return;
     TdOut oo = o;
     oo.list = nullptr;            // the exact pass only rewrites gate bytes
     oo.crest_dbg = nullptr;       // (the diagnostic plane keeps the float32 values)
+    td_stage_tables<NS, double>(tb, smem_raw);
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const int2 ct = o.list[i];
         td_tile<NS, PCM, double>(p, b, pcm, tile_off, tb, oo, ct.x, ct.y, smem_raw);
         __syncthreads();          // shared memory is reused by the next tile
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Float32 fast path of the TD gate for the default prefilter (two biquad sections), written for instruction count: the
+// decision consumes one bit per frame (crest > td_gate_threshold), so nothing here has to match the float64 filter bit
+// for bit -- only to stay far inside the guard band (measured deviation of the crest factor ~1e-5 relative, guard 1e-3).
+//   tile    = the 56 frames of one tile of the exact kernel (so a flagged tile is re-decided by td_recheck_kernel):
+//             7296 samples + 384 / 512 samples of warm-up before / behind = 8192 = 256 threads x 32 samples
+//   thread  = 32 consecutive samples in registers through both filter directions (block-parallel IIR as in the exact
+//             kernel: direct pass from rest, scan of the chunk-final states, homogeneous response added)
+//   crest   = per-thread sum of squares / peak of its 32 samples, 4 threads per 128-sample block by shuffles, two
+//             blocks per frame: the filtered waveform never goes back to shared memory
+//   edges   = tiles whose buffer would cross a clip end (scipy's odd extension, zi initial state, the zero-filled tail
+//             frames) are not computed here at all: they are put on the re-check list
+// int16 input runs unscaled through the (linear) filter; the 1/32767 scale is applied to the frame statistics.
+// ---------------------------------------------------------------------------------------------
+constexpr int TDF_NT = 256;
+constexpr int TDF_CH = 32;                 // samples per thread
+constexpr int TDF_WARM = 384;              // warm-up samples before the first frame (pole radius 0.928: 0.928^384 ~ 3e-13);
+                                           // 12 thread chunks = 3 blocks of 128, so frames start on 4-thread groups
+constexpr int TDF_LB = TDF_NT * TDF_CH;    // 8192: 384 + 7296 payload + 512 behind
+static_assert(TDF_LB - TDF_WARM - ((TD_FT - 1) * 128 + 256) >= 384 && TDF_WARM % 128 == 0, "fast TD tile geometry");
+constexpr int TDF_XS = TDF_NT * (TDF_CH + 4) + 8;   // staged samples: 4 floats of padding per thread chunk (conflict-free 128-bit reads)
+// float tables (global, built at plan time for chunk = 32): H[32][4], A^(2^k)[5][16], A^pos[32][20 (16 used)]
+constexpr int TDF_TAB_H = 0, TDF_TAB_A2K = 128, TDF_TAB_APOS = 208, TDF_TAB_N = 208 + 32 * 20;
+struct TdFastParams {
+    float c[2][6];        // biquad coefficients
+    float thr, guard;     // td_gate_threshold, relative guard band
+    float eps;            // feature_extraction eps (1e-9)
+    const float* tab;     // [TDF_TAB_N]
+    uint8_t* gate;        // [nF]
+    float* crest_dbg;     // optional [nF]
+    int2* list; int* list_count; int list_cap;
+};
+inline size_t tdf_smem_bytes() { return sizeof(float) * (TDF_XS + TDF_TAB_N + 4 * (TDF_NT / 32) + 2 * 64); }
+
+template <bool REV>
+__device__ __forceinline__ void tdf_pass(const TdFastParams& q, const float* __restrict__ s_tab, float* __restrict__ s_vend,
+                                         float (&y)[TDF_CH]) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int NW = TDF_NT / 32;
+    const float b10 = q.c[0][0], b11 = q.c[0][1], b12 = q.c[0][2], a11 = q.c[0][4], a12 = q.c[0][5];
+    const float b20 = q.c[1][0], b21 = q.c[1][1], b22 = q.c[1][2], a21 = q.c[1][4], a22 = q.c[1][5];
+    // (1) direct pass from rest
+    float z10 = 0.0f, z11 = 0.0f, z20 = 0.0f, z21 = 0.0f;
+#pragma unroll
+    for (int jj = 0; jj < TDF_CH; jj++) {
+        const int j = REV ? TDF_CH - 1 - jj : jj;
+        const float x = y[j];
+        const float y1 = fmaf(b10, x, z10);
+        z10 = fmaf(-a11, y1, fmaf(b11, x, z11));
+        z11 = fmaf(-a12, y1, b12 * x);
+        const float y2 = fmaf(b20, y1, z20);
+        z20 = fmaf(-a21, y2, fmaf(b21, y1, z21));
+        z21 = fmaf(-a22, y2, b22 * y1);
+        y[j] = y2;
+    }
+    // (2) scan of the chunk-final states over the chunk order (Kogge-Stone inside the warp, previous warp by one exchange)
+    float v0 = z10, v1 = z11, v2 = z20, v3 = z21;
+    const int pos = REV ? 31 - lane : lane;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int d = 1 << k;
+        const float u0 = REV ? __shfl_down_sync(0xffffffffu, v0, d) : __shfl_up_sync(0xffffffffu, v0, d);
+        const float u1 = REV ? __shfl_down_sync(0xffffffffu, v1, d) : __shfl_up_sync(0xffffffffu, v1, d);
+        const float u2 = REV ? __shfl_down_sync(0xffffffffu, v2, d) : __shfl_up_sync(0xffffffffu, v2, d);
+        const float u3 = REV ? __shfl_down_sync(0xffffffffu, v3, d) : __shfl_up_sync(0xffffffffu, v3, d);
+        if (pos >= d) {
+            const float4* A = reinterpret_cast<const float4*>(s_tab + TDF_TAB_A2K + 16 * k);
+            const float4 r0 = A[0], r1 = A[1], r2 = A[2], r3 = A[3];
+            v0 = fmaf(r0.x, u0, fmaf(r0.y, u1, fmaf(r0.z, u2, fmaf(r0.w, u3, v0))));
+            v1 = fmaf(r1.x, u0, fmaf(r1.y, u1, fmaf(r1.z, u2, fmaf(r1.w, u3, v1))));
+            v2 = fmaf(r2.x, u0, fmaf(r2.y, u1, fmaf(r2.z, u2, fmaf(r2.w, u3, v2))));
+            v3 = fmaf(r3.x, u0, fmaf(r3.y, u1, fmaf(r3.z, u2, fmaf(r3.w, u3, v3))));
+        }
+    }
+    if (pos == 31) { s_vend[4 * w + 0] = v0; s_vend[4 * w + 1] = v1; s_vend[4 * w + 2] = v2; s_vend[4 * w + 3] = v3; }
+    // state entering this chunk = scanned state of the previous chunk in order
+    float s0 = REV ? __shfl_down_sync(0xffffffffu, v0, 1) : __shfl_up_sync(0xffffffffu, v0, 1);
+    float s1 = REV ? __shfl_down_sync(0xffffffffu, v1, 1) : __shfl_up_sync(0xffffffffu, v1, 1);
+    float s2 = REV ? __shfl_down_sync(0xffffffffu, v2, 1) : __shfl_up_sync(0xffffffffu, v2, 1);
+    float s3 = REV ? __shfl_down_sync(0xffffffffu, v3, 1) : __shfl_up_sync(0xffffffffu, v3, 1);
+    if (pos == 0) { s0 = 0.0f; s1 = 0.0f; s2 = 0.0f; s3 = 0.0f; }
+    __syncthreads();
+    const bool has_prev = REV ? (w < NW - 1) : (w > 0);
+    if (has_prev) {
+        const float* ve = s_vend + 4 * (REV ? w + 1 : w - 1);
+        const float e0 = ve[0], e1 = ve[1], e2 = ve[2], e3 = ve[3];
+        const float4* A = reinterpret_cast<const float4*>(s_tab + TDF_TAB_APOS + 20 * pos);    // A^pos
+        const float4 r0 = A[0], r1 = A[1], r2 = A[2], r3 = A[3];
+        s0 = fmaf(r0.x, e0, fmaf(r0.y, e1, fmaf(r0.z, e2, fmaf(r0.w, e3, s0))));
+        s1 = fmaf(r1.x, e0, fmaf(r1.y, e1, fmaf(r1.z, e2, fmaf(r1.w, e3, s1))));
+        s2 = fmaf(r2.x, e0, fmaf(r2.y, e1, fmaf(r2.z, e2, fmaf(r2.w, e3, s2))));
+        s3 = fmaf(r3.x, e0, fmaf(r3.y, e1, fmaf(r3.z, e2, fmaf(r3.w, e3, s3))));
+    }
+    // (3) homogeneous response to the entering state
+    const float4* H = reinterpret_cast<const float4*>(s_tab + TDF_TAB_H);
+#pragma unroll
+    for (int m = 0; m < TDF_CH; m++) {
+        const int j = REV ? TDF_CH - 1 - m : m;
+        const float4 h = H[m];
+        y[j] = fmaf(h.x, s0, fmaf(h.y, s1, fmaf(h.z, s2, fmaf(h.w, s3, y[j]))));
+    }
+    __syncthreads();     // s_vend is reused by the next pass
+}
+
+template <typename PCM>
+__global__ void __launch_bounds__(TDF_NT, 3) td_gate_fast_kernel(Batch b, const PCM* __restrict__ pcm,
+                                                                 const int64_t* __restrict__ tile_off, const TdFastParams q) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_x = reinterpret_cast<float*>(smem_raw);          // [TDF_XS] staged samples
+    float* s_tab = s_x + TDF_XS;                              // [TDF_TAB_N]
+    float* s_vend = s_tab + TDF_TAB_N;                        // [NW][4]
+    float* s_bsum = s_vend + 4 * (TDF_NT / 32);               // [64] per 128-sample block: sum of squares
+    float* s_bmax = s_bsum + 64;                              // [64] peak
+    constexpr bool RAW = sizeof(PCM) == 2;
+    const int tid = threadIdx.x;
+    int64_t tile_in_clip;
+    int c;
+    if (!tile_clip(b, tile_off, c, tile_in_clip)) return;
+    const int tile = (int)tile_in_clip;
+    const int64_t base = __ldg(b.samp_off + c);
+    const int64_t N = __ldg(b.samp_off + c + 1) - base;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int t0 = tile * TD_FT;
+    const int64_t bs = (int64_t)t0 * 128 - TDF_WARM;
+    if (bs < 0 || bs + TDF_LB > N) {          // buffer crosses a clip end: the exact kernel decides this tile
+        if (tid == 0) {
+            const int pos = atomicAdd(q.list_count, 1);
+            if (pos < q.list_cap) q.list[pos] = make_int2(c, tile);
+        }
+        return;
+    }
+    for (int i = tid; i < TDF_TAB_N; i += TDF_NT) s_tab[i] = __ldg(q.tab + i);
+    // stage: coalesced 128-bit loads -> float, sample u at u + 4 * (u / 32) (+ sh: alignment of the vector stores)
+    const int sh = (4 - (run_head<PCM>(base + bs) & 3)) & 3;
+    {
+        auto xpos = [&](int u) { const int v = u + sh; return v + ((v >> 5) << 2); };
+        auto put1 = [&](int i, float v) { s_x[xpos(i)] = v; };
+        auto put4 = [&](int i, float4 v) { *reinterpret_cast<float4*>(s_x + xpos(i)) = v; };
+        load_run<TDF_LB / 4 / TDF_NT + 1, PCM, decltype(put1), decltype(put4), RAW>(pcm, base + bs, TDF_LB, put1, put4);
+    }
+    __syncthreads();
+    float y[TDF_CH];
+    {
+        // thread chunk = samples 32 tid .. 32 tid + 31 = staged positions sh + 32 tid + j
+        if (sh == 0) {
+            const float4* src = reinterpret_cast<const float4*>(s_x + tid * (TDF_CH + 4));
+#pragma unroll
+            for (int j = 0; j < TDF_CH / 4; j++) { const float4 v = src[j]; y[4 * j] = v.x; y[4 * j + 1] = v.y; y[4 * j + 2] = v.z; y[4 * j + 3] = v.w; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < TDF_CH; j++) { const int v = tid * TDF_CH + j + sh; y[j] = s_x[v + ((v >> 5) << 2)]; }
+        }
+    }
+    tdf_pass<false>(q, s_tab, s_vend, y);
+    tdf_pass<true>(q, s_tab, s_vend, y);
+    // frame statistics: thread -> (sum of squares, peak) of its 32 samples, 4 threads -> one 128-sample block
+    float ss = 0.0f, pk = 0.0f;
+#pragma unroll
+    for (int j = 0; j < TDF_CH; j++) { ss = fmaf(y[j], y[j], ss); pk = fmaxf(pk, fabsf(y[j])); }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1); pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, 1));
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2); pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, 2));
+    if ((tid & 3) == 0) { s_bsum[tid >> 2] = ss; s_bmax[tid >> 2] = pk; }     // block tid/4 of the buffer (64 blocks)
+    __syncthreads();
+    // frame f = 128-sample blocks TDF_WARM / 128 + f and + f + 1 of the buffer
+    bool near = false;
+    if (tid < TD_FT) {
+        constexpr int B0 = TDF_WARM / 128;
+        float sumsq = s_bsum[B0 + tid] + s_bsum[B0 + tid + 1];
+        float pkf = fmaxf(s_bmax[B0 + tid], s_bmax[B0 + tid + 1]);
+        if (RAW) { pkf *= 3.0518509447574615e-05f; sumsq *= 3.0518509447574615e-05f * 3.0518509447574615e-05f; }   // 1 / 32767
+        const float rms = sqrtf(sumsq * (1.0f / 256.0f) + q.eps);
+        float cf = pkf / fmaxf(rms, q.eps);
+        if (!(cf == cf) || isinf(cf)) cf = 0.0f;
+        const int64_t g = f0 + t0 + tid;
+        q.gate[g] = cf > q.thr ? 1 : 0;
+        if (q.crest_dbg) q.crest_dbg[g] = cf;
+        near = fabsf(cf - q.thr) <= q.guard * fabsf(q.thr);
+    }
+    if (__syncthreads_or(near ? 1 : 0) && tid == 0) {
+        const int pos = atomicAdd(q.list_count, 1);
+        if (pos < q.list_cap) q.list[pos] = make_int2(c, tile);
     }
 }
 

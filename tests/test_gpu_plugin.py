@@ -197,7 +197,8 @@ def test_td_fast_path_gate_equals_exact(goldens):
     assert np.array_equal(fast["event_count"], exact["event_count"])
     assert np.array_equal(fast["clip_stats"], exact["clip_stats"])
     c64, c32 = exact["td"][0], fast["td_fast_crest"]
-    ok = c64 > 0
+    ok = (c64 > 0) & (c32 > 0)          # tiles at the clip ends are decided by the exact kernel alone (no float32 value)
+    assert ok.mean() > 0.8
     dev = float(np.max(np.abs(c32[ok] - c64[ok]) / c64[ok]))
     near = float(np.mean(np.abs(c64[ok] - 2.5) <= 1e-3 * 2.5))
     print(f"float32 crest factor: max relative deviation {dev:.3e} over {int(ok.sum())} frames; {near:.4%} of frames inside the guard band")
