@@ -788,7 +788,12 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     // The two bulk kernels share ONE stream (STFT of a segment, then its TD kernel): run side by side they take 95 ms
     // for the 1 000-clip batch, back to back 67 ms (both live on the FP64 pipe and on most of an SM's shared memory;
     // profiles/r2/trace_*.txt) -- the chain kernels are what overlaps them.
-    int td_own = 0, two_phase = 0;     // experiment knobs (profiles/variants.py)
+    // Schedule.  Large batches (the serial kernels alone hold >= 12 warps per SM: they are throughput-bound themselves,
+    // and every CTA of theirs that sits on an SM takes a third of its registers away from the bulk kernels) run the
+    // bulk kernels of all segments first and pipeline only the chain behind them ("two-phase": 89.7 against 92.2 ms at
+    // 1 000 clips); smaller batches pipeline everything (125 clips: 14.5 against 17.4 ms).  profiles/r2/variants_*.txt
+    int td_own = 0;
+    int two_phase = ((double)n_clips * d.K / 32.0 / std::max(1, ctx->sm_count)) >= 12.0 ? 1 : 0;
     if (const char* e = getenv("APT_TD_OWN_STREAM")) td_own = atoi(e);
     if (const char* e = getenv("APT_TWO_PHASE")) two_phase = atoi(e);
     if (!td_own) S[apt_plan::SK_TD] = S[apt_plan::SK_STFT];

@@ -2193,31 +2193,38 @@ __global__ void __launch_bounds__(ISTFT_NT) istft256_kernel(const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
-// Noise-floor statistics of a clip: mean and exact median of d = 10*log10(N2 + eps) over its T*K values
-// (rain_signal_processor.py:1286-1298).  The dB values are never stored: every pass recomputes them from the
-// noise PSD plane (log10 is cheap next to the plane's bytes).
-//   dbsum_kernel     per time segment, right behind trk2: float64 chunk sums in a fixed order + a histogram of the
-//                    dB values over 2048 LINEAR bins of 1/16 dB on [-96, +32) dB (a monotone binning, so the bin that
-//                    holds a rank is found by a prefix sum; the values cluster within a few dB, so a 1/16 dB bin holds
-//                    about 1 % of them, where the top radix digit of the float would hold a third)
-//   sel_scan0_kernel warp per clip: the bins holding the two middle ranks (numpy's even-count rule) + ranks inside
-//   sel_collect_kernel  second read of the plane: the order-preserving keys of the values in those bins are
-//                    appended to the clip's candidate list (warp-aggregated)
-//   sel_final_kernel CTA per clip: 4 x 8-bit radix select of both ranks inside the candidate list (L2-resident)
-// A clip whose candidates overflow its list (constant or near-constant planes) is flagged and goes through the
-// 3-level radix select over the whole plane instead (select_hist / select_scan: 11 + 11 + 10 key bits); those
-// kernels return at once for every other clip.
+// Noise-floor statistics of a clip: mean and exact median of d = 10*log10(w), w = N2 + eps, over its T*K values
+// (rain_signal_processor.py:1286-1298).  The dB values are never stored.
+//
+// Median.  d(w) -- the float32 log10 polynomial numpy uses, times 10 -- is monotone non-decreasing in w over every
+// float32 in [1e-9, 2^20] EXCEPT inside six tiny intervals at w = 1.5 * 2^k (k = -29, -21, -18, -15, 14, 17; at most 24
+// consecutive floats each; exhaustive scan, tests/test_kernel_math_emul.py), and every inversion d(a) > d(b), a < b, has
+// both a and b inside one of them.  So the order statistics of d are d of the order statistics of w, unless a selected
+// value falls into one of those intervals.  The select therefore runs on the bit patterns of w (positive floats order
+// like their bits), with no transcendental per element:
+//   dbsum_kernel     per time segment, right behind trk2: histogram of bits 30..19 of w (4096 bins of 1/16 octave, about
+//                    3 % of a clip's values in the fullest), and the float64 sum of log2(w) (hardware lg2: 2 ulp, far
+//                    inside the 1e-5 tolerance of the mean; one multiplication by 10*log10(2) per chunk)
+//   sel_scan0_kernel warp per clip: the bins holding the two middle ranks (numpy's even-count rule) + ranks inside;
+//                    clips whose bins touch an exclusion interval, or whose w leaves [1e-9, 2^20), are flagged
+//   sel_collect_kernel  second read of the plane: the bit patterns of the values in those bins are appended to the clip's
+//                    candidate list (warp-aggregated)
+//   sel_final_kernel CTA per clip: radix select of both ranks inside the candidate list (L2-resident)
+//   finalize_kernel  d of the two selected values with the exact polynomial
+// A flagged clip (exclusion interval, candidate overflow of a constant plane, eps < 1e-9) goes through the 3-level radix
+// select on the exact dB keys of the whole plane instead (select_hist / select_scan); those kernels return at once for
+// every other clip.
 // ---------------------------------------------------------------------------------------------
-constexpr int SEL_BINS = 2048;
+constexpr int SEL_BINS = 2048;       // histogram words per rank slot; the w histogram uses both slots as 4096 bins
+constexpr int SEL_WBINS = 4096;
 constexpr int DB_CF = 896;           // frames per chunk of dbsum / collect / select_hist (chunk = DB_CF * K values)
 struct SelState {
-    uint32_t prefix[2];   // fallback: key prefix found so far; finally: the two selected keys
+    uint32_t prefix[2];   // the two selected keys: bit patterns of w, or (fallback) order-preserving keys of d
     int64_t rank[2];      // fallback: rank inside the prefix
-    int64_t brank[2];     // rank inside the linear bin
-    int bin[2];           // linear bins holding the two middle ranks
+    int64_t brank[2];     // rank inside the w bin
+    int bin[2];           // w bins holding the two middle ranks
     int cnt;              // candidates appended
-    int overflow;         // candidate list too small: fallback
-    float v_lo, v_hi;     // noise-PSD range that surely contains every value of those bins (prefilter of the collect pass)
+    int overflow;         // fallback flag
 };
 __device__ __forceinline__ uint32_t db_key(float v) {
     const uint32_t u = f2u(v);
@@ -2226,11 +2233,10 @@ __device__ __forceinline__ uint32_t db_key(float v) {
 __device__ __forceinline__ float key_db(uint32_t k) {
     return u2f((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
-__device__ __forceinline__ int db_bin(float d) {   // monotone non-decreasing in d
-    float x = (d + 96.0f) * 16.0f;
-    x = fminf(fmaxf(x, 0.0f), (float)(SEL_BINS - 1));
-    return (int)x;
-}
+__device__ __forceinline__ int w_bin(float w) { return (int)((f2u(w) >> 19) & (SEL_WBINS - 1)); }   // w >= 0
+// exclusion intervals of the monotonicity of d(w), as bit patterns [first, last] (oracle: tests/test_kernel_math_emul.py)
+__constant__ uint32_t kDbExcl[6][2] = {{0x313ffff1u, 0x31400007u}, {0x353ffff8u, 0x35400000u}, {0x36bffff8u, 0x36c00000u},
+                                       {0x383ffff8u, 0x38400000u}, {0x46bffff8u, 0x46c00000u}, {0x483ffff8u, 0x48400000u}};
 
 // chunk `blockIdx.x + b.tile0` of clip `blockIdx.y`: returns false when the clip has no such chunk
 __device__ __forceinline__ bool db_chunk(const Batch& b, int K, const int64_t* __restrict__ chunk_off, int& c, int64_t& chunk,
@@ -2247,15 +2253,13 @@ __device__ __forceinline__ bool db_chunk(const Batch& b, int K, const int64_t* _
 __global__ void __launch_bounds__(256) dbsum_kernel(const __grid_constant__ DevParams p, Batch b, const float* __restrict__ N2,
                                                     const int64_t* __restrict__ chunk_off, uint32_t* __restrict__ hist,
                                                     double* __restrict__ chunk_sum) {
-    __shared__ uint32_t s_h[SEL_BINS];
-    __shared__ float s_ltab[64];
+    __shared__ uint32_t s_h[SEL_WBINS];
     __shared__ double s_part[8];
     const int tid = threadIdx.x;
     int c, ne;
     int64_t chunk, f0, e0;
     if (!db_chunk(b, p.K, chunk_off, c, chunk, f0, ne, e0)) return;
-    if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
-    for (int i = tid; i < SEL_BINS; i += 256) s_h[i] = 0;
+    for (int i = tid; i < SEL_WBINS; i += 256) s_h[i] = 0;
     __syncthreads();
     const float* src = N2 + f0 * p.K + e0;      // the chunk: 32-bit indices from here on
     double acc = 0.0;
@@ -2269,13 +2273,14 @@ __global__ void __launch_bounds__(256) dbsum_kernel(const __grid_constant__ DevP
             const int i = base + u * 256;
             v[u] = i < ne ? __ldg(src + i) : 1.0f;
         }
+        float part = 0.0f;      // 8 values in float32, then float64: |log2| < 64, 8 terms -> error below 1e-5 of one value's ulp budget
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int i = base + u * 256;
             if (i < ne) {
-                const float d = 10.0f * svml_log10f(v[u] + p.eps32, s_ltab);
-                acc += (double)d;
-                const int bin = db_bin(d);
+                const float w = v[u] + p.eps32;
+                part += __log2f(w);
+                const int bin = w_bin(w);
                 if (bin == run_bin) run_cnt++;
                 else {
                     if (run_cnt) atomicAdd(&s_h[run_bin], run_cnt);
@@ -2283,6 +2288,7 @@ __global__ void __launch_bounds__(256) dbsum_kernel(const __grid_constant__ DevP
                 }
             }
         }
+        acc += (double)part;
     }
     if (run_cnt) atomicAdd(&s_h[run_bin], run_cnt);
     // fixed-order block sum: shuffle tree inside the warp, then warps in order
@@ -2293,10 +2299,10 @@ __global__ void __launch_bounds__(256) dbsum_kernel(const __grid_constant__ DevP
     if (tid == 0) {
         double sm = 0.0;
         for (int w = 0; w < 8; w++) sm += s_part[w];
-        chunk_sum[__ldg(chunk_off + c) + chunk] = sm;
+        chunk_sum[__ldg(chunk_off + c) + chunk] = sm * 3.010299956639812;    // 10 * log10(2)
     }
     uint32_t* hg = hist + (size_t)c * 2 * SEL_BINS;
-    for (int i = tid; i < SEL_BINS; i += 256) {
+    for (int i = tid; i < SEL_WBINS; i += 256) {
         const uint32_t cnt = s_h[i];
         if (cnt) atomicAdd(hg + i, cnt);
     }
@@ -2314,7 +2320,6 @@ __global__ void select_init_kernel(Batch b, int K, SelState* st) {
     z.brank[0] = z.brank[1] = 0;
     z.bin[0] = z.bin[1] = 0;
     z.cnt = 0; z.overflow = 0;
-    z.v_lo = 0.0f; z.v_hi = 3.0e38f;
     st[c] = z;
 }
 
@@ -2352,40 +2357,40 @@ __global__ void sel_scan0_kernel(int clip0, int n_clips, float eps32, SelState* 
     const int c = clip0 + ci;
     const uint32_t* h = hist + (size_t)c * 2 * SEL_BINS;
     int64_t b0, b1;
-    const int f0 = warp_find_rank(h, SEL_BINS, st[c].rank[0], b0);
-    const int f1 = warp_find_rank(h, SEL_BINS, st[c].rank[1], b1);
+    const int f0 = warp_find_rank(h, SEL_WBINS, st[c].rank[0], b0);
+    const int f1 = warp_find_rank(h, SEL_WBINS, st[c].rank[1], b1);
     if (lane == 0) {
         const int q0 = f0 < 0 ? 0 : f0, q1 = f1 < 0 ? 0 : f1;
         st[c].bin[0] = q0; st[c].bin[1] = q1;
         st[c].brank[0] = st[c].rank[0] - b0; st[c].brank[1] = st[c].rank[1] - b1;
-        // Values of the bins [min, max] have dB values in [lo_db, hi_db): in the noise PSD itself that is
-        // v in [10^(lo_db/10) - eps, 10^(hi_db/10) - eps), widened by 1e-4 relative (0.0004 dB: the float32 log10
-        // polynomial is within 1e-6 dB of the true value).  The end bins are open-ended.
+        // the selected values lie in [w_lo, w_hi]: exact only if that range is inside [1e-9, 2^20) and clear of the
+        // exclusion intervals of d(w)
         const int lo_bin = q0 < q1 ? q0 : q1, hi_bin = q0 < q1 ? q1 : q0;
-        const double lo_db = (double)lo_bin / 16.0 - 96.0, hi_db = (double)(hi_bin + 1) / 16.0 - 96.0;
-        const double vl = (exp10(lo_db / 10.0) - (double)eps32) * (1.0 - 1e-4) - 1e-12;
-        const double vh = (exp10(hi_db / 10.0) - (double)eps32) * (1.0 + 1e-4) + 1e-12;
-        st[c].v_lo = lo_bin <= 0 ? -1.0f : (float)(vl > 0.0 ? vl : -1.0);
-        st[c].v_hi = hi_bin >= SEL_BINS - 1 ? 3.0e38f : (float)vh;
+        const uint32_t w_lo = (uint32_t)lo_bin << 19, w_hi = (((uint32_t)hi_bin + 1u) << 19) - 1u;
+        bool bad = !(eps32 >= 1e-9f) || w_lo < 0x3089705fu /* 1e-9f */ || w_hi >= 0x49800000u /* 2^20 */ || f0 < 0 || f1 < 0;
+        for (int i = 0; i < 6; i++) bad = bad || (w_lo <= kDbExcl[i][1] && w_hi >= kDbExcl[i][0]);
+        if (bad) st[c].overflow = 1;
     }
 }
 
+constexpr int SEL_STAGE = 8192;      // candidates a CTA stages in shared memory before its one append to the clip's list
 __global__ void __launch_bounds__(256) sel_collect_kernel(const __grid_constant__ DevParams p, Batch b, const float* __restrict__ N2,
                                                           const int64_t* __restrict__ chunk_off, SelState* st,
                                                           const int64_t* __restrict__ cand_off, uint32_t* __restrict__ cand) {
-    __shared__ float s_ltab[64];
+    __shared__ uint32_t s_buf[SEL_STAGE];
+    __shared__ int s_n, s_base;
     const int tid = threadIdx.x, lane = tid & 31;
     int c, ne;
     int64_t chunk, f0, e0;
     if (!db_chunk(b, p.K, chunk_off, c, chunk, f0, ne, e0)) return;
-    if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
-    __syncthreads();
+    if (st[c].overflow) return;
     const int bin0 = st[c].bin[0], bin1 = st[c].bin[1];
-    const float v_lo = st[c].v_lo, v_hi = st[c].v_hi;
     const int64_t co = __ldg(cand_off + c);
     const int cap = (int)(__ldg(cand_off + c + 1) - co);
     uint32_t* dst = cand + co;
     const float* src = N2 + f0 * p.K + e0;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
     constexpr int U = 8;
     const int n_iter = (ne + U * 256 - 1) / (U * 256);     // uniform over the CTA: the ballots below need every lane
     for (int it = 0; it < n_iter; it++) {
@@ -2394,37 +2399,49 @@ __global__ void __launch_bounds__(256) sel_collect_kernel(const __grid_constant_
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int i = base + u * 256;
-            v[u] = i < ne ? __ldg(src + i) : -2.0f;        // -2: outside every prefilter range
+            v[u] = i < ne ? __ldg(src + i) : -1.0f;        // -1: never taken
         }
-        // cheap prefilter on the noise PSD itself; only the ~1 % that pass pay for the log10
         bool any = false;
+        bool take[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) any = any || (v[u] >= v_lo && v[u] <= v_hi);
+        for (int u = 0; u < U; u++) {
+            const uint32_t wb = f2u(v[u] + p.eps32) >> 19;
+            take[u] = v[u] >= 0.0f && ((int)wb == bin0 || (int)wb == bin1);
+            any = any || take[u];
+        }
         if (!__any_sync(0xffffffffu, any)) continue;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            bool take = false;
-            float d = 0.0f;
-            if (v[u] >= v_lo && v[u] <= v_hi) {
-                d = 10.0f * svml_log10f(v[u] + p.eps32, s_ltab);
-                const int bin = db_bin(d);
-                take = bin == bin0 || bin == bin1;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, take);
+            const unsigned m = __ballot_sync(0xffffffffu, take[u]);
             if (m) {
+                // candidates are staged in shared memory (one shared-memory atomic per warp and instruction); what does not
+                // fit goes to the clip's list at once
                 int pos0 = 0;
-                if (lane == 0) pos0 = atomicAdd(&st[c].cnt, __popc(m));
+                if (lane == 0) pos0 = atomicAdd(&s_n, __popc(m));
                 pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-                if (take) {
+                if (take[u]) {
                     const int pos = pos0 + __popc(m & ((1u << lane) - 1u));
-                    if (pos < cap) dst[pos] = db_key(d);
+                    const uint32_t key = f2u(v[u] + p.eps32);
+                    if (pos < SEL_STAGE) s_buf[pos] = key;
+                    else {
+                        const int gp = atomicAdd(&st[c].cnt, 1);
+                        if (gp < cap) dst[gp] = key;
+                    }
                 }
             }
         }
     }
+    __syncthreads();
+    const int n = min(s_n, SEL_STAGE);
+    if (tid == 0) s_base = n ? atomicAdd(&st[c].cnt, n) : 0;     // ONE append per CTA
+    __syncthreads();
+    const int gb = s_base;
+    for (int i = tid; i < n; i += 256)
+        if (gb + i < cap) dst[gb + i] = s_buf[i];
 }
 
-// one CTA per clip: both ranks inside the candidate list, 8 key bits per pass
+// one CTA per clip: both ranks inside the candidate list, 8 key bits per pass (keys = bit patterns of w; the 12 top bits
+// are the bin)
 __global__ void __launch_bounds__(256) sel_final_kernel(int clip0, SelState* st, const int64_t* __restrict__ cand_off,
                                                         const uint32_t* __restrict__ cand) {
     __shared__ uint32_t s_h[2][256];
@@ -2432,41 +2449,44 @@ __global__ void __launch_bounds__(256) sel_final_kernel(int clip0, SelState* st,
     __shared__ int64_t s_rank[2];
     const int c = clip0 + (int)blockIdx.x;
     const int tid = threadIdx.x;
+    if (st[c].overflow) return;
     const int64_t co = __ldg(cand_off + c);
     const int cap = (int)(__ldg(cand_off + c + 1) - co);
     const int m = st[c].cnt;
     if (m > cap) { if (tid == 0) st[c].overflow = 1; return; }
     const uint32_t* src = cand + co;
-    const int bin0 = st[c].bin[0], bin1 = st[c].bin[1];
+    const uint32_t bin0 = (uint32_t)st[c].bin[0], bin1 = (uint32_t)st[c].bin[1];
     if (tid == 0) { s_pre[0] = s_pre[1] = 0; s_rank[0] = st[c].brank[0]; s_rank[1] = st[c].brank[1]; }
-    for (int pass = 0; pass < 4; pass++) {
-        const int sh = 24 - 8 * pass;
+    // keys inside a bin share bits 31..19; the select runs over bits 18..0 in passes of 8, 8 and 3 bits
+    for (int pass = 0; pass < 3; pass++) {
+        const int sh = pass == 0 ? 11 : (pass == 1 ? 3 : 0);
+        const int nb = pass == 2 ? 3 : 8;
         s_h[0][tid] = 0; s_h[1][tid] = 0;
         __syncthreads();
         const uint32_t pre0 = s_pre[0], pre1 = s_pre[1];
         for (int i = tid; i < m; i += 256) {
             const uint32_t key = src[i];
-            const int bin = db_bin(key_db(key));
-            const uint32_t hi = pass == 0 ? 0u : key >> (sh + 8);
-            const uint32_t dg = (key >> sh) & 255u;
-            if (bin == bin0 && hi == pre0) atomicAdd(&s_h[0][dg], 1u);
-            if (bin == bin1 && hi == pre1) atomicAdd(&s_h[1][dg], 1u);
+            const uint32_t low = key & 0x7ffffu;
+            const uint32_t hi = pass == 0 ? 0u : low >> (sh + nb);
+            const uint32_t dg = (low >> sh) & ((1u << nb) - 1u);
+            if ((key >> 19) == bin0 && hi == pre0) atomicAdd(&s_h[0][dg], 1u);
+            if ((key >> 19) == bin1 && hi == pre1) atomicAdd(&s_h[1][dg], 1u);
         }
         __syncthreads();
         if (tid < 2) {
             int64_t r = s_rank[tid], cum = 0;
-            int dgt = 255;
-            for (int j = 0; j < 256; j++) {
+            int dgt = (1 << nb) - 1;
+            for (int j = 0; j < (1 << nb); j++) {
                 const int64_t nx = cum + s_h[tid][j];
                 if (nx > r) { dgt = j; break; }
                 cum = nx;
             }
-            s_pre[tid] = (s_pre[tid] << 8) | (uint32_t)dgt;
+            s_pre[tid] = (s_pre[tid] << nb) | (uint32_t)dgt;
             s_rank[tid] = r - cum;
         }
         __syncthreads();
     }
-    if (tid == 0) { st[c].prefix[0] = s_pre[0]; st[c].prefix[1] = s_pre[1]; }
+    if (tid == 0) { st[c].prefix[0] = (bin0 << 19) | s_pre[0]; st[c].prefix[1] = (bin1 << 19) | s_pre[1]; }
 }
 
 // Fallback for clips flagged `overflow`: 3-level MSD radix select (11 + 11 + 10 key bits) over the whole plane, both
@@ -2560,7 +2580,14 @@ __global__ void finalize_kernel(const __grid_constant__ DevParams p, Batch b, co
         double s = 0.0;   // chunk sums in chunk order: independent of the launch geometry
         for (int64_t q = chunk_off[c]; q < chunk_off[c + 1]; q++) s += chunk_sum[q];
         r[6] = d2f(s / ((double)T * (double)p.K));
-        const float a = key_db(st[c].prefix[0]), bb = key_db(st[c].prefix[1]);
+        float a, bb;
+        if (st[c].overflow) { a = key_db(st[c].prefix[0]); bb = key_db(st[c].prefix[1]); }   // fallback: keys of d
+        else {   // bit patterns of w: d with the exact polynomial
+            float lt[64];
+            for (int i = 0; i < 64; i++) lt[i] = u2f(kSvmlLog10TabDev[i]);
+            a = 10.0f * svml_log10f(u2f(st[c].prefix[0]), lt);
+            bb = 10.0f * svml_log10f(u2f(st[c].prefix[1]), lt);
+        }
         r[7] = f_div(a + bb, 2.0f);
     }
 }

@@ -68,21 +68,52 @@ def install():
         be.__getattr__ = lambda n: type(n, (Exception,), {})
         sys.modules["botocore.exceptions"] = be
     if "kaitaistruct" not in sys.modules:
+        # Stand-in for the un-vendored `kaitaistruct` runtime (uv.lock pins kaitaistruct 0.11), restating the few calls the
+        # reference's generated class AudioBinary makes (parse.py:29-54): KaitaiStruct.from_bytes, and on the stream
+        # read_bytes / read_u1 / read_u4le / read_f4le / read_bytes_full.  Little-endian fixed-width reads of a byte buffer.
+        import struct as _struct
         ks = types.ModuleType("kaitaistruct")
+
+        class KaitaiStream:
+            def __init__(self, io_):
+                self._io = io_
+
+            def read_bytes(self, n):
+                b = self._io.read(n)
+                if len(b) < n:
+                    raise EOFError(f"requested {n} bytes, but only {len(b)} bytes available")
+                return b
+
+            def read_bytes_full(self):
+                return self._io.read()
+
+            def read_u1(self):
+                return _struct.unpack("<B", self.read_bytes(1))[0]
+
+            def read_u4le(self):
+                return _struct.unpack("<I", self.read_bytes(4))[0]
+
+            def read_f4le(self):
+                return _struct.unpack("<f", self.read_bytes(4))[0]
 
         class KaitaiStruct:
             def __init__(self, _io=None, _parent=None, _root=None):
                 self._io = _io
 
+            @classmethod
+            def from_bytes(cls, buf):
+                return cls(KaitaiStream(__import__("io").BytesIO(buf)))
+
         class ValidationNotEqualError(Exception):
-            pass
+            def __init__(self, expected=None, actual=None, io_=None, src_path=None):
+                super().__init__(f"not equal, expected {expected!r}, but got {actual!r} ({src_path})")
 
         ks.KaitaiStruct = KaitaiStruct
+        ks.KaitaiStream = KaitaiStream
         ks.ValidationNotEqualError = ValidationNotEqualError
-        ks.KaitaiStream = mock.MagicMock(name="KaitaiStream")
         ks.BytesIO = __import__("io").BytesIO
-        ks.__version__ = "0.10"
-        ks.API_VERSION = (0, 10)
+        ks.__version__ = "0.11"
+        ks.API_VERSION = (0, 11)
         sys.modules["kaitaistruct"] = ks
     import audio_processing_tools  # noqa: F401  (the reference package)
     try:

@@ -18,6 +18,7 @@ DEFAULT_GOLDENS = [n for n in golden_names(max_seconds=60) if not n.startswith("
 
 @pytest.fixture(scope="module")
 def goldens():
+    """(golden arrays, meta, int16 PCM, params) of the reference fixtures up to 60 s, default parameters."""
     out = {}
     for name in DEFAULT_GOLDENS:
         g, meta, pcm, params = load_golden(name)
@@ -206,4 +207,29 @@ def test_td_fast_path_gate_equals_exact(goldens):
     for n, c in zip(names, range(len(names))):
         f0, f1 = int(plan.frame_off[c]), int(plan.frame_off[c + 1])
         assert np.array_equal(fast["frame_class"][f0:f1], goldens[n][0]["frame_class"])
+    eng.close()
+
+
+def test_noise_floor_statistics_fallback_paths(oracle_mod):
+    """Median / mean of the noise-floor dB values on planes that leave the fast select: a silent clip (every value is eps:
+    below the verified range of the monotonicity table, and a constant plane overflows the candidate list), a clip with
+    long silent stretches, next to ordinary clips in the same batch.  Exact median, mean within 1e-5 of the oracle."""
+    from audio_processing_tools_b200.config import build_noise_config
+    from audio_processing_tools_b200.engine import BatchEngine
+    rng = np.random.default_rng(5)
+    silent = np.zeros(int(FS * 6.0), np.int16)
+    gappy = synth_clip_i16(25.0, 811, 3.0)
+    gappy[40000:200000] = 0
+    tiny = (rng.standard_normal(int(FS * 7.5)) * 1.2).round().astype(np.int16)       # a few LSBs of noise
+    clips = [silent, synth_clip_i16(8.0, 812, 10.0), gappy, tiny, synth_clip_i16(41.0, 813, 0.5)]
+    params = default_params(check_duration=5)
+    eng = BatchEngine(build_noise_config(FS, params), FS)
+    plan, out = eng.run_clips(clips, ())
+    for c, pcm in enumerate(clips):
+        m, s = oracle_mod.run(pcm_to_f32(pcm), dict(params, keep_state_debug=True))
+        st = out["clip_stats"][c]
+        assert st[7] == np.float32(m["median_noise_floor_db"]), (c, st[7], m["median_noise_floor_db"])
+        assert st[6] == pytest.approx(m["mean_noise_floor_db"], rel=1e-5)
+        f0, f1 = int(plan.frame_off[c]), int(plan.frame_off[c + 1])
+        assert np.array_equal(out["frame_class"][f0:f1], s["frame_class"])
     eng.close()

@@ -20,7 +20,7 @@ def emul():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     deps = [SRC, os.path.join(REPO, "audio_processing_tools_b200", "csrc", "apt_math.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", OUT, SRC])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-o", OUT, SRC])
     L = C.CDLL(OUT)
     L.emul_pairwise_f32.restype = C.c_float
     return L
@@ -100,3 +100,26 @@ def test_exchange_swizzle_is_conflict_free():
         for rows in (rows_a, rows_b):
             groups = [(idx(r, j) * 16 // 16) % 8 for r in rows]      # 16-byte slot inside the 128-byte bank window
             assert sorted(groups) == list(range(8)), (j, rows)
+
+
+def test_db_monotone_except_six_intervals(emul):
+    """The median select of the noise-floor dB values runs on the bit patterns of w = N2 + eps instead of on d(w) =
+    10 * log10f(w) (csrc/apt_kernels.cuh, dbsum / sel_* kernels).  That is exact as long as d is monotone in w; this scans
+    EVERY float32 in [1e-9, 2^20] with the kernel's own log10 polynomial and pins the only places where it is not: six
+    intervals of at most 24 floats at w = 1.5 * 2^k, which the kernels exclude (kDbExcl) by falling back to the select
+    on the dB keys themselves."""
+    import re
+    lo = int(np.float32(1e-9).view(np.uint32))
+    hi = int(np.float32(2.0 ** 20).view(np.uint32))
+    out = np.zeros(2 * 64, np.uint32)
+    emul.emul_db_monotone_scan.restype = C.c_int
+    n = emul.emul_db_monotone_scan(C.c_uint(lo), C.c_uint(hi), out.ctypes.data, 64, os.cpu_count() or 4)
+    got = sorted((int(out[2 * i]), int(out[2 * i + 1])) for i in range(n))
+    src = open(os.path.join(REPO, "audio_processing_tools_b200", "csrc", "apt_kernels.cuh")).read()
+    body = src[src.index("kDbExcl[6][2]"):]
+    body = body[:body.index("};")]
+    table = sorted((int(a, 16), int(b, 16)) for a, b in re.findall(r"\{0x([0-9a-f]{8})u, 0x([0-9a-f]{8})u\}", body))
+    assert len(table) == 6
+    assert got == table, (got, table)
+    for a, b in got:
+        assert b - a < 24

@@ -47,3 +47,24 @@ def test_batch_loader_packs_contiguously():
     assert list(lengths) == [11162] * 5 and np.array_equal(pcm[:11162], clips[0][:11162])
     with pytest.raises(ValueError):
         parse.Mark3BatchLoader(10, pin=False).load(files)
+
+
+def test_parser_matches_unmodified_reference():
+    """tests/golden/mark3_cases.npz holds what the reference's own parse.parse_mark_audio_file (parse.py:164-289) returned
+    for six byte strings assembled with struct.pack (oracle/make_golden_mark3.py: little / big endian, odd trailing byte,
+    bit depth 0, channel flag 2, missing magic, empty payload, forced PCM on a version-1 header): samples, dtype, every
+    metadata field and pcm_to_float must be identical."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "mark3_cases.npz"), allow_pickle=False)
+    index = json.loads(str(g["index"]))
+    assert len(index) == 6
+    for case in index:
+        name = case["name"]
+        blob = g[f"{name}__blob"].tobytes()
+        sig, meta = parse.parse_mark_audio_file(blob, force_file_type=case["force"])
+        assert str(sig.dtype) == case["sig_dtype"], name
+        assert np.array_equal(sig, g[f"{name}__sig"]), name
+        assert meta == case["meta"], (name, meta, case["meta"])
+        assert np.array_equal(parse.pcm_to_float(sig), g[f"{name}__float"]), name
