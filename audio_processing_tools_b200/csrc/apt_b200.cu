@@ -80,7 +80,7 @@ struct apt_plan {
     bool tdf_ok = false;                 // the dedicated float32 gate kernel (two biquad sections) is usable
     DevBuf<float> d_tdf_tab;
     TdFastParams tdf;
-    float td_guard = 1e-3f;
+    float td_guard = 2.5e-4f;
     // scratch
     DevBuf<float> d_Pband, d_n2, d_td, d_mf, d_nl, d_nl_all, d_Dscr;
     DevBuf<double> d_dbsum;   // [dB chunks] float64 sums of the noise-floor dB values
@@ -870,7 +870,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             if (fast_td) {
                 TdOut tf = to;
                 tf.td = nullptr; tf.want_block = 0; tf.want_kurt = 0;
-                tf.gate = pl->d_gate.p; tf.crest_dbg = out->td_fast_crest; tf.guard = pl->td_guard;
+                tf.gate = pl->d_gate.p; tf.crest_dbg = out->td_fast_crest; tf.guard = std::max(pl->td_guard, 1e-3f);
                 // flagged tiles of this segment: its own slice of the list (at most every tile of the segment) and counter
                 int64_t max_tiles = 1;
                 for (int c = clip0; c < clip0 + n_clips; c++) max_tiles = std::max(max_tiles, pl->td_tile_off[c + 1] - pl->td_tile_off[c]);

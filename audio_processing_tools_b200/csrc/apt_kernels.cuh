@@ -1241,7 +1241,7 @@ struct TdFastParams {
     float* crest_dbg;     // optional [nF]
     int2* list; int* list_count; int list_cap;
 };
-inline size_t tdf_smem_bytes() { return sizeof(float) * (TDF_XS + TDF_TAB_N + 4 * (TDF_NT / 32) + 2 * 64); }
+inline size_t tdf_smem_bytes() { return sizeof(float) * (TDF_XS + TDF_TAB_N + 4 * (TDF_NT / 32) + 3 * 64); }
 
 template <bool REV>
 __device__ __forceinline__ void tdf_pass(const TdFastParams& q, const float* __restrict__ s_tab, float* __restrict__ s_vend,
@@ -1322,6 +1322,7 @@ __global__ void __launch_bounds__(TDF_NT, 3) td_gate_fast_kernel(Batch b, const 
     float* s_vend = s_tab + TDF_TAB_N;                        // [NW][4]
     float* s_bsum = s_vend + 4 * (TDF_NT / 32);               // [64] per 128-sample block: sum of squares
     float* s_bmax = s_bsum + 64;                              // [64] peak
+    float* s_bin = s_bmax + 64;                               // [64] peak of the unfiltered input
     constexpr bool RAW = sizeof(PCM) == 2;
     const int tid = threadIdx.x;
     int64_t tile_in_clip;
@@ -1362,6 +1363,9 @@ __global__ void __launch_bounds__(TDF_NT, 3) td_gate_fast_kernel(Batch b, const 
             for (int j = 0; j < TDF_CH; j++) { const int v = tid * TDF_CH + j + sh; y[j] = s_x[v + ((v >> 5) << 2)]; }
         }
     }
+    float pin = 0.0f;        // peak of the unfiltered input: scales the rounding-error bound of the float32 filter
+#pragma unroll
+    for (int j = 0; j < TDF_CH; j++) pin = fmaxf(pin, fabsf(y[j]));
     tdf_pass<false>(q, s_tab, s_vend, y);
     tdf_pass<true>(q, s_tab, s_vend, y);
     // frame statistics: thread -> (sum of squares, peak) of its 32 samples, 4 threads -> one 128-sample block
@@ -1370,7 +1374,9 @@ __global__ void __launch_bounds__(TDF_NT, 3) td_gate_fast_kernel(Batch b, const 
     for (int j = 0; j < TDF_CH; j++) { ss = fmaf(y[j], y[j], ss); pk = fmaxf(pk, fabsf(y[j])); }
     ss += __shfl_xor_sync(0xffffffffu, ss, 1); pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, 1));
     ss += __shfl_xor_sync(0xffffffffu, ss, 2); pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, 2));
-    if ((tid & 3) == 0) { s_bsum[tid >> 2] = ss; s_bmax[tid >> 2] = pk; }     // block tid/4 of the buffer (64 blocks)
+    pin = fmaxf(pin, __shfl_xor_sync(0xffffffffu, pin, 1));
+    pin = fmaxf(pin, __shfl_xor_sync(0xffffffffu, pin, 2));
+    if ((tid & 3) == 0) { s_bsum[tid >> 2] = ss; s_bmax[tid >> 2] = pk; s_bin[tid >> 2] = pin; }     // block tid/4 of the buffer (64 blocks)
     __syncthreads();
     // frame f = 128-sample blocks TDF_WARM / 128 + f and + f + 1 of the buffer
     bool near = false;
@@ -1385,7 +1391,17 @@ __global__ void __launch_bounds__(TDF_NT, 3) td_gate_fast_kernel(Batch b, const 
         const int64_t g = f0 + t0 + tid;
         q.gate[g] = cf > q.thr ? 1 : 0;
         if (q.crest_dbg) q.crest_dbg[g] = cf;
-        near = fabsf(cf - q.thr) <= q.guard * fabsf(q.thr);
+        // Guard band: a fixed relative part plus a bound on what float32 rounding in the filter can do to the crest factor.
+        // Every operation of the recursion rounds at 2^-24 of values of the size of the INPUT (the states of a high-pass
+        // carry the low-frequency content it removes), and the filter spreads an error over its memory: |d crest| / crest
+        // <= 2 * C * 2^-24 * peak_in / rms_out with C ~ 10 measured (deviation 5e-6 at peak_in / rms_out ~ 5); C = 100 here,
+        // so input dominated by rumble far below the pass band widens the band by itself instead of escaping it.
+        float pin_f = 0.0f;
+#pragma unroll
+        for (int k = -2; k <= 3; k++) pin_f = fmaxf(pin_f, s_bin[B0 + tid + k]);
+        if (RAW) pin_f *= 3.0518509447574615e-05f;
+        const float tol = q.guard + 200.0f * 5.9604645e-08f * pin_f / fmaxf(rms, 1e-20f);
+        near = fabsf(cf - q.thr) <= tol * fabsf(q.thr);
     }
     if (__syncthreads_or(near ? 1 : 0) && tid == 0) {
         const int pos = atomicAdd(q.list_count, 1);
@@ -2373,13 +2389,12 @@ __global__ void sel_scan0_kernel(int clip0, int n_clips, float eps32, SelState* 
     }
 }
 
-constexpr int SEL_STAGE = 8192;      // candidates a CTA stages in shared memory before its one append to the clip's list
+constexpr int SEL_STAGE_W = 1024;    // candidates a WARP stages in shared memory before its one append to the clip's list
 __global__ void __launch_bounds__(256) sel_collect_kernel(const __grid_constant__ DevParams p, Batch b, const float* __restrict__ N2,
                                                           const int64_t* __restrict__ chunk_off, SelState* st,
                                                           const int64_t* __restrict__ cand_off, uint32_t* __restrict__ cand) {
-    __shared__ uint32_t s_buf[SEL_STAGE];
-    __shared__ int s_n, s_base;
-    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ uint32_t s_buf[8][SEL_STAGE_W];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     int c, ne;
     int64_t chunk, f0, e0;
     if (!db_chunk(b, p.K, chunk_off, c, chunk, f0, ne, e0)) return;
@@ -2389,55 +2404,40 @@ __global__ void __launch_bounds__(256) sel_collect_kernel(const __grid_constant_
     const int cap = (int)(__ldg(cand_off + c + 1) - co);
     uint32_t* dst = cand + co;
     const float* src = N2 + f0 * p.K + e0;
-    if (tid == 0) s_n = 0;
-    __syncthreads();
+    uint32_t* mine = s_buf[w];
+    int wn = 0;                                            // candidates this warp has staged (warp-uniform, no atomics)
     constexpr int U = 8;
-    const int n_iter = (ne + U * 256 - 1) / (U * 256);     // uniform over the CTA: the ballots below need every lane
-    for (int it = 0; it < n_iter; it++) {
-        const int base = it * U * 256 + tid;
+    for (int base = tid; base - lane - 32 * w < ne; base += U * 256) {     // warp-uniform trip count
         float v[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int i = base + u * 256;
             v[u] = i < ne ? __ldg(src + i) : -1.0f;        // -1: never taken
         }
-        bool any = false;
-        bool take[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const uint32_t wb = f2u(v[u] + p.eps32) >> 19;
-            take[u] = v[u] >= 0.0f && ((int)wb == bin0 || (int)wb == bin1);
-            any = any || take[u];
-        }
-        if (!__any_sync(0xffffffffu, any)) continue;
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const unsigned m = __ballot_sync(0xffffffffu, take[u]);
-            if (m) {
-                // candidates are staged in shared memory (one shared-memory atomic per warp and instruction); what does not
-                // fit goes to the clip's list at once
-                int pos0 = 0;
-                if (lane == 0) pos0 = atomicAdd(&s_n, __popc(m));
-                pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-                if (take[u]) {
-                    const int pos = pos0 + __popc(m & ((1u << lane) - 1u));
-                    const uint32_t key = f2u(v[u] + p.eps32);
-                    if (pos < SEL_STAGE) s_buf[pos] = key;
-                    else {
-                        const int gp = atomicAdd(&st[c].cnt, 1);
-                        if (gp < cap) dst[gp] = key;
-                    }
+            const uint32_t key = f2u(v[u] + p.eps32);
+            const uint32_t wb = key >> 19;
+            const bool take = v[u] >= 0.0f && ((int)wb == bin0 || (int)wb == bin1);
+            const unsigned m = __ballot_sync(0xffffffffu, take);
+            if (take) {
+                const int pos = wn + __popc(m & ((1u << lane) - 1u));
+                if (pos < SEL_STAGE_W) mine[pos] = key;
+                else {                                     // staging full (a plane with > 12 % of its values in one bin)
+                    const int gp = atomicAdd(&st[c].cnt, 1);
+                    if (gp < cap) dst[gp] = key;
                 }
             }
+            wn += __popc(m);
         }
     }
-    __syncthreads();
-    const int n = min(s_n, SEL_STAGE);
-    if (tid == 0) s_base = n ? atomicAdd(&st[c].cnt, n) : 0;     // ONE append per CTA
-    __syncthreads();
-    const int gb = s_base;
-    for (int i = tid; i < n; i += 256)
-        if (gb + i < cap) dst[gb + i] = s_buf[i];
+    __syncwarp();
+    const int n = min(wn, SEL_STAGE_W);
+    int gb = 0;
+    if (lane == 0 && n) gb = atomicAdd(&st[c].cnt, n);    // ONE append per warp
+    gb = __shfl_sync(0xffffffffu, gb, 0);
+    for (int i = lane; i < n; i += 32)
+        if (gb + i < cap) dst[gb + i] = mine[i];
 }
 
 // one CTA per clip: both ranks inside the candidate list, 8 key bits per pass (keys = bit patterns of w; the 12 top bits

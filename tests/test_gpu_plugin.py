@@ -182,13 +182,23 @@ def test_orchestrator_with_gpu_processors(goldens, tmp_path):
 
 def test_td_fast_path_gate_equals_exact(goldens):
     """Default flags decide the TD gate with the float32 filter + exact float64 re-check of the tiles that hold a frame
-    within the guard band of td_gate_threshold.  The gate plane and the labels must equal the float64 path's bit for bit,
-    and the float32 crest factor must sit far inside the guard band (1e-3 relative) everywhere."""
+    within the guard band of td_gate_threshold (2.5e-4 relative + a rounding-error bound that grows with the input's
+    low-frequency content).  The gate plane and the labels must equal the float64 path's bit for bit, and the float32
+    crest factor must sit far inside the guard band everywhere (asserted: 10x)."""
     from audio_processing_tools_b200.config import build_noise_config
     from audio_processing_tools_b200.engine import BatchEngine
     names = [n for n in goldens if goldens[n][1]["seconds"] == 60][:4]
     clips = [goldens[n][2] for n in names] + [synth_clip_i16(s, 700 + i, lam) for i, (s, lam) in
                                                enumerate(((7.3, 3.0), (33.1, 10.0), (20.6, 0.0), (3.2, 10.0)))]
+    n_std = len(clips)
+    # hard cases for the float32 filter: rumble 50 dB above the pass-band content (its rounding errors scale with the INPUT),
+    # a near-silent clip, and a full-scale clip
+    rng = np.random.default_rng(9)
+    t = np.arange(int(FS * 30.0)) / FS
+    rumble = 0.7 * np.sin(2 * np.pi * 23.0 * t) + 0.002 * rng.standard_normal(t.size)
+    clips.append(np.round(np.clip(rumble, -1, 1) * 32767).astype(np.int16))
+    clips.append(np.round(rng.standard_normal(int(FS * 22.0)) * 1.5).astype(np.int16))
+    clips.append(np.round(np.clip(rng.standard_normal(int(FS * 22.0)) * 0.5, -1, 1) * 32767).astype(np.int16))
     params = default_params(check_duration=3)
     eng = BatchEngine(build_noise_config(FS, params), FS)
     plan, fast = eng.run_clips(clips, ("gate", "td_fast_crest"))
@@ -197,13 +207,17 @@ def test_td_fast_path_gate_equals_exact(goldens):
     assert np.array_equal(fast["frame_class"], exact["frame_class"])
     assert np.array_equal(fast["event_count"], exact["event_count"])
     assert np.array_equal(fast["clip_stats"], exact["clip_stats"])
-    c64, c32 = exact["td"][0], fast["td_fast_crest"]
+    n_std_frames = int(plan.frame_off[n_std])
+    c64, c32 = exact["td"][0][:n_std_frames], fast["td_fast_crest"][:n_std_frames]
     ok = (c64 > 0) & (c32 > 0)          # tiles at the clip ends are decided by the exact kernel alone (no float32 value)
     assert ok.mean() > 0.8
+    h64, h32 = exact["td"][0][n_std_frames:], fast["td_fast_crest"][n_std_frames:]
+    okh = (h64 > 0) & (h32 > 0)
+    print(f"hard clips: max relative deviation {float(np.max(np.abs(h32[okh] - h64[okh]) / h64[okh])):.3e}")
     dev = float(np.max(np.abs(c32[ok] - c64[ok]) / c64[ok]))
-    near = float(np.mean(np.abs(c64[ok] - 2.5) <= 1e-3 * 2.5))
+    near = float(np.mean(np.abs(c64[ok] - 2.5) <= 2.5e-4 * 2.5))
     print(f"float32 crest factor: max relative deviation {dev:.3e} over {int(ok.sum())} frames; {near:.4%} of frames inside the guard band")
-    assert dev < 1e-4, dev
+    assert dev < 2.5e-5, dev
     for n, c in zip(names, range(len(names))):
         f0, f1 = int(plan.frame_off[c]), int(plan.frame_off[c + 1])
         assert np.array_equal(fast["frame_class"][f0:f1], goldens[n][0]["frame_class"])
