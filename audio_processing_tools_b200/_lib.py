@@ -124,7 +124,7 @@ EXPORTS = ("apt_init", "apt_destroy", "apt_last_error", "apt_abi_version", "apt_
            "apt_sizeof_out", "apt_params_default", "apt_plan_create", "apt_plan_destroy",
            "apt_plan_offsets", "apt_plan_total_frames", "apt_plan_total_samples",
            "apt_plan_scratch_bytes", "apt_run_i16", "apt_run_f32", "apt_plan_last_launches",
-           "apt_run_host_i16", "apt_run_host_clips", "apt_source_hash", "apt_plan_enable_timing", "apt_plan_enable_trace", "apt_plan_trace", "apt_plan_kernel_ms", "apt_selftest",
+           "apt_run_host_i16", "apt_run_host_clips", "apt_source_hash", "apt_plan_enable_timing", "apt_plan_enable_trace", "apt_plan_trace", "apt_plan_tc_error", "apt_plan_kernel_ms", "apt_selftest",
            "apt_dsd_run_i16", "apt_sizeof_bne_params", "apt_bne_run",
            "apt_sizeof_roe_params", "apt_roe_run")
 
@@ -224,6 +224,7 @@ def load():
         raise RuntimeError("libapt_b200.so apt_bne_params_t layout differs from the Python binding")
     L.apt_dsd_run_i16.argtypes = [vp, C.POINTER(AptDsdParams), C.c_int, i64p, C.POINTER(C.c_double), vp, vp, vp, C.c_int, vp]
     L.apt_plan_enable_timing.argtypes = [vp, C.c_int]
+    L.apt_plan_tc_error.argtypes = [vp]
     L.apt_plan_enable_trace.argtypes = [vp, C.c_int]
     L.apt_plan_trace.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float)]
     L.apt_plan_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]

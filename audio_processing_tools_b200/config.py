@@ -316,7 +316,8 @@ class ResolvedParams:
         P.rolloff_fraction = float(dv.get("raw_spectral_rolloff_fraction", 0.85))
         P.suppressor_bypass = int(bool(cfg.suppressor_bypass))
         P.clip_rain_min_frames = int(max(1, int(clip_rain_min_frames)))
-        P.fft_f64 = int(bool(fft_f64))
+        # True / 1: float64 FFT (reference arithmetic); False / 0: float32 FFT; "tc" / 2: tensor-core DFT (tolerance path)
+        P.fft_f64 = 2 if fft_f64 in ("tc", 2) else int(bool(fft_f64))
 
         # --- suppressor gain (_compute_gain, rain_signal_processor.py:400-533).  noise_conf is binary on this
         # path (1 - rain_conf), so the per-frame scalars take two values; they are formed here with the same

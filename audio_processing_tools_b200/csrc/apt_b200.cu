@@ -17,6 +17,7 @@
 #include "apt_dsd.cuh"
 #include "apt_bne.cuh"
 #include "apt_roe.cuh"
+#include "apt_tcdft.cuh"
 
 using namespace apt;
 
@@ -77,6 +78,9 @@ struct apt_plan {
     DevBuf<int> d_td_cnt;
     int64_t td_list_cap = 0;
     int td_fast = 1;
+    // tensor-core DFT (fft mode 2): B image (window x twiddles in two fp16 limbs, shared-memory layout), error flag
+    DevBuf<unsigned char> d_tc_B;
+    DevBuf<int> d_tc_err;
     bool tdf_ok = false;                 // the dedicated float32 gate kernel (two biquad sections) is usable
     DevBuf<float> d_tdf_tab;
     TdFastParams tdf;
@@ -406,6 +410,28 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         std::vector<float> fr(p->freqs, p->freqs + F);
         PL_OK(upload(pl->d_freqs, fr));
     }
+    if (p->fft_f64 == 2) {
+        // B[n][col] = window[n] * (cos, -sin)(2 pi k n / 256) for the band bins k, times 1024, as two fp16 limbs, laid out
+        // as the K-major SWIZZLE_128B shared-memory image the tensor-core kernel copies in: [limb][chunk of 64 n][row col]
+        if (2 * K > TC_N) { apt_plan_destroy(pl); return fail(ctx, -22, "tensor-core DFT: at most %d band bins", TC_N / 2); }
+        std::vector<unsigned char> img(TC_B_BYTES, 0);
+        for (int col = 0; col < 2 * K; col++) {
+            const int k = p->band_lo + (col >> 1);
+            for (int n = 0; n < 256; n++) {
+                const double ang = 2.0 * M_PI * (double)((k * n) & 255) / 256.0;
+                const double v = p->window[n] * ((col & 1) ? -sin(ang) : cos(ang)) * (double)TC_BSCALE;
+                const __half h1 = __float2half_rn((float)v);
+                const __half h2 = __float2half_rn((float)(v - (double)__half2float(h1)));
+                const int chunk = n / TC_KC, kk = n % TC_KC;
+                const int off = tc_swz(col, kk >> 3) + (kk & 7) * 2;
+                memcpy(&img[(size_t)(0 * TC_NCHUNK + chunk) * TC_B_TILE + off], &h1, 2);
+                memcpy(&img[(size_t)(1 * TC_NCHUNK + chunk) * TC_B_TILE + off], &h2, 2);
+            }
+        }
+        PL_OK(upload(pl->d_tc_B, img));
+        PL_OK(pl->d_tc_err.alloc(1));
+        PL_OK(cudaMemset(pl->d_tc_err.p, 0, sizeof(int)));
+    }
     // TD tables
     {
         const int halo = (p->blk_post_pre + 2) * p->blk_hop + p->blk_len;
@@ -565,6 +591,14 @@ int apt_plan_enable_timing(apt_plan_t* plan, int enable) {
     return 0;
 }
 
+int apt_plan_tc_error(apt_plan_t* plan) {
+    if (!plan) return -1;
+    if (!plan->d_tc_err.p) return 0;
+    int h = 0;
+    if (cudaMemcpy(&h, plan->d_tc_err.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -10;
+    return h;
+}
+
 int apt_plan_enable_trace(apt_plan_t* plan, int enable) {
     if (!plan) return -1;
     if (enable && !plan->tr_origin) {
@@ -646,6 +680,41 @@ static cudaError_t launch_stft(apt_plan* pl, const Batch& b, dim3 grid, const PC
     kern<<<grid, STFT_NT, smem, st>>>(pl->dp, b, pcm, pl->d_stft_tile_off.p, tab, so);
     pl->last_launches++;
     return cudaGetLastError();
+}
+
+// tensor-core DFT (fft mode 2, int16 input, band plane / band energies only)
+static cudaError_t launch_tcdft(apt_plan* pl, const Batch& b, const int16_t* pcm, const StftOut& so, cudaStream_t st) {
+    TcParams q;
+    memset(&q, 0, sizeof(q));
+    q.Bimg = pl->d_tc_B.p; q.P_band = so.P_band; q.band_energy = so.band_energy; q.nF = pl->nF;
+    q.K = pl->dp.K; q.band_lo = pl->dp.band_lo; q.n_modes = pl->dp.M;
+    for (int m = 0; m < APT_MAX_MODES; m++) { q.mode_blo[m] = pl->dp.mode_blo[m]; q.mode_bhi[m] = pl->dp.mode_bhi[m]; }
+    q.eps = (float)pl->dp.eps64; q.error_flag = pl->d_tc_err.p;
+    int64_t maxT = 1;
+    for (int c = b.clip0; c < b.clip0 + b.n_clips; c++) maxT = std::max(maxT, pl->frame_off[c + 1] - pl->frame_off[c]);
+    const int64_t t_hi = std::min<int64_t>(maxT, b.tb);
+    const int64_t tiles = std::max<int64_t>(0, (t_hi + TC_M - 1) / TC_M - b.ta / TC_M);
+    if (tiles == 0) return cudaSuccess;
+    const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(tiles, (pl->ctx->sm_count + b.n_clips - 1) / b.n_clips));
+    auto kern = tcdft256_kernel<int16_t>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e != cudaSuccess) return e;
+    kern<<<dim3((unsigned)gx, (unsigned)b.n_clips), TC_NT, TC_SMEM, st>>>(b, pcm, pl->d_stft_tile_off.p, q);
+    pl->last_launches++;
+    return cudaGetLastError();
+}
+// STFT of the 256-sample geometry in the plan's arithmetic: 1 = float64 FFT (the reference's), 0 = float32 FFT,
+// 2 = tensor-core DFT (tolerance path; int16 input, band plane / band energies only -- anything else runs the float32 FFT)
+template <typename PCM>
+static cudaError_t launch_stft_mode(apt_plan* pl, const Batch& b, dim3 grid, const PCM* pcm, const StftOut& so, cudaStream_t st) {
+    const int mode = pl->prm.fft_f64;
+    if (mode == 2) {
+        if constexpr (sizeof(PCM) == 2) {
+            if (!so.S && !so.P && !so.raw && pl->d_tc_B.p) return launch_tcdft(pl, b, pcm, so, st);
+        }
+        return launch_stft<float, PCM>(pl, b, grid, pcm, so, st);
+    }
+    return mode ? launch_stft<double, PCM>(pl, b, grid, pcm, so, st) : launch_stft<float, PCM>(pl, b, grid, pcm, so, st);
 }
 
 template <typename T, typename PCM>
@@ -755,7 +824,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     if (!full) {
         pl->mark(APT_KERNEL_STFT, st);
         const dim3 g = persistent_grid(pl, seg_grid(pl->stft_tile_off, clip0, n_clips, 0, INT64_MAX), 3);
-        cudaError_t e = pl->prm.fft_f64 ? launch_stft<double, PCM>(pl, b, g, pcm, so, st) : launch_stft<float, PCM>(pl, b, g, pcm, so, st);
+        cudaError_t e = launch_stft_mode<PCM>(pl, b, g, pcm, so, st);
         if (e != cudaSuccess) return fail(ctx, -11, "stft launch failed: %s", cudaGetErrorString(e));
         pl->mark(-1, st);
         return 0;
@@ -857,7 +926,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         {
             const dim3 g = persistent_grid(pl, seg_grid(pl->stft_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / STFT_TF), 3);
             tmark(apt_plan::SK_STFT, sg, 0);
-            RR(pl->prm.fft_f64 ? launch_stft<double, PCM>(pl, bs, g, pcm, so, S[apt_plan::SK_STFT]) : launch_stft<float, PCM>(pl, bs, g, pcm, so, S[apt_plan::SK_STFT]));
+            RR(launch_stft_mode<PCM>(pl, bs, g, pcm, so, S[apt_plan::SK_STFT]));
             RR(rec(apt_plan::SK_STFT, sg));
         }
         // TD features

@@ -319,7 +319,8 @@ def run_features(args, torch, dist, rank, world, local_rank, dev):
                         "algorithmic_bytes": bytes_algo, "peak_source": peak_src},
            "clocks": clocks, "gpu_launches": int(eng.last_launches * args.steps)}
     if rank == 0:
-        print(json.dumps(res))
+        print(json.dumps(res), flush=True)
+    eng.close()
 
 
 def main():
@@ -556,11 +557,12 @@ def main():
                                        "sample": f"{workers} x 60s clips, the UNMODIFIED reference (baseline/_ref) through its own "
                                                  f"process_audio_batches_v2 + RainDetectorProcessor, parallel=True, {workers} worker "
                                                  f"processes ({dtr:.1f}s wall); librosa stand-in from oracle/refharness"}
+    if rank == 0:
+        print(json.dumps(result), flush=True)      # before any teardown: a line lost in a buffer is a lost measurement
+    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if rank == 0:
-        print(json.dumps(result))
 
 
 if __name__ == "__main__":

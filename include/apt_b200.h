@@ -91,7 +91,10 @@ typedef struct apt_params_t {
     int32_t suppressor_bypass;
     int32_t clip_rain_min_frames;              /* rain_signal_processor.py:1256-1257 */
     /* arithmetic of the STFT: 1 = float64 FFT rounded to complex64 (the reference's arithmetic,
-       librosa/scipy.fft on float64), 0 = float32 FFT (faster, spectra within 1e-6 of frame max) */
+       librosa/scipy.fft on float64), 0 = float32 FFT (spectra within 2e-6 of frame max),
+       2 = DFT as a GEMM on the tcgen05 tensor cores (n_fft = 256, hop = 128, int16 input, band plane / band energies
+       only; exact int8 limbs of the samples x two fp16 limbs of window x twiddle, fp32 accumulation in tensor memory:
+       the same tolerance class as 0; requests it cannot serve run as 0) */
     int32_t fft_f64;
     /* suppressor gain, rain_signal_processor.py:400-533 (_compute_gain) and :1028-1091; float32 values are
        the ones numpy forms when the reference mixes Python floats with float32 arrays */
@@ -217,6 +220,9 @@ int  apt_plan_enable_timing(apt_plan_t* plan, int enable);
    (0 stft, 1 td, 2 trk1, 3 flux, 4 base, 5 decide, 6 trk2, 7 dbsum) and time segment s the start and end of that
    launch in ms since the start of the call: out_ms[(k * 64 + s) * 2 + {0, 1}]; *n_seg = segments of the last run
    (0: it did not run pipelined), *total_ms = duration of the whole call on the caller's stream. */
+/* Tensor-core DFT only: 1 if one of its bounded barrier waits gave up (the results of that run are invalid), else 0.
+   Synchronises the device. */
+int  apt_plan_tc_error(apt_plan_t* plan);
 int  apt_plan_enable_trace(apt_plan_t* plan, int enable);
 int  apt_plan_trace(apt_plan_t* plan, float* out_ms /* [8][64][2] */, int* n_seg, float* total_ms);
 int  apt_plan_kernel_ms(apt_plan_t* plan, float* out_ms /* [APT_N_KERNELS] */);

@@ -247,3 +247,35 @@ def test_noise_floor_statistics_fallback_paths(oracle_mod):
         f0, f1 = int(plan.frame_off[c]), int(plan.frame_off[c + 1])
         assert np.array_equal(out["frame_class"][f0:f1], s["frame_class"])
     eng.close()
+
+
+def test_tensor_core_dft_variant(oracle_mod):
+    """DFT-as-GEMM on the tcgen05 tensor cores (fft = "tc": exact int8 limbs of the samples x two fp16 limbs of
+    window x twiddle, fp32 accumulation in tensor memory) against the float64 FFT path: band energies within 1e-4
+    (north_star tolerance for spectra / band energies in fp32), and -- feeding the full pipeline as the tolerance-path
+    front end -- frame labels compared with the oracle (flips counted and bounded, as for the float32 FFT)."""
+    from audio_processing_tools_b200.config import build_noise_config
+    from audio_processing_tools_b200.engine import BatchEngine
+    specs = [(60.0, 900, 3.0), (7.3, 901, 10.0), (33.1, 902, 0.0), (2.5, 903, 3.0), (20.0, 904, 0.5)]
+    clips = [synth_clip_i16(s, seed, lam) for s, seed, lam in specs]
+    params = default_params(check_duration=2)
+    e64 = BatchEngine(build_noise_config(FS, params), FS)
+    etc = BatchEngine(build_noise_config(FS, params), FS, fft_f64="tc")
+    plan, ref = e64.run_clips(clips, ("band_energy",), full=False)
+    plan2, got = etc.run_clips(clips, ("band_energy",), full=False)
+    assert etc.L.apt_plan_tc_error(plan2.h) == 0, "a barrier wait of the tensor-core kernel gave up"
+    rel = np.abs(got["band_energy"] - ref["band_energy"]) / np.maximum(ref["band_energy"], 1e-12)
+    print(f"tensor-core DFT band energies: max relative deviation {float(rel.max()):.3e}")
+    assert rel.max() <= 1e-4
+    # full pipeline on top of the tensor-core spectra
+    plan3, full = etc.run_clips(clips, ())
+    assert etc.L.apt_plan_tc_error(plan3.h) == 0
+    flips = 0
+    for c, pcm in enumerate(clips):
+        m, s = oracle_mod.run(pcm_to_f32(pcm), dict(params, keep_state_debug=True))
+        f0, f1 = int(plan3.frame_off[c]), int(plan3.frame_off[c + 1])
+        flips += int((full["frame_class"][f0:f1] != s["frame_class"]).sum())
+        assert full["clip_stats"][c][7] == pytest.approx(m["median_noise_floor_db"], abs=2e-3)
+    print(f"tensor-core DFT front end: {flips} of {plan3.nF} frame labels differ from the oracle")
+    assert flips <= plan3.nF // 2000
+    e64.close(); etc.close()
