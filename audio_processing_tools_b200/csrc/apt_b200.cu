@@ -695,7 +695,8 @@ static cudaError_t launch_tcdft(apt_plan* pl, const Batch& b, const int16_t* pcm
     const int64_t t_hi = std::min<int64_t>(maxT, b.tb);
     const int64_t tiles = std::max<int64_t>(0, (t_hi + TC_M - 1) / TC_M - b.ta / TC_M);
     if (tiles == 0) return cudaSuccess;
-    const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(tiles, (pl->ctx->sm_count + b.n_clips - 1) / b.n_clips));
+    // one CTA per SM (214 KB of shared memory): as many CTAs per clip as fit in ONE wave over the launch's clips
+    const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(tiles, pl->ctx->sm_count / b.n_clips));
     auto kern = tcdft256_kernel<int16_t>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e != cudaSuccess) return e;

@@ -6,19 +6,20 @@
 // is one GEMM  D[frames x 2K] = A[frames x 256] * B[256 x 2K]  (B = window x twiddles: the real and imaginary column of every
 // band bin; 2K = 142 -> N = 144).  Arithmetic: the int16 sample is split exactly into two 8-bit limbs, x = 256 xh + xl, both
 // exact in fp16; B is split into two fp16 limbs (B ~ B1 + B2, |error| < 2^-22 of the largest coefficient); the products run
-// as kind::f16 MMAs with fp32 accumulation in tensor memory, one accumulator per sample limb (D_hi, D_lo), combined in the
-// epilogue:  S = (256 D_hi + D_lo) / (1024 * 32767).  Accuracy class of the float32 FFT (spectra ~1e-6 of the frame maximum):
+// as kind::f16 MMAs with fp32 accumulation in tensor memory (the high limb enters as 256 xh, so one accumulator takes all
+// four products):  S = D / (1024 * 32767).  Accuracy class of the float32 FFT (spectra ~1e-6 of the frame maximum):
 // this is the tolerance path (fft = "tc"), not the bit-exact float64 default.
 //
 // One CTA per SM, persistent over tiles of 128 frames:
 //   B (144 KB, both limbs, all of K) is brought in ONCE per CTA by bulk-tensor-style TMA copies (cp.async.bulk, mbarrier
 //   complete_tx) into the canonical K-major SWIZZLE_128B layout the MMA reads (the image is prepared on the host);
-//   A is produced per tile in four K-chunks of 64 samples by the 128 worker threads: coalesced 128-bit loads of the raw int16
-//   samples (overlapping frames come from L1/L2), limb split with two logic + two half2 operations per sample pair, 128-bit
-//   stores into the same swizzled layout, double buffered against the MMA through full/empty mbarriers;
+//   A is produced per tile in four K-chunks of 64 samples by 8 producer warps: coalesced 128-bit loads of the raw int16
+//   samples (overlapping frames come from L1/L2), limb split with two logic + two / three half2 operations per sample pair
+//   (the high limb is stored as 256 xh, exact in fp16, so that both limbs accumulate into ONE accumulator), 128-bit stores
+//   into the same swizzled layout, double buffered against the MMA through full / empty mbarriers;
 //   one elected thread issues the tcgen05.mma instructions (M = 128, N = 144, K = 16 each: 4 per K-step) and commits to the
-//   mbarriers; the 128 worker threads then read the accumulators with tcgen05.ld (thread = frame row), form |S|^2 and write
-//   the band plane (through shared memory, coalesced) and / or the band energies.
+//   mbarriers; the accumulator (144 of 512 TMEM columns) is double buffered, so 4 epilogue warps read tile n with tcgen05.ld
+//   (thread = frame row), form |S|^2 and write the band plane / the band energies while the MMAs of tile n + 1 run.
 // Every mbarrier wait is bounded: a barrier that never completes sets an error flag and returns instead of hanging the GPU.
 #pragma once
 #include <cuda_fp16.h>
@@ -34,8 +35,10 @@ constexpr int TC_A_TILE = TC_M * TC_KC * 2;        // 16 KB: one limb of one chu
 constexpr int TC_B_TILE = TC_N * TC_KC * 2;        // 18 KB
 constexpr int TC_B_BYTES = 2 * TC_NCHUNK * TC_B_TILE;   // 144 KB
 constexpr int TC_A_BYTES = 2 * 2 * TC_A_TILE;      // 2 slots x 2 limbs
-constexpr int TC_SMEM = TC_B_BYTES + TC_A_BYTES + 1024 /* barriers + tmem pointer */ + 1024 /* alignment slack */;
-constexpr int TC_NT = 160;           // 4 worker warps + 1 MMA / TMA warp
+constexpr int TC_E_BYTES = 4 * 32 * 9 * 4;         // epilogue staging: per warp 32 rows x (8 + 1) floats
+constexpr int TC_SMEM = TC_B_BYTES + TC_A_BYTES + TC_E_BYTES + 1024 /* barriers + tmem pointer */ + 1024 /* alignment slack */;
+constexpr int TC_NPROD = 256;        // producer threads (warps 0..7)
+constexpr int TC_NT = TC_NPROD + 128 + 32;   // + 4 epilogue warps (8..11) + the MMA / TMA warp (12)
 constexpr float TC_BSCALE = 1024.0f; // B is stored times 1024 (keeps the low limb out of fp16's subnormal range)
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 26;
 
@@ -125,36 +128,36 @@ __global__ void __launch_bounds__(TC_NT, 1) tcdft256_kernel(Batch b, const PCM* 
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sB = sm;                                  // [limb][chunk][TC_B_TILE]
     unsigned char* sA = sm + TC_B_BYTES;                     // [slot][limb][TC_A_TILE]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + TC_A_BYTES);
+    float* sE = reinterpret_cast<float*>(sA + TC_A_BYTES);   // [4 warps][32][9] epilogue staging
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + TC_A_BYTES + TC_E_BYTES);
     uint64_t* bar_b = bars + 0;          // B image landed
-    uint64_t* bar_full = bars + 1;       // [2] A slot filled (128 arrivals)
+    uint64_t* bar_full = bars + 1;       // [2] A slot filled (TC_NPROD arrivals)
     uint64_t* bar_empty = bars + 3;      // [2] A slot consumed by the MMAs (tcgen05.commit)
-    uint64_t* bar_acc = bars + 5;        // accumulators complete (tcgen05.commit)
-    uint64_t* bar_accfree = bars + 6;    // accumulators read out (128 arrivals)
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* bar_acc = bars + 5;        // [2] accumulator stage complete (tcgen05.commit)
+    uint64_t* bar_accfree = bars + 7;    // [2] accumulator stage read out (128 arrivals)
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 10);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool worker = warp < 4;
+    const bool producer = warp < 8, epilogue = warp >= 8 && warp < 12, mma_thread = tid == TC_NPROD + 128;
 
     if (tid == 0) {
         tc_mbar_init(bar_b, 1);
-        tc_mbar_init(bar_full + 0, 128); tc_mbar_init(bar_full + 1, 128);
-        tc_mbar_init(bar_empty + 0, 1); tc_mbar_init(bar_empty + 1, 1);
-        tc_mbar_init(bar_acc, 1);
-        tc_mbar_init(bar_accfree, 128);
+        for (int i = 0; i < 2; i++) {
+            tc_mbar_init(bar_full + i, TC_NPROD); tc_mbar_init(bar_empty + i, 1);
+            tc_mbar_init(bar_acc + i, 1); tc_mbar_init(bar_accfree + i, 128);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == 12) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *s_tmem;
-    const uint32_t tm_hi = tmem, tm_lo = tmem + 256;         // accumulator columns [0,144) and [256,400)
+    const uint32_t tmem = *s_tmem;                           // accumulator stage s: columns [256 s, 256 s + 144)
 
     // the B image: eight TMA bulk copies (limb x chunk), one mbarrier
-    if (tid == 128) {
+    if (mma_thread) {
         tc_mbar_expect_tx(bar_b, (uint32_t)TC_B_BYTES);
         for (int i = 0; i < 2 * TC_NCHUNK; i++) tc_bulk_g2s(sB + (size_t)i * TC_B_TILE, q.Bimg + (size_t)i * TC_B_TILE, TC_B_TILE, bar_b);
     }
@@ -169,48 +172,59 @@ __global__ void __launch_bounds__(TC_NT, 1) tcdft256_kernel(Batch b, const PCM* 
     const int n_tiles = (int)((min((int64_t)T_clip, (int64_t)b.tb) + TC_M - 1) / TC_M);
     const bool aligned = ((base & 7) == 0) && sizeof(PCM) == 2;
     bool ok = true;
-    uint32_t it_fill = 0, it_mma = 0;        // chunks filled / consumed so far (slot = it & 1, phase = (it >> 1) & 1)
-    uint32_t n_tile_done = 0;
+    uint32_t it = 0;                 // K-chunks filled (producers) / consumed (MMA thread) so far: slot = it & 1
+    uint32_t nt = 0;                 // tiles done: accumulator stage = nt & 1
 
-    for (int tile = tile_lo + (int)blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, n_tile_done++) {
-        const int t0 = tile * TC_M;
-        if (worker) {
-            // ---- A producer: chunk kc = samples 64 kc .. 64 kc + 63 of every frame of the tile
-            for (int kc = 0; kc < TC_NCHUNK && ok; kc++, it_fill++) {
-                const int slot = it_fill & 1;
-                if (it_fill >= 2) ok = tc_mbar_wait(bar_empty + slot, ((it_fill >> 1) - 1) & 1);
+    if (producer) {
+        // ---- A producers: chunk kc = samples 64 kc .. 64 kc + 63 of every frame of the tile, both limbs
+        for (int tile = tile_lo + (int)blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+            const int t0 = tile * TC_M;
+            for (int kc = 0; kc < TC_NCHUNK && ok; kc++, it++) {
+                const int slot = it & 1;
+                // all four loads of this thread's items first (in flight while the slot is still being read)
+                uint4 raw[4];
+                bool fast[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int item = tid + u * TC_NPROD;
+                    const int r = item >> 3, c16 = item & 7;
+                    const int64_t s = (int64_t)(t0 + r - 1) * 128 + kc * TC_KC + c16 * 8;     // first of 8 samples (clip-relative)
+                    fast[u] = aligned && (t0 + r) < T_clip && s >= 0 && s + 8 <= N;
+                    raw[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if constexpr (sizeof(PCM) == 2) {
+                        if (fast[u]) raw[u] = __ldg(reinterpret_cast<const uint4*>(pcm + base + s));
+                        else if ((t0 + r) < T_clip) {
+                            uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                            for (int e = 0; e < 8; e++) {
+                                const int64_t se = s + e;
+                                const uint32_t h = (se >= 0 && se < N) ? (uint32_t)(uint16_t)__ldg(pcm + base + se) : 0u;
+                                w[e >> 1] |= h << (16 * (e & 1));
+                            }
+                            raw[u] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
+                if (it >= 2) ok = tc_mbar_wait(bar_empty + slot, ((it >> 1) - 1) & 1);
                 if (!ok) break;
                 unsigned char* a_hi = sA + (size_t)(slot * 2 + 0) * TC_A_TILE;
                 unsigned char* a_lo = sA + (size_t)(slot * 2 + 1) * TC_A_TILE;
-#pragma unroll 2
-                for (int item = tid; item < TC_M * 8; item += 128) {
-                    const int r = item >> 3, c16 = item & 7;
-                    const int t = t0 + r;
-                    const int64_t s = (int64_t)(t - 1) * 128 + kc * TC_KC + c16 * 8;     // first of 8 samples (clip-relative)
-                    uint32_t w[4] = {0u, 0u, 0u, 0u};                                      // 8 int16, little endian pairs
-                    if (t < T_clip) {
-                        if constexpr (sizeof(PCM) == 2) {
-                            if (aligned && s >= 0 && s + 8 <= N) {
-                                const uint4 v = __ldg(reinterpret_cast<const uint4*>(pcm + base + s));
-                                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-                            } else {
+                const __half2 c1024 = __floats2half2_rn(1024.0f, 1024.0f), c1152 = __floats2half2_rn(1152.0f, 1152.0f);
+                const __half2 c256 = __floats2half2_rn(256.0f, 256.0f);
 #pragma unroll
-                                for (int e = 0; e < 8; e++) {
-                                    const int64_t se = s + e;
-                                    const uint32_t h = (se >= 0 && se < N) ? (uint32_t)(uint16_t)__ldg(pcm + base + se) : 0u;
-                                    w[e >> 1] |= h << (16 * (e & 1));
-                                }
-                            }
-                        }
-                    }
-                    // limb split: xl = low byte (0..255), xh = high byte as signed (-128..127); 0x6400 | n is the fp16 1024 + n
+                for (int u = 0; u < 4; u++) {
+                    const int item = tid + u * TC_NPROD;
+                    const int r = item >> 3, c16 = item & 7;
+                    const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+                    // limb split: xl = low byte (0..255), xh = high byte as signed (-128..127); 0x6400 | n is the fp16 1024 + n.
+                    // The high limb is stored as 256 * xh (exact in fp16), so that both limbs accumulate into one accumulator.
                     uint32_t lo[4], hi[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const uint32_t l = (w[i] & 0x00ff00ffu) | 0x64006400u;
                         const uint32_t h = (((w[i] >> 8) & 0x00ff00ffu) ^ 0x00800080u) | 0x64006400u;
-                        const __half2 lh = __hsub2(*reinterpret_cast<const __half2*>(&l), __floats2half2_rn(1024.0f, 1024.0f));
-                        const __half2 hh = __hsub2(*reinterpret_cast<const __half2*>(&h), __floats2half2_rn(1152.0f, 1152.0f));
+                        const __half2 lh = __hsub2(*reinterpret_cast<const __half2*>(&l), c1024);
+                        const __half2 hh = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&h), c1152), c256);
                         lo[i] = *reinterpret_cast<const uint32_t*>(&lh);
                         hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
                     }
@@ -221,13 +235,17 @@ __global__ void __launch_bounds__(TC_NT, 1) tcdft256_kernel(Batch b, const PCM* 
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA
                 tc_mbar_arrive(bar_full + slot);
             }
-        } else if (tid == 128) {
-            // ---- MMA issuer
-            if (n_tile_done == 0) ok = tc_mbar_wait(bar_b, 0);
-            if (ok && n_tile_done > 0) ok = tc_mbar_wait(bar_accfree, (n_tile_done - 1) & 1);     // epilogue of the previous tile done
-            for (int kc = 0; kc < TC_NCHUNK && ok; kc++, it_mma++) {
-                const int slot = it_mma & 1;
-                ok = tc_mbar_wait(bar_full + slot, (it_mma >> 1) & 1);
+        }
+    } else if (mma_thread) {
+        // ---- MMA issuer: per K-chunk 4 K-steps x (hi, lo) x (B1, B2) into the tile's accumulator stage
+        ok = tc_mbar_wait(bar_b, 0);
+        for (int tile = tile_lo + (int)blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, nt++) {
+            const uint32_t stage = nt & 1;
+            if (nt >= 2) ok = tc_mbar_wait(bar_accfree + stage, ((nt >> 1) - 1) & 1);     // epilogue of tile nt - 2 has drained this stage
+            const uint32_t tm = tmem + 256u * stage;
+            for (int kc = 0; kc < TC_NCHUNK && ok; kc++, it++) {
+                const int slot = it & 1;
+                ok = tc_mbar_wait(bar_full + slot, (it >> 1) & 1);
                 if (!ok) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = tc_smem_u32(sA + (size_t)(slot * 2 + 0) * TC_A_TILE);
@@ -237,72 +255,84 @@ __global__ void __launch_bounds__(TC_NT, 1) tcdft256_kernel(Batch b, const PCM* 
 #pragma unroll
                 for (int ks = 0; ks < TC_KC / 16; ks++) {
                     const uint32_t ko = ks * 32;                      // 16 fp16 = 32 bytes along K inside the swizzled row
-                    const uint32_t acc = (kc | ks) ? 1u : 0u;
-                    tc_mma(tm_hi, tc_desc(a_hi + ko), tc_desc(b1 + ko), acc);
-                    tc_mma(tm_hi, tc_desc(a_hi + ko), tc_desc(b2 + ko), 1u);
-                    tc_mma(tm_lo, tc_desc(a_lo + ko), tc_desc(b1 + ko), acc);
-                    tc_mma(tm_lo, tc_desc(a_lo + ko), tc_desc(b2 + ko), 1u);
+                    tc_mma(tm, tc_desc(a_hi + ko), tc_desc(b1 + ko), (kc | ks) ? 1u : 0u);
+                    tc_mma(tm, tc_desc(a_hi + ko), tc_desc(b2 + ko), 1u);
+                    tc_mma(tm, tc_desc(a_lo + ko), tc_desc(b1 + ko), 1u);
+                    tc_mma(tm, tc_desc(a_lo + ko), tc_desc(b2 + ko), 1u);
                 }
                 tc_commit(bar_empty + slot);                          // slot free once these MMAs have read it
             }
-            if (ok) tc_commit(bar_acc);
+            if (ok) tc_commit(bar_acc + stage);
         }
-        if (worker && ok) {
-            // ---- epilogue: thread = frame row; TMEM lane = 32 * warp + lane
-            ok = tc_mbar_wait(bar_acc, n_tile_done & 1);
-            if (ok) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const int r = tid;
-                const int t = t0 + r;
-                const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-                const float k1 = 256.0f, k2 = 1.0f / (TC_BSCALE * 32767.0f);
-                float be[APT_MAX_MODES + 1];
+    } else if (epilogue) {
+        // ---- epilogue: thread = frame row; TMEM lane = 32 * (warp - 8) + lane
+        const int ew = warp - 8, r = ew * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
+        float* st = sE + ew * 32 * 9;
+        const float k2 = 1.0f / (TC_BSCALE * 32767.0f);
+        const int K = q.K;
+        for (int tile = tile_lo + (int)blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, nt++) {
+            const int t0 = tile * TC_M;
+            const int t = t0 + r;
+            const uint32_t stage = nt & 1;
+            ok = tc_mbar_wait(bar_acc + stage, (nt >> 1) & 1);
+            if (!ok) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tm = tmem + 256u * stage + lane_off;
+            float be[APT_MAX_MODES + 1];
 #pragma unroll
-                for (int m = 0; m <= APT_MAX_MODES; m++) be[m] = 0.0f;
-                // the band plane goes through the (now idle) A slots: [row][K] floats, then a coalesced copy out
-                float* sP = reinterpret_cast<float*>(sA);
-                const int K = q.K;
-                for (int cb = 0; cb < TC_N; cb += 16) {
-                    float vh[16], vl[16];
-                    tc_ld16(tm_hi + lane_off + cb, vh);
-                    tc_ld16(tm_lo + lane_off + cb, vl);
+            for (int m = 0; m <= APT_MAX_MODES; m++) be[m] = 0.0f;
+            const int nrow = min(32, T_clip - (t0 + ew * 32));         // rows of this warp that exist
+            for (int cb = 0; cb < TC_N; cb += 16) {
+                float v[16];
+                tc_ld16(tm + cb, v);
+                float pw[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int kb = (cb >> 1) + j;
-                        if (kb < K) {
-                            const float re = fmaf(k1, vh[2 * j], vl[2 * j]) * k2;
-                            const float im = fmaf(k1, vh[2 * j + 1], vl[2 * j + 1]) * k2;
-                            const float pw = fmaf(re, re, im * im);
-                            if (q.P_band) sP[r * K + kb] = pw;
-                            if (q.band_energy) {
-                                be[q.n_modes] += pw;
+                for (int j = 0; j < 8; j++) {
+                    const float re = v[2 * j] * k2, im = v[2 * j + 1] * k2;
+                    pw[j] = fmaf(re, re, im * im);
+                }
+                const int kb0 = cb >> 1;
+                if (q.band_energy) {
+                    // the eight bins of this step against every mode band that intersects them (a band spans one or two steps)
+                    const int nv = min(8, K - kb0);
 #pragma unroll
-                                for (int m = 0; m < APT_MAX_MODES; m++)
-                                    if (m < q.n_modes && kb >= q.mode_blo[m] && kb <= q.mode_bhi[m]) be[m] += pw;
-                            }
+                    for (int j = 0; j < 8; j++) if (j < nv) be[APT_MAX_MODES] += pw[j];
+#pragma unroll
+                    for (int m = 0; m < APT_MAX_MODES; m++) {
+                        const int lo = max(q.mode_blo[m] - kb0, 0), hi = min(min(q.mode_bhi[m] - kb0, 7), nv - 1);
+                        if (m < q.n_modes && lo <= hi) {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) if (j >= lo && j <= hi) be[m] += pw[j];
                         }
                     }
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                tc_mbar_arrive(bar_accfree);                          // the next tile's MMAs may overwrite the accumulators
-                if (q.band_energy && t < T_clip) {
-                    for (int m = 0; m < q.n_modes; m++) q.band_energy[(int64_t)m * q.nF + f0 + t] = be[m];
-                    q.band_energy[(int64_t)q.n_modes * q.nF + f0 + t] = be[q.n_modes] + q.eps;
-                }
                 if (q.P_band) {
-                    asm volatile("bar.sync 1, 128;" ::: "memory");    // the four worker warps only
-                    const int nrow = min(TC_M, T_clip - t0);
-                    float* dst = q.P_band + (f0 + t0) * K;
-                    for (int i = tid; i < nrow * K; i += 128) dst[i] = sP[i];
-                    asm volatile("bar.sync 1, 128;" ::: "memory");    // sP is the next tile's A slot
+                    // 8 bins of 32 rows through the warp's staging tile, so that the stores cover whole 32-byte runs of a row
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; j++) st[lane * 9 + j] = pw[j];
+                    __syncwarp();
+                    float* dst = q.P_band + (f0 + t0 + ew * 32) * K + kb0;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int idx = e * 32 + lane, rr = idx >> 3, cc = idx & 7;
+                        if (rr < nrow && kb0 + cc < K) dst[(int64_t)rr * K + cc] = st[rr * 9 + cc];
+                    }
                 }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tc_mbar_arrive(bar_accfree + stage);                      // the MMAs of tile nt + 2 may overwrite this stage
+            if (q.band_energy && t < T_clip) {
+                for (int m = 0; m < q.n_modes; m++) q.band_energy[(int64_t)m * q.nF + f0 + t] = be[m];
+                q.band_energy[(int64_t)q.n_modes * q.nF + f0 + t] = be[APT_MAX_MODES] + q.eps;
             }
         }
     }
     if (!ok && q.error_flag) *q.error_flag = 1;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 }  // namespace apt

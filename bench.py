@@ -34,6 +34,7 @@ sys.path.insert(0, REPO)
 
 FS = 11162
 HOP = 128
+FFT_MODE = {"f64": True, "f32": False, "tc": "tc"}
 
 
 def parse():
@@ -46,7 +47,8 @@ def parse():
     ap.add_argument("--clip-seconds", type=float, default=600.0)
     ap.add_argument("--base-clips", type=int, default=16, help="distinct synthetic clips tiled to --clips")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--fft", default="f64", choices=("f64", "f32"))
+    ap.add_argument("--fft", default="f64", choices=("f64", "f32", "tc"),
+                    help="STFT arithmetic: f64 = the reference's (default, bit-exact events), f32 = float32 FFT, tc = tensor-core DFT (both tolerance paths)")
     ap.add_argument("--scaling", default="strong", choices=("strong", "weak"))
     ap.add_argument("--workload", default="full", choices=("full", "features_1h", "sweep"))
     ap.add_argument("--n-fft", type=int, default=256)
@@ -288,7 +290,7 @@ def run_features(args, torch, dist, rank, world, local_rank, dev):
     seconds = 3600.0
     params = default_params(check_duration=seconds, n_fft=n_fft, hop=hop)
     cfg = build_noise_config(FS, params)
-    eng = BatchEngine(cfg, FS, device=local_rank, fft_f64=(args.fft == "f64"))
+    eng = BatchEngine(cfg, FS, device=local_rank, fft_f64=FFT_MODE[args.fft])
     base = synth_clip_i16(60.0, 7 + rank, 3.0)
     N = int(FS * seconds)
     pcm = np.tile(base, N // base.size + 1)[:N]
@@ -310,11 +312,11 @@ def run_features(args, torch, dist, rank, world, local_rank, dev):
     res = {"metric": "audio_seconds_per_second", "value": world * n_clips * seconds / (ms_step * 1e-3), "unit": "audio-s/s",
            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32+f64" if args.fft == "f64" else "f32", "data": "synthetic",
+           "dtype": {"f64": "f32+f64", "f32": "f32", "tc": "f16x2 limbs, f32 accumulate"}[args.fft], "data": "synthetic",
            "config": {"workload": f"features stage (STFT + band energies{' + spectra' if args.write_spectra else ''}), {n_clips} x 1-hour clip per GPU, "
                                   f"n_fft={n_fft} hop={hop} (BASELINE configs[{1 if args.workload == 'features_1h' else 4}])",
                       "l2": "input %.0f MB per step; L2 flushed by the %s" % (plan.nS * 2 / 1e6, "spectra written" if args.write_spectra else "80 MB input itself (half of L2: partly resident)")},
-           "roofline": {"bound": "hbm", "kernel": "stft256_kernel" if (n_fft == 256 and hop <= 128) else "stft_generic_kernel",
+           "roofline": {"bound": "hbm", "kernel": ("tcdft256_kernel" if args.fft == "tc" and (n_fft, hop) == (256, 128) else "stft256_kernel") if (n_fft == 256 and hop <= 128) else "stft_generic_kernel",
                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                         "algorithmic_bytes": bytes_algo, "peak_source": peak_src},
            "clocks": clocks, "gpu_launches": int(eng.last_launches * args.steps)}
@@ -354,7 +356,7 @@ def main():
 
     params = default_params(check_duration=args.clip_seconds, **({"operating_band": tuple(args.operating_band)} if args.operating_band else {}))
     cfg = build_noise_config(FS, params)
-    eng = BatchEngine(cfg, FS, device=local_rank, fft_f64=(args.fft == "f64"))
+    eng = BatchEngine(cfg, FS, device=local_rank, fft_f64=FFT_MODE[args.fft])
     N = int(FS * args.clip_seconds)
     strong = args.scaling == "strong"
     if strong:
@@ -452,7 +454,8 @@ def main():
     result = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32+f64" if args.fft == "f64" else "f32",
+        "scaling": args.scaling, "vs_baseline": None,
+        "dtype": {"f64": "f32+f64", "f32": "f32", "tc": "f16 limbs (tensor cores) + f32 + f64"}[args.fft],
         "data": "synthetic",
         "config": {"workload": (f"full pipeline (STFT -> noise floor -> rain events), {total_clips} x {args.clip_seconds:g}s clips"
                                 + (f" in one batch split over {world} GPU(s) ({', '.join(str(c) for c in sorted(set(counts)))} per GPU)" if strong
@@ -479,7 +482,7 @@ def main():
         else:
             host_clips = [pcm_to_f32(base[i % n_base]) for i in range(lo, hi)]
         esz = host_clips[0].itemsize
-        proc = RainDetectorProcessor(device=local_rank, fft_f64=(args.fft == "f64"))
+        proc = RainDetectorProcessor(device=local_rank, fft_f64=FFT_MODE[args.fft])
         outs = proc.run_batch(host_clips, params)          # warm (plan, pinned ring, staging buffers)
         del outs
         if world > 1:
