@@ -30,7 +30,7 @@ for n, r in launches:
     d["ncu_us_per_pass"] += to_us(r[ix["gpu__time_duration.sum"]], units[ix["gpu__time_duration.sum"]])
 for d in k.values():
     d["dram_bytes_per_frame"] = d["dram_bytes_per_pass"] / frames
-json.dump({"workload": "profiles/run_small.py 444 20 (444 clips x 20 s, full pipeline, one pass)", "frames": frames, "passes_in_report": n_pass,
+json.dump({"workload": (sys.argv[4] if len(sys.argv) > 4 else "profiles/run_small.py (full pipeline, one pass, one time segment)"), "frames": frames, "passes_in_report": n_pass,
            "how": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum per kernel; per_frame = bytes / frames",
            "kernels": k}, open(out, "w"), indent=1)
 print(json.dumps({n: round(d["dram_bytes_per_frame"], 1) for n, d in k.items()}))

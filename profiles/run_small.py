@@ -11,7 +11,7 @@ n_clips = int(sys.argv[1]) if len(sys.argv) > 1 else 444
 seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 20.0
 fft = sys.argv[3] if len(sys.argv) > 3 else "f64"
 params = default_params(check_duration=seconds)
-eng = BatchEngine(build_noise_config(11162, params), 11162, fft_f64=(fft == "f64"))
+eng = BatchEngine(build_noise_config(11162, params), 11162, fft_f64={"f64": True, "f32": False, "tc": "tc"}[fft])
 base = [synth_clip_i16(seconds, *batch_clip_spec(i)) for i in range(8)]
 N = base[0].size
 plan = eng.plan_for([N] * n_clips)

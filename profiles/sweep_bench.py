@@ -10,15 +10,25 @@ from audio_processing_tools_b200.engine import BatchEngine
 from audio_processing_tools_b200.synth import default_params, synth_clip_i16
 
 seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 3600.0
+only = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else None      # one geometry (for an ncu capture)
+only_fft = sys.argv[4] if len(sys.argv) > 4 else None
 pcm_h = synth_clip_i16(seconds, 77, 3.0)
 pcm = torch.from_numpy(pcm_h).cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
 for n_fft, hop in ((256, 128), (256, 64), (512, 256), (512, 128), (1024, 512), (1024, 256), (2048, 1024), (2048, 512), (4096, 2048), (4096, 1024)):
-    for fft in ("f64", "f32"):
+    if only and (n_fft, hop) != only:
+        continue
+    for fft in ("f64", "f32", "tc"):
+        if only_fft and fft != only_fft:
+            continue
+        if fft == "tc" and (n_fft, hop) != (256, 128):
+            continue            # the DFT-as-GEMM variant exists for the short frame only (its work grows with n_fft^2)
         for planes in (("band_energy",), ("band_energy", "S")):
+            if fft == "tc" and "S" in planes:
+                continue
             params = default_params(check_duration=seconds, n_fft=n_fft, hop=hop)
-            eng = BatchEngine(build_noise_config(11162, params), 11162, fft_f64=(fft == "f64"))
+            eng = BatchEngine(build_noise_config(11162, params), 11162, fft_f64={"f64": True, "f32": False, "tc": "tc"}[fft])
             plan = eng.plan_for([pcm_h.size])
             bufs = eng.alloc_outputs(plan, planes, full=False)
             for _ in range(3):
