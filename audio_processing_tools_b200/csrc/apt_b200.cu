@@ -99,7 +99,10 @@ struct apt_plan {
     int mf_stride = 8;
     int st_stride = 0;      // lanes per clip in the carried-state arrays
     bool generic = false;   // generic frame-size STFT kernel
-    bool full_ok = true;    // the full pipeline is planned (n_fft = 256, hop = 128)
+    bool full_ok = true;    // the full pipeline is planned (n_fft = 256 / hop = 128, or frame size and hop multiples of 128)
+    int flux_ft = FLUX_FT;  // frames per tile of the flux kernel
+    DevBuf<unsigned short> d_lane_modes, d_lane_all;   // pass-1 lane tables beyond SEQ_KMAX lanes
+    DevBuf<float> d_blk_sum, d_blk_max;                // 128-sample block statistics of the prefiltered waveform (generic geometry)
     DevBuf<double> d_gwin64; DevBuf<cx<double>> d_gtw64; DevBuf<float> d_gwin32; DevBuf<cx<float>> d_gtw32;
     DevBuf<SelState> d_sel;
     DevBuf<uint32_t> d_hist;
@@ -276,13 +279,15 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     if (n_clips > 65535) return fail(ctx, -1, "apt_plan_create: at most 65535 clips per plan (grid.y limit), got %d", n_clips);
     *out = nullptr;
     if (p->abi_version != APT_ABI_VERSION) return fail(ctx, -20, "params abi_version %d != %d", p->abi_version, APT_ABI_VERSION);
-    // (256, 128) runs the full pipeline on the specialised kernels; any other power-of-two frame size up to 4096
-    // with 1 <= hop <= n_fft runs the features stage (STFT, power, band energies, raw features) on the generic kernel
+    // (256, 128) runs the full pipeline on the specialised kernels.  Any other power-of-two frame size up to 4096 with
+    // 1 <= hop <= n_fft runs the features stage (STFT, power, band energies, raw features) on the generic STFT kernel,
+    // and the full pipeline too when the hop is a multiple of 128 (the TD crest factor is then assembled from 128-sample
+    // block statistics; the kurtosis gate, the peak features and the gain planes stay with the 256-sample geometry)
     if (p->n_fft < 256 || p->n_fft > 4096 || (p->n_fft & (p->n_fft - 1)) != 0 || p->hop < 1 || p->hop > p->n_fft)
         return fail(ctx, -21, "unsupported STFT geometry n_fft=%d hop=%d (power of two 256..4096, 1 <= hop <= n_fft)", p->n_fft, p->hop);
     // n_fft = 256 with any hop <= 128 stays on the specialised STFT kernel (features stage unless hop = 128)
     const bool generic = !(p->n_fft == 256 && p->hop <= 128);
-    const bool full_ok = p->n_fft == 256 && p->hop == 128;
+    const bool full_ok = (p->n_fft == 256 && p->hop == 128) || (generic && p->hop % 128 == 0 && !p->has_kurt_upper);
     const int F = p->n_fft / 2 + 1;
     const int K = p->band_hi - p->band_lo + 1;
     if (p->band_lo < 0 || p->band_hi >= F || K < 1 || (!generic && K > SEQ_KMAX)) return fail(ctx, -22, "operating band bins [%d,%d] unsupported", p->band_lo, p->band_hi);
@@ -356,18 +361,23 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     pl->len.assign(clip_len, clip_len + n_clips);
     pl->samp_off.assign(n_clips + 1, 0); pl->frame_off.assign(n_clips + 1, 0);
     pl->stft_tile_off.assign(n_clips + 1, 0); pl->td_tile_off.assign(n_clips + 1, 0); pl->sel_chunk_off.assign(n_clips + 1, 0); pl->flux_tile_off.assign(n_clips + 1, 0);
+    {
+        int nl_modes = 0;
+        for (int m = 0; m < p->n_modes; m++) nl_modes += std::max(0, p->mode_band_hi[m] - p->mode_band_lo[m] + 1);
+        pl->flux_ft = flux_tile_frames(std::max(K, nl_modes));
+    }
     for (int c = 0; c < n_clips; c++) {
         const int64_t N = clip_len[c];
         if (N < p->n_fft || N <= d.padlen + 1) { apt_plan_destroy(pl); return fail(ctx, -28, "clip %d too short (%lld samples)", c, (long long)N); }
         const int64_t T = 1 + N / p->hop;
-        const int64_t Tloc = 1 + (N - p->n_fft) / p->hop;
+        const int64_t Tloc = 1 + (N - 256) / 128;   // TD tiles are cut in 256 / 128 frames (= 128-sample block pairs) at every geometry
         if (T * (int64_t)std::max(K, 128) >= (int64_t)1 << 31) { apt_plan_destroy(pl); return fail(ctx, -28, "clip %d too long (%lld frames): per-clip plane offsets are 32-bit", c, (long long)T); }
         pl->samp_off[c + 1] = pl->samp_off[c] + N;
         pl->frame_off[c + 1] = pl->frame_off[c] + T;
         pl->stft_tile_off[c + 1] = pl->stft_tile_off[c] + (generic ? (T + stftg_frames_per_cta(p->n_fft) - 1) / stftg_frames_per_cta(p->n_fft) : (T + STFT_TF - 1) / STFT_TF);
         pl->td_tile_off[c + 1] = pl->td_tile_off[c] + std::max<int64_t>(1, (Tloc + TD_FT - 1) / TD_FT);
         pl->sel_chunk_off[c + 1] = pl->sel_chunk_off[c] + (T + DB_CF - 1) / DB_CF;
-        pl->flux_tile_off[c + 1] = pl->flux_tile_off[c] + (T + FLUX_FT - 1) / FLUX_FT;
+        pl->flux_tile_off[c + 1] = pl->flux_tile_off[c] + (T + pl->flux_ft - 1) / pl->flux_ft;
     }
     pl->nS = pl->samp_off[n_clips]; pl->nF = pl->frame_off[n_clips];
     if (pl->stft_tile_off[n_clips] > 0x7fffffffLL || pl->td_tile_off[n_clips] > 0x7fffffffLL) { apt_plan_destroy(pl); return fail(ctx, -29, "batch too large for one launch"); }
@@ -391,13 +401,17 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         PL_OK(upload(pl->d_gwin64, w64)); PL_OK(upload(pl->d_gtw64, tw)); PL_OK(upload(pl->d_gwin32, w32)); PL_OK(upload(pl->d_gtw32, twf));
         std::vector<float> fr(p->freqs, p->freqs + F);
         PL_OK(upload(pl->d_freqs, fr));
-        PL_OK(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
-        for (int i = 0; i < apt_plan::N_COMP; i++) PL_OK(cudaStreamCreateWithFlags(&pl->s_comp[i], cudaStreamNonBlocking));
-        *out = pl;
-        return 0;
+        if (!full_ok) {
+            PL_OK(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
+            for (int i = 0; i < apt_plan::N_COMP; i++) PL_OK(cudaStreamCreateWithFlags(&pl->s_comp[i], cudaStreamNonBlocking));
+            *out = pl;
+            return 0;
+        }
+        PL_OK(pl->d_blk_sum.alloc((size_t)(pl->nS / 128 + n_clips + 2)));
+        PL_OK(pl->d_blk_max.alloc((size_t)(pl->nS / 128 + n_clips + 2)));
     }
     // FFT tables
-    {
+    if (!generic) {
         std::vector<double> w64(p->window, p->window + 256);
         std::vector<float> w32(256);
         for (int i = 0; i < 256; i++) w32[i] = (float)w64[i];
@@ -410,7 +424,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         std::vector<float> fr(p->freqs, p->freqs + F);
         PL_OK(upload(pl->d_freqs, fr));
     }
-    if (p->fft_f64 == 2) {
+    if (p->fft_f64 == 2 && !generic) {
         // B[n][col] = window[n] * (cos, -sin)(2 pi k n / 256) for the band bins k, times 1024, as two fp16 limbs, laid out
         // as the K-major SWIZZLE_128B shared-memory image the tensor-core kernel copies in: [limb][chunk of 64 n][row col]
         if (2 * K > TC_N) { apt_plan_destroy(pl); return fail(ctx, -22, "tensor-core DFT: at most %d band bins", TC_N / 2); }
@@ -435,7 +449,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     // TD tables
     {
         const int halo = (p->blk_post_pre + 2) * p->blk_hop + p->blk_len;
-        const int lb = TD_FT * p->hop + p->n_fft + 2 * halo + 2 * TD_WARM + p->hop;
+        const int lb = TD_FT * 128 + 256 + 2 * halo + 2 * TD_WARM + 128;
         if (halo > 128 || lb > TD_LB) { apt_plan_destroy(pl); return fail(ctx, -26, "block-energy geometry needs a %d-sample tile buffer (max %d)", lb, TD_LB); }
         std::vector<double> Apow, H;
         build_td_tables(*p, ns, sos, TD_CHUNK, Apow, H);
@@ -454,7 +468,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
             for (int m = 0; m < TD_CHUNK; m++) for (int r = 0; r < dim; r++) pl->tdt.Hc[m * dim + r] = H[(size_t)m * dim + r];
             for (int k = 0; k < 5; k++) for (int i = 0; i < dim * dim; i++) pl->tdt.Adc[k * 16 + i] = Apow[(size_t)i * 32 + (1 << k)];
         }
-        pl->tdt.env_cap = (TD_FT * p->hop + p->n_fft + 2 * halo) / std::max(1, p->blk_hop) + 8;
+        pl->tdt.env_cap = (TD_FT * 128 + 256 + 2 * halo) / std::max(1, p->blk_hop) + 8;
         if (ns == 2) {   // tables of the float32 gate kernel (chunk = 32 samples)
             std::vector<double> Ap32, H32;
             build_td_tables(*p, ns, sos, TDF_CH, Ap32, H32);
@@ -488,20 +502,28 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         Trk1Tab& tm = pl->tab_modes; Trk1Tab& ta = pl->tab_all;
         memset(&tm, 0, sizeof(tm)); memset(&ta, 0, sizeof(ta));
         int nl = 0;
+        std::vector<unsigned short> lm, la(K);
         for (int m = 0; m < p->n_modes; m++) {
             const int lo = p->mode_band_lo[m], hi = p->mode_band_hi[m];
             const int n = hi >= lo ? hi - lo + 1 : 0;
             tm.mode_l0[m] = nl; tm.mode_n[m] = n;
             ta.mode_l0[m] = n ? lo : 0; ta.mode_n[m] = n;
             for (int i = 0; i < n; i++) {
-                if (nl >= SEQ_KMAX) { apt_plan_destroy(pl); return fail(ctx, -27, "mode bands cover more than %d bins", SEQ_KMAX); }
-                tm.lane_bin[nl++] = (unsigned char)(lo + i);
+                if (nl >= SEQ_KMAX && !generic) { apt_plan_destroy(pl); return fail(ctx, -27, "mode bands cover more than %d bins", SEQ_KMAX); }
+                if (nl < SEQ_KMAX) tm.lane_bin[nl] = (unsigned char)(lo + i);
+                lm.push_back((unsigned short)(lo + i));
+                nl++;
             }
         }
         tm.n_lanes = nl; tm.nls = std::max(8, (nl + 7) / 8 * 8);
         ta.n_lanes = K;  ta.nls = (K + 7) / 8 * 8;
         PL_OK(pl->d_nl.alloc((size_t)pl->nF * tm.nls));   // the all-bins plane (debug outputs) is allocated on first use
-        for (int k = 0; k < K; k++) ta.lane_bin[k] = (unsigned char)k;
+        for (int k = 0; k < K; k++) { if (k < SEQ_KMAX) ta.lane_bin[k] = (unsigned char)k; la[k] = (unsigned short)k; }
+        // frame sizes whose tables outgrow the kernel-parameter arrays (255 as a bin index, SEQ_KMAX lanes) read them from global memory
+        if (nl > SEQ_KMAX || K > SEQ_KMAX) {
+            PL_OK(upload(pl->d_lane_modes, lm)); PL_OK(upload(pl->d_lane_all, la));
+            tm.lane_bin_g = pl->d_lane_modes.p; ta.lane_bin_g = pl->d_lane_all.p;
+        }
     }
     PL_OK(pl->d_sel.alloc(n_clips));
     PL_OK(pl->d_hist.alloc((size_t)n_clips * 2 * SEL_BINS));
@@ -790,8 +812,13 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         return fail(ctx, -30, "full pipeline requires frame_class, rain_conf, noise_conf, event_idx, event_count, clip_stats buffers");
     if (!full && !(out->band_energy || out->P || out->S || out->raw))
         return fail(ctx, -31, "features stage requires at least one of band_energy / P / S / raw");
-    if (full && (!pl->full_ok || pl->generic))
-        return fail(ctx, -34, "the full pipeline runs at n_fft=256 / hop=128 only; n_fft=%d hop=%d supports the features stage", d.n_fft, d.hop);
+    if (full && !pl->full_ok)
+        return fail(ctx, -34, "the full pipeline needs n_fft=256 / hop=128, or a hop that is a multiple of 128 (and no kurtosis gate); "
+                              "n_fft=%d hop=%d supports the features stage", d.n_fft, d.hop);
+    if (full && pl->generic && (out->G || out->S_hat || out->y || out->peak_ratio || out->peak_gate_score || out->peak_valid_count ||
+                                out->peak_count_by_mode || out->ratio_med))
+        return fail(ctx, -34, "n_fft=%d hop=%d: the gain / resynthesis planes and the peak features exist at n_fft=256 / hop=128 only",
+                    d.n_fft, d.hop);
     const bool want_peaks = out->peak_ratio || out->peak_gate_score || out->peak_valid_count || out->peak_count_by_mode;
     const bool want_gain = out->G || out->S_hat || out->y;
     if (full) {
@@ -815,7 +842,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     StftOut so;
     so.S = out->S; so.P = out->P; so.P_band = full ? pl->d_Pband.p : nullptr; so.band_energy = out->band_energy;
     so.raw = out->raw; so.freqs = pl->d_freqs.p; so.nF = pl->nF;
-    if (pl->generic) {
+    if (pl->generic && !full) {
         pl->mark(APT_KERNEL_STFT, st);
         cudaError_t eg = pl->prm.fft_f64 ? launch_stft_generic<double, PCM>(pl, b, pcm, so, st) : launch_stft_generic<float, PCM>(pl, b, pcm, so, st);
         if (eg != cudaSuccess) return fail(ctx, -11, "stft launch failed: %s", cudaGetErrorString(eg));
@@ -839,7 +866,8 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     // With per-kernel timing on (or APT_PIPELINE=0) everything runs on the caller's stream in one segment.
     int64_t maxT = 1;
     for (int c = clip0; c < clip0 + n_clips; c++) maxT = std::max(maxT, pl->frame_off[c + 1] - pl->frame_off[c]);
-    const bool piped = want_seg > 1 && pl->pipeline && !pl->timing;
+    // (the generic frame sizes run in one segment on the caller's stream: their TD tiles are not aligned with frame ranges)
+    const bool piped = want_seg > 1 && pl->pipeline && !pl->timing && !pl->generic;
     int seg_frames, n_seg;
     if (piped) {
         int want = want_seg;
@@ -887,7 +915,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     // Default flags consume one bit of the TD features per frame (crest > td_gate_threshold): the float32 filter
     // decides it wherever the crest factor is outside a guard band around the threshold, and the float64 filter
     // re-decides the tiles holding a frame inside the band -- the gate plane equals the float64 one bit for bit.
-    const bool fast_td = pl->td_fast && !out->td && !out->x_td && !d.has_ku && d.gate_thr != 0.0f;
+    const bool fast_td = pl->td_fast && !out->td && !out->x_td && !d.has_ku && d.gate_thr != 0.0f && !pl->generic;
 
     // start of the run on the caller's stream: selection state and histograms, then the fork
     if (!d.suppressor_bypass) {
@@ -927,6 +955,11 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         {
             const dim3 g = persistent_grid(pl, seg_grid(pl->stft_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / STFT_TF), 3);
             tmark(apt_plan::SK_STFT, sg, 0);
+            if (pl->generic) {
+                bs.tile0 = 0;
+                RR(pl->prm.fft_f64 ? launch_stft_generic<double, PCM>(pl, bs, pcm, so, S[apt_plan::SK_STFT])
+                                   : launch_stft_generic<float, PCM>(pl, bs, pcm, so, S[apt_plan::SK_STFT]));
+            } else
             RR(launch_stft_mode<PCM>(pl, bs, g, pcm, so, S[apt_plan::SK_STFT]));
             RR(rec(apt_plan::SK_STFT, sg));
         }
@@ -968,6 +1001,18 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
                     RR(launch_td<PCM, float>(pl, bs, g, pcm, tf, S[apt_plan::SK_TD]));
                 }
                 if (g.x > 0 && tf.list_cap > 0) RR(launch_td_recheck<PCM>(pl, bs, pcm, tf, S[apt_plan::SK_TD]));
+            } else if (pl->generic) {
+                // block statistics of the prefiltered waveform, then the crest factor of every (n_fft, hop) frame from them
+                TdOut tg = to;
+                tg.td = nullptr; tg.want_block = 0; tg.want_kurt = 0;
+                tg.blk_sum = pl->d_blk_sum.p; tg.blk_max = pl->d_blk_max.p;
+                RR(launch_td<PCM, double>(pl, bs, g, pcm, tg, S[apt_plan::SK_TD]));
+                if (e == cudaSuccess) {
+                    CrestIO cio{pl->d_blk_sum.p, pl->d_blk_max.p, to.td, pl->nF, out->td != nullptr};
+                    crest_blocks_kernel<<<dim3((unsigned)((maxT + 255) / 256), (unsigned)n_clips), 256, 0, S[apt_plan::SK_TD]>>>(pl->dp, bs, cio);
+                    pl->last_launches++;
+                    RR(cudaGetLastError());
+                }
             } else {
                 RR(launch_td<PCM, double>(pl, bs, g, pcm, to, S[apt_plan::SK_TD]));
             }
@@ -1003,9 +1048,10 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             FluxIO io;
             io.P_band = pl->d_Pband.p; io.NL = nl_plane; io.nls = tab.nls; io.mf = pl->d_mf.p; io.stride = pl->mf_stride;
             io.det_noise_lag = out->det_noise_lag; io.D = D_plane; io.mode_flux = out->mode_flux; io.nF = pl->nF;
-            bs.tile0 = bs.ta / FLUX_FT;
-            const dim3 g = seg_grid(pl->flux_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / FLUX_FT);
-            const size_t fsm = flux_smem_bytes(d.K, tab.n_lanes, tab.nls);
+            io.ft = pl->flux_ft;
+            bs.tile0 = bs.ta / pl->flux_ft;
+            const dim3 g = seg_grid(pl->flux_tile_off, clip0, n_clips, bs.tile0, n_seg == 1 ? INT64_MAX : seg_frames / pl->flux_ft);
+            const size_t fsm = flux_smem_bytes(pl->flux_ft, tab.n_lanes);
             RR(wait(apt_plan::SK_FLUX, d.use_norm ? apt_plan::SK_TRK1 : apt_plan::SK_STFT, sg));
             tmark(apt_plan::SK_FLUX, sg, 0);
             if (g.x > 0 && e == cudaSuccess) {

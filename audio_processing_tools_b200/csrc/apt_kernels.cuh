@@ -508,6 +508,7 @@ __global__ void __launch_bounds__(STFTG_NT) stft_generic_kernel(const __grid_con
         const float pw = a * a;
         s_P[f * PS + k] = pw;
         if (o.P) o.P[fr * F + k] = pw;
+        if (o.P_band && k >= p.band_lo && k < p.band_lo + p.K) o.P_band[fr * p.K + (k - p.band_lo)] = pw;
     }
     __syncthreads();
     if (o.band_energy) {
@@ -646,11 +647,20 @@ struct TdOut {
     int2* list;      // [list_cap] flagged (clip, tile) pairs of this launch
     int* list_count;
     int list_cap;
+    // Block mode (frame sizes other than 256 / 128).  blk_sum != NULL: the kernel writes the float32 sum of squares
+    // (numpy's 8-accumulator order) and the peak of every 128-sample block of the prefiltered waveform instead of
+    // frame features; see td_block_base for the layout.
+    float* blk_sum;
+    float* blk_max;
 #ifdef APT_PROFILE_PHASES
     long long* dbg;  // [16] clock64 stamps of one interior tile (profiling builds only)
 #endif
 };
 
+
+// first entry of clip c (whose samples start at `base`) in the block-statistics arrays: floor(base / 128) + c leaves every
+// clip its floor(N / 128) entries (floor(a + b) >= floor(a) + floor(b)); the arrays hold nS / 128 + n_clips + 1 entries
+__host__ __device__ __forceinline__ int64_t td_block_base(int64_t base, int c) { return (base >> 7) + c; }
 
 inline size_t td_smem_bytes(int ns, int env_cap, size_t real_bytes = sizeof(double)) {
     return sizeof(float) * TD_XF + real_bytes * ((size_t)2 * ns * (TD_NT / 32) + 32 * 4 * ns * ns + (size_t)TD_CHUNK * 2 * ns) + 8 +
@@ -1025,6 +1035,14 @@ __device__ __forceinline__ void td_tile(const DevParams& p, const Batch& b, cons
         if (lane == 0) { s_bsum[blk] = bsum; s_bmax[blk] = pk; }
     }
     __syncthreads();
+    if (o.blk_sum) {
+        // block mode (frame sizes other than 256 / 128): the tile hands out the statistics of the 128-sample blocks it
+        // owns -- [t0, t0 + TD_FT), the clip's last tile through its last block -- and crest_blocks_kernel combines them
+        const int nown = nfr > 0 ? (last ? nfr + 1 : min(nfr + 1, TD_FT)) : 0;
+        const int64_t bo = td_block_base(base, c) + t0;
+        for (int i = tid; i < nown; i += TD_NT) { o.blk_sum[bo + i] = s_bsum[i]; o.blk_max[bo + i] = s_bmax[i]; }
+        return;
+    }
     if (tid < nfr) {
         const int t = t0 + tid;
         float sumsq = 0.0f + (s_bsum[tid] + s_bsum[tid + 1]);
@@ -1222,6 +1240,51 @@ __global__ void __launch_bounds__(TD_NT, 2) td_recheck_kernel(const __grid_const
 //   edges   = tiles whose buffer would cross a clip end (scipy's odd extension, zi initial state, the zero-filled tail
 //             frames) are not computed here at all: they are put on the re-check list
 // int16 input runs unscaled through the (linear) filter; the 1/32767 scale is applied to the frame statistics.
+
+// Crest factor of the frames of ANY frame size L = 128 * 2^k at a hop that is a multiple of 128, from the block statistics
+// the TD kernel wrote in block mode (feature_extraction.py:514-523).  numpy sums the L float32 squares pairwise:
+// vectors longer than 128 are halved down to 128-element leaves, each summed with 8 strided accumulators -- the leaves
+// are exactly the 128-sample blocks, and the tree over them is the balanced binary tree in index order.
+struct CrestIO {
+    const float* blk_sum; const float* blk_max;
+    float* td;        // [5][nF]: row 0 crest factor; kurtosis and the block-energy rows are not produced at these geometries
+    int64_t nF;
+    int mark_missing; // the plane goes to the caller: rows 1..4 are filled with NaN (not computed), not with zeros
+};
+__global__ void __launch_bounds__(256) crest_blocks_kernel(const __grid_constant__ DevParams p, Batch b, CrestIO io) {
+    const int c = b.clip0 + (int)blockIdx.y;
+    const int64_t base = __ldg(b.samp_off + c);
+    const int64_t N = __ldg(b.samp_off + c + 1) - base;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (t >= T) return;
+    const int L = p.n_fft, nbk = L >> 7, hb = p.hop >> 7;
+    const int Tloc = N < L ? 0 : (int)(1 + (N - L) / p.hop);
+    float cf = 0.0f;   // frames beyond the TD grid are zero (rain_frame_classifier.py:178-194)
+    if (t < Tloc) {
+        const int64_t bo = td_block_base(base, c) + (int64_t)t * hb;
+        float v[32];
+        float pk = 0.0f;
+        for (int i = 0; i < nbk; i++) { v[i] = __ldg(io.blk_sum + bo + i); pk = fmaxf(pk, __ldg(io.blk_max + bo + i)); }
+        for (int w = 1; w < nbk; w <<= 1)
+            for (int i = 0; i < nbk; i += 2 * w) v[i] = v[i] + v[i + w];
+        const float sumsq = 0.0f + v[0];
+        const float mean_sq = f_div(sumsq, (float)L);
+        const float rms = f_sqrt(mean_sq + d2f(p.eps64));
+        const double r = (double)rms;
+        cf = d2f((double)pk / (r > p.eps64 ? r : p.eps64));
+        if (isnan(cf) || isinf(cf)) cf = 0.0f;
+    }
+    io.td[f0 + t] = cf;
+    if (io.mark_missing) {
+        const float nanv = u2f(0x7fc00000u);
+        for (int r = 1; r < APT_N_TD_FEATURES; r++) io.td[(int64_t)r * io.nF + f0 + t] = nanv;
+    } else {
+        io.td[io.nF + f0 + t] = 0.0f;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 constexpr int TDF_NT = 256;
 constexpr int TDF_CH = 32;                 // samples per thread
@@ -1470,6 +1533,8 @@ struct Trk1Tab {
     int mode_l0[APT_MAX_MODES];     // first lane of mode m (its bins are consecutive lanes)
     int mode_n[APT_MAX_MODES];      // bins of mode m
     unsigned char lane_bin[SEQ_KMAX];  // band-relative bin of lane j
+    const unsigned short* lane_bin_g;  // the same table in global memory when there are more than SEQ_KMAX lanes, else NULL
+    __device__ __forceinline__ int bin_of(int j) const { return lane_bin_g ? (int)__ldg(lane_bin_g + j) : (int)lane_bin[j]; }
 };
 
 // Serial-lane bookkeeping shared by the three serial kernels: global lane -> (clip, sub-lane).  Lanes past
@@ -1520,7 +1585,7 @@ __global__ void __launch_bounds__(128) trk1_kernel(const __grid_constant__ DevPa
                                                    const __grid_constant__ Trk1Tab tab, Trk1IO io) {
     const SerialLane L = serial_lane(b, tab.n_lanes);
     const int K = p.K, nls = tab.nls;
-    const int kb = tab.lane_bin[L.sub];
+    const int kb = tab.bin_of(L.sub);
     const float* Pk = io.P_band + L.f0 * K + kb;
     float* NLk = io.NL + L.f0 * nls + L.sub;
     float* N1k = io.det_noise_psd ? io.det_noise_psd + L.f0 * K + kb : nullptr;
@@ -1575,12 +1640,18 @@ struct FluxIO {
     float* det_noise_lag; float* D;   // optional [nF][K]
     float* mode_flux;      // optional [M][nF]
     int64_t nF;
+    int ft;                // frames per tile (FLUX_FT, or a smaller power of two when the lanes of a tile would not fit)
 };
 constexpr int FLUX_FT = 256;  // frames per tile (the per-CTA set-up is a large share of a 64-frame tile's instructions)
 
-inline size_t flux_smem_bytes(int K, int n_lanes, int nls) {
-    (void)K; (void)nls;
-    return sizeof(float) * (size_t)(FLUX_FT + 2) * (n_lanes + 1);
+inline size_t flux_smem_bytes(int ft, int n_lanes) {
+    return sizeof(float) * (size_t)(ft + 2) * (n_lanes + 1);
+}
+// frames per tile for a plan whose widest lane table has n_lanes entries: the D tile stays below ~190 KB
+inline int flux_tile_frames(int n_lanes) {
+    int ft = FLUX_FT;
+    while (ft > 8 && flux_smem_bytes(ft, n_lanes) > 190 * 1024) ft >>= 1;
+    return ft;
 }
 
 __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevParams p, Batch b,
@@ -1595,7 +1666,7 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevPa
     if (!tile_clip(b, tile_off, c, tile_in_clip)) return;
     const int64_t f0 = __ldg(b.frame_off + c);
     const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
-    const int t0 = (int)tile_in_clip * FLUX_FT, nt = min(FLUX_FT, T - t0);
+    const int t0 = (int)tile_in_clip * io.ft, nt = min(io.ft, T - t0);
     const int K = p.K, M = p.M, nl_ = tab.n_lanes, nls = io.nls, ds = nl_ + 1;
     if (tid < 64) s_ltab[tid] = u2f(kSvmlLog10TabDev[tid]);
     __syncthreads();
@@ -1604,8 +1675,30 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevPa
     const int r0 = t0 >= 2 ? 0 : 2 - t0;           // first row that exists (frames before the clip start do not)
     const int LP = (nl_ + 31) & ~31;               // lanes padded to whole warps
     const int j = tid % LP, rg = tid / LP, RP = 256 / LP;
-    if (j < nl_ && rg < RP) {
-        const int kb = tab.lane_bin[j];
+    if (LP > 256) {
+        // more lanes than threads (large frame sizes): flattened (row, lane) walk
+        const int rows = nt + 2 - r0;
+        for (int idx = tid; idx < rows * nl_; idx += 256) {
+            const int r = r0 + idx / nl_, jj = idx - (r - r0) * nl_;
+            const int kb = tab.bin_of(jj);
+            const int64_t fr = f0 + t0 - 2 + r;
+            const float pk = __ldg(io.P_band + fr * K + kb);
+            const float nl = p.use_norm ? __ldg(io.NL + fr * nls + jj) : 0.0f;
+            float dval;
+            if (p.use_norm) {
+                if (p.ratio_db) dval = 10.0f * svml_log10f(f_div(pk, nl + p.eps32) + p.eps32, s_ltab);
+                else dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab) - 10.0f * svml_log10f(nl + p.eps32, s_ltab);
+            } else {
+                dval = 10.0f * svml_log10f(pk + p.eps32, s_ltab);
+            }
+            s_D[r * ds + jj] = dval;
+            if (r >= 2) {
+                if (io.D) io.D[fr * K + kb] = dval;
+                if (io.det_noise_lag) io.det_noise_lag[fr * K + kb] = nl;
+            }
+        }
+    } else if (j < nl_ && rg < RP) {
+        const int kb = tab.bin_of(j);
         const float* Pp = io.P_band + (f0 + t0 - 2) * K + kb;
         const float* Np = io.NL + (f0 + t0 - 2) * nls + j;
         constexpr int U = 3;

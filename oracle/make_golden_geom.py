@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Golden vectors of the FULL detector at frame sizes other than 256 / 128 (BASELINE config 5 with the whole pipeline).
+
+Runs the UNMODIFIED reference (RainDetectorProcessor.run with n_fft / hop overrides, keep_state_debug) in the build
+container and freezes labels, confidences, clip statistics and the per-frame detector features.  The PCM is regenerated
+from the seed by the tests (sha1 recorded).  Test infrastructure; see make_golden.py for the harness.
+
+    python oracle/make_golden_geom.py
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, REPO)
+
+import make_golden as mg  # noqa: E402  (installs the reference harness)
+from audio_processing_tools_b200.synth import synth_clip_i16  # noqa: E402
+
+# (n_fft, hop, seconds, seed, rain rate): every hop is a multiple of 128 (the CUDA path's condition for the full pipeline)
+CASES = ((512, 256, 30, 51, 3.0), (1024, 256, 30, 52, 10.0), (2048, 1024, 40, 53, 3.0), (4096, 1024, 40, 54, 3.0),
+         (256, 256, 20, 55, 3.0), (512, 128, 20, 56, 0.5))
+
+
+def main():
+    for n_fft, hop, seconds, seed, lam in CASES:
+        pcm = synth_clip_i16(seconds, seed, lam)
+        metrics, state, params = mg.run_reference(pcm, seconds, {"n_fft": n_fft, "hop": hop})
+        d = mg.pack(pcm, seconds, seed, lam, metrics, state, level=1, params=params)
+        path = os.path.join(mg.OUT, f"geom_nfft{n_fft}_hop{hop}.npz")
+        np.savez_compressed(path, **d)
+        fc = d["frame_class"]
+        print(path, fc.size, "frames,", int((fc == 2).sum()), "rain,", os.path.getsize(path) // 1024, "KiB", flush=True)
+
+
+if __name__ == "__main__":
+    main()

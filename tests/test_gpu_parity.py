@@ -271,8 +271,43 @@ def test_frame_size_sweep_features(torch_cuda, n_fft, hop, fft_f64):
             np.testing.assert_allclose(out["raw"][i], g["det_" + k], rtol=1e-4, atol=1e-6, err_msg=k)
     band = g["band_mask"]
     np.testing.assert_allclose(out["band_energy"][-1], out["P"][:, band].astype(np.float64).sum(axis=1) + 1e-9, rtol=1e-6)
-    with pytest.raises(AptError):      # the full pipeline is planned for 256/128 only
-        eng.run_clips([g["pcm"]], ())
+    if hop % 128:
+        with pytest.raises(AptError):      # the full pipeline needs a hop that is a multiple of 128
+            eng.run_clips([g["pcm"]], ())
+    eng.close()
+
+
+@pytest.mark.parametrize("n_fft,hop", [(512, 256), (1024, 256), (2048, 1024), (4096, 1024), (256, 256), (512, 128)])
+def test_full_pipeline_other_frame_sizes(torch_cuda, n_fft, hop):
+    """The whole detector at frame sizes other than 256 / 128 against the unmodified reference (geom_* fixtures): the
+    TD crest factor and gate bit for bit; labels, confidences and events identical; per-mode flux, score and the
+    noise-floor statistics within the float32 spectrum tolerance (the generic FFT is another algorithm than pocketfft,
+    so single power values differ in the last bit).  Batched with a second, ragged clip to cover the offsets."""
+    from conftest import load_golden
+    from audio_processing_tools_b200.synth import synth_clip_i16
+    g, meta, pcm, params = load_golden(f"geom_nfft{n_fft}_hop{hop}")
+    other = synth_clip_i16(7.3, 900 + n_fft // 256, 10.0)
+    eng = make_engine(params)
+    plan, out = eng.run_clips([other, pcm], ("td", "gate", "score", "norm_flux"))
+    f0, f1 = int(plan.frame_off[1]), int(plan.frame_off[2])
+    T = g["frame_class"].size
+    assert f1 - f0 == T
+    assert np.array_equal(out["td"][0][f0:f1], g["det_td_crest_factor"])
+    assert np.all(np.isnan(out["td"][1:]))
+    assert np.array_equal(out["gate"][f0:f1].astype(bool), g["det_td_gate_mask"])
+    np.testing.assert_allclose(out["score"][f0:f1], g["det_mode_flux_score"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["norm_flux"][0][f0:f1], g["det_primary_mode_flux"], rtol=1e-4, atol=1e-5)
+    assert np.array_equal(out["frame_class"][f0:f1], g["frame_class"])
+    assert np.array_equal(out["rain_conf"][f0:f1], g["rain_conf"])
+    assert np.array_equal(out["noise_conf"][f0:f1], g["noise_conf"])
+    n_ev = int(out["event_count"][1])
+    assert np.array_equal(out["event_idx"][f0:f0 + n_ev], g["event_idx"])
+    st = out["clip_stats"][1]
+    assert st[6] == pytest.approx(g["metric_mean_noise_floor_db"].item(), rel=1e-5)
+    assert st[7] == pytest.approx(g["metric_median_noise_floor_db"].item(), rel=1e-5)
+    # the host path (pageable clips in, labels out) gives the same labels
+    _, res = eng.run_host_clips([other, pcm])
+    assert np.array_equal(res["frame_class"][f0:f1], g["frame_class"])
     eng.close()
 
 

@@ -129,3 +129,24 @@ def test_oracle_frame_size_sweep(oracle_mod, n_fft, hop):
     assert (s["S"] != g["S"]).mean() < 2e-3
     for i, k in enumerate(oracle_mod.RAW_NAMES):
         np.testing.assert_allclose(s["raw"][i], g["det_" + k], rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+GEOM = ((512, 256), (1024, 256), (2048, 1024), (4096, 1024), (256, 256), (512, 128))
+
+
+@pytest.mark.parametrize("n_fft,hop", GEOM)
+def test_oracle_full_pipeline_other_frame_sizes(oracle_mod, n_fft, hop):
+    """The whole detector at frame sizes other than 256 / 128 (oracle/make_golden_geom.py froze the unmodified
+    reference): labels, confidences, clip statistics, gate and per-mode flux, bit for bit."""
+    g, meta, pcm, params = load_golden(f"geom_nfft{n_fft}_hop{hop}")
+    params["keep_state_debug"] = True
+    m, s = oracle_mod.run(pcm_to_f32(pcm), params)
+    assert np.array_equal(s["frame_class"], g["frame_class"])
+    assert np.array_equal(s["rain_conf"], g["rain_conf"])
+    assert np.array_equal(s["noise_conf"], g["noise_conf"])
+    assert np.array_equal(s["td"][0], g["det_td_crest_factor"])
+    assert np.array_equal(s["gate"].astype(bool), g["det_td_gate_mask"])
+    assert np.array_equal(s["score"], g["det_mode_flux_score"])
+    assert m["rain_frame_count"] == g["metric_rain_frame_count"].item()
+    assert m["mean_noise_floor_db"] == pytest.approx(g["metric_mean_noise_floor_db"].item(), rel=1e-6)
+    assert m["median_noise_floor_db"] == pytest.approx(g["metric_median_noise_floor_db"].item(), rel=1e-6)
