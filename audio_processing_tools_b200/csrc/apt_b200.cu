@@ -395,9 +395,9 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         std::vector<double> w64(p->window, p->window + N);
         std::vector<float> w32(N);
         for (int i = 0; i < N; i++) w32[i] = (float)w64[i];
-        std::vector<cx<double>> tw(N / 2 + 1);
-        std::vector<cx<float>> twf(N / 2 + 1);
-        for (int k = 0; k <= N / 2; k++) { tw[k] = {cos(2.0 * M_PI * k / N), -sin(2.0 * M_PI * k / N)}; twf[k] = {(float)tw[k].x, (float)tw[k].y}; }
+        std::vector<cx<double>> tw(N);
+        std::vector<cx<float>> twf(N);
+        for (int k = 0; k < N; k++) { tw[k] = {cos(2.0 * M_PI * k / N), -sin(2.0 * M_PI * k / N)}; twf[k] = {(float)tw[k].x, (float)tw[k].y}; }
         PL_OK(upload(pl->d_gwin64, w64)); PL_OK(upload(pl->d_gtw64, tw)); PL_OK(upload(pl->d_gwin32, w32)); PL_OK(upload(pl->d_gtw32, twf));
         std::vector<float> fr(p->freqs, p->freqs + F);
         PL_OK(upload(pl->d_freqs, fr));

@@ -428,26 +428,74 @@ __global__ void __launch_bounds__(STFT_NT, 3) stft256_kernel(const __grid_consta
 // unpacked to the n_fft/2+1 rfft bins.  Arithmetic type T as in stft256_kernel (float64 = reference).
 // ---------------------------------------------------------------------------------------------
 constexpr int STFTG_NT = 256;
+constexpr int STFTG_PTS = 2048;      // complex points a CTA transforms at once: STFTG_PTS / (n_fft / 2) frames
 template <typename T>
 struct FftTablesG {
     const T* win;        // [n_fft]
-    const cx<T>* tw;     // [n_fft/2 + 1]  W_N^k
+    const cx<T>* tw;     // [n_fft]  W_N^k for every k (the Stockham passes index it up to (R-1)/R of the circle)
 };
-inline int stftg_frames_per_cta(int n_fft) { return n_fft >= 2048 ? 1 : 2048 / n_fft; }   // 512 -> 4, 1024 -> 2
+inline int stftg_frames_per_cta(int n_fft) { return 2 * STFTG_PTS / n_fft; }   // 256 -> 16, 512 -> 8, ..., 4096 -> 1
+__host__ __device__ __forceinline__ int stftg_pos(int p) { return p + (p >> 3); }   // one pad element per 8: the stride-8 stores of a pass spread over the banks
 template <typename T>
 inline size_t stftg_smem_bytes(int n_fft) {
-    return (size_t)stftg_frames_per_cta(n_fft) * (sizeof(cx<T>) * (size_t)n_fft + sizeof(float) * (size_t)(n_fft / 2 + 4));
+    return sizeof(cx<T>) * (size_t)(STFTG_PTS + STFTG_PTS / 8) + sizeof(float) * (size_t)(STFTG_PTS + 4 * stftg_frames_per_cta(n_fft) + 64);
 }
 
+__device__ __forceinline__ cx<double> ldg_cx(const cx<double>* p) { const double2 v = __ldg(reinterpret_cast<const double2*>(p)); return {v.x, v.y}; }
+__device__ __forceinline__ cx<float> ldg_cx(const cx<float>* p) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); return {v.x, v.y}; }
+// 128-bit (double) / 64-bit (float) shared-memory accesses of one complex element (cx<T> itself carries no alignment)
+__device__ __forceinline__ cx<double> ld_cx(const cx<double>* p) { const double2 v = *reinterpret_cast<const double2*>(p); return {v.x, v.y}; }
+__device__ __forceinline__ cx<float> ld_cx(const cx<float>* p) { const float2 v = *reinterpret_cast<const float2*>(p); return {v.x, v.y}; }
+__device__ __forceinline__ void st_cx(cx<double>* p, cx<double> v) { *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y); }
+__device__ __forceinline__ void st_cx(cx<float>* p, cx<float> v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
+
+// one radix-R Stockham butterfly of stride q on the registers a[r] = x[i + r * H / R]; results to x[j + r * q]
+template <typename T, int R>
+__device__ __forceinline__ void stftg_butterfly(cx<T>* a, int i, int q, int twstep, const cx<T>* __restrict__ tw, cx<T>* __restrict__ x) {
+    const int k = i & (q - 1);
+    const int j = (i - k) * R + k;
+    if (q > 1) {
+        const cx<T>* twk = tw + k * twstep;
+#pragma unroll
+        for (int r = 1; r < R; r++) a[r] = cmul(a[r], ldg_cx(twk + (r - 1) * k * twstep));   // W_{Rq}^{r k}
+    }
+    if constexpr (R == 8) fft8(a);
+    else if constexpr (R == 4) fft4(a[0], a[1], a[2], a[3]);
+    else { const cx<T> u = a[0]; a[0] = cadd(u, a[1]); a[1] = csub(u, a[1]); }
+#pragma unroll
+    for (int r = 0; r < R; r++) st_cx(x + stftg_pos(j + r * q), a[r]);
+}
+// one in-place pass: every thread first takes the eight points of its 8 / R butterflies into registers, the CTA meets at a
+// barrier, then the results overwrite the frame
+template <typename T, int R>
+__device__ __forceinline__ void stftg_pass(cx<T>* __restrict__ x, int tif, int H, int q, int N, const cx<T>* __restrict__ tw) {
+    constexpr int NB = 8 / R;
+    const int m = H / R, tpf = H >> 3, twstep = N / (R * q);
+    cx<T> a[NB][R];
+#pragma unroll
+    for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+        for (int r = 0; r < R; r++) a[nb][r] = ld_cx(x + stftg_pos(tif + nb * tpf + r * m));
+    __syncthreads();
+#pragma unroll
+    for (int nb = 0; nb < NB; nb++) stftg_butterfly<T, R>(a[nb], tif + nb * tpf, q, twstep, tw, x);
+    __syncthreads();
+}
+
+// STFT of any power-of-two frame size 256..4096 at any hop: the real FFT of a frame is a complex FFT of H = n_fft / 2
+// points (even samples real, odd samples imaginary) plus the unpack.  H / 8 threads own a frame, a CTA 2048 / H frames.
+// Mixed-radix Stockham autosort passes (8, 8, ... then 4s), each butterfly in registers: the first pass reads its eight
+// inputs (i + r * H / 8: consecutive threads -> consecutive sample pairs) straight from global memory, windowed; the
+// later passes work in place on one padded shared-memory buffer.  Threads of frames beyond the clip end run the same
+// code on their (unused) frame area and skip the global accesses, so every barrier is met without divergence.
 template <typename T, typename PCM>
-__global__ void __launch_bounds__(STFTG_NT) stft_generic_kernel(const __grid_constant__ DevParams p, Batch b,
+__global__ void __launch_bounds__(STFTG_NT, 3) stft_generic_kernel(const __grid_constant__ DevParams p, Batch b,
                                                                 const PCM* __restrict__ pcm, FftTablesG<T> tab, StftOut o, int fpc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.n_fft, H = N >> 1, F = H + 1, PS = H + 4;
-    const int lgH2 = 31 - __clz(H >> 1);                       // log2(H/2)
-    cx<T>* bufA = reinterpret_cast<cx<T>*>(smem_raw);          // [fpc][H]
-    cx<T>* bufB = bufA + (size_t)fpc * H;                      // [fpc][H]
-    float* s_P = reinterpret_cast<float*>(bufB + (size_t)fpc * H);   // [fpc][PS]
+    constexpr int BUF = STFTG_PTS + STFTG_PTS / 8;
+    cx<T>* buf = reinterpret_cast<cx<T>*>(smem_raw);
+    float* s_P = reinterpret_cast<float*>(buf + BUF);   // [fpc][PS]
     const int tid = threadIdx.x;
     const int c = b.clip0 + (int)blockIdx.y;
     const int64_t base = __ldg(b.samp_off + c);
@@ -457,68 +505,109 @@ __global__ void __launch_bounds__(STFTG_NT) stft_generic_kernel(const __grid_con
     const int t0 = (b.tile0 + (int)blockIdx.x) * fpc;
     if (t0 >= T_clip) return;
     const int nfr = min(fpc, T_clip - t0);
-    // windowed frames, centre-padded with zeros (librosa center=True, pad_mode="constant")
-    for (int i = tid; i < nfr * H; i += STFTG_NT) {
-        const int f = i / H, n = i - f * H;
-        const int64_t sa = (int64_t)(t0 + f) * p.hop - H + 2 * n, sb = sa + 1;
-        const T xa = (sa >= 0 && sa < Ns) ? (T)load_sample(pcm, base + sa) : (T)0;
-        const T xb = (sb >= 0 && sb < Ns) ? (T)load_sample(pcm, base + sb) : (T)0;
-        bufA[i] = {tab.win[2 * n] * xa, tab.win[2 * n + 1] * xb};
+    const int lgt = 31 - __clz(H >> 3);           // threads per frame = H / 8 = 1 << lgt
+    const int tpf = 1 << lgt;
+    const int f = tid >> lgt, tif = tid & (tpf - 1);
+    const bool live = f < nfr;
+    cx<T>* x = buf + f * (H + (H >> 3));          // the frame's area: H points + their pads
+    // ---- pass 1 (radix 8, q = 1: no twiddles), inputs from global memory; centre padding with zeros (librosa center=True)
+    {
+        cx<T> a[8];
+        const int64_t start = (int64_t)(t0 + f) * p.hop - H;       // clip-relative index of the frame's first sample
+        const bool inside = start >= 0 && start + N <= Ns;
+        const PCM* src = pcm + base + start;
+        const cx<T>* win2 = reinterpret_cast<const cx<T>*>(tab.win);
+        bool pair_ok = false;
+        if constexpr (sizeof(PCM) == 2) pair_ok = live && inside && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
+        float xe[8], xo[8];
+        if (pair_ok) {          // the common case: whole frame inside the clip, sample pairs 32-bit aligned
+            if constexpr (sizeof(PCM) == 2) {
+                const uint32_t* src2 = reinterpret_cast<const uint32_t*>(src) + tif;
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const uint32_t w = __ldg(src2 + r * tpf);
+                    xe[r] = pcm_to_f32((int16_t)(w & 0xffffu)); xo[r] = pcm_to_f32((int16_t)(w >> 16));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int n = tif + r * tpf;
+                const int64_t sa = start + 2 * n;
+                xe[r] = (live && sa >= 0 && sa < Ns) ? load_sample(src, 2 * n) : 0.0f;
+                xo[r] = (live && sa + 1 >= 0 && sa + 1 < Ns) ? load_sample(src, 2 * n + 1) : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const cx<T> w = ldg_cx(win2 + tif + r * tpf);
+            a[r] = {w.x * (T)xe[r], w.y * (T)xo[r]};
+        }
+        stftg_butterfly<T, 8>(a, tif, 1, 0, tab.tw, x);
     }
     __syncthreads();
-    cx<T>* x = bufA;
-    cx<T>* y = bufB;
-    for (int q = 1; q < H; q <<= 1) {   // radix-2 Stockham passes, q = 1, 2, ..., H/2
-        const int tstep = H / q;        // W_{2q}^k = W_N^{k * H / q}
-        for (int ii = tid; ii < nfr * (H >> 1); ii += STFTG_NT) {
-            const int f = ii >> lgH2, i = ii & ((H >> 1) - 1);
-            const cx<T>* xf = x + (size_t)f * H;
-            cx<T>* yf = y + (size_t)f * H;
-            const int k = i & (q - 1);
-            const int j = ((i - k) << 1) + k;
-            const cx<T> u0 = xf[i];
-            const cx<T> xv = xf[i + (H >> 1)];
-            const cx<T> u1 = (k == 0) ? xv : cmul(xv, tab.tw[k * tstep]);
-            yf[j] = cadd(u0, u1);
-            yf[j + q] = csub(u0, u1);
-        }
-        __syncthreads();
-        cx<T>* tmp = x; x = y; y = tmp;
+    // ---- remaining passes; schedule 8,4,4 | 8,8,4 | 8,8,8 | 8,8,4,4 | 8,8,8,4 for H = 128 .. 2048
+    for (int q = 8; q < H;) {
+        const int rem = H / q;                       // product of the radices still to do
+        if (rem % 8 == 0 && rem != 16) { stftg_pass<T, 8>(x, tif, H, q, N, tab.tw); q *= 8; }
+        else if (rem % 4 == 0) { stftg_pass<T, 4>(x, tif, H, q, N, tab.tw); q *= 4; }
+        else { stftg_pass<T, 2>(x, tif, H, q, N, tab.tw); q *= 2; }
     }
-    // real-FFT unpack: X[k] = E + W_N^k O with E = (Z[k] + conj(Z[H-k]))/2, O = (Z[k] - conj(Z[H-k]))/(2i)
+    // ---- real-FFT unpack: X[k] = E + W_N^k O with E = (Z[k] + conj(Z[H-k]))/2, O = (Z[k] - conj(Z[H-k]))/(2i).
+    // Thread tif takes k = tif + r * H/8, r = 0..7 (k = 0 comes out of the same formula with Z[H] = Z[0]); k = H apart.
     const T half = (T)0.5;
-    for (int i = tid; i < nfr * F; i += STFTG_NT) {
-        const int f = i / F, k = i - f * F;
-        const cx<T>* xf = x + (size_t)f * H;
-        T re, im;
-        if (k == 0) { re = xf[0].x + xf[0].y; im = (T)0; }
-        else if (k == H) { re = xf[0].x - xf[0].y; im = (T)0; }
-        else {
-            const cx<T> zk = xf[k], cn = cconj(xf[H - k]);
+    if (live) {
+        const int64_t fr = f0 + t0 + f;
+        float* Pt = s_P + f * PS;
+        float2* Sg = o.S ? reinterpret_cast<float2*>(o.S) + fr * F : nullptr;
+        float* Pg = o.P ? o.P + fr * F : nullptr;
+        float* Pb = o.P_band ? o.P_band + fr * p.K - p.band_lo : nullptr;
+        const int bhi = p.band_lo + p.K;
+        const bool keep = o.band_energy || o.raw;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int k = tif + r * tpf;
+            const cx<T> zk = ld_cx(x + stftg_pos(k)), cn = cconj(ld_cx(x + stftg_pos((H - k) & (H - 1))));
             const cx<T> e = {(zk.x + cn.x) * half, (zk.y + cn.y) * half};
             const cx<T> d = csub(zk, cn);
             const cx<T> od = {d.y * half, -d.x * half};
-            const cx<T> wo = cmul(od, tab.tw[k]);
-            re = e.x + wo.x; im = e.y + wo.y;
+            const cx<T> wo = cmul(od, ldg_cx(tab.tw + k));
+            const float sr = d2f((double)(e.x + wo.x)), si = k == 0 ? 0.0f : d2f((double)(e.y + wo.y));
+            if (Sg) Sg[k] = make_float2(sr, si);
+            const float av = np_cabsf_fast(sr, si);
+            const float pw = av * av;
+            if (keep) Pt[k] = pw;
+            if (Pg) Pg[k] = pw;
+            if (Pb && k >= p.band_lo && k < bhi) Pb[k] = pw;
         }
-        const float sr = d2f((double)re), si = d2f((double)im);
-        const int64_t fr = f0 + t0 + f;
-        if (o.S) { float2* Sg = reinterpret_cast<float2*>(o.S) + fr * F; Sg[k] = make_float2(sr, si); }
-        const float a = np_cabsf(sr, si);
-        const float pw = a * a;
-        s_P[f * PS + k] = pw;
-        if (o.P) o.P[fr * F + k] = pw;
-        if (o.P_band && k >= p.band_lo && k < p.band_lo + p.K) o.P_band[fr * p.K + (k - p.band_lo)] = pw;
+        if (tif == 0) {   // k = H (Nyquist): real
+            const cx<T> z0 = ld_cx(x);
+            const float sr = d2f((double)(z0.x - z0.y));
+            if (Sg) Sg[H] = make_float2(sr, 0.0f);
+            const float av = np_cabsf_fast(sr, 0.0f);
+            const float pw = av * av;
+            if (keep) Pt[H] = pw;
+            if (Pg) Pg[H] = pw;
+            if (Pb && H >= p.band_lo && H < bhi) Pb[H] = pw;
+        }
     }
+    if (!(o.band_energy || o.raw)) return;
     __syncthreads();
     if (o.band_energy) {
-        for (int i = tid; i < nfr * (p.M + 1); i += STFTG_NT) {
-            const int f = i / (p.M + 1), m = i - f * (p.M + 1);
-            const float* Pt = s_P + f * PS;
-            double s = 0.0;
-            if (m < p.M) { for (int k = p.mode_lo[m]; k <= p.mode_hi[m]; k++) s += (double)Pt[k]; }
-            else { for (int k = 0; k < p.K; k++) s += (double)Pt[p.band_lo + k]; s += p.eps64; }
-            o.band_energy[(int64_t)m * o.nF + f0 + t0 + f] = d2f(s);
+        // one warp per frame, row after row: float64 partial sums per lane, combined by shuffles (tolerance feature)
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int ff = warp; ff < nfr; ff += STFTG_NT / 32) {
+            const float* Pt = s_P + ff * PS;
+            float* be = o.band_energy + f0 + t0 + ff;
+#pragma unroll 1
+            for (int m = 0; m <= p.M; m++) {
+                const int lo = m < p.M ? p.mode_lo[m] : p.band_lo, hi = m < p.M ? p.mode_hi[m] : p.band_lo + p.K - 1;
+                double sacc = 0.0;
+                for (int k = lo + lane; k <= hi; k += 32) sacc += (double)Pt[k];
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, d);
+                if (lane == 0) be[(int64_t)m * o.nF] = d2f(m < p.M ? sacc : sacc + p.eps64);
+            }
         }
     }
     if (o.raw && tid < nfr) raw_features_frame(p, s_P + tid * PS, o.freqs, o.raw + f0 + t0 + tid, o.nF);

@@ -155,7 +155,7 @@ def reference_available():
     return _REF["ok"]
 
 
-def cpu_reference(seconds, n_clips, workers):
+def cpu_reference(seconds, n_clips, workers, geom=None):
     """The reference's own CPU path: process_audio_batches_v2 with its RainDetectorProcessor, injected
     synthetic loaders, parallel=True over `workers` processes (the reference's rule: cpu_count - 1)."""
     import contextlib
@@ -172,7 +172,7 @@ def cpu_reference(seconds, n_clips, workers):
     def loader(keys, InputType, Fs, check_duration, localStatus, local_cache, read_size=None, bytes_per_sample=2, **kw):
         return {k["source_file"]: {"file_contents": distinct[int(k["source_file"][4:]) % 4], "raining": False} for k in keys}
 
-    params = {"sample_rate": FS, "check_duration": seconds, "detector": {"mode_bands": [tuple(m) for m in MODES]}}
+    params = {"sample_rate": FS, "check_duration": seconds, "detector": {"mode_bands": [tuple(m) for m in MODES]}, **(geom or {})}
     t0 = time.perf_counter()
     with contextlib.redirect_stdout(io.StringIO()):
         res, _ = process_audio_batches_v2(processors=[RainDetectorProcessor()], params_global=params,
@@ -190,7 +190,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from audio_processing_tools_b200.synth import default_params
-    params = default_params(check_duration=args.clip_seconds, **({"operating_band": tuple(args.operating_band)} if args.operating_band else {}))
+    geom = {} if (args.n_fft, args.hop) == (256, 128) else {"n_fft": args.n_fft, "hop": args.hop}
+    params = default_params(check_duration=args.clip_seconds, **geom,
+                            **({"operating_band": tuple(args.operating_band)} if args.operating_band else {}))
     cores = os.cpu_count() or 1
     workers = max(1, cores - 1)
     port_v, port_n, port_dt = cpu_port(params, args.clip_seconds, cores, target_wall=8.0)
@@ -203,10 +205,10 @@ def run_reference(args, rank, world):
         # bounded sample: `workers` clips of 60 s per step (the reference needs ~4 s per 60 s of audio per core)
         sec, n = 60.0, workers
         for _ in range(min(1, args.warmup)):
-            cpu_reference(sec, n, workers)
+            cpu_reference(sec, n, workers, geom)
         vals, times = [], []
         for _ in range(max(1, min(args.steps, 5))):
-            v, dt = cpu_reference(sec, n, workers)
+            v, dt = cpu_reference(sec, n, workers, geom)
             vals.append(v)
             times.append(dt)
         value = float(np.mean(vals))
@@ -214,7 +216,7 @@ def run_reference(args, rank, world):
                   f"(baseline/_ref) through its own process_audio_batches_v2 + RainDetectorProcessor, parallel=True, {workers} worker processes "
                   f"(its own default rule cpu_count - 1); librosa 0.11 is not installable offline: oracle/refharness supplies the stft stand-in")
         print(json.dumps({**common, "value": value, "ms_per_step": float(np.mean(times) * 1e3),
-                          "config": {"workload": f"full pipeline, {args.clips} x {args.clip_seconds:g}s synthetic clips (BASELINE configs[2]); "
+                          "config": {"workload": f"full pipeline, {args.clips} x {args.clip_seconds:g}s synthetic clips (BASELINE configs[{4 if geom else 2}]) n_fft={args.n_fft} hop={args.hop}; "
                                                  f"the CPU arm runs a bounded sample per step"},
                           "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": workers, "kind": "reference", "sample": sample},
                           "cpu_port": port,
@@ -228,7 +230,7 @@ def run_reference(args, rank, world):
     value = float(np.mean(vals))
     port["value"] = value
     print(json.dumps({**common, "value": value, "ms_per_step": float(np.mean(times) * 1e3),
-                      "config": {"workload": f"full pipeline, {args.clips} x {args.clip_seconds:g}s synthetic clips (BASELINE configs[2]); "
+                      "config": {"workload": f"full pipeline, {args.clips} x {args.clip_seconds:g}s synthetic clips (BASELINE configs[{4 if geom else 2}]) n_fft={args.n_fft} hop={args.hop}; "
                                              f"the CPU arm runs a bounded sample per step"},
                       "cpu_baseline": port, "reference_unavailable": _REF.get("why"),
                       "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -354,7 +356,9 @@ def main():
             dist.destroy_process_group()
         return
 
-    params = default_params(check_duration=args.clip_seconds, **({"operating_band": tuple(args.operating_band)} if args.operating_band else {}))
+    geom = {} if (args.n_fft, args.hop) == (256, 128) else {"n_fft": args.n_fft, "hop": args.hop}   # configs[4]: the whole pipeline at another frame size
+    params = default_params(check_duration=args.clip_seconds, **geom,
+                            **({"operating_band": tuple(args.operating_band)} if args.operating_band else {}))
     cfg = build_noise_config(FS, params)
     eng = BatchEngine(cfg, FS, device=local_rank, fft_f64=FFT_MODE[args.fft])
     N = int(FS * args.clip_seconds)
@@ -372,7 +376,7 @@ def main():
     # really is one batch cut in pieces
     base = make_base_clips(n_base, args.clip_seconds, seed0=0)
     plan = eng.plan_for([N] * n_clips)
-    T = 1 + N // HOP
+    T = 1 + N // args.hop
 
     # device-resident shard (13.4 GB int16 at 1 000 clips, >> L2)
     base_dev = torch.from_numpy(np.stack(base)).to(dev)
@@ -460,7 +464,7 @@ def main():
         "config": {"workload": (f"full pipeline (STFT -> noise floor -> rain events), {total_clips} x {args.clip_seconds:g}s clips"
                                 + (f" in one batch split over {world} GPU(s) ({', '.join(str(c) for c in sorted(set(counts)))} per GPU)" if strong
                                    else f" ({args.clips} per GPU)")
-                                + f", fs=11162 n_fft=256 hop=128 (BASELINE configs[{2 if world == 1 else 3}])"),
+                                + f", fs=11162 n_fft={args.n_fft} hop={args.hop} (BASELINE configs[{(2 if world == 1 else 3) if not geom else 4}])"),
                    "clips_total": total_clips, "clips_per_gpu": n_clips, "clip_seconds": args.clip_seconds, "input": "int16 PCM",
                    "fft": args.fft, "distinct_clips": n_base,
                    "l2": "inputs (%.1f GB per GPU per step) are far larger than the 126 MB L2" % (plan.nS * 2 / 1e9),
