@@ -234,3 +234,29 @@ def load():
         raise RuntimeError("libapt_b200.so struct layout differs from the Python binding")
     _lib = L
     return L
+
+
+# Optional device timing of the C-ABI calls of the engines beside the main path (bench.py --workload bne|roe|dsd):
+# CUDA events on the stream the call launches on, recorded around the call (inputs already in HBM).
+DEVICE_TIMING = False
+LAST_DEVICE_MS = {}
+
+
+class device_timer:
+    def __init__(self, torch, key, device):
+        self.torch, self.key, self.device = torch, key, device
+        self.on = DEVICE_TIMING
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = self.torch.cuda.Event(enable_timing=True)
+            self.e1 = self.torch.cuda.Event(enable_timing=True)
+            self.e0.record(self.torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if self.on and exc[0] is None:
+            self.e1.record(self.torch.cuda.current_stream(self.device))
+            self.e1.synchronize()
+            LAST_DEVICE_MS[self.key] = float(self.e0.elapsed_time(self.e1))
+        return False

@@ -21,10 +21,32 @@
 
 using namespace apt;
 
+// grow-only device scratch of the engines beside the main path (apt_dsd_run_i16 / apt_bne_run / apt_roe_run): one slot
+// per buffer, kept from call to call so that a steady stream of same-sized batches never reaches cudaMalloc
+struct ScratchPool {
+    std::vector<void*> ptr;
+    std::vector<size_t> cap;
+    cudaError_t get(int slot, size_t bytes, void** out) {
+        if ((int)ptr.size() <= slot) { ptr.resize(slot + 1, nullptr); cap.resize(slot + 1, 0); }
+        if (cap[slot] < bytes) {
+            if (ptr[slot]) cudaFree(ptr[slot]);
+            ptr[slot] = nullptr; cap[slot] = 0;
+            const size_t want = bytes + bytes / 4 + 256;
+            cudaError_t e = cudaMalloc(&ptr[slot], want);
+            if (e != cudaSuccess) return e;
+            cap[slot] = want;
+        }
+        *out = ptr[slot];
+        return cudaSuccess;
+    }
+    ~ScratchPool() { for (void* q : ptr) if (q) cudaFree(q); }
+};
+
 struct apt_ctx {
     int device;
     int sm_count;
     std::string err;
+    ScratchPool pool;
 };
 
 static int fail(apt_ctx* ctx, int code, const char* fmt, ...) {
@@ -54,6 +76,22 @@ struct DevBuf {
     }
     void free_() { if (p) cudaFree(p); p = nullptr; n = 0; }
     ~DevBuf() { free_(); }
+};
+// same interface on a slot of the context's scratch pool (not owned)
+template <typename T>
+struct PoolBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    apt_ctx* ctx;
+    int slot;
+    PoolBuf(apt_ctx* c, int s) : ctx(c), slot(s) {}
+    cudaError_t alloc(size_t count) {
+        n = count;
+        void* q = nullptr;
+        cudaError_t e = ctx->pool.get(slot, std::max<size_t>(count, 1) * sizeof(T), &q);
+        p = (T*)q;
+        return e;
+    }
 };
 
 struct apt_plan {
@@ -182,8 +220,8 @@ static void build_td_tables(const apt_params_t& prm, int ns, const double sos[][
     (void)prm;
 }
 
-template <typename T>
-static cudaError_t upload(DevBuf<T>& b, const std::vector<T>& h) {
+template <typename B, typename T>
+static cudaError_t upload(B& b, const std::vector<T>& h) {
     cudaError_t e = b.alloc(h.size());
     if (e != cudaSuccess) return e;
     if (h.empty()) return cudaSuccess;
@@ -1532,7 +1570,8 @@ extern "C" int apt_dsd_run_i16(apt_ctx* ctx, const apt_dsd_params_t* p, int n_cl
         so[c + 1] = so[c] + n; fo[c + 1] = fo[c] + nf;
         max_fr = std::max(max_fr, nf);
     }
-    DevBuf<int64_t> d_so, d_fo; DevBuf<double> d_ts, d_drop, d_pkv, d_win; DevBuf<int> d_pki; DevBuf<cx<double>> d_tw;
+    PoolBuf<int64_t> d_so(ctx, 0), d_fo(ctx, 1); PoolBuf<double> d_ts(ctx, 2), d_drop(ctx, 3), d_pkv(ctx, 4), d_win(ctx, 5);
+    PoolBuf<int> d_pki(ctx, 6); PoolBuf<cx<double>> d_tw(ctx, 7);
     CUDA_OK(ctx, upload(d_so, so)); CUDA_OK(ctx, upload(d_fo, fo));
     CUDA_OK(ctx, upload(d_ts, std::vector<double>(ts, ts + n_clips)));
     std::vector<cx<double>> tw(L / 2 + 1);
@@ -1574,7 +1613,8 @@ extern "C" int apt_bne_run(apt_ctx* ctx, const apt_bne_params_t* p, int n_clips,
         so[c + 1] = so[c] + clip_len[c]; fo[c + 1] = fo[c] + nf; sg[c + 1] = sg[c] + (nf + BNE_SEG - 1) / BNE_SEG;
         max_fr = std::max(max_fr, nf);
     }
-    DevBuf<int64_t> d_so, d_fo, d_sg; DevBuf<double> d_xhp, d_subEh, d_fftq; DevBuf<cx<double>> d_tw;
+    PoolBuf<int64_t> d_so(ctx, 10), d_fo(ctx, 11), d_sg(ctx, 12); PoolBuf<double> d_xhp(ctx, 13), d_subEh(ctx, 14), d_fftq(ctx, 15);
+    PoolBuf<cx<double>> d_tw(ctx, 16);
     CUDA_OK(ctx, upload(d_so, so)); CUDA_OK(ctx, upload(d_fo, fo)); CUDA_OK(ctx, upload(d_sg, sg));
     std::vector<cx<double>> tw(N / 2 + 1);
     for (int k = 0; k <= N / 2; k++) tw[k] = {cos(2.0 * M_PI * k / N), -sin(2.0 * M_PI * k / N)};
@@ -1624,10 +1664,10 @@ extern "C" int apt_roe_run(apt_ctx* ctx, const apt_roe_params_t* p, int n_clips,
     for (int c = 0; c < n_clips; c++) cp0[c + 1] += cp0[c];
     CUDA_OK(ctx, cudaMemsetAsync(dev_clip_out, 0, sizeof(double) * (size_t)n_clips * APT_ROE_CLIP_F, st));
     *max_harmonics_out = max_harmonics_in;
-    DevBuf<int> d_cp0; CUDA_OK(ctx, upload(d_cp0, cp0));
+    PoolBuf<int> d_cp0(ctx, 20); CUDA_OK(ctx, upload(d_cp0, cp0));
     if (n_parts > 0) {
-        DevBuf<int64_t> d_fo, d_yo, d_start; DevBuf<int32_t> d_clip, d_len; DevBuf<int> d_mh;
-        DevBuf<double> d_y, d_t, d_mag, d_harm; DevBuf<cx<double>> d_twA, d_tw256;
+        PoolBuf<int64_t> d_fo(ctx, 21), d_yo(ctx, 22), d_start(ctx, 23); PoolBuf<int32_t> d_clip(ctx, 24), d_len(ctx, 25); PoolBuf<int> d_mh(ctx, 26);
+        PoolBuf<double> d_y(ctx, 27), d_t(ctx, 28), d_mag(ctx, 29), d_harm(ctx, 30); PoolBuf<cx<double>> d_twA(ctx, 31), d_tw256(ctx, 32);
         CUDA_OK(ctx, upload(d_fo, fo)); CUDA_OK(ctx, upload(d_yo, yo));
         CUDA_OK(ctx, upload(d_start, std::vector<int64_t>(part_start, part_start + n_parts)));
         CUDA_OK(ctx, upload(d_clip, std::vector<int32_t>(part_clip, part_clip + n_parts)));

@@ -175,9 +175,10 @@ class BandNoiseEstimatorProcessor:
         d_mask = torch.zeros(max(nF, 1), dtype=torch.uint8, device=dev)
         d_sub = torch.zeros((max(nF, 1), _lib.BNE_MAX_S), dtype=torch.float64, device=dev)
         d_st = torch.zeros((len(clips), _lib.BNE_STATS), dtype=torch.float64, device=dev)
-        rc = L.apt_bne_run(ctx, C.byref(P), len(clips), lens.ctypes.data_as(C.POINTER(C.c_int64)), d_pcm.data_ptr(), int(is_f32),
-                           d_fo.data_ptr(), d_mask.data_ptr(), d_sub.data_ptr(), d_st.data_ptr(),
-                           torch.cuda.current_stream(self._device).cuda_stream)
+        with _lib.device_timer(torch, "bne", self._device):
+            rc = L.apt_bne_run(ctx, C.byref(P), len(clips), lens.ctypes.data_as(C.POINTER(C.c_int64)), d_pcm.data_ptr(), int(is_f32),
+                               d_fo.data_ptr(), d_mask.data_ptr(), d_sub.data_ptr(), d_st.data_ptr(),
+                               torch.cuda.current_stream(self._device).cuda_stream)
         if rc != 0:
             raise AptError(f"apt_bne_run failed ({rc}): {L.apt_last_error(ctx).decode()}")
         fo, mask, sub, st = d_fo.cpu().numpy(), d_mask.cpu().numpy(), d_sub.cpu().numpy(), d_st.cpu().numpy()

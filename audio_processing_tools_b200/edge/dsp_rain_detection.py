@@ -178,10 +178,11 @@ def rain_detection_algo_batch(audio_list: Sequence[np.ndarray], **kwargs) -> Lis
     d_p = torch.zeros((max(n_parts, 1), _lib.ROE_PART_F), dtype=torch.float64, device=dev)
     d_c = torch.zeros((len(clips), _lib.ROE_CLIP_F), dtype=torch.float64, device=dev)
     mh_out = C.c_int(0)
-    rc = L.apt_roe_run(ctx, C.byref(P), len(clips), d_pcm.data_ptr(), int(is_f32), n_parts,
-                       pclip.ctypes.data_as(C.POINTER(C.c_int32)), pstart.ctypes.data_as(C.POINTER(C.c_int64)),
-                       plen.ctypes.data_as(C.POINTER(C.c_int32)), int(max_harmonics), d_f.data_ptr(), d_p.data_ptr(), d_c.data_ptr(),
-                       C.byref(mh_out), torch.cuda.current_stream(_device).cuda_stream)
+    with _lib.device_timer(torch, "roe", _device):
+        rc = L.apt_roe_run(ctx, C.byref(P), len(clips), d_pcm.data_ptr(), int(is_f32), n_parts,
+                           pclip.ctypes.data_as(C.POINTER(C.c_int32)), pstart.ctypes.data_as(C.POINTER(C.c_int64)),
+                           plen.ctypes.data_as(C.POINTER(C.c_int32)), int(max_harmonics), d_f.data_ptr(), d_p.data_ptr(), d_c.data_ptr(),
+                           C.byref(mh_out), torch.cuda.current_stream(_device).cuda_stream)
     if rc != 0:
         raise AptError(f"apt_roe_run failed ({rc}): {L.apt_last_error(ctx).decode()}")
     max_harmonics = int(mh_out.value)

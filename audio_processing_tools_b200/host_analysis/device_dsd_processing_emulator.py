@@ -93,9 +93,10 @@ class DsdProcessingEmualtor:
         win = np.ascontiguousarray(get_window("hann", int(self.frame_length)).astype(np.float64))
         prm.window = win.ctypes.data_as(C.c_void_p)
         tsa = np.ascontiguousarray(np.asarray(ts, dtype=np.float64))
-        rc = L.apt_dsd_run_i16(ctx, C.byref(prm), len(pcm), lens.ctypes.data_as(C.POINTER(C.c_int64)),
-                               tsa.ctypes.data_as(C.POINTER(C.c_double)), d_pcm.data_ptr(), d_out.data_ptr(),
-                               d_n.data_ptr(), max_minutes, torch.cuda.current_stream(self._device).cuda_stream)
+        with _lib.device_timer(torch, "dsd", self._device):
+            rc = L.apt_dsd_run_i16(ctx, C.byref(prm), len(pcm), lens.ctypes.data_as(C.POINTER(C.c_int64)),
+                                   tsa.ctypes.data_as(C.POINTER(C.c_double)), d_pcm.data_ptr(), d_out.data_ptr(),
+                                   d_n.data_ptr(), max_minutes, torch.cuda.current_stream(self._device).cuda_stream)
         if rc != 0:
             raise AptError(f"apt_dsd_run_i16 failed ({rc}): {L.apt_last_error(ctx).decode()}")
         out, n = d_out.cpu().numpy(), d_n.cpu().numpy()

@@ -50,7 +50,11 @@ def parse():
     ap.add_argument("--fft", default="f64", choices=("f64", "f32", "tc"),
                     help="STFT arithmetic: f64 = the reference's (default, bit-exact events), f32 = float32 FFT, tc = tensor-core DFT (both tolerance paths)")
     ap.add_argument("--scaling", default="strong", choices=("strong", "weak"))
-    ap.add_argument("--workload", default="full", choices=("full", "features_1h", "sweep"))
+    ap.add_argument("--workload", default="full", choices=("full", "features_1h", "sweep", "bne", "roe", "dsd"),
+                    help="full / features_1h / sweep: the hot path; bne, roe, dsd: the engines beside it (SURVEY 8(f) rows 1-3)")
+    ap.add_argument("--config", type=int, default=None, choices=(1, 2, 3, 4),
+                    help="shorthand for BASELINE configs[i]: 1 = --workload features_1h, 2 / 3 = --workload full (3 under torchrun), "
+                         "4 = --workload sweep at --n-fft / --hop (default 1024 / 256)")
     ap.add_argument("--n-fft", type=int, default=256)
     ap.add_argument("--hop", type=int, default=128)
     ap.add_argument("--write-spectra", action="store_true", help="features workloads: also write S (the HBM-bound variant)")
@@ -60,7 +64,17 @@ def parse():
                     help="experiment knob: another operating band (the BASELINE workload uses the default 400..3500 Hz = 71 bins)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cpu-reference", action="store_true", help="skip the leg that times the unmodified reference")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.config is not None:
+        if args.config == 1:
+            args.workload = "features_1h"
+        elif args.config in (2, 3):
+            args.workload = "full"
+        else:
+            args.workload = "sweep"
+            if (args.n_fft, args.hop) == (256, 128):
+                args.n_fft, args.hop = 1024, 256
+    return args
 
 
 def make_base_clips(n_base, seconds, seed0):
@@ -281,6 +295,127 @@ def timed_steps(torch, dist, world, dev, step, steps, warmup, local_rank):
     return ms_total / steps, sampler.summary()
 
 
+def run_neighbour(args, torch, local_rank, dev):
+    """band noise estimator, legacy RoE detector, DSD emulator.  `value`: the C-ABI call timed with
+    CUDA events, inputs resident in HBM; `e2e`: the public Python call on host arrays (H2D, kernels, D2H, packaging);
+    `cpu_baseline`: the unmodified reference (baseline/_ref) when importable, else its numpy restatement (oracle/), one core."""
+    from audio_processing_tools_b200 import _lib
+    from audio_processing_tools_b200.synth import batch_clip_spec, pcm_to_f32, synth_clip_i16
+    kind = args.workload
+    peak, peak_src = load_peak()
+    if kind == "bne":
+        from audio_processing_tools_b200.edge.band_noise_processor import BandNoiseEstimatorProcessor
+        n, sec = 512, 60.0
+        base = [synth_clip_i16(sec, *batch_clip_spec(i)) for i in range(8)]
+        batch = [base[i % 8] for i in range(n)]
+        proc = BandNoiseEstimatorProcessor()
+        call = lambda: proc.run_batch(batch, {"sample_rate": FS})
+        N = 256
+        frames = n * (int(FS * sec) // N)
+        bytes_algo = n * int(FS * sec) * 2 + frames * (_lib.BNE_FRAME_F * 8 + 1 + _lib.BNE_MAX_S * 8)
+        what = f"band noise estimator (edge/band_noise_estimator.py), {n} x {sec:g}s clips, frame 256"
+
+        def cpu(nc):
+            if reference_available():
+                from audio_processing_tools.edge.band_noise_processor import BandNoiseEstimatorProcessor as Ref
+                r = Ref()
+                t0 = time.perf_counter()
+                for i in range(nc):
+                    r.run(pcm_to_f32(base[i % 8]), {"sample_rate": FS})
+                return time.perf_counter() - t0, "reference"
+            from oracle import band_noise_oracle
+            t0 = time.perf_counter()
+            for i in range(nc):
+                band_noise_oracle.run(pcm_to_f32(base[i % 8]), {"sample_rate": FS})
+            return time.perf_counter() - t0, "port"
+        cpu_n = 32
+    elif kind == "roe":
+        from audio_processing_tools_b200.edge import dsp_rain_detection as roe
+        n, sec = 2000, 10.0
+        base = [synth_clip_i16(sec, *batch_clip_spec(i)) for i in range(8)]
+        batch = [base[i % 8] for i in range(n)]
+        call = lambda: roe.rain_detection_algo_batch(batch, **roe.default_params)
+        frames = n * (1 + int(FS * sec) // 128)
+        bytes_algo = n * int(FS * sec) * 2 + frames * _lib.ROE_FRAME_F * 8
+        what = f"legacy RoE detector (edge/dsp_rain_detection.py rain_detection_algo), {n} x {sec:g}s clips"
+
+        def cpu(nc):
+            if reference_available():
+                import audio_processing_tools.edge.dsp_rain_detection as ref
+                import contextlib
+                import io
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    for i in range(nc):
+                        ref.rain_detection_algo(pcm_to_f32(base[i % 8]), **roe.default_params)
+                return time.perf_counter() - t0, "reference"
+            from oracle import roe_oracle
+            t0 = time.perf_counter()
+            for i in range(nc):
+                roe_oracle.rain_detection_algo(pcm_to_f32(base[i % 8]), **roe.default_params)
+            return time.perf_counter() - t0, "port"
+        cpu_n = 32
+    else:
+        from audio_processing_tools_b200.host_analysis.device_dsd_processing_emulator import DsdProcessingEmualtor
+        n, sec = 256, 300.0
+        base = [synth_clip_i16(sec, *batch_clip_spec(i)) for i in range(4)]
+        batch = [base[i % 4] for i in range(n)]
+        em = DsdProcessingEmualtor(fs=FS, frame_length=512, hop_length=512, bwindow=False, ts=0)
+        call = lambda: em.process_audio_batch(batch, [0.0] * n)
+        frames = n * (int(FS * sec) // 512)
+        bytes_algo = n * int(FS * sec) * 2 + n * int(np.ceil(sec / 60.0)) * 100 * 8
+        what = f"DSD emulator (host_analysis/device_dsd_processing_emulator.py), {n} x {sec:g}s clips, frame 512"
+
+        def cpu(nc):
+            if reference_available():
+                from audio_processing_tools.host_analysis.device_dsd_processing_emulator import DsdProcessingEmualtor as Ref
+                t0 = time.perf_counter()
+                for i in range(nc):
+                    Ref(fs=FS, frame_length=512, hop_length=512, bwindow=False, ts=0, verbose=False).process_audio_data(base[i % 4], 0)
+                return time.perf_counter() - t0, "reference"
+            from oracle import dsd_oracle
+            t0 = time.perf_counter()
+            for i in range(nc):
+                dsd_oracle.process_audio_data(base[i % 4], 0.0)
+            return time.perf_counter() - t0, "port"
+        cpu_n = 64
+    audio_s = n * sec
+    _lib.DEVICE_TIMING = True
+    for _ in range(max(3, args.warmup)):
+        call()
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    samp = ClockSampler(local_rank)
+    samp.start()
+    dev_ms, wall = [], []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        call()
+        wall.append(time.perf_counter() - t0)
+        dev_ms.append(_lib.LAST_DEVICE_MS[kind])
+    samp.stop_flag.set()
+    samp.join(timeout=2)
+    ms = float(np.mean(dev_ms))
+    res = {"metric": "audio_seconds_per_second", "value": audio_s / (ms * 1e-3), "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": what + " (SURVEY 8(f)); a 256 MB write flushes L2 before every timed call", "clips": n, "clip_seconds": sec},
+           "roofline": {"bound": "hbm", "kernel": f"apt_{kind}_run (all its kernels + table uploads, C-ABI call timed with CUDA events)",
+                        "achieved": bytes_algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": bytes_algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes": bytes_algo},
+           "e2e": {"value": audio_s / float(np.mean(wall)), "unit": "audio-s/s", "ms_per_step": float(np.mean(wall) * 1e3),
+                   "h2d_bytes_per_step": int(n * int(FS * sec) * 2), "d2h_bytes_per_step": int(bytes_algo - n * int(FS * sec) * 2),
+                   "note": "public Python call on a list of host arrays: concatenate, H2D, kernels, D2H, per-clip result packaging; wall clock"},
+           "clocks": samp.summary(), "gpu_launches": None}
+    if not args.no_cpu:
+        dt, how = cpu(cpu_n)
+        res["cpu_baseline"] = {"value": cpu_n * sec / dt, "unit": "audio-s/s", "cores": 1, "kind": how,
+                               "sample": f"{cpu_n} x {sec:g}s clips, one process ({dt:.1f}s)"}
+    print(json.dumps(res), flush=True)
+
+
 def run_features(args, torch, dist, rank, world, local_rank, dev):
     """BASELINE configs[1] / configs[4]: features stage (framing, window, FFT, power, band energies) on one long clip."""
     from audio_processing_tools_b200 import _lib
@@ -350,6 +485,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.workload in ("bne", "roe", "dsd"):
+        if rank == 0:
+            run_neighbour(args, torch, local_rank, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload != "full":
         run_features(args, torch, dist, rank, world, local_rank, dev)
         if world > 1:
