@@ -145,6 +145,8 @@ class SpectralNoiseProcessor:
             }
             if keep_det:
                 res["det_debug"] = self._det_debug(out, f0, f1, rp, dv)
+            if bool(cfg.dump_features):
+                res["features"] = self._features(cfg, times, res["frame_class"], res["rain_conf"], res["noise_conf"], res.get("det_debug"))
             if keep_debug:
                 res["debug"] = self._debug(out, f0, f1, rp, dv, times)
             if keep_filt:
@@ -187,6 +189,29 @@ class SpectralNoiseProcessor:
             cls._times_cache[key] = t
         return t.copy()
 
+    @staticmethod
+    def _features(cfg, times, fc, rc, nc, det_debug=None) -> Dict[str, Any]:
+        """`dump_features` payload (rain_signal_processor.py:723-787): the five per-frame arrays, plus whatever the
+        detector exported when its debug output is on, every array decimated along its frame axis by `feature_decim`."""
+        step = max(1, int(getattr(cfg, "feature_decim", 1)))
+
+        def dec(v):
+            if step <= 1 or v is None:
+                return v
+            if isinstance(v, np.ndarray):
+                return v if v.ndim == 0 else v[..., ::step]
+            if isinstance(v, (list, tuple)):
+                return v[::step]
+            return v
+
+        f = {"frame_times": dec(np.asarray(times, dtype=np.float32)), "frame_class": dec(np.asarray(fc)),
+             "is_rain": dec(np.asarray(fc) == FrameClass.RAIN), "rain_conf": dec(np.asarray(rc, dtype=np.float32)),
+             "noise_conf": dec(np.asarray(nc, dtype=np.float32))}
+        if isinstance(det_debug, dict):
+            for k, v in det_debug.items():
+                f[k] = dec(v)
+        return f
+
     def _package_core(self, plan, out, cfg, sr, rp, with_stats) -> List[Dict[str, Any]]:
         """Result dictionaries of the default-flags path: per-clip views of the batch's (caller-owned) host arrays."""
         results = []
@@ -198,6 +223,8 @@ class SpectralNoiseProcessor:
             res: Dict[str, Any] = {"frame_class": fc[f0:f1], "freqs": rp.freqs.copy(),
                                    "times": self._times(f1 - f0, cfg.hop, sr),
                                    "rain_conf": rc[f0:f1], "noise_conf": nc[f0:f1]}
+            if bool(cfg.dump_features):
+                res["features"] = self._features(cfg, res["times"], res["frame_class"], res["rain_conf"], res["noise_conf"])
             if with_stats:
                 res["_clip_stats"] = out["clip_stats"][c]
                 res["_event_idx"] = ev[f0:f0 + int(out["event_count"][c])] if ev is not None else None

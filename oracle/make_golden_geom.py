@@ -38,5 +38,24 @@ def main():
         print(path, fc.size, "frames,", int((fc == 2).sum()), "rain,", os.path.getsize(path) // 1024, "KiB", flush=True)
 
 
+def features_case():
+    """`dump_features` payload (state["features"]) at feature_decim = 3, default detector flags."""
+    import hashlib
+    import json
+    from audio_processing_tools.edge.rain_signal_processor import RainDetectorProcessor
+    from audio_processing_tools_b200.synth import default_params, pcm_to_f32
+    seconds, seed, lam = 8, 61, 3.0
+    pcm = synth_clip_i16(seconds, seed, lam)
+    params = default_params(check_duration=seconds, dump_features=True, feature_decim=3)
+    _, state = RainDetectorProcessor().run(pcm_to_f32(pcm), params)
+    d = {"feat_" + k: np.asarray(v) for k, v in state["features"].items()}
+    d["meta"] = np.array(json.dumps({"seconds": seconds, "seed": seed, "lam": lam, "feature_decim": 3,
+                                     "pcm_sha1": hashlib.sha1(pcm.tobytes()).hexdigest(), "numpy": np.__version__}))
+    path = os.path.join(mg.OUT, "features_s61_decim3.npz")
+    np.savez_compressed(path, **d)
+    print(path, sorted(d), flush=True)
+
+
 if __name__ == "__main__":
     main()
+    features_case()

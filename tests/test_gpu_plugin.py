@@ -279,3 +279,33 @@ def test_tensor_core_dft_variant(oracle_mod):
     print(f"tensor-core DFT front end: {flips} of {plan3.nF} frame labels differ from the oracle")
     assert flips <= plan3.nF // 2000
     e64.close(); etc.close()
+
+
+def test_dump_features_payload_matches_reference():
+    """state["features"] under dump_features (rain_signal_processor.py:723-787, :1318): the five per-frame arrays
+    decimated by feature_decim, as the unmodified reference returned them (oracle/make_golden_geom.py); with the
+    detector debug on, the detector's per-frame features ride along, decimated the same way."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from audio_processing_tools_b200.edge.rain_signal_processor import RainDetectorProcessor
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "features_s61_decim3.npz"), allow_pickle=False))
+    meta = json.loads(str(g["meta"]))
+    pcm = synth_clip_i16(meta["seconds"], meta["seed"], meta["lam"])
+    assert hashlib.sha1(pcm.tobytes()).hexdigest() == meta["pcm_sha1"]
+    params = default_params(check_duration=meta["seconds"], dump_features=True, feature_decim=3)
+    proc = RainDetectorProcessor()
+    _, st = proc.run(pcm_to_f32(pcm), params)
+    f = st["features"]
+    assert set(f) == {"frame_times", "frame_class", "is_rain", "rain_conf", "noise_conf"}
+    for k in f:
+        assert f[k].dtype == g["feat_" + k].dtype and np.array_equal(f[k], g["feat_" + k]), k
+    # int16 input through the batch entry point gives the same payload; keep_state_features=False drops it
+    outs = proc.run_batch([pcm, synth_clip_i16(meta["seconds"] + 1.5, 62, 10.0)], params)
+    assert np.array_equal(outs[0][1]["features"]["frame_class"], g["feat_frame_class"])
+    assert "features" not in proc.run(pcm, dict(params, keep_state_features=False))[1]
+    _, st2 = proc.run(pcm, dict(params, keep_state_debug=True))
+    f2 = st2["features"]
+    assert np.array_equal(f2["td_crest_factor"], st2["det_debug"]["td_crest_factor"][::3])
+    assert np.array_equal(f2["frame_class"], g["feat_frame_class"])
