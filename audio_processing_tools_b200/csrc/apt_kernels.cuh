@@ -1580,7 +1580,10 @@ __global__ void __launch_bounds__(TDF_NT, 3) td_gate_fast_kernel(Batch b, const 
 // plan): the 64-bit multiply per element costs instructions these loops are made of.  trk2 keeps 64-bit offsets: with
 // fewer registers all its CTAs become co-resident and it runs slower.
 constexpr int SEQ_KMAX = 128;    // operating-band bins supported (n_fft = 256 -> 71)
-constexpr int SEQ_PF = 16;       // frames per straight-line group of the serial loops (register prefetch)
+#ifndef APT_SEQ_PF
+#define APT_SEQ_PF 16
+#endif
+constexpr int SEQ_PF = APT_SEQ_PF;       // frames per straight-line group of the serial loops (register prefetch)
 
 struct Tracker {
     float trk, ts, nprev;
