@@ -174,8 +174,6 @@ class ResolvedParams:
                 raise NotImplementedError(f"detector.{flag}=True is not implemented on the CUDA path")
         if str(cfg.process_dtype).lower() != "float32":
             raise NotImplementedError("process_dtype='float64' is not implemented on the CUDA path")
-        if bool(cfg.adaptive_q_enable):
-            raise NotImplementedError("adaptive_q_enable=True is not implemented on the CUDA path")
         if int(cfg.median_frames or 0) > 1 or int(cfg.pre_smooth_frames or 0) > 1:
             raise NotImplementedError("median_frames / pre_smooth_frames > 1 are not implemented on the CUDA path")
         if str(dv.get("td_input_mode", "default")).lower() != "default":
@@ -239,6 +237,11 @@ class ResolvedParams:
         P.trk_eta, P.trk_scale_alpha, P.trk_one_minus_alpha = f32(eta), f32(alpha), f32(1.0 - alpha)
         P.trk_step_floor = f32(float(max(cfg.eps, 1e-9)))
         P.trk_q, P.trk_neg_one_minus_q, P.trk_maxr = f32(q), f32(-(1.0 - q)), f32(maxr)
+        # adaptive quantile of pass 2 (rain_signal_processor.py:570-576); pass 1 excludes no frame, so its q never moves
+        P.adaptive_q = int(bool(cfg.adaptive_q_enable))
+        P.aq_base = q
+        P.aq_min = float(np.clip(float(cfg.adaptive_q_min), 1e-4, q))
+        P.aq_alpha = float(np.clip(float(cfg.adaptive_q_alpha), 0.0, 1.0))
         P.ema_up, P.ema_down = float(cfg.ema_up), float(cfg.ema_down)
         P.warmup_need = max(10, W // 2)
         P.eps_f32 = f32(cfg.eps)

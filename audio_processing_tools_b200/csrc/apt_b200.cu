@@ -129,6 +129,7 @@ struct apt_plan {
     // state carried between the time segments of the pipelined run
     DevBuf<float4> d_st_trk1, d_st_trk2;   // [clips][K]
     DevBuf<double2> d_st_base;             // [clips][APT_MAX_MODES + 1]
+    DevBuf<double> d_st_aq;                // [clips] rain_prev_ema of the adaptive tracker quantile
     // candidate lists of the median select
     std::vector<int64_t> cand_off;
     DevBuf<int64_t> d_cand_off;
@@ -301,6 +302,7 @@ int apt_params_default(apt_params_t* p) {
     p->blk_len = 8; p->blk_hop = 8; p->blk_post_pre = 4; p->blk_smooth = 1;
     p->low_lo = 2; p->low_hi = 4; p->rain_lo = 10; p->rain_hi = 18; p->rolloff_fraction = 0.85;
     p->suppressor_bypass = 0; p->clip_rain_min_frames = 1; p->fft_f64 = 1;
+    p->adaptive_q = 0; p->aq_base = 0.25; p->aq_min = 0.10; p->aq_alpha = 0.95;
     p->gain_mode = 0; p->adaptive_gain = 1; p->gain_freq_smooth = 1; p->n_gain_taps = 3; p->use_lagged_noise_psd = 0;
     p->oversub_noise = 3.0f; p->oversub_rain = 1.0f; p->gain_floor = 0.0f; p->gain_ceil = 1.0f;
     p->gain_taps[0] = 0.2f; p->gain_taps[1] = 0.6f; p->gain_taps[2] = 0.2f;
@@ -356,6 +358,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     d.trk_eta = p->trk_eta; d.trk_alpha = p->trk_scale_alpha; d.trk_1m_alpha = p->trk_one_minus_alpha; d.trk_floor = p->trk_step_floor;
     d.trk_q = p->trk_q; d.trk_nq = p->trk_neg_one_minus_q; d.trk_maxr = p->trk_maxr;
     d.ema_up = p->ema_up; d.ema_down = p->ema_down; d.warm_need = p->warmup_need; d.eps32 = p->eps_f32;
+    d.adaptive_q = p->adaptive_q; d.aq_base = p->aq_base; d.aq_min = p->aq_min; d.aq_alpha = p->aq_alpha;
     d.use_norm = p->detector_use_noise_norm; d.ratio_db = p->norm_ratio_db;
     d.bl_q = p->bl_q; d.bl_eta = p->bl_eta; d.bl_alpha = p->bl_scale_alpha; d.bl_floor = p->bl_floor;
     d.norm_enable = p->norm_enable; d.norm_min = p->norm_min_f32;
@@ -580,6 +583,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     PL_OK(pl->d_st_trk1.alloc((size_t)n_clips * pl->st_stride));
     PL_OK(pl->d_st_trk2.alloc((size_t)n_clips * pl->st_stride));
     PL_OK(pl->d_st_base.alloc((size_t)n_clips * (APT_MAX_MODES + 1)));
+    PL_OK(pl->d_st_aq.alloc((size_t)n_clips));
     {   // candidate lists of the median select: an eighth of the plane per clip (a 1/16 dB bin holds ~1 % of a clip's
         // values; clips that overflow fall back to the full radix select)
         pl->cand_off.assign(n_clips + 1, 0);
@@ -1138,7 +1142,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             pl->mark(APT_KERNEL_TRK2, st);
             Trk2IO io;
             io.P_band = pl->d_Pband.p; io.frame_class = out->frame_class; io.N2 = n2_plane; io.nF = pl->nF;
-            io.state = pl->d_st_trk2.p; io.state_stride = pl->st_stride;
+            io.state = pl->d_st_trk2.p; io.state_stride = pl->st_stride; io.aq_state = pl->d_st_aq.p;
             const int64_t lanes = (int64_t)n_clips * d.K;
             // Every lane runs the whole time chain, so the kernel's time is (waves of CTAs) x (chain time at that
             // residency); measured per frame step: ~170 cycles up to 4 warps/SM, 185 at 8, 228 at 12, and a cliff
@@ -1150,7 +1154,9 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             RR(wait(apt_plan::SK_TRK2, apt_plan::SK_DEC, sg));
             tmark(apt_plan::SK_TRK2, sg, 0);
             if (e == cudaSuccess) {
-                if (!piped && warps_per_sm > 12.0 && warps_per_sm <= 16.0) {
+                if (d.adaptive_q) {
+                    trk2_kernel<128, true><<<(unsigned)((lanes + 127) / 128), 128, 0, S[apt_plan::SK_TRK2]>>>(pl->dp, bs, io);
+                } else if (!piped && warps_per_sm > 12.0 && warps_per_sm <= 16.0) {
                     RR(cudaFuncSetAttribute(trk2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
                     if (e == cudaSuccess) trk2_kernel<256><<<(unsigned)((lanes + 255) / 256), 256, 120 * 1024, S[apt_plan::SK_TRK2]>>>(pl->dp, bs, io);
                 } else {

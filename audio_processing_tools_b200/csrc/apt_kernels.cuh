@@ -47,6 +47,7 @@ struct DevParams {
     double mode_w[APT_MAX_MODES];
     float trk_eta, trk_alpha, trk_1m_alpha, trk_floor, trk_q, trk_nq, trk_maxr;
     double ema_up, ema_down;
+    int adaptive_q; double aq_base, aq_min, aq_alpha;   // adaptive quantile of pass 2
     int warm_need;
     float eps32;
     int use_norm, ratio_db;
@@ -489,7 +490,7 @@ __device__ __forceinline__ void stftg_pass(cx<T>* __restrict__ x, int tif, int H
 // later passes work in place on one padded shared-memory buffer.  Threads of frames beyond the clip end run the same
 // code on their (unused) frame area and skip the global accesses, so every barrier is met without divergence.
 template <typename T, typename PCM>
-__global__ void __launch_bounds__(STFTG_NT, 3) stft_generic_kernel(const __grid_constant__ DevParams p, Batch b,
+__global__ void __launch_bounds__(STFTG_NT, 4) stft_generic_kernel(const __grid_constant__ DevParams p, Batch b,
                                                                 const PCM* __restrict__ pcm, FftTablesG<T> tab, StftOut o, int fpc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.n_fft, H = N >> 1, F = H + 1, PS = H + 4;
@@ -1590,11 +1591,11 @@ struct Tracker {
 };
 
 // one step of _update_noise_psd_frame for one bin (rain_signal_processor.py:594-666); t > 0.  Branch-free.
-__device__ __forceinline__ float tracker_step(const DevParams& p, Tracker& s, float pk, bool allow) {
+__device__ __forceinline__ float tracker_step(const DevParams& p, Tracker& s, float pk, bool allow, float q, float nq) {
     const float err = pk - s.trk;
     s.ts = p.trk_alpha * s.ts + p.trk_1m_alpha * fabsf(err);
     const float step = p.trk_eta * f_max(s.ts, p.trk_floor);
-    const float delta = (pk >= s.trk) ? p.trk_q * step : p.trk_nq * step;
+    const float delta = (pk >= s.trk) ? q * step : nq * step;
     const float cand = f_max(s.trk + delta, 0.0f);
     s.trk = allow ? cand : s.trk;
     const float raw = s.trk;
@@ -1609,6 +1610,9 @@ __device__ __forceinline__ float tracker_step(const DevParams& p, Tracker& s, fl
     nf = f_max(nf, 0.0f);
     s.nprev = nf;
     return nf;
+}
+__device__ __forceinline__ float tracker_step(const DevParams& p, Tracker& s, float pk, bool allow) {
+    return tracker_step(p, s, pk, allow, p.trk_q, p.trk_nq);
 }
 __device__ __forceinline__ float tracker_first(const DevParams& p, Tracker& s, float pk) {
     s.trk = f_max(pk, 0.0f);
@@ -2014,11 +2018,14 @@ struct Trk2IO {
     float4* state;              // [plan clips][state_stride]: (trk, ts, nprev, warm-up count) between time segments
     int state_stride;
     int64_t nF;
+    double* aq_state;           // [plan clips] rain_prev_ema between time segments (adaptive quantile only)
 };
 
 // NT = CTA size of the launch (128: the compiler takes ~130 registers, three CTAs fit an SM; 256: see the launch site)
 // Frames [b.ta, b.tb) of every lane; ta == 0 starts the recursion, ta > 0 resumes from `state`.
-template <int NT>
+// AQ: adaptive tracker quantile (adaptive_q_enable).  Every lane of a clip carries the clip's scalar recursion
+// rain_ema <- alpha * rain_ema + (1 - alpha) * [frame excluded], in float64 like the reference's Python floats.
+template <int NT, bool AQ = false>
 __global__ void __launch_bounds__(NT) trk2_kernel(const __grid_constant__ DevParams p, Batch b, Trk2IO io) {
     const int K = p.K;
     const SerialLane L = serial_lane(b, K);
@@ -2029,14 +2036,25 @@ __global__ void __launch_bounds__(NT) trk2_kernel(const __grid_constant__ DevPar
     const int te = L.t_end;
     Tracker tr = {0, 0, 0};
     int warm;
+    double rain_ema = 0.0;
+    const double aq_1m = 1.0 - p.aq_alpha;
+    auto aq_q = [&](float& q, float& nq) {       // q_eff of the frame about to be processed (:634-638)
+        double qe = p.aq_base - (p.aq_base - p.aq_min) * rain_ema;
+        qe = qe < p.aq_min ? p.aq_min : (qe > p.aq_base ? p.aq_base : qe);
+        q = d2f(qe); nq = d2f(-(1.0 - qe));
+    };
+    auto aq_upd = [&](int8_t cls) { rain_ema = p.aq_alpha * rain_ema + aq_1m * (cls != 0 ? 1.0 : 0.0); };   // (:663-664)
     if (b.ta == 0) {
         // frame 0 counts as an update when it is allowed (rain_signal_processor.py:700-703)
-        warm = ((0 < p.warm_need) || (__ldg(fc) == 0)) ? 1 : 0;
+        const int8_t c0 = __ldg(fc);
+        warm = ((0 < p.warm_need) || (c0 == 0)) ? 1 : 0;
         const float n2 = tracker_first(p, tr, __ldg(Pk));
         if (L.store) Nk[0] = n2;
+        if (AQ) aq_upd(c0);
     } else {
         const float4 st = *stp;
         tr.trk = st.x; tr.ts = st.y; tr.nprev = st.z; warm = __float_as_int(st.w);
+        if (AQ) rain_ema = io.aq_state[L.c];
     }
     int t = max(b.ta, 1);
     const int tl = max(te - 1, 0);
@@ -2063,20 +2081,28 @@ __global__ void __launch_bounds__(NT) trk2_kernel(const __grid_constant__ DevPar
         for (int u = 0; u < SEQ_PF; u++) {
             // tracker pass 2: the quantile tracker only moves on warm-up frames and NOISE frames (:1006-1028)
             const bool allow = (warm < p.warm_need) || (ec[u] == 0);
-            const float n2 = tracker_step(p, tr, pc[u], allow);
+            float q = p.trk_q, nq = p.trk_nq;
+            if (AQ) aq_q(q, nq);
+            const float n2 = tracker_step(p, tr, pc[u], allow, q, nq);
+            if (AQ) aq_upd(ec[u]);
             warm += allow ? 1 : 0;
             if (L.store) Nk[(size_t)(t + u) * K] = n2;
         }
     }
     for (; t < L.emax; t++) {
         if (t < te) {
-            const bool allow = (warm < p.warm_need) || (__ldg(fc + t) == 0);
-            const float n2 = tracker_step(p, tr, __ldg(Pk + (size_t)t * K), allow);
+            const int8_t cls = __ldg(fc + t);
+            const bool allow = (warm < p.warm_need) || (cls == 0);
+            float q = p.trk_q, nq = p.trk_nq;
+            if (AQ) aq_q(q, nq);
+            const float n2 = tracker_step(p, tr, __ldg(Pk + (size_t)t * K), allow, q, nq);
+            if (AQ) aq_upd(cls);
             warm += allow ? 1 : 0;
             if (L.store) Nk[(size_t)t * K] = n2;
         }
     }
     if (L.store) *stp = make_float4(tr.trk, tr.ts, tr.nprev, __int_as_float(warm));
+    if (AQ && L.store && L.sub == 0) io.aq_state[L.c] = rain_ema;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -39,7 +39,7 @@ extern "C" {
 #define APT_N_TD_FEATURES 5   /* crest, kurtosis, block crest, block width50, block post/pre */
 #define APT_N_CLIP_STATS 8
 #define APT_MAX_GAIN_TAPS 9
-#define APT_ABI_VERSION 5
+#define APT_ABI_VERSION 6
 
 typedef struct apt_ctx apt_ctx;
 typedef struct apt_plan apt_plan_t;
@@ -110,6 +110,12 @@ typedef struct apt_params_t {
     int32_t peak_top_p, primary_top_m;
     double  peak_prominence_db, peak_min_db_above_floor, peak_ratio_min;
     float   peak_valid_prom_min_db, peak_valid_prom_max_db;
+    /* adaptive tracker quantile of the suppressor's noise-PSD pass (adaptive_q_enable, rain_signal_processor.py:570-576,
+     * :634-638, :663-664): q_eff = clip(q - (q - q_min) * rain_ema, q_min, q) with rain_ema the EMA (coefficient alpha) of
+     * the "frame excluded from the update" flags, all in float64, cast to float32 where it meets the step */
+    int32_t adaptive_q;
+    int32_t reserved0;
+    double  aq_base, aq_min, aq_alpha;
     /* host pointers, copied at plan creation */
     const double* window;                      /* n_fft analysis window (scipy get_window) */
     const float*  freqs;                       /* n_fft/2+1 bin frequencies as float32 */

@@ -78,7 +78,8 @@ typedef struct {
     int32_t low_lo, low_hi, rain_lo, rain_hi; /* inclusive bins; lo > hi == empty */
     double rolloff_fraction;
     int32_t suppressor_bypass;
-    int32_t reserved;
+    int32_t adaptive_q;                       /* adaptive_q_enable (rain_signal_processor.py:570-576, :634-638) */
+    double aq_base, aq_min, aq_alpha;
 } orc_params;
 
 typedef struct {
@@ -337,6 +338,7 @@ static void track_noise_psd(const orc_params *p, const float *P, int64_t T, int 
     const int K = p->band_hi - p->band_lo + 1;
     float *trk = malloc(sizeof(float) * K), *ts = malloc(sizeof(float) * K);
     int warm = 0;
+    double rain_ema = 0.0;                    /* rain_prev_ema: EMA of the excluded-frame flags, a Python float */
     for (int k = 0; k < K; k++) {
         float p0 = P[p->band_lo + k];
         trk[k] = fmaxf(p0, 0.0f);
@@ -353,15 +355,22 @@ static void track_noise_psd(const orc_params *p, const float *P, int64_t T, int 
                 float nb = fminf(trk[k], p->trk_maxr * Pt[k]);
                 Nt[k] = fmaxf(nb, 0.0f);
             }
+            rain_ema = p->aq_alpha * rain_ema + (1.0 - p->aq_alpha) * (excl ? 1.0 : 0.0);
             continue;
         }
         const float *Np = N + (t - 1) * K;
+        float qf = p->trk_q, nqf = p->trk_neg_one_minus_q;
+        if (p->adaptive_q) {                  /* q_eff is a Python float; numpy casts it to float32 at the product */
+            double q = p->aq_base - (p->aq_base - p->aq_min) * rain_ema;
+            q = q < p->aq_min ? p->aq_min : (q > p->aq_base ? p->aq_base : q);
+            qf = (float)q; nqf = (float)(-(1.0 - q));
+        }
         for (int k = 0; k < K; k++) {
             float pk = Pt[k];
             float err = pk - trk[k];
             ts[k] = p->trk_scale_alpha * ts[k] + p->trk_one_minus_alpha * fabsf(err);
             float step = p->trk_eta * fmaxf(ts[k], p->trk_step_floor);
-            float delta = (pk >= trk[k]) ? p->trk_q * step : p->trk_neg_one_minus_q * step;
+            float delta = (pk >= trk[k]) ? qf * step : nqf * step;
             float cand = fmaxf(trk[k] + delta, 0.0f);
             if (allow) trk[k] = cand;
             float raw = trk[k];
@@ -373,6 +382,7 @@ static void track_noise_psd(const orc_params *p, const float *P, int64_t T, int 
             Nt[k] = (float)nb;
         }
         if (allow) warm++;
+        rain_ema = p->aq_alpha * rain_ema + (1.0 - p->aq_alpha) * (excl ? 1.0 : 0.0);
     }
     free(trk); free(ts);
 }

@@ -56,6 +56,30 @@ def features_case():
     print(path, sorted(d), flush=True)
 
 
+def adaptive_q_cases():
+    """adaptive_q_enable (rain_signal_processor.py:570-576, :634-638): level-2 fixtures (every exported array), appended
+    to INDEX.json so that the oracle and GPU parity tests pick them up with the other fixtures."""
+    import json
+    idx_path = os.path.join(mg.OUT, "INDEX.json")
+    with open(idx_path) as f:
+        index = json.load(f)
+    for name, seconds, seed, lam, extra in (
+            ("alt_s33_l3_10s_adaptq", 10, 33, 3.0, {"adaptive_q_enable": True}),
+            ("alt_s34_l10_10s_adaptq", 10, 34, 10.0, {"adaptive_q_enable": True, "adaptive_q_min": 0.05, "adaptive_q_alpha": 0.9, "q": 0.3})):
+        pcm = synth_clip_i16(seconds, seed, lam)
+        metrics, state, params = mg.run_reference(pcm, seconds, extra, spectra=True)
+        d = mg.pack(pcm, seconds, seed, lam, metrics, state, level=2, params=params)
+        np.savez_compressed(os.path.join(mg.OUT, name + ".npz"), **d)
+        fc = d["frame_class"]
+        entry = {"name": name, "seconds": seconds, "seed": seed, "lam": lam, "level": 2, "T": int(fc.size),
+                 "rain": int((fc == 2).sum()), "uncertain": int((fc == 1).sum()), "noise": int((fc == 0).sum()), "extra": extra}
+        index = [e for e in index if e["name"] != name] + [entry]
+        print(entry, os.path.getsize(os.path.join(mg.OUT, name + ".npz")) // 1024, "KiB", flush=True)
+    with open(idx_path, "w") as f:
+        json.dump(index, f, indent=1)
+
+
 if __name__ == "__main__":
     main()
     features_case()
+    adaptive_q_cases()

@@ -59,7 +59,8 @@ class OrcParams(C.Structure):
         ("blk_len", C.c_int32), ("blk_hop", C.c_int32), ("blk_post_pre", C.c_int32), ("blk_smooth", C.c_int32),
         ("low_lo", C.c_int32), ("low_hi", C.c_int32), ("rain_lo", C.c_int32), ("rain_hi", C.c_int32),
         ("rolloff_fraction", C.c_double),
-        ("suppressor_bypass", C.c_int32), ("reserved", C.c_int32),
+        ("suppressor_bypass", C.c_int32), ("adaptive_q", C.c_int32),
+        ("aq_base", C.c_double), ("aq_min", C.c_double), ("aq_alpha", C.c_double),
     ]
 
 
@@ -105,8 +106,8 @@ def lib():
 # ----------------------------------------------------------------------------
 _CFG_DEFAULTS = dict(
     n_fft=256, hop=128, hp_cutoff_hz=350.0, hp_order=4, pre_filter_mode="highpass", bp_order=4,
-    operating_band=(400.0, 3500.0), q=0.25, win_sec=0.5, adaptive_q_enable=False,
-    median_frames=0, eps=1e-9, noise_psd_max_ratio=1.0, pre_smooth_frames=0, ema_up=0.6,
+    operating_band=(400.0, 3500.0), q=0.25, win_sec=0.5, adaptive_q_enable=False, adaptive_q_min=0.10,
+    adaptive_q_alpha=0.95, median_frames=0, eps=1e-9, noise_psd_max_ratio=1.0, pre_smooth_frames=0, ema_up=0.6,
     ema_down=0.95, detector_use_noise_norm=True, detector_noise_norm_mode="log_sub",
     suppressor_bypass=False, classifier_only_mode=False, process_dtype="float32")
 
@@ -136,7 +137,7 @@ def resolve(params):
             return cfg[name]
         return default
 
-    for flag, bad in (("adaptive_q_enable", True), ("process_dtype", "float64")):
+    for flag, bad in (("process_dtype", "float64"),):
         if cfg[flag] == bad:
             raise NotImplementedError(f"oracle: {flag}={bad!r} not restated")
     if int(cfg["median_frames"]) > 1 or int(cfg["pre_smooth_frames"]) > 1:
@@ -195,6 +196,10 @@ def make_params(params):
     P.trk_eta, P.trk_scale_alpha, P.trk_one_minus_alpha = f32(eta), f32(scale_alpha), f32(1.0 - scale_alpha)
     P.trk_step_floor, P.trk_q, P.trk_neg_one_minus_q, P.trk_maxr = f32(step_floor), f32(q), f32(-(1.0 - q)), f32(maxr)
     P.ema_up, P.ema_down = float(cfg["ema_up"]), float(cfg["ema_down"])
+    P.adaptive_q = int(bool(cfg["adaptive_q_enable"]))            # rain_signal_processor.py:570-576
+    P.aq_base = q
+    P.aq_min = float(np.clip(float(cfg["adaptive_q_min"]), 1e-4, q))
+    P.aq_alpha = float(np.clip(float(cfg["adaptive_q_alpha"]), 0.0, 1.0))
     P.warmup_need = max(10, W // 2)
     P.eps_f32 = f32(cfg["eps"])
     P.detector_use_noise_norm = int(bool(dget("detector_use_noise_norm", True)))

@@ -244,7 +244,7 @@ def test_host_path_and_errors(torch_cuda):
     with pytest.raises(AttributeError):
         proc.run(np.zeros(6 * 11162, np.float32), {"sample_rate": 11162, "check_duration": 6})
     with pytest.raises(NotImplementedError):
-        proc.run(np.zeros(6 * 11162, np.float32), dict(params, adaptive_q_enable=True))
+        proc.run(np.zeros(6 * 11162, np.float32), dict(params, median_frames=3))
 
 
 @pytest.mark.parametrize("n_fft,hop", [(256, 64), (512, 256), (1024, 256), (2048, 1024), (4096, 1024)])
@@ -520,3 +520,26 @@ def test_rain_processor_run_batch_uses_the_gpu_batch(torch_cuda):
     for (r1, s1), (r2, s2) in zip(single, batch):
         assert r1["rain_drops"] == r2["rain_drops"] and r1["rain_drop_count"] == r2["rain_drop_count"]
         assert np.array_equal(s1["raining"], s2["raining"])
+
+
+def test_adaptive_q_across_time_segments(torch_cuda, oracle_mod):
+    """adaptive_q_enable on clips long enough for several time segments (the clip's rain EMA is carried between the
+    segments of the pipelined run): the suppressor's noise PSD equals the oracle's bit for bit, ragged batch."""
+    from audio_processing_tools_b200.synth import default_params, synth_clip_i16
+    params = default_params(check_duration=60, adaptive_q_enable=True, adaptive_q_min=0.08, adaptive_q_alpha=0.97)
+    clips = [synth_clip_i16(95.0, 71, 10.0), synth_clip_i16(61.5, 72, 3.0), synth_clip_i16(140.0, 73, 0.5)]
+    eng = make_engine(params)
+    plan, out = eng.run_clips(clips, ("noise_psd",))
+    for c, pcm in enumerate(clips):
+        f0, f1 = int(plan.frame_off[c]), int(plan.frame_off[c + 1])
+        m, s = oracle_mod.run(pcm_to_f32(pcm), dict(params, keep_state_debug=True))
+        assert np.array_equal(out["frame_class"][f0:f1], s["frame_class"])
+        assert np.array_equal(out["noise_psd"][f0:f1], s["N2_band"])
+        assert out["clip_stats"][c][6] == pytest.approx(m["mean_noise_floor_db"], rel=1e-6)
+        assert out["clip_stats"][c][7] == pytest.approx(m["median_noise_floor_db"], rel=1e-6)
+    # and it is not the fixed-q result
+    eng0 = make_engine(default_params(check_duration=60))
+    _, out0 = eng0.run_clips(clips, ("noise_psd",))
+    assert not np.array_equal(out0["noise_psd"], out["noise_psd"])
+    eng.close()
+    eng0.close()
