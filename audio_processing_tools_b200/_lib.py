@@ -17,8 +17,9 @@ LIB_PATH = os.path.join(_PKG, "libapt_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 MAX_MODES, MAX_SOS, N_RAW, N_TD, N_STATS = 8, 4, 21, 5, 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_GAIN_TAPS = 9
+MAX_PRE_SMOOTH, MAX_MEDIAN = 16, 31
 STAGE_FEATURES, STAGE_FULL = 1, 2
 KERNEL_NAMES = ("stft256_kernel", "td_features_kernel", "trk1_kernel", "flux_kernel", "base_kernel",
                 "decide_kernels", "trk2_kernel", "db_kernel", "select_kernels", "finalize_kernel", "gain_kernels")
@@ -62,8 +63,9 @@ class AptParams(C.Structure):
         ("peak_top_p", C.c_int32), ("primary_top_m", C.c_int32),
         ("peak_prominence_db", C.c_double), ("peak_min_db_above_floor", C.c_double), ("peak_ratio_min", C.c_double),
         ("peak_valid_prom_min_db", C.c_float), ("peak_valid_prom_max_db", C.c_float),
-        ("adaptive_q", C.c_int32), ("reserved0", C.c_int32),
+        ("adaptive_q", C.c_int32), ("pre_smooth_frames", C.c_int32),
         ("aq_base", C.c_double), ("aq_min", C.c_double), ("aq_alpha", C.c_double),
+        ("median_frames", C.c_int32), ("reserved1", C.c_int32),
         ("window", C.c_void_p), ("freqs", C.c_void_p),
     ]
 

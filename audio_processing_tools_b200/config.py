@@ -174,8 +174,9 @@ class ResolvedParams:
                 raise NotImplementedError(f"detector.{flag}=True is not implemented on the CUDA path")
         if str(cfg.process_dtype).lower() != "float32":
             raise NotImplementedError("process_dtype='float64' is not implemented on the CUDA path")
-        if int(cfg.median_frames or 0) > 1 or int(cfg.pre_smooth_frames or 0) > 1:
-            raise NotImplementedError("median_frames / pre_smooth_frames > 1 are not implemented on the CUDA path")
+        if int(cfg.pre_smooth_frames or 0) > _lib.MAX_PRE_SMOOTH or int(cfg.median_frames or 0) > _lib.MAX_MEDIAN - 1:
+            raise NotImplementedError(f"pre_smooth_frames > {_lib.MAX_PRE_SMOOTH} / median_frames > {_lib.MAX_MEDIAN - 1} "
+                                      "are not implemented on the CUDA path")
         if str(dv.get("td_input_mode", "default")).lower() != "default":
             raise NotImplementedError("td_input_mode other than 'default' is not implemented on the CUDA path")
         if int(dv.get("feature_dump_level", 0)) > 0:
@@ -242,6 +243,8 @@ class ResolvedParams:
         P.aq_base = q
         P.aq_min = float(np.clip(float(cfg.adaptive_q_min), 1e-4, q))
         P.aq_alpha = float(np.clip(float(cfg.adaptive_q_alpha), 0.0, 1.0))
+        P.pre_smooth_frames = int(cfg.pre_smooth_frames or 0)      # rain_signal_processor.py:690-692
+        P.median_frames = int(cfg.median_frames or 0)              # :717-719
         P.ema_up, P.ema_down = float(cfg.ema_up), float(cfg.ema_down)
         P.warmup_need = max(10, W // 2)
         P.eps_f32 = f32(cfg.eps)

@@ -130,6 +130,9 @@ struct apt_plan {
     DevBuf<float4> d_st_trk1, d_st_trk2;   // [clips][K]
     DevBuf<double2> d_st_base;             // [clips][APT_MAX_MODES + 1]
     DevBuf<double> d_st_aq;                // [clips] rain_prev_ema of the adaptive tracker quantile
+    // optional smoothing around the tracker passes (pre_smooth_frames / median_frames): smoothed band power and its carried
+    // state, raw pass-1 / pass-2 planes ahead of the median, filtered pass-1 plane
+    DevBuf<float> d_Psm, d_st_ps, d_N1raw, d_N1med, d_N2raw;
     // candidate lists of the median select
     std::vector<int64_t> cand_off;
     DevBuf<int64_t> d_cand_off;
@@ -359,6 +362,13 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     d.trk_q = p->trk_q; d.trk_nq = p->trk_neg_one_minus_q; d.trk_maxr = p->trk_maxr;
     d.ema_up = p->ema_up; d.ema_down = p->ema_down; d.warm_need = p->warmup_need; d.eps32 = p->eps_f32;
     d.adaptive_q = p->adaptive_q; d.aq_base = p->aq_base; d.aq_min = p->aq_min; d.aq_alpha = p->aq_alpha;
+    d.pre_smooth = p->pre_smooth_frames > 1 ? p->pre_smooth_frames : 0;
+    d.median = p->median_frames > 1 ? p->median_frames : 0;
+    if (d.pre_smooth > APT_MAX_PRE_SMOOTH || d.median + ((d.median & 1) == 0 ? 1 : 0) > APT_MAX_MEDIAN) {
+        apt_plan_destroy(pl);
+        return fail(ctx, -26, "pre_smooth_frames=%d (max %d) / median_frames=%d (max %d) unsupported", p->pre_smooth_frames, APT_MAX_PRE_SMOOTH,
+                    p->median_frames, APT_MAX_MEDIAN - 1);
+    }
     d.use_norm = p->detector_use_noise_norm; d.ratio_db = p->norm_ratio_db;
     d.bl_q = p->bl_q; d.bl_eta = p->bl_eta; d.bl_alpha = p->bl_scale_alpha; d.bl_floor = p->bl_floor;
     d.norm_enable = p->norm_enable; d.norm_min = p->norm_min_f32;
@@ -584,6 +594,12 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     PL_OK(pl->d_st_trk2.alloc((size_t)n_clips * pl->st_stride));
     PL_OK(pl->d_st_base.alloc((size_t)n_clips * (APT_MAX_MODES + 1)));
     PL_OK(pl->d_st_aq.alloc((size_t)n_clips));
+    if (d.pre_smooth) {
+        PL_OK(pl->d_Psm.alloc((size_t)pl->nF * K));
+        PL_OK(pl->d_st_ps.alloc((size_t)n_clips * pl->st_stride * PS_STATE));
+    }
+    if (d.pre_smooth || d.median) PL_OK(pl->d_N1raw.alloc((size_t)pl->nF * K));
+    if (d.median) { PL_OK(pl->d_N1med.alloc((size_t)pl->nF * K)); PL_OK(pl->d_N2raw.alloc((size_t)pl->nF * K)); }
     {   // candidate lists of the median select: an eighth of the plane per clip (a 1/16 dB bin holds ~1 % of a clip's
         // values; clips that overflow fall back to the full radix select)
         pl->cand_off.assign(n_clips + 1, 0);
@@ -948,6 +964,17 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     const Trk1Tab& tab = dbg ? pl->tab_all : pl->tab_modes;
     float* nl_plane = dbg ? pl->d_nl_all.p : pl->d_nl.p;
     float* n2_plane = out->noise_psd ? out->noise_psd : pl->d_n2.p;
+    // optional smoothing: the trackers read the smoothed power; pass 1's result goes through the median and a lag / clamp
+    // pass of its own, pass 2's through the median
+    const bool PS = d.pre_smooth > 1, MED = d.median > 1, post1 = PS || MED;
+    const float* trk_in = PS ? pl->d_Psm.p : pl->d_Pband.p;
+    float* n1_raw = !post1 ? out->det_noise_psd : (MED ? pl->d_N1raw.p : (out->det_noise_psd ? out->det_noise_psd : pl->d_N1raw.p));
+    float* n1_fin = MED ? (out->det_noise_psd ? out->det_noise_psd : pl->d_N1med.p) : n1_raw;
+    float* n2_raw = MED ? pl->d_N2raw.p : n2_plane;
+    auto frame_lane_grid = [&](const Batch& bb, int lanes_) {
+        const int64_t fr = std::max<int64_t>(0, std::min<int64_t>(maxT - bb.ta, n_seg == 1 ? maxT : (int64_t)seg_frames));
+        return dim3((unsigned)((fr * lanes_ + 255) / 256), (unsigned)n_clips);
+    };
     uint32_t* hist = pl->d_hist.p;
     const size_t hist_bytes = sizeof(uint32_t) * (size_t)n_clips * 2 * SEL_BINS;
     TdOut to;
@@ -1070,9 +1097,20 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         }
         // tracker pass 1 on the mode bins (every band bin when one of its planes is requested)
         pl->mark(APT_KERNEL_TRK1, st);
+        if (PS) {
+            const int64_t lanes = (int64_t)n_clips * d.K;
+            RR(wait(apt_plan::SK_TRK1, apt_plan::SK_STFT, sg));
+            if (e == cudaSuccess) {
+                presmooth_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, S[apt_plan::SK_TRK1]>>>(pl->dp, bs, pl->d_Pband.p, pl->d_Psm.p,
+                                                                                                   pl->d_st_ps.p, pl->st_stride);
+                pl->last_launches++;
+                RR(cudaGetLastError());
+            }
+            if (!d.use_norm) RR(rec(apt_plan::SK_TRK1, sg));
+        }
         if (d.use_norm) {
             Trk1IO io;
-            io.P_band = pl->d_Pband.p; io.NL = nl_plane; io.det_noise_psd = out->det_noise_psd; io.nF = pl->nF;
+            io.P_band = trk_in; io.NL = nl_plane; io.det_noise_psd = n1_raw; io.nF = pl->nF;
             io.state = pl->d_st_trk1.p; io.state_stride = pl->st_stride;
             const int64_t lanes = (int64_t)n_clips * tab.n_lanes;
             RR(wait(apt_plan::SK_TRK1, apt_plan::SK_STFT, sg));
@@ -1081,6 +1119,15 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
                 trk1_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, S[apt_plan::SK_TRK1]>>>(pl->dp, bs, tab, io);
                 pl->last_launches++;
                 RR(cudaGetLastError());
+            }
+            if (post1 && e == cudaSuccess) {
+                const dim3 g = frame_lane_grid(bs, tab.n_lanes);
+                if (g.x > 0) {
+                    if (MED) { median_time_kernel<<<g, 256, 0, S[apt_plan::SK_TRK1]>>>(pl->dp, bs, tab, n1_raw, n1_fin); pl->last_launches++; }
+                    lag_clamp_kernel<<<g, 256, 0, S[apt_plan::SK_TRK1]>>>(pl->dp, bs, tab, n1_fin, pl->d_Pband.p, nl_plane, tab.nls);
+                    pl->last_launches++;
+                    RR(cudaGetLastError());
+                }
             }
             RR(rec(apt_plan::SK_TRK1, sg));
         }
@@ -1141,7 +1188,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             // tracker pass 2, then the noise-floor dB sums and histogram of the segment
             pl->mark(APT_KERNEL_TRK2, st);
             Trk2IO io;
-            io.P_band = pl->d_Pband.p; io.frame_class = out->frame_class; io.N2 = n2_plane; io.nF = pl->nF;
+            io.P_band = trk_in; io.frame_class = out->frame_class; io.N2 = n2_raw; io.nF = pl->nF;
             io.state = pl->d_st_trk2.p; io.state_stride = pl->st_stride; io.aq_state = pl->d_st_aq.p;
             const int64_t lanes = (int64_t)n_clips * d.K;
             // Every lane runs the whole time chain, so the kernel's time is (waves of CTAs) x (chain time at that
@@ -1152,6 +1199,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             // are faster there when the kernel has the GPU to itself (1 000 x 71 lanes: 10.8 -> 9.7 ms).
             const double warps_per_sm = (double)((lanes + 31) / 32) / (double)std::max(1, ctx->sm_count);
             RR(wait(apt_plan::SK_TRK2, apt_plan::SK_DEC, sg));
+            if (PS && !d.use_norm) RR(wait(apt_plan::SK_TRK2, apt_plan::SK_TRK1, sg));
             tmark(apt_plan::SK_TRK2, sg, 0);
             if (e == cudaSuccess) {
                 if (d.adaptive_q) {
@@ -1164,6 +1212,14 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
                 }
                 pl->last_launches++;
                 RR(cudaGetLastError());
+                if (MED && e == cudaSuccess) {
+                    const dim3 g = frame_lane_grid(bs, pl->tab_all.n_lanes);
+                    if (g.x > 0) {
+                        median_time_kernel<<<g, 256, 0, S[apt_plan::SK_TRK2]>>>(pl->dp, bs, pl->tab_all, n2_raw, n2_plane);
+                        pl->last_launches++;
+                        RR(cudaGetLastError());
+                    }
+                }
             }
             RR(rec(apt_plan::SK_TRK2, sg));
             pl->mark(APT_KERNEL_DB, st);

@@ -48,6 +48,7 @@ struct DevParams {
     float trk_eta, trk_alpha, trk_1m_alpha, trk_floor, trk_q, trk_nq, trk_maxr;
     double ema_up, ema_down;
     int adaptive_q; double aq_base, aq_min, aq_alpha;   // adaptive quantile of pass 2
+    int pre_smooth, median;                              // pre_smooth_frames / median_frames (<= 1: off)
     int warm_need;
     float eps32;
     int use_norm, ratio_db;
@@ -1727,6 +1728,84 @@ __global__ void __launch_bounds__(128) trk1_kernel(const __grid_constant__ DevPa
         }
     }
     if (L.store) *stp = make_float4(tr.trk, tr.ts, tr.nprev, 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Optional smoothing around the tracker passes (off by default; rain_signal_processor.py:366-396, :690-692, :717-719)
+// ---------------------------------------------------------------------------------------------
+constexpr int PS_STATE = APT_MAX_PRE_SMOOTH + 1;    // floats of carried state per lane: running sum + ring of past sums
+
+// pre_smooth_frames = L: moving average of the band power over the last L frames from a float32 cumulative sum
+// (np.cumsum is sequential in time).  lane = (clip, band bin), frames [b.ta, b.tb), state carried between segments.
+__global__ void __launch_bounds__(128) presmooth_kernel(const __grid_constant__ DevParams p, Batch b, const float* __restrict__ P_band,
+                                                        float* __restrict__ Psm, float* __restrict__ state, int state_stride) {
+    const int K = p.K, Lw = p.pre_smooth;
+    const SerialLane L = serial_lane(b, K);
+    const float* Pk = P_band + L.f0 * K + L.sub;
+    float* Yk = Psm + L.f0 * K + L.sub;
+    float* stp = state + ((size_t)L.c * state_stride + L.sub) * PS_STATE;
+    float ring[APT_MAX_PRE_SMOOTH];
+    float cs = 0.0f;
+    if (b.ta > 0) {
+        cs = stp[0];
+        for (int i = 0; i < Lw; i++) ring[i] = stp[1 + i];
+    }
+    for (int t = b.ta; t < L.t_end; t++) {
+        const float pk = __ldg(Pk + (size_t)t * K);
+        const int slot = t % Lw;
+        const float old = ring[slot];                       // csum[t - L] once t >= L
+        cs = (t == 0) ? pk : cs + pk;
+        const float y = (t < Lw) ? f_div(cs, (float)(t + 1)) : f_div(cs - old, (float)Lw);
+        ring[slot] = cs;
+        if (L.store) Yk[(size_t)t * K] = y;
+    }
+    if (L.store) {
+        stp[0] = cs;
+        for (int i = 0; i < Lw; i++) stp[1 + i] = ring[i];
+    }
+}
+
+// median_frames = L (made odd): Y[t] = np.median(X[max(0, t-L+1) .. t]) per column; even counts (clip start) average the two
+// middle values in float32.  Columns = the lanes of `tab` (mode bins or every band bin), planes [nF][K] indexed by band bin.
+// grid.x covers (frames of the launch) x lanes, grid.y = clip.
+__global__ void __launch_bounds__(256) median_time_kernel(const __grid_constant__ DevParams p, Batch b, const __grid_constant__ Trk1Tab tab,
+                                                          const float* __restrict__ X, float* __restrict__ Y) {
+    const int c = b.clip0 + (int)blockIdx.y;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int nl = tab.n_lanes, K = p.K;
+    int Lw = p.median; if ((Lw & 1) == 0) Lw += 1;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = b.ta + (int)(idx / nl), j = (int)(idx % nl);
+    if (t >= min(T, b.tb)) return;
+    const int kb = tab.bin_of(j);
+    const int t0 = max(0, t - Lw + 1), n = t - t0 + 1;
+    float w[APT_MAX_MEDIAN];
+    for (int i = 0; i < n; i++) {                            // insertion sort of the window
+        const float v = __ldg(X + (f0 + t0 + i) * K + kb);
+        int q = i - 1;
+        while (q >= 0 && w[q] > v) { w[q + 1] = w[q]; q--; }
+        w[q + 1] = v;
+    }
+    Y[(f0 + t) * K + kb] = (n & 1) ? w[n >> 1] : f_div(w[(n >> 1) - 1] + w[n >> 1], 2.0f);
+}
+
+// Lag by one frame and clamp to the current power (rain_signal_processor.py:874-882) as a pass of its own, for the runs in
+// which pass 1's result is post-processed (median) or its input is not the power itself (pre-smoothing):
+// NL[t][j] = min(N1[max(t-1, 0)][bin_j], maxr * P[t][bin_j]).
+__global__ void __launch_bounds__(256) lag_clamp_kernel(const __grid_constant__ DevParams p, Batch b, const __grid_constant__ Trk1Tab tab,
+                                                        const float* __restrict__ N1, const float* __restrict__ P_band,
+                                                        float* __restrict__ NL, int nls) {
+    const int c = b.clip0 + (int)blockIdx.y;
+    const int64_t f0 = __ldg(b.frame_off + c);
+    const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
+    const int nl = tab.n_lanes, K = p.K;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = b.ta + (int)(idx / nl), j = (int)(idx % nl);
+    if (t >= min(T, b.tb)) return;
+    const int kb = tab.bin_of(j);
+    const float n1 = __ldg(N1 + (f0 + max(t - 1, 0)) * K + kb);
+    NL[(f0 + t) * nls + j] = f_min(n1, p.trk_maxr * __ldg(P_band + (f0 + t) * K + kb));
 }
 
 struct FluxIO {

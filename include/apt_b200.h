@@ -38,8 +38,10 @@ extern "C" {
 #define APT_N_RAW_FEATURES 21 /* feature_extraction.py:9-31 RAW_SPECTRAL_FEATURE_NAMES */
 #define APT_N_TD_FEATURES 5   /* crest, kurtosis, block crest, block width50, block post/pre */
 #define APT_N_CLIP_STATS 8
+#define APT_MAX_PRE_SMOOTH 16
+#define APT_MAX_MEDIAN 31
 #define APT_MAX_GAIN_TAPS 9
-#define APT_ABI_VERSION 6
+#define APT_ABI_VERSION 7
 
 typedef struct apt_ctx apt_ctx;
 typedef struct apt_plan apt_plan_t;
@@ -114,8 +116,13 @@ typedef struct apt_params_t {
      * :634-638, :663-664): q_eff = clip(q - (q - q_min) * rain_ema, q_min, q) with rain_ema the EMA (coefficient alpha) of
      * the "frame excluded from the update" flags, all in float64, cast to float32 where it meets the step */
     int32_t adaptive_q;
-    int32_t reserved0;
+    /* moving average over time of the band power before both tracker passes (pre_smooth_frames, :366-379, :690-692;
+     * float32 cumulative sum like np.cumsum), <= 1: off, at most APT_MAX_PRE_SMOOTH */
+    int32_t pre_smooth_frames;
     double  aq_base, aq_min, aq_alpha;
+    /* causal median over time of both passes' noise PSD (median_frames, :381-396, :717-719), <= 1: off, at most APT_MAX_MEDIAN */
+    int32_t median_frames;
+    int32_t reserved1;
     /* host pointers, copied at plan creation */
     const double* window;                      /* n_fft analysis window (scipy get_window) */
     const float*  freqs;                       /* n_fft/2+1 bin frequencies as float32 */

@@ -80,6 +80,8 @@ typedef struct {
     int32_t suppressor_bypass;
     int32_t adaptive_q;                       /* adaptive_q_enable (rain_signal_processor.py:570-576, :634-638) */
     double aq_base, aq_min, aq_alpha;
+    int32_t pre_smooth_frames;                /* _time_smooth before the tracker (:366-379, :690-692); <= 1: off */
+    int32_t median_frames;                    /* _causal_time_median_filter after it (:381-396, :717-719); <= 1: off */
 } orc_params;
 
 typedef struct {
@@ -332,10 +334,34 @@ static void stft_power(const orc_params *p, const double *win, const float *x, i
 /* exclude[t] != 0  <=> is_rain_for_psd[t]                              */
 /* P: [T][F]; N out: [T][K]                                             */
 /* ------------------------------------------------------------------ */
-static void track_noise_psd(const orc_params *p, const float *P, int64_t T, int F,
+static int cmp_f32(const void *a, const void *b) { float x = *(const float *)a, y = *(const float *)b; return (x > y) - (x < y); }
+
+static void track_noise_psd(const orc_params *p, const float *P_in, int64_t T, int F_in,
                             const uint8_t *exclude, float *N)
 {
     const int K = p->band_hi - p->band_lo + 1;
+    const float *P = P_in;
+    int F = F_in;
+    float *Y = NULL;
+    if (p->pre_smooth_frames > 1) {
+        /* moving average from a float32 cumulative sum over time (np.cumsum is sequential), band bins only */
+        const int L = p->pre_smooth_frames;
+        float *cs = malloc(sizeof(float) * T * K);
+        Y = malloc(sizeof(float) * T * K);
+        for (int k = 0; k < K; k++) {
+            float acc = 0.0f;
+            for (int64_t t = 0; t < T; t++) {
+                acc = (t == 0) ? P_in[p->band_lo + k] : acc + P_in[t * F_in + p->band_lo + k];
+                cs[t * K + k] = acc;
+                int64_t t0 = t - L + 1 > 0 ? t - L + 1 : 0;
+                Y[t * K + k] = (t0 == 0) ? cs[t * K + k] / (float)(t + 1)
+                                         : (cs[t * K + k] - cs[(t0 - 1) * K + k]) / (float)(t - t0 + 1);
+            }
+        }
+        free(cs);
+        P = Y - p->band_lo;      /* rows of K values: the code below reads P[t * F + band_lo + k] */
+        F = K;
+    }
     float *trk = malloc(sizeof(float) * K), *ts = malloc(sizeof(float) * K);
     int warm = 0;
     double rain_ema = 0.0;                    /* rain_prev_ema: EMA of the excluded-frame flags, a Python float */
@@ -385,6 +411,25 @@ static void track_noise_psd(const orc_params *p, const float *P, int64_t T, int 
         rain_ema = p->aq_alpha * rain_ema + (1.0 - p->aq_alpha) * (excl ? 1.0 : 0.0);
     }
     free(trk); free(ts);
+    free(Y);
+    if (p->median_frames > 1) {
+        /* causal median over time per bin, window [max(0, t - L + 1), t], L made odd; np.median: even counts average
+         * the two middle values in float32 */
+        int L = p->median_frames;
+        if (L % 2 == 0) L += 1;
+        float *R = malloc(sizeof(float) * T * K), *w = malloc(sizeof(float) * L);
+        memcpy(R, N, sizeof(float) * T * K);
+        for (int64_t t = 0; t < T; t++) {
+            int64_t t0 = t - L + 1 > 0 ? t - L + 1 : 0;
+            int n = (int)(t - t0 + 1);
+            for (int k = 0; k < K; k++) {
+                for (int i = 0; i < n; i++) w[i] = R[(t0 + i) * K + k];
+                qsort(w, n, sizeof(float), cmp_f32);
+                N[t * K + k] = (n & 1) ? w[n / 2] : (w[n / 2 - 1] + w[n / 2]) / 2.0f;
+            }
+        }
+        free(R); free(w);
+    }
 }
 
 /* ------------------------------------------------------------------ */

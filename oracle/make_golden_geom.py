@@ -79,7 +79,32 @@ def adaptive_q_cases():
         json.dump(index, f, indent=1)
 
 
+def smoothing_cases():
+    """pre_smooth_frames / median_frames (rain_signal_processor.py:366-396, :690-692, :717-719): level-1 fixtures (labels,
+    per-frame detector features, clip statistics); both options move the labels through the detector's noise baseline."""
+    import json
+    idx_path = os.path.join(mg.OUT, "INDEX.json")
+    with open(idx_path) as f:
+        index = json.load(f)
+    for name, seconds, seed, lam, extra in (
+            ("alt_s35_l3_20s_presmooth3", 20, 35, 3.0, {"pre_smooth_frames": 3}),
+            ("alt_s36_l10_20s_median5", 20, 36, 10.0, {"median_frames": 5}),
+            ("alt_s37_l3_20s_smooth_all", 20, 37, 3.0, {"pre_smooth_frames": 4, "median_frames": 4, "adaptive_q_enable": True})):
+        pcm = synth_clip_i16(seconds, seed, lam)
+        metrics, state, params = mg.run_reference(pcm, seconds, extra)
+        d = mg.pack(pcm, seconds, seed, lam, metrics, state, level=1, params=params)
+        np.savez_compressed(os.path.join(mg.OUT, name + ".npz"), **d)
+        fc = d["frame_class"]
+        entry = {"name": name, "seconds": seconds, "seed": seed, "lam": lam, "level": 1, "T": int(fc.size),
+                 "rain": int((fc == 2).sum()), "uncertain": int((fc == 1).sum()), "noise": int((fc == 0).sum()), "extra": extra}
+        index = [e for e in index if e["name"] != name] + [entry]
+        print(entry, os.path.getsize(os.path.join(mg.OUT, name + ".npz")) // 1024, "KiB", flush=True)
+    with open(idx_path, "w") as f:
+        json.dump(index, f, indent=1)
+
+
 if __name__ == "__main__":
     main()
     features_case()
     adaptive_q_cases()
+    smoothing_cases()

@@ -61,6 +61,7 @@ class OrcParams(C.Structure):
         ("rolloff_fraction", C.c_double),
         ("suppressor_bypass", C.c_int32), ("adaptive_q", C.c_int32),
         ("aq_base", C.c_double), ("aq_min", C.c_double), ("aq_alpha", C.c_double),
+        ("pre_smooth_frames", C.c_int32), ("median_frames", C.c_int32),
     ]
 
 
@@ -140,8 +141,6 @@ def resolve(params):
     for flag, bad in (("process_dtype", "float64"),):
         if cfg[flag] == bad:
             raise NotImplementedError(f"oracle: {flag}={bad!r} not restated")
-    if int(cfg["median_frames"]) > 1 or int(cfg["pre_smooth_frames"]) > 1:
-        raise NotImplementedError("oracle: median_frames / pre_smooth_frames not restated")
     for name in ("peak_features_enable", "flux_modes_winsor_enable", "td_envelope_features_enable",
                  "bypass_classifier"):
         if bool(dget(name, False)):
@@ -200,6 +199,8 @@ def make_params(params):
     P.aq_base = q
     P.aq_min = float(np.clip(float(cfg["adaptive_q_min"]), 1e-4, q))
     P.aq_alpha = float(np.clip(float(cfg["adaptive_q_alpha"]), 0.0, 1.0))
+    P.pre_smooth_frames = int(cfg["pre_smooth_frames"] or 0)      # rain_signal_processor.py:690-692
+    P.median_frames = int(cfg["median_frames"] or 0)              # :717-719
     P.warmup_need = max(10, W // 2)
     P.eps_f32 = f32(cfg["eps"])
     P.detector_use_noise_norm = int(bool(dget("detector_use_noise_norm", True)))

@@ -244,7 +244,7 @@ def test_host_path_and_errors(torch_cuda):
     with pytest.raises(AttributeError):
         proc.run(np.zeros(6 * 11162, np.float32), {"sample_rate": 11162, "check_duration": 6})
     with pytest.raises(NotImplementedError):
-        proc.run(np.zeros(6 * 11162, np.float32), dict(params, median_frames=3))
+        proc.run(np.zeros(6 * 11162, np.float32), dict(params, snr_gating_enable=True))
 
 
 @pytest.mark.parametrize("n_fft,hop", [(256, 64), (512, 256), (1024, 256), (2048, 1024), (4096, 1024)])
@@ -543,3 +543,29 @@ def test_adaptive_q_across_time_segments(torch_cuda, oracle_mod):
     assert not np.array_equal(out0["noise_psd"], out["noise_psd"])
     eng.close()
     eng0.close()
+
+
+@pytest.mark.parametrize("extra", [{"pre_smooth_frames": 3}, {"median_frames": 5}, {"median_frames": 8, "pre_smooth_frames": 16},
+                                   {"pre_smooth_frames": 4, "median_frames": 4, "adaptive_q_enable": True}])
+def test_tracker_smoothing_options_across_time_segments(torch_cuda, oracle_mod, extra):
+    """pre_smooth_frames / median_frames on clips long enough for several time segments (cumulative sums, ring and median
+    windows cross the segment borders), ragged batch: labels, both passes' noise PSD planes and the lagged baseline equal
+    the oracle's bit for bit (the oracle equals the reference on the alt_*_presmooth / median fixtures)."""
+    from audio_processing_tools_b200.synth import default_params, synth_clip_i16
+    params = default_params(check_duration=60, **extra)
+    clips = [synth_clip_i16(95.0, 81, 10.0), synth_clip_i16(61.5, 82, 3.0), synth_clip_i16(130.0, 83, 0.5)]
+    eng = make_engine(params)
+    plan, out = eng.run_clips(clips, ("noise_psd", "det_noise_psd", "det_noise_lag"))
+    for c, pcm in enumerate(clips):
+        f0, f1 = int(plan.frame_off[c]), int(plan.frame_off[c + 1])
+        m, s = oracle_mod.run(pcm_to_f32(pcm), dict(params, keep_state_debug=True))
+        assert np.array_equal(out["det_noise_psd"][f0:f1], s["N1_band"])
+        assert np.array_equal(out["det_noise_lag"][f0:f1], s["Nlag_band"])
+        assert np.array_equal(out["frame_class"][f0:f1], s["frame_class"])
+        assert np.array_equal(out["noise_psd"][f0:f1], s["N2_band"])
+        assert out["clip_stats"][c][7] == pytest.approx(m["median_noise_floor_db"], rel=1e-6)
+    # default flags (mode-bin lanes only, no debug planes): same labels
+    plan2, out2 = eng.run_clips(clips, ())
+    assert np.array_equal(out2["frame_class"], out["frame_class"])
+    assert np.array_equal(out2["clip_stats"], out["clip_stats"])
+    eng.close()
