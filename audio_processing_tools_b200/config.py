@@ -328,8 +328,24 @@ class ResolvedParams:
         # --- suppressor gain (_compute_gain, rain_signal_processor.py:400-533).  noise_conf is binary on this
         # path (1 - rain_conf), so the per-frame scalars take two values; they are formed here with the same
         # numpy float32 / Python-float promotions the reference applies.
-        if bool(cfg.snr_gating_enable):
-            raise NotImplementedError("snr_gating_enable=True is not implemented on the CUDA path")
+        P.snr_gating = int(bool(cfg.snr_gating_enable))           # rain_signal_processor.py:1050-1077
+        if P.snr_gating:
+            pwr = float(cfg.snr_gating_power)
+            if pwr != 1.0 and np.isfinite(pwr) and pwr > 0.0:
+                raise NotImplementedError("snr_gating_power != 1 is not implemented on the CUDA path")
+            Kb = int(P.band_hi - P.band_lo + 1)
+            if Kb > 128:
+                raise NotImplementedError("snr_gating_enable needs an operating band of at most 128 bins")
+            mask = np.zeros(Kb, dtype=bool)
+            if bool(cfg.snr_gating_use_mode_bands):
+                for i in range(int(P.n_modes)):
+                    if P.mode_band_lo[i] <= P.mode_band_hi[i]:
+                        mask[P.mode_band_lo[i]:P.mode_band_hi[i] + 1] = True
+            if not mask.any():
+                mask[:] = True
+            for k in np.flatnonzero(mask):
+                P.snr_mask[int(k) >> 5] |= (1 << (int(k) & 31))
+            P.snr_gating_snr1 = f32(max(1e-9, float(cfg.snr_gating_snr1)))
         mode = str(cfg.gain_mode).lower()
         P.gain_mode = 1 if mode == "wiener" else 0
         P.adaptive_gain = int(bool(cfg.adaptive_gain_enable))

@@ -49,6 +49,7 @@ struct DevParams {
     double ema_up, ema_down;
     int adaptive_q; double aq_base, aq_min, aq_alpha;   // adaptive quantile of pass 2
     int pre_smooth, median;                              // pre_smooth_frames / median_frames (<= 1: off)
+    int snr_gate; float snr1; uint32_t snr_mask[4];      // spectral SNR gating of the oversubtraction
     int warm_need;
     float eps32;
     int use_norm, ratio_db;
@@ -2315,6 +2316,8 @@ __global__ void __launch_bounds__(256) gain_kernel(const __grid_constant__ DevPa
                                                    const int64_t* __restrict__ tile_off, GainIO io) {
     __shared__ float s_g[GAIN_FT][SEQ_KMAX + 2 * GAIN_HALF];
     __shared__ float s_r[GAIN_FT][SEQ_KMAX];
+    __shared__ float s_pn[GAIN_FT][2][SEQ_KMAX];   // SNR gating: power and effective noise of the frame's bins
+    __shared__ float s_sg[GAIN_FT];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     int64_t tile_in_clip;
     int c;
@@ -2336,6 +2339,7 @@ __global__ void __launch_bounds__(256) gain_kernel(const __grid_constant__ DevPa
             const float neff = f_min(n, p.trk_maxr * pk);
             const float ratio = f_div(neff, pk + p.gain_eps);
             s_r[tt][k] = ratio;
+            if (p.snr_gate) { s_pn[tt][0][k] = pk; s_pn[tt][1][k] = neff; continue; }
             const bool rain = __ldg(io.frame_class + f0 + t) == 2;
             const float osub = rain ? p.oversub_rain : p.oversub_noise;
             float g;
@@ -2348,6 +2352,40 @@ __global__ void __launch_bounds__(256) gain_kernel(const __grid_constant__ DevPa
             s_g[tt][GAIN_HALF + k] = f_min(f_max(g, p.gain_floor), p.gain_ceil);
         }
         __syncthreads();
+        if (p.snr_gate) {
+            // frame-level SNR over the selected bins: np.sum(axis=0) adds the rows in bin order (:1064-1067), then the gate
+            if (tid < GAIN_FT && tb + tid < t1) {
+                float pm = 0.0f, nm = 0.0f;
+                bool first = true;
+                for (int k = 0; k < K; k++)
+                    if ((p.snr_mask[k >> 5] >> (k & 31)) & 1u) {
+                        if (first) { pm = s_pn[tid][0][k]; nm = s_pn[tid][1][k]; first = false; }
+                        else { pm += s_pn[tid][0][k]; nm += s_pn[tid][1][k]; }
+                    }
+                const float snr = f_div(pm, nm + p.gain_eps);
+                const float gate = f_div(snr, snr + p.snr1);
+                s_sg[tid] = f_min(f_max(gate, 0.0f), 1.0f);
+            }
+            __syncthreads();
+            for (int idx = tid; idx < GAIN_FT * K; idx += 256) {
+                const int tt = idx / K, k = idx - tt * K;
+                const int t = tb + tt;
+                if (t >= t1) continue;
+                const bool rain = __ldg(io.frame_class + f0 + t) == 2;
+                float osub = rain ? p.oversub_rain : p.oversub_noise;
+                if (p.adaptive_gain) osub = osub * (1.0f - s_sg[tt]);          // (:433-438)
+                const float pk = s_pn[tt][0][k], neff = s_pn[tt][1][k];
+                float g;
+                if (p.gain_mode == 0) {
+                    const float r = f_min(f_max(s_r[tt][k], 0.0f), 1.0f);
+                    g = 1.0f - osub * f_sqrt(r);
+                } else {
+                    g = f_div(f_max(pk - osub * neff, 0.0f), pk + p.gain_eps);
+                }
+                s_g[tt][GAIN_HALF + k] = f_min(f_max(g, p.gain_floor), p.gain_ceil);
+            }
+            __syncthreads();
+        }
         for (int idx = tid; idx < GAIN_FT * K; idx += 256) {
             const int tt = idx / K, k = idx - tt * K;
             const int t = tb + tt;

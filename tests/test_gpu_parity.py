@@ -244,7 +244,7 @@ def test_host_path_and_errors(torch_cuda):
     with pytest.raises(AttributeError):
         proc.run(np.zeros(6 * 11162, np.float32), {"sample_rate": 11162, "check_duration": 6})
     with pytest.raises(NotImplementedError):
-        proc.run(np.zeros(6 * 11162, np.float32), dict(params, snr_gating_enable=True))
+        proc.run(np.zeros(6 * 11162, np.float32), dict(params, process_dtype="float64"))
 
 
 @pytest.mark.parametrize("n_fft,hop", [(256, 64), (512, 256), (1024, 256), (2048, 1024), (4096, 1024)])
