@@ -142,6 +142,7 @@ struct apt_plan {
     int st_stride = 0;      // lanes per clip in the carried-state arrays
     bool generic = false;   // generic frame-size STFT kernel
     bool full_ok = true;    // the full pipeline is planned (n_fft = 256 / hop = 128, or frame size and hop multiples of 128)
+    bool td_blocks = false; // geometry other than 256 / 128: TD crest factor from block statistics (one segment, no fast gate)
     int flux_ft = FLUX_FT;  // frames per tile of the flux kernel
     DevBuf<unsigned short> d_lane_modes, d_lane_all;   // pass-1 lane tables beyond SEQ_KMAX lanes
     DevBuf<float> d_blk_sum, d_blk_max;                // 128-sample block statistics of the prefiltered waveform (generic geometry)
@@ -330,7 +331,10 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
         return fail(ctx, -21, "unsupported STFT geometry n_fft=%d hop=%d (power of two 256..4096, 1 <= hop <= n_fft)", p->n_fft, p->hop);
     // n_fft = 256 with any hop <= 128 stays on the specialised STFT kernel (features stage unless hop = 128)
     const bool generic = !(p->n_fft == 256 && p->hop <= 128);
-    const bool full_ok = (p->n_fft == 256 && p->hop == 128) || (generic && p->hop % 128 == 0 && !p->has_kurt_upper);
+    // full pipeline: 256 / 128, or any supported frame size at a hop that is a multiple of 64 (128-sample leaves of numpy's
+    // pairwise sums start at multiples of the block stride g = 128 or 64)
+    const bool td_blocks = !(p->n_fft == 256 && p->hop == 128);
+    const bool full_ok = !td_blocks || (p->hop % 64 == 0 && !p->has_kurt_upper);
     const int F = p->n_fft / 2 + 1;
     const int K = p->band_hi - p->band_lo + 1;
     if (p->band_lo < 0 || p->band_hi >= F || K < 1 || (!generic && K > SEQ_KMAX)) return fail(ctx, -22, "operating band bins [%d,%d] unsupported", p->band_lo, p->band_hi);
@@ -345,6 +349,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     pl->ctx = ctx;
     pl->prm = *p;
     pl->generic = generic;
+    pl->td_blocks = td_blocks;
     pl->full_ok = full_ok;
     pl->n_clips = n_clips;
     DevParams& d = pl->dp;
@@ -460,8 +465,11 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
             *out = pl;
             return 0;
         }
-        PL_OK(pl->d_blk_sum.alloc((size_t)(pl->nS / 128 + n_clips + 2)));
-        PL_OK(pl->d_blk_max.alloc((size_t)(pl->nS / 128 + n_clips + 2)));
+    }
+    d.td_g = (p->hop % 128 == 0) ? 128 : 64;
+    if (td_blocks && full_ok) {
+        PL_OK(pl->d_blk_sum.alloc((size_t)(pl->nS / d.td_g + n_clips + 2)));
+        PL_OK(pl->d_blk_max.alloc((size_t)(pl->nS / d.td_g + n_clips + 2)));
     }
     // FFT tables
     if (!generic) {
@@ -873,9 +881,9 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     if (!full && !(out->band_energy || out->P || out->S || out->raw))
         return fail(ctx, -31, "features stage requires at least one of band_energy / P / S / raw");
     if (full && !pl->full_ok)
-        return fail(ctx, -34, "the full pipeline needs n_fft=256 / hop=128, or a hop that is a multiple of 128 (and no kurtosis gate); "
+        return fail(ctx, -34, "the full pipeline needs n_fft=256 / hop=128, or a hop that is a multiple of 64 (and no kurtosis gate); "
                               "n_fft=%d hop=%d supports the features stage", d.n_fft, d.hop);
-    if (full && pl->generic && (out->G || out->S_hat || out->y || out->peak_ratio || out->peak_gate_score || out->peak_valid_count ||
+    if (full && pl->td_blocks && (out->G || out->S_hat || out->y || out->peak_ratio || out->peak_gate_score || out->peak_valid_count ||
                                 out->peak_count_by_mode || out->ratio_med))
         return fail(ctx, -34, "n_fft=%d hop=%d: the gain / resynthesis planes and the peak features exist at n_fft=256 / hop=128 only",
                     d.n_fft, d.hop);
@@ -927,7 +935,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     int64_t maxT = 1;
     for (int c = clip0; c < clip0 + n_clips; c++) maxT = std::max(maxT, pl->frame_off[c + 1] - pl->frame_off[c]);
     // (the generic frame sizes run in one segment on the caller's stream: their TD tiles are not aligned with frame ranges)
-    const bool piped = want_seg > 1 && pl->pipeline && !pl->timing && !pl->generic;
+    const bool piped = want_seg > 1 && pl->pipeline && !pl->timing && !pl->td_blocks;
     int seg_frames, n_seg;
     if (piped) {
         int want = want_seg;
@@ -986,7 +994,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
     // Default flags consume one bit of the TD features per frame (crest > td_gate_threshold): the float32 filter
     // decides it wherever the crest factor is outside a guard band around the threshold, and the float64 filter
     // re-decides the tiles holding a frame inside the band -- the gate plane equals the float64 one bit for bit.
-    const bool fast_td = pl->td_fast && !out->td && !out->x_td && !d.has_ku && d.gate_thr != 0.0f && !pl->generic;
+    const bool fast_td = pl->td_fast && !out->td && !out->x_td && !d.has_ku && d.gate_thr != 0.0f && !pl->td_blocks;
 
     // start of the run on the caller's stream: selection state and histograms, then the fork
     if (!d.suppressor_bypass) {
@@ -1072,7 +1080,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
                     RR(launch_td<PCM, float>(pl, bs, g, pcm, tf, S[apt_plan::SK_TD]));
                 }
                 if (g.x > 0 && tf.list_cap > 0) RR(launch_td_recheck<PCM>(pl, bs, pcm, tf, S[apt_plan::SK_TD]));
-            } else if (pl->generic) {
+            } else if (pl->td_blocks) {
                 // block statistics of the prefiltered waveform, then the crest factor of every (n_fft, hop) frame from them
                 TdOut tg = to;
                 tg.td = nullptr; tg.want_block = 0; tg.want_kurt = 0;

@@ -50,6 +50,7 @@ struct DevParams {
     int adaptive_q; double aq_base, aq_min, aq_alpha;   // adaptive quantile of pass 2
     int pre_smooth, median;                              // pre_smooth_frames / median_frames (<= 1: off)
     int snr_gate; float snr1; uint32_t snr_mask[4];      // spectral SNR gating of the oversubtraction
+    int td_g;                                            // stride of the TD block statistics (128, or 64 when the hop asks for it)
     int warm_need;
     float eps32;
     int use_norm, ratio_db;
@@ -752,7 +753,7 @@ struct TdOut {
 
 // first entry of clip c (whose samples start at `base`) in the block-statistics arrays: floor(base / 128) + c leaves every
 // clip its floor(N / 128) entries (floor(a + b) >= floor(a) + floor(b)); the arrays hold nS / 128 + n_clips + 1 entries
-__host__ __device__ __forceinline__ int64_t td_block_base(int64_t base, int c) { return (base >> 7) + c; }
+__host__ __device__ __forceinline__ int64_t td_block_base(int64_t base, int c, int g = 128) { return base / g + c; }
 
 inline size_t td_smem_bytes(int ns, int env_cap, size_t real_bytes = sizeof(double)) {
     return sizeof(float) * TD_XF + real_bytes * ((size_t)2 * ns * (TD_NT / 32) + 32 * 4 * ns * ns + (size_t)TD_CHUNK * 2 * ns) + 8 +
@@ -980,7 +981,7 @@ __device__ __forceinline__ void td_tile(const DevParams& p, const Batch& b, cons
     double* s_renv = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_H + TD_CHUNK * DIM) + 7) & ~(uintptr_t)7);   // [env_cap] raw block envelope (want_block)
     double* s_env = s_renv + tb.env_cap;                            // [env_cap] smoothed block envelope
     float* s_x = reinterpret_cast<float*>(s_env + tb.env_cap);      // [TD_XF] staged PCM, then the float32 result
-    __shared__ float s_bsum[TD_FT + 1], s_bmax[TD_FT + 1];
+    __shared__ float s_bsum[2 * TD_FT + 4], s_bmax[2 * TD_FT + 4];   // (block mode at stride 64: two leaves per 128 samples)
     __shared__ int s_near;
     constexpr int L = 256, hop = 128;     // n_fft / hop (enforced by the plan)
     // float32 fast path on int16 input: unscaled samples through the (linear) filter, the scale is applied to the
@@ -1128,10 +1129,36 @@ __device__ __forceinline__ void td_tile(const DevParams& p, const Batch& b, cons
     }
     __syncthreads();
     if (o.blk_sum) {
-        // block mode (frame sizes other than 256 / 128): the tile hands out the statistics of the 128-sample blocks it
-        // owns -- [t0, t0 + TD_FT), the clip's last tile through its last block -- and crest_blocks_kernel combines them
-        const int nown = nfr > 0 ? (last ? nfr + 1 : min(nfr + 1, TD_FT)) : 0;
-        const int64_t bo = td_block_base(base, c) + t0;
+        // block mode (geometries other than 256 / 128): the tile hands out the statistics of the 128-sample leaves it owns --
+        // those starting in [t0 * 128, (t0 + TD_FT) * 128) at stride g, the clip's last tile through its last leaf -- and
+        // crest_blocks_kernel combines them
+        const int g = p.td_g, sb = 128 / g;
+        // leaves that fit the tile's samples: starts t0 * 128 + j * g with all 128 samples before (t1 + 1) * 128, the clip's
+        // last tile up to the clip end (a leaf at an odd multiple of 64 can fit behind the last whole 128-sample block)
+        const int nleaf = nfr > 0 ? (last ? (int)((N - (int64_t)t0 * 128 - 128) / g) + 1 : nfr * sb + 1) : 0;
+        if (sb > 1) {                                          // stride 64: leaves straddle the padded 128-sample rows
+            __syncthreads();
+            for (int lf = grp; lf < nleaf; lf += TD_NT / 8) {
+                const int u = 128 + lf * g;
+                float v = s_x[td_xf_pos(u + lane)];
+                float r = v * v, pk = fabsf(v);
+#pragma unroll
+                for (int i = 1; i < 16; i++) { v = s_x[td_xf_pos(u + 8 * i + lane)]; r += v * v; pk = fmaxf(pk, fabsf(v)); }
+                const float o1 = __shfl_xor_sync(gmask, r, 1);
+                const float s1 = (lane & 1) ? o1 + r : r + o1;
+                const float o2 = __shfl_xor_sync(gmask, s1, 2);
+                const float s2 = (lane & 2) ? o2 + s1 : s1 + o2;
+                const float o4 = __shfl_xor_sync(gmask, s2, 4);
+                const float bsum = (lane & 4) ? o4 + s2 : s2 + o4;
+                pk = fmaxf(pk, __shfl_xor_sync(gmask, pk, 1));
+                pk = fmaxf(pk, __shfl_xor_sync(gmask, pk, 2));
+                pk = fmaxf(pk, __shfl_xor_sync(gmask, pk, 4));
+                if (lane == 0) { s_bsum[lf] = bsum; s_bmax[lf] = pk; }
+            }
+            __syncthreads();
+        }
+        const int nown = nleaf > 0 ? (last ? nleaf : min(nleaf, TD_FT * sb)) : 0;
+        const int64_t bo = td_block_base(base, c, g) + (int64_t)t0 * sb;
         for (int i = tid; i < nown; i += TD_NT) { o.blk_sum[bo + i] = s_bsum[i]; o.blk_max[bo + i] = s_bmax[i]; }
         return;
     }
@@ -1351,14 +1378,14 @@ __global__ void __launch_bounds__(256) crest_blocks_kernel(const __grid_constant
     const int T = (int)(__ldg(b.frame_off + c + 1) - f0);
     const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (t >= T) return;
-    const int L = p.n_fft, nbk = L >> 7, hb = p.hop >> 7;
+    const int L = p.n_fft, nbk = L >> 7, g = p.td_g, sb = 128 / g, hb = p.hop / g;
     const int Tloc = N < L ? 0 : (int)(1 + (N - L) / p.hop);
     float cf = 0.0f;   // frames beyond the TD grid are zero (rain_frame_classifier.py:178-194)
     if (t < Tloc) {
-        const int64_t bo = td_block_base(base, c) + (int64_t)t * hb;
+        const int64_t bo = td_block_base(base, c, g) + (int64_t)t * hb;      // leaf i of the frame starts at t * hop + 128 * i
         float v[32];
         float pk = 0.0f;
-        for (int i = 0; i < nbk; i++) { v[i] = __ldg(io.blk_sum + bo + i); pk = fmaxf(pk, __ldg(io.blk_max + bo + i)); }
+        for (int i = 0; i < nbk; i++) { v[i] = __ldg(io.blk_sum + bo + i * sb); pk = fmaxf(pk, __ldg(io.blk_max + bo + i * sb)); }
         for (int w = 1; w < nbk; w <<= 1)
             for (int i = 0; i < nbk; i += 2 * w) v[i] = v[i] + v[i + w];
         const float sumsq = 0.0f + v[0];

@@ -271,13 +271,15 @@ def test_frame_size_sweep_features(torch_cuda, n_fft, hop, fft_f64):
             np.testing.assert_allclose(out["raw"][i], g["det_" + k], rtol=1e-4, atol=1e-6, err_msg=k)
     band = g["band_mask"]
     np.testing.assert_allclose(out["band_energy"][-1], out["P"][:, band].astype(np.float64).sum(axis=1) + 1e-9, rtol=1e-6)
-    if hop % 128:
-        with pytest.raises(AptError):      # the full pipeline needs a hop that is a multiple of 128
-            eng.run_clips([g["pcm"]], ())
     eng.close()
+    if (n_fft, hop) == (256, 64):          # the full pipeline needs a hop that is a multiple of 64
+        eng = make_engine(dict(params, hop=96), fft_f64=fft_f64)
+        with pytest.raises(AptError):
+            eng.run_clips([g["pcm"]], ())
+        eng.close()
 
 
-@pytest.mark.parametrize("n_fft,hop", [(512, 256), (1024, 256), (2048, 1024), (4096, 1024), (256, 256), (512, 128)])
+@pytest.mark.parametrize("n_fft,hop", [(512, 256), (1024, 256), (2048, 1024), (4096, 1024), (256, 256), (512, 128), (256, 64), (512, 192)])
 def test_full_pipeline_other_frame_sizes(torch_cuda, n_fft, hop):
     """The whole detector at frame sizes other than 256 / 128 against the unmodified reference (geom_* fixtures): the
     TD crest factor and gate bit for bit; labels, confidences and events identical; per-mode flux, score and the

@@ -131,7 +131,7 @@ def test_oracle_frame_size_sweep(oracle_mod, n_fft, hop):
         np.testing.assert_allclose(s["raw"][i], g["det_" + k], rtol=1e-4, atol=1e-6, err_msg=k)
 
 
-GEOM = ((512, 256), (1024, 256), (2048, 1024), (4096, 1024), (256, 256), (512, 128))
+GEOM = ((512, 256), (1024, 256), (2048, 1024), (4096, 1024), (256, 256), (512, 128), (256, 64), (512, 192))
 
 
 @pytest.mark.parametrize("n_fft,hop", GEOM)
