@@ -141,7 +141,7 @@ struct apt_plan {
     int mf_stride = 8;
     int st_stride = 0;      // lanes per clip in the carried-state arrays
     bool generic = false;   // generic frame-size STFT kernel
-    bool full_ok = true;    // the full pipeline is planned (n_fft = 256 / hop = 128, or frame size and hop multiples of 128)
+    bool full_ok = true;    // the full pipeline is planned (n_fft = 256 / hop = 128, or any supported frame size at a hop that is a multiple of 64)
     bool td_blocks = false; // geometry other than 256 / 128: TD crest factor from block statistics (one segment, no fast gate)
     int flux_ft = FLUX_FT;  // frames per tile of the flux kernel
     DevBuf<unsigned short> d_lane_modes, d_lane_all;   // pass-1 lane tables beyond SEQ_KMAX lanes
@@ -325,7 +325,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     if (p->abi_version != APT_ABI_VERSION) return fail(ctx, -20, "params abi_version %d != %d", p->abi_version, APT_ABI_VERSION);
     // (256, 128) runs the full pipeline on the specialised kernels.  Any other power-of-two frame size up to 4096 with
     // 1 <= hop <= n_fft runs the features stage (STFT, power, band energies, raw features) on the generic STFT kernel,
-    // and the full pipeline too when the hop is a multiple of 128 (the TD crest factor is then assembled from 128-sample
+    // and the full pipeline too when the hop is a multiple of 64 (the TD crest factor is then assembled from 128-sample
     // block statistics; the kurtosis gate, the peak features and the gain planes stay with the 256-sample geometry)
     if (p->n_fft < 256 || p->n_fft > 4096 || (p->n_fft & (p->n_fft - 1)) != 0 || p->hop < 1 || p->hop > p->n_fft)
         return fail(ctx, -21, "unsupported STFT geometry n_fft=%d hop=%d (power of two 256..4096, 1 <= hop <= n_fft)", p->n_fft, p->hop);
