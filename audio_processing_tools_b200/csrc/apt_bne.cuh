@@ -201,15 +201,38 @@ __global__ void bne_state_kernel(const __grid_constant__ BneDev p, int n_clips, 
     double prev_rain = 0.0, prev_prim = 0.0, prev_Eb = 0.0, prev_Lb = 0.0, prev_Lh = 0.0;
     double noise_sum = 0.0, rain_sum = 0.0, total_sum = 0.0;
     long long noise_frames = 0, rain_frames = 0, total_frames = 0, min_valid = 0, underflow = 0, learned_total = 0, repl_total = 0;
+    // The valid entries are also kept as a sorted array, updated by one removal / insertion per ring operation: the noise
+    // level is np.quantile of the valid entries EVERY frame; sorting 64 values from scratch per frame (an insertion sort
+    // in local memory, ~1 000 dependent steps) cost 41.7 -> 34.0 ms on 512 clips x 60 s.
+    double sv[BNE_MAX_W];
+    for (int i = 0; i < BNE_MAX_W; i++) sv[i] = 0.0;
+    int ns = 0;
+    auto sv_remove = [&](double v) {
+        int i = 0;
+        while (i < ns && sv[i] != v) i++;
+        if (i == ns) return;                      // (cannot happen: every valid entry is in sv)
+        for (; i + 1 < ns; i++) sv[i] = sv[i + 1];
+        ns--;
+    };
+    auto sv_insert = [&](double v) {
+        int b = ns - 1;
+        while (b >= 0 && sv[b] > v) { sv[b + 1] = sv[b]; b--; }
+        sv[b + 1] = v;
+        ns++;
+    };
     auto expire = [&](long long frame_idx) {
         if (p.ttl <= 0 || count_valid <= 0) return;
+        // entries enter in frame order, so the slot about to be overwritten holds the oldest one: if it is valid and
+        // young enough, nothing is stale
+        if (valid[wr] && (frame_idx - bidx[wr]) <= p.ttl) return;
         int n = 0;
         for (int i = 0; i < W; i++)
-            if (valid[i] && (frame_idx - bidx[i]) > p.ttl) { valid[i] = false; buf[i] = 0.0; bidx[i] = -1; n++; }
+            if (valid[i] && (frame_idx - bidx[i]) > p.ttl) { sv_remove(buf[i]); valid[i] = false; buf[i] = 0.0; bidx[i] = -1; n++; }
         count_valid = max(0, count_valid - n);
     };
     auto push = [&](double v, long long frame_idx) {
-        if (!valid[wr]) count_valid++;
+        if (!valid[wr]) count_valid++; else sv_remove(buf[wr]);
+        sv_insert(v);
         buf[wr] = v; valid[wr] = true; bidx[wr] = frame_idx;
         wr = (wr + 1) % W;
     };
@@ -261,10 +284,10 @@ __global__ void bne_state_kernel(const __grid_constant__ BneDev p, int n_clips, 
             if (p.learn_all || !((mask >> s) & 1u)) { push(sE[s] > p.eps ? sE[s] : p.eps, frame_idx); learned++; }
         int repl = 0;
         if (p.replenish && learned == 0 && (!p.replenish_only_not_full || count_valid < W)) {
-            double sv[BNE_MAX_S];
-            for (int s = 0; s < S; s++) sv[s] = sE[s];
-            for (int a = 1; a < S; a++) { const double v = sv[a]; int b = a - 1; while (b >= 0 && sv[b] > v) { sv[b + 1] = sv[b]; b--; } sv[b + 1] = v; }
-            const double qn = np_quantile_sorted(sv, S, p.repl_q);
+            double rs[BNE_MAX_S];
+            for (int s = 0; s < S; s++) rs[s] = sE[s];
+            for (int a = 1; a < S; a++) { const double v = rs[a]; int b = a - 1; while (b >= 0 && rs[b] > v) { rs[b + 1] = rs[b]; b--; } rs[b + 1] = v; }
+            const double qn = np_quantile_sorted(rs, S, p.repl_q);
             push(qn > p.eps ? qn : p.eps, frame_idx);
             repl = 1;
         }
@@ -280,12 +303,7 @@ __global__ void bne_state_kernel(const __grid_constant__ BneDev p, int n_clips, 
         double nsub = 0.0;
         if (count_valid < p.W_min) { noise_ema = 0.0; ne_smooth = 0.0; }
         else {
-            double sv[BNE_MAX_W];
-            int n = 0;
-            for (int k = 0; k < W; k++) if (valid[k]) {       // insertion into a sorted copy
-                const double v = buf[k]; int b = n - 1; while (b >= 0 && sv[b] > v) { sv[b + 1] = sv[b]; b--; } sv[b + 1] = v; n++;
-            }
-            const double qv = np_quantile_sorted(sv, n, q_eff);
+            const double qv = np_quantile_sorted(sv, ns, q_eff);
             noise_ema = (1.0 - p.ema_alpha) * noise_ema + p.ema_alpha * qv;
             nsub = noise_ema;
         }
