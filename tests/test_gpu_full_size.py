@@ -111,3 +111,49 @@ def test_config2_one_hour_clip_scaling():
         lhs = P[t, 0] + P[t, 128] + 2.0 * P[t, 1:128].sum()
         assert lhs == pytest.approx(256.0 * float((fr * fr).sum()), rel=1e-5)
     eng.close()
+
+
+@pytest.mark.parametrize("n_fft,hop,extra", [(1024, 256, {}), (256, 64, {}),
+                                             (256, 128, {"pre_smooth_frames": 3, "median_frames": 5, "adaptive_q_enable": True})])
+def test_config5_full_pipeline_other_geometries_at_size(oracle_mod, n_fft, hop, extra):
+    """BASELINE configs[4] with the WHOLE pipeline at size: 96 x 10-min clips (6 distinct) at another frame size / with the
+    optional tracker smoothing.  Batch invariance (every copy of a clip agrees bit for bit wherever it sits), compaction,
+    determinism of a second pass, and full-length parity of the distinct clips with the oracle."""
+    import torch
+    n_clips, n_base = 96, 6
+    params = default_params(check_duration=SECONDS, n_fft=n_fft, hop=hop, **extra)
+    eng = _engine(params)
+    base = [synth_clip_i16(SECONDS, *batch_clip_spec(7000 + i)) for i in range(n_base)]
+    N = base[0].size
+    plan = eng.plan_for([N] * n_clips)
+    T = 1 + N // hop
+    assert plan.nF == n_clips * T
+    dev = torch.device("cuda", 0)
+    order = np.random.default_rng(5).integers(0, n_base, n_clips)
+    order[:n_base] = np.arange(n_base)
+    base_dev = torch.from_numpy(np.stack(base)).to(dev)
+    pcm = base_dev[torch.from_numpy(order).to(dev)].reshape(-1).contiguous()
+    del base_dev
+    bufs = eng.alloc_outputs(plan, (), full=True)
+    eng.run_device(plan, pcm, bufs, full=True)
+    torch.cuda.synchronize()
+    out = {k: v.cpu().numpy() for k, v in bufs.items()}
+    eng.run_device(plan, pcm, bufs, full=True)
+    torch.cuda.synchronize()
+    for k in ("frame_class", "rain_conf", "noise_conf", "event_count", "clip_stats"):
+        assert np.array_equal(bufs[k].cpu().numpy(), out[k]), k
+    fc = out["frame_class"].reshape(n_clips, T)
+    ev = out["event_idx"].reshape(n_clips, T)
+    cnt = out["event_count"]
+    assert np.array_equal(cnt, (fc == 2).sum(axis=1))
+    for c in range(0, n_clips, 11):
+        assert np.array_equal(ev[c, :cnt[c]], np.flatnonzero(fc[c] == 2))
+    digest = {}
+    for c in range(n_clips):
+        h = hashlib.sha1(fc[c].tobytes() + out["clip_stats"][c, 1:].tobytes()).hexdigest()
+        assert digest.setdefault(int(order[c]), h) == h, f"clip at position {c} differs from its other copies"
+    fcs, counts = oracle_mod.process_batch_i16(base, params, n_threads=6)
+    for i in range(n_base):
+        assert np.array_equal(fc[i], fcs[i]), f"labels of distinct clip {i} differ from the oracle"
+        assert int(cnt[i]) == int(counts[i])
+    eng.close()
