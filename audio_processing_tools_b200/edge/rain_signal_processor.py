@@ -194,8 +194,8 @@ class SpectralNoiseProcessor:
 
     @staticmethod
     def _features(cfg, times, fc, rc, nc, det_debug=None) -> Dict[str, Any]:
-        """`dump_features` payload (rain_signal_processor.py:723-787): the five per-frame arrays, plus whatever the
-        detector exported when its debug output is on, every array decimated along its frame axis by `feature_decim`."""
+        """`dump_features` payload (rain_signal_processor.py:723-787): the five per-frame arrays (plus the detector-side
+        feature dump, which is empty at the supported feature_dump_level = 0), decimated along the frame axis by `feature_decim`."""
         step = max(1, int(getattr(cfg, "feature_decim", 1)))
 
         def dec(v):
@@ -211,8 +211,16 @@ class SpectralNoiseProcessor:
              "is_rain": dec(np.asarray(fc) == FrameClass.RAIN), "rain_conf": dec(np.asarray(rc, dtype=np.float32)),
              "noise_conf": dec(np.asarray(nc, dtype=np.float32))}
         if isinstance(det_debug, dict):
+            # the detector-side dump wins when it is a dict (:771-776) -- and under feature_dump_level = 0 it is an EMPTY
+            # dict, so the reference's payload is the five arrays above; only without it are the detector's arrays passed on
+            fd = det_debug.get("feature_dump", None)
+            if isinstance(fd, dict):
+                for k, v in fd.items():
+                    f[k] = dec(v)
+                return f
             for k, v in det_debug.items():
-                f[k] = dec(v)
+                if k != "feature_dump":
+                    f[k] = dec(v)
         return f
 
     def _package_core(self, plan, out, cfg, sr, rp, with_stats) -> List[Dict[str, Any]]:
@@ -273,9 +281,52 @@ class SpectralNoiseProcessor:
         d["primary_mode_flux_gated"] = d["primary_mode_flux"] * gs
         for i, name in enumerate(TD_FEATURE_ROWS):
             d[name] = out["td"][i, f0:f1].copy()
-        if "raw" in out:
-            for i, name in enumerate(RAW_SPECTRAL_FEATURE_NAMES):
-                d[name] = out["raw"][i, f0:f1].copy()
+        raw_on = "raw" in out
+        for i, name in enumerate(RAW_SPECTRAL_FEATURE_NAMES):
+            d[name] = out["raw"][i, f0:f1].copy() if raw_on else np.zeros(f1 - f0, dtype=np.float32)
+        # soft TD label (assign_td_soft_label, rain_frame_classifier.py:85-110, :618-629): votes of crest factor and kurtosis
+        T = f1 - f0
+        votes = np.zeros(T, dtype=np.int32)
+        if bool(dv.get("td_soft_enable", False)):
+            votes += (d["td_crest_factor"] >= float(dv.get("td_soft_crest_factor_min", 4.0))).astype(np.int32)
+            votes += (d["td_kurtosis"] >= float(dv.get("td_soft_kurtosis_min", 6.0))).astype(np.int32)
+            d["td_soft_score"] = votes.astype(np.float32) / 2.0
+            d["td_soft_label"] = votes >= int(dv.get("td_soft_min_positive_votes", 2))
+        else:
+            d["td_soft_score"] = np.zeros(T, dtype=np.float32)
+            d["td_soft_label"] = np.zeros(T, dtype=bool)
+        d["td_vote_count"] = votes
+        # sparse-dump bookkeeping (:945-967) and the scalar echoes of the detector's configuration (:1022-1045)
+        gate_feature = str(dv.get("feature_dump_sparse_gate_feature", "td_block_energy_crest"))
+        sparse_on = bool(dv.get("feature_dump_sparse_enable", False))
+        sparse_thr = float(dv.get("feature_dump_sparse_gate_threshold", 3.5))
+        if sparse_on:
+            src = d["td_crest_factor"] if gate_feature == "td_crest_factor" else d["td_block_energy_crest"]
+            mask = np.nan_to_num(src, nan=0.0, posinf=0.0, neginf=0.0) > sparse_thr
+        else:
+            mask = np.ones(T, dtype=bool)
+        d["raw_spectral_dump_mask"] = mask
+        d["raw_spectral_dump_mask_fraction"] = float(np.mean(mask.astype(np.float32))) if T > 0 else 0.0
+        d["sparse_frame_idx"] = np.flatnonzero(mask).astype(np.int32)
+        blk_len = int(dv.get("td_block_energy_len", 8))
+        blk_hop = dv.get("td_block_energy_hop", None)
+        d.update({
+            "td_block_energy_len": blk_len,
+            "td_block_energy_hop": int(blk_hop) if blk_hop is not None else None,
+            "td_block_energy_post_pre_blocks": int(dv.get("td_block_energy_post_pre_blocks", 4)),
+            "td_block_energy_smooth_enable": bool(dv.get("td_block_energy_smooth_enable", True)),
+            "feature_dump_dense_enable": bool(dv.get("feature_dump_dense_enable", True)),
+            "feature_dump_sparse_enable": sparse_on,
+            "feature_dump_clip_summary_enable": bool(dv.get("feature_dump_clip_summary_enable", False)),
+            "feature_dump_sparse_gate_feature": gate_feature,
+            "feature_dump_sparse_gate_threshold": sparse_thr,
+            "raw_spectral_shape_enable": bool(dv.get("raw_spectral_shape_enable", True)),
+            "raw_spectral_uses_raw_power": True,
+            "td_apply_input_prefilter": bool(dv.get("td_apply_input_prefilter", True)),
+            "td_prefilter_mode": str(dv.get("td_prefilter_mode", dv.get("pre_filter_mode", "none"))).lower(),
+            "clip_spectral_occupancy_enable": bool(dv.get("clip_spectral_occupancy_enable", False)),
+            "feature_dump": {},          # feature_dump_level = 0 (higher levels are refused): the reference attaches an empty dict
+        })
         return d
 
     def _debug(self, out, f0, f1, rp, dv, times) -> Dict[str, Any]:

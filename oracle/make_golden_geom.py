@@ -107,7 +107,34 @@ def smoothing_cases():
         json.dump(index, f, indent=1)
 
 
+def detdebug_case():
+    """The full key set of the detector's debug dictionary (state["det_debug"]) with the scalar echoes, and the soft TD
+    label arrays under td_soft_enable (rain_frame_classifier.py:85-110, :1000-1047)."""
+    import hashlib
+    import json
+    from audio_processing_tools.edge.rain_signal_processor import RainDetectorProcessor
+    from audio_processing_tools_b200.synth import default_params, pcm_to_f32
+    seconds, seed, lam = 8, 63, 10.0
+    pcm = synth_clip_i16(seconds, seed, lam)
+    params = default_params(check_duration=seconds, keep_state_debug=True)
+    params["detector"] = dict(params["detector"], td_soft_enable=True, td_soft_crest_factor_min=3.0, td_soft_kurtosis_min=4.0)
+    _, state = RainDetectorProcessor().run(pcm_to_f32(pcm), params)
+    dd = state["det_debug"]
+    scalars = {k: (v if not isinstance(v, (np.floating, np.integer, np.bool_)) else v.item())
+               for k, v in dd.items() if not isinstance(v, np.ndarray) and not isinstance(v, dict)}
+    d = {"meta": np.array(json.dumps({"seconds": seconds, "seed": seed, "lam": lam,
+                                      "pcm_sha1": hashlib.sha1(pcm.tobytes()).hexdigest(), "numpy": np.__version__,
+                                      "keys": sorted(dd.keys()), "scalars": scalars}, default=str)),
+         "td_vote_count": np.asarray(dd["td_vote_count"]), "td_soft_score": np.asarray(dd["td_soft_score"]),
+         "td_soft_label": np.asarray(dd["td_soft_label"]), "raw_spectral_dump_mask": np.asarray(dd["raw_spectral_dump_mask"]),
+         "sparse_frame_idx": np.asarray(dd["sparse_frame_idx"])}
+    path = os.path.join(mg.OUT, "detdebug_s63.npz")
+    np.savez_compressed(path, **d)
+    print(path, len(dd), "keys", scalars, flush=True)
+
+
 if __name__ == "__main__":
+    detdebug_case()
     main()
     features_case()
     adaptive_q_cases()

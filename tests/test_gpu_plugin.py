@@ -305,7 +305,36 @@ def test_dump_features_payload_matches_reference():
     outs = proc.run_batch([pcm, synth_clip_i16(meta["seconds"] + 1.5, 62, 10.0)], params)
     assert np.array_equal(outs[0][1]["features"]["frame_class"], g["feat_frame_class"])
     assert "features" not in proc.run(pcm, dict(params, keep_state_features=False))[1]
+    # with the detector debug on the reference still returns the five arrays: its detector-side dump is an empty dict at
+    # feature_dump_level = 0 and takes precedence (rain_signal_processor.py:771-776)
     _, st2 = proc.run(pcm, dict(params, keep_state_debug=True))
     f2 = st2["features"]
-    assert np.array_equal(f2["td_crest_factor"], st2["det_debug"]["td_crest_factor"][::3])
+    assert set(f2) == set(f) and st2["det_debug"]["feature_dump"] == {}
     assert np.array_equal(f2["frame_class"], g["feat_frame_class"])
+
+
+def test_det_debug_key_set_and_soft_labels_match_reference():
+    """state["det_debug"] carries every key the reference's detector exports under default dump flags
+    (rain_frame_classifier.py:1000-1047), the scalar echoes have the reference's values, and the soft TD label arrays
+    under td_soft_enable (:85-110) are equal (tests/golden/detdebug_s63.npz from oracle/make_golden_geom.py)."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from audio_processing_tools_b200.edge.rain_signal_processor import RainDetectorProcessor
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "detdebug_s63.npz"), allow_pickle=False))
+    meta = json.loads(str(g["meta"]))
+    pcm = synth_clip_i16(meta["seconds"], meta["seed"], meta["lam"])
+    assert hashlib.sha1(pcm.tobytes()).hexdigest() == meta["pcm_sha1"]
+    params = default_params(check_duration=meta["seconds"], keep_state_debug=True)
+    params["detector"] = dict(params["detector"], td_soft_enable=True, td_soft_crest_factor_min=3.0, td_soft_kurtosis_min=4.0)
+    _, st = RainDetectorProcessor().run(pcm_to_f32(pcm), params)
+    dd = st["det_debug"]
+    assert set(dd) == set(meta["keys"]), sorted(set(dd) ^ set(meta["keys"]))
+    for k, v in meta["scalars"].items():
+        got = dd[k]
+        got = got.item() if isinstance(got, (np.floating, np.integer, np.bool_)) else got
+        assert (str(got) == v) if isinstance(v, str) and not isinstance(got, str) else (got == v), (k, got, v)
+    for k in ("td_vote_count", "td_soft_score", "td_soft_label", "raw_spectral_dump_mask", "sparse_frame_idx"):
+        assert dd[k].dtype == g[k].dtype and np.array_equal(dd[k], g[k]), k
+    assert int(g["td_vote_count"].sum()) > 0
