@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_PKG, "libapt_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 MAX_MODES, MAX_SOS, N_RAW, N_TD, N_STATS = 8, 4, 21, 5, 8
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_GAIN_TAPS = 9
 MAX_PRE_SMOOTH, MAX_MEDIAN = 16, 31
 STAGE_FEATURES, STAGE_FULL = 1, 2
@@ -74,7 +74,8 @@ class AptParams(C.Structure):
 OUT_FIELDS = ("frame_class", "rain_conf", "noise_conf", "event_idx", "event_count", "clip_stats",
               "S", "P", "det_noise_psd", "det_noise_lag", "D", "noise_psd", "mode_flux", "norm_flux",
               "score", "td", "raw", "band_energy", "gate", "x_td", "G", "ratio_med", "S_hat",
-              "peak_ratio", "peak_gate_score", "peak_valid_count", "peak_count_by_mode", "y", "td_fast_crest")
+              "peak_ratio", "peak_gate_score", "peak_valid_count", "peak_count_by_mode", "y", "td_fast_crest",
+              "snr_mode", "snr_gate")
 
 
 class AptDsdParams(C.Structure):

@@ -1280,6 +1280,7 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             GainIO gio;
             gio.P_band = pl->d_Pband.p; gio.N2 = n2_plane; gio.frame_class = out->frame_class; gio.G = out->G;
             gio.ratio_med = out->ratio_med; gio.nF = pl->nF;
+            gio.snr_mode = (out->snr_mode && out->snr_gate) ? out->snr_mode : nullptr; gio.snr_gate = gio.snr_mode ? out->snr_gate : nullptr;
             gain_kernel<<<seg_grid(pl->flux_tile_off, clip0, n_clips, 0, INT64_MAX), 256, 0, st>>>(pl->dp, bw, pl->d_flux_tile_off.p, gio);
             const int64_t lanes = (int64_t)n_clips * d.K;
             gain_time_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(pl->dp, bw, out->frame_class, out->G);

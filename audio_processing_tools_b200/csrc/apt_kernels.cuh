@@ -2335,6 +2335,7 @@ struct GainIO {
     float* G;            // [nF][K]
     float* ratio_med;    // optional [nF]
     int64_t nF;
+    float* snr_mode; float* snr_gate;   // optional [nF] (SNR gating)
 };
 constexpr int GAIN_FT = 8;        // frames per inner batch (one warp per frame for the median)
 constexpr int GAIN_HALF = APT_MAX_GAIN_TAPS / 2;
@@ -2392,6 +2393,7 @@ __global__ void __launch_bounds__(256) gain_kernel(const __grid_constant__ DevPa
                 const float snr = f_div(pm, nm + p.gain_eps);
                 const float gate = f_div(snr, snr + p.snr1);
                 s_sg[tid] = f_min(f_max(gate, 0.0f), 1.0f);
+                if (io.snr_mode) { io.snr_mode[f0 + tb + tid] = snr; io.snr_gate[f0 + tb + tid] = s_sg[tid]; }
             }
             __syncthreads();
             for (int idx = tid; idx < GAIN_FT * K; idx += 256) {

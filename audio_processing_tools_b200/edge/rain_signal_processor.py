@@ -99,6 +99,8 @@ class SpectralNoiseProcessor:
             want += ["det_noise_psd", "det_noise_lag", "noise_psd"]
             if suppress:
                 want += ["G", "ratio_med"]
+                if bool(cfg.snr_gating_enable):
+                    want += ["snr_mode", "snr_gate"]
         if keep_noise and "noise_psd" not in want:
             want.append("noise_psd")
         peaks = keep_det and bool(dv.get("peak_features_enable", False))
@@ -355,7 +357,14 @@ class SpectralNoiseProcessor:
             "operating_band": (float(cfg.operating_band[0]), float(cfg.operating_band[1])),
             "band_mask": rp.band_mask.copy(),
             "pre_filter_mode": str(cfg.pre_filter_mode).lower(),
+            "pre_filter_band": (float(cfg.operating_band[0]), float(cfg.operating_band[1])),
             "noise_psd_max_ratio": float(cfg.noise_psd_max_ratio),
+            "td_soft_enable": bool(dv.get("td_soft_enable", False)),
+            "bypass_classifier": False,                 # (bypass_classifier = True is refused)
+            "features_available": bool(cfg.dump_features),
+            # frame SNR and gate of the spectral SNR gating (:1050-1077); None when it is off, as in the reference
+            "snr_mode": out["snr_mode"][f0:f1].copy() if "snr_mode" in out else None,
+            "snr_gate": out["snr_gate"][f0:f1].copy() if "snr_gate" in out else None,
         }
 
 

@@ -40,6 +40,8 @@ _PLANES = {
     "peak_valid_count": ("int32", lambda nF, nS, rp: (nF,)),
     "peak_count_by_mode": ("int32", lambda nF, nS, rp: (rp.M, nF)),
     "td_fast_crest": ("float32", lambda nF, nS, rp: (nF,)),
+    "snr_mode": ("float32", lambda nF, nS, rp: (nF,)),
+    "snr_gate": ("float32", lambda nF, nS, rp: (nF,)),
 }
 _CORE = {
     "frame_class": ("int8", lambda nF, nC: (nF,)),

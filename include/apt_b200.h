@@ -41,7 +41,7 @@ extern "C" {
 #define APT_MAX_PRE_SMOOTH 16
 #define APT_MAX_MEDIAN 31
 #define APT_MAX_GAIN_TAPS 9
-#define APT_ABI_VERSION 8
+#define APT_ABI_VERSION 9
 
 typedef struct apt_ctx apt_ctx;
 typedef struct apt_plan apt_plan_t;
@@ -175,6 +175,8 @@ typedef struct apt_out_t {
     float*   td_fast_crest;   /* [nF]       diagnostic: crest factor as the float32 fast path of the TD gate computed it
                                             (the decision uses it only outside the guard band around td_gate_threshold;
                                             frames inside are re-decided by the float64 filter).  Not with td / x_td. */
+    float*   snr_mode;        /* [nF]       debug["snr_mode"]: frame SNR over the gating bins (snr_gating_enable; needs G) */
+    float*   snr_gate;        /* [nF]       debug["snr_gate"]: clip(snr / (snr + snr1), 0, 1)   (both or none) */
 } apt_out_t;
 
 /* which stages a run executes */

@@ -73,6 +73,9 @@ def adaptive_q_cases():
         pcm = synth_clip_i16(seconds, seed, lam)
         metrics, state, params = mg.run_reference(pcm, seconds, extra, spectra=True)
         d = mg.pack(pcm, seconds, seed, lam, metrics, state, level=2, params=params)
+        if state["debug"].get("snr_gate") is not None:
+            d["snr_gate_t"] = np.asarray(state["debug"]["snr_gate"])
+            d["snr_mode_t"] = np.asarray(state["debug"]["snr_mode"])
         np.savez_compressed(os.path.join(mg.OUT, name + ".npz"), **d)
         fc = d["frame_class"]
         entry = {"name": name, "seconds": seconds, "seed": seed, "lam": lam, "level": 2, "T": int(fc.size),
@@ -124,7 +127,8 @@ def detdebug_case():
                for k, v in dd.items() if not isinstance(v, np.ndarray) and not isinstance(v, dict)}
     d = {"meta": np.array(json.dumps({"seconds": seconds, "seed": seed, "lam": lam,
                                       "pcm_sha1": hashlib.sha1(pcm.tobytes()).hexdigest(), "numpy": np.__version__,
-                                      "keys": sorted(dd.keys()), "scalars": scalars}, default=str)),
+                                      "keys": sorted(dd.keys()), "scalars": scalars,
+                                      "debug_keys": sorted(state["debug"].keys()), "state_keys": sorted(state.keys())}, default=str)),
          "td_vote_count": np.asarray(dd["td_vote_count"]), "td_soft_score": np.asarray(dd["td_soft_score"]),
          "td_soft_label": np.asarray(dd["td_soft_label"]), "raw_spectral_dump_mask": np.asarray(dd["raw_spectral_dump_mask"]),
          "sparse_frame_idx": np.asarray(dd["sparse_frame_idx"])}

@@ -44,8 +44,12 @@ def frame_rel_err(a, b):
 def test_full_planes_match_reference_golden(torch_cuda, name):
     g, meta, pcm, params = load_golden(name)
     eng = make_engine(params)
-    plan, out = eng.run_clips([pcm], ALL_PLANES)
+    snr = "snr_gate_t" in g
+    plan, out = eng.run_clips([pcm], ALL_PLANES + (("snr_mode", "snr_gate") if snr else ()))
     T = plan.nF
+    if snr:     # frame SNR over the mode bins and its gate (rain_signal_processor.py:1064-1077)
+        np.testing.assert_allclose(out["snr_mode"], g["snr_mode_t"], rtol=1e-5)
+        np.testing.assert_allclose(out["snr_gate"], g["snr_gate_t"], rtol=1e-5, atol=1e-7)
     S = out["S"].view(np.complex64).reshape(T, -1)
     # spectra: <= 1e-6 of the frame maximum (float64 FFT rounded to complex64; bit-equal in practice)
     assert frame_rel_err(S, g["S"]) <= 1e-6

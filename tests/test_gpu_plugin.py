@@ -338,3 +338,8 @@ def test_det_debug_key_set_and_soft_labels_match_reference():
     for k in ("td_vote_count", "td_soft_score", "td_soft_label", "raw_spectral_dump_mask", "sparse_frame_idx"):
         assert dd[k].dtype == g[k].dtype and np.array_equal(dd[k], g[k]), k
     assert int(g["td_vote_count"].sum()) > 0
+    # the suppressor-side debug dictionary and the state itself: same keys, except the per-frame statistics of the gain
+    # stages (debug["gain_dbg"]: medians / percentiles of G_raw, G_freq, G_time), which are not produced
+    assert set(meta["debug_keys"]) - set(st["debug"]) == {"gain_dbg"}
+    assert set(st["debug"]) <= set(meta["debug_keys"])
+    assert set(st) == set(meta["state_keys"])
