@@ -179,8 +179,6 @@ class ResolvedParams:
                                       "are not implemented on the CUDA path")
         if str(dv.get("td_input_mode", "default")).lower() != "default":
             raise NotImplementedError("td_input_mode other than 'default' is not implemented on the CUDA path")
-        if int(dv.get("feature_dump_level", 0)) > 0:
-            raise NotImplementedError("detector feature dumps (feature_dump_level > 0) are not implemented on the CUDA path")
 
         P = _lib.AptParams()
         P.abi_version = _lib.ABI_VERSION

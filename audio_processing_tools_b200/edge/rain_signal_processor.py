@@ -90,6 +90,8 @@ class SpectralNoiseProcessor:
         dv = DetectorView(cfg)
         keep_debug = bool(cfg.return_debug) or bool(cfg.debug_enable)
         keep_det = bool(cfg.return_detector_debug) or bool(cfg.debug_enable)
+        # the features payload carries the detector-side dump when feature_dump_level > 0: its arrays are needed then
+        need_det = keep_det or (bool(cfg.dump_features) and int(dv.get("feature_dump_level", 0)) > 0)
         keep_spectra = bool(cfg.return_spectra)
         keep_noise = bool(cfg.return_noise_psd)
         keep_filt = bool(cfg.return_filtered_audio)
@@ -103,10 +105,10 @@ class SpectralNoiseProcessor:
                     want += ["snr_mode", "snr_gate"]
         if keep_noise and "noise_psd" not in want:
             want.append("noise_psd")
-        peaks = keep_det and bool(dv.get("peak_features_enable", False))
+        peaks = need_det and bool(dv.get("peak_features_enable", False))
         if peaks:
             want += ["peak_ratio", "peak_gate_score", "peak_valid_count", "peak_count_by_mode"]
-        if keep_det:
+        if need_det:
             want += ["norm_flux", "score", "td", "gate"]
             if dv.get("raw_spectral_shape_enable", True):
                 want.append("raw")
@@ -145,10 +147,11 @@ class SpectralNoiseProcessor:
                 "rain_conf": out["rain_conf"][f0:f1].copy(),
                 "noise_conf": out["noise_conf"][f0:f1].copy(),
             }
+            dd = self._det_debug(out, f0, f1, rp, dv) if need_det else None
             if keep_det:
-                res["det_debug"] = self._det_debug(out, f0, f1, rp, dv)
+                res["det_debug"] = dd
             if bool(cfg.dump_features):
-                res["features"] = self._features(cfg, times, res["frame_class"], res["rain_conf"], res["noise_conf"], res.get("det_debug"))
+                res["features"] = self._features(cfg, times, res["frame_class"], res["rain_conf"], res["noise_conf"], dd)
             if keep_debug:
                 res["debug"] = self._debug(out, f0, f1, rp, dv, times)
             if keep_filt:
@@ -327,8 +330,36 @@ class SpectralNoiseProcessor:
             "td_apply_input_prefilter": bool(dv.get("td_apply_input_prefilter", True)),
             "td_prefilter_mode": str(dv.get("td_prefilter_mode", dv.get("pre_filter_mode", "none"))).lower(),
             "clip_spectral_occupancy_enable": bool(dv.get("clip_spectral_occupancy_enable", False)),
-            "feature_dump": {},          # feature_dump_level = 0 (higher levels are refused): the reference attaches an empty dict
         })
+        # detector-side feature dump (rain_frame_classifier.py:1096-1162): empty at feature_dump_level = 0, else the dense
+        # per-frame arrays and / or the raw spectral features at the sparse frames (the clip summary needs
+        # clip_spectral_occupancy_enable, which is refused)
+        fd: Dict[str, Any] = {}
+        if int(dv.get("feature_dump_level", 0)) > 0:
+            if d["feature_dump_dense_enable"]:
+                for k in ("primary_mode_flux", "support_mode_flux_1", "support_mode_flux_2", "support_mode_flux_3",
+                          "support_mode_flux_4", "td_block_energy_crest", "td_block_peak_width_50",
+                          "td_block_post_pre_energy_ratio", "td_gate_mask"):
+                    fd[k] = d[k]
+                if bool(dv.get("feature_dump_include_frame_class", True)):
+                    fd["frame_class"] = d["frame_class"]
+                if bool(dv.get("feature_dump_include_td_soft", False)):
+                    for k in ("td_crest_factor", "td_kurtosis", "td_vote_count", "td_soft_score"):
+                        fd[k] = d[k]
+            if sparse_on:
+                idx = d["sparse_frame_idx"]
+                fd["sparse_frame_idx"] = idx
+                basic = ("raw_spectral_centroid_hz", "raw_rain_band_ratio", "raw_spectral_rolloff_hz")
+                inc_basic = bool(dv.get("feature_dump_include_raw_spectral_basic", False))
+                if bool(dv.get("feature_dump_include_raw_spectral_frame_features", True)):
+                    for name in RAW_SPECTRAL_FEATURE_NAMES:
+                        if name in basic and not inc_basic:
+                            continue
+                        fd["sparse_" + name] = d[name][idx]
+                elif inc_basic:
+                    for name in basic:
+                        fd["sparse_" + name] = d[name][idx]
+        d["feature_dump"] = fd
         return d
 
     def _debug(self, out, f0, f1, rp, dv, times) -> Dict[str, Any]:

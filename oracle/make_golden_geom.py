@@ -110,6 +110,28 @@ def smoothing_cases():
         json.dump(index, f, indent=1)
 
 
+def feature_dump_case():
+    """dump_features with the detector-side dump on (feature_dump_level = 1, dense + sparse, soft TD votes), decimated by 2:
+    every array of state["features"] (rain_frame_classifier.py:1096-1162, rain_signal_processor.py:723-787)."""
+    import hashlib
+    import json
+    from audio_processing_tools.edge.rain_signal_processor import RainDetectorProcessor
+    from audio_processing_tools_b200.synth import default_params, pcm_to_f32
+    seconds, seed, lam = 8, 64, 10.0
+    pcm = synth_clip_i16(seconds, seed, lam)
+    det = {"feature_dump_level": 1, "feature_dump_sparse_enable": True, "feature_dump_sparse_gate_threshold": 3.0,
+           "feature_dump_include_td_soft": True, "td_soft_enable": True}
+    params = default_params(check_duration=seconds, dump_features=True, feature_decim=2)
+    params["detector"] = dict(params["detector"], **det)
+    _, state = RainDetectorProcessor().run(pcm_to_f32(pcm), params)
+    d = {"feat_" + k: np.asarray(v) for k, v in state["features"].items()}
+    d["meta"] = np.array(json.dumps({"seconds": seconds, "seed": seed, "lam": lam, "feature_decim": 2, "detector": det,
+                                     "pcm_sha1": hashlib.sha1(pcm.tobytes()).hexdigest(), "numpy": np.__version__}))
+    path = os.path.join(mg.OUT, "featuredump_s64.npz")
+    np.savez_compressed(path, **d)
+    print(path, len(d) - 1, "arrays", {k: v.shape for k, v in d.items() if k != "meta"}, flush=True)
+
+
 def detdebug_case():
     """The full key set of the detector's debug dictionary (state["det_debug"]) with the scalar echoes, and the soft TD
     label arrays under td_soft_enable (rain_frame_classifier.py:85-110, :1000-1047)."""
@@ -139,6 +161,7 @@ def detdebug_case():
 
 if __name__ == "__main__":
     detdebug_case()
+    feature_dump_case()
     main()
     features_case()
     adaptive_q_cases()

@@ -343,3 +343,36 @@ def test_det_debug_key_set_and_soft_labels_match_reference():
     assert set(meta["debug_keys"]) - set(st["debug"]) == {"gain_dbg"}
     assert set(st["debug"]) <= set(meta["debug_keys"])
     assert set(st) == set(meta["state_keys"])
+
+
+def test_feature_dump_payload_matches_reference():
+    """dump_features with feature_dump_level = 1 (dense + sparse detector dump, soft TD votes), feature_decim = 2: the
+    payload's key set equals the reference's and every array matches (integer / boolean arrays and the TD features bit for
+    bit, kurtosis and the raw spectral features at their tolerance) -- tests/golden/featuredump_s64.npz."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from audio_processing_tools_b200.edge.rain_signal_processor import RainDetectorProcessor
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "featuredump_s64.npz"), allow_pickle=False))
+    meta = json.loads(str(g["meta"]))
+    pcm = synth_clip_i16(meta["seconds"], meta["seed"], meta["lam"])
+    assert hashlib.sha1(pcm.tobytes()).hexdigest() == meta["pcm_sha1"]
+    params = default_params(check_duration=meta["seconds"], dump_features=True, feature_decim=meta["feature_decim"])
+    params["detector"] = dict(params["detector"], **meta["detector"])
+    _, st = RainDetectorProcessor().run(pcm_to_f32(pcm), params)
+    f = st["features"]
+    assert "det_debug" not in st                      # the dump rides in the features payload, not in the debug state
+    assert {"feat_" + k for k in f} == set(g) - {"meta"}
+    for k, v in f.items():
+        ref = g["feat_" + k]
+        assert v.shape == ref.shape and v.dtype == ref.dtype, k
+        if v.dtype.kind in "biu" or k.startswith("td_block") or k in ("td_crest_factor", "frame_times", "rain_conf", "noise_conf"):
+            assert np.array_equal(v, ref), k
+        elif k == "td_kurtosis":
+            np.testing.assert_allclose(v, ref, rtol=2e-6, atol=1e-6, err_msg=k)
+        elif k.startswith("sparse_raw"):
+            np.testing.assert_allclose(v, ref, rtol=1e-6, atol=1e-30, err_msg=k)
+        else:
+            np.testing.assert_allclose(v, ref, rtol=1e-6, atol=1e-7, err_msg=k)
+    assert f["sparse_frame_idx"].size > 0
