@@ -66,7 +66,7 @@ class AptParams(C.Structure):
         ("adaptive_q", C.c_int32), ("pre_smooth_frames", C.c_int32),
         ("aq_base", C.c_double), ("aq_min", C.c_double), ("aq_alpha", C.c_double),
         ("median_frames", C.c_int32), ("snr_gating", C.c_int32), ("snr_gating_snr1", C.c_float),
-        ("snr_mask", C.c_uint32 * 4), ("reserved1", C.c_int32),
+        ("snr_mask", C.c_uint32 * 4), ("bypass_classifier", C.c_int32),
         ("window", C.c_void_p), ("freqs", C.c_void_p),
     ]
 

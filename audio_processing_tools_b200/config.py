@@ -157,8 +157,7 @@ def _contiguous_bins(mask):
 
 
 _UNSUPPORTED_DETECTOR_FLAGS = ("feature_dump_include_peak_payload", "flux_modes_winsor_enable",
-                               "td_envelope_features_enable", "bypass_classifier",
-                               "clip_spectral_occupancy_enable")
+                               "td_envelope_features_enable", "clip_spectral_occupancy_enable")
 
 
 class ResolvedParams:
@@ -326,6 +325,7 @@ class ResolvedParams:
         # --- suppressor gain (_compute_gain, rain_signal_processor.py:400-533).  noise_conf is binary on this
         # path (1 - rain_conf), so the per-frame scalars take two values; they are formed here with the same
         # numpy float32 / Python-float promotions the reference applies.
+        P.bypass_classifier = int(bool(dv.get("bypass_classifier", False)))   # rain_signal_processor.py:846-857
         P.snr_gating = int(bool(cfg.snr_gating_enable))           # rain_signal_processor.py:1050-1077
         if P.snr_gating:
             pwr = float(cfg.snr_gating_power)

@@ -367,6 +367,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     d.trk_q = p->trk_q; d.trk_nq = p->trk_neg_one_minus_q; d.trk_maxr = p->trk_maxr;
     d.ema_up = p->ema_up; d.ema_down = p->ema_down; d.warm_need = p->warmup_need; d.eps32 = p->eps_f32;
     d.adaptive_q = p->adaptive_q; d.aq_base = p->aq_base; d.aq_min = p->aq_min; d.aq_alpha = p->aq_alpha;
+    d.bypass_cls = p->bypass_classifier;
     d.snr_gate = p->snr_gating; d.snr1 = p->snr_gating_snr1;
     for (int i = 0; i < 4; i++) d.snr_mask[i] = p->snr_mask[i];
     d.pre_smooth = p->pre_smooth_frames > 1 ? p->pre_smooth_frames : 0;

@@ -51,6 +51,7 @@ struct DevParams {
     int pre_smooth, median;                              // pre_smooth_frames / median_frames (<= 1: off)
     int snr_gate; float snr1; uint32_t snr_mask[4];      // spectral SNR gating of the oversubtraction
     int td_g;                                            // stride of the TD block statistics (128, or 64 when the hop asks for it)
+    int bypass_cls;                                      // bypass_classifier: every frame NOISE
     int warm_need;
     float eps32;
     int use_norm, ratio_db;
@@ -2084,7 +2085,8 @@ __global__ void __launch_bounds__(256) decide_kernel(const __grid_constant__ Dev
     int8_t cls = 1;
     if (nc >= p.noise_hi && weak && !is_rain) cls = 0;
     if (is_rain) cls = 2;
-    io.frame_class[g] = cls; io.rain_conf[g] = rc; io.noise_conf[g] = nc;
+    if (p.bypass_cls) { cls = 0; io.frame_class[g] = 0; io.rain_conf[g] = 0.0f; io.noise_conf[g] = 1.0f; }
+    else { io.frame_class[g] = cls; io.rain_conf[g] = rc; io.noise_conf[g] = nc; }
     if (io.score) io.score[g] = score;
     if (io.gate) io.gate[g] = gate ? 1 : 0;
     if (io.norm_flux)

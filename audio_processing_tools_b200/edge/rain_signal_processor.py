@@ -92,6 +92,7 @@ class SpectralNoiseProcessor:
         keep_det = bool(cfg.return_detector_debug) or bool(cfg.debug_enable)
         # the features payload carries the detector-side dump when feature_dump_level > 0: its arrays are needed then
         need_det = keep_det or (bool(cfg.dump_features) and int(dv.get("feature_dump_level", 0)) > 0)
+        bypass_cls = bool(dv.get("bypass_classifier", False))
         keep_spectra = bool(cfg.return_spectra)
         keep_noise = bool(cfg.return_noise_psd)
         keep_filt = bool(cfg.return_filtered_audio)
@@ -108,7 +109,7 @@ class SpectralNoiseProcessor:
         peaks = need_det and bool(dv.get("peak_features_enable", False))
         if peaks:
             want += ["peak_ratio", "peak_gate_score", "peak_valid_count", "peak_count_by_mode"]
-        if need_det:
+        if need_det and not bypass_cls:
             want += ["norm_flux", "score", "td", "gate"]
             if dv.get("raw_spectral_shape_enable", True):
                 want.append("raw")
@@ -147,7 +148,14 @@ class SpectralNoiseProcessor:
                 "rain_conf": out["rain_conf"][f0:f1].copy(),
                 "noise_conf": out["noise_conf"][f0:f1].copy(),
             }
-            dd = self._det_debug(out, f0, f1, rp, dv) if need_det else None
+            if need_det and bypass_cls:
+                # bypass_classifier (rain_signal_processor.py:846-857): the reference's placeholder dictionary
+                fcn = res["frame_class"]
+                dd = {"frame_class": fcn, "frame_class_name": np.array(["noise"] * T, dtype=object),
+                      "rain_score_raw": np.zeros(T, dtype=np.float32), "is_rain_raw": np.zeros(T, dtype=bool),
+                      "onset_mask": np.zeros(T, dtype=bool), "onset_indices": np.zeros(0, dtype=np.int32)}
+            else:
+                dd = self._det_debug(out, f0, f1, rp, dv) if need_det else None
             if keep_det:
                 res["det_debug"] = dd
             if bool(cfg.dump_features):
@@ -371,8 +379,9 @@ class SpectralNoiseProcessor:
             "suppressor_params": dict(cfg.suppressor or {}),
             "times_s": times,
             "freqs": rp.freqs.copy(),
-            "detector_noise_psd": self._embed(out["det_noise_psd"][f0:f1], rp),
-            "detector_noise_psd_lag": self._embed(out["det_noise_lag"][f0:f1], rp),
+            # (no detector pass under bypass_classifier: the reference leaves both None)
+            "detector_noise_psd": None if bool(dv.get("bypass_classifier", False)) else self._embed(out["det_noise_psd"][f0:f1], rp),
+            "detector_noise_psd_lag": None if bool(dv.get("bypass_classifier", False)) else self._embed(out["det_noise_lag"][f0:f1], rp),
             "detector_use_noise_norm": bool(dv.get("detector_use_noise_norm", True)),
             "detector_noise_norm_mode": str(cfg.detector_noise_norm_mode).lower(),
             "suppressor_bypass": bool(cfg.suppressor_bypass),
@@ -391,7 +400,7 @@ class SpectralNoiseProcessor:
             "pre_filter_band": (float(cfg.operating_band[0]), float(cfg.operating_band[1])),
             "noise_psd_max_ratio": float(cfg.noise_psd_max_ratio),
             "td_soft_enable": bool(dv.get("td_soft_enable", False)),
-            "bypass_classifier": False,                 # (bypass_classifier = True is refused)
+            "bypass_classifier": bool(dv.get("bypass_classifier", False)),
             "features_available": bool(cfg.dump_features),
             # frame SNR and gate of the spectral SNR gating (:1050-1077); None when it is off, as in the reference
             "snr_mode": out["snr_mode"][f0:f1].copy() if "snr_mode" in out else None,

@@ -128,7 +128,7 @@ typedef struct apt_params_t {
     int32_t snr_gating;
     float   snr_gating_snr1;
     uint32_t snr_mask[4];
-    int32_t reserved1;
+    int32_t bypass_classifier;                 /* every frame NOISE, rain_conf 0, noise_conf 1 (:846-857): the suppressor alone */
     /* host pointers, copied at plan creation */
     const double* window;                      /* n_fft analysis window (scipy get_window) */
     const float*  freqs;                       /* n_fft/2+1 bin frequencies as float32 */

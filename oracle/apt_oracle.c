@@ -82,6 +82,8 @@ typedef struct {
     double aq_base, aq_min, aq_alpha;
     int32_t pre_smooth_frames;                /* _time_smooth before the tracker (:366-379, :690-692); <= 1: off */
     int32_t median_frames;                    /* _causal_time_median_filter after it (:381-396, :717-719); <= 1: off */
+    int32_t bypass_classifier;                /* every frame NOISE, rain_conf 0 (rain_signal_processor.py:846-857) */
+    int32_t reserved;
 } orc_params;
 
 typedef struct {
@@ -814,6 +816,7 @@ int orc_process(const orc_params *p, const double *window, const float *freqs,
         int8_t cls = 1;
         if (nc >= p->noise_hi && weak && !is_rain) cls = 0;
         if (is_rain) cls = 2;
+        if (p->bypass_classifier) { cls = 0; rc = 0.0f; nc = 1.0f; }
         o->frame_class[t] = cls; o->rain_conf[t] = rc; o->noise_conf[t] = nc;
         if (o->gate) o->gate[t] = (uint8_t)gate;
         excl[t] = cls != 0;                     /* is_rain_for_psd = ~is_noise */

@@ -96,13 +96,16 @@ def smoothing_cases():
     for name, seconds, seed, lam, extra in (
             ("alt_s35_l3_20s_presmooth3", 20, 35, 3.0, {"pre_smooth_frames": 3}),
             ("alt_s36_l10_20s_median5", 20, 36, 10.0, {"median_frames": 5}),
-            ("alt_s37_l3_20s_smooth_all", 20, 37, 3.0, {"pre_smooth_frames": 4, "median_frames": 4, "adaptive_q_enable": True})):
+            ("alt_s37_l3_20s_smooth_all", 20, 37, 3.0, {"pre_smooth_frames": 4, "median_frames": 4, "adaptive_q_enable": True}),
+            # bypass_classifier (:846-857): every frame NOISE, the suppressor's noise PSD alone (level 0: labels + clip statistics)
+            ("alt_s40_l10_20s_bypasscls", 20, 40, 10.0, {"detector": {"bypass_classifier": True}})):
         pcm = synth_clip_i16(seconds, seed, lam)
         metrics, state, params = mg.run_reference(pcm, seconds, extra)
-        d = mg.pack(pcm, seconds, seed, lam, metrics, state, level=1, params=params)
+        level = 0 if "detector" in extra else 1
+        d = mg.pack(pcm, seconds, seed, lam, metrics, state, level=level, params=params)
         np.savez_compressed(os.path.join(mg.OUT, name + ".npz"), **d)
         fc = d["frame_class"]
-        entry = {"name": name, "seconds": seconds, "seed": seed, "lam": lam, "level": 1, "T": int(fc.size),
+        entry = {"name": name, "seconds": seconds, "seed": seed, "lam": lam, "level": level, "T": int(fc.size),
                  "rain": int((fc == 2).sum()), "uncertain": int((fc == 1).sum()), "noise": int((fc == 0).sum()), "extra": extra}
         index = [e for e in index if e["name"] != name] + [entry]
         print(entry, os.path.getsize(os.path.join(mg.OUT, name + ".npz")) // 1024, "KiB", flush=True)

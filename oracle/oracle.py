@@ -62,6 +62,7 @@ class OrcParams(C.Structure):
         ("suppressor_bypass", C.c_int32), ("adaptive_q", C.c_int32),
         ("aq_base", C.c_double), ("aq_min", C.c_double), ("aq_alpha", C.c_double),
         ("pre_smooth_frames", C.c_int32), ("median_frames", C.c_int32),
+        ("bypass_classifier", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -141,8 +142,7 @@ def resolve(params):
     for flag, bad in (("process_dtype", "float64"),):
         if cfg[flag] == bad:
             raise NotImplementedError(f"oracle: {flag}={bad!r} not restated")
-    for name in ("peak_features_enable", "flux_modes_winsor_enable", "td_envelope_features_enable",
-                 "bypass_classifier"):
+    for name in ("peak_features_enable", "flux_modes_winsor_enable", "td_envelope_features_enable"):
         if bool(dget(name, False)):
             raise NotImplementedError(f"oracle: detector.{name} not restated")
     if str(dget("td_input_mode", "default")).lower() != "default":
@@ -199,6 +199,7 @@ def make_params(params):
     P.aq_base = q
     P.aq_min = float(np.clip(float(cfg["adaptive_q_min"]), 1e-4, q))
     P.aq_alpha = float(np.clip(float(cfg["adaptive_q_alpha"]), 0.0, 1.0))
+    P.bypass_classifier = int(bool(dget("bypass_classifier", False)))   # rain_signal_processor.py:846-857
     P.pre_smooth_frames = int(cfg["pre_smooth_frames"] or 0)      # rain_signal_processor.py:690-692
     P.median_frames = int(cfg["median_frames"] or 0)              # :717-719
     P.warmup_need = max(10, W // 2)
