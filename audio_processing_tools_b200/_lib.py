@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_PKG, "libapt_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 MAX_MODES, MAX_SOS, N_RAW, N_TD, N_STATS = 8, 4, 21, 5, 8
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_GAIN_TAPS = 9
 MAX_PRE_SMOOTH, MAX_MEDIAN = 16, 31
 STAGE_FEATURES, STAGE_FULL = 1, 2
@@ -66,6 +66,7 @@ class AptParams(C.Structure):
         ("adaptive_q", C.c_int32), ("pre_smooth_frames", C.c_int32),
         ("aq_base", C.c_double), ("aq_min", C.c_double), ("aq_alpha", C.c_double),
         ("median_frames", C.c_int32), ("snr_gating", C.c_int32), ("snr_gating_snr1", C.c_float),
+        ("snr_gating_power", C.c_float),
         ("snr_mask", C.c_uint32 * 4), ("bypass_classifier", C.c_int32),
         ("window", C.c_void_p), ("freqs", C.c_void_p),
     ]

@@ -329,8 +329,7 @@ class ResolvedParams:
         P.snr_gating = int(bool(cfg.snr_gating_enable))           # rain_signal_processor.py:1050-1077
         if P.snr_gating:
             pwr = float(cfg.snr_gating_power)
-            if pwr != 1.0 and np.isfinite(pwr) and pwr > 0.0:
-                raise NotImplementedError("snr_gating_power != 1 is not implemented on the CUDA path")
+            P.snr_gating_power = f32(pwr) if (pwr != 1.0 and np.isfinite(pwr) and pwr > 0.0) else f32(1.0)   # :1073-1075
             Kb = int(P.band_hi - P.band_lo + 1)
             if Kb > 128:
                 raise NotImplementedError("snr_gating_enable needs an operating band of at most 128 bins")

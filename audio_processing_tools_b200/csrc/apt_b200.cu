@@ -369,6 +369,7 @@ int apt_plan_create(apt_ctx* ctx, const apt_params_t* p, int n_clips, const int6
     d.adaptive_q = p->adaptive_q; d.aq_base = p->aq_base; d.aq_min = p->aq_min; d.aq_alpha = p->aq_alpha;
     d.bypass_cls = p->bypass_classifier;
     d.snr_gate = p->snr_gating; d.snr1 = p->snr_gating_snr1;
+    d.snr_pow = (p->snr_gating_power > 0.0f && isfinite(p->snr_gating_power)) ? p->snr_gating_power : 1.0f;
     for (int i = 0; i < 4; i++) d.snr_mask[i] = p->snr_mask[i];
     d.pre_smooth = p->pre_smooth_frames > 1 ? p->pre_smooth_frames : 0;
     d.median = p->median_frames > 1 ? p->median_frames : 0;
@@ -1682,9 +1683,11 @@ extern "C" int apt_bne_run(apt_ctx* ctx, const apt_bne_params_t* p, int n_clips,
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<int64_t> so(n_clips + 1, 0), fo(n_clips + 1, 0), sg(n_clips + 1, 0);
     int64_t max_fr = 1;
+    int seg_frames = BNE_SEG;
+    if (const char* e = getenv("APT_BNE_SEG")) seg_frames = std::max(1, std::min(4096, atoi(e)));
     for (int c = 0; c < n_clips; c++) {
         const int64_t nf = clip_len[c] / N;
-        so[c + 1] = so[c] + clip_len[c]; fo[c + 1] = fo[c] + nf; sg[c + 1] = sg[c] + (nf + BNE_SEG - 1) / BNE_SEG;
+        so[c + 1] = so[c] + clip_len[c]; fo[c + 1] = fo[c] + nf; sg[c + 1] = sg[c] + (nf + seg_frames - 1) / seg_frames;
         max_fr = std::max(max_fr, nf);
     }
     PoolBuf<int64_t> d_so(ctx, 10), d_fo(ctx, 11), d_sg(ctx, 12); PoolBuf<double> d_xhp(ctx, 13), d_subEh(ctx, 14), d_fftq(ctx, 15);
@@ -1698,13 +1701,33 @@ extern "C" int apt_bne_run(apt_ctx* ctx, const apt_bne_params_t* p, int n_clips,
     CUDA_OK(ctx, d_subEh.alloc(nf_tot * BNE_MAX_S)); CUDA_OK(ctx, d_fftq.alloc(nf_tot * 4));
     const int64_t nseg = sg[n_clips];
     if (nseg > 0) {
-        if (is_f32) bne_filter_kernel<float><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, (const float*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
-        else bne_filter_kernel<int16_t><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, (const int16_t*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
-        const size_t smem = sizeof(cx<double>) * (size_t)N + sizeof(double) * (size_t)(N + 2);
-        CUDA_OK(ctx, cudaFuncSetAttribute(bne_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bne_fft_kernel<<<dim3((unsigned)max_fr, (unsigned)n_clips), BNE_NT, smem, st>>>(*p, d_so.p, d_fo.p, d_xhp.p, d_tw.p, d_fftq.p);
+        if (is_f32) bne_filter_kernel<float><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, seg_frames, (const float*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
+        else bne_filter_kernel<int16_t><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, seg_frames, (const int16_t*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
+        const char* e_gen = getenv("APT_BNE_FFT_GENERIC");
+        if (N == 256 && !(e_gen && atoi(e_gen) != 0)) {
+            // the sensor's frame length: 8 lanes per frame, 32 frames per CTA (APT_BNE_FFT_GENERIC=1 keeps the generic kernel)
+            const size_t smem = bne_fft256_smem();
+            CUDA_OK(ctx, cudaFuncSetAttribute(bne_fft256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bne_fft256_kernel<<<dim3((unsigned)((max_fr + BNE_F256_TF - 1) / BNE_F256_TF), (unsigned)n_clips), BNE_F256_NT, smem, st>>>(
+                *p, d_so.p, d_fo.p, d_xhp.p, d_tw.p, d_fftq.p);
+        } else if (N == 512 && !(e_gen && atoi(e_gen) != 0)) {
+            // the reference's default frame length: 16 lanes per frame, 16 frames per CTA
+            const size_t smem = bne_fft512_smem();
+            CUDA_OK(ctx, cudaFuncSetAttribute(bne_fft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bne_fft512_kernel<<<dim3((unsigned)((max_fr + BNE_F512_TF - 1) / BNE_F512_TF), (unsigned)n_clips), BNE_F512_NT, smem, st>>>(
+                *p, d_so.p, d_fo.p, d_xhp.p, d_tw.p, d_fftq.p);
+        } else {
+            const size_t smem = sizeof(cx<double>) * (size_t)N + sizeof(double) * (size_t)(N + 2);
+            CUDA_OK(ctx, cudaFuncSetAttribute(bne_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bne_fft_kernel<<<dim3((unsigned)max_fr, (unsigned)n_clips), BNE_NT, smem, st>>>(*p, d_so.p, d_fo.p, d_xhp.p, d_tw.p, d_fftq.p);
+        }
     }
-    bne_state_kernel<<<(n_clips + 63) / 64, 64, 0, st>>>(*p, n_clips, d_fo.p, d_subEh.p, dev_subE, d_fftq.p, dev_frame_out, dev_mask, dev_stats);
+    // one warp per clip; APT_BNE_STATE_SERIAL=1 keeps the one-thread-per-clip kernel (bit-equal, for comparison)
+    const char* e_serial = getenv("APT_BNE_STATE_SERIAL");
+    if (e_serial && atoi(e_serial) != 0)
+        bne_state_kernel<<<(n_clips + 63) / 64, 64, 0, st>>>(*p, n_clips, d_fo.p, d_subEh.p, dev_subE, d_fftq.p, dev_frame_out, dev_mask, dev_stats);
+    else
+        bne_state_warp_kernel<<<n_clips, 32, 0, st>>>(*p, n_clips, d_fo.p, d_subEh.p, dev_subE, d_fftq.p, dev_frame_out, dev_mask, dev_stats);
     CUDA_OK(ctx, cudaGetLastError());
     CUDA_OK(ctx, cudaStreamSynchronize(st));
     return 0;

@@ -49,7 +49,7 @@ struct DevParams {
     double ema_up, ema_down;
     int adaptive_q; double aq_base, aq_min, aq_alpha;   // adaptive quantile of pass 2
     int pre_smooth, median;                              // pre_smooth_frames / median_frames (<= 1: off)
-    int snr_gate; float snr1; uint32_t snr_mask[4];      // spectral SNR gating of the oversubtraction
+    int snr_gate; float snr1; float snr_pow; uint32_t snr_mask[4];      // spectral SNR gating of the oversubtraction
     int td_g;                                            // stride of the TD block statistics (128, or 64 when the hop asks for it)
     int bypass_cls;                                      // bypass_classifier: every frame NOISE
     int warm_need;
@@ -2393,7 +2393,10 @@ __global__ void __launch_bounds__(256) gain_kernel(const __grid_constant__ DevPa
                         else { pm += s_pn[tid][0][k]; nm += s_pn[tid][1][k]; }
                     }
                 const float snr = f_div(pm, nm + p.gain_eps);
-                const float gate = f_div(snr, snr + p.snr1);
+                float gate = f_div(snr, snr + p.snr1);
+                // snr_gating_power (:1073-1075): np.power on the clipped float32 gate; evaluated in float64 and rounded once
+                // (numpy's float32 pow is within an ulp of that)
+                if (p.snr_pow != 1.0f) gate = d2f(pow((double)f_min(f_max(gate, 0.0f), 1.0f), (double)p.snr_pow));
                 s_sg[tid] = f_min(f_max(gate, 0.0f), 1.0f);
                 if (io.snr_mode) { io.snr_mode[f0 + tb + tid] = snr; io.snr_gate[f0 + tb + tid] = s_sg[tid]; }
             }

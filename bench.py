@@ -310,10 +310,10 @@ def run_neighbour(args, torch, local_rank, dev):
         batch = [base[i % 8] for i in range(n)]
         proc = BandNoiseEstimatorProcessor()
         call = lambda: proc.run_batch(batch, {"sample_rate": FS})
-        N = 256
+        N = 512                       # BandNoiseEstimatorConfig.frame_len, the reference's default
         frames = n * (int(FS * sec) // N)
         bytes_algo = n * int(FS * sec) * 2 + frames * (_lib.BNE_FRAME_F * 8 + 1 + _lib.BNE_MAX_S * 8)
-        what = f"band noise estimator (edge/band_noise_estimator.py), {n} x {sec:g}s clips, frame 256"
+        what = f"band noise estimator (edge/band_noise_estimator.py), {n} x {sec:g}s clips, frame {N} (the reference default)"
 
         def cpu(nc):
             if reference_available():

@@ -41,7 +41,7 @@ extern "C" {
 #define APT_MAX_PRE_SMOOTH 16
 #define APT_MAX_MEDIAN 31
 #define APT_MAX_GAIN_TAPS 9
-#define APT_ABI_VERSION 9
+#define APT_ABI_VERSION 10
 
 typedef struct apt_ctx apt_ctx;
 typedef struct apt_plan apt_plan_t;
@@ -122,11 +122,12 @@ typedef struct apt_params_t {
     double  aq_base, aq_min, aq_alpha;
     /* causal median over time of both passes' noise PSD (median_frames, :381-396, :717-719), <= 1: off, at most APT_MAX_MEDIAN */
     int32_t median_frames;
-    /* spectral SNR gating of the oversubtraction (snr_gating_enable, :1050-1077, :433-438; snr_gating_power = 1 only):
-     * sg[t] = clip(s / (s + snr1), 0, 1), s = sum(P[mask]) / (sum(N_eff[mask]) + eps), oversub[t] *= 1 - sg[t];
+    /* spectral SNR gating of the oversubtraction (snr_gating_enable, :1050-1077, :433-438):
+     * sg[t] = clip(clip(s / (s + snr1), 0, 1) ^ snr_gating_power, 0, 1) (the power only when it is not 1), s = sum(P[mask]) / (sum(N_eff[mask]) + eps), oversub[t] *= 1 - sg[t];
      * mask = bit k of snr_mask for band bin k (union of the mode bands, or the whole band), at most 128 band bins */
     int32_t snr_gating;
     float   snr_gating_snr1;
+    float   snr_gating_power;                  /* 1: no power step (:1073-1075) */
     uint32_t snr_mask[4];
     int32_t bypass_classifier;                 /* every frame NOISE, rain_conf 0, noise_conf 1 (:846-857): the suppressor alone */
     /* host pointers, copied at plan creation */

@@ -69,7 +69,10 @@ def adaptive_q_cases():
             ("alt_s33_l3_10s_adaptq", 10, 33, 3.0, {"adaptive_q_enable": True}),
             ("alt_s34_l10_10s_adaptq", 10, 34, 10.0, {"adaptive_q_enable": True, "adaptive_q_min": 0.05, "adaptive_q_alpha": 0.9, "q": 0.3}),
             # spectral SNR gating of the oversubtraction (:1050-1077): seen in the gain plane G_band
-            ("alt_s39_l3_10s_snrgate", 10, 39, 3.0, {"snr_gating_enable": True, "snr_gating_snr1": 2.0})):
+            ("alt_s39_l3_10s_snrgate", 10, 39, 3.0, {"snr_gating_enable": True, "snr_gating_snr1": 2.0}),
+            # the same with the power step on the gate (:1073-1075) over the whole operating band
+            ("alt_s40_l10_10s_snrgate_pow", 10, 40, 10.0, {"snr_gating_enable": True, "snr_gating_snr1": 0.5, "snr_gating_power": 2.5,
+                                                           "snr_gating_use_mode_bands": False})):
         pcm = synth_clip_i16(seconds, seed, lam)
         metrics, state, params = mg.run_reference(pcm, seconds, extra, spectra=True)
         d = mg.pack(pcm, seconds, seed, lam, metrics, state, level=2, params=params)

@@ -474,6 +474,48 @@ def test_band_noise_batch_and_int16(torch_cuda):
         assert np.array_equal(s1["rain_submask"], st["rain_submask"])
 
 
+def test_band_noise_warp_kernel_equals_serial(torch_cuda, monkeypatch):
+    """The warp-per-clip state machine (ring buffer and its sorted copy spread over the lanes) and the 8-lanes-per-frame
+    FFT of the band noise estimator against the kernels they replace (APT_BNE_STATE_SERIAL / APT_BNE_FFT_GENERIC keep
+    those): with the same FFT the state machine's outputs are bit-equal -- every array, the counters and the adaptive
+    quantile; the two FFT algorithms agree to 1e-12 relative on the band sums and give the same flags."""
+    from audio_processing_tools_b200.edge.band_noise_processor import BandNoiseEstimatorProcessor
+    clips = [synth_clip_i16(41.0, 181, 3.0), synth_clip_i16(0.03, 182, 3.0), synth_clip_i16(63.7, 183, 30.0),
+             synth_clip_i16(25.2, 184, 0.0), synth_clip_i16(12.0, 185, 10.0)]
+    variants = [{},                                                                   # frame 512, S = 4
+                {"noise_buffer_ttl_frames": 12, "W": 24, "W_min": 6},                 # entries expire
+                {"W": 64, "W_min": 10, "force_learn_all": True},                      # both register halves of the ring
+                {"frame_len": 256},                                                   # S = 2, the 8-lane FFT
+                {"smooth_N_E": True, "noise_replenish_from_all_subframes": True, "noise_buffer_ttl_frames": 40,
+                 "det.k_subframes": 3, "W": 20, "W_min": 5},                          # replenish + smoothing
+                {"frame_len": 1024, "W": 40}]                                         # S = 8 (generic FFT kernel on both sides)
+    for extra in variants:
+        params = {"sample_rate": 11162, **extra}
+        proc = BandNoiseEstimatorProcessor()
+        monkeypatch.setenv("APT_BNE_FFT_GENERIC", "1")
+        monkeypatch.setenv("APT_BNE_STATE_SERIAL", "1")
+        old = proc.run_batch(clips, params)
+        monkeypatch.delenv("APT_BNE_STATE_SERIAL")
+        warp = proc.run_batch(clips, params)          # warp state machine on the generic FFT: bit-equal
+        monkeypatch.delenv("APT_BNE_FFT_GENERIC")
+        new = proc.run_batch(clips, params)           # both new kernels
+        for (r0, s0), (r1, s1), (r2, s2) in zip(old, warp, new):
+            assert r0.keys() == r1.keys() == r2.keys()
+            for k, v in r0.items():
+                if isinstance(v, float) and np.isnan(v):
+                    assert np.isnan(r1[k]) and np.isnan(r2[k]), k
+                else:
+                    assert r1[k] == v, k
+                    assert r2[k] == (pytest.approx(v, rel=1e-9) if isinstance(v, float) else v), k
+            for k, v in s0.items():
+                if isinstance(v, np.ndarray):
+                    assert np.array_equal(s1[k], v, equal_nan=v.dtype.kind == "f"), k
+                    if v.dtype.kind == "f":
+                        np.testing.assert_allclose(s2[k], v, rtol=1e-9, atol=0, equal_nan=True, err_msg=k)
+                    else:
+                        assert np.array_equal(s2[k], v), k
+
+
 def test_legacy_roe_matches_reference(torch_cuda):
     """the legacy RoE detector on the GPU against ten runs of the unmodified reference, in the
     reference's call order (its `max_harmonics` module state carries over): drop / peak counts and the per-frame rain
