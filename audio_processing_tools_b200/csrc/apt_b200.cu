@@ -1701,7 +1701,15 @@ extern "C" int apt_bne_run(apt_ctx* ctx, const apt_bne_params_t* p, int n_clips,
     CUDA_OK(ctx, d_subEh.alloc(nf_tot * BNE_MAX_S)); CUDA_OK(ctx, d_fftq.alloc(nf_tot * 4));
     const int64_t nseg = sg[n_clips];
     if (nseg > 0) {
-        if (is_f32) bne_filter_kernel<float><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, seg_frames, (const float*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
+        const char* e_ser = getenv("APT_BNE_FILTER_SERIAL");
+        const int G = p->ns_h + p->ns_b;
+        if (p->ns_h >= 1 && G <= 32 && !(e_ser && atoi(e_ser) != 0)) {
+            // wavefront over the cascade: one lane per second-order section (APT_BNE_FILTER_SERIAL=1 keeps one thread per segment)
+            const int64_t warps = (nseg + (32 / G) - 1) / (32 / G);
+            const unsigned blocks = (unsigned)((warps + 3) / 4);
+            if (is_f32) bne_filter_wave_kernel<float><<<blocks, 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, seg_frames, (const float*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
+            else bne_filter_wave_kernel<int16_t><<<blocks, 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, seg_frames, (const int16_t*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
+        } else if (is_f32) bne_filter_kernel<float><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, seg_frames, (const float*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
         else bne_filter_kernel<int16_t><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, seg_frames, (const int16_t*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
         const char* e_gen = getenv("APT_BNE_FFT_GENERIC");
         if (N == 256 && !(e_gen && atoi(e_gen) != 0)) {

@@ -95,6 +95,101 @@ __global__ void __launch_bounds__(128) bne_filter_kernel(const __grid_constant__
     }
 }
 
+// The same streaming filters as a WAVEFRONT over the cascade: the ns_h + ns_b second-order sections of one segment sit
+// on consecutive lanes, lane s runs section s one sample behind lane s - 1 and takes its input from it by a shuffle, so
+// a sample costs one section's latency (a multiply, an add, a shuffle) instead of the whole cascade's, and a warp holds
+// 32 / (ns_h + ns_b) segments.  Every section performs the operations of bne_sos on the same values in the same order:
+// the outputs are bit-equal to bne_filter_kernel's.  The last HPF lane stores the HPF signal and accumulates its
+// subframe energies, the last BPF lane those of the band signal; the eight strided partial sums of numpy's pairwise
+// order live in registers named by the step (k & 7), a per-lane rotation of numpy's (sample & 7), undone once per subframe.
+template <typename PCM>
+__global__ void __launch_bounds__(128) bne_filter_wave_kernel(const __grid_constant__ BneDev p, int n_clips,
+                                                              const int64_t* __restrict__ samp_off, const int64_t* __restrict__ fr_off,
+                                                              const int64_t* __restrict__ seg_off, int seg_frames, const PCM* __restrict__ pcm,
+                                                              double* __restrict__ xhp, double* __restrict__ subEh, double* __restrict__ subEb) {
+    const unsigned FULL = 0xffffffffu;
+    const int G = p.ns_h + p.ns_b;                  // lanes per segment (host: ns_h >= 1, G <= 32)
+    const int gpw = 32 / G;                         // segments per warp
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int grp = lane / G, s = lane - grp * G;
+    const int64_t nseg = seg_off[n_clips];
+    const int64_t gi = warp * gpw + grp;
+    const bool live = grp < gpw && gi < nseg;
+    int64_t base = 0, f0 = 0, s0 = 0;
+    int n_total = 0, n_warm = 0, fa = 0;
+    double x0 = 0.0;
+    if (live) {
+        int lo = 0, hi = n_clips;                   // clip of this segment
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= gi) lo = mid; else hi = mid; }
+        const int seg = (int)(gi - seg_off[lo]);
+        base = samp_off[lo];
+        f0 = fr_off[lo];
+        const int nfr = (int)(fr_off[lo + 1] - f0);
+        fa = seg * seg_frames;
+        const int fb = min(nfr, fa + seg_frames);
+        const int64_t s_begin = (int64_t)fa * p.N, s_end = (int64_t)fb * p.N;
+        s0 = s_begin - p.warm;
+        const bool exact = s0 <= 0;
+        if (exact) s0 = 0;
+        x0 = exact ? (double)load_sample(pcm, base) : 0.0;            // _need_zi_seed: zi * x[0] (:782-788)
+        n_total = (int)(s_end - s0);
+        n_warm = (int)(s_begin - s0);
+    }
+    const bool is_h = s < p.ns_h;
+    const int si = is_h ? s : s - p.ns_h;
+    const double c0 = is_h ? p.sos_h[si][0] : p.sos_b[si][0], c1 = is_h ? p.sos_h[si][1] : p.sos_b[si][1];
+    const double c2 = is_h ? p.sos_h[si][2] : p.sos_b[si][2], c4 = is_h ? p.sos_h[si][4] : p.sos_b[si][4];
+    const double c5 = is_h ? p.sos_h[si][5] : p.sos_b[si][5];
+    double z0 = (is_h ? p.zi_h[si][0] : p.zi_b[si][0]) * x0, z1 = (is_h ? p.zi_h[si][1] : p.zi_b[si][1]) * x0;
+    const bool out_h = live && s == p.ns_h - 1, out_b = live && s == G - 1;
+    const bool outl = out_h || out_b;
+    double* subE = out_h ? subEh : subEb;
+    const int spf = p.N / p.sub_len;
+    int steps = n_total + G - 1;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, d));
+    double R[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) R[u] = 0.0;
+    int within = 0, sub = 0;                        // position inside the subframe, subframe index inside the segment
+    double yprev = 0.0;
+    const PCM* src = pcm + base + s0;
+    double* dst = xhp + base + s0;
+    for (int k0 = 0; k0 < steps; k0 += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int m = k0 + u - s;               // this lane's sample of the run
+            const bool act = m >= 0 && m < n_total;
+            double xin = __shfl_up_sync(FULL, yprev, 1);
+            if (s == 0) xin = act ? (double)load_sample(src, m) : 0.0;
+            const double y = c0 * xin + z0;                           // scipy _sosfilt: plain mul/add, no FMA
+            if (act) {
+                z0 = c1 * xin - c4 * y + z1;
+                z1 = c2 * xin - c5 * y;
+            }
+            yprev = y;
+            if (act && outl && m >= n_warm) {
+                if (out_h) dst[m] = y;
+                const double sq = y * y;
+                R[u] = within < 8 ? sq : R[u] + sq;
+                if (++within == p.sub_len) {
+                    // numpy's partial sum j (samples = j mod 8 of the subframe) is R[(j + s) & 7]
+                    double t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) t[j] = R[j];
+                    const int d = s & 7;
+                    const double r0 = t[d & 7], r1 = t[(1 + d) & 7], r2 = t[(2 + d) & 7], r3 = t[(3 + d) & 7];
+                    const double r4 = t[(4 + d) & 7], r5 = t[(5 + d) & 7], r6 = t[(6 + d) & 7], r7 = t[(7 + d) & 7];
+                    const int64_t fr = f0 + fa + sub / spf;
+                    subE[fr * BNE_MAX_S + (sub % spf)] = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+                    within = 0; sub++;
+                }
+            }
+        }
+    }
+}
+
 constexpr int BNE_NT = 128;
 __global__ void __launch_bounds__(BNE_NT) bne_fft_kernel(const __grid_constant__ BneDev p, const int64_t* __restrict__ samp_off,
                                                          const int64_t* __restrict__ fr_off, const double* __restrict__ xhp,

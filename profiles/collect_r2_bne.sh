@@ -6,9 +6,10 @@ O=gpurun_out/r2bne; mkdir -p $O
 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.txt 2>&1; tail -3 $O/pytest_gpu.txt
 B="python bench.py --workload bne --steps 3 --warmup 3"
 $B 2> $O/bne_default.err | tail -1 > $O/bench_bne.json
-APT_BNE_STATE_SERIAL=1 APT_BNE_FFT_GENERIC=1 $B --no-cpu 2> /dev/null | tail -1 > $O/bench_bne_old_kernels.json
+APT_BNE_STATE_SERIAL=1 APT_BNE_FFT_GENERIC=1 APT_BNE_FILTER_SERIAL=1 $B --no-cpu 2> /dev/null | tail -1 > $O/bench_bne_old_kernels.json
 APT_BNE_FFT_GENERIC=1 $B --no-cpu 2> /dev/null | tail -1 > $O/bench_bne_generic_fft.json
-for s in 4 8 32; do APT_BNE_SEG=$s $B --no-cpu 2> /dev/null | tail -1 > $O/bench_bne_seg$s.json; done
+APT_BNE_FILTER_SERIAL=1 $B --no-cpu 2> /dev/null | tail -1 > $O/bench_bne_serial_filter.json
+for s in 4 8 32 64; do APT_BNE_SEG=$s $B --no-cpu 2> /dev/null | tail -1 > $O/bench_bne_seg$s.json; done
 for f in $O/bench_bne*.json; do python - "$f" <<'PY'
 import json, sys
 try:

@@ -475,10 +475,11 @@ def test_band_noise_batch_and_int16(torch_cuda):
 
 
 def test_band_noise_warp_kernel_equals_serial(torch_cuda, monkeypatch):
-    """The warp-per-clip state machine (ring buffer and its sorted copy spread over the lanes) and the 8-lanes-per-frame
-    FFT of the band noise estimator against the kernels they replace (APT_BNE_STATE_SERIAL / APT_BNE_FFT_GENERIC keep
-    those): with the same FFT the state machine's outputs are bit-equal -- every array, the counters and the adaptive
-    quantile; the two FFT algorithms agree to 1e-12 relative on the band sums and give the same flags."""
+    """The band noise estimator's wavefront filters (one lane per second-order section), warp-per-clip state machine (ring
+    buffer and its sorted copy spread over the lanes) and 16- / 8-lanes-per-frame FFT against the kernels they replace
+    (APT_BNE_FILTER_SERIAL / APT_BNE_STATE_SERIAL / APT_BNE_FFT_GENERIC keep those): with the same FFT every output is
+    bit-equal -- all arrays, the counters and the adaptive quantile; the two FFT algorithms agree to 1e-9 relative on
+    the float64 series and give the same masks and flags."""
     from audio_processing_tools_b200.edge.band_noise_processor import BandNoiseEstimatorProcessor
     clips = [synth_clip_i16(41.0, 181, 3.0), synth_clip_i16(0.03, 182, 3.0), synth_clip_i16(63.7, 183, 30.0),
              synth_clip_i16(25.2, 184, 0.0), synth_clip_i16(12.0, 185, 10.0)]
@@ -494,9 +495,11 @@ def test_band_noise_warp_kernel_equals_serial(torch_cuda, monkeypatch):
         proc = BandNoiseEstimatorProcessor()
         monkeypatch.setenv("APT_BNE_FFT_GENERIC", "1")
         monkeypatch.setenv("APT_BNE_STATE_SERIAL", "1")
+        monkeypatch.setenv("APT_BNE_FILTER_SERIAL", "1")
         old = proc.run_batch(clips, params)
         monkeypatch.delenv("APT_BNE_STATE_SERIAL")
-        warp = proc.run_batch(clips, params)          # warp state machine on the generic FFT: bit-equal
+        monkeypatch.delenv("APT_BNE_FILTER_SERIAL")
+        warp = proc.run_batch(clips, params)          # wavefront filters + warp state machine on the generic FFT: bit-equal
         monkeypatch.delenv("APT_BNE_FFT_GENERIC")
         new = proc.run_batch(clips, params)           # both new kernels
         for (r0, s0), (r1, s1), (r2, s2) in zip(old, warp, new):
