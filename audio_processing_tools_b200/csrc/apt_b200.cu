@@ -1785,7 +1785,15 @@ extern "C" int apt_roe_run(apt_ctx* ctx, const apt_roe_params_t* p, int n_clips,
         CUDA_OK(ctx, d_mag.alloc((size_t)(fo[n_parts] - n_parts) * 129)); CUDA_OK(ctx, d_harm.alloc((size_t)fo[n_parts] * 5));
         CUDA_OK(ctx, d_mh.alloc((size_t)n_parts + 1));
         const RoeParts pt{n_parts, d_clip.p, d_start.p, d_len.p, d_fo.p, d_yo.p};
-        if (is_f32) roe_filter_kernel<float><<<n_parts, 32, 0, st>>>(*p, pt, (const float*)dev_pcm, d_y.p, d_t.p);
+        const char* e_ser = getenv("APT_ROE_FILTER_SERIAL");
+        const int nl = p->ns_in + (p->want_td ? p->ns_td : 0);
+        if (nl >= 1 && nl <= 32 && !(e_ser && atoi(e_ser) != 0)) {
+            // 32 / nl parts per warp, one shuffle per step (APT_ROE_FILTER_SERIAL=1 keeps one warp per part)
+            const int warps = (n_parts + (32 / nl) - 1) / (32 / nl);
+            const unsigned blocks = (unsigned)((warps + 3) / 4);
+            if (is_f32) roe_filter_wave_kernel<float><<<blocks, 128, 0, st>>>(*p, pt, (const float*)dev_pcm, d_y.p, d_t.p);
+            else roe_filter_wave_kernel<int16_t><<<blocks, 128, 0, st>>>(*p, pt, (const int16_t*)dev_pcm, d_y.p, d_t.p);
+        } else if (is_f32) roe_filter_kernel<float><<<n_parts, 32, 0, st>>>(*p, pt, (const float*)dev_pcm, d_y.p, d_t.p);
         else roe_filter_kernel<int16_t><<<n_parts, 32, 0, st>>>(*p, pt, (const int16_t*)dev_pcm, d_y.p, d_t.p);
         const size_t smem = sizeof(cx<double>) * (32 * kExSize + 128 + 130) + sizeof(double) * 256;
         CUDA_OK(ctx, cudaFuncSetAttribute(roe_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

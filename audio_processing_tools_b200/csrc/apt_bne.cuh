@@ -157,12 +157,15 @@ __global__ void __launch_bounds__(128) bne_filter_wave_kernel(const __grid_const
     const PCM* src = pcm + base + s0;
     double* dst = xhp + base + s0;
     for (int k0 = 0; k0 < steps; k0 += 8) {
+        double xs[8];                               // section 0: the block's eight samples, loaded ahead of the recursion
+#pragma unroll
+        for (int u = 0; u < 8; u++) xs[u] = (s == 0 && k0 + u < n_total) ? (double)load_sample(src, k0 + u) : 0.0;
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             const int m = k0 + u - s;               // this lane's sample of the run
             const bool act = m >= 0 && m < n_total;
             double xin = __shfl_up_sync(FULL, yprev, 1);
-            if (s == 0) xin = act ? (double)load_sample(src, m) : 0.0;
+            if (s == 0) xin = xs[u];
             const double y = c0 * xin + z0;                           // scipy _sosfilt: plain mul/add, no FMA
             if (act) {
                 z0 = c1 * xin - c4 * y + z1;

@@ -100,6 +100,57 @@ __global__ void __launch_bounds__(32) roe_filter_kernel(const __grid_constant__ 
     }
 }
 
+// The same cascade with 32 / (ns_in + ns_td) parts per warp: a group of consecutive lanes per part, section 0 loads its
+// samples itself (eight ahead of the recursion), every other section takes the previous lane's output of the previous
+// step by one shuffle, and the two emitting sections store their outputs directly -- one double shuffle per step
+// instead of four plus the collect.  Same operations on the same values as roe_filter_kernel (bit-equal outputs).
+template <typename PCM>
+__global__ void __launch_bounds__(128) roe_filter_wave_kernel(const __grid_constant__ RoeDev p, RoeParts pt, const PCM* __restrict__ pcm,
+                                                              double* __restrict__ ybuf, double* __restrict__ tbuf) {
+    const unsigned FULL = 0xffffffffu;
+    const int ns1 = p.ns_in, ns2 = p.want_td ? p.ns_td : 0, nl = ns1 + ns2;
+    const int gpw = 32 / nl;
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int grp = lane / nl, s = lane - grp * nl;
+    const int part = warp * gpw + grp;
+    const bool live = grp < gpw && part < pt.n_parts;
+    const int pi = live ? part : 0;
+    const int len = live ? pt.len[pi] : 0;
+    const PCM* src = pcm + pt.start[pi];
+    double* y = ybuf + pt.yo[pi];
+    double* f2 = tbuf + pt.yo[pi] + (int64_t)256 * pi;          // len + 256 values: zeros(128), y, zeros(128) filtered
+    double b0 = 0, b1 = 0, b2 = 0, a1 = 0, a2 = 0;
+    if (s < ns1) { b0 = p.sos_in[s][0]; b1 = p.sos_in[s][1]; b2 = p.sos_in[s][2]; a1 = p.sos_in[s][4]; a2 = p.sos_in[s][5]; }
+    else { const int q = s - ns1; b0 = p.sos_td[q][0]; b1 = p.sos_td[q][1]; b2 = p.sos_td[q][2]; a1 = p.sos_td[q][4]; a2 = p.sos_td[q][5]; }
+    if (live && ns2 > 0) for (int i = s; i < 128; i += nl) f2[i] = 0.0;   // a filter at rest stays at rest on the leading zeros
+    int steps = live ? len + 128 + nl : 0;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, d));
+    const bool emit_y = live && s == ns1 - 1, emit_f = live && ns2 > 0 && s == nl - 1;
+    double z0 = 0.0, z1 = 0.0, out = 0.0;
+    for (int k0 = 0; k0 < steps; k0 += 8) {
+        double xs[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) xs[u] = (s == 0 && k0 + u < len) ? roe_load(src, k0 + u) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int m = k0 + u - s;                           // this section's sample at this step
+            const double prev = __shfl_up_sync(FULL, out, 1);   // output of the previous section at the previous step
+            double x = (s == 0) ? xs[u] : prev;
+            // the time-domain band-pass sees zeros behind the end of the part, not the ringing of the input filter
+            if (s == ns1 && m >= len) x = 0.0;
+            // scipy _sosfilt: x_cur = b0 x + z0; z0 = b1 x - a1 x_cur + z1; z1 = b2 x - a2 x_cur
+            const double yv = b0 * x + z0;
+            z0 = (b1 * x - a1 * yv) + z1;
+            z1 = b2 * x - a2 * yv;
+            out = yv;
+            if (emit_y && m >= 0 && m < len) y[m] = yv;
+            if (emit_f && m >= 0 && m < len + 128) f2[128 + m] = yv;
+        }
+    }
+}
+
 // pairwise (numpy order) sum of f(n), n = 0..255, spread over the 8 lanes of a frame: lane j adds elements 8i + j of
 // each 128-block in ascending i, the lanes combine as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), block 0 + block 1
 template <typename F>

@@ -14,6 +14,7 @@ import numpy as np
 import scipy.signal as spsig
 
 from .. import _lib
+from .._staging import upload_clips
 from ..engine import AptError, _torch
 from .band_noise_estimator import BandNoiseEstimatorConfig, NoiseFrameDetectorConfig, db_to_ratio, hz_to_bin
 
@@ -170,7 +171,7 @@ class BandNoiseEstimatorProcessor:
         nfr = lens // N
         nF = int(nfr.sum())
         dev = torch.device("cuda", self._device)
-        d_pcm = torch.from_numpy(np.concatenate(clips)).to(dev)
+        d_pcm = upload_clips(torch, dev, clips, lens)
         d_fo = torch.zeros((max(nF, 1), _lib.BNE_FRAME_F), dtype=torch.float64, device=dev)
         d_mask = torch.zeros(max(nF, 1), dtype=torch.uint8, device=dev)
         d_sub = torch.zeros((max(nF, 1), _lib.BNE_MAX_S), dtype=torch.float64, device=dev)
@@ -181,52 +182,72 @@ class BandNoiseEstimatorProcessor:
                                torch.cuda.current_stream(self._device).cuda_stream)
         if rc != 0:
             raise AptError(f"apt_bne_run failed ({rc}): {L.apt_last_error(ctx).decode()}")
-        fo, mask, sub, st = d_fo.cpu().numpy(), d_mask.cpu().numpy(), d_sub.cpu().numpy(), d_st.cpu().numpy()
+        # per-frame columns leave the device column-major, so that a clip's column is one contiguous run of the batch array
+        fo_t = d_fo.t().contiguous().cpu().numpy()
+        mask, st = d_mask.cpu().numpy(), d_st.cpu().numpy()
+        sub = d_sub[:, :S].contiguous().cpu().numpy()
+        return self._package_batch(cfg, clips, params, fo_t, mask, sub, st, nfr, S, N, fs)
+
+    @staticmethod
+    def _median(a: np.ndarray) -> float:
+        """np.median of a 1-D float array without its per-call overhead (same two-element mean for even sizes)."""
+        n = a.size
+        h = n >> 1
+        if n & 1:
+            return float(np.partition(a, h)[h])
+        part = np.partition(a, (h - 1, h))
+        r = float((part[h - 1] + part[h]) / 2.0)
+        return r if r == r or not np.isnan(a).any() else float("nan")
+
+    def _package_batch(self, cfg, clips, params, fo_t, mask, sub, st, nfr, S, N, fs):
+        """Result / state dictionaries of every clip (edge/band_noise_processor.py:200-281), built from batch-wide arrays."""
+        dtype = cfg.dtype
+        nF = int(nfr.sum())
+        submask_all = ((mask[:nF, None] >> np.arange(S, dtype=np.uint8)[None, :]) & 1).astype(bool)
+        fft_rain_all = fo_t[11, :nF] > 0.5
+        nsub_all = np.repeat(fo_t[10, :nF, None], S, axis=1).astype(dtype, copy=False)
+        sub_all = sub[:nF].astype(dtype, copy=False)
+        want_audio = bool(params.get("include_audio_in_state", False))
         outs, f0 = [], 0
+        nan = np.nan
         for c, x in enumerate(clips):
             n = int(nfr[c])
-            outs.append(self._package(cfg, x, params, fo[f0:f0 + n], mask[f0:f0 + n], sub[f0:f0 + n, :S], st[c], S, N, fs))
-            f0 += n
+            f1 = f0 + n
+            if n == 0:
+                energy = {k: (0.0 if "sum" in k or k == "noise_effective_q" else 0) for k in _STAT_KEYS
+                          if k not in ("noise_buffer_min_valid_count", "noise_buffer_underflow_frame_count", "frames_since_noise_update")}
+                energy["noise_effective_q"] = float(cfg.q)
+                energy.update(noise_energy_mean=0.0, rain_energy_mean=0.0, total_energy_mean=0.0)
+            else:
+                row = st[c]
+                energy = {k: (float(row[i]) if ("sum" in k or k == "noise_effective_q") else int(row[i])) for i, k in enumerate(_STAT_KEYS)}
+                energy["noise_energy_mean"] = energy["noise_energy_sum"] / max(1, energy["noise_frame_count"])
+                energy["rain_energy_mean"] = energy["rain_energy_sum"] / max(1, energy["rain_frame_count"])
+                energy["total_energy_mean"] = energy["total_energy_sum"] / max(1, energy["total_frame_count"])
+            blk = fo_t[:len(_FRAME_KEYS), f0:f1].astype(dtype, copy=True)     # one block per clip, a row per series
+            cols = {k: blk[i] for i, k in enumerate(_FRAME_KEYS)}
+            fft_rain = fft_rain_all[f0:f1].copy()
+            results = {
+                "processor": self.name, "mode": self.mode, "n_frames": n,
+                "M_clean_med": self._median(cols["M_clean"]) if n else nan,
+                "noise_E_med": self._median(cols["N_E"]) if n else nan,
+                "gain_med": self._median(cols["G_mag"]) if n else nan,
+                "noise_effective_q_last": float(cols["noise_effective_q"][-1]) if n else nan,
+                "noise_effective_q_med": self._median(cols["noise_effective_q"]) if n else nan,
+                "fft_rain_frac": float(np.mean(fft_rain)) if n else nan,
+                **{f"energy_stats__{k}": v for k, v in energy.items()},
+            }
+            state: Dict[str, Any] = {
+                "processor": self.name, "mode": self.mode, "times_s": (np.arange(n, dtype=np.float64) * N) / fs,
+                **cols,
+                "subE": sub_all[f0:f1].copy(),
+                "N_sub": nsub_all[f0:f1].copy(),
+                "rain_submask": submask_all[f0:f1].copy(),
+                "fft_rain_frame": fft_rain,
+                "config": cfg, "energy_stats": energy,
+            }
+            if want_audio:
+                state["x_in"] = np.asarray(x, dtype=dtype).copy() if x.dtype != np.int16 else (x.astype(np.float32) / np.float32(32767.0)).astype(dtype)
+            outs.append((results, state))
+            f0 = f1
         return outs
-
-    def _package(self, cfg, x, params, fo, mask, sub, st, S, N, fs):
-        n = fo.shape[0]
-        dtype = cfg.dtype
-        times_s = (np.arange(n, dtype=np.float64) * N) / fs
-        if n == 0:
-            energy = {k: (0.0 if "sum" in k or k == "noise_effective_q" else 0) for k in _STAT_KEYS
-                      if k not in ("noise_buffer_min_valid_count", "noise_buffer_underflow_frame_count", "frames_since_noise_update")}
-            energy["noise_effective_q"] = float(cfg.q)
-            energy.update(noise_energy_mean=0.0, rain_energy_mean=0.0, total_energy_mean=0.0)
-        else:
-            energy = {}
-            for i, k in enumerate(_STAT_KEYS):
-                energy[k] = float(st[i]) if ("sum" in k or k == "noise_effective_q") else int(st[i])
-            energy["noise_energy_mean"] = energy["noise_energy_sum"] / max(1, energy["noise_frame_count"])
-            energy["rain_energy_mean"] = energy["rain_energy_sum"] / max(1, energy["rain_frame_count"])
-            energy["total_energy_mean"] = energy["total_energy_sum"] / max(1, energy["total_frame_count"])
-        cols = {k: np.ascontiguousarray(fo[:, i]).astype(dtype, copy=False) for i, k in enumerate(_FRAME_KEYS)}
-        fft_rain = fo[:, 11] > 0.5 if n else np.zeros(0, dtype=bool)
-        nan = np.nan
-        results = {
-            "processor": self.name, "mode": self.mode, "n_frames": int(n),
-            "M_clean_med": float(np.median(cols["M_clean"])) if n else nan,
-            "noise_E_med": float(np.median(cols["N_E"])) if n else nan,
-            "gain_med": float(np.median(cols["G_mag"])) if n else nan,
-            "noise_effective_q_last": float(cols["noise_effective_q"][-1]) if n else nan,
-            "noise_effective_q_med": float(np.median(cols["noise_effective_q"])) if n else nan,
-            "fft_rain_frac": float(np.mean(fft_rain)) if n else nan,
-            **{f"energy_stats__{k}": v for k, v in energy.items()},
-        }
-        state: Dict[str, Any] = {
-            "processor": self.name, "mode": self.mode, "times_s": times_s,
-            **cols,
-            "subE": np.ascontiguousarray(sub).astype(dtype, copy=False),
-            "N_sub": np.repeat(fo[:, 10:11], S, axis=1).astype(dtype, copy=False),
-            "rain_submask": ((mask[:, None] >> np.arange(S)[None, :]) & 1).astype(bool),
-            "fft_rain_frame": np.asarray(fft_rain, dtype=bool),
-            "config": cfg, "energy_stats": energy,
-        }
-        if bool(params.get("include_audio_in_state", False)):
-            state["x_in"] = np.asarray(x, dtype=dtype).copy() if x.dtype != np.int16 else (x.astype(np.float32) / np.float32(32767.0)).astype(dtype)
-        return results, state

@@ -26,6 +26,7 @@ import numpy as np
 import scipy.signal as spsig
 
 from .. import _lib
+from .._staging import upload_clips
 from ..engine import AptError, _torch
 
 default_params = {
@@ -163,17 +164,15 @@ def rain_detection_algo_batch(audio_list: Sequence[np.ndarray], **kwargs) -> Lis
         raise TypeError("a batch must be all int16 or all float")
     lens = [c.size for c in clips]
     pclip, pstart, plen, last_ok = _part_table(lens, cfg)
-    if P.want_td:
-        for c in range(len(clips)):
-            if not np.any(pclip == c):
-                raise KeyError("raining")      # time_domain_raining_status on an empty state (:787)
+    if P.want_td and (np.bincount(pclip, minlength=len(clips)) == 0).any():
+        raise KeyError("raining")              # time_domain_raining_status on an empty state (:787)
     torch = _torch()
     L, ctx = _context()
     dev = torch.device("cuda", _device)
     n_parts = int(pclip.size)
     T1 = plen // 128 + 2                                # frame slots per part
     fo = np.concatenate(([0], np.cumsum(T1))).astype(np.int64)
-    d_pcm = torch.from_numpy(np.concatenate(clips) if sum(lens) else np.zeros(1, clips[0].dtype)).to(dev)
+    d_pcm = upload_clips(torch, dev, clips, np.asarray(lens, dtype=np.int64))      # pinned staging, one asynchronous copy
     d_f = torch.zeros((max(int(fo[-1]), 1), _lib.ROE_FRAME_F), dtype=torch.float64, device=dev)
     d_p = torch.zeros((max(n_parts, 1), _lib.ROE_PART_F), dtype=torch.float64, device=dev)
     d_c = torch.zeros((len(clips), _lib.ROE_CLIP_F), dtype=torch.float64, device=dev)
@@ -186,20 +185,33 @@ def rain_detection_algo_batch(audio_list: Sequence[np.ndarray], **kwargs) -> Lis
     if rc != 0:
         raise AptError(f"apt_roe_run failed ({rc}): {L.apt_last_error(ctx).decode()}")
     max_harmonics = int(mh_out.value)
-    F, Pp, Cc = d_f.cpu().numpy(), d_p.cpu().numpy(), d_c.cpu().numpy()
+    # per-frame columns leave the device column-major: a clip's series is one contiguous run of the batch array
+    Ft, Pp, Cc = d_f.t().contiguous().cpu().numpy(), d_p.cpu().numpy(), d_c.cpu().numpy()
+    # parts of a clip are consecutive (pclip ascending): [p0[c], p1[c])
+    p0 = np.searchsorted(pclip, np.arange(len(clips)), side="left")
+    p1 = np.searchsorted(pclip, np.arange(len(clips)), side="right")
+    kurt_thr, crest_thr, de_thr = P.kurtosis_thr, P.crest_thr, P.diff_energy_thr
+    want_td = bool(P.want_td)
+    time_rows = {}           # frame times of a part by its slot count (shared by every part of that length)
     outs = []
     for c in range(len(clips)):
-        parts = np.flatnonzero(pclip == c)
-        sl = slice(int(fo[parts[0]]), int(fo[parts[-1] + 1])) if parts.size else slice(0, 0)
-        rows = F[sl]
-        state: Dict[str, Any] = {"raining": rows[:, 0].copy(), "Nov0": rows[:, 6].copy(), "novk": rows[:, 6].copy(), "novt": rows[:, 7].copy()}
-        if P.want_td:
-            times = [np.concatenate(([0.0], np.arange(int(T1[q]) - 1) * 128 / FS_ANALYSIS)) for q in parts]
-            state.update(kurtosis=rows[:, 1].copy(), crest_factor=rows[:, 2].copy(), diff_energy=rows[:, 3].copy(),
-                         energy_list=rows[:, 4].copy(), min_energy=rows[:, 5].copy(), times=np.concatenate(times))
-            state["rain_peaks"] = (state["kurtosis"] > P.kurtosis_thr) & (state["crest_factor"] > P.crest_thr) & (state["diff_energy"] > P.diff_energy_thr)
+        a, b = int(p0[c]), int(p1[c])
+        f0, f1 = (int(fo[a]), int(fo[b])) if b > a else (0, 0)
+        blk = Ft[:8, f0:f1].copy()                     # one block per clip, a row per series
+        state: Dict[str, Any] = {"raining": blk[0], "Nov0": blk[6], "novk": blk[6].copy(), "novt": blk[7]}
+        if want_td:
+            tl = []
+            for q in range(a, b):
+                t1 = int(T1[q])
+                row = time_rows.get(t1)
+                if row is None:
+                    row = time_rows[t1] = np.concatenate(([0.0], np.arange(t1 - 1) * 128 / FS_ANALYSIS))
+                tl.append(row)
+            state.update(kurtosis=blk[1], crest_factor=blk[2], diff_energy=blk[3], energy_list=blk[4], min_energy=blk[5],
+                         times=np.concatenate(tl))
+            state["rain_peaks"] = (blk[1] > kurt_thr) & (blk[2] > crest_thr) & (blk[3] > de_thr)
         state.update(rain_drop_count=int(Cc[c, 1]), rain_peaks_count=int(Cc[c, 2]), rain_drop_count_mod=int(Cc[c, 3]))
-        frain_mean = float(Pp[parts[-1], 0]) if (parts.size and last_ok[c]) else 0
+        frain_mean = float(Pp[b - 1, 0]) if (b > a and last_ok[c]) else 0
         outs.append((int(Cc[c, 0]), frain_mean, state))
     return outs
 

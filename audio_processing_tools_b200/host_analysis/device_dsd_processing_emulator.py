@@ -20,6 +20,7 @@ import numpy as np
 from scipy.signal import get_window
 
 from .. import _lib
+from .._staging import upload_clips
 from ..engine import AptError, _torch
 
 
@@ -84,7 +85,7 @@ class DsdProcessingEmualtor:
         lens = np.array([p.size for p in pcm], dtype=np.int64)
         max_minutes = max(1, int(max(math.ceil(n / (self.fs * 60)) for n in lens)))
         dev = torch.device("cuda", self._device)
-        d_pcm = torch.from_numpy(np.concatenate(pcm)).to(dev)
+        d_pcm = upload_clips(torch, dev, pcm, lens)            # pinned staging buffer, one asynchronous copy
         d_out = torch.zeros((len(pcm), max_minutes, 100), dtype=torch.float64, device=dev)
         d_n = torch.zeros(len(pcm), dtype=torch.int32, device=dev)
         prm = _lib.AptDsdParams()

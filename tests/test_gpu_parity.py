@@ -558,6 +558,29 @@ def test_legacy_roe_batch_and_rain_processor(torch_cuda):
     assert st["processor"] == "rain"
 
 
+def test_legacy_roe_filter_kernels_agree(torch_cuda, monkeypatch):
+    """The RoE filter cascade with several parts per warp (one shuffle per step) against the one-warp-per-part kernel
+    it replaces (APT_ROE_FILTER_SERIAL=1): same operations on the same values, every output bit-equal."""
+    from audio_processing_tools_b200.edge import dsp_rain_detection as roe
+    clips = [synth_clip_i16(10.0, 191, 10.0), synth_clip_i16(7.5, 192, 3.0), synth_clip_i16(3.1, 193, 30.0),
+             synth_clip_i16(10.0, 194, 0.0), synth_clip_i16(5.9, 195, 3.0)]
+    roe.max_harmonics = 6
+    monkeypatch.setenv("APT_ROE_FILTER_SERIAL", "1")
+    old = roe.rain_detection_algo_batch(clips, **roe.default_params)
+    mh = roe.max_harmonics
+    monkeypatch.delenv("APT_ROE_FILTER_SERIAL")
+    roe.max_harmonics = 6
+    new = roe.rain_detection_algo_batch(clips, **roe.default_params)
+    assert roe.max_harmonics == mh
+    for (d1, f1, s1), (d2, f2, s2) in zip(old, new):
+        assert d1 == d2 and f1 == f2 and s1.keys() == s2.keys()
+        for k, v in s1.items():
+            if isinstance(v, np.ndarray):
+                assert np.array_equal(v, s2[k], equal_nan=v.dtype.kind == "f"), k
+            else:
+                assert v == s2[k], k
+
+
 def test_rain_processor_run_batch_uses_the_gpu_batch(torch_cuda):
     """RainProcessor.run_batch over the legacy RoE fn: one GPU pass for the list, same results as run() per file."""
     from audio_processing_tools_b200.edge import dsp_rain_detection as roe
