@@ -1707,8 +1707,9 @@ extern "C" int apt_bne_run(apt_ctx* ctx, const apt_bne_params_t* p, int n_clips,
             // wavefront over the cascade: one lane per second-order section (APT_BNE_FILTER_SERIAL=1 keeps one thread per segment)
             const int64_t warps = (nseg + (32 / G) - 1) / (32 / G);
             const unsigned blocks = (unsigned)((warps + 3) / 4);
-            if (is_f32) bne_filter_wave_kernel<float><<<blocks, 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, seg_frames, (const float*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
-            else bne_filter_wave_kernel<int16_t><<<blocks, 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, seg_frames, (const int16_t*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
+            const int steps = (int)std::min<int64_t>((int64_t)seg_frames * N + p->warm, max_fr * N) + G - 1;   // longest run + lanes
+            if (is_f32) bne_filter_wave_kernel<float><<<blocks, 128, 0, st>>>(*p, n_clips, steps, d_so.p, d_fo.p, d_sg.p, seg_frames, (const float*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
+            else bne_filter_wave_kernel<int16_t><<<blocks, 128, 0, st>>>(*p, n_clips, steps, d_so.p, d_fo.p, d_sg.p, seg_frames, (const int16_t*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
         } else if (is_f32) bne_filter_kernel<float><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, seg_frames, (const float*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
         else bne_filter_kernel<int16_t><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(*p, n_clips, d_so.p, d_fo.p, d_sg.p, seg_frames, (const int16_t*)dev_pcm, d_xhp.p, d_subEh.p, dev_subE);
         const char* e_gen = getenv("APT_BNE_FFT_GENERIC");
@@ -1791,8 +1792,11 @@ extern "C" int apt_roe_run(apt_ctx* ctx, const apt_roe_params_t* p, int n_clips,
             // 32 / nl parts per warp, one shuffle per step (APT_ROE_FILTER_SERIAL=1 keeps one warp per part)
             const int warps = (n_parts + (32 / nl) - 1) / (32 / nl);
             const unsigned blocks = (unsigned)((warps + 3) / 4);
-            if (is_f32) roe_filter_wave_kernel<float><<<blocks, 128, 0, st>>>(*p, pt, (const float*)dev_pcm, d_y.p, d_t.p);
-            else roe_filter_wave_kernel<int16_t><<<blocks, 128, 0, st>>>(*p, pt, (const int16_t*)dev_pcm, d_y.p, d_t.p);
+            int max_len = 0;
+            for (int q = 0; q < n_parts; q++) max_len = std::max(max_len, (int)part_len[q]);
+            const int steps = max_len + 128 + nl;
+            if (is_f32) roe_filter_wave_kernel<float><<<blocks, 128, 0, st>>>(*p, pt, steps, (const float*)dev_pcm, d_y.p, d_t.p);
+            else roe_filter_wave_kernel<int16_t><<<blocks, 128, 0, st>>>(*p, pt, steps, (const int16_t*)dev_pcm, d_y.p, d_t.p);
         } else if (is_f32) roe_filter_kernel<float><<<n_parts, 32, 0, st>>>(*p, pt, (const float*)dev_pcm, d_y.p, d_t.p);
         else roe_filter_kernel<int16_t><<<n_parts, 32, 0, st>>>(*p, pt, (const int16_t*)dev_pcm, d_y.p, d_t.p);
         const size_t smem = sizeof(cx<double>) * (32 * kExSize + 128 + 130) + sizeof(double) * 256;

@@ -14,6 +14,7 @@
 //                      buffer with TTL, np.quantile + EMA noise estimate, adaptive q, optional smoothing,
 //                      telemetry counters, Wiener-like gain (process_frame :770-986)
 #pragma once
+#include <type_traits>
 #include "apt_kernels.cuh"
 
 namespace apt {
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(128) bne_filter_kernel(const __grid_constant__
 // subframe energies, the last BPF lane those of the band signal; the eight strided partial sums of numpy's pairwise
 // order live in registers named by the step (k & 7), a per-lane rotation of numpy's (sample & 7), undone once per subframe.
 template <typename PCM>
-__global__ void __launch_bounds__(128) bne_filter_wave_kernel(const __grid_constant__ BneDev p, int n_clips,
+__global__ void __launch_bounds__(128) bne_filter_wave_kernel(const __grid_constant__ BneDev p, int n_clips, int steps /* uniform: longest run + lanes */,
                                                               const int64_t* __restrict__ samp_off, const int64_t* __restrict__ fr_off,
                                                               const int64_t* __restrict__ seg_off, int seg_frames, const PCM* __restrict__ pcm,
                                                               double* __restrict__ xhp, double* __restrict__ subEh, double* __restrict__ subEb) {
@@ -143,12 +144,10 @@ __global__ void __launch_bounds__(128) bne_filter_wave_kernel(const __grid_const
     const double c5 = is_h ? p.sos_h[si][5] : p.sos_b[si][5];
     double z0 = (is_h ? p.zi_h[si][0] : p.zi_b[si][0]) * x0, z1 = (is_h ? p.zi_h[si][1] : p.zi_b[si][1]) * x0;
     const bool out_h = live && s == p.ns_h - 1, out_b = live && s == G - 1;
-    const bool outl = out_h || out_b;
     double* subE = out_h ? subEh : subEb;
     const int spf = p.N / p.sub_len;
-    int steps = n_total + G - 1;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, d));
+    // samples [n_warm, n_total) of the run are this lane's outputs (none for the sections in between)
+    const unsigned n_out = (out_h || out_b) ? (unsigned)(n_total - n_warm) : 0u;
     double R[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) R[u] = 0.0;
@@ -156,31 +155,33 @@ __global__ void __launch_bounds__(128) bne_filter_wave_kernel(const __grid_const
     double yprev = 0.0;
     const PCM* src = pcm + base + s0;
     double* dst = xhp + base + s0;
-    for (int k0 = 0; k0 < steps; k0 += 8) {
+    const bool first = s == 0;
+    // gated: the first 16 steps, while the later sections still wait for their first sample (their seeded state must
+    // not move); afterwards every step updates -- a section running past its last sample only produces unused values
+    auto block = [&](int k0, auto gated) {
         double xs[8];                               // section 0: the block's eight samples, loaded ahead of the recursion
 #pragma unroll
-        for (int u = 0; u < 8; u++) xs[u] = (s == 0 && k0 + u < n_total) ? (double)load_sample(src, k0 + u) : 0.0;
+        for (int u = 0; u < 8; u++) xs[u] = (first && k0 + u < n_total) ? (double)load_sample(src, k0 + u) : 0.0;
+        const int mb = k0 - s;                      // this lane's sample of the run at step k0
+        double* db = dst + mb;                      // dereferenced only inside the output range
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const int m = k0 + u - s;               // this lane's sample of the run
-            const bool act = m >= 0 && m < n_total;
-            double xin = __shfl_up_sync(FULL, yprev, 1);
-            if (s == 0) xin = xs[u];
+            const double prev = __shfl_up_sync(FULL, yprev, 1);
+            const double xin = first ? xs[u] : prev;
             const double y = c0 * xin + z0;                           // scipy _sosfilt: plain mul/add, no FMA
-            if (act) {
+            if (!decltype(gated)::value || mb + u >= 0) {
                 z0 = c1 * xin - c4 * y + z1;
                 z1 = c2 * xin - c5 * y;
             }
             yprev = y;
-            if (act && outl && m >= n_warm) {
-                if (out_h) dst[m] = y;
-                const double sq = y * y;
-                R[u] = within < 8 ? sq : R[u] + sq;
+            if ((unsigned)(mb + u - n_warm) < n_out) {
+                if (out_h) db[u] = y;
+                R[u] += y * y;                      // 0.0 + sq == sq: the first eight samples of a subframe start the sums
                 if (++within == p.sub_len) {
                     // numpy's partial sum j (samples = j mod 8 of the subframe) is R[(j + s) & 7]
                     double t[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) t[j] = R[j];
+                    for (int j = 0; j < 8; j++) { t[j] = R[j]; R[j] = 0.0; }
                     const int d = s & 7;
                     const double r0 = t[d & 7], r1 = t[(1 + d) & 7], r2 = t[(2 + d) & 7], r3 = t[(3 + d) & 7];
                     const double r4 = t[(4 + d) & 7], r5 = t[(5 + d) & 7], r6 = t[(6 + d) & 7], r7 = t[(7 + d) & 7];
@@ -190,7 +191,12 @@ __global__ void __launch_bounds__(128) bne_filter_wave_kernel(const __grid_const
                 }
             }
         }
-    }
+    };
+    block(0, std::true_type{});
+    block(8, std::true_type{});
+    block(16, std::true_type{});
+    block(24, std::true_type{});
+    for (int k0 = 32; k0 < steps; k0 += 8) block(k0, std::false_type{});
 }
 
 constexpr int BNE_NT = 128;

@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(32) roe_filter_kernel(const __grid_constant__ 
 // step by one shuffle, and the two emitting sections store their outputs directly -- one double shuffle per step
 // instead of four plus the collect.  Same operations on the same values as roe_filter_kernel (bit-equal outputs).
 template <typename PCM>
-__global__ void __launch_bounds__(128) roe_filter_wave_kernel(const __grid_constant__ RoeDev p, RoeParts pt, const PCM* __restrict__ pcm,
-                                                              double* __restrict__ ybuf, double* __restrict__ tbuf) {
+__global__ void __launch_bounds__(128) roe_filter_wave_kernel(const __grid_constant__ RoeDev p, RoeParts pt, int steps /* uniform: longest part + 128 + lanes */,
+                                                              const PCM* __restrict__ pcm, double* __restrict__ ybuf, double* __restrict__ tbuf) {
     const unsigned FULL = 0xffffffffu;
     const int ns1 = p.ns_in, ns2 = p.want_td ? p.ns_td : 0, nl = ns1 + ns2;
     const int gpw = 32 / nl;
@@ -124,29 +124,32 @@ __global__ void __launch_bounds__(128) roe_filter_wave_kernel(const __grid_const
     if (s < ns1) { b0 = p.sos_in[s][0]; b1 = p.sos_in[s][1]; b2 = p.sos_in[s][2]; a1 = p.sos_in[s][4]; a2 = p.sos_in[s][5]; }
     else { const int q = s - ns1; b0 = p.sos_td[q][0]; b1 = p.sos_td[q][1]; b2 = p.sos_td[q][2]; a1 = p.sos_td[q][4]; a2 = p.sos_td[q][5]; }
     if (live && ns2 > 0) for (int i = s; i < 128; i += nl) f2[i] = 0.0;   // a filter at rest stays at rest on the leading zeros
-    int steps = live ? len + 128 + nl : 0;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, d));
+    // what this lane stores: the input filter's last section y[m], m < len; the last section of all f2[128 + m], m < len + 128
     const bool emit_y = live && s == ns1 - 1, emit_f = live && ns2 > 0 && s == nl - 1;
+    double* outp = emit_y ? y : f2 + 128;
+    const unsigned lim = emit_y ? (unsigned)len : (emit_f ? (unsigned)(len + 128) : 0u);
+    // the time-domain band-pass (section ns1) sees zeros behind the end of the part, not the ringing of the input filter
+    const int zlim = (ns2 > 0 && s == ns1) ? len : 0x7fffffff;
+    const bool first = s == 0;
     double z0 = 0.0, z1 = 0.0, out = 0.0;
+    // every state starts at rest and a section's input is zero until its first sample arrives, so no step needs gating
     for (int k0 = 0; k0 < steps; k0 += 8) {
         double xs[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) xs[u] = (s == 0 && k0 + u < len) ? roe_load(src, k0 + u) : 0.0;
+        for (int u = 0; u < 8; u++) xs[u] = (first && k0 + u < len) ? roe_load(src, k0 + u) : 0.0;
+        const int mb = k0 - s;                                  // this section's sample at step k0
+        double* ob = outp + mb;                                 // dereferenced only where 0 <= mb + u < lim
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const int m = k0 + u - s;                           // this section's sample at this step
             const double prev = __shfl_up_sync(FULL, out, 1);   // output of the previous section at the previous step
-            double x = (s == 0) ? xs[u] : prev;
-            // the time-domain band-pass sees zeros behind the end of the part, not the ringing of the input filter
-            if (s == ns1 && m >= len) x = 0.0;
+            double x = first ? xs[u] : prev;
+            if (mb + u >= zlim) x = 0.0;
             // scipy _sosfilt: x_cur = b0 x + z0; z0 = b1 x - a1 x_cur + z1; z1 = b2 x - a2 x_cur
             const double yv = b0 * x + z0;
             z0 = (b1 * x - a1 * yv) + z1;
             z1 = b2 * x - a2 * yv;
             out = yv;
-            if (emit_y && m >= 0 && m < len) y[m] = yv;
-            if (emit_f && m >= 0 && m < len + 128) f2[128 + m] = yv;
+            if ((unsigned)(mb + u) < lim) ob[u] = yv;
         }
     }
 }
