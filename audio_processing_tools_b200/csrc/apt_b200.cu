@@ -1655,11 +1655,24 @@ extern "C" int apt_dsd_run_i16(apt_ctx* ctx, const apt_dsd_params_t* p, int n_cl
     if (p->apply_window) CUDA_OK(ctx, upload(d_win, std::vector<double>(p->window, p->window + L)));
     const size_t nf_tot = (size_t)std::max<int64_t>(1, fo[n_clips]);
     CUDA_OK(ctx, d_drop.alloc(nf_tot)); CUDA_OK(ctx, d_pkv.alloc(nf_tot)); CUDA_OK(ctx, d_pki.alloc(nf_tot));
-    const size_t smem = sizeof(cx<double>) * (size_t)L + sizeof(double) * (size_t)(L / 2);
-    CUDA_OK(ctx, cudaFuncSetAttribute(dsd_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dsd_frame_kernel<<<dim3((unsigned)max_fr, (unsigned)n_clips), DSD_NT, smem, st>>>(d, 0, d_so.p, d_fo.p, dev_pcm, d_win.p, d_tw.p,
-                                                                                       d_drop.p, d_pki.p, d_pkv.p);
-    dsd_minutes_kernel<<<(n_clips + 63) / 64, 64, 0, st>>>(d, n_clips, d_so.p, d_fo.p, d_ts.p, d_drop.p, d_pki.p, d_pkv.p, dev_out, dev_n_minutes);
+    const char* e_gen = getenv("APT_DSD_FFT_GENERIC");
+    if (L == 512 && !(e_gen && atoi(e_gen) != 0)) {
+        // the emulator's frame length: 16 lanes per frame, 16 frames per CTA (APT_DSD_FFT_GENERIC=1 keeps one CTA per frame)
+        const size_t smem = dsd_fft512_smem();
+        CUDA_OK(ctx, cudaFuncSetAttribute(dsd_fft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dsd_fft512_kernel<<<dim3((unsigned)((max_fr + DSD_F512_TF - 1) / DSD_F512_TF), (unsigned)n_clips), DSD_F512_NT, smem, st>>>(
+            d, d_so.p, d_fo.p, dev_pcm, d_win.p, d_tw.p, d_drop.p, d_pki.p, d_pkv.p);
+    } else {
+        const size_t smem = sizeof(cx<double>) * (size_t)L + sizeof(double) * (size_t)(L / 2);
+        CUDA_OK(ctx, cudaFuncSetAttribute(dsd_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dsd_frame_kernel<<<dim3((unsigned)max_fr, (unsigned)n_clips), DSD_NT, smem, st>>>(d, 0, d_so.p, d_fo.p, dev_pcm, d_win.p, d_tw.p,
+                                                                                           d_drop.p, d_pki.p, d_pkv.p);
+    }
+    // position-only quantities (timestamps, 2-second slots, drop-size bins) for every hop position, then the serial machine
+    PoolBuf<double> d_tsc(ctx, 8); PoolBuf<int> d_aux(ctx, 9);
+    CUDA_OK(ctx, d_tsc.alloc(nf_tot + (size_t)n_clips)); CUDA_OK(ctx, d_aux.alloc(nf_tot));
+    dsd_times_kernel<<<dim3((unsigned)((max_fr + 1 + 255) / 256), (unsigned)n_clips), 256, 0, st>>>(d, d_fo.p, d_ts.p, d_drop.p, d_tsc.p, d_aux.p);
+    dsd_minutes_kernel<<<(n_clips + 63) / 64, 64, 0, st>>>(d, n_clips, d_so.p, d_fo.p, d_ts.p, d_tsc.p, d_aux.p, d_pki.p, d_pkv.p, dev_out, dev_n_minutes);
     CUDA_OK(ctx, cudaGetLastError());
     CUDA_OK(ctx, cudaStreamSynchronize(st));
     return 0;

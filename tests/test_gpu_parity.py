@@ -354,6 +354,24 @@ def test_dsd_emulator_matches_reference(torch_cuda):
         DsdProcessingEmualtor().process_audio_data(pcm.astype(np.float64) / 32767.0, 0)
 
 
+def test_dsd_fft_kernels_agree(torch_cuda, monkeypatch):
+    """The 16-lanes-per-frame FFT of the drop-size emulator (frame 512) against the generic one-CTA-per-frame kernel
+    (APT_DSD_FFT_GENERIC=1) on clips with odd lengths and timestamps inside a minute: the same per-minute vectors."""
+    from audio_processing_tools_b200.host_analysis.device_dsd_processing_emulator import DsdProcessingEmualtor
+    clips = [synth_clip_i16(130.3, 201, 10.0), synth_clip_i16(59.0, 202, 30.0), synth_clip_i16(0.03, 203, 3.0),
+             synth_clip_i16(75.7, 204, 0.0), synth_clip_i16(190.0, 205, 3.0)]
+    ts = [0.0, 17.25, 3.0, 59.99, 1714564800.5]
+    for win in (False, True):
+        em = DsdProcessingEmualtor(fs=11162, frame_length=512, hop_length=512, bwindow=win)
+        monkeypatch.setenv("APT_DSD_FFT_GENERIC", "1")
+        old = em.process_audio_batch(clips, ts)
+        monkeypatch.delenv("APT_DSD_FFT_GENERIC")
+        new = em.process_audio_batch(clips, ts)
+        assert [len(o) for o in old] == [len(o) for o in new]
+        for o, n in zip(old, new):
+            assert np.array_equal(np.asarray(o), np.asarray(n))
+
+
 def test_transform_dsd_entry_points(torch_cuda):
     import datetime as dt
     from test_dsd_oracle import case_pcm, dsd_cases
