@@ -1672,7 +1672,14 @@ extern "C" int apt_dsd_run_i16(apt_ctx* ctx, const apt_dsd_params_t* p, int n_cl
     PoolBuf<double> d_tsc(ctx, 8); PoolBuf<int> d_aux(ctx, 9);
     CUDA_OK(ctx, d_tsc.alloc(nf_tot + (size_t)n_clips)); CUDA_OK(ctx, d_aux.alloc(nf_tot));
     dsd_times_kernel<<<dim3((unsigned)((max_fr + 1 + 255) / 256), (unsigned)n_clips), 256, 0, st>>>(d, d_fo.p, d_ts.p, d_drop.p, d_tsc.p, d_aux.p);
-    dsd_minutes_kernel<<<(n_clips + 63) / 64, 64, 0, st>>>(d, n_clips, d_so.p, d_fo.p, d_ts.p, d_tsc.p, d_aux.p, d_pki.p, d_pkv.p, dev_out, dev_n_minutes);
+    const char* e_ser = getenv("APT_DSD_STATE_SERIAL");
+    if (e_ser && atoi(e_ser) != 0) {
+        dsd_minutes_kernel<<<(n_clips + 63) / 64, 64, 0, st>>>(d, n_clips, d_so.p, d_fo.p, d_ts.p, d_tsc.p, d_aux.p, d_pki.p, d_pkv.p, dev_out, dev_n_minutes);
+    } else {
+        // one warp per clip, histograms in shared memory (APT_DSD_STATE_SERIAL=1 keeps one thread per clip)
+        const size_t smem_m = sizeof(double) * (size_t)(d.n_bins + DSD_OUT) + sizeof(int) * (size_t)d.n_bins;
+        dsd_minutes_warp_kernel<<<n_clips, 32, smem_m, st>>>(d, n_clips, d_so.p, d_fo.p, d_ts.p, d_tsc.p, d_aux.p, d_pki.p, d_pkv.p, dev_out, dev_n_minutes);
+    }
     CUDA_OK(ctx, cudaGetLastError());
     CUDA_OK(ctx, cudaStreamSynchronize(st));
     return 0;
@@ -1748,8 +1755,10 @@ extern "C" int apt_bne_run(apt_ctx* ctx, const apt_bne_params_t* p, int n_clips,
     const char* e_serial = getenv("APT_BNE_STATE_SERIAL");
     if (e_serial && atoi(e_serial) != 0)
         bne_state_kernel<<<(n_clips + 63) / 64, 64, 0, st>>>(*p, n_clips, d_fo.p, d_subEh.p, dev_subE, d_fftq.p, dev_frame_out, dev_mask, dev_stats);
+    else if (p->S == 4)
+        bne_state_warp_kernel<4><<<n_clips, 32, 0, st>>>(*p, n_clips, d_fo.p, d_subEh.p, dev_subE, d_fftq.p, dev_frame_out, dev_mask, dev_stats);
     else
-        bne_state_warp_kernel<<<n_clips, 32, 0, st>>>(*p, n_clips, d_fo.p, d_subEh.p, dev_subE, d_fftq.p, dev_frame_out, dev_mask, dev_stats);
+        bne_state_warp_kernel<0><<<n_clips, 32, 0, st>>>(*p, n_clips, d_fo.p, d_subEh.p, dev_subE, d_fftq.p, dev_frame_out, dev_mask, dev_stats);
     CUDA_OK(ctx, cudaGetLastError());
     CUDA_OK(ctx, cudaStreamSynchronize(st));
     return 0;

@@ -605,6 +605,7 @@ __global__ void bne_state_kernel(const __grid_constant__ BneDev p, int n_clips, 
 // its order are those of the serial kernel (same values selected, same operations), so the outputs are bit-equal to it
 // (tests/test_gpu_parity.py::test_band_noise_warp_kernel_equals_serial).
 // ---------------------------------------------------------------------------------------------
+template <int ST>    // ST = 4: the default four subframes per frame at compile time (loops and shuffles sized for it); 0: any S <= 8
 __global__ void __launch_bounds__(32) bne_state_warp_kernel(const __grid_constant__ BneDev p, int n_clips, const int64_t* __restrict__ fr_off,
                                                             const double* __restrict__ subEh, const double* __restrict__ subEb,
                                                             const double* __restrict__ fftq, double* __restrict__ fo,
@@ -615,7 +616,8 @@ __global__ void __launch_bounds__(32) bne_state_warp_kernel(const __grid_constan
     const int l = threadIdx.x;
     const int64_t f0 = fr_off[c];
     const int nfr = (int)(fr_off[c + 1] - f0);
-    const int S = p.S, W = p.W;
+    constexpr int SM = ST ? ST : BNE_MAX_S;
+    const int S = ST ? ST : p.S, W = p.W;
     const double EPS = 1e-12;
     // ring slots l (A) and l + 32 (B): value and frame index (-1 = empty); sorted copy elements l (A) and l + 32 (B)
     double bufA = 0.0, bufB = 0.0, svA = 0.0, svB = 0.0;
@@ -711,9 +713,9 @@ __global__ void __launch_bounds__(32) bne_state_warp_kernel(const __grid_constan
         // pass; the values are the same wherever it does)
         const double lv = l < 8 ? (cur > EPS ? cur : EPS) : cur;
         const double Ldb = l < 16 ? 10.0 * log10(lv + EPS) : 0.0;
-        double sE[BNE_MAX_S], sH[BNE_MAX_S], LB[BNE_MAX_S], LH[BNE_MAX_S];
+        double sE[SM], sH[SM], LB[SM], LH[SM];
 #pragma unroll
-        for (int s = 0; s < BNE_MAX_S; s++) {
+        for (int s = 0; s < SM; s++) {
             sE[s] = __shfl_sync(FULL, cur, s); sH[s] = __shfl_sync(FULL, cur, 8 + s);
             LB[s] = __shfl_sync(FULL, Ldb, s); LH[s] = __shfl_sync(FULL, Ldb, 8 + s);
         }
@@ -724,14 +726,14 @@ __global__ void __launch_bounds__(32) bne_state_warp_kernel(const __grid_constan
         else {
             Eb = 0.0; Ehpf = 0.0;
 #pragma unroll
-            for (int k = 0; k < BNE_MAX_S; k++) if (k < S) { Eb += sE[k]; Ehpf += sH[k]; }
+            for (int k = 0; k < SM; k++) if (k < S) { Eb += sE[k]; Ehpf += sH[k]; }
         }
         bool fft_rain = false;
         if (has_prev_fft) fft_rain = (fq0 > (prev_rain + EPS) * p.M_ratio) && (fq1 > (prev_prim + EPS) * p.N_ratio);
         prev_rain = fq0; prev_prim = fq1; has_prev_fft = true;
         unsigned mask = 0u;
 #pragma unroll
-        for (int s = 0; s < BNE_MAX_S; s++) {
+        for (int s = 0; s < SM; s++) {
             if (s < S) {
                 const double e = sE[s] > EPS ? sE[s] : EPS;
                 if (hold > 0) { mask |= 1u << s; hold--; }
@@ -761,7 +763,7 @@ __global__ void __launch_bounds__(32) bne_state_warp_kernel(const __grid_constan
         expire(frame_idx);
         int learned = 0;
 #pragma unroll
-        for (int s = 0; s < BNE_MAX_S; s++)
+        for (int s = 0; s < SM; s++)
             if (s < S && (p.learn_all || !((mask >> s) & 1u))) { push(sE[s] > p.eps ? sE[s] : p.eps, frame_idx); learned++; }
         int repl = 0;
         if (p.replenish && learned == 0 && (!p.replenish_only_not_full || count_valid < W)) {
@@ -775,11 +777,11 @@ __global__ void __launch_bounds__(32) bne_state_warp_kernel(const __grid_constan
             ip = max(0, min(ip, S - 1)); in_ = max(0, min(in_, S - 1));
             double a = 0.0, b = 0.0;
 #pragma unroll
-            for (int x = 0; x < BNE_MAX_S; x++) {
+            for (int x = 0; x < SM; x++) {
                 if (x < S) {
                     int rank = 0;
 #pragma unroll
-                    for (int y = 0; y < BNE_MAX_S; y++)
+                    for (int y = 0; y < SM; y++)
                         if (y < S && (sE[y] < sE[x] || (sE[y] == sE[x] && y < x))) rank++;
                     if (rank == ip) a = sE[x];
                     if (rank == in_) b = sE[x];
@@ -820,7 +822,7 @@ __global__ void __launch_bounds__(32) bne_state_warp_kernel(const __grid_constan
         {
             double r = -0.0, d = -0.0; bool anyr = false, anyd = false;
 #pragma unroll
-            for (int s = 0; s < BNE_MAX_S; s++) {
+            for (int s = 0; s < SM; s++) {
                 if (s < S) {
                     if ((mask >> s) & 1u) { r += sE[s]; anyr = true; } else { d += sE[s]; anyd = true; }
                 }

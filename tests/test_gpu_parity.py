@@ -355,8 +355,9 @@ def test_dsd_emulator_matches_reference(torch_cuda):
 
 
 def test_dsd_fft_kernels_agree(torch_cuda, monkeypatch):
-    """The 16-lanes-per-frame FFT of the drop-size emulator (frame 512) against the generic one-CTA-per-frame kernel
-    (APT_DSD_FFT_GENERIC=1) on clips with odd lengths and timestamps inside a minute: the same per-minute vectors."""
+    """The 16-lanes-per-frame FFT and the warp-per-clip state machine of the drop-size emulator against the generic
+    one-CTA-per-frame FFT and the thread-per-clip machine (APT_DSD_FFT_GENERIC=1, APT_DSD_STATE_SERIAL=1) on clips with
+    odd lengths and timestamps inside a minute: the same per-minute vectors."""
     from audio_processing_tools_b200.host_analysis.device_dsd_processing_emulator import DsdProcessingEmualtor
     clips = [synth_clip_i16(130.3, 201, 10.0), synth_clip_i16(59.0, 202, 30.0), synth_clip_i16(0.03, 203, 3.0),
              synth_clip_i16(75.7, 204, 0.0), synth_clip_i16(190.0, 205, 3.0)]
@@ -364,8 +365,10 @@ def test_dsd_fft_kernels_agree(torch_cuda, monkeypatch):
     for win in (False, True):
         em = DsdProcessingEmualtor(fs=11162, frame_length=512, hop_length=512, bwindow=win)
         monkeypatch.setenv("APT_DSD_FFT_GENERIC", "1")
+        monkeypatch.setenv("APT_DSD_STATE_SERIAL", "1")
         old = em.process_audio_batch(clips, ts)
         monkeypatch.delenv("APT_DSD_FFT_GENERIC")
+        monkeypatch.delenv("APT_DSD_STATE_SERIAL")
         new = em.process_audio_batch(clips, ts)
         assert [len(o) for o in old] == [len(o) for o in new]
         for o, n in zip(old, new):
