@@ -172,7 +172,7 @@ __device__ __forceinline__ double roe_sum256(F f, int lane, unsigned gmask) {
     return tot[0] + tot[1];
 }
 
-__global__ void __launch_bounds__(ROE_NT) roe_frame_kernel(const __grid_constant__ RoeDev p, RoeParts pt, const double* __restrict__ ybuf,
+__global__ void __launch_bounds__(ROE_NT, 2) roe_frame_kernel(const __grid_constant__ RoeDev p, RoeParts pt, const double* __restrict__ ybuf,
                                                            const double* __restrict__ tbuf, const cx<double>* __restrict__ twA,
                                                            const cx<double>* __restrict__ tw256, double* __restrict__ mag,
                                                            double* __restrict__ fout) {
