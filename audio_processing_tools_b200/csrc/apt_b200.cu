@@ -1021,14 +1021,19 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
 #define RR(...) do { if (e == cudaSuccess) { e = (__VA_ARGS__); if (e != cudaSuccess) what = #__VA_ARGS__; } } while (0)
     // two-phase schedule: every bulk launch (STFT, TD of all segments) is enqueued before the first chain launch, and the
     // chain waits for the last of them, so that the bulk kernels have the GPU to themselves
-    for (int phase = 0; phase < (two_phase && piped ? 2 : 1); phase++)
+    // two_phase == 2 ("three-phase"): the STFT of every segment, then the TD kernel of every segment on the same stream,
+    // and the chain starts behind the last STFT -- its first half (tracker pass 1, flux, baselines) needs nothing from the
+    // TD kernel, so those latency-bound kernels run beside it; decide waits for its segment's TD launch as always
+    const int n_phase = !(two_phase && piped) ? 1 : (two_phase == 2 ? 3 : 2);
+    for (int phase = 0; phase < n_phase; phase++)
     for (int sg = 0; sg < n_seg && e == cudaSuccess; sg++) {
-        const bool do_bulk = !(two_phase && piped) || phase == 0;
-        const bool do_chain = !(two_phase && piped) || phase == 1;
+        const bool do_stft = n_phase == 1 || phase == 0;
+        const bool do_td = n_phase == 1 || (n_phase == 2 ? phase == 0 : phase == 1);
+        const bool do_chain = n_phase == 1 || phase == n_phase - 1;
         Batch bs = b;
         bs.ta = sg * seg_frames;
         bs.tb = n_seg == 1 ? INT32_MAX : bs.ta + seg_frames;
-        if (do_bulk) {
+        if (do_stft) {
         // STFT
         pl->mark(APT_KERNEL_STFT, st);
         bs.tile0 = bs.ta / STFT_TF;
@@ -1044,6 +1049,8 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
             RR(launch_stft_mode<PCM>(pl, bs, g, pcm, so, S[apt_plan::SK_STFT]));
             RR(rec(apt_plan::SK_STFT, sg));
         }
+        }
+        if (do_td) {
         // TD features
         pl->mark(APT_KERNEL_TD, st);
         bs.tile0 = bs.ta / TD_FT;
@@ -1102,8 +1109,10 @@ static int run_range(apt_plan* pl, int stages, int clip0, int n_clips, const PCM
         }
         if (!do_chain) continue;
         if (two_phase && piped && sg == 0) {
-            RR(cudaStreamWaitEvent(S[apt_plan::SK_TRK1], pl->ev_seg[apt_plan::SK_TD][n_seg - 1], 0));
-            RR(cudaStreamWaitEvent(S[apt_plan::SK_FLUX], pl->ev_seg[apt_plan::SK_TD][n_seg - 1], 0));
+            if (n_phase == 2) {
+                RR(cudaStreamWaitEvent(S[apt_plan::SK_TRK1], pl->ev_seg[apt_plan::SK_TD][n_seg - 1], 0));
+                RR(cudaStreamWaitEvent(S[apt_plan::SK_FLUX], pl->ev_seg[apt_plan::SK_TD][n_seg - 1], 0));
+            }
             RR(cudaStreamWaitEvent(S[apt_plan::SK_FLUX], pl->ev_seg[apt_plan::SK_STFT][n_seg - 1], 0));
             RR(cudaStreamWaitEvent(S[apt_plan::SK_TRK1], pl->ev_seg[apt_plan::SK_STFT][n_seg - 1], 0));
         }

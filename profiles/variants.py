@@ -19,6 +19,9 @@ ref = None
 for name, env in (("pipelined 16 seg", {}),
                   ("td own stream", {"APT_TD_OWN_STREAM": "1"}),
                   ("two-phase", {"APT_TWO_PHASE": "1"}),
+                  ("three-phase", {"APT_TWO_PHASE": "2"}),
+                  ("three-phase 8 seg", {"APT_TWO_PHASE": "2", "APT_SEGMENTS": "8"}),
+                  ("three-phase 32 seg", {"APT_TWO_PHASE": "2", "APT_SEGMENTS": "32"}),
                   ("two-phase + td own stream", {"APT_TWO_PHASE": "1", "APT_TD_OWN_STREAM": "1"}),
                   ("two-phase 8 seg", {"APT_TWO_PHASE": "1", "APT_SEGMENTS": "8"}),
                   ("two-phase 32 seg", {"APT_TWO_PHASE": "1", "APT_SEGMENTS": "32"}),
