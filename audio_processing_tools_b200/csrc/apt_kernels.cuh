@@ -128,20 +128,23 @@ __device__ __forceinline__ int run_head(int64_t g) { return (int)((4 - (g % 4 + 
 template <bool RAW> __device__ __forceinline__ float cvt_pcm(int16_t s) { return RAW ? (float)s : pcm_to_f32(s); }
 template <bool RAW> __device__ __forceinline__ float load_in(const int16_t* p, int64_t i) { return cvt_pcm<RAW>(__ldg(p + i)); }
 template <bool RAW> __device__ __forceinline__ float load_in(const float* p, int64_t i) { return __ldg(p + i); }
-template <int MAXV, typename PCM, typename Put, typename Put4, bool RAW = false>
+// NT: the CTA size when the caller knows it at compile time (the vector loads of a thread then sit at immediate offsets
+// from one pointer instead of a 64-bit multiply-add each), 0: blockDim.x.
+template <int MAXV, typename PCM, typename Put, typename Put4, bool RAW = false, int NT = 0>
 __device__ __forceinline__ void load_run(const PCM* __restrict__ pcm, int64_t g, int n, Put put, Put4 put4) {
     constexpr int VEC = 4;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = NT ? NT : (int)blockDim.x;
     int head = run_head<PCM>(g);
     if (head > n) head = n;
     const int nvec = (n - head) / VEC;
     const int tail0 = head + nvec * VEC;
     if constexpr (sizeof(PCM) == 2) {
         int2 raw[MAXV];
+        const int2* vp = reinterpret_cast<const int2*>(pcm + g + head) + tid;
 #pragma unroll
         for (int r = 0; r < MAXV; r++) {
             const int v = tid + r * nt;
-            if (v < nvec) raw[r] = __ldg(reinterpret_cast<const int2*>(pcm + g + head + (int64_t)v * VEC));
+            if (v < nvec) raw[r] = __ldg(vp + r * nt);
         }
         if (tid < head) put(tid, load_in<RAW>(pcm, g + tid));
         if (tail0 + tid < n) put(tail0 + tid, load_in<RAW>(pcm, g + tail0 + tid));
@@ -156,10 +159,11 @@ __device__ __forceinline__ void load_run(const PCM* __restrict__ pcm, int64_t g,
         }
     } else {
         float4 raw[MAXV];
+        const float4* vp = reinterpret_cast<const float4*>(pcm + g + head) + tid;
 #pragma unroll
         for (int r = 0; r < MAXV; r++) {
             const int v = tid + r * nt;
-            if (v < nvec) raw[r] = __ldg(reinterpret_cast<const float4*>(pcm + g + head + (int64_t)v * VEC));
+            if (v < nvec) raw[r] = __ldg(vp + r * nt);
         }
         if (tid < head) put(tid, load_sample(pcm, g + tid));
         if (tail0 + tid < n) put(tail0 + tid, load_sample(pcm, g + tail0 + tid));
@@ -310,12 +314,12 @@ __global__ void __launch_bounds__(STFT_NT, 3) stft256_kernel(const __grid_consta
         if (s0 >= 0 && s0 + NS_ <= N) {
             sh = (4 - (run_head<PCM>(base + s0) & 3)) & 3;
             auto xpos = [&](int u) { return u + sh + padk * (u >> 7); };
-            load_run<(NS_MAX / 4 + STFT_NT - 1) / STFT_NT + 1>(
-                pcm, base + s0, NS_, [&](int i, float v) { s_x[xpos(i)] = v; },
-                [&](int i, float4 v) {
-                    if ((i & 127) > 124) { s_x[xpos(i)] = v.x; s_x[xpos(i + 1)] = v.y; s_x[xpos(i + 2)] = v.z; s_x[xpos(i + 3)] = v.w; }
-                    else *reinterpret_cast<float4*>(s_x + xpos(i)) = v;
-                });
+            auto put1 = [&](int i, float v) { s_x[xpos(i)] = v; };
+            auto put4 = [&](int i, float4 v) {
+                if ((i & 127) > 124) { s_x[xpos(i)] = v.x; s_x[xpos(i + 1)] = v.y; s_x[xpos(i + 2)] = v.z; s_x[xpos(i + 3)] = v.w; }
+                else *reinterpret_cast<float4*>(s_x + xpos(i)) = v;
+            };
+            load_run<(NS_MAX / 4 + STFT_NT - 1) / STFT_NT + 1, PCM, decltype(put1), decltype(put4), false, STFT_NT>(pcm, base + s0, NS_, put1, put4);
         } else {
             stage_clip_f32(pcm, base, N, s0, NS_, s_x, [&](int u) { return u + padk * (u >> 7); });
         }
@@ -1531,7 +1535,7 @@ __global__ void __launch_bounds__(TDF_NT, 3) td_gate_fast_kernel(Batch b, const 
         auto xpos = [&](int u) { const int v = u + sh; return v + ((v >> 5) << 2); };
         auto put1 = [&](int i, float v) { s_x[xpos(i)] = v; };
         auto put4 = [&](int i, float4 v) { *reinterpret_cast<float4*>(s_x + xpos(i)) = v; };
-        load_run<TDF_LB / 4 / TDF_NT + 1, PCM, decltype(put1), decltype(put4), RAW>(pcm, base + bs, TDF_LB, put1, put4);
+        load_run<TDF_LB / 4 / TDF_NT + 1, PCM, decltype(put1), decltype(put4), RAW, TDF_NT>(pcm, base + bs, TDF_LB, put1, put4);
     }
     __syncthreads();
     float y[TDF_CH];
