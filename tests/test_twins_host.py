@@ -89,3 +89,45 @@ def test_rain_processor_batch_hook_uses_the_companion():
     with pytest.raises(ValueError):
         RainProcessor(name="rain", fn=fn).run_batch([np.zeros(5, np.float32)], params)     # shorter than check_duration
     assert roe.rain_detection_algo.batch is roe.rain_detection_algo_batch
+
+
+def test_band_noise_packaging_from_batch_arrays():
+    """Host side of BandNoiseEstimatorProcessor.run_batch: the per-clip result / state dictionaries are cut out of the
+    batch-wide column-major arrays the device returns (no GPU needed: synthetic device outputs).  Medians follow
+    np.median (two-element mean for even counts), masks unpack bit s = subframe s, every array is the clip's own copy."""
+    from audio_processing_tools_b200 import _lib
+    rng = np.random.default_rng(5)
+    proc = BandNoiseEstimatorProcessor()
+    for n in (1, 2, 5, 6, 1307, 1308):
+        a = rng.random(n)
+        assert proc._median(a) == float(np.median(a)), n
+    params = {"sample_rate": 11162}
+    cfg = proc._build_config(params)
+    N, S = 512, 4
+    nfr = np.array([7, 0, 12, 1], dtype=np.int64)
+    nF = int(nfr.sum())
+    clips = [np.zeros(int(n) * N + 3, dtype=np.int16) for n in nfr]
+    fo_t = rng.random((_lib.BNE_FRAME_F, nF))
+    fo_t[11] = (rng.random(nF) > 0.5).astype(np.float64)
+    mask = rng.integers(0, 16, nF).astype(np.uint8)
+    sub = rng.random((nF, S))
+    st = np.arange(len(clips) * _lib.BNE_STATS, dtype=np.float64).reshape(len(clips), _lib.BNE_STATS)
+    outs = proc._package_batch(cfg, clips, params, fo_t, mask, sub, st, nfr, S, N, 11162)
+    assert len(outs) == len(clips)
+    f0 = 0
+    for c, (res, state) in enumerate(outs):
+        n = int(nfr[c])
+        assert res["n_frames"] == n and state["M_band"].shape == (n,) and state["rain_submask"].shape == (n, S)
+        if n == 0:
+            assert np.isnan(res["gain_med"]) and res["energy_stats__noise_effective_q"] == float(cfg.q)
+            continue
+        assert np.array_equal(state["M_band"], fo_t[0, f0:f0 + n]) and np.array_equal(state["G_mag"], fo_t[4, f0:f0 + n])
+        assert res["gain_med"] == float(np.median(fo_t[4, f0:f0 + n]))
+        assert res["fft_rain_frac"] == float(np.mean(fo_t[11, f0:f0 + n] > 0.5))
+        assert np.array_equal(state["rain_submask"], ((mask[f0:f0 + n, None] >> np.arange(S)[None, :]) & 1).astype(bool))
+        assert np.array_equal(state["N_sub"], np.repeat(fo_t[10, f0:f0 + n, None], S, axis=1))
+        assert np.array_equal(state["subE"], sub[f0:f0 + n]) and np.array_equal(state["times_s"], np.arange(n) * N / 11162)
+        assert res["energy_stats__noise_frame_count"] == int(st[c, 3]) and res["energy_stats__noise_energy_sum"] == float(st[c, 0])
+        state["M_band"][0] = -1.0          # the clip's own copy: the batch array is untouched
+        assert fo_t[0, f0] != -1.0
+        f0 += n
