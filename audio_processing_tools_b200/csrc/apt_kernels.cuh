@@ -338,9 +338,11 @@ __global__ void __launch_bounds__(STFT_NT, 3) stft256_kernel(const __grid_consta
     // pass B: every lane emits its bins as complex64 into the frame's own (now consumed) exchange area
     {
         float2* sS = S_row(fr);
+        // the default path reads the operating band only: bins no lane needs are neither unpacked nor stored
+        const bool all_bins = o.S || o.P || o.raw || o.band_energy;
         rfft256_passB<T>(lane, ex, s_tw256,
                          [&](int k, T re, T im) { sS[k] = make_float2(d2f((double)re), d2f((double)im)); },
-                         [&]() { __syncwarp(); });
+                         [&]() { __syncwarp(); }, all_bins ? 0 : p.band_lo, all_bins ? 128 : p.band_lo + p.K - 1);
     }
     APT_STAMP2(23);
 
